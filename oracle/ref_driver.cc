@@ -1,0 +1,241 @@
+// oracle/ref_driver.cc — TEST INFRASTRUCTURE (checker / CPU baseline), never shipped.
+//
+// A thin C-ABI over the UNMODIFIED reference library (oracle/_ref/libct2ref.so,
+// built by oracle/Makefile.ref from /root/reference).  It lets the Python tests,
+// tools/make_golden.py and bench.py's `--impl reference` / `cpu_baseline` legs call
+// the reference's own public C++ API:
+//   ctranslate2::Generator::generate_batch_async   include/ctranslate2/generator.h:14-18
+//   ctranslate2::Generator::forward_batch_async    include/ctranslate2/generator.h:30-32
+//   ctranslate2::ops::{Quantize,Gemm,Dequantize,RMSNorm,Rotary,SoftMax,TopK,Gather}
+// Only `tests/`, `__graft_entry__.smoke()` and bench.py's CPU legs may load this.
+
+#include <cstdint>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include <ctranslate2/generator.h>
+#include <ctranslate2/models/language_model.h>
+#include <ctranslate2/ops/ops.h>
+#include <ctranslate2/utils.h>
+
+using namespace ctranslate2;
+
+namespace {
+  thread_local std::string g_error;
+
+  struct RefGenerator {
+    std::shared_ptr<const models::Model> model;
+    std::unique_ptr<Generator> generator;
+    const Vocabulary* vocab = nullptr;
+  };
+
+  template <typename F>
+  int guarded(F&& f) {
+    try {
+      f();
+      return 0;
+    } catch (const std::exception& e) {
+      g_error = e.what();
+      return 1;
+    }
+  }
+
+  StorageView view_f32(const float* p, Shape shape) {
+    return StorageView(std::move(shape), const_cast<float*>(p), Device::CPU);
+  }
+}
+
+extern "C" {
+
+const char* ref_last_error() { return g_error.c_str(); }
+
+void* ref_generator_open(const char* model_dir, const char* compute_type, int intra_threads) {
+  RefGenerator* g = nullptr;
+  int rc = guarded([&] {
+    auto holder = std::make_unique<RefGenerator>();
+    holder->model = models::Model::load(model_dir, Device::CPU, 0,
+                                        str_to_compute_type(compute_type));
+    ReplicaPoolConfig config;
+    config.num_threads_per_replica = intra_threads > 0 ? intra_threads : 0;
+    holder->generator = std::make_unique<Generator>(holder->model, config);
+    auto lm = dynamic_cast<const models::LanguageModel*>(holder->model.get());
+    if (!lm)
+      throw std::runtime_error("model is not a language model");
+    holder->vocab = &lm->get_vocabulary();
+    g = holder.release();
+  });
+  return rc == 0 ? g : nullptr;
+}
+
+void ref_generator_close(void* handle) { delete static_cast<RefGenerator*>(handle); }
+
+// Greedy generate_batch (beam 1, sampling_topk 1, include_prompt_in_result=false,
+// end_token = `end_id` (pass an id that is never the argmax to force max_len tokens)).
+// prompt_ids [B,P] int32, out_ids [B,max_len] int32 (padded with -1), out_lens [B].
+int ref_generate(void* handle, const int32_t* prompt_ids, int B, int P, int max_len, int min_len,
+                 int end_id, int32_t* out_ids, int32_t* out_lens) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> prompts(B);
+    for (int b = 0; b < B; ++b) {
+      prompts[b].reserve(P);
+      for (int t = 0; t < P; ++t)
+        prompts[b].push_back(g->vocab->to_token(prompt_ids[b * P + t]));
+    }
+    GenerationOptions opt;
+    opt.beam_size = 1;
+    opt.sampling_topk = 1;
+    opt.max_length = max_len;
+    opt.min_length = min_len;
+    opt.include_prompt_in_result = false;
+    opt.return_scores = false;
+    opt.end_token = std::vector<size_t>{static_cast<size_t>(end_id)};
+    auto futures = g->generator->generate_batch_async(prompts, opt);
+    for (int b = 0; b < B; ++b) {
+      auto result = futures[b].get();
+      const auto& ids = result.sequences_ids.at(0);
+      out_lens[b] = static_cast<int32_t>(ids.size());
+      for (int t = 0; t < max_len; ++t)
+        out_ids[b * max_len + t] = t < (int)ids.size() ? (int32_t)ids[t] : -1;
+    }
+  });
+}
+
+// Full-sequence forward: ids [B,T] -> logits (or log-probs) [B,T,V] fp32.
+int ref_forward(void* handle, const int32_t* ids, int B, int T, int return_log_probs,
+                float* out, int64_t out_capacity) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<size_t>> v(B, std::vector<size_t>(T));
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < T; ++t)
+        v[b][t] = ids[b * T + t];
+    StorageView logits = g->generator->forward_batch_async(v, return_log_probs != 0).get();
+    StorageView f = logits.to_float32();
+    if (f.size() > out_capacity)
+      throw std::runtime_error("ref_forward: output buffer too small");
+    std::memcpy(out, f.data<float>(), f.size() * sizeof(float));
+  });
+}
+
+int ref_vocab_size(void* handle) {
+  return (int)static_cast<RefGenerator*>(handle)->vocab->size();
+}
+
+void ref_set_num_threads(int n) { set_num_threads(n); }
+
+// ---- op-level entry points (CPU, fp32 activations) ----
+
+// ops::Quantize (src/ops/quantize.cc:21-50): x [rows,cols] -> q int8, scale [rows]
+int ref_quantize(const float* x, int rows, int cols, int round_before_cast, int8_t* q, float* scale) {
+  return guarded([&] {
+    StorageView in = view_f32(x, {rows, cols});
+    StorageView out(DataType::INT8), sc(DataType::FLOAT32);
+    ops::Quantize(ops::Quantize::ScaleType::GLOBAL, false, round_before_cast != 0)(in, out, sc);
+    std::memcpy(q, out.data<int8_t>(), (size_t)rows * cols);
+    std::memcpy(scale, sc.data<float>(), rows * sizeof(float));
+  });
+}
+
+// ops::Gemm int8 (src/ops/gemm.cc:45-107), alpha=1 beta=0 trans_b: a [m,k], b [n,k] -> c [m,n] int32
+int ref_gemm_s8(const int8_t* a, const int8_t* b, int m, int n, int k, int32_t* c) {
+  return guarded([&] {
+    StorageView A({m, k}, const_cast<int8_t*>(a), Device::CPU);
+    StorageView B({n, k}, const_cast<int8_t*>(b), Device::CPU);
+    StorageView C(DataType::INT32);
+    ops::Gemm(1.f, 0.f, false, true)(A, B, C);
+    std::memcpy(c, C.data<int32_t>(), (size_t)m * n * sizeof(int32_t));
+  });
+}
+
+// ops::Gemm fp32 with bias / residual / activation (src/ops/gemm.cc:10-43)
+int ref_gemm_f32(const float* a, const float* b, const float* bias, const float* residual, int act,
+                 int m, int n, int k, float* c) {
+  return guarded([&] {
+    StorageView A = view_f32(a, {m, k}), B = view_f32(b, {n, k});
+    StorageView C(DataType::FLOAT32);
+    StorageView biasv, resv;
+    if (bias) biasv = view_f32(bias, {n});
+    if (residual) resv = view_f32(residual, {m, n});
+    ops::ActivationType at = static_cast<ops::ActivationType>(act < 0 ? 0 : act);
+    ops::Gemm(1.f, 0.f, false, true, false, false, act >= 0 ? &at : nullptr)(
+      A, B, C, nullptr, bias ? &biasv : nullptr, residual ? &resv : nullptr);
+    std::memcpy(c, C.data<float>(), (size_t)m * n * sizeof(float));
+  });
+}
+
+// ops::Dequantize gemm-output form (src/ops/dequantize.cc:46-59); act<0 = none.
+int ref_dequantize_gemm(const int32_t* c, const float* a_scale, const float* b_scale, const float* bias,
+                        int act, int m, int n, float* y) {
+  return guarded([&] {
+    StorageView C({m, n}, const_cast<int32_t*>(c), Device::CPU);
+    StorageView sa = view_f32(a_scale, {m}), sb = view_f32(b_scale, {n});
+    StorageView biasv;
+    if (bias) biasv = view_f32(bias, {n});
+    StorageView Y(DataType::FLOAT32);
+    ops::ActivationType at = static_cast<ops::ActivationType>(act < 0 ? 0 : act);
+    ops::Dequantize(act >= 0 ? &at : nullptr)(C, sa, sb, false, true, Y, bias ? &biasv : nullptr);
+    std::memcpy(y, Y.data<float>(), (size_t)m * n * sizeof(float));
+  });
+}
+
+// ops::RMSNorm (src/ops/rms_norm.cc)
+int ref_rms_norm(const float* gamma, const float* x, int rows, int cols, float eps, float* y) {
+  return guarded([&] {
+    StorageView G = view_f32(gamma, {cols}), X = view_f32(x, {rows, cols});
+    StorageView Y(DataType::FLOAT32);
+    ops::RMSNorm(eps, false)(G, X, Y);
+    std::memcpy(y, Y.data<float>(), (size_t)rows * cols * sizeof(float));
+  });
+}
+
+// ops::Rotary (src/ops/rotary.cc): x [b,h,t,d] (is_transpose=true), sin/cos [t,ndims]
+int ref_rotary(const float* x, const float* sin, const float* cos, int b, int h, int t, int d,
+               int ndims, int interleave, float* y) {
+  return guarded([&] {
+    StorageView X = view_f32(x, {b, h, t, d});
+    StorageView S = view_f32(sin, {t, ndims}), C = view_f32(cos, {t, ndims});
+    StorageView Y(DataType::FLOAT32);
+    ops::Rotary(ndims, interleave != 0)(X, S, C, Y, true);
+    std::memcpy(y, Y.data<float>(), (size_t)b * h * t * d * sizeof(float));
+  });
+}
+
+// ops::SoftMax / LogSoftMax with optional per-row lengths (src/ops/softmax.cc:28-47)
+int ref_softmax(const float* x, const int32_t* lengths, int rows, int cols, int log, float* y) {
+  return guarded([&] {
+    StorageView X = view_f32(x, {rows, cols});
+    StorageView L;
+    if (lengths) L = StorageView({rows}, const_cast<int32_t*>(lengths), Device::CPU);
+    StorageView Y(DataType::FLOAT32);
+    ops::SoftMax(log != 0)(X, lengths ? &L : nullptr, Y);
+    std::memcpy(y, Y.data<float>(), (size_t)rows * cols * sizeof(float));
+  });
+}
+
+// ops::TopK (src/ops/topk.cc:14-22)
+int ref_topk(const float* x, int rows, int cols, int k, float* values, int32_t* indices) {
+  return guarded([&] {
+    StorageView X = view_f32(x, {rows, cols});
+    StorageView V(DataType::FLOAT32), I(DataType::INT32);
+    const ops::TopK topk_op(k);
+    topk_op(X, V, I);
+    std::memcpy(values, V.data<float>(), (size_t)rows * k * sizeof(float));
+    std::memcpy(indices, I.data<int32_t>(), (size_t)rows * k * sizeof(int32_t));
+  });
+}
+
+// ops::Gather axis 0 (src/ops/gather.cc:49-86): data [n,d], ids [m] -> [m,d]
+int ref_gather(const float* data, int n, int d, const int32_t* ids, int m, float* out) {
+  return guarded([&] {
+    StorageView D = view_f32(data, {n, d});
+    StorageView I({m}, const_cast<int32_t*>(ids), Device::CPU);
+    StorageView O(DataType::FLOAT32);
+    ops::Gather(0, 0)(D, I, O);
+    std::memcpy(out, O.data<float>(), (size_t)m * d * sizeof(float));
+  });
+}
+
+}  // extern "C"
