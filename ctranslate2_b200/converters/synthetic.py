@@ -1,0 +1,200 @@
+"""Writer for CTranslate2 model directories (model.bin binary version 6 + config.json +
+vocabulary.json) holding SYNTHETIC Llama-class decoders.
+
+The on-disk format is the reference's own, so directories written here load unchanged in the
+reference (python/ctranslate2/specs/model_spec.py:382-414 is the reference writer,
+src/models/model.cc:561-660 the reader) and directories written by the reference converters load
+unchanged in ctranslate2_b200.  There is no network in this environment, so the benchmark and the
+tests use random-init weights of the named architecture.
+
+Variable names follow TransformerDecoderSpec revision 8 as emitted for LlamaForCausalLM by
+python/ctranslate2/converters/transformers.py:1697-1843.
+"""
+from __future__ import annotations
+
+import json
+import os
+import struct
+from dataclasses import dataclass
+from typing import Dict, Optional
+
+import numpy as np
+
+BINARY_VERSION = 6
+_TYPE_IDS = {"float32": 0, "int8": 1, "int16": 2, "int32": 3, "float16": 4, "bfloat16": 5}
+
+
+@dataclass
+class LlamaConfig:
+    num_layers: int = 32
+    num_heads: int = 32
+    num_heads_kv: int = 8
+    head_dim: int = 128
+    ffn_dim: int = 14336
+    vocab_size: int = 128256
+    rotary_base: float = 500000.0
+    rms_eps: float = 1e-5
+    rotary_scaling_type: int = -1          # attention_spec.RotaryScalingType: Linear=0, Su=1, Llama3=2
+    rotary_scaling_factor: float = 1.0
+    rotary_low_freq_factor: float = 1.0
+    rotary_high_freq_factor: float = 4.0
+    original_max_position_embeddings: int = 0
+
+    @property
+    def d_model(self) -> int:
+        return self.num_heads * self.head_dim
+
+
+LLAMA3_8B = LlamaConfig()
+LLAMA3_70B = LlamaConfig(num_layers=80, num_heads=64, num_heads_kv=8, head_dim=128, ffn_dim=28672)
+
+
+def to_bf16_bits(x: np.ndarray) -> np.ndarray:
+    """float32 -> bfloat16 bit pattern (uint16), round-to-nearest-even."""
+    u = np.ascontiguousarray(x, dtype=np.float32).view(np.uint32)
+    r = ((u >> 16) & 1) + np.uint32(0x7FFF)
+    return ((u + r) >> 16).astype(np.uint16)
+
+
+def quantize_int8(w: np.ndarray):
+    """Converter-side weight quantization (model_spec.py:222-243): scale = 127/amax per output row."""
+    amax = np.max(np.abs(w), axis=1).astype(np.float32)
+    amax[amax == 0] = 127.0
+    scale = (np.float32(127.0) / amax).astype(np.float32)
+    return np.rint(w * scale[:, None]).astype(np.int8), scale
+
+
+class ModelWriter:
+    """Streams variables into model.bin without holding the whole model in memory."""
+
+    def __init__(self, model_dir: str, spec: str = "TransformerDecoderSpec", revision: int = 8):
+        os.makedirs(model_dir, exist_ok=True)
+        self.dir = model_dir
+        self.f = open(os.path.join(model_dir, "model.bin"), "wb")
+        self.count = 0
+        self.aliases = []
+        self.f.write(struct.pack("I", BINARY_VERSION))
+        self._str(spec)
+        self.f.write(struct.pack("I", revision))
+        self._count_pos = self.f.tell()
+        self.f.write(struct.pack("I", 0))
+
+    def _str(self, s: str):
+        b = s.encode("utf-8")
+        self.f.write(struct.pack("H", len(b) + 1))
+        self.f.write(b)
+        self.f.write(b"\0")
+
+    def add(self, name: str, value, dtype: Optional[str] = None):
+        a = np.asarray(value)
+        dtype = dtype or str(a.dtype)
+        if dtype == "bfloat16" and a.dtype != np.uint16:
+            a = to_bf16_bits(a.astype(np.float32))
+        elif dtype != "bfloat16":
+            a = a.astype(dtype)
+        if a.ndim > 0:
+            a = np.ascontiguousarray(a)   # (ascontiguousarray would promote a 0-d scalar to 1-d)
+        if a.nbytes >= 2 ** 32:
+            raise ValueError(f"variable {name} is too large for the model.bin format")
+        self._str(name)
+        self.f.write(struct.pack("B", a.ndim))
+        for d in a.shape:
+            self.f.write(struct.pack("I", d))
+        self.f.write(struct.pack("B", _TYPE_IDS[dtype]))
+        self.f.write(struct.pack("I", a.nbytes))
+        self.f.write(a.tobytes())
+        self.count += 1
+
+    def alias(self, alias: str, target: str):
+        self.aliases.append((alias, target))
+
+    def close(self, config: Dict, vocabulary):
+        self.f.write(struct.pack("I", len(self.aliases)))
+        for a, t in self.aliases:
+            self._str(a)
+            self._str(t)
+        self.f.seek(self._count_pos)
+        self.f.write(struct.pack("I", self.count))
+        self.f.close()
+        with open(os.path.join(self.dir, "config.json"), "w") as f:
+            json.dump(config, f, indent=2, sort_keys=True)
+        with open(os.path.join(self.dir, "vocabulary.json"), "w") as f:
+            json.dump(list(vocabulary), f)
+
+
+def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int8_float16",
+                      seed: int = 1234, init_std: float = 0.02, fast_int8: bool = False) -> None:
+    """Writes a random-init Llama-class model directory.
+
+    quantization: "int8" / "int8_float32" / "int8_float16" / "int8_bfloat16" (int8 linear + embedding
+    weights with fp32 row scales, norms in the float type), or "float32" / "float16" / "bfloat16".
+    fast_int8: draw int8 weights and scales directly (same distribution as quantizing N(0, std^2)
+    rows whose amax sits near 4 sigma) instead of quantizing an fp32 draw — used for the 8B bench
+    model where generating 8e9 gaussians on the host would dominate the run.
+    """
+    rng = np.random.default_rng(seed)
+    is_int8 = quantization.startswith("int8")
+    ftype = {"int8": "float32", "int8_float32": "float32", "int8_float16": "float16",
+             "int8_bfloat16": "bfloat16"}.get(quantization, quantization)
+    d, D = cfg.d_model, cfg.head_dim
+    w = ModelWriter(model_dir)
+
+    def linear(prefix, n, k):
+        if is_int8 and fast_int8:
+            # rows of N(0, std) quantized with scale 127/amax, amax ~ 4.2 sigma  =>  q ~ N(0, 30)
+            q = np.clip(np.rint(rng.standard_normal((n, k), dtype=np.float32) * 30.0), -127, 127).astype(np.int8)
+            q[:, 0] = 127    # each row attains its amax, as a real quantized row does
+            scale = np.full((n,), 127.0 / (4.2 * init_std), np.float32) * \
+                rng.uniform(0.9, 1.1, size=n).astype(np.float32)
+            w.add(prefix + "/weight", q, "int8")
+            w.add(prefix + "/weight_scale", scale, "float32")
+            return
+        wt = (rng.standard_normal((n, k), dtype=np.float32) * np.float32(init_std))
+        if is_int8:
+            q, scale = quantize_int8(wt)
+            w.add(prefix + "/weight", q, "int8")
+            w.add(prefix + "/weight_scale", scale, "float32")
+        else:
+            w.add(prefix + "/weight", wt, ftype)
+
+    w.add("decoder/activation", np.int8(2))                      # common_spec.Activation.SWISH
+    w.add("decoder/alibi", np.int8(0))
+    w.add("decoder/alibi_use_positive_positions", np.int8(0))
+    w.add("decoder/alignment_heads", np.int16(1))
+    w.add("decoder/alignment_layer", np.int16(-1))
+    linear("decoder/embeddings", cfg.vocab_size, d)
+    gamma0 = None
+    for l in range(cfg.num_layers):
+        p = f"decoder/layer_{l}/"
+        g = (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+        w.add(p + "ffn/layer_norm/gamma", g, ftype)
+        linear(p + "ffn/linear_0", cfg.ffn_dim, d)
+        linear(p + "ffn/linear_0_noact", cfg.ffn_dim, d)
+        linear(p + "ffn/linear_1", d, cfg.ffn_dim)
+        g = (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+        w.add(p + "self_attention/layer_norm/gamma", g, ftype)
+        linear(p + "self_attention/linear_0", (cfg.num_heads + 2 * cfg.num_heads_kv) * D, d)
+        linear(p + "self_attention/linear_1", d, cfg.num_heads * D)
+        w.add(p + "self_attention/num_heads_kv", np.int32(cfg.num_heads_kv))
+        w.add(p + "self_attention/head_dim", np.int32(cfg.head_dim))
+        w.add(p + "self_attention/rotary_base", np.float32(cfg.rotary_base))
+        w.add(p + "self_attention/rotary_dim", np.int32(0))
+        w.add(p + "self_attention/rotary_interleave", np.int8(0))
+        if cfg.rotary_scaling_type >= 0:
+            w.add(p + "self_attention/rotary_scaling_type", np.int8(cfg.rotary_scaling_type))
+            w.add(p + "self_attention/rotary_scaling_factor", np.float32(cfg.rotary_scaling_factor))
+            w.add(p + "self_attention/rotary_low_freq_factor", np.float32(cfg.rotary_low_freq_factor))
+            w.add(p + "self_attention/rotary_high_freq_factor", np.float32(cfg.rotary_high_freq_factor))
+            w.add(p + "self_attention/original_max_position_embeddings",
+                  np.int32(cfg.original_max_position_embeddings))
+    g = (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+    w.add("decoder/layer_norm/gamma", g, ftype)
+    w.add("decoder/num_heads", np.int16(cfg.num_heads))
+    w.add("decoder/pre_norm", np.int8(1))
+    linear("decoder/projection", cfg.vocab_size, d)
+    w.add("decoder/scale_alibi", np.int8(0))
+    w.add("decoder/scale_embeddings", np.int8(0))
+    w.add("decoder/start_from_zero_embedding", np.int8(0))
+    config = {"bos_token": "<t1>", "eos_token": "<t2>", "unk_token": "<t0>",
+              "layer_norm_epsilon": cfg.rms_eps, "multi_query_attention": cfg.num_heads_kv != cfg.num_heads}
+    w.close(config, (f"<t{i}>" for i in range(cfg.vocab_size)))

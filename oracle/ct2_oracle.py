@@ -1,0 +1,553 @@
+"""CPU restatement (numpy) of the reference's quantized-decoder hot path.
+
+TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Only `tests/`, `__graft_entry__.smoke()` and
+bench.py's `cpu_baseline` / `--impl reference` legs may import this module; the product
+(`ctranslate2_b200`) never does and fails loudly when its CUDA library is missing.
+
+Parity status: PINNED.  Every function below is checked (tests/test_oracle_*.py, `-m "not gpu"`)
+against (a) the golden vectors the reference's own gtests hold for this path (tests/golden/
+ref_ops_vectors.py, transcribed from /root/reference/tests/ops_test.cc and layers_test.cc) and
+(b) outputs of the UNMODIFIED reference compiled by oracle/Makefile.ref (oracle/_ref), whose
+fixtures are committed under tests/golden/ by tools/make_golden.py.
+
+Each function cites the reference file:line it follows (paths relative to /root/reference).
+All arithmetic is float32 unless stated; integer paths are exact.
+"""
+from __future__ import annotations
+
+import math
+from dataclasses import dataclass, field
+from typing import Dict, List, Optional, Sequence, Tuple
+
+import numpy as np
+
+f32 = np.float32
+
+# ops::ActivationType order, include/ctranslate2/ops/activation.h:9-17
+ACT_NONE = -1
+ACT_RELU, ACT_GELU_TANH, ACT_SWISH, ACT_GELU, ACT_GELU_SIGMOID, ACT_TANH, ACT_SIGMOID = range(7)
+
+_erf = np.vectorize(math.erf, otypes=[np.float64])
+
+
+def activation(x: np.ndarray, act: int) -> np.ndarray:
+    """Epilogue functors: src/cpu/kernels.cc:140-206 (CPU) == src/cuda/helpers.h:244-305 (CUDA)."""
+    x = x.astype(f32)
+    if act == ACT_NONE:
+        return x
+    if act == ACT_RELU:
+        return np.maximum(x, f32(0))
+    if act == ACT_SWISH:
+        return (x / (f32(1) + np.exp(-x, dtype=f32))).astype(f32)
+    if act == ACT_GELU:
+        return (f32(0.5) * x * (f32(1) + _erf(x.astype(np.float64) * 0.7071067811865475).astype(f32))).astype(f32)
+    if act == ACT_GELU_TANH:
+        u = f32(0.7978845608028654) * (x + f32(0.044715) * x * x * x)
+        return (f32(0.5) * x * (f32(1) + np.tanh(u, dtype=f32))).astype(f32)
+    if act == ACT_GELU_SIGMOID:
+        return (x / (f32(1) + np.exp(f32(-1.702) * x, dtype=f32))).astype(f32)
+    if act == ACT_TANH:
+        return np.tanh(x, dtype=f32)
+    if act == ACT_SIGMOID:
+        return (f32(1) / (f32(1) + np.exp(-x, dtype=f32))).astype(f32)
+    raise ValueError(f"unknown activation {act}")
+
+
+# --------------------------------------------------------------------------------------
+# Quantize / INT8 GEMM / Dequantize  
+# --------------------------------------------------------------------------------------
+
+def quantize_rows(x: np.ndarray, round_before_cast: bool = True) -> Tuple[np.ndarray, np.ndarray]:
+    """ops::Quantize, int8 arm.  src/ops/quantize.cc:21-50, src/cpu/kernels.cc:577-651 (CPU),
+    src/ops/quantize_gpu.cu:57-105 (CUDA).  Per row: amax; scale = amax != 0 ? 127/amax : 1;
+    q = int8(nearbyint(x * scale)) (round-half-even; no rounding => C truncation for
+    binary_version < 5).  The amax is reduced in the INPUT dtype (exact for any dtype: max of abs)."""
+    x2 = np.asarray(x)
+    depth = x2.shape[-1]
+    rows = x2.reshape(-1, depth).astype(f32)
+    amax = np.max(np.abs(rows), axis=1).astype(f32)
+    scale = np.where(amax != 0, f32(127) / np.where(amax != 0, amax, f32(1)), f32(1)).astype(f32)
+    v = (rows * scale[:, None]).astype(f32)
+    q = np.rint(v) if round_before_cast else np.trunc(v)
+    return q.astype(np.int8).reshape(x2.shape), scale.reshape(x2.shape[:-1])
+
+
+def gemm_s8(a: np.ndarray, b: np.ndarray) -> np.ndarray:
+    """ops::Gemm int8 arm with alpha=1, beta=0, trans_b=true (the only form layers::Dense uses).
+    src/ops/gemm.cc:45-107 -> primitives<>::gemm<int8_t,int32_t> (src/cuda/primitives.cu:571-597,
+    CPU: src/cpu/primitives.cc Ruy/MKL/oneDNN).  a [M,K] int8, b [N,K] int8 -> c [M,N] int32, exact."""
+    return a.astype(np.int32) @ b.astype(np.int32).T
+
+
+def dequantize_gemm_output(c: np.ndarray, a_scale: np.ndarray, b_scale: np.ndarray,
+                           bias: Optional[np.ndarray] = None, act: int = ACT_NONE,
+                           flavor: str = "cuda") -> np.ndarray:
+    """ops::Dequantize, GEMM-output form.  src/ops/dequantize.cc:46-59.
+    flavor="cpu":  y = act(c * (1/a_scale) / b_scale + bias)      src/cpu/kernels.cc:653-686
+    flavor="cuda": y = act(c / (a_scale * b_scale) + bias)        src/ops/dequantize_gpu.cu:30-54
+    (the two differ in the last ulp; both are within the reference's own fp32 tolerance 1e-5)."""
+    c32 = c.astype(f32)
+    sa = np.asarray(a_scale, f32).reshape(-1, 1)
+    sb = np.asarray(b_scale, f32).reshape(1, -1)
+    if flavor == "cpu":
+        v = (c32 * (f32(1) / sa)).astype(f32) / sb
+    else:
+        v = c32 / (sa * sb).astype(f32)
+    v = v.astype(f32)
+    if bias is not None:
+        v = (v + np.asarray(bias, f32).reshape(1, -1)).astype(f32)
+    return activation(v, act)
+
+
+def dense_int8(x: np.ndarray, w_q: np.ndarray, w_scale: np.ndarray, bias: Optional[np.ndarray] = None,
+               act: int = ACT_NONE, residual: Optional[np.ndarray] = None, flavor: str = "cuda") -> np.ndarray:
+    """layers::Dense::operator(), quantized arm.  src/layers/common.cc:353-401:
+    Quantize(x) -> Gemm s8 -> Dequantize(+bias, activation) -> Add(residual)."""
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1])
+    xq, xs = quantize_rows(x2)
+    y = dequantize_gemm_output(gemm_s8(xq, w_q), xs, w_scale, bias, act, flavor)
+    if residual is not None:
+        y = (y + residual.reshape(y.shape).astype(f32)).astype(f32)
+    return y.reshape(shape[:-1] + (w_q.shape[0],))
+
+
+def quantize_weight(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Weight quantization done by the converter / on load: python/ctranslate2/specs/model_spec.py:222-243
+    == src/models/model.cc:304-369.  scale[i] = 127/amax(W[i,:]) (amax 0 -> 127), W_q = rint(W*scale)."""
+    amax = np.max(np.abs(w), axis=1).astype(f32)
+    amax = np.where(amax == 0, f32(127), amax)
+    scale = (f32(127) / amax).astype(f32)
+    q = np.rint(w.astype(f32) * scale[:, None]).astype(np.int8)
+    return q, scale
+
+
+# --------------------------------------------------------------------------------------
+# Norms / rotary / softmax / topk / gather  
+# --------------------------------------------------------------------------------------
+
+def rms_norm(x: np.ndarray, gamma: np.ndarray, eps: float = 1e-6, use_residual: bool = False) -> np.ndarray:
+    """ops::RMSNorm.  src/ops/rms_norm_gpu.cu:19-63 / src/cpu/kernels.cc rms_norm:
+    y = x * rsqrt(mean(x^2) + eps) * gamma   (gamma -> 1 + gamma when use_residual)."""
+    x = x.astype(f32)
+    ms = np.sum(x * x, axis=-1, dtype=f32, keepdims=True) / f32(x.shape[-1])
+    inv = (f32(1) / np.sqrt(ms + f32(eps), dtype=f32)).astype(f32)
+    g = gamma.astype(f32) + (f32(1) if use_residual else f32(0))
+    return (x * inv * g).astype(f32)
+
+
+def rotary_tables(num_positions: int, dim: int, base: float = 10000.0, interleave: bool = False,
+                  scaling_type: int = -1, scaling_factor: float = 1.0,
+                  low_freq_factor: float = 1.0, high_freq_factor: float = 4.0,
+                  original_max_position_embeddings: int = 0) -> Tuple[np.ndarray, np.ndarray]:
+    """layers::RotaryEmbeddings::initialize.  src/layers/attention_layer.cc:252-343 (None / Linear=0 /
+    Llama3=2 scaling; Su is out of scope).  Returns (sin, cos) [num_positions, dim] float32."""
+    i = np.arange(dim // 2, dtype=f32)
+    inv_freq = (f32(1) / np.power(f32(base), (i * f32(2)) / f32(dim), dtype=f32)).astype(f32)
+    if scaling_type == 2:  # Llama3, attention_layer.cc:271-294
+        old_len = f32(original_max_position_embeddings)
+        low_wavelen = old_len / f32(low_freq_factor)
+        high_wavelen = old_len / f32(high_freq_factor)
+        new = inv_freq.copy()
+        for j in range(inv_freq.size):
+            wavelen = f32(2.0 * math.pi) / inv_freq[j]
+            if wavelen < high_wavelen:
+                pass
+            elif wavelen > low_wavelen:
+                new[j] = inv_freq[j] / f32(scaling_factor)
+            else:
+                smooth = (old_len / wavelen - f32(low_freq_factor)) / (f32(high_freq_factor) - f32(low_freq_factor))
+                new[j] = (f32(1) - smooth) * inv_freq[j] / f32(scaling_factor) + smooth * inv_freq[j]
+        inv_freq = new.astype(f32)
+    t = np.arange(num_positions, dtype=f32)
+    if scaling_type == 0:  # Linear
+        t = (t / f32(scaling_factor)).astype(f32)
+    freqs = (t[:, None] * inv_freq[None, :]).astype(f32)
+    if interleave:
+        emb = np.repeat(freqs, 2, axis=1)
+    else:
+        emb = np.concatenate([freqs, freqs], axis=1)
+    return np.sin(emb, dtype=f32), np.cos(emb, dtype=f32)
+
+
+def rotary(x: np.ndarray, sin: np.ndarray, cos: np.ndarray, interleave: bool = False) -> np.ndarray:
+    """ops::Rotary.  src/ops/rotary_cpu.cc:8-37 == src/ops/rotary_gpu.cu:27-85.
+    x [..., T, D]; sin/cos [T, ndims] (ndims <= D; trailing dims are copied).
+    interleave:      y[i] = x[i]*c[i] + (i even ? -x[i+1] : x[i-1]) * s[i]
+    non-interleaved: y[i] = x[i]*c[i] + (i < n/2 ? -x[i+n/2] : x[i-n/2]) * s[i]"""
+    x = x.astype(f32)
+    nd = sin.shape[-1]
+    xr = x[..., :nd]
+    rot = np.empty_like(xr)
+    if interleave:
+        rot[..., 0::2] = -xr[..., 1::2]
+        rot[..., 1::2] = xr[..., 0::2]
+    else:
+        h = nd // 2
+        rot[..., :h] = -xr[..., h:]
+        rot[..., h:] = xr[..., :h]
+    y = x.copy()
+    y[..., :nd] = (xr * cos.astype(f32) + rot * sin.astype(f32)).astype(f32)
+    return y
+
+
+def softmax(x: np.ndarray, lengths: Optional[np.ndarray] = None, log: bool = False) -> np.ndarray:
+    """ops::SoftMax / LogSoftMax over the last axis with optional per-row valid lengths.
+    src/ops/softmax.cc:28-47, src/ops/softmax_gpu.cu:190-256, src/cpu/kernels.cc softmax:
+    only the first lengths[row] columns participate; the masked tail of the output is 0."""
+    x2 = x.reshape(-1, x.shape[-1]).astype(f32)
+    out = np.zeros_like(x2)
+    for r in range(x2.shape[0]):
+        n = x2.shape[1] if lengths is None else int(np.asarray(lengths).reshape(-1)[r])
+        if n == 0:
+            continue
+        row = x2[r, :n]
+        m = row.max()
+        e = np.exp(row - m, dtype=f32)
+        s = e.sum(dtype=f32)
+        out[r, :n] = (row - m - np.log(s, dtype=f32)) if log else e / s
+    return out.reshape(x.shape)
+
+
+def topk(x: np.ndarray, k: int) -> Tuple[np.ndarray, np.ndarray]:
+    """ops::TopK over the last axis.  src/ops/topk.cc:14-22, CPU src/ops/topk_cpu.cc:12-55
+    (k=1: std::max_element => lowest index wins ties; k>1: descending values).  The product kernel
+    defines ties as lowest-index-first for every k; values are returned unchanged."""
+    x2 = x.reshape(-1, x.shape[-1])
+    order = np.argsort(-x2.astype(np.float64), axis=1, kind="stable")[:, :k]
+    vals = np.take_along_axis(x2, order, axis=1)
+    return vals.reshape(x.shape[:-1] + (k,)), order.astype(np.int32).reshape(x.shape[:-1] + (k,))
+
+
+def gather_rows(data: np.ndarray, ids: np.ndarray) -> np.ndarray:
+    """ops::Gather(axis=0, batch_dims=0).  src/ops/gather.cc:49-86 — pure copy."""
+    return data[np.asarray(ids).astype(np.int64)]
+
+
+# --------------------------------------------------------------------------------------
+# AWQ-INT4  (SURVEY §8 a7).  The reference has NO CPU implementation and NO tests for AWQ;
+# this restates src/ops/awq/dequantize.cuh:14-77 (nibble order) + dequantize_gpu.cu:8-62 (GEMM
+# layout) and src/ops/awq/gemv_gpu.cu:289-422 (GEMV layout).  Parity for AWQ is pinned only by
+# self-consistency between the two layouts and the pack/unpack round trip.
+# --------------------------------------------------------------------------------------
+
+AWQ_ORDER = np.array([0, 4, 1, 5, 2, 6, 3, 7])  # output column 8c+i lives in nibble AWQ_ORDER[i]
+
+
+def awq_pack_gemm(w_int: np.ndarray, zeros_int: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
+    """Pack AWQ_GEMM layout: w_int [K,N] in 0..15 -> qweight int32 [K,N/8]; zeros [K/G,N] -> [K/G,N/8]."""
+    def pack(m):
+        r, n = m.shape
+        m = m.reshape(r, n // 8, 8).astype(np.uint32)
+        out = np.zeros((r, n // 8), np.uint32)
+        for i in range(8):
+            out |= (m[:, :, i] & 0xF) << np.uint32(4 * AWQ_ORDER[i])
+        return out.view(np.int32)
+    return pack(w_int), pack(zeros_int)
+
+
+def awq_unpack_gemm(q: np.ndarray) -> np.ndarray:
+    u = q.view(np.uint32)
+    r, c = u.shape
+    out = np.zeros((r, c, 8), np.int32)
+    for i in range(8):
+        out[:, :, i] = (u >> np.uint32(4 * AWQ_ORDER[i])) & 0xF
+    return out.reshape(r, c * 8)
+
+
+def awq_dequantize_gemm(qweight: np.ndarray, scales: np.ndarray, qzeros: np.ndarray) -> np.ndarray:
+    """ops::DequantizeAwq (AWQ_GEMM layout) -> W [K,N] float32: (nibble - zero) * scale, group = K / scales.rows.
+    src/ops/awq/dequantize_gpu.cu:8-62 (computed there in fp16: sub.f16x2 then fma.rn.f16x2)."""
+    w = awq_unpack_gemm(qweight).astype(f32)
+    z = awq_unpack_gemm(qzeros).astype(f32)
+    g = w.shape[0] // scales.shape[0]
+    return ((w - np.repeat(z, g, axis=0)) * np.repeat(scales.astype(f32), g, axis=0)).astype(f32)
+
+
+def awq_gemm(x: np.ndarray, qweight: np.ndarray, scales: np.ndarray, qzeros: np.ndarray) -> np.ndarray:
+    """ops::GemmAwq: y[M,N] = x[M,K] @ deq(W)[K,N].  src/ops/awq/gemm.cc:8-33."""
+    return (x.astype(f32) @ awq_dequantize_gemm(qweight, scales, qzeros)).astype(f32)
+
+
+def awq_gemv_widths(ic: int, group: int) -> Tuple[int, int]:
+    """zeros_w / sf_w padding rules of the AWQ_GEMV layout.  src/ops/awq/gemv_gpu.cu:305-307, 380-382."""
+    div = lambda c, d: (c + d - 1) // d
+    if group == 64:
+        zw = div(div(ic // 64, 8), 2) * 2
+    else:
+        zw = div(ic // group, 8)
+    return zw, zw * 8
+
+
+def awq_pack_gemv(w_int: np.ndarray, zeros_int: np.ndarray, scales: np.ndarray, group: int):
+    """Pack AWQ_GEMV layout: w_int [OC,IC] -> [OC,IC/8] (nibble i = input channel 8w+i, sequential);
+    zeros [OC,IC/G] -> [OC,zeros_w]; scales [OC,IC/G] -> fp16 [OC,sf_w]."""
+    oc, ic = w_int.shape
+    zw, sw = awq_gemv_widths(ic, group)
+    m = w_int.reshape(oc, ic // 8, 8).astype(np.uint32)
+    qw = np.zeros((oc, ic // 8), np.uint32)
+    for i in range(8):
+        qw |= (m[:, :, i] & 0xF) << np.uint32(4 * i)
+    ng = ic // group
+    zpad = np.zeros((oc, zw * 8), np.uint32)
+    zpad[:, :ng] = zeros_int
+    zp = zpad.reshape(oc, zw, 8)
+    qz = np.zeros((oc, zw), np.uint32)
+    for i in range(8):
+        qz |= (zp[:, :, i] & 0xF) << np.uint32(4 * i)
+    sc = np.zeros((oc, sw), np.float16)
+    sc[:, :ng] = scales
+    return qw.view(np.int32), qz.view(np.int32), sc
+
+
+def awq_gemv(x: np.ndarray, qweight: np.ndarray, scales: np.ndarray, qzeros: np.ndarray, group: int) -> np.ndarray:
+    """ops::GemvAwq: y[M,OC] = x[M,IC] @ deq(W)^T with W in AWQ_GEMV layout; fp32 scale*(nibble-zero), fp32 FMA.
+    src/ops/awq/gemv_gpu.cu:289-422."""
+    u = qweight.view(np.uint32)
+    oc, w8 = u.shape
+    ic = w8 * 8
+    w = np.zeros((oc, w8, 8), f32)
+    for i in range(8):
+        w[:, :, i] = ((u >> np.uint32(4 * i)) & 0xF).astype(f32)
+    w = w.reshape(oc, ic)
+    ng = ic // group
+    uz = qzeros.view(np.uint32)
+    z = np.zeros((oc, uz.shape[1], 8), f32)
+    for i in range(8):
+        z[:, :, i] = ((uz >> np.uint32(4 * i)) & 0xF).astype(f32)
+    z = z.reshape(oc, -1)[:, :ng]
+    s = scales.astype(f32)[:, :ng]
+    deq = (np.repeat(s, group, axis=1) * (w - np.repeat(z, group, axis=1))).astype(f32)
+    return (x.astype(f32) @ deq.T).astype(f32)
+
+
+# --------------------------------------------------------------------------------------
+# model.bin reader (src/models/model.cc:561-660; writer python/ctranslate2/specs/model_spec.py:382-414)
+# --------------------------------------------------------------------------------------
+
+_DTYPES = {0: np.float32, 1: np.int8, 2: np.int16, 3: np.int32, 4: np.float16, 5: np.uint16}  # 5 = bfloat16 bits
+
+
+def read_model_bin(path: str) -> Tuple[str, int, Dict[str, np.ndarray], Dict[str, str]]:
+    import struct
+    variables: Dict[str, np.ndarray] = {}
+    aliases: Dict[str, str] = {}
+    with open(path, "rb") as f:
+        def rd(fmt):
+            size = struct.calcsize(fmt)
+            return struct.unpack(fmt, f.read(size))[0]
+
+        def rd_str():
+            n = rd("H")
+            s = f.read(n)
+            return s[:-1].decode("utf-8")
+
+        version = rd("I")
+        spec = rd_str() if version >= 2 else ""
+        revision = rd("I") if version >= 2 else 1
+        nvars = rd("I")
+        for _ in range(nvars):
+            name = rd_str()
+            rank = rd("B")
+            dims = [rd("I") for _ in range(rank)]
+            if version >= 4:
+                type_id = rd("B")
+                nbytes = rd("I")
+                dt = _DTYPES[type_id]
+            else:
+                item = rd("B")
+                nbytes = rd("I") * item
+                dt = {4: np.float32, 2: np.int16, 1: np.int8}[item]
+            buf = f.read(nbytes)
+            variables[name] = np.frombuffer(buf, dtype=dt).reshape(dims).copy()
+        if version >= 3:
+            for _ in range(rd("I")):
+                alias = rd_str()
+                aliases[alias] = rd_str()
+    for a, t in aliases.items():
+        variables[a] = variables[t]
+    return spec, revision, variables, aliases
+
+
+# --------------------------------------------------------------------------------------
+# Llama-class decoder and greedy search (a17)
+# --------------------------------------------------------------------------------------
+
+@dataclass
+class DecoderWeights:
+    """The variables layers::TransformerDecoder reads for a pre-norm / RMSNorm / SwiGLU / RoPE decoder
+    (src/layers/transformer.cc:473-535, attention_layer.cc:112-142)."""
+    v: Dict[str, np.ndarray]
+    num_layers: int
+    num_heads: int
+    num_heads_kv: int
+    head_dim: int
+    eps: float
+    rotary_base: float
+    rotary_interleave: bool
+    rotary_scaling_type: int = -1
+    rotary_scaling_factor: float = 1.0
+    rotary_low_freq_factor: float = 1.0
+    rotary_high_freq_factor: float = 4.0
+    original_max_position_embeddings: int = 0
+    flavor: str = "cpu"   # dequantize arithmetic flavor
+
+    @staticmethod
+    def from_dir(model_dir: str, flavor: str = "cpu") -> "DecoderWeights":
+        import json, os
+        _, _, v, _ = read_model_bin(os.path.join(model_dir, "model.bin"))
+        cfg = {}
+        cpath = os.path.join(model_dir, "config.json")
+        if os.path.exists(cpath):
+            cfg = json.load(open(cpath))
+        L = 0
+        while f"decoder/layer_{L}/self_attention/linear_0/weight" in v:
+            L += 1
+        H = int(v["decoder/num_heads"])
+        a = "decoder/layer_0/self_attention/"
+        Hkv = int(v.get(a + "num_heads_kv", np.array(H)))
+        d_model = v["decoder/embeddings/weight"].shape[1]
+        head_dim = int(v[a + "head_dim"]) if a + "head_dim" in v else d_model // H
+        get = lambda k, d: (v[a + k].item() if a + k in v else d)
+        return DecoderWeights(
+            v=v, num_layers=L, num_heads=H, num_heads_kv=Hkv, head_dim=head_dim,
+            eps=float(cfg.get("layer_norm_epsilon") or 1e-6),   # model.cc / common.cc:455-462 default 1e-6
+            rotary_base=float(get("rotary_base", 10000.0)),
+            rotary_interleave=bool(get("rotary_interleave", True)),
+            rotary_scaling_type=int(get("rotary_scaling_type", -1)),
+            rotary_scaling_factor=float(get("rotary_scaling_factor", 1.0)),
+            rotary_low_freq_factor=float(get("rotary_low_freq_factor", 1.0)),
+            rotary_high_freq_factor=float(get("rotary_high_freq_factor", 4.0)),
+            original_max_position_embeddings=int(get("original_max_position_embeddings", 0)),
+            flavor=flavor)
+
+
+class LlamaOracle:
+    """fp32 restatement of TransformerDecoder::decode (src/layers/transformer.cc:621-871) for the
+    Llama family: Embeddings (common.cc:64-81) -> L x [MultiHeadAttention (attention.cc:442-615) ->
+    FeedForwardNetwork (transformer.cc:21-51)] -> output RMSNorm -> projection Dense."""
+
+    def __init__(self, w: DecoderWeights):
+        self.w = w
+        self._sin = None
+        self._cos = None
+        self.reset(0)
+
+    # -- state ------------------------------------------------------------------------
+    def reset(self, batch: int):
+        w = self.w
+        self.k_cache = [np.zeros((batch, w.num_heads_kv, 0, w.head_dim), f32) for _ in range(w.num_layers)]
+        self.v_cache = [np.zeros((batch, w.num_heads_kv, 0, w.head_dim), f32) for _ in range(w.num_layers)]
+
+    def _tables(self, n):
+        w = self.w
+        if self._sin is None or self._sin.shape[0] < n:
+            self._sin, self._cos = rotary_tables(
+                max(n, 64), w.head_dim, w.rotary_base, w.rotary_interleave, w.rotary_scaling_type,
+                w.rotary_scaling_factor, w.rotary_low_freq_factor, w.rotary_high_freq_factor,
+                w.original_max_position_embeddings)
+        return self._sin, self._cos
+
+    # -- layers -----------------------------------------------------------------------
+    def _dense(self, prefix: str, x: np.ndarray, act: int = ACT_NONE, residual=None) -> np.ndarray:
+        v = self.w.v
+        wq = v[prefix + "/weight"]
+        bias = v.get(prefix + "/bias")
+        if wq.dtype == np.int8:
+            return dense_int8(x, wq, v[prefix + "/weight_scale"], bias, act, residual, self.w.flavor)
+        y = x.astype(f32) @ wq.astype(f32).T      # float arm, common.cc:440
+        if bias is not None:
+            y = y + bias.astype(f32)
+        y = activation(y, act)
+        if residual is not None:
+            y = y + residual
+        return y.astype(f32)
+
+    def _embed(self, ids: np.ndarray) -> np.ndarray:
+        v = self.w.v
+        e = v["decoder/embeddings/weight"]
+        rows = gather_rows(e, ids)
+        if e.dtype == np.int8:   # common.cc:64-81: gather int8 rows + scales, Dequantize: x / scale
+            sc = gather_rows(v["decoder/embeddings/weight_scale"], ids)
+            rows = (rows.astype(f32) / sc[..., None].astype(f32)).astype(f32)
+        return rows.astype(f32)
+
+    def forward(self, ids: np.ndarray, offset: int = 0, all_logits: bool = True) -> np.ndarray:
+        """ids [B,T] at positions offset..offset+T-1 (all rows share `offset`, as in the reference,
+        flash_attention_gpu.cu:269).  Appends K/V to the cache.  Returns logits [B,T,V] (or [B,1,V])."""
+        w = self.w
+        B, T = ids.shape
+        H, Hkv, D = w.num_heads, w.num_heads_kv, w.head_dim
+        sin, cos = self._tables(offset + T)
+        sin, cos = sin[offset:offset + T], cos[offset:offset + T]
+        x = self._embed(ids)                                                    # [B,T,d]
+        for l in range(w.num_layers):
+            p = f"decoder/layer_{l}/"
+            a = p + "self_attention/"
+            h = rms_norm(x, w.v[a + "layer_norm/gamma"], w.eps)
+            qkv = self._dense(a + "linear_0", h)                                # [B,T,(H+2Hkv)D]
+            q = qkv[..., :H * D].reshape(B, T, H, D).transpose(0, 2, 1, 3)
+            k = qkv[..., H * D:(H + Hkv) * D].reshape(B, T, Hkv, D).transpose(0, 2, 1, 3)
+            vv = qkv[..., (H + Hkv) * D:].reshape(B, T, Hkv, D).transpose(0, 2, 1, 3)
+            q = rotary(q, sin, cos, w.rotary_interleave)
+            k = rotary(k, sin, cos, w.rotary_interleave)
+            self.k_cache[l] = np.concatenate([self.k_cache[l], k], axis=2)
+            self.v_cache[l] = np.concatenate([self.v_cache[l], vv], axis=2)
+            K, V = self.k_cache[l], self.v_cache[l]                             # [B,Hkv,S,D]
+            S = K.shape[2]
+            g = H // Hkv
+            Kr = np.repeat(K, g, axis=1)                                        # replicate_heads, attention.cc:291-295
+            Vr = np.repeat(V, g, axis=1)
+            scores = (np.einsum("bhtd,bhsd->bhts", q, Kr) * f32(1.0 / math.sqrt(D))).astype(f32)
+            # causal mask: query t (absolute offset+t) sees keys 0..offset+t  (attention_layer.cc:152-174)
+            lens = np.minimum(np.arange(T) + offset + 1, S)
+            lens_rows = np.broadcast_to(lens, (B, H, T)).reshape(-1)
+            probs = softmax(scores.reshape(-1, S), lens_rows).reshape(B, H, T, S)
+            ctx = np.einsum("bhts,bhsd->bhtd", probs, Vr).astype(f32)
+            ctx = ctx.transpose(0, 2, 1, 3).reshape(B, T, H * D)
+            x = self._dense(a + "linear_1", ctx, residual=x)
+            f = p + "ffn/"
+            h = rms_norm(x, w.v[f + "layer_norm/gamma"], w.eps)
+            gate = self._dense(f + "linear_0", h, act=ACT_SWISH)
+            up = self._dense(f + "linear_0_noact", h)
+            x = self._dense(f + "linear_1", (gate * up).astype(f32), residual=x)
+        if not all_logits:
+            x = x[:, -1:, :]
+        x = rms_norm(x, w.v["decoder/layer_norm/gamma"], w.eps)
+        return self._dense("decoder/projection", x)
+
+    # -- greedy search ----------------------------------------------------------------
+    def generate(self, prompts: np.ndarray, max_length: int, min_length: int = 0,
+                 end_ids: Sequence[int] = ()) -> List[List[int]]:
+        """Generator::generate_batch, greedy, include_prompt_in_result=false.
+        src/models/language_model.cc:217-238 (prefill of P-1 tokens) + GreedySearch::search
+        (src/decoding.cc:732-974): argmax = TopK k=1 lowest-index ties; EOS forbidden until min_length;
+        a finished row stops (its tokens are not reported further)."""
+        B, P = prompts.shape
+        self.reset(B)
+        if P > 1:
+            self.forward(prompts[:, :P - 1], 0, all_logits=False)
+        cur = prompts[:, P - 1:P].copy()
+        out: List[List[int]] = [[] for _ in range(B)]
+        done = [False] * B
+        for step in range(max_length):
+            logits = self.forward(cur, P - 1 + step, all_logits=False)[:, 0, :]
+            if step < min_length:
+                for e in end_ids:
+                    logits[:, e] = np.finfo(f32).min     # DisableTokens, decoding.cc:852-856
+            _, idx = topk(logits, 1)
+            nxt = idx[:, 0]
+            for b in range(B):
+                if done[b]:
+                    continue
+                tok = int(nxt[b])
+                if tok in end_ids:
+                    done[b] = True
+                else:
+                    out[b].append(tok)
+                    if len(out[b]) >= max_length:
+                        done[b] = True
+            cur = nxt.reshape(B, 1).astype(np.int64)
+            if all(done):
+                break
+        return out

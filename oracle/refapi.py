@@ -1,0 +1,155 @@
+"""ctypes binding of oracle/_ref/libct2ref_driver.so (the UNMODIFIED reference, CPU build).
+
+TEST INFRASTRUCTURE: only tests/, tools/make_golden.py, __graft_entry__.smoke() and bench.py's
+CPU legs import this.  `available()` is False when oracle/_ref was not built (run
+`make -f oracle/Makefile.ref -j8` in a container that has /root/reference).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Optional
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_PATH = os.path.join(_HERE, "_ref", "libct2ref_driver.so")
+_lib = None
+
+
+def available() -> bool:
+    return os.path.exists(_PATH)
+
+
+def lib():
+    global _lib
+    if _lib is None:
+        _lib = ctypes.CDLL(_PATH)
+        _lib.ref_last_error.restype = ctypes.c_char_p
+        _lib.ref_generator_open.restype = ctypes.c_void_p
+        _lib.ref_generator_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
+        _lib.ref_generator_close.argtypes = [ctypes.c_void_p]
+        _lib.ref_vocab_size.argtypes = [ctypes.c_void_p]
+    return _lib
+
+
+def _p(a):
+    return None if a is None else ctypes.c_void_p(a.ctypes.data)
+
+
+def _check(rc):
+    if rc != 0:
+        raise RuntimeError("reference: " + lib().ref_last_error().decode())
+
+
+def _c(a, dt):
+    return None if a is None else np.ascontiguousarray(a, dtype=dt)
+
+
+class RefGenerator:
+    def __init__(self, model_dir: str, compute_type: str = "int8", threads: int = 0):
+        self.h = lib().ref_generator_open(model_dir.encode(), compute_type.encode(), threads)
+        if not self.h:
+            raise RuntimeError("reference: " + lib().ref_last_error().decode())
+        self.vocab = lib().ref_vocab_size(ctypes.c_void_p(self.h))
+
+    def close(self):
+        if self.h:
+            lib().ref_generator_close(ctypes.c_void_p(self.h))
+            self.h = None
+
+    def forward(self, ids: np.ndarray, log_probs: bool = False) -> np.ndarray:
+        ids = _c(ids, np.int32)
+        B, T = ids.shape
+        out = np.zeros((B, T, self.vocab), np.float32)
+        _check(lib().ref_forward(ctypes.c_void_p(self.h), _p(ids), B, T, int(log_probs), _p(out),
+                                 ctypes.c_int64(out.size)))
+        return out
+
+    def generate(self, prompts: np.ndarray, max_length: int, min_length: int = 0, end_id: int = 2):
+        prompts = _c(prompts, np.int32)
+        B, P = prompts.shape
+        out = np.zeros((B, max_length), np.int32)
+        lens = np.zeros(B, np.int32)
+        _check(lib().ref_generate(ctypes.c_void_p(self.h), _p(prompts), B, P, max_length, min_length,
+                                  end_id, _p(out), _p(lens)))
+        return [out[b, :lens[b]].tolist() for b in range(B)]
+
+
+def quantize(x, round_before_cast=True):
+    x = _c(x, np.float32)
+    r, c = x.shape
+    q = np.zeros((r, c), np.int8)
+    s = np.zeros(r, np.float32)
+    _check(lib().ref_quantize(_p(x), r, c, int(round_before_cast), _p(q), _p(s)))
+    return q, s
+
+
+def gemm_s8(a, b):
+    a, b = _c(a, np.int8), _c(b, np.int8)
+    m, k = a.shape
+    n = b.shape[0]
+    c = np.zeros((m, n), np.int32)
+    _check(lib().ref_gemm_s8(_p(a), _p(b), m, n, k, _p(c)))
+    return c
+
+
+def gemm_f32(a, b, bias=None, residual=None, act=-1):
+    a, b = _c(a, np.float32), _c(b, np.float32)
+    bias, residual = _c(bias, np.float32), _c(residual, np.float32)
+    m, k = a.shape
+    n = b.shape[0]
+    c = np.zeros((m, n), np.float32)
+    _check(lib().ref_gemm_f32(_p(a), _p(b), _p(bias), _p(residual), act, m, n, k, _p(c)))
+    return c
+
+
+def dequantize_gemm(c, a_scale, b_scale, bias=None, act=-1):
+    c = _c(c, np.int32)
+    a_scale, b_scale, bias = _c(a_scale, np.float32), _c(b_scale, np.float32), _c(bias, np.float32)
+    m, n = c.shape
+    y = np.zeros((m, n), np.float32)
+    _check(lib().ref_dequantize_gemm(_p(c), _p(a_scale), _p(b_scale), _p(bias), act, m, n, _p(y)))
+    return y
+
+
+def rms_norm(gamma, x, eps):
+    gamma, x = _c(gamma, np.float32), _c(x, np.float32)
+    r, c = x.shape
+    y = np.zeros_like(x)
+    _check(lib().ref_rms_norm(_p(gamma), _p(x), r, c, ctypes.c_float(eps), _p(y)))
+    return y
+
+
+def rotary(x, sin, cos, interleave):
+    x, sin, cos = _c(x, np.float32), _c(sin, np.float32), _c(cos, np.float32)
+    b, h, t, d = x.shape
+    y = np.zeros_like(x)
+    _check(lib().ref_rotary(_p(x), _p(sin), _p(cos), b, h, t, d, sin.shape[1], int(interleave), _p(y)))
+    return y
+
+
+def softmax(x, lengths=None, log=False):
+    x = _c(x, np.float32)
+    lengths = _c(lengths, np.int32)
+    r, c = x.shape
+    y = np.zeros_like(x)
+    _check(lib().ref_softmax(_p(x), _p(lengths), r, c, int(log), _p(y)))
+    return y
+
+
+def topk(x, k):
+    x = _c(x, np.float32)
+    r, c = x.shape
+    v = np.zeros((r, k), np.float32)
+    i = np.zeros((r, k), np.int32)
+    _check(lib().ref_topk(_p(x), r, c, k, _p(v), _p(i)))
+    return v, i
+
+
+def gather(data, ids):
+    data, ids = _c(data, np.float32), _c(ids, np.int32)
+    n, d = data.shape
+    out = np.zeros((ids.size, d), np.float32)
+    _check(lib().ref_gather(_p(data), n, d, _p(ids), ids.size, _p(out)))
+    return out
