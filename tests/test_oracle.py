@@ -1,0 +1,184 @@
+"""The oracle (oracle/ct2_oracle.py) against (1) the golden vectors of the reference's own gtests,
+(2) committed outputs of the unmodified reference, (3) the live reference when oracle/_ref is built."""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from oracle import ct2_oracle as O
+from oracle import refapi
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+GT = json.load(open(os.path.join(GOLDEN, "ref_gtest_vectors.json")))
+RND = np.load(os.path.join(GOLDEN, "ref_ops_random.npz"))
+
+
+def vec(test, name, dtype=np.float32, nth=0):
+    items = [i for i in GT[test] if i["name"] == name]
+    return np.array(items[nth]["values"], dtype=dtype).reshape(items[nth]["shape"])
+
+
+# ---- the reference's own gtest goldens (tests/ops_test.cc, tests/layers_test.cc) ----
+
+def test_gtest_gemm_int8():
+    a, b = vec("GemmInt8", "a", np.int8), vec("GemmInt8", "b", np.int8)   # b is [K,N] there
+    np.testing.assert_array_equal(O.gemm_s8(a, b.T.copy()), vec("GemmInt8", "expected", np.int32))
+
+
+def test_gtest_quantize_int8():
+    a = vec("QuantizeINT8", "a")
+    q, s = O.quantize_rows(a, True)
+    np.testing.assert_array_equal(q, vec("QuantizeINT8", "expected_qa", np.int8, 0))
+    np.testing.assert_allclose(s, vec("QuantizeINT8", "expected_scale"), rtol=1e-6)
+    q, _ = O.quantize_rows(a, False)   # legacy: no rounding before cast
+    np.testing.assert_array_equal(q, vec("QuantizeINT8", "expected_qa", np.int8, 2))
+    a = vec("QuantizeINT8ZeroRow", "a")
+    q, s = O.quantize_rows(a, True)
+    np.testing.assert_array_equal(q, vec("QuantizeINT8ZeroRow", "expected_qa", np.int8, 0))
+    np.testing.assert_allclose(s, vec("QuantizeINT8ZeroRow", "expected_scale"), rtol=1e-6)
+
+
+@pytest.mark.parametrize("test", ["TopK", "TopKVariableDepth"])
+def test_gtest_topk(test):
+    v, i = O.topk(vec(test, "input"), 3)
+    np.testing.assert_array_equal(i, vec(test, "expected_indices", np.int32))
+    np.testing.assert_allclose(v, vec(test, "expected_values"))
+    v, i = O.topk(vec("TopKChangeK", "input"), 2)
+    np.testing.assert_array_equal(i, vec("TopKChangeK", "expected_indices_k2", np.int32))
+
+
+def test_gtest_softmax():
+    np.testing.assert_allclose(O.softmax(vec("SoftMax", "x")), vec("SoftMax", "expected"), atol=1e-5)
+    np.testing.assert_allclose(O.softmax(vec("LogSoftMax", "x"), log=True), vec("LogSoftMax", "expected"), atol=1e-5)
+    y = O.softmax(vec("MaskedSoftMax", "x"), vec("MaskedSoftMax", "lengths", np.int32))
+    np.testing.assert_allclose(y, vec("MaskedSoftMax", "expected"), atol=1e-5)
+
+
+def test_gtest_rms_norm():
+    y = O.rms_norm(vec("RMSNorm", "x"), vec("RMSNorm", "gamma"), 1e-6)
+    np.testing.assert_allclose(y, vec("RMSNorm", "expected"), atol=1e-5)
+
+
+@pytest.mark.parametrize("test,act", [("Swish", O.ACT_SWISH), ("ReLU", O.ACT_RELU), ("GELU", O.ACT_GELU),
+                                      ("GELUTanh", O.ACT_GELU_TANH), ("GELUSigmoid", O.ACT_GELU_SIGMOID)])
+def test_gtest_activations(test, act):
+    np.testing.assert_allclose(O.activation(vec(test, "input"), act), vec(test, "expected"), atol=1e-5)
+
+
+def test_gtest_rotary_embedding():
+    x, exp = vec("RotaryEmbedding", "input"), vec("RotaryEmbedding", "expected")
+    # default RotaryEmbeddings(): dim 0 (= depth), interleave, base 10000, applied at offset 2
+    sin, cos = O.rotary_tables(4, 6, 10000.0, interleave=True)
+    np.testing.assert_allclose(O.rotary(x, sin[2:4], cos[2:4], True), exp, atol=1e-5)
+
+    def permute(t):
+        return t.reshape(8, 2, 3, 2).transpose(0, 1, 3, 2).reshape(2, 4, 2, 6)
+    sin, cos = O.rotary_tables(4, 6, 10000.0, interleave=False)
+    np.testing.assert_allclose(O.rotary(permute(x), sin[2:4], cos[2:4], False), permute(exp), atol=1e-5)
+
+
+def test_gtest_gather():
+    for t in ("GatherData1D", "GatherData2D", "GatherData3D"):
+        np.testing.assert_array_equal(O.gather_rows(vec(t, "data"), vec(t, "ids", np.int32)), vec(t, "expected"))
+
+
+# ---- committed outputs of the unmodified reference on seeded random inputs ----
+
+def test_ref_random_quantize_gemm_dequantize():
+    q, s = O.quantize_rows(RND["q_x"])
+    np.testing.assert_array_equal(q, RND["q_q"])
+    np.testing.assert_array_equal(s, RND["q_s"])
+    np.testing.assert_array_equal(O.gemm_s8(RND["g_a"], RND["g_b"]), RND["g_c"])
+    for act in (-1, 0, 1, 2, 3, 4, 5, 6):
+        y = O.dequantize_gemm_output(RND["g_c"], RND["dq_sa"], RND["dq_sb"], RND["dq_bias"], act, "cpu")
+        # GELU/tanh use the reference's vectorised erf/tanh approximations on CPU (avx_mathfun): ~2e-5 abs
+        tol = 3e-5 if act in (1, 3, 5) else 2e-6
+        np.testing.assert_allclose(y, RND["dq_y_act%d" % act], rtol=tol, atol=tol)
+        y = O.dequantize_gemm_output(RND["g_c"], RND["dq_sa"], RND["dq_sb"], RND["dq_bias"], act, "cuda")
+        np.testing.assert_allclose(y, RND["dq_y_act%d" % act], rtol=3e-5, atol=3e-5)
+
+
+def test_ref_random_norm_rotary_softmax_topk_gather():
+    np.testing.assert_allclose(O.rms_norm(RND["q_x"], RND["rn_gamma"], 1e-5), RND["rn_y"], rtol=1e-5, atol=1e-6)
+    for key, inter in (("ro_y_interleave", True), ("ro_y_half", False)):
+        np.testing.assert_allclose(O.rotary(RND["ro_x"], RND["ro_sin"], RND["ro_cos"], inter), RND[key], atol=1e-6)
+    np.testing.assert_allclose(O.softmax(RND["sm_x"]), RND["sm_y"], atol=1e-6)
+    np.testing.assert_allclose(O.softmax(RND["sm_x"], RND["sm_len"]), RND["sm_y_len"], atol=1e-6)
+    np.testing.assert_allclose(O.softmax(RND["sm_x"], None, True), RND["sm_logy"], atol=1e-5)
+    for k in (1, 4):
+        v, i = O.topk(RND["tk_x"], k)
+        np.testing.assert_array_equal(i, RND["tk_i%d" % k])
+        np.testing.assert_array_equal(v, RND["tk_v%d" % k])
+    assert RND["tk_i1"][1, 0] == 17          # exact tie 17 vs 500: lowest index wins in the reference
+    np.testing.assert_array_equal(O.gather_rows(RND["ga_d"], RND["ga_i"]), RND["ga_y"])
+
+
+def test_tiny_llama_against_reference_fixture():
+    fx = np.load(os.path.join(GOLDEN, "tiny_llama_int8_ref.npz"), allow_pickle=True)
+    w = O.DecoderWeights.from_dir(os.path.join(GOLDEN, "tiny_llama_int8"), flavor="cpu")
+    m = O.LlamaOracle(w)
+    prompts = fx["prompts"].astype(np.int64)
+    m.reset(prompts.shape[0])
+    logits = m.forward(prompts, 0)
+    np.testing.assert_allclose(logits, fx["logits"], atol=2e-5)
+    gen = m.generate(prompts, 12, 0, [2])
+    assert gen == [list(g) for g in fx["generated"]]
+    gen = m.generate(prompts, 12, 12, [2])
+    assert gen == fx["generated_min12"].tolist()
+    # step-by-step decode == full forward (reference tests/model_test.cc:99-151 DecoderIterativeSequence)
+    m.reset(prompts.shape[0])
+    steps = [m.forward(prompts[:, t:t + 1], t)[:, 0] for t in range(prompts.shape[1])]
+    np.testing.assert_allclose(np.stack(steps, 1), logits, atol=2e-5)
+
+
+def test_awq_layouts_agree():
+    r = np.random.default_rng(3)
+    K, N, G = 256, 64, 128
+    w_int = r.integers(0, 16, size=(K, N))
+    z_int = r.integers(0, 16, size=(K // G, N))
+    scales = (r.uniform(0.005, 0.02, size=(K // G, N))).astype(np.float16)
+    qw, qz = O.awq_pack_gemm(w_int, z_int)
+    np.testing.assert_array_equal(O.awq_unpack_gemm(qw), w_int)
+    x = r.standard_normal((3, K)).astype(np.float32)
+    y_gemm = O.awq_gemm(x, qw, scales, qz)
+    qw2, qz2, sc2 = O.awq_pack_gemv(w_int.T.copy(), z_int.T.copy(), scales.T.copy(), G)
+    y_gemv = O.awq_gemv(x, qw2, sc2, qz2, G)
+    np.testing.assert_allclose(y_gemm, y_gemv, rtol=1e-5, atol=1e-5)
+    deq = (w_int - np.repeat(z_int, G, 0)) * np.repeat(scales.astype(np.float32), G, 0)
+    np.testing.assert_allclose(y_gemm, x @ deq, rtol=1e-5, atol=1e-5)
+
+
+# ---- live cross-check against the compiled reference, when it is present ----
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref not built")
+def test_live_reference_ops():
+    r = np.random.default_rng(11)
+    x = (r.standard_normal((9, 200)) * 2).astype(np.float32)
+    q, s = O.quantize_rows(x)
+    rq, rs = refapi.quantize(x)
+    np.testing.assert_array_equal(q, rq)
+    np.testing.assert_array_equal(s, rs)
+    b = r.integers(-127, 128, size=(40, 200), dtype=np.int8)
+    np.testing.assert_array_equal(O.gemm_s8(q, b), refapi.gemm_s8(q, b))
+    v, i = O.topk(x, 5)
+    rv, ri = refapi.topk(x, 5)
+    np.testing.assert_array_equal(i, ri)
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref not built")
+def test_live_reference_synthetic_writer_roundtrip(tmp_path):
+    """A model dir written by OUR writer loads in the unmodified reference and the oracle agrees."""
+    from ctranslate2_b200.converters.synthetic import LlamaConfig, write_llama_model
+    cfg = LlamaConfig(num_layers=2, num_heads=4, num_heads_kv=2, head_dim=32, ffn_dim=192, vocab_size=150)
+    mdir = str(tmp_path / "m")
+    write_llama_model(mdir, cfg, "int8", seed=5)
+    g = refapi.RefGenerator(mdir, "int8", 2)
+    prompts = np.random.default_rng(0).integers(3, 150, size=(2, 6), dtype=np.int32)
+    ref_logits = g.forward(prompts)
+    ref_gen = g.generate(prompts, 10, 10, 2)
+    g.close()
+    m = O.LlamaOracle(O.DecoderWeights.from_dir(mdir, "cpu"))
+    m.reset(2)
+    np.testing.assert_allclose(m.forward(prompts.astype(np.int64), 0), ref_logits, atol=2e-5)
+    assert m.generate(prompts.astype(np.int64), 10, 10, [2]) == ref_gen

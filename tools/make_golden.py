@@ -1,0 +1,173 @@
+#!/usr/bin/env python
+"""Generates the committed fixtures under tests/golden/ from the reference itself.
+
+Run in the build container (needs /root/reference and oracle/_ref built by oracle/Makefile.ref):
+
+    python tools/make_golden.py
+
+1. tests/golden/ref_gtest_vectors.json — the golden vectors the reference's own gtests hold for
+   this path, extracted verbatim (by parsing, not by hand) from /root/reference/tests/ops_test.cc and
+   layers_test.cc: every `StorageView name({shape}, std::vector<T>{...})` inside the named TEST_P blocks.
+2. tests/golden/tiny_llama_int8/ — a 2-layer GQA/SwiGLU/RoPE decoder written by the REFERENCE's
+   python spec writer (python/ctranslate2/specs), quantization="int8".
+3. tests/golden/tiny_llama_int8_ref.npz — outputs of the UNMODIFIED reference (oracle/_ref, CPU):
+   forward logits for a seeded prompt batch and greedy generate_batch tokens.
+4. tests/golden/ref_ops_random.npz — reference op outputs (Quantize, Gemm s8, Dequantize, RMSNorm,
+   Rotary, SoftMax, TopK, Gather) on seeded random inputs.
+
+Nothing here runs at test time on the GPU box; the tests read only the files this script wrote.
+"""
+import json
+import os
+import re
+import shutil
+import sys
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF = "/root/reference"
+OUT = os.path.join(ROOT, "tests", "golden")
+sys.path.insert(0, ROOT)
+
+GTESTS = {
+    "ops_test.cc": ["GemmInt8", "TopK", "TopKVariableDepth", "TopKChangeK", "SoftMax", "LogSoftMax",
+                    "MaskedSoftMax", "RMSNorm", "QuantizeINT8", "QuantizeINT8ZeroRow", "Swish", "ReLU",
+                    "GELU", "GELUTanh", "GELUSigmoid", "Gemm", "GemmBias", "GemmResidual", "GemmGELU",
+                    "GatherData1D", "GatherData1DIndex2D", "GatherData2D", "GatherData3D",
+                    "GatherData2DIndex2D", "BiasAdd", "BiasAddResidual"],
+    "layers_test.cc": ["RotaryEmbedding"],
+}
+
+
+def extract_gtest_vectors():
+    out = {}
+    sv = re.compile(r"StorageView\s+(\w+)\s*(?:=\s*StorageView)?\((\{[^}]*\}|\w+\.shape\(\)),\s*std::vector<(\w+)>\s*\{([^}]*)\}", re.S)
+    for fname, names in GTESTS.items():
+        text = open(os.path.join(REF, "tests", fname)).read()
+        for name in names:
+            m = re.search(r"TEST_P\(\w+,\s*%s\)\s*\{" % re.escape(name), text)
+            if not m:
+                print("  (no such test in this reference version: %s)" % name)
+                continue
+            nxt = re.search(r"\nTEST(_P|_F)?\(", text[m.end():])
+            body = text[m.end(): m.end() + (nxt.start() if nxt else len(text))]
+            items = []
+            for v in sv.finditer(body):
+                if v.group(2).startswith("{"):
+                    shape = [int(s) for s in v.group(2).strip("{}").split(",") if s.strip()]
+                else:   # `other.shape()`: same shape as the named vector of this test
+                    other = v.group(2).split(".")[0]
+                    shape = next(i["shape"] for i in items if i["name"] == other)
+                vals = [float(t.rstrip("f")) for t in re.split(r"[,\s]+", v.group(4).strip()) if t]
+                items.append({"name": v.group(1), "shape": shape, "ctype": v.group(3), "values": vals})
+            out[name] = items
+            print("  %-24s %d vectors" % (name, len(items)))
+    return out
+
+
+def make_tiny_model(model_dir):
+    sys.path.insert(0, os.path.join(REF, "python"))
+    from ctranslate2.specs import common_spec, transformer_spec
+    L, H, Hkv, D, F, V = 2, 4, 2, 32, 256, 200
+    d = H * D
+    spec = transformer_spec.TransformerDecoderModelSpec.from_config(
+        L, H, activation=common_spec.Activation.SWISH, pre_norm=True, ffn_glu=True, rms_norm=True,
+        rotary_dim=0, rotary_interleave=False, rotary_base=500000.0, num_heads_kv=Hkv)
+    rng = np.random.default_rng(1234)
+
+    def lin(s, n, k):
+        s.weight = (rng.standard_normal((n, k)) * 0.05).astype(np.float32)
+
+    dec = spec.decoder
+    dec.scale_embeddings = False
+    dec.embeddings.weight = (rng.standard_normal((V, d)) * 0.05).astype(np.float32)
+    dec.layer_norm.gamma = (1 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+    for l in dec.layer:
+        l.self_attention.layer_norm.gamma = (1 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+        l.ffn.layer_norm.gamma = (1 + 0.1 * rng.standard_normal(d)).astype(np.float32)
+        lin(l.self_attention.linear[0], d + 2 * Hkv * D, d)
+        lin(l.self_attention.linear[1], d, d)
+        lin(l.ffn.linear_0, F, d)
+        lin(l.ffn.linear_0_noact, F, d)
+        lin(l.ffn.linear_1, d, F)
+    lin(dec.projection, V, d)
+    spec.register_vocabulary(["<t%d>" % i for i in range(V)])
+    spec.config.bos_token = "<t1>"
+    spec.config.eos_token = "<t2>"
+    spec.config.unk_token = "<t0>"
+    spec.config.layer_norm_epsilon = 1e-5
+    spec.validate()
+    spec.optimize(quantization="int8")
+    shutil.rmtree(model_dir, ignore_errors=True)
+    os.makedirs(model_dir)
+    spec.save(model_dir)
+    return V
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    print("extracting gtest golden vectors")
+    with open(os.path.join(OUT, "ref_gtest_vectors.json"), "w") as f:
+        json.dump(extract_gtest_vectors(), f)
+
+    from oracle import refapi
+    assert refapi.available(), "build oracle/_ref first: make -f oracle/Makefile.ref -j8"
+
+    print("tiny model via the reference spec writer")
+    mdir = os.path.join(OUT, "tiny_llama_int8")
+    V = make_tiny_model(mdir)
+    g = refapi.RefGenerator(mdir, "int8", 4)
+    rng = np.random.default_rng(42)
+    prompts = rng.integers(3, V, size=(3, 7), dtype=np.int32)
+    logits = g.forward(prompts)
+    gen = g.generate(prompts, max_length=12, min_length=0, end_id=2)
+    gen_min = g.generate(prompts, max_length=12, min_length=12, end_id=2)
+    np.savez(os.path.join(OUT, "tiny_llama_int8_ref.npz"), prompts=prompts, logits=logits,
+             generated=np.array(gen, dtype=object), generated_min12=np.array(gen_min, dtype=np.int32),
+             allow_pickle=True)
+    g.close()
+
+    print("reference ops on seeded random inputs")
+    r = np.random.default_rng(7)
+    d = {}
+    x = (r.standard_normal((5, 96)) * 3).astype(np.float32)
+    x[3] = 0
+    d["q_x"] = x
+    d["q_q"], d["q_s"] = refapi.quantize(x)
+    a = r.integers(-127, 128, size=(5, 96), dtype=np.int8)
+    b = r.integers(-127, 128, size=(24, 96), dtype=np.int8)
+    d["g_a"], d["g_b"], d["g_c"] = a, b, refapi.gemm_s8(a, b)
+    sa = r.uniform(1, 50, 5).astype(np.float32)
+    sb = r.uniform(100, 900, 24).astype(np.float32)
+    bias = r.standard_normal(24).astype(np.float32)
+    d["dq_sa"], d["dq_sb"], d["dq_bias"] = sa, sb, bias
+    for act in (-1, 0, 1, 2, 3, 4, 5, 6):
+        d["dq_y_act%d" % act] = refapi.dequantize_gemm(d["g_c"], sa, sb, bias, act)
+    d["dq_y_nobias"] = refapi.dequantize_gemm(d["g_c"], sa, sb, None, -1)
+    gamma = r.standard_normal(96).astype(np.float32)
+    d["rn_gamma"], d["rn_y"] = gamma, refapi.rms_norm(gamma, x, 1e-5)
+    xr = r.standard_normal((2, 3, 4, 16)).astype(np.float32)
+    ang = r.standard_normal((4, 16)).astype(np.float32)
+    d["ro_x"], d["ro_sin"], d["ro_cos"] = xr, np.sin(ang), np.cos(ang)
+    d["ro_y_interleave"] = refapi.rotary(xr, d["ro_sin"], d["ro_cos"], True)
+    d["ro_y_half"] = refapi.rotary(xr, d["ro_sin"], d["ro_cos"], False)
+    sx = r.standard_normal((6, 33)).astype(np.float32)
+    lens = np.array([33, 1, 7, 20, 33, 2], np.int32)
+    d["sm_x"], d["sm_len"] = sx, lens
+    d["sm_y"], d["sm_y_len"] = refapi.softmax(sx), refapi.softmax(sx, lens)
+    d["sm_logy"] = refapi.softmax(sx, None, True)
+    tx = r.standard_normal((4, 1000)).astype(np.float32)
+    tx[1, 17] = tx[1, 500] = 9.0   # exact tie: lowest index must win
+    d["tk_x"] = tx
+    d["tk_v1"], d["tk_i1"] = refapi.topk(tx, 1)
+    d["tk_v4"], d["tk_i4"] = refapi.topk(tx, 4)
+    gd = r.standard_normal((50, 8)).astype(np.float32)
+    gi = r.integers(0, 50, 9).astype(np.int32)
+    d["ga_d"], d["ga_i"], d["ga_y"] = gd, gi, refapi.gather(gd, gi)
+    np.savez(os.path.join(OUT, "ref_ops_random.npz"), **d)
+    print("done")
+
+
+if __name__ == "__main__":
+    main()
