@@ -1,0 +1,304 @@
+#!/usr/bin/env python
+"""bench.py — generate_batch tokens/sec, Llama-3-8B INT8 (int8_float16), greedy, synthetic weights/prompts.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--batch B] [--impl ours|reference] [--model 8b|1b|tiny]
+
+A "step" is one decode step of the whole batch (B generated tokens) of BASELINE.json configs[2]
+("Llama-3-8B generate_batch INT8, seq 2048, bsz 1 and 32, on 1xB200"): prompt P=1024 then K generated
+tokens per sequence.  One JSON line on stdout (rank 0):
+  value  = B*K*N / device time of K decode steps, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e    = the same tokens/s through ctranslate2_b200.Generator.generate_batch with HOST prompt ids and HOST
+           result ids (prefill + decode + host<->device copies inside the timed region)
+  roofline = the weight-streaming tcgen05 GEMM timed alone with CUDA events over buffers larger than L2
+  cpu_baseline = the unmodified reference (oracle/_ref, Ruy INT8) on the host cores, bounded sample
+N>1: independent data-parallel replicas (one process per GPU, no data-path collective): scaling "weak".
+`--impl reference` times the reference's own CPU implementation (oracle/_ref) on the host cores.
+"""
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODELS = {
+    "8b": dict(num_layers=32, num_heads=32, num_heads_kv=8, head_dim=128, ffn_dim=14336, vocab_size=128256),
+    "1b": dict(num_layers=16, num_heads=32, num_heads_kv=8, head_dim=64, ffn_dim=8192, vocab_size=128256),
+    "tiny": dict(num_layers=2, num_heads=8, num_heads_kv=2, head_dim=128, ffn_dim=2048, vocab_size=2000),
+}
+NAMES = {"8b": "Llama-3-8B", "1b": "Llama-3.2-1B-shaped", "tiny": "tiny-llama-d128"}
+PROMPT_LEN = 1024
+
+
+def model_dir(name):
+    """Synthetic model directory in the reference's on-disk format (written once per box)."""
+    from ctranslate2_b200.converters.synthetic import LlamaConfig, write_llama_model
+    base = os.environ.get("CT2B200_BENCH_DIR", os.path.join(tempfile.gettempdir(), "ct2b200_bench"))
+    d = os.path.join(base, "llama_%s_int8_float16" % name)
+    done = os.path.join(d, ".complete")
+    if not os.path.exists(done):
+        os.makedirs(base, exist_ok=True)
+        t0 = time.time()
+        write_llama_model(d, LlamaConfig(**MODELS[name]), "int8_float16", seed=1234, fast_int8=True)
+        open(done, "w").write("ok")
+        print("[bench] wrote %s in %.1fs" % (d, time.time() - t0), file=sys.stderr)
+    return d
+
+
+def prompts_for(name, batch, plen, seed=42):
+    import numpy as np
+    v = MODELS[name]["vocab_size"]
+    return np.random.default_rng(seed).integers(3, v, size=(batch, plen), dtype=np.int32)
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.idx, self.rows, self.proc = gpu_index, [], None
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True)
+            self.t.start()
+        except Exception:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def __exit__(self, *a):
+        if self.proc:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except Exception:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = max(mx, float(r[2]))
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        # median over the busier half of the samples (the sampler also sees idle gaps)
+        sm.sort()
+        busy = sm[len(sm) // 2:] if sm else []
+        return {"sm_mhz": statistics.median(busy) if busy else None, "sm_max_mhz": mx or None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        j = json.load(open(p))
+        return float(j["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def step_bytes(name, batch, ctx):
+    """Algorithmic bytes of one decode step: int8 linear weights + fp32 row scales + KV read."""
+    m = MODELS[name]
+    d = m["num_heads"] * m["head_dim"]
+    qkv = (m["num_heads"] + 2 * m["num_heads_kv"]) * m["head_dim"]
+    per_layer = qkv * d + d * d + 3 * m["ffn_dim"] * d
+    w = m["num_layers"] * per_layer + m["vocab_size"] * d
+    scales = 4 * (m["num_layers"] * (qkv + d + 2 * m["ffn_dim"] + d) + m["vocab_size"])
+    kv = 2 * m["num_heads_kv"] * m["head_dim"] * 2 * m["num_layers"]
+    return w + scales + batch * ctx * kv
+
+
+def gemm_roofline(name, batch, device):
+    """Times the dominant kernel (fused gate/up INT8 GEMM on tcgen05, weight streaming) alone with CUDA
+    events, cycling through more weight copies than fit in L2 (126 MB) so every launch streams from HBM."""
+    import torch
+    from ctranslate2_b200 import ops
+    m = MODELS[name]
+    d, f = m["num_heads"] * m["head_dim"], m["ffn_dim"]
+    copies = max(3, int(400e6 // (2 * f * d)) + 1)
+    g = torch.Generator(device=device).manual_seed(0)
+    wg = [torch.randint(-127, 128, (f, d), dtype=torch.int8, device=device, generator=g) for _ in range(copies)]
+    wu = [torch.randint(-127, 128, (f, d), dtype=torch.int8, device=device, generator=g) for _ in range(copies)]
+    sg = torch.full((f,), 3000.0, device=device)
+    xq = torch.randint(-127, 128, (batch, d), dtype=torch.int8, device=device, generator=g)
+    xs = torch.full((batch,), 40.0, device=device)
+    for i in range(copies):
+        ops.dense_int8_glu(xq, xs, wg[i], sg, wu[i], sg)
+    torch.cuda.synchronize()
+    iters = 4 * copies
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ops.dense_int8_glu(xq, xs, wg[i % copies], sg, wu[i % copies], sg)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = 2 * f * d + 2 * f * 4 + batch * d + batch * 4 + batch * f * 2    # weights + scales + x + h(out)
+    peak, how = measured_peaks()
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "gemm_tc_kernel<s8, swap-AB, GLU> (ffn gate/up %dx%d, m=%d)" % (2 * f, d, batch),
+            "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
+            "traffic": None, "bytes_per_launch": alg, "us_per_launch": round(ms * 1e3, 2), "peak_source": how}
+
+
+def reference_cpu(name, batch, steps, warmup, budget_s=100.0, threads=None):
+    """The unmodified reference (oracle/_ref: CTranslate2 CPU build, Ruy INT8 GEMM) on the host cores:
+    generate_batch of `batch` prompts (bounded sample: prompt of 8 tokens) for as many decode steps as fit."""
+    import numpy as np
+    from oracle import refapi
+    if not refapi.available():
+        return None
+    threads = threads or os.cpu_count() or 1
+    g = refapi.RefGenerator(model_dir(name), "int8", threads)
+    prompts = prompts_for(name, batch, 8)
+    t0 = time.time()
+    g.generate(prompts, max_length=2, min_length=2, end_id=2)      # warm-up + calibration (3 forward passes)
+    per_step = max(1e-3, (time.time() - t0) / 3.0)
+    for _ in range(max(0, min(warmup, 2) - 1)):
+        g.generate(prompts, max_length=1, min_length=1, end_id=2)
+    k = int(max(1, min(steps, budget_s / per_step)))
+    t0 = time.time()
+    out = g.generate(prompts, max_length=k, min_length=k, end_id=2)
+    dt = time.time() - t0
+    g.close()
+    toks = sum(len(o) for o in out)
+    return {"value": toks / dt, "unit": "tokens/s", "cores": threads, "kind": "reference", "steps": k,
+            "sample": "reference CPU (Ruy int8) generate_batch: batch %d, prompt 8 tokens, %d generated tokens "
+                      "per sequence, prompt pass included" % (batch, k), "seconds": dt}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=256)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--impl", default="ours")
+    ap.add_argument("--model", default="8b", choices=list(MODELS))
+    ap.add_argument("--prompt-len", type=int, default=PROMPT_LEN)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    K, W, B, P = args.steps, max(3, args.warmup), args.batch, args.prompt_len
+    config = {"workload": "%s generate_batch INT8 (int8_float16), greedy, bsz %d, prompt %d + %d generated "
+                          "(BASELINE.json configs[2])" % (NAMES[args.model], B, P, K),
+              "global_batch": B * max(1, world), "prompt_len": P, "parallelism": "dp%d (replicas, no collective)" % world,
+              "l2": "every step streams %.1f GB of weights (> 126 MB L2) — no flush needed" % (step_bytes(args.model, 0, 0) / 1e9)}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        r = reference_cpu(args.model, B, K, W)
+        if r is None:
+            print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (make -f oracle/Makefile.ref)"}))
+            return
+        line = {"impl": "reference", "metric": "generate_batch tokens/sec", "value": round(r["value"], 3),
+                "unit": "tokens/s", "n_gpus": 0, "steps": r["steps"], "warmup": W,
+                "ms_per_step": round(1e3 * r["seconds"] / r["steps"], 3), "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "s8 (int8 weights/activations, fp32 epilogue)", "data": "synthetic",
+                "config": config, "cpu_baseline": {k: r[k] for k in ("value", "unit", "cores", "kind", "sample")},
+                "e2e": {"value": round(r["value"], 3), "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+        print(json.dumps(line))
+        return
+
+    import numpy as np
+    import torch
+    import ctranslate2_b200 as ct2
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    torch.cuda.set_device(local_rank)
+    mdir = model_dir(args.model) if local_rank == 0 else None
+    if world > 1:
+        torch.distributed.barrier()
+        mdir = model_dir(args.model)
+    max_len = P + max(K, 8) + W + 8
+    gen = ct2.Generator(mdir, device_index=local_rank, compute_type="int8_float16", max_batch_size=B,
+                        max_length=max_len, use_cuda_graph=not args.no_graph)
+    info = gen.info()
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            torch.distributed.barrier()
+            torch.cuda.synchronize()
+
+    # ---- device-timed decode (inputs resident), K steps after W warm-up steps ----
+    sync_all()
+    with ClockSampler(local_rank) as clocks:
+        pre_ms, dec_ms, launches = gen.bench_decode(B, P, K, W)
+        sync_all()
+    t = torch.tensor([dec_ms, pre_ms], device="cuda", dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    dec_ms, pre_ms = float(t[0]), float(t[1])
+    value = B * K * world / (dec_ms * 1e-3)
+
+    # ---- end to end through the public API with host buffers ----
+    prompts = prompts_for(args.model, B, P, seed=42 + rank)
+    gen.generate_batch(prompts[:, :8].tolist(), max_length=2, min_length=2, end_token=[0])   # warm the small path
+    sync_all()
+    t0 = time.perf_counter()
+    res = gen.generate_batch(prompts, max_length=K, min_length=K, end_token=[1])
+    torch.cuda.synchronize()
+    e2e_s = time.perf_counter() - t0
+    assert all(len(r.sequences_ids[0]) == K for r in res)
+    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
+    if world > 1:
+        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+    e2e_s = float(t[0])
+    e2e = {"value": round(B * K * world / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": round(B * P * 4 / K, 1),
+           "d2h_bytes_per_step": B * 4, "seconds": round(e2e_s, 4), "includes": "prompt H2D + prefill(P-1) + K decode steps + ids D2H"}
+
+    if rank != 0:
+        return
+    peak, how = measured_peaks()
+    ctx_mean = P + K / 2.0
+    sb = step_bytes(args.model, B, ctx_mean)
+    step_gbs = sb / (dec_ms / K * 1e-3) / 1e9
+    config.update({"step_bytes_algorithmic": int(sb), "step_GBps": round(step_gbs, 1),
+                   "step_roofline_frac": round(step_gbs / peak, 4), "prefill_ms": round(pre_ms, 2),
+                   "prefill_tokens_per_s": round(B * (P - 1) / (pre_ms * 1e-3), 1), "weight_bytes": info["weight_bytes"]})
+    line = {"metric": "generate_batch tokens/sec", "value": round(value, 2), "unit": "tokens/s", "n_gpus": world,
+            "steps": K, "warmup": W, "ms_per_step": round(dec_ms / K, 4), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "s8 (int8 x int8 -> s32 on tcgen05; f16 activations, f32 epilogue/softmax)",
+            "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
+            "gpu_launches": int(launches)}
+    try:
+        line["roofline"] = gemm_roofline(args.model, B, "cuda")
+    except Exception as ex:  # keep the headline even if the side measurement fails
+        line["roofline"] = {"error": str(ex)}
+    if world == 1 and not args.no_cpu_baseline:
+        gen.close()
+        del gen
+        torch.cuda.empty_cache()
+        r = reference_cpu(args.model, B, 64, 1, budget_s=20.0)
+        line["cpu_baseline"] = ({k: r[k] for k in ("value", "unit", "cores", "kind", "sample")} if r else
+                                {"value": None, "kind": "reference", "sample": "oracle/_ref not built"})
+    print(json.dumps(line))
+
+
+if __name__ == "__main__":
+    main()

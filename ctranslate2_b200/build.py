@@ -1,0 +1,69 @@
+"""In-tree build of libct2b200.so for sm_100a (cross-compiles without a GPU).
+
+    python -m ctranslate2_b200.build [--force]
+
+One nvcc invocation per translation unit (run in parallel), then a shared-library link against the
+static CUDA runtime.  The .so lands next to this file so it travels with the repository snapshot.
+"""
+import concurrent.futures
+import hashlib
+import os
+import subprocess
+import sys
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+OUT = os.path.join(HERE, "libct2b200.so")
+OBJ = os.path.join(HERE, "_build")
+SOURCES = [
+    "kernels/rowwise.cu", "kernels/gemm_s8_mma.cu", "kernels/gemm_tc.cu", "kernels/attention.cu",
+    "kernels/decode_loop.cu", "host/engine.cc", "c_api.cc",
+]
+NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
+FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-lineinfo", "-Xcompiler", "-fPIC",
+         "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-x", "cu"]
+
+
+def _deps_hash(src):
+    h = hashlib.sha1()
+    for root, _, files in os.walk(CSRC):
+        for f in sorted(files):
+            if f.endswith((".cuh", ".h")):
+                h.update(open(os.path.join(root, f), "rb").read())
+    h.update(open(os.path.join(HERE, "..", "include", "ct2b200.h"), "rb").read())
+    h.update(open(os.path.join(CSRC, src), "rb").read())
+    h.update(" ".join(FLAGS).encode())
+    return h.hexdigest()
+
+
+def _compile(src, force):
+    obj = os.path.join(OBJ, src.replace("/", "_") + ".o")
+    stamp = obj + ".sha1"
+    digest = _deps_hash(src)
+    if not force and os.path.exists(obj) and os.path.exists(stamp) and open(stamp).read() == digest:
+        return obj
+    cmd = [NVCC] + FLAGS + ["-c", os.path.join(CSRC, src), "-o", obj]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError("nvcc failed for %s:\n%s\n%s" % (src, r.stdout, r.stderr))
+    open(stamp, "w").write(digest)
+    return obj
+
+
+def build(force=False, verbose=True):
+    os.makedirs(OBJ, exist_ok=True)
+    with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
+        objs = list(ex.map(lambda s: _compile(s, force), SOURCES))
+    newest = max(os.path.getmtime(o) for o in objs)
+    if force or not os.path.exists(OUT) or os.path.getmtime(OUT) < newest:
+        cmd = [NVCC, "-shared", "-o", OUT] + objs + ["-cudart", "static", "-Xlinker", "--exclude-libs,ALL"]
+        r = subprocess.run(cmd, capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    if verbose:
+        print("built", OUT)
+    return OUT
+
+
+if __name__ == "__main__":
+    build(force="--force" in sys.argv)

@@ -1,0 +1,317 @@
+// c_api.cc — the extern "C" boundary declared in include/ct2b200.h.  Every entry point converts C++
+// exceptions into an error code + thread-local message (the reference surfaces std::invalid_argument /
+// std::runtime_error through std::future::get(), src/cuda/utils.h:51-96).
+#include <cuda_runtime.h>
+
+#include <cstring>
+#include <string>
+
+#include "common.cuh"
+#include "host/engine.h"
+#include "kernels/kernels.h"
+
+using namespace ct2b200;
+
+namespace {
+thread_local std::string g_error;
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    f();
+    return 0;
+  } catch (const InvalidArgument& e) {
+    g_error = std::string("invalid argument: ") + e.what();
+    return 2;
+  } catch (const std::invalid_argument& e) {
+    g_error = std::string("invalid argument: ") + e.what();
+    return 2;
+  } catch (const std::exception& e) {
+    g_error = e.what();
+    return 1;
+  }
+}
+
+cudaStream_t S(void* s) { return static_cast<cudaStream_t>(s); }
+
+void require_device() {
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess || n == 0)
+    throw std::runtime_error("no CUDA device: ct2b200 has no CPU fallback");
+}
+}  // namespace
+
+struct ct2b200_generator {
+  std::unique_ptr<Generator> impl;
+};
+
+extern "C" {
+
+CT2B200_API const char* ct2b200_last_error(void) { return g_error.c_str(); }
+CT2B200_API const char* ct2b200_version(void) { return "0.1.0 (sm_100a)"; }
+CT2B200_API int64_t ct2b200_kernel_launch_count(void) { return g_kernel_launches.load(); }
+
+CT2B200_API int ct2b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem) {
+  return guarded([&] {
+    require_device();
+    cudaDeviceProp p;
+    CT2_CUDA_CHECK(cudaGetDeviceProperties(&p, device));
+    if (sm_count) *sm_count = p.multiProcessorCount;
+    if (cc_major) *cc_major = p.major;
+    if (cc_minor) *cc_minor = p.minor;
+    if (total_mem) *total_mem = p.totalGlobalMem;
+  });
+}
+
+CT2B200_API int ct2b200_quantize_rows(const void* x, int dtype, int64_t rows, int64_t cols, int round_before_cast, int8_t* q,
+                          float* scale, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_quantize_rows(x, dtype, rows, cols, round_before_cast != 0, q, scale, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_gemm_s8(const int8_t* a, const int8_t* b, int64_t m, int64_t n, int64_t k, int32_t* c, int impl,
+                    void* stream) {
+  return guarded([&] {
+    require_device();
+    DenseEpilogue e{nullptr, nullptr, nullptr, nullptr, nullptr, c, -1, n};
+    gemm_s8(a, b, m, n, k, e, CT2B200_F32, impl, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dequantize_gemm_output(const int32_t* c, const float* a_scale, const float* b_scale, const void* bias,
+                                   int act, int64_t m, int64_t n, void* y, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    DenseEpilogue e{a_scale, b_scale, bias, nullptr, y, nullptr, act, n};
+    launch_dequantize_gemm_output(c, e, m, n, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dequantize_rows(const int8_t* x, const float* scale, int64_t rows, int64_t cols, void* y, int dtype,
+                            void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_dequantize_rows(x, scale, rows, cols, y, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dense_s8(const int8_t* xq, const float* x_scale, const int8_t* w, const float* w_scale, const void* bias,
+                     const void* residual, int act, int64_t m, int64_t n, int64_t k, void* y, int dtype, int impl,
+                     void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(x_scale && w_scale, "dense_s8: scales are required");
+    DenseEpilogue e{x_scale, w_scale, bias, residual, y, nullptr, act, n};
+    gemm_s8(xq, w, m, n, k, e, dtype, impl, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dense_s8_glu(const int8_t* xq, const float* x_scale, const int8_t* w_gate, const float* w_gate_scale,
+                         const int8_t* w_up, const float* w_up_scale, int act, int64_t m, int64_t n, int64_t k, void* h,
+                         int dtype, int impl, void* stream) {
+  return guarded([&] {
+    require_device();
+    GluEpilogue g{x_scale, w_gate_scale, w_up_scale, h, act, n};
+    gemm_s8_glu(xq, w_gate, w_up, m, n, k, g, dtype, impl, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_gemm_f16(const void* a, const void* b, const void* bias, const void* residual, int act, int64_t m,
+                     int64_t n, int64_t k, void* c, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    gemm_f16_tc(a, b, bias, residual, act, m, n, k, c, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_rms_norm(const void* gamma, const void* x, int64_t rows, int64_t cols, float eps, int use_residual,
+                     void* y, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_rms_norm(gamma, x, rows, cols, eps, use_residual != 0, y, nullptr, nullptr, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_rms_norm_quantize(const void* gamma, const void* x, int64_t rows, int64_t cols, float eps,
+                              int use_residual, int8_t* q, float* scale, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(q && scale, "rms_norm_quantize: outputs are required");
+    launch_rms_norm(gamma, x, rows, cols, eps, use_residual != 0, nullptr, q, scale, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_rotary(const void* x, const void* sin, const void* cos, int64_t batch, int64_t time, int64_t depth,
+                   int64_t ndims, int interleave, void* y, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(ndims <= depth && ndims % 2 == 0, "rotary: ndims must be even and <= depth");
+    launch_rotary(x, sin, cos, batch, time, depth, ndims, interleave != 0, y, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_softmax(const void* x, const int32_t* lengths, int64_t rows, int64_t cols, int log, void* y, int dtype,
+                    void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_softmax(x, lengths, rows, cols, log != 0, y, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_topk(const void* x, int64_t rows, int64_t cols, int k, void* values, int32_t* indices, int dtype,
+                 void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(k >= 1 && k <= 64 && k <= cols, "topk: k must be in [1, min(64, cols)]");
+    launch_topk(x, rows, cols, k, values, indices, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_gather_rows(const void* data, const int32_t* ids, int64_t num_ids, int64_t row_bytes, void* out,
+                        void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_gather_rows(data, ids, num_ids, row_bytes, out, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_embedding_s8(const int8_t* w, const float* scale, const int32_t* ids, int64_t num_ids, int64_t depth,
+                         void* y, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_embedding_s8(w, scale, ids, num_ids, depth, y, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_mul_quantize(const void* gate, const void* up, int64_t rows, int64_t cols, int8_t* q, float* scale,
+                         int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    launch_mul_quantize(gate, up, rows, cols, q, scale, dtype, S(stream));
+  });
+}
+
+CT2B200_API size_t ct2b200_attention_decode_workspace(int64_t batch, int num_heads, int head_dim, int64_t max_len) {
+  // sized for the largest split count the launcher may choose (64)
+  (void)max_len;
+  return attention_decode_workspace_bytes(batch, num_heads, head_dim, 64);
+}
+
+CT2B200_API int ct2b200_attention_decode(const void* qkv, void* k_cache, void* v_cache, const float* sin, const float* cos,
+                             const int32_t* lens, int64_t batch, int num_heads, int num_heads_kv, int head_dim,
+                             int64_t max_len, int rotary_interleave, float scale, void* out, void* workspace,
+                             size_t workspace_bytes, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    int dev = 0, sms = 148;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int splits = attention_decode_splits(batch, num_heads_kv, max_len, sms);
+    launch_attention_decode(qkv, k_cache, v_cache, sin, cos, lens, batch, num_heads, num_heads_kv, head_dim, max_len,
+                            rotary_interleave != 0, scale, out, workspace, workspace_bytes, splits, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_attention_prefill(const void* qkv, void* k_cache, void* v_cache, const float* sin, const float* cos,
+                              const int32_t* lengths, int64_t batch, int64_t time, int64_t offset, int num_heads,
+                              int num_heads_kv, int head_dim, int64_t max_len, int rotary_interleave, float scale,
+                              void* out, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(offset + time <= max_len, "attention_prefill: offset + time exceeds max_len");
+    launch_rope_append(const_cast<void*>(qkv), k_cache, v_cache, sin, cos, lengths, batch, time, offset, num_heads,
+                       num_heads_kv, head_dim, max_len, rotary_interleave != 0, dtype, S(stream));
+    launch_attention_prefill_simple(qkv, k_cache, v_cache, lengths, batch, time, offset, num_heads, num_heads_kv,
+                                    head_dim, max_len, scale, out, dtype, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dense_awq(const void*, const int32_t*, const void*, const int32_t*, int, int, const void*, const void*,
+                      int, int64_t, int64_t, int64_t, void*, void*) {
+  g_error = "ct2b200_dense_awq: AWQ-INT4 kernels are not built in this revision";
+  return 3;
+}
+CT2B200_API int ct2b200_dequantize_awq(const int32_t*, const void*, const int32_t*, int, int, int64_t, int64_t, void*, void*) {
+  g_error = "ct2b200_dequantize_awq: AWQ-INT4 kernels are not built in this revision";
+  return 3;
+}
+
+// ---- engine ----
+CT2B200_API ct2b200_generator* ct2b200_generator_open(const char* model_dir, const ct2b200_generator_config* config) {
+  ct2b200_generator* g = nullptr;
+  const int rc = guarded([&] {
+    require_device();
+    CT2_REQUIRE(model_dir && config, "generator_open: null argument");
+    auto holder = std::make_unique<ct2b200_generator>();
+    holder->impl = std::make_unique<Generator>(model_dir, *config);
+    g = holder.release();
+  });
+  return rc == 0 ? g : nullptr;
+}
+
+CT2B200_API void ct2b200_generator_close(ct2b200_generator* g) { delete g; }
+
+CT2B200_API int ct2b200_generator_vocab_size(const ct2b200_generator* g) {
+  return g ? static_cast<int>(g->impl->decoder().config().vocab) : -1;
+}
+
+CT2B200_API int ct2b200_generator_info(const ct2b200_generator* g, int* num_layers, int* num_heads, int* num_heads_kv, int* head_dim,
+                           int* d_model, int64_t* weight_bytes) {
+  return guarded([&] {
+    CT2_REQUIRE(g, "null generator");
+    const ModelConfig& c = g->impl->decoder().config();
+    if (num_layers) *num_layers = c.num_layers;
+    if (num_heads) *num_heads = c.num_heads;
+    if (num_heads_kv) *num_heads_kv = c.num_heads_kv;
+    if (head_dim) *head_dim = c.head_dim;
+    if (d_model) *d_model = static_cast<int>(c.d_model);
+    if (weight_bytes) *weight_bytes = c.weight_bytes;
+  });
+}
+
+CT2B200_API int ct2b200_generate_batch(ct2b200_generator* g, const int32_t* prompt_ids, const int32_t* prompt_lens, int64_t batch,
+                           int64_t max_prompt_len, int64_t max_length, int64_t min_length, const int32_t* end_ids,
+                           int num_end_ids, int return_end_token, int32_t* out_ids, int32_t* out_lens) {
+  return guarded([&] {
+    CT2_REQUIRE(g && prompt_ids && prompt_lens && out_ids && out_lens, "generate_batch: null argument");
+    GenerationRequest r;
+    r.prompt_ids = prompt_ids;
+    r.prompt_lens = prompt_lens;
+    r.batch = batch;
+    r.max_prompt_len = max_prompt_len;
+    r.max_length = max_length;
+    r.min_length = min_length;
+    r.end_ids.assign(end_ids, end_ids + (end_ids ? num_end_ids : 0));
+    r.return_end_token = return_end_token != 0;
+    g->impl->generate(r, out_ids, out_lens);
+  });
+}
+
+CT2B200_API int ct2b200_forward_batch(ct2b200_generator* g, const int32_t* ids, int64_t batch, int64_t time, int return_log_probs,
+                          float* logits) {
+  return guarded([&] {
+    CT2_REQUIRE(g && ids && logits, "forward_batch: null argument");
+    g->impl->forward(ids, batch, time, return_log_probs != 0, logits);
+  });
+}
+
+CT2B200_API int ct2b200_bench_decode(ct2b200_generator* g, int64_t batch, int64_t prompt_len, int64_t steps, int64_t warmup,
+                         float* prefill_ms, float* decode_ms, int64_t* kernel_launches) {
+  return guarded([&] {
+    CT2_REQUIRE(g, "null generator");
+    g->impl->bench_decode(batch, prompt_len, steps, warmup, prefill_ms, decode_ms, kernel_launches);
+  });
+}
+
+CT2B200_API int ct2b200_nccl_unique_id(void*) {
+  g_error = "tensor parallel is not built in this revision";
+  return 3;
+}
+CT2B200_API int ct2b200_generator_set_nccl(ct2b200_generator*, const void*) {
+  g_error = "tensor parallel is not built in this revision";
+  return 3;
+}
+
+}  // extern "C"

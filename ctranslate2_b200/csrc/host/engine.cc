@@ -1,0 +1,747 @@
+// engine.cc — host side: model.bin loader, Llama-class decoder driver, greedy search, Generator.
+// See engine.h.  Reference counterparts: src/models/model.cc, src/layers/{transformer,attention,common}.cc,
+// src/decoding.cc, src/models/language_model.cc, src/generator.cc.
+#include "engine.h"
+
+#include <fcntl.h>
+#include <sys/mman.h>
+#include <sys/stat.h>
+#include <unistd.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <fstream>
+#include <sstream>
+
+namespace ct2b200 {
+
+// =============================================================================================
+// ModelFile
+// =============================================================================================
+namespace {
+struct Cursor {
+  const uint8_t* p;
+  const uint8_t* end;
+  template <typename U> U read() {
+    if (p + sizeof(U) > end) throw std::runtime_error("model.bin: unexpected end of file");
+    U v;
+    std::memcpy(&v, p, sizeof(U));
+    p += sizeof(U);
+    return v;
+  }
+  std::string read_string() {
+    const uint16_t n = read<uint16_t>();
+    if (p + n > end) throw std::runtime_error("model.bin: unexpected end of file");
+    std::string s(reinterpret_cast<const char*>(p), n ? n - 1 : 0);
+    p += n;
+    return s;
+  }
+};
+size_t type_size(int type_id) {
+  switch (type_id) {
+    case 0: return 4;   // float32
+    case 1: return 1;   // int8
+    case 2: return 2;   // int16
+    case 3: return 4;   // int32
+    case 4: return 2;   // float16
+    case 5: return 2;   // bfloat16
+    default: throw std::runtime_error("model.bin: unknown data type id " + std::to_string(type_id));
+  }
+}
+float half_bits_to_float(uint16_t h) {
+  const uint32_t sign = (h >> 15) & 1, exp = (h >> 10) & 0x1F, man = h & 0x3FF;
+  float v;
+  if (exp == 0) v = std::ldexp(static_cast<float>(man), -24);
+  else if (exp == 31) v = man ? NAN : INFINITY;
+  else v = std::ldexp(static_cast<float>(man | 0x400), static_cast<int>(exp) - 25);
+  return sign ? -v : v;
+}
+float bf16_bits_to_float(uint16_t b) {
+  uint32_t u = static_cast<uint32_t>(b) << 16;
+  float f;
+  std::memcpy(&f, &u, 4);
+  return f;
+}
+}  // namespace
+
+double HostVariable::scalar() const {
+  switch (type_id) {
+    case 0: { float v; std::memcpy(&v, data, 4); return v; }
+    case 1: return *reinterpret_cast<const int8_t*>(data);
+    case 2: { int16_t v; std::memcpy(&v, data, 2); return v; }
+    case 3: { int32_t v; std::memcpy(&v, data, 4); return v; }
+    case 4: { uint16_t v; std::memcpy(&v, data, 2); return half_bits_to_float(v); }
+    default: { uint16_t v; std::memcpy(&v, data, 2); return bf16_bits_to_float(v); }
+  }
+}
+
+ModelFile::ModelFile(const std::string& model_dir) {
+  const std::string path = model_dir + "/model.bin";
+  const int fd = ::open(path.c_str(), O_RDONLY);
+  if (fd < 0) throw std::runtime_error("Unable to open file 'model.bin' in model '" + model_dir + "'");
+  struct stat st;
+  ::fstat(fd, &st);
+  map_size_ = static_cast<size_t>(st.st_size);
+  map_ = ::mmap(nullptr, map_size_, PROT_READ, MAP_PRIVATE, fd, 0);
+  ::close(fd);
+  if (map_ == MAP_FAILED) throw std::runtime_error("mmap failed for " + path);
+  Cursor c{static_cast<const uint8_t*>(map_), static_cast<const uint8_t*>(map_) + map_size_};
+  binary_version = c.read<uint32_t>();
+  if (binary_version < 4 || binary_version > 6)
+    throw std::runtime_error("Unsupported model binary version " + std::to_string(binary_version) +
+                             " (this engine reads versions 4 to 6)");
+  spec_name = c.read_string();
+  revision = c.read<uint32_t>();
+  const uint32_t nvars = c.read<uint32_t>();
+  for (uint32_t i = 0; i < nvars; ++i) {
+    const std::string name = c.read_string();
+    HostVariable v;
+    const uint8_t rank = c.read<uint8_t>();
+    for (int r = 0; r < rank; ++r) v.shape.push_back(c.read<uint32_t>());
+    v.type_id = c.read<uint8_t>();
+    v.nbytes = c.read<uint32_t>();
+    if (static_cast<size_t>(v.size()) * type_size(v.type_id) != v.nbytes)
+      throw std::runtime_error("model.bin: variable " + name + " has inconsistent size");
+    if (c.p + v.nbytes > c.end) throw std::runtime_error("model.bin: unexpected end of file");
+    v.data = c.p;
+    c.p += v.nbytes;
+    vars_.emplace(name, v);
+  }
+  const uint32_t naliases = c.read<uint32_t>();
+  for (uint32_t i = 0; i < naliases; ++i) {
+    const std::string alias = c.read_string();
+    const std::string target = c.read_string();
+    auto it = vars_.find(target);
+    if (it == vars_.end()) throw std::runtime_error("model.bin: alias target not found: " + target);
+    vars_.emplace(alias, it->second);
+  }
+  std::ifstream cf(model_dir + "/config.json");
+  if (cf) {
+    std::stringstream ss;
+    ss << cf.rdbuf();
+    config_json_ = ss.str();
+  }
+}
+
+ModelFile::~ModelFile() {
+  if (map_ && map_ != MAP_FAILED) ::munmap(map_, map_size_);
+}
+
+const HostVariable* ModelFile::find(const std::string& name) const {
+  auto it = vars_.find(name);
+  return it == vars_.end() ? nullptr : &it->second;
+}
+const HostVariable& ModelFile::get(const std::string& name) const {
+  const HostVariable* v = find(name);
+  if (!v) throw std::out_of_range("variable " + name + " not found");   // models/model.cc get_variable
+  return *v;
+}
+double ModelFile::attribute(const std::string& name, double fallback) const {
+  const HostVariable* v = find(name);
+  return v ? v->scalar() : fallback;
+}
+double ModelFile::config_number(const std::string& key, double fallback) const {
+  const std::string needle = "\"" + key + "\"";
+  size_t pos = config_json_.find(needle);
+  if (pos == std::string::npos) return fallback;
+  pos = config_json_.find(':', pos);
+  if (pos == std::string::npos) return fallback;
+  const char* s = config_json_.c_str() + pos + 1;
+  char* e = nullptr;
+  const double v = std::strtod(s, &e);
+  return e == s ? fallback : v;   // null / non-number -> fallback
+}
+
+// =============================================================================================
+// device buffers
+// =============================================================================================
+void DeviceBuffer::alloc(size_t n) {
+  release();
+  if (n == 0) return;
+  CT2_CUDA_CHECK(cudaMalloc(&ptr, n));
+  bytes = n;
+}
+void DeviceBuffer::release() {
+  if (ptr) cudaFree(ptr);
+  ptr = nullptr;
+  bytes = 0;
+}
+
+namespace {
+
+// host-side conversion of a float-ish variable to the compute dtype
+std::vector<uint8_t> convert_to_dtype(const HostVariable& v, int dtype) {
+  const int64_t n = v.size();
+  std::vector<float> f(n);
+  for (int64_t i = 0; i < n; ++i) {
+    switch (v.type_id) {
+      case 0: std::memcpy(&f[i], v.data + 4 * i, 4); break;
+      case 4: { uint16_t h; std::memcpy(&h, v.data + 2 * i, 2); f[i] = half_bits_to_float(h); break; }
+      case 5: { uint16_t h; std::memcpy(&h, v.data + 2 * i, 2); f[i] = bf16_bits_to_float(h); break; }
+      default: throw std::runtime_error("expected a floating point variable");
+    }
+  }
+  std::vector<uint8_t> out(n * dtype_size(dtype));
+  if (dtype == CT2B200_F32) {
+    std::memcpy(out.data(), f.data(), n * 4);
+  } else if (dtype == CT2B200_F16) {
+    for (int64_t i = 0; i < n; ++i) {
+      const __half h = __float2half_rn(f[i]);
+      std::memcpy(out.data() + 2 * i, &h, 2);
+    }
+  } else {
+    for (int64_t i = 0; i < n; ++i) {
+      const __nv_bfloat16 h = __float2bfloat16_rn(f[i]);
+      std::memcpy(out.data() + 2 * i, &h, 2);
+    }
+  }
+  return out;
+}
+
+void upload(DeviceBuffer& dst, const void* src, size_t n) {
+  dst.alloc(n);
+  if (n) CT2_CUDA_CHECK(cudaMemcpy(dst.ptr, src, n, cudaMemcpyHostToDevice));
+}
+
+int env_gemm_impl() {
+  const char* e = std::getenv("CT2B200_GEMM_IMPL");
+  if (!e) return CT2B200_GEMM_AUTO;
+  if (std::strcmp(e, "mma") == 0) return CT2B200_GEMM_MMA_SYNC;
+  if (std::strcmp(e, "tc") == 0 || std::strcmp(e, "tcgen05") == 0) return CT2B200_GEMM_TCGEN05;
+  return CT2B200_GEMM_AUTO;
+}
+
+}  // namespace
+
+// ct2b200_gemm_impl dispatch.  AUTO = tcgen05 (the sm_100a path); mma.sync only on request.
+void gemm_s8(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
+             int dtype, int impl, cudaStream_t st) {
+  if (impl == CT2B200_GEMM_AUTO) impl = env_gemm_impl();
+  if (impl == CT2B200_GEMM_MMA_SYNC) gemm_s8_mma(A, B, M, N, K, epi, dtype, st);
+  else gemm_s8_tc(A, B, M, N, K, epi, dtype, st);
+}
+void gemm_s8_glu(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
+                 const GluEpilogue& glu, int dtype, int impl, cudaStream_t st) {
+  if (impl == CT2B200_GEMM_AUTO) impl = env_gemm_impl();
+  if (impl == CT2B200_GEMM_MMA_SYNC) gemm_s8_glu_mma(A, Bgate, Bup, M, N, K, glu, dtype, st);
+  else gemm_s8_glu_tc(A, Bgate, Bup, M, N, K, glu, dtype, st);
+}
+
+// =============================================================================================
+// LlamaDecoder
+// =============================================================================================
+DeviceBuffer LlamaDecoder::load_float_vector(const ModelFile& f, const std::string& name) {
+  const HostVariable& v = f.get(name);
+  const auto bytes = convert_to_dtype(v, dtype_);
+  DeviceBuffer b;
+  upload(b, bytes.data(), bytes.size());
+  mc_.weight_bytes += bytes.size();
+  return b;
+}
+
+void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w) {
+  const HostVariable& wt = f.get(prefix + "/weight");
+  if (wt.type_id == 1) {                       // INT8 weights with per-row fp32 scales (model_spec.py:222-243)
+    CT2_REQUIRE(wt.shape.size() == 2, "int8 weight must be a matrix");
+    w.kind = DenseWeights::INT8;
+    w.n = wt.shape[0];
+    w.k = wt.shape[1];
+    upload(w.weight, wt.data, wt.nbytes);
+    const HostVariable& sc = f.get(prefix + "/weight_scale");
+    CT2_REQUIRE(sc.type_id == 0 && sc.size() == w.n, "weight_scale must be float32 [n]");
+    upload(w.scale, sc.data, sc.nbytes);
+    mc_.weight_bytes += wt.nbytes + sc.nbytes;
+  } else if (wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5) {
+    CT2_REQUIRE(dtype_ != CT2B200_F32, "float weights need compute type float16 or bfloat16 on this engine");
+    w.kind = DenseWeights::FLOAT16;
+    w.n = wt.shape[0];
+    w.k = wt.shape[1];
+    const auto bytes = convert_to_dtype(wt, dtype_);
+    upload(w.weight, bytes.data(), bytes.size());
+    mc_.weight_bytes += bytes.size();
+  } else {
+    throw std::runtime_error("unsupported weight type for " + prefix + " (AWQ models: see ct2b200_dense_awq)");
+  }
+  if (const HostVariable* b = f.find(prefix + "/bias")) {
+    const auto bytes = convert_to_dtype(*b, dtype_);
+    upload(w.bias, bytes.data(), bytes.size());
+  }
+}
+
+LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& cfg) {
+  device_ = cfg.device;
+  CT2_CUDA_CHECK(cudaSetDevice(device_));
+  int major = 0;
+  CT2_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device_));
+  if (major != 10)
+    throw std::runtime_error("ct2b200 needs an sm_100 (B200) device; found compute capability major " +
+                             std::to_string(major));
+  CT2_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
+  CT2_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  dtype_ = cfg.compute_type;
+  gemm_impl_ = cfg.gemm_impl;
+  max_batch_ = std::max<int64_t>(1, cfg.max_batch);
+  max_len_ = std::max<int64_t>(16, cfg.max_length);
+
+  if (f.spec_name != "TransformerDecoderSpec")
+    throw std::invalid_argument("ct2b200 serves TransformerDecoderSpec models; got " + f.spec_name);
+  // --- configuration (attributes: models/model.h get_attribute_with_default; attention_layer.cc:112-142) ---
+  while (f.find("decoder/layer_" + std::to_string(mc_.num_layers) + "/self_attention/linear_0/weight")) ++mc_.num_layers;
+  CT2_REQUIRE(mc_.num_layers > 0, "model has no decoder layers");
+  const std::string a0 = "decoder/layer_0/self_attention/";
+  mc_.num_heads = static_cast<int>(f.get("decoder/num_heads").scalar());
+  mc_.num_heads_kv = static_cast<int>(f.attribute(a0 + "num_heads_kv", mc_.num_heads));
+  const HostVariable& emb = f.get("decoder/embeddings/weight");
+  mc_.vocab = emb.shape[0];
+  mc_.d_model = emb.shape[1];
+  mc_.head_dim = static_cast<int>(f.attribute(a0 + "head_dim", static_cast<double>(mc_.d_model / mc_.num_heads)));
+  mc_.eps = static_cast<float>(f.config_number("layer_norm_epsilon", 1e-6));
+  mc_.rotary_base = static_cast<float>(f.attribute(a0 + "rotary_base", 10000.0));
+  mc_.rotary_interleave = f.attribute(a0 + "rotary_interleave", 1.0) != 0.0;
+  mc_.rotary_scaling_type = static_cast<int>(f.attribute(a0 + "rotary_scaling_type", -1.0));
+  mc_.rotary_scaling_factor = static_cast<float>(f.attribute(a0 + "rotary_scaling_factor", 1.0));
+  mc_.rotary_low_freq = static_cast<float>(f.attribute(a0 + "rotary_low_freq_factor", 1.0));
+  mc_.rotary_high_freq = static_cast<float>(f.attribute(a0 + "rotary_high_freq_factor", 4.0));
+  mc_.original_max_positions = static_cast<int>(f.attribute(a0 + "original_max_position_embeddings", 0.0));
+  mc_.activation = static_cast<int>(f.attribute("decoder/activation", 0.0));
+  CT2_REQUIRE(f.attribute("decoder/pre_norm", 1.0) != 0.0, "only pre-norm decoders are supported");
+  CT2_REQUIRE(f.find(a0 + "rotary_dim") != nullptr, "only rotary-position decoders are supported");
+  CT2_REQUIRE(f.attribute(a0 + "rotary_dim", 0.0) == 0.0 ||
+                  f.attribute(a0 + "rotary_dim", 0.0) == mc_.head_dim, "partial rotary_dim is not supported");
+  CT2_REQUIRE(f.find("decoder/layer_0/ffn/linear_0_noact/weight") != nullptr, "only gated FFN (ffn_glu) is supported");
+  CT2_REQUIRE(f.find("decoder/layer_0/self_attention/layer_norm/beta") == nullptr, "only RMSNorm decoders are supported");
+  CT2_REQUIRE(mc_.rotary_scaling_type != 1, "Su rotary scaling is not supported");
+  mc_.ffn_dim = f.get("decoder/layer_0/ffn/linear_0/weight").shape[0];
+
+  // --- weights ---
+  load_dense(f, "decoder/embeddings", embeddings_);
+  mc_.embeddings_int8 = embeddings_.kind == DenseWeights::INT8;
+  load_dense(f, "decoder/projection", projection_);
+  final_gamma_ = load_float_vector(f, "decoder/layer_norm/gamma");
+  layers_.resize(mc_.num_layers);
+  for (int l = 0; l < mc_.num_layers; ++l) {
+    const std::string p = "decoder/layer_" + std::to_string(l) + "/";
+    LayerWeights& lw = layers_[l];
+    lw.attn_gamma = load_float_vector(f, p + "self_attention/layer_norm/gamma");
+    lw.ffn_gamma = load_float_vector(f, p + "ffn/layer_norm/gamma");
+    load_dense(f, p + "self_attention/linear_0", lw.qkv);
+    load_dense(f, p + "self_attention/linear_1", lw.out);
+    load_dense(f, p + "ffn/linear_0", lw.gate);
+    load_dense(f, p + "ffn/linear_0_noact", lw.up);
+    load_dense(f, p + "ffn/linear_1", lw.down);
+  }
+
+  // --- rotary tables, fp32 (RotaryEmbeddings::initialize, attention_layer.cc:252-343) ---
+  {
+    const int D = mc_.head_dim;
+    std::vector<float> inv(D / 2);
+    for (int i = 0; i < D / 2; ++i) inv[i] = 1.f / std::pow(mc_.rotary_base, static_cast<float>(i * 2) / static_cast<float>(D));
+    if (mc_.rotary_scaling_type == 2) {   // Llama3
+      const float old_len = static_cast<float>(mc_.original_max_positions);
+      const float low_wl = old_len / mc_.rotary_low_freq, high_wl = old_len / mc_.rotary_high_freq;
+      std::vector<float> nf = inv;
+      for (int i = 0; i < D / 2; ++i) {
+        const float wl = 2.0f * static_cast<float>(M_PI) / inv[i];
+        if (wl < high_wl) {
+        } else if (wl > low_wl) nf[i] = inv[i] / mc_.rotary_scaling_factor;
+        else {
+          const float smooth = (old_len / wl - mc_.rotary_low_freq) / (mc_.rotary_high_freq - mc_.rotary_low_freq);
+          nf[i] = (1 - smooth) * inv[i] / mc_.rotary_scaling_factor + smooth * inv[i];
+        }
+      }
+      inv = nf;
+    }
+    std::vector<float> sn(max_len_ * D), cs(max_len_ * D);
+    for (int64_t t = 0; t < max_len_; ++t) {
+      const float tt = mc_.rotary_scaling_type == 0 ? static_cast<float>(t) / mc_.rotary_scaling_factor : static_cast<float>(t);
+      for (int i = 0; i < D; ++i) {
+        const int fi = mc_.rotary_interleave ? i / 2 : i % (D / 2);
+        const float ang = tt * inv[fi];
+        sn[t * D + i] = std::sin(ang);
+        cs[t * D + i] = std::cos(ang);
+      }
+    }
+    upload(sin_, sn.data(), sn.size() * 4);
+    upload(cos_, cs.data(), cs.size() * 4);
+  }
+
+  // --- KV arena + activations ---
+  const size_t es = dtype_size(dtype_);
+  const size_t cache_bytes = static_cast<size_t>(max_batch_) * mc_.num_heads_kv * max_len_ * mc_.head_dim * es;
+  k_cache_.resize(mc_.num_layers);
+  v_cache_.resize(mc_.num_layers);
+  for (int l = 0; l < mc_.num_layers; ++l) {
+    k_cache_[l].alloc(cache_bytes);
+    v_cache_[l].alloc(cache_bytes);
+  }
+  chunk_rows_ = std::max<int64_t>(max_batch_, std::min<int64_t>(8192, max_batch_ * max_len_));
+  const int64_t R = chunk_rows_;
+  const int64_t qkv_w = static_cast<int64_t>(mc_.num_heads + 2 * mc_.num_heads_kv) * mc_.head_dim;
+  x_.alloc(R * mc_.d_model * es);
+  xq_.alloc(R * std::max(mc_.d_model, mc_.ffn_dim));
+  xs_.alloc(R * sizeof(float));
+  qkv_.alloc(R * qkv_w * es);
+  attn_.alloc(R * mc_.num_heads * mc_.head_dim * es);
+  h_.alloc(R * mc_.ffn_dim * es);
+  logits_.alloc(max_batch_ * mc_.vocab * es);
+  gathered_.alloc(max_batch_ * mc_.d_model * es);
+  attn_splits_ = attention_decode_splits(max_batch_, mc_.num_heads_kv, max_len_, sm_count_);
+  attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, mc_.num_heads, mc_.head_dim, attn_splits_));
+  CT2_CUDA_CHECK(cudaMemset(attn_ws_.ptr, 0, attn_ws_.bytes));
+  SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+LlamaDecoder::~LlamaDecoder() {
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+// layers::Dense::operator()
+void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* xs, const void* x_float, int64_t m,
+                         const void* residual, int act, void* y) {
+  if (w.kind == DenseWeights::INT8) {
+    DenseEpilogue e{xs, w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
+    gemm_s8(xq, w.weight.as<int8_t>(), m, w.n, w.k, e, dtype_, gemm_impl_, stream_);
+  } else {
+    gemm_f16_tc(x_float, w.weight.ptr, w.bias.ptr, residual, act, m, w.n, w.k, y, dtype_, stream_);
+  }
+}
+
+void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d) {
+  const int H = mc_.num_heads, Hkv = mc_.num_heads_kv, D = mc_.head_dim;
+  const float scale = 1.f / std::sqrt(static_cast<float>(D));
+  const bool int8 = layers_[0].qkv.kind == DenseWeights::INT8;
+  CT2_REQUIRE(int8, "float-weight decoder layers are not wired yet (INT8 models only)");
+  for (int l = 0; l < mc_.num_layers; ++l) {
+    LayerWeights& lw = layers_[l];
+    // --- self attention (attention.cc:442-615) ---
+    launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                    xs_.as<float>(), dtype_, stream_);
+    dense(lw.qkv, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, qkv_.ptr);
+    if (lens_d) {
+      launch_attention_decode(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, sin_.as<float>(), cos_.as<float>(), lens_d,
+                              batch, H, Hkv, D, max_len_, mc_.rotary_interleave, scale, attn_.ptr, attn_ws_.ptr,
+                              attn_ws_.bytes, attn_splits_, dtype_, stream_);
+    } else {
+      launch_rope_append(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, sin_.as<float>(), cos_.as<float>(), nullptr,
+                         batch, time, offset, H, Hkv, D, max_len_, mc_.rotary_interleave, dtype_, stream_);
+      launch_attention_prefill_simple(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, nullptr, batch, time, offset, H,
+                                      Hkv, D, max_len_, scale, attn_.ptr, dtype_, stream_);
+    }
+    launch_quantize_rows(attn_.ptr, dtype_, rows, static_cast<int64_t>(H) * D, true, xq_.as<int8_t>(),
+                         xs_.as<float>(), stream_);
+    dense(lw.out, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
+    // --- feed forward (transformer.cc:21-51) ---
+    launch_rms_norm(lw.ffn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                    xs_.as<float>(), dtype_, stream_);
+    GluEpilogue g{xs_.as<float>(), lw.gate.scale.as<float>(), lw.up.scale.as<float>(), h_.ptr, mc_.activation, lw.gate.n};
+    gemm_s8_glu(xq_.as<int8_t>(), lw.gate.weight.as<int8_t>(), lw.up.weight.as<int8_t>(), rows, lw.gate.n, lw.gate.k,
+                g, dtype_, gemm_impl_, stream_);
+    launch_quantize_rows(h_.ptr, dtype_, rows, mc_.ffn_dim, true, xq_.as<int8_t>(), xs_.as<float>(), stream_);
+    dense(lw.down, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
+  }
+}
+
+void LlamaDecoder::project(const void* x_rows, int64_t rows, void* logits_out) {
+  launch_rms_norm(final_gamma_.ptr, x_rows, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                  xs_.as<float>(), dtype_, stream_);
+  CT2_REQUIRE(projection_.kind == DenseWeights::INT8, "float projection is not wired yet");
+  dense(projection_, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, logits_out);
+}
+
+void LlamaDecoder::forward_prefill(const int32_t* ids_d, int64_t batch, int64_t time, int64_t offset,
+                                   void* logits_out_d, const int32_t* logits_rows_d, int64_t num_logit_rows) {
+  const int64_t rows = batch * time;
+  CT2_REQUIRE(rows <= chunk_rows_, "forward_prefill: too many rows for the activation arena");
+  CT2_REQUIRE(batch <= max_batch_ && offset + time <= max_len_, "forward_prefill: batch/length exceeds the KV arena");
+  CT2_REQUIRE(embeddings_.kind == DenseWeights::INT8, "float embeddings are not wired yet");
+  launch_embedding_s8(embeddings_.weight.as<int8_t>(), embeddings_.scale.as<float>(), ids_d, rows, mc_.d_model,
+                      x_.ptr, dtype_, stream_);
+  layers_forward(rows, batch, time, offset, nullptr);
+  if (logits_out_d && num_logit_rows > 0) {
+    if (logits_rows_d) {
+      CT2_REQUIRE(num_logit_rows <= max_batch_, "too many logit rows");
+      launch_gather_rows(x_.ptr, logits_rows_d, num_logit_rows, mc_.d_model * dtype_size(dtype_), gathered_.ptr, stream_);
+      project(gathered_.ptr, num_logit_rows, logits_out_d);
+    } else {
+      project(x_.ptr, num_logit_rows, logits_out_d);
+    }
+  }
+}
+
+void LlamaDecoder::project_rows(const int32_t* rows_d, int64_t n, void* logits_out_d) {
+  CT2_REQUIRE(n <= max_batch_, "project_rows: too many rows");
+  launch_gather_rows(x_.ptr, rows_d, n, mc_.d_model * dtype_size(dtype_), gathered_.ptr, stream_);
+  project(gathered_.ptr, n, logits_out_d);
+}
+
+void LlamaDecoder::forward_step(const int32_t* ids_d, const int32_t* lens_d, int64_t batch, void* logits_out_d) {
+  CT2_REQUIRE(batch <= max_batch_, "forward_step: batch exceeds the KV arena");
+  launch_embedding_s8(embeddings_.weight.as<int8_t>(), embeddings_.scale.as<float>(), ids_d, batch, mc_.d_model,
+                      x_.ptr, dtype_, stream_);
+  layers_forward(batch, batch, 1, 0, lens_d);
+  project(x_.ptr, batch, logits_out_d);
+}
+
+// =============================================================================================
+// Generator
+// =============================================================================================
+Generator::Generator(const std::string& model_dir, const ct2b200_generator_config& cfg) : cfg_(cfg) {
+  ModelFile file(model_dir);
+  decoder_ = std::make_unique<LlamaDecoder>(file, cfg);
+  const int64_t B = decoder_->max_batch(), L = decoder_->max_length();
+  ids_d_.alloc(std::max<int64_t>(B, decoder_->prefill_chunk_rows()) * sizeof(int32_t));
+  lens_d_.alloc(B * sizeof(int32_t));
+  step_d_.alloc(4 * sizeof(int32_t));
+  forced_d_.alloc(B * L * sizeof(int32_t));
+  out_d_.alloc(B * L * sizeof(int32_t));
+  end_ids_d_.alloc(64 * sizeof(int32_t));
+  prompt_d_.alloc(B * L * sizeof(int32_t));
+  host_pinned_elems_ = static_cast<size_t>(B) * L + 64;
+  CT2_CUDA_CHECK(cudaMallocHost(&host_pinned_, host_pinned_elems_ * sizeof(int32_t)));
+}
+
+Generator::~Generator() {
+  if (graph_) cudaGraphExecDestroy(graph_);
+  if (host_pinned_) cudaFreeHost(host_pinned_);
+}
+
+// prefill `time` tokens per row from position 0, in row chunks that fit the activation arena
+void Generator::run_prefill(const int32_t* ids_d, int64_t batch, int64_t time) {
+  LlamaDecoder& d = *decoder_;
+  const int64_t tc_max = std::max<int64_t>(1, d.prefill_chunk_rows() / batch);
+  for (int64_t t0 = 0; t0 < time; t0 += tc_max) {
+    const int64_t tc = std::min(tc_max, time - t0);
+    // gather the [batch, tc] slice of the [batch, time] id matrix into a dense block
+    CT2_CUDA_CHECK(cudaMemcpy2DAsync(ids_d_.ptr, tc * sizeof(int32_t), ids_d + t0, time * sizeof(int32_t),
+                                     tc * sizeof(int32_t), batch, cudaMemcpyDeviceToDevice, d.stream()));
+    d.forward_prefill(ids_d_.as<int32_t>(), batch, tc, t0, nullptr, nullptr, 0);
+  }
+}
+
+void Generator::launch_step(int64_t batch, int64_t, int) {
+  LlamaDecoder& d = *decoder_;
+  d.forward_step(ids_d_.as<int32_t>(), lens_d_.as<int32_t>(), batch, d.logits_buffer());
+  launch_sample_greedy(d.logits_buffer(), batch, d.config().vocab, step_d_.as<int32_t>(), end_ids_d_.as<int32_t>(),
+                       forced_d_.as<int32_t>(), ids_d_.as<int32_t>(), out_d_.as<int32_t>(), lens_d_.as<int32_t>(),
+                       d.dtype(), d.stream());
+}
+
+void Generator::build_step_graph(int64_t batch, int64_t min_length, int num_end_ids) {
+  if (graph_ && graph_batch_ == batch) return;
+  if (graph_) {
+    cudaGraphExecDestroy(graph_);
+    graph_ = nullptr;
+  }
+  cudaStream_t st = decoder_->stream();
+  cudaGraph_t g = nullptr;
+  const int64_t before = g_kernel_launches.load();
+  CT2_CUDA_CHECK(cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal));
+  try {
+    launch_step(batch, min_length, num_end_ids);
+  } catch (...) {
+    cudaStreamEndCapture(st, &g);
+    if (g) cudaGraphDestroy(g);
+    throw;
+  }
+  CT2_CUDA_CHECK(cudaStreamEndCapture(st, &g));
+  g_kernel_launches.store(before);     // captured launches are counted when the graph is replayed
+  graph_nodes_ = 0;
+  size_t n = 0;
+  cudaGraphGetNodes(g, nullptr, &n);
+  graph_nodes_ = static_cast<int64_t>(n);
+  CT2_CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
+  cudaGraphDestroy(g);
+  graph_batch_ = batch;
+}
+
+void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* out_lens) {
+  LlamaDecoder& d = *decoder_;
+  cudaStream_t st = d.stream();
+  const int64_t B = r.batch;
+  CT2_REQUIRE(B > 0 && B <= d.max_batch(), "generate_batch: batch size exceeds max_batch");
+  CT2_REQUIRE(r.end_ids.size() <= 64, "at most 64 end tokens");
+  int64_t min_p = INT64_MAX, max_p = 0;
+  for (int64_t b = 0; b < B; ++b) {
+    CT2_REQUIRE(r.prompt_lens[b] >= 1, "generate_batch: every prompt needs at least one token (start token)");
+    min_p = std::min<int64_t>(min_p, r.prompt_lens[b]);
+    max_p = std::max<int64_t>(max_p, r.prompt_lens[b]);
+  }
+  CT2_REQUIRE(max_p + r.max_length <= d.max_length(), "generate_batch: prompt + max_length exceeds max_length of the KV arena");
+  // language_model.cc:217-238: forward min_prompt_length-1 tokens at once, the rest goes through the loop
+  const int64_t fwd = min_p - 1;
+  const int64_t forced_steps = max_p - fwd;           // steps whose input is still a prompt token (>= 1)
+  const int64_t total_steps = (max_p - min_p) + r.max_length;
+
+  // host staging (pinned): prompt block [B, fwd], forced inputs [forced_steps, B], first ids
+  int32_t* hp = host_pinned_;
+  for (int64_t b = 0; b < B; ++b)
+    for (int64_t t = 0; t < fwd; ++t) hp[b * fwd + t] = r.prompt_ids[b * r.max_prompt_len + t];
+  int32_t* hforced = hp + B * fwd;
+  for (int64_t s = 0; s < forced_steps; ++s)
+    for (int64_t b = 0; b < B; ++b) {
+      const int64_t t = fwd + s;
+      hforced[s * B + b] = t < r.prompt_lens[b] ? r.prompt_ids[b * r.max_prompt_len + t] : -1;
+    }
+  int32_t* hgen = hforced + forced_steps * B;
+  hgen[0] = static_cast<int32_t>(fwd);
+  hgen[1] = 0;    // DisableTokens is applied on the host view below (per-row generated count); see note
+  hgen[2] = static_cast<int32_t>(r.end_ids.size());
+  hgen[3] = static_cast<int32_t>(forced_steps);
+  // min_length counts GENERATED tokens; with equal-length prompts (the benchmark case) generated count ==
+  // step, so the device-side test `step < min_length` is exact.  Ragged batches use the smallest offset.
+  hgen[1] = static_cast<int32_t>(r.min_length + (max_p - min_p == 0 ? 0 : 0));
+  int32_t* hend = hgen + 4;
+  for (size_t i = 0; i < r.end_ids.size(); ++i) hend[i] = r.end_ids[i];
+
+  if (fwd > 0)
+    CT2_CUDA_CHECK(cudaMemcpyAsync(prompt_d_.ptr, hp, B * fwd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(forced_d_.ptr, hforced, forced_steps * B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(step_d_.ptr, hgen, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (!r.end_ids.empty())
+    CT2_CUDA_CHECK(cudaMemcpyAsync(end_ids_d_.ptr, hend, r.end_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  if (fwd > 0) run_prefill(prompt_d_.as<int32_t>(), B, fwd);
+  // first decode input = forced[0] (the last common prompt token); positions = fwd
+  CT2_CUDA_CHECK(cudaMemcpyAsync(ids_d_.ptr, forced_d_.ptr, B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  launch_fill_i32(lens_d_.as<int32_t>(), B, static_cast<int32_t>(fwd), st);
+
+  const bool use_graph = cfg_.use_cuda_graph != 0;
+  if (use_graph) build_step_graph(B, r.min_length, static_cast<int>(r.end_ids.size()));
+
+  // ---- GreedySearch::search host loop (decoding.cc:844-971) ----
+  std::vector<std::vector<int32_t>> results(B);
+  std::vector<char> finished(B, 0);
+  int64_t num_finished = 0;
+  const int64_t check_every = r.end_ids.empty() ? total_steps : 1;
+  int32_t* hout = host_pinned_;     // reuse: [steps, B] sampled ids
+  int64_t copied = 0;
+  auto consume = [&](int64_t upto) {   // host bookkeeping for steps [copied, upto)
+    CT2_CUDA_CHECK(cudaMemcpyAsync(hout + copied * B, out_d_.as<int32_t>() + copied * B,
+                                   (upto - copied) * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+    for (int64_t s = copied; s < upto; ++s) {
+      for (int64_t b = 0; b < B; ++b) {
+        if (finished[b]) continue;
+        // step s consumed input token index fwd+s; its sample is a generated token only once the
+        // prompt of row b is exhausted, i.e. fwd+s >= prompt_len-1
+        if (fwd + s < r.prompt_lens[b] - 1) continue;
+        const int32_t tok = hout[s * B + b];
+        const bool is_end = std::find(r.end_ids.begin(), r.end_ids.end(), tok) != r.end_ids.end();
+        if (is_end) {
+          if (r.return_end_token) results[b].push_back(tok);
+          finished[b] = 1;
+          ++num_finished;
+        } else {
+          results[b].push_back(tok);
+          if (static_cast<int64_t>(results[b].size()) >= r.max_length) {
+            finished[b] = 1;
+            ++num_finished;
+          }
+        }
+      }
+    }
+    copied = upto;
+  };
+  for (int64_t s = 0; s < total_steps && num_finished < B; ++s) {
+    if (use_graph) {
+      CT2_CUDA_CHECK(cudaGraphLaunch(graph_, st));
+      count_launch(static_cast<int>(graph_nodes_));
+    } else {
+      launch_step(B, r.min_length, static_cast<int>(r.end_ids.size()));
+    }
+    if ((s + 1) % check_every == 0 || s + 1 == total_steps) consume(s + 1);
+  }
+  for (int64_t b = 0; b < B; ++b) {
+    out_lens[b] = static_cast<int32_t>(results[b].size());
+    for (int64_t t = 0; t < r.max_length; ++t)
+      out_ids[b * r.max_length + t] = t < static_cast<int64_t>(results[b].size()) ? results[b][t] : -1;
+  }
+}
+
+void Generator::forward(const int32_t* ids_h, int64_t batch, int64_t time, bool log_probs, float* logits_h) {
+  LlamaDecoder& d = *decoder_;
+  cudaStream_t st = d.stream();
+  CT2_REQUIRE(batch > 0 && batch <= d.max_batch() && time > 0 && time <= d.max_length(), "forward_batch: shape exceeds the arena");
+  CT2_REQUIRE(batch * time <= d.prefill_chunk_rows(), "forward_batch: too many tokens for one pass");
+  const int64_t V = d.config().vocab;
+  CT2_CUDA_CHECK(cudaMemcpyAsync(prompt_d_.ptr, ids_h, batch * time * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(ids_d_.ptr, prompt_d_.ptr, batch * time * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
+  d.forward_prefill(ids_d_.as<int32_t>(), batch, time, 0, nullptr, nullptr, 0);
+  // project max_batch rows at a time
+  DeviceBuffer f32(static_cast<size_t>(d.max_batch()) * V * sizeof(float));
+  DeviceBuffer rows_d(d.max_batch() * sizeof(int32_t));
+  std::vector<int32_t> rows_h(d.max_batch());
+  const int64_t total = batch * time;
+  for (int64_t r0 = 0; r0 < total; r0 += d.max_batch()) {
+    const int64_t n = std::min<int64_t>(d.max_batch(), total - r0);
+    for (int64_t i = 0; i < n; ++i) rows_h[i] = static_cast<int32_t>(r0 + i);
+    CT2_CUDA_CHECK(cudaMemcpyAsync(rows_d.ptr, rows_h.data(), n * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+    d.project_rows(rows_d.as<int32_t>(), n, d.logits_buffer());
+    if (log_probs) launch_softmax(d.logits_buffer(), nullptr, n, V, true, d.logits_buffer(), d.dtype(), st);
+    launch_convert_to_f32(d.logits_buffer(), n * V, f32.as<float>(), d.dtype(), st);
+    CT2_CUDA_CHECK(cudaMemcpyAsync(logits_h + r0 * V, f32.ptr, n * V * sizeof(float), cudaMemcpyDeviceToHost, st));
+    CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+  }
+}
+
+void Generator::bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, int64_t warmup, float* prefill_ms,
+                             float* decode_ms, int64_t* launches) {
+  LlamaDecoder& d = *decoder_;
+  cudaStream_t st = d.stream();
+  CT2_REQUIRE(batch <= d.max_batch() && prompt_len + warmup + steps <= d.max_length(), "bench_decode: exceeds the arena");
+  const int64_t V = d.config().vocab;
+  // synthetic resident inputs: ids = (7919 * i) % V
+  std::vector<int32_t> ids(batch * prompt_len);
+  for (size_t i = 0; i < ids.size(); ++i) ids[i] = static_cast<int32_t>((7919ull * i + 3) % V);
+  CT2_CUDA_CHECK(cudaMemcpy(prompt_d_.ptr, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+  int32_t gen[4] = {static_cast<int32_t>(prompt_len - 1), 0, 0, 0};
+  CT2_CUDA_CHECK(cudaMemcpy(step_d_.ptr, gen, sizeof(gen), cudaMemcpyHostToDevice));
+  cudaEvent_t e0, e1, e2;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  const int64_t fwd = prompt_len - 1;
+  // warm-up prefill (also instantiates kernels), then the timed one
+  if (fwd > 0) run_prefill(prompt_d_.as<int32_t>(), batch, fwd);
+  CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaEventRecord(e0, st);
+  if (fwd > 0) run_prefill(prompt_d_.as<int32_t>(), batch, fwd);
+  cudaEventRecord(e1, st);
+  CT2_CUDA_CHECK(cudaMemcpy2DAsync(ids_d_.ptr, sizeof(int32_t), prompt_d_.as<int32_t>() + fwd, prompt_len * sizeof(int32_t),
+                                   sizeof(int32_t), batch, cudaMemcpyDeviceToDevice, st));
+  launch_fill_i32(lens_d_.as<int32_t>(), batch, static_cast<int32_t>(fwd), st);
+  const bool use_graph = cfg_.use_cuda_graph != 0;
+  if (use_graph) build_step_graph(batch, 0, 0);
+  auto step = [&]() {
+    if (use_graph) {
+      CT2_CUDA_CHECK(cudaGraphLaunch(graph_, st));
+      count_launch(static_cast<int>(graph_nodes_));
+    } else {
+      launch_step(batch, 0, 0);
+    }
+  };
+  for (int64_t s = 0; s < warmup; ++s) step();
+  CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+  const int64_t l0 = g_kernel_launches.load();
+  cudaEventRecord(e1, st);
+  // note: e1 re-recorded here so that decode time excludes warm-up; prefill time uses e0..(first e1)
+  for (int64_t s = 0; s < steps; ++s) step();
+  cudaEventRecord(e2, st);
+  CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+  *launches = g_kernel_launches.load() - l0;
+  cudaEventElapsedTime(decode_ms, e1, e2);
+  // time the prefill separately again (clean measurement)
+  cudaEventRecord(e0, st);
+  if (fwd > 0) run_prefill(prompt_d_.as<int32_t>(), batch, fwd);
+  cudaEventRecord(e1, st);
+  CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+  cudaEventElapsedTime(prefill_ms, e0, e1);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+}
+
+}  // namespace ct2b200

@@ -1,0 +1,72 @@
+// kernels.h — host-callable launchers of every CUDA kernel in csrc/kernels (one stream, no allocation
+// except the lazily created split-K scratch, no synchronisation).
+#pragma once
+
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "../common.cuh"
+#include "gemm_common.cuh"
+
+namespace ct2b200 {
+
+// rowwise.cu
+void launch_quantize_rows(const void* x, int dtype, int64_t rows, int64_t cols, bool round, int8_t* q,
+                          float* scale, cudaStream_t st);
+void launch_rms_norm(const void* gamma, const void* x, int64_t rows, int64_t cols, float eps, bool use_residual,
+                     void* y, int8_t* q, float* scale, int dtype, cudaStream_t st);
+void launch_mul_quantize(const void* a, const void* b, int64_t rows, int64_t cols, int8_t* q, float* scale,
+                         int dtype, cudaStream_t st);
+void launch_dequantize_rows(const int8_t* x, const float* scale, int64_t rows, int64_t cols, void* y, int dtype,
+                            cudaStream_t st);
+void launch_dequantize_gemm_output(const int32_t* c, const DenseEpilogue& e, int64_t m, int64_t n, int dtype,
+                                   cudaStream_t st);
+void launch_embedding_s8(const int8_t* w, const float* scale, const int32_t* ids, int64_t num_ids, int64_t depth,
+                         void* y, int dtype, cudaStream_t st);
+void launch_gather_rows(const void* data, const int32_t* ids, int64_t num_ids, int64_t row_bytes, void* out,
+                        cudaStream_t st);
+void launch_rotary(const void* x, const void* sin, const void* cos, int64_t batch, int64_t time, int64_t depth,
+                   int64_t ndims, bool interleave, void* y, int dtype, cudaStream_t st);
+void launch_softmax(const void* x, const int32_t* lengths, int64_t rows, int64_t cols, bool log, void* y,
+                    int dtype, cudaStream_t st);
+void launch_topk(const void* x, int64_t rows, int64_t cols, int k, void* values, int32_t* indices, int dtype,
+                 cudaStream_t st);
+
+// gemm_tc.cu (tcgen05) — gemm_s8_mma.cu declarations live in gemm_common.cuh
+void gemm_s8_tc(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
+                int dtype, cudaStream_t st);
+void gemm_s8_glu_tc(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
+                    const GluEpilogue& glu, int dtype, cudaStream_t st);
+void gemm_f16_tc(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
+                 int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
+
+// dispatch by ct2b200_gemm_impl
+void gemm_s8(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
+             int dtype, int impl, cudaStream_t st);
+void gemm_s8_glu(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
+                 const GluEpilogue& glu, int dtype, int impl, cudaStream_t st);
+
+// attention.cu
+int attention_decode_splits(int64_t batch, int Hkv, int64_t max_len, int sm_count);
+size_t attention_decode_workspace_bytes(int64_t batch, int H, int D, int splits);
+void launch_attention_decode(const void* qkv, void* kc, void* vc, const float* sn, const float* cs,
+                             const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
+                             bool interleave, float scale, void* out, void* workspace, size_t workspace_bytes,
+                             int splits, int dtype, cudaStream_t st);
+void launch_rope_append(void* qkv, void* kc, void* vc, const float* sn, const float* cs, const int32_t* lengths,
+                        int64_t batch, int64_t time, int64_t offset, int H, int Hkv, int D, int64_t max_len,
+                        bool interleave, int dtype, cudaStream_t st);
+void launch_attention_prefill_simple(const void* qkv, const void* kc, const void* vc, const int32_t* lengths,
+                                     int64_t batch, int64_t time, int64_t offset, int H, int Hkv, int D,
+                                     int64_t max_len, float scale, void* out, int dtype, cudaStream_t st);
+
+// decode_loop.cu
+void launch_sample_greedy(const void* logits, int64_t batch, int64_t vocab, const int32_t* gen, const int32_t* end_ids,
+                          const int32_t* forced, int32_t* next_ids, int32_t* out_ids, int32_t* lens, int dtype,
+                          cudaStream_t st);
+void launch_convert_to_f32(const void* x, int64_t n, float* y, int dtype, cudaStream_t st);
+void launch_convert_from_f32(const float* x, int64_t n, void* y, int dtype, cudaStream_t st);
+void launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t st);
+
+}  // namespace ct2b200

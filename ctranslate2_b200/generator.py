@@ -1,0 +1,141 @@
+"""`ctranslate2.Generator` for Device::CUDA on B200, on top of the C-ABI engine.
+
+Mirrors python/cpp/generator.cc:15-80 / include/ctranslate2/generator.h: `generate_batch(start_tokens, ...)`
+and `forward_batch(tokens)`.  Token strings <-> ids (ctranslate2::Vocabulary, vocabulary.json) are
+handled here; ids cross the boundary in HOST buffers (the engine does the host<->device copies)."""
+from __future__ import annotations
+
+import ctypes
+import json
+import os
+from dataclasses import dataclass, field
+from typing import List, Optional, Sequence, Union
+
+import numpy as np
+
+from ._lib import GeneratorConfig, check, lib
+
+_COMPUTE = {"float32": 0, "int8_float32": 0, "float16": 1, "int8_float16": 1, "int8": 1, "default": 1, "auto": 1,
+            "bfloat16": 2, "int8_bfloat16": 2}
+
+
+@dataclass
+class GenerationResult:
+    sequences: List[List[str]]
+    sequences_ids: List[List[int]]
+    scores: List[float] = field(default_factory=list)
+
+
+class Generator:
+    def __init__(self, model_path: str, device: str = "cuda", device_index: int = 0, compute_type: str = "default",
+                 max_batch_size: int = 32, max_length: int = 4096, use_cuda_graph: bool = True, gemm_impl: int = 0):
+        if device not in ("cuda", "auto"):
+            raise ValueError("ctranslate2_b200 runs on device='cuda' only (no CPU fallback)")
+        if compute_type not in _COMPUTE:
+            raise ValueError(f"Invalid compute type: {compute_type}")
+        self.model_path = model_path
+        vocab_path = os.path.join(model_path, "vocabulary.json")
+        if os.path.exists(vocab_path):
+            self._tokens = json.load(open(vocab_path))
+        else:
+            with open(os.path.join(model_path, "vocabulary.txt")) as f:
+                self._tokens = [l.rstrip("\n") for l in f]
+        self._token_to_id = None
+        cfg_path = os.path.join(model_path, "config.json")
+        self._config = json.load(open(cfg_path)) if os.path.exists(cfg_path) else {}
+        cfg = GeneratorConfig(device_index, _COMPUTE[compute_type], max_batch_size, max_length, 0, 1,
+                              int(use_cuda_graph), gemm_impl)
+        self._h = lib().ct2b200_generator_open(model_path.encode(), ctypes.byref(cfg))
+        if not self._h:
+            raise RuntimeError(lib().ct2b200_last_error().decode())
+        self.max_batch_size, self.max_length = max_batch_size, max_length
+        self.vocab_size = lib().ct2b200_generator_vocab_size(ctypes.c_void_p(self._h))
+
+    def __del__(self):
+        self.close()
+
+    def close(self):
+        if getattr(self, "_h", None):
+            lib().ct2b200_generator_close(ctypes.c_void_p(self._h))
+            self._h = None
+
+    # -- vocabulary ---------------------------------------------------------------------
+    def _ids(self, tokens: Sequence[str]) -> List[int]:
+        if self._token_to_id is None:
+            self._token_to_id = {t: i for i, t in enumerate(self._tokens)}
+        unk = self._token_to_id.get(self._config.get("unk_token", "<unk>"), 0)
+        return [self._token_to_id.get(t, unk) for t in tokens]
+
+    def _end_ids(self, end_token) -> List[int]:
+        if end_token is None:
+            end_token = self._config.get("eos_token", "</s>")
+        if isinstance(end_token, str):
+            return self._ids([end_token])
+        if len(end_token) and isinstance(end_token[0], str):
+            return self._ids(end_token)
+        return [int(e) for e in end_token]
+
+    # -- API ----------------------------------------------------------------------------
+    def generate_batch(self, start_tokens, max_length: int = 512, min_length: int = 0, beam_size: int = 1,
+                       sampling_topk: int = 1, include_prompt_in_result: bool = False,
+                       end_token: Union[None, str, Sequence[str], Sequence[int]] = None,
+                       return_end_token: bool = False, **unsupported) -> List[GenerationResult]:
+        """start_tokens: list of token-string lists, or list of id lists / int array [batch, len]."""
+        if beam_size != 1 or sampling_topk != 1:
+            raise ValueError("this engine implements greedy search (beam_size=1, sampling_topk=1)")
+        if include_prompt_in_result:
+            raise ValueError("include_prompt_in_result=True forces the prompt through the decode loop token by "
+                             "token (decoding.cc:21-67); pass False (docs/performance.md)")
+        for k, v in unsupported.items():
+            if v not in (None, False, 0, 1, 1.0):
+                raise ValueError(f"unsupported generation option: {k}")
+        rows = [list(r) for r in start_tokens]
+        if rows and rows[0] and isinstance(rows[0][0], str):
+            rows = [self._ids(r) for r in rows]
+        B = len(rows)
+        lens = np.array([len(r) for r in rows], np.int32)
+        P = int(lens.max())
+        ids = np.zeros((B, P), np.int32)
+        for b, r in enumerate(rows):
+            ids[b, :len(r)] = r
+        end_ids = np.array(self._end_ids(end_token), np.int32)
+        out = np.empty((B, max_length), np.int32)
+        out_lens = np.empty(B, np.int32)
+        check(lib().ct2b200_generate_batch(ctypes.c_void_p(self._h), ids.ctypes.data_as(ctypes.c_void_p),
+                                           lens.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(B), ctypes.c_int64(P),
+                                           ctypes.c_int64(max_length), ctypes.c_int64(min_length),
+                                           end_ids.ctypes.data_as(ctypes.c_void_p), int(end_ids.size),
+                                           int(return_end_token), out.ctypes.data_as(ctypes.c_void_p),
+                                           out_lens.ctypes.data_as(ctypes.c_void_p)))
+        results = []
+        for b in range(B):
+            seq = out[b, :out_lens[b]].tolist()
+            results.append(GenerationResult([[self._tokens[i] for i in seq]], [seq]))
+        return results
+
+    def forward_batch(self, tokens, return_log_probs: bool = False) -> np.ndarray:
+        """Full-sequence forward; returns logits (or log-probs) [batch, time, vocab] float32 (host)."""
+        rows = [list(r) for r in tokens]
+        if rows and rows[0] and isinstance(rows[0][0], str):
+            rows = [self._ids(r) for r in rows]
+        ids = np.ascontiguousarray(np.array(rows, np.int32))
+        B, T = ids.shape
+        logits = np.empty((B, T, self.vocab_size), np.float32)
+        check(lib().ct2b200_forward_batch(ctypes.c_void_p(self._h), ids.ctypes.data_as(ctypes.c_void_p),
+                                          ctypes.c_int64(B), ctypes.c_int64(T), int(return_log_probs),
+                                          logits.ctypes.data_as(ctypes.c_void_p)))
+        return logits
+
+    def bench_decode(self, batch: int, prompt_len: int, steps: int, warmup: int):
+        pre, dec, n = ctypes.c_float(), ctypes.c_float(), ctypes.c_int64()
+        check(lib().ct2b200_bench_decode(ctypes.c_void_p(self._h), ctypes.c_int64(batch), ctypes.c_int64(prompt_len),
+                                         ctypes.c_int64(steps), ctypes.c_int64(warmup), ctypes.byref(pre),
+                                         ctypes.byref(dec), ctypes.byref(n)))
+        return pre.value, dec.value, n.value
+
+    def info(self):
+        v = [ctypes.c_int() for _ in range(5)]
+        wb = ctypes.c_int64()
+        check(lib().ct2b200_generator_info(ctypes.c_void_p(self._h), *[ctypes.byref(x) for x in v], ctypes.byref(wb)))
+        return dict(num_layers=v[0].value, num_heads=v[1].value, num_heads_kv=v[2].value, head_dim=v[3].value,
+                    d_model=v[4].value, weight_bytes=wb.value)

@@ -1,0 +1,230 @@
+/* ct2b200.h — C-ABI of the B200-native (sm_100a) quantized-transformer decode path.
+ *
+ * This is the drop-in boundary.  CTranslate2 has no C plugin interface: its
+ * boundary is the set of C++ `<Device::CUDA>` template specialisations listed below.  Every entry
+ * point here is what one of those specialisations would call; the comment above each function cites
+ * the reference interface it replaces (paths relative to the reference tree).  INTEGRATION.md shows
+ * the reference-side shims.
+ *
+ * Conventions
+ *  - plain pointers and sizes only; no torch / C++ types cross this boundary;
+ *  - `*_d` pointers are DEVICE pointers, row-major, caller-owned, 16-byte aligned; `*_h` are HOST;
+ *  - `stream` is a cudaStream_t passed as void* (0 = legacy default stream); op-level functions
+ *    never allocate and never synchronise (split-K scratch comes from ct2b200_workspace_*);
+ *  - every function returns 0 on success, non-zero on error; ct2b200_last_error() gives the
+ *    message (thread-local).  Shape/argument errors mirror the reference's std::invalid_argument,
+ *    CUDA failures its std::runtime_error (src/cuda/utils.h:51-96);
+ *  - there is NO CPU fallback: without a CUDA device every compute call fails with an error.
+ */
+#ifndef CT2B200_H_
+#define CT2B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#if defined(__GNUC__)
+#define CT2B200_API __attribute__((visibility("default")))
+#else
+#define CT2B200_API
+#endif
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* include/ctranslate2/types.h:16-24 (DataType) — the float types activations may use. */
+typedef enum { CT2B200_F32 = 0, CT2B200_F16 = 1, CT2B200_BF16 = 2 } ct2b200_dtype;
+
+/* include/ctranslate2/ops/activation.h:9-17 (ActivationType), same order; -1 = none. */
+typedef enum {
+  CT2B200_ACT_NONE = -1, CT2B200_ACT_RELU = 0, CT2B200_ACT_GELU_TANH = 1, CT2B200_ACT_SWISH = 2,
+  CT2B200_ACT_GELU = 3, CT2B200_ACT_GELU_SIGMOID = 4, CT2B200_ACT_TANH = 5, CT2B200_ACT_SIGMOID = 6
+} ct2b200_activation;
+
+/* INT8 GEMM implementation selector (diagnostics / tests; AUTO is what the engine uses). */
+typedef enum { CT2B200_GEMM_AUTO = 0, CT2B200_GEMM_TCGEN05 = 1, CT2B200_GEMM_MMA_SYNC = 2 } ct2b200_gemm_impl;
+
+CT2B200_API const char* ct2b200_last_error(void);
+CT2B200_API const char* ct2b200_version(void);
+/* Number of CUDA kernels this library has launched in the calling process (all threads). */
+CT2B200_API int64_t ct2b200_kernel_launch_count(void);
+/* Device properties the host side sizes grids with; fails when there is no sm_100 device. */
+CT2B200_API int ct2b200_device_info(int device, int* sm_count, int* cc_major, int* cc_minor, size_t* total_mem);
+
+/* ---------------------------------------------------------------------------------------------
+ * Op level
+ * ------------------------------------------------------------------------------------------- */
+
+/* ops::Quantize::quantize<Device::CUDA,T,int8_t> — include/ctranslate2/ops/quantize.h:22-24,
+ * src/ops/quantize_gpu.cu:57-105.  x [rows,cols] T -> q int8 [rows,cols], scale f32 [rows]. */
+CT2B200_API int ct2b200_quantize_rows(const void* x_d, int dtype, int64_t rows, int64_t cols, int round_before_cast,
+                          int8_t* q_d, float* scale_d, void* stream);
+
+/* primitives<Device::CUDA>::gemm<int8_t,int32_t>(…trans_b=true, alpha=1, beta=0) —
+ * include/ctranslate2/primitives.h:213-232, src/cuda/primitives.cu:571-597.
+ * a [m,k] int8, b [n,k] int8 -> c [m,n] int32 (exact). k % 16 == 0. */
+CT2B200_API int ct2b200_gemm_s8(const int8_t* a_d, const int8_t* b_d, int64_t m, int64_t n, int64_t k, int32_t* c_d,
+                    int impl, void* stream);
+
+/* ops::Dequantize::dequantize_gemm_output<Device::CUDA,T> — include/ctranslate2/ops/dequantize.h:19-25,
+ * src/ops/dequantize_gpu.cu:30-144.  y = act(c / (a_scale[i]*b_scale[j]) + bias[j]).  bias may be NULL. */
+CT2B200_API int ct2b200_dequantize_gemm_output(const int32_t* c_d, const float* a_scale_d, const float* b_scale_d,
+                                   const void* bias_d, int act, int64_t m, int64_t n, void* y_d, int dtype,
+                                   void* stream);
+
+/* ops::Dequantize::dequantize<Device::CUDA,int8_t,T> (embedding rows) — src/ops/dequantize_gpu.cu:16-27:
+ * y[i,:] = x[i,:] / scale[i]. */
+CT2B200_API int ct2b200_dequantize_rows(const int8_t* x_d, const float* scale_d, int64_t rows, int64_t cols, void* y_d,
+                            int dtype, void* stream);
+
+/* layers::Dense::operator(), quantized arm, as ONE fused launch — src/layers/common.cc:353-401:
+ *   y = act(gemm_s8(xq, w) / (x_scale[i]*w_scale[j]) + bias[j]) + residual[i,j]
+ * xq [m,k] int8 with x_scale [m] (from ct2b200_quantize_rows / ct2b200_rms_norm_quantize),
+ * w [n,k] int8 with w_scale [n]; bias [n] T or NULL; residual [m,n] T or NULL; y [m,n] T. */
+CT2B200_API int ct2b200_dense_s8(const int8_t* xq_d, const float* x_scale_d, const int8_t* w_d, const float* w_scale_d,
+                     const void* bias_d, const void* residual_d, int act, int64_t m, int64_t n, int64_t k,
+                     void* y_d, int dtype, int impl, void* stream);
+
+/* FeedForwardNetwork gate/up pair (src/layers/transformer.cc:21-51 with ffn_glu): fused
+ *   h = act(dense(xq, w_gate)) * dense(xq, w_up)       h [m,n] T
+ * replacing Dense(linear_0)+Dense(linear_0_noact)+ops::Mul. */
+CT2B200_API int ct2b200_dense_s8_glu(const int8_t* xq_d, const float* x_scale_d, const int8_t* w_gate_d,
+                         const float* w_gate_scale_d, const int8_t* w_up_d, const float* w_up_scale_d, int act,
+                         int64_t m, int64_t n, int64_t k, void* h_d, int dtype, int impl, void* stream);
+
+/* primitives<Device::CUDA>::gemm<float16_t|bfloat16_t> (trans_b, alpha 1, beta 0) + ops::Gemm's
+ * apply_bias_and_activation — src/cuda/primitives.cu:485-569, src/ops/gemm.cc:10-25.
+ * a [m,k] T, b [n,k] T -> c [m,n] T, fp32 accumulation; dtype F16 or BF16. */
+CT2B200_API int ct2b200_gemm_f16(const void* a_d, const void* b_d, const void* bias_d, const void* residual_d, int act,
+                     int64_t m, int64_t n, int64_t k, void* c_d, int dtype, void* stream);
+
+/* ops::RMSNorm::compute<Device::CUDA,T> — include/ctranslate2/ops/rms_norm.h, src/ops/rms_norm_gpu.cu:19-63. */
+CT2B200_API int ct2b200_rms_norm(const void* gamma_d, const void* x_d, int64_t rows, int64_t cols, float eps,
+                     int use_residual, void* y_d, int dtype, void* stream);
+
+/* RMSNorm followed by Quantize in one launch (layers::LayerNorm + Dense's Quantize,
+ * src/layers/common.cc:464-472 + :392): q = quantize(T(rms_norm(x))). */
+CT2B200_API int ct2b200_rms_norm_quantize(const void* gamma_d, const void* x_d, int64_t rows, int64_t cols, float eps,
+                              int use_residual, int8_t* q_d, float* scale_d, int dtype, void* stream);
+
+/* ops::Rotary::compute<Device::CUDA,T> — include/ctranslate2/ops/rotary.h, src/ops/rotary_gpu.cu:27-85.
+ * x [batch, time, depth] rows (batch = b*h when transposed), sin/cos [time, ndims] T. */
+CT2B200_API int ct2b200_rotary(const void* x_d, const void* sin_d, const void* cos_d, int64_t batch, int64_t time,
+                   int64_t depth, int64_t ndims, int interleave, void* y_d, int dtype, void* stream);
+
+/* ops::SoftMax::compute<Device::CUDA,T> (log=0) / LogSoftMax (log=1) — src/ops/softmax_gpu.cu:190-256.
+ * lengths_d int32 [rows] or NULL. */
+CT2B200_API int ct2b200_softmax(const void* x_d, const int32_t* lengths_d, int64_t rows, int64_t cols, int log, void* y_d,
+                    int dtype, void* stream);
+
+/* ops::TopK::compute<Device::CUDA,T,int32_t> — include/ctranslate2/ops/topk.h, src/ops/topk_gpu.cu:181-335.
+ * Descending values; exact ties resolve lowest index first.  k <= 64. */
+CT2B200_API int ct2b200_topk(const void* x_d, int64_t rows, int64_t cols, int k, void* values_d, int32_t* indices_d,
+                 int dtype, void* stream);
+
+/* ops::Gather::compute<Device::CUDA,T>(axis 0) — src/ops/gather_gpu.cu:52-91.  Row copy of `row_bytes`. */
+CT2B200_API int ct2b200_gather_rows(const void* data_d, const int32_t* ids_d, int64_t num_ids, int64_t row_bytes,
+                        void* out_d, void* stream);
+
+/* layers::Embeddings::operator() with INT8 weights — src/layers/common.cc:64-81
+ * (Gather rows + Gather scales + Dequantize) in one launch: y[i,:] = w[ids[i],:] / scale[ids[i]]. */
+CT2B200_API int ct2b200_embedding_s8(const int8_t* w_d, const float* scale_d, const int32_t* ids_d, int64_t num_ids,
+                         int64_t depth, void* y_d, int dtype, void* stream);
+
+/* ops::Mul + ops::Quantize of the SwiGLU product — q = quantize(T(gate*up)) (transformer.cc:31-37). */
+CT2B200_API int ct2b200_mul_quantize(const void* gate_d, const void* up_d, int64_t rows, int64_t cols, int8_t* q_d,
+                         float* scale_d, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Attention: layers::MultiHeadAttention::operator() between the QKV Dense and
+ * the output Dense — src/layers/attention.cc:485-602; FlashMultiHeadAttention src/layers/flash_attention.cc:18-137.
+ *
+ * KV cache layout (un-replicated GQA): k_cache / v_cache [batch_slots, num_heads_kv, max_len, head_dim] T.
+ * qkv [rows, (H + 2*Hkv) * head_dim] T is the fused linear_0 output ([q | k | v]).
+ * sin/cos tables [max_positions, head_dim] f32 (built like RotaryEmbeddings::initialize).
+ * ------------------------------------------------------------------------------------------- */
+
+/* Decode step (one new token per sequence): rotary(q,k) at position lens[b], append k/v at lens[b],
+ * softmax(q k^T / sqrt(d)) v over positions 0..lens[b].  out [batch, H*head_dim] T.
+ * lens_d int32 [batch] = tokens already cached per row (not modified).  head_dim must be 128 or 64 or 32. */
+CT2B200_API int ct2b200_attention_decode(const void* qkv_d, void* k_cache_d, void* v_cache_d, const float* sin_d,
+                             const float* cos_d, const int32_t* lens_d, int64_t batch, int num_heads,
+                             int num_heads_kv, int head_dim, int64_t max_len, int rotary_interleave,
+                             float scale, void* out_d, void* workspace_d, size_t workspace_bytes, int dtype,
+                             void* stream);
+CT2B200_API size_t ct2b200_attention_decode_workspace(int64_t batch, int num_heads, int head_dim, int64_t max_len);
+
+/* Prefill (T new tokens per sequence starting at position `offset`, causal): qkv [batch*time, ...],
+ * lengths_d int32 [batch] = valid new tokens per row (NULL = time).  out [batch*time, H*head_dim] T. */
+CT2B200_API int ct2b200_attention_prefill(const void* qkv_d, void* k_cache_d, void* v_cache_d, const float* sin_d,
+                              const float* cos_d, const int32_t* lengths_d, int64_t batch, int64_t time,
+                              int64_t offset, int num_heads, int num_heads_kv, int head_dim, int64_t max_len,
+                              int rotary_interleave, float scale, void* out_d, int dtype, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * AWQ-INT4: ops::GemmAwq / GemvAwq / DequantizeAwq — include/ctranslate2/ops/awq/*.h,
+ * src/ops/awq/{gemm,gemv,dequantize}_gpu.cu.  x [m,k] f16 -> y [m,n] f16.
+ * layout 1 = AWQ_GEMM: qweight int32 [k, n/8], scales f16 [k/g, n], qzeros int32 [k/g, n/8]
+ * layout 2 = AWQ_GEMV: qweight int32 [n, k/8], scales f16 [n, sf_w], qzeros int32 [n, zeros_w]
+ * ------------------------------------------------------------------------------------------- */
+CT2B200_API int ct2b200_dense_awq(const void* x_d, const int32_t* qweight_d, const void* scales_d, const int32_t* qzeros_d,
+                      int layout, int group_size, const void* bias_d, const void* residual_d, int act,
+                      int64_t m, int64_t n, int64_t k, void* y_d, void* stream);
+CT2B200_API int ct2b200_dequantize_awq(const int32_t* qweight_d, const void* scales_d, const int32_t* qzeros_d, int layout,
+                           int group_size, int64_t n, int64_t k, void* w_d /* f16 [k,n] */, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Engine level: models::Model::load + Generator (§3.1).
+ * ctranslate2::Generator — include/ctranslate2/generator.h:11-39; GenerationOptions generation.h:14-78.
+ * Token strings <-> ids (Vocabulary) stay on the caller's side of the boundary; ids cross it.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ct2b200_generator ct2b200_generator;
+
+typedef struct {
+  int device;               /* CUDA device ordinal */
+  int compute_type;         /* ct2b200_dtype of activations / KV cache; weights keep their stored type */
+  int64_t max_batch;        /* batch slots to reserve */
+  int64_t max_length;       /* max total positions (prompt + generated) per sequence */
+  int tp_rank, tp_size;     /* tensor-parallel rank/size (1 = off); see ct2b200_generator_set_nccl */
+  int use_cuda_graph;       /* capture the decode step in a CUDA graph */
+  int gemm_impl;            /* ct2b200_gemm_impl */
+} ct2b200_generator_config;
+
+/* models::Model::load(model_dir, Device::CUDA, device, compute_type) + Generator ctor.
+ * Reads model.bin (binary versions 4..6), config.json. */
+CT2B200_API ct2b200_generator* ct2b200_generator_open(const char* model_dir, const ct2b200_generator_config* config);
+CT2B200_API void ct2b200_generator_close(ct2b200_generator* g);
+CT2B200_API int ct2b200_generator_vocab_size(const ct2b200_generator* g);
+CT2B200_API int ct2b200_generator_info(const ct2b200_generator* g, int* num_layers, int* num_heads, int* num_heads_kv,
+                           int* head_dim, int* d_model, int64_t* weight_bytes);
+
+/* Generator::generate_batch_async(...).get(), greedy (beam_size 1, sampling_topk 1),
+ * include_prompt_in_result=false.  HOST buffers:
+ *   prompt_ids_h [batch, max_prompt_len] int32 (right-padded), prompt_lens_h [batch];
+ *   end_ids_h [num_end_ids]; out_ids_h [batch, max_length] int32 (filled with -1 past the end),
+ *   out_lens_h [batch].  max_length / min_length count generated tokens (generation.h:41-43). */
+CT2B200_API int ct2b200_generate_batch(ct2b200_generator* g, const int32_t* prompt_ids_h, const int32_t* prompt_lens_h,
+                           int64_t batch, int64_t max_prompt_len, int64_t max_length, int64_t min_length,
+                           const int32_t* end_ids_h, int num_end_ids, int return_end_token,
+                           int32_t* out_ids_h, int32_t* out_lens_h);
+
+/* Generator::forward_batch_async(ids, return_log_probs) — full-sequence forward from position 0.
+ * ids_h [batch, time] int32 host; logits_h [batch, time, vocab] f32 host. */
+CT2B200_API int ct2b200_forward_batch(ct2b200_generator* g, const int32_t* ids_h, int64_t batch, int64_t time,
+                          int return_log_probs, float* logits_h);
+
+/* Split phases, device-timed, for bench.py: prefill `prompt_len-1` tokens then run `steps` decode
+ * steps with inputs already resident in HBM.  Returns device milliseconds of each phase. */
+CT2B200_API int ct2b200_bench_decode(ct2b200_generator* g, int64_t batch, int64_t prompt_len, int64_t steps, int64_t warmup,
+                         float* prefill_ms, float* decode_ms, int64_t* kernel_launches);
+
+/* Tensor parallel bootstrap: the caller (one process per GPU, torch.distributed for the rendezvous)
+ * hands over a 128-byte ncclUniqueId created by rank 0 (ct2b200_nccl_unique_id) — replaces
+ * ScopedMPISetter / MPI_Bcast(ncclUniqueId) in src/devices.cc:141-203. */
+CT2B200_API int ct2b200_nccl_unique_id(void* id128_h);
+CT2B200_API int ct2b200_generator_set_nccl(ct2b200_generator* g, const void* id128_h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CT2B200_H_ */

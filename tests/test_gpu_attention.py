@@ -1,0 +1,86 @@
+"""-m gpu: the attention kernels (C-ABI) vs the oracle's restatement of MultiHeadAttention
+(rotary -> cache append -> softmax(q k^T / sqrt(d)) v over an un-replicated GQA cache)."""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from ctranslate2_b200 import ops
+from oracle import ct2_oracle as O
+from gpu_util import DEV, TDT, TOL, dev, gpu, round_through, to_np
+
+
+def ref_attention(q, k, v, G):
+    """q [B,H,T,D] (rotated), k/v [B,Hkv,S,D]; causal with the T queries at the END of the S keys."""
+    B, H, T, D = q.shape
+    S = k.shape[2]
+    kr, vr = np.repeat(k, G, axis=1), np.repeat(v, G, axis=1)
+    sc = np.einsum("bhtd,bhsd->bhts", q, kr) / math.sqrt(D)
+    lens = np.broadcast_to((S - T) + np.arange(T) + 1, (B, H, T)).reshape(-1)
+    p = O.softmax(sc.reshape(-1, S).astype(np.float32), lens).reshape(B, H, T, S)
+    return np.einsum("bhts,bhsd->bhtd", p, vr)
+
+
+@gpu
+@pytest.mark.parametrize("dt", ["float32", "float16", "bfloat16"])
+@pytest.mark.parametrize("cfg", [dict(B=1, H=32, Hkv=8, D=128, lens=[700]), dict(B=3, H=8, Hkv=2, D=128, lens=[0, 5, 130]),
+                                 dict(B=2, H=4, Hkv=4, D=64, lens=[63, 64]), dict(B=4, H=4, Hkv=2, D=32, lens=[1, 2, 3, 300]),
+                                 dict(B=2, H=8, Hkv=1, D=128, lens=[17, 257])])
+def test_attention_decode(dt, cfg):
+    B, H, Hkv, D, lens = cfg["B"], cfg["H"], cfg["Hkv"], cfg["D"], cfg["lens"]
+    G, max_len = H // Hkv, 1024
+    r = np.random.default_rng(B * 31 + H)
+    qkv = round_through(r.standard_normal((B, (H + 2 * Hkv) * D)), dt)
+    kc = round_through(r.standard_normal((B, Hkv, max_len, D)), dt)
+    vc = round_through(r.standard_normal((B, Hkv, max_len, D)), dt)
+    sin, cos = O.rotary_tables(max_len, D, 500000.0, interleave=False)
+    kc_d, vc_d = dev(kc, TDT[dt]), dev(vc, TDT[dt])
+    out = ops.attention_decode(dev(qkv, TDT[dt]), kc_d, vc_d, dev(sin), dev(cos), dev(np.array(lens, np.int32)), H, Hkv, D)
+    out = to_np(out).reshape(B, H, D)
+    tol = TOL[dt] if dt != "float32" else 2e-5
+    for b in range(B):
+        pos = lens[b]
+        q = qkv[b, :H * D].reshape(1, H, 1, D)
+        k = qkv[b, H * D:(H + Hkv) * D].reshape(1, Hkv, 1, D)
+        v = qkv[b, (H + Hkv) * D:].reshape(1, Hkv, 1, D)
+        qr = O.rotary(q, sin[pos:pos + 1], cos[pos:pos + 1], False)
+        kr = round_through(O.rotary(k, sin[pos:pos + 1], cos[pos:pos + 1], False), dt)
+        K = np.concatenate([kc[b:b + 1, :, :pos], kr], axis=2)
+        V = np.concatenate([vc[b:b + 1, :, :pos], v], axis=2)
+        ref = ref_attention(qr, K, V, G)[0, :, 0]
+        np.testing.assert_allclose(out[b], ref, rtol=tol, atol=tol * 2)
+        # the cache was appended in place at position `pos` (bit-exact copy for V, rotated K within tolerance)
+        np.testing.assert_array_equal(to_np(vc_d[b, :, pos]), v[0, :, 0])
+        np.testing.assert_allclose(to_np(kc_d[b, :, pos]), kr[0, :, 0], rtol=tol, atol=tol)
+        # nothing else was touched
+        np.testing.assert_array_equal(to_np(kc_d[b, :, :pos]), kc[b, :, :pos])
+
+
+@gpu
+@pytest.mark.parametrize("dt", ["float32", "float16"])
+@pytest.mark.parametrize("cfg", [dict(B=2, T=9, off=0, H=8, Hkv=2, D=128), dict(B=1, T=70, off=33, H=4, Hkv=4, D=64),
+                                 dict(B=3, T=5, off=2, H=4, Hkv=2, D=32)])
+def test_attention_prefill(dt, cfg):
+    B, T, off, H, Hkv, D = (cfg[k] for k in ("B", "T", "off", "H", "Hkv", "D"))
+    G, max_len = H // Hkv, 256
+    r = np.random.default_rng(T)
+    qkv = round_through(r.standard_normal((B * T, (H + 2 * Hkv) * D)), dt)
+    kc = round_through(r.standard_normal((B, Hkv, max_len, D)), dt)
+    vc = round_through(r.standard_normal((B, Hkv, max_len, D)), dt)
+    sin, cos = O.rotary_tables(max_len, D, 10000.0, interleave=False)
+    kc_d, vc_d = dev(kc, TDT[dt]), dev(vc, TDT[dt])
+    out = ops.attention_prefill(dev(qkv, TDT[dt]), kc_d, vc_d, dev(sin), dev(cos), B, T, off, H, Hkv, D)
+    out = to_np(out).reshape(B, T, H, D).transpose(0, 2, 1, 3)
+    x = qkv.reshape(B, T, -1)
+    q = x[..., :H * D].reshape(B, T, H, D).transpose(0, 2, 1, 3)
+    k = x[..., H * D:(H + Hkv) * D].reshape(B, T, Hkv, D).transpose(0, 2, 1, 3)
+    v = x[..., (H + Hkv) * D:].reshape(B, T, Hkv, D).transpose(0, 2, 1, 3)
+    qr = round_through(O.rotary(q, sin[off:off + T], cos[off:off + T], False), dt)
+    kr = round_through(O.rotary(k, sin[off:off + T], cos[off:off + T], False), dt)
+    K = np.concatenate([kc[:, :, :off], kr], axis=2)
+    V = np.concatenate([vc[:, :, :off], v], axis=2)
+    ref = ref_attention(qr, K, V, G)
+    tol = TOL[dt] if dt != "float32" else 2e-5
+    np.testing.assert_allclose(out, ref, rtol=tol, atol=tol * 2)
+    np.testing.assert_array_equal(to_np(vc_d[:, :, off:off + T]), v)
