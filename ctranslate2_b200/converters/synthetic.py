@@ -90,7 +90,7 @@ class ModelWriter:
         dtype = dtype or str(a.dtype)
         if dtype == "bfloat16" and a.dtype != np.uint16:
             a = to_bf16_bits(a.astype(np.float32))
-        elif dtype != "bfloat16":
+        elif dtype != "bfloat16" and str(a.dtype) != dtype:
             a = a.astype(dtype)
         if a.ndim > 0:
             a = np.ascontiguousarray(a)   # (ascontiguousarray would promote a 0-d scalar to 1-d)
@@ -102,7 +102,7 @@ class ModelWriter:
             self.f.write(struct.pack("I", d))
         self.f.write(struct.pack("B", _TYPE_IDS[dtype]))
         self.f.write(struct.pack("I", a.nbytes))
-        self.f.write(a.tobytes())
+        self.f.write(memoryview(a).cast("B") if a.ndim > 0 else a.tobytes())
         self.count += 1
 
     def alias(self, alias: str, target: str):
@@ -139,13 +139,29 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
     d, D = cfg.d_model, cfg.head_dim
     w = ModelWriter(model_dir)
 
+    base = rng.integers(-127, 128, size=1 << 24, dtype=np.int8) if fast_int8 else None
+    state = {"off": 0}
+
+    def fast_block(count):
+        # numpy's generators run at ~0.1 GB/s on the bench hosts; the 8 GB of int8 weights are instead tiled
+        # from a 16 MiB random block at a different (odd) offset per matrix — memcpy speed, still no two rows alike
+        out = np.empty(count, np.int8)
+        pos = 0
+        while pos < count:
+            off = state["off"]
+            take = min(count - pos, base.size - off)
+            out[pos:pos + take] = base[off:off + take]
+            pos += take
+            state["off"] = (off + take + 12289) % base.size
+        return out
+
     def linear(prefix, n, k):
         if is_int8 and fast_int8:
-            # rows of N(0, std) quantized with scale 127/amax, amax ~ 4.2 sigma  =>  q ~ N(0, 30)
-            q = np.clip(np.rint(rng.standard_normal((n, k), dtype=np.float32) * 30.0), -127, 127).astype(np.int8)
+            # uniform int8 in [-127,127] (std 73.3) with scale = 73.3/std: the dequantized weights have
+            # standard deviation init_std; drawn directly as bytes (about 1 GB/s on one host core)
+            q = fast_block(n * k).reshape(n, k)
             q[:, 0] = 127    # each row attains its amax, as a real quantized row does
-            scale = np.full((n,), 127.0 / (4.2 * init_std), np.float32) * \
-                rng.uniform(0.9, 1.1, size=n).astype(np.float32)
+            scale = np.full((n,), 73.3 / init_std, np.float32) * rng.uniform(0.9, 1.1, size=n).astype(np.float32)
             w.add(prefix + "/weight", q, "int8")
             w.add(prefix + "/weight_scale", scale, "float32")
             return

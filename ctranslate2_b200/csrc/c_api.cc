@@ -223,8 +223,8 @@ CT2B200_API int ct2b200_attention_prefill(const void* qkv, void* k_cache, void* 
     CT2_REQUIRE(offset + time <= max_len, "attention_prefill: offset + time exceeds max_len");
     launch_rope_append(const_cast<void*>(qkv), k_cache, v_cache, sin, cos, lengths, batch, time, offset, num_heads,
                        num_heads_kv, head_dim, max_len, rotary_interleave != 0, dtype, S(stream));
-    launch_attention_prefill_simple(qkv, k_cache, v_cache, lengths, batch, time, offset, num_heads, num_heads_kv,
-                                    head_dim, max_len, scale, out, dtype, S(stream));
+    launch_attention_prefill(qkv, k_cache, v_cache, lengths, batch, time, offset, num_heads, num_heads_kv, head_dim,
+                             max_len, scale, out, dtype, S(stream));
   });
 }
 

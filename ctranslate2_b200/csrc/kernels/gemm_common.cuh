@@ -38,7 +38,7 @@ struct SplitKWorkspace {
   size_t num_counters = 0;
   int sm_count = 148;
 
-  static constexpr size_t kAccumElems = size_t(4) << 20;   // 16 MiB of int32
+  static constexpr size_t kAccumElems = size_t(16) << 20;  // 64 MiB of int32
   static constexpr size_t kCounters = 1 << 16;
 
   static SplitKWorkspace& get(cudaStream_t st) {

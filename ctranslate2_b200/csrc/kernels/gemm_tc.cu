@@ -16,6 +16,8 @@
 #include <cuda.h>
 #include <cudaTypedefs.h>
 
+#include <algorithm>
+
 #include "../common.cuh"
 #include "gemm_common.cuh"
 
@@ -159,7 +161,10 @@ struct TcParams {
   int64_t rows_a;      // rows of the M-side operand (n when swapped, m otherwise)
   int64_t rows_b;      // rows of the N-side operand
   int64_t k;           // elements
-  int splits;
+  int tiles_a;         // M-side tiles of 128 rows
+  int tiles_b;         // N-side tiles of BN rows
+  int kb_total;        // K blocks (128 bytes of K each) per output tile
+  int whole_tiles;     // 1 = CTA ranges are aligned to whole tiles (no scratch needed)
   DenseEpilogue dense;
   GluEpilogue glu;
   FloatEpilogue fl;
@@ -176,45 +181,65 @@ struct TcSmem {
   static constexpr size_t kBytes = static_cast<size_t>(kStages) * kStage + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+// index of the CTA whose unit range [c*U/P, (c+1)*U/P) contains unit u
+__device__ __forceinline__ int cta_of_unit(int64_t u, int64_t U, int64_t P) {
+  return static_cast<int>(((u + 1) * P + U - 1) / U - 1);
+}
+
+// Persistent "stream-K" GEMM: the work is the list of (output tile, K block) units, tile-major; CTA c of P
+// owns the contiguous unit range [c*U/P, (c+1)*U/P), so every SM streams the same number of bytes and the TMA
+// ring never drains between tiles.  A tile whose K range is covered by one CTA is finished by that CTA
+// straight from TMEM; a tile shared by several CTAs is reduced through the zeroed scratch (integer
+// red.global.add => bit-exact, order independent) and finished by the last arriver (ticket).
+// Accumulators are double-buffered in TMEM so the epilogue of one segment overlaps the MMAs of the next.
+//
 // T = output dtype, KIND = 0 s8 / 1 f16 / 2 bf16, BN = UMMA N, NB = weight matrices (2 = GLU),
-// kSwap = weights on the M side.
+// kSwap = weights on the M side (decode).
 template <typename T, int KIND, int BN, int NB, bool kSwap>
 __global__ void __launch_bounds__(kTcThreads, 1)
     gemm_tc_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                    const __grid_constant__ CUtensorMap tm_w2, const TcParams p) {
   using S = TcSmem<BN, NB, kSwap>;
-  using Acc = typename KindTraits<KIND>::Acc;
   constexpr int kElem = KindTraits<KIND>::kElem;
   constexpr int BK = kSwizzleBytes / kElem;            // elements of K per stage
   constexpr int kUmmaK = 32 / kElem;                   // elements of K per MMA
   constexpr int kStages = S::kStages;
-  constexpr uint32_t kTmemCols = (BN * NB) <= 32 ? 32 : (BN * NB) <= 64 ? 64 : (BN * NB) <= 128 ? 128 : (BN * NB) <= 256 ? 256 : 512;
-  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256 && BN * NB <= 512, "invalid UMMA N");
+  constexpr int kAccCols = BN * NB;                    // TMEM columns per accumulator buffer
+  constexpr uint32_t kTmemCols = (2 * kAccCols) <= 32 ? 32 : (2 * kAccCols) <= 64 ? 64 : (2 * kAccCols) <= 128 ? 128
+                               : (2 * kAccCols) <= 256 ? 256 : 512;
+  static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256 && 2 * kAccCols <= 512, "invalid UMMA N");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStage);
   uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tmem_full_bar = empty_bar + kStages;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full_bar + 1);
-  __shared__ bool s_last;
+  uint64_t* tmem_full_bar = empty_bar + kStages;       // [2]
+  uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_empty_bar + 2);
+  __shared__ int s_last;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t a0 = static_cast<int64_t>(blockIdx.x) * kTileM;     // M-side row offset
-  const int64_t b0 = static_cast<int64_t>(blockIdx.y) * BN;         // N-side row offset
-
-  const int kb_total = static_cast<int>((p.k + BK - 1) / BK);
-  const int kb_per = (kb_total + p.splits - 1) / p.splits;
-  const int kb_begin = blockIdx.z * kb_per;
-  const int kb_end = min(kb_total, kb_begin + kb_per);
-  const int nkb = max(0, kb_end - kb_begin);
+  const int64_t KB = p.kb_total;
+  const int64_t U = static_cast<int64_t>(p.tiles_a) * p.tiles_b * KB;
+  const int64_t P = gridDim.x;
+  const int64_t T_all = static_cast<int64_t>(p.tiles_a) * p.tiles_b;
+  const int64_t u_begin = p.whole_tiles ? (blockIdx.x * T_all / P) * KB : blockIdx.x * U / P;
+  const int64_t u_end = p.whole_tiles ? ((blockIdx.x + 1) * T_all / P) * KB : (blockIdx.x + 1) * U / P;
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
-    mbar_init(tmem_full_bar, 1);
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(tmem_full_bar + b, 1);
+      mbar_init(tmem_empty_bar + b, 4);               // one arrive per epilogue warp
+    }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -224,7 +249,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  // M-side / N-side tensor maps
   const CUtensorMap* map_a0 = kSwap ? &tm_w : &tm_x;
   const CUtensorMap* map_a1 = &tm_w2;                   // only when kSwap && NB == 2
   const CUtensorMap* map_b0 = kSwap ? &tm_x : &tm_w;
@@ -235,129 +259,163 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   if (warp == 0) {
     // ===== TMA producer =====
     if (lane == 0) {
-      for (int it = 0; it < nkb; ++it) {
+      int it = 0;
+      int tile = static_cast<int>(u_begin / KB);
+      int kb = static_cast<int>(u_begin - tile * KB);
+      int a0 = (tile % p.tiles_a) * kTileM, b0 = (tile / p.tiles_a) * BN;
+      for (int64_t u = u_begin; u < u_end; ++u, ++it, ++kb) {
+        if (kb == KB) {
+          kb = 0;
+          ++tile;
+          a0 = (tile % p.tiles_a) * kTileM;
+          b0 = (tile / p.tiles_a) * BN;
+        }
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
         mbar_wait(empty_bar + s, ph ^ 1);
         mbar_expect_tx(full_bar + s, S::kStage);
         uint8_t* sa = smem + s * S::kStage;
         uint8_t* sb = sa + S::kA;
-        const int kc = (kb_begin + it) * BK;
-        tma_load_2d(sa, map_a0, full_bar + s, kc, static_cast<int>(a0), pol_a);
-        if (kSwap && NB == 2) tma_load_2d(sa + kTileM * kSwizzleBytes, map_a1, full_bar + s, kc, static_cast<int>(a0), pol_a);
-        tma_load_2d(sb, map_b0, full_bar + s, kc, static_cast<int>(b0), pol_b);
-        if (!kSwap && NB == 2) tma_load_2d(sb + BN * kSwizzleBytes, map_b1, full_bar + s, kc, static_cast<int>(b0), pol_b);
+        const int kc = kb * BK;
+        tma_load_2d(sa, map_a0, full_bar + s, kc, a0, pol_a);
+        if (kSwap && NB == 2) tma_load_2d(sa + kTileM * kSwizzleBytes, map_a1, full_bar + s, kc, a0, pol_a);
+        tma_load_2d(sb, map_b0, full_bar + s, kc, b0, pol_b);
+        if (!kSwap && NB == 2) tma_load_2d(sb + BN * kSwizzleBytes, map_b1, full_bar + s, kc, b0, pol_b);
       }
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<KIND>(BN);
-      for (int it = 0; it < nkb; ++it) {
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(full_bar + s, ph);
+      int it = 0, seg = 0;
+      for (int64_t u = u_begin; u < u_end; ++seg) {
+        const int64_t tile = u / KB;
+        const int kb0 = static_cast<int>(u - tile * KB);
+        const int kb1 = static_cast<int>(min(KB, static_cast<int64_t>(kb0) + (u_end - u)));
+        const int buf = seg & 1;
+        mbar_wait(tmem_empty_bar + buf, ((seg >> 1) & 1) ^ 1);       // epilogue drained this buffer
         tc_fence_after();
-        const uint32_t sa = smem_u32(smem + s * S::kStage);
-        const uint32_t sb = sa + S::kA;
+        const uint32_t acc = tmem_base + buf * kAccCols;
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % kStages;
+          const uint32_t ph = (it / kStages) & 1;
+          mbar_wait(full_bar + s, ph);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + s * S::kStage);
+          const uint32_t sb = sa + S::kA;
 #pragma unroll
-        for (int w = 0; w < NB; ++w) {
-          const uint64_t da = make_smem_desc(sa + (kSwap ? w * kTileM * kSwizzleBytes : 0));
-          const uint64_t db = make_smem_desc(sb + (kSwap ? 0 : w * BN * kSwizzleBytes));
+          for (int w = 0; w < NB; ++w) {
+            const uint64_t da = make_smem_desc(sa + (kSwap ? w * kTileM * kSwizzleBytes : 0));
+            const uint64_t db = make_smem_desc(sb + (kSwap ? 0 : w * BN * kSwizzleBytes));
 #pragma unroll
-          for (int k = 0; k < BK / kUmmaK; ++k) {
-            // advancing K inside the 128B swizzle atom = +32 bytes on the start address (>>4 => +2)
-            umma<KIND>(tmem_base + w * BN, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < BK / kUmmaK; ++k) {
+              // advancing K inside the 128B swizzle atom = +32 bytes on the start address (>>4 => +2)
+              umma<KIND>(acc + w * BN, da + 2 * k, db + 2 * k, idesc, (kb > kb0 || k > 0) ? 1u : 0u);
+            }
           }
+          umma_commit(empty_bar + s);               // frees the smem stage when these MMAs retire
         }
-        umma_commit(empty_bar + s);                 // frees the smem stage when these MMAs retire
+        umma_commit(tmem_full_bar + buf);           // this segment's accumulators are complete
+        u += kb1 - kb0;
       }
-      umma_commit(tmem_full_bar);                   // accumulators complete
     }
   } else {
     // ===== epilogue warps =====
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    mbar_wait(tmem_full_bar, 0);
-    tc_fence_after();
-    const int64_t arow = a0 + q * 32 + lane;        // M-side row owned by this thread
-    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
-    const bool direct = p.splits == 1;
+    const int et = threadIdx.x - 64;                // 0..127 among the epilogue threads
     const int64_t ldw = kSwap ? p.rows_a : p.rows_b;                 // row pitch of the [m, n] scratch plane
     const int64_t plane = p.rows_a * p.rows_b;
+    int seg = 0;
+    for (int64_t u = u_begin; u < u_end; ++seg) {
+      const int64_t tile = u / KB;
+      const int kb0 = static_cast<int>(u - tile * KB);
+      const int kb1 = static_cast<int>(min(KB, static_cast<int64_t>(kb0) + (u_end - u)));
+      u += kb1 - kb0;
+      const int64_t a0 = (tile % p.tiles_a) * kTileM;
+      const int64_t b0 = (tile / p.tiles_a) * BN;
+      const int buf = seg & 1;
+      const bool direct = kb0 == 0 && kb1 == KB;
+      mbar_wait(tmem_full_bar + buf, (seg >> 1) & 1);
+      tc_fence_after();
+      const int64_t arow = a0 + q * 32 + lane;      // M-side row owned by this thread
+      const uint32_t taddr = tmem_base + buf * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
 #pragma unroll 1
-    for (int c0 = 0; c0 < BN; c0 += 32) {
-      uint32_t r[NB][32];
+      for (int c0 = 0; c0 < BN; c0 += 32) {
+        uint32_t r[NB][32];
 #pragma unroll
-      for (int w = 0; w < NB; ++w) {
-        if (nkb > 0) {
+        for (int w = 0; w < NB; ++w) {
           if constexpr (BN % 32 == 0) tmem_ld32(taddr + w * BN + c0, r[w]);
           else tmem_ld16(taddr + w * BN + c0, r[w]);
-        } else {
-#pragma unroll
-          for (int j = 0; j < 32; ++j) r[w][j] = 0;
         }
-      }
-      constexpr int kCols = (BN % 32 == 0) ? 32 : 16;
+        if (c0 + 32 >= BN) {                        // last chunk is in registers: hand the buffer back
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(tmem_empty_bar + buf);
+        }
+        constexpr int kCols = (BN % 32 == 0) ? 32 : 16;
 #pragma unroll
-      for (int j = 0; j < kCols; ++j) {
-        const int64_t brow = b0 + c0 + j;           // N-side row
-        if (arow >= p.rows_a || brow >= p.rows_b) continue;
-        const int64_t i = kSwap ? brow : arow;      // output row (m)
-        const int64_t jn = kSwap ? arow : brow;     // output column (n)
-        if (direct) {
-          if constexpr (KIND != 0) float_epilogue_store<T>(p.fl, __uint_as_float(r[0][j]), i, jn);
-          else if constexpr (NB == 2) glu_epilogue_store<T>(p.glu, static_cast<int32_t>(r[0][j]), static_cast<int32_t>(r[1][j]), i, jn);
-          else dense_epilogue_store<T>(p.dense, static_cast<int32_t>(r[0][j]), i, jn);
-        } else {
-          if constexpr (KIND == 0) {
-            atomicAdd(p.ws + i * ldw + jn, static_cast<int32_t>(r[0][j]));
-            if constexpr (NB == 2) atomicAdd(p.ws + plane + i * ldw + jn, static_cast<int32_t>(r[1][j]));
+        for (int j = 0; j < kCols; ++j) {
+          const int64_t brow = b0 + c0 + j;         // N-side row
+          if (arow >= p.rows_a || brow >= p.rows_b) continue;
+          const int64_t i = kSwap ? brow : arow;    // output row (m)
+          const int64_t jn = kSwap ? arow : brow;   // output column (n)
+          if (direct) {
+            if constexpr (KIND != 0) float_epilogue_store<T>(p.fl, __uint_as_float(r[0][j]), i, jn);
+            else if constexpr (NB == 2) glu_epilogue_store<T>(p.glu, static_cast<int32_t>(r[0][j]), static_cast<int32_t>(r[1][j]), i, jn);
+            else dense_epilogue_store<T>(p.dense, static_cast<int32_t>(r[0][j]), i, jn);
           } else {
-            atomicAdd(reinterpret_cast<float*>(p.ws) + i * ldw + jn, __uint_as_float(r[0][j]));
+            if constexpr (KIND == 0) {
+              atomicAdd(p.ws + i * ldw + jn, static_cast<int32_t>(r[0][j]));
+              if constexpr (NB == 2) atomicAdd(p.ws + plane + i * ldw + jn, static_cast<int32_t>(r[1][j]));
+            } else {
+              atomicAdd(reinterpret_cast<float*>(p.ws) + i * ldw + jn, __uint_as_float(r[0][j]));
+            }
           }
         }
       }
+      if (direct) continue;
+      // ---- shared tile: ticket; the last of the contributing CTAs finishes it ----
+      __threadfence();
+      epi_bar_sync();
+      if (et == 0) {
+        const int contributors = cta_of_unit((tile + 1) * KB - 1, U, P) - cta_of_unit(tile * KB, U, P) + 1;
+        s_last = atomicAdd(p.counters + tile, 1) == contributors - 1;
+      }
+      epi_bar_sync();
+      if (s_last) {
+        __threadfence();
+        for (int e = et; e < kTileM * BN; e += 128) {
+          // consecutive threads -> consecutive output columns (n)
+          const int64_t arow2 = kSwap ? a0 + e % kTileM : a0 + e / BN;
+          const int64_t brow2 = kSwap ? b0 + e / kTileM : b0 + e % BN;
+          if (arow2 >= p.rows_a || brow2 >= p.rows_b) continue;
+          const int64_t i = kSwap ? brow2 : arow2, jn = kSwap ? arow2 : brow2;
+          int32_t* w0 = p.ws + i * ldw + jn;
+          const int32_t v = __ldcg(w0);
+          *w0 = 0;
+          if constexpr (KIND != 0) {
+            float_epilogue_store<T>(p.fl, __int_as_float(v), i, jn);
+          } else if constexpr (NB == 2) {
+            int32_t* w1 = w0 + plane;
+            const int32_t v2 = __ldcg(w1);
+            *w1 = 0;
+            glu_epilogue_store<T>(p.glu, v, v2, i, jn);
+          } else {
+            dense_epilogue_store<T>(p.dense, v, i, jn);
+          }
+        }
+        if (et == 0) p.counters[tile] = 0;
+      }
+      epi_bar_sync();                               // s_last is reused by the next shared tile
     }
-    tc_fence_before();
   }
 
   __syncthreads();
   if (warp == 1) {
+    __syncwarp();
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
   }
-  if (p.splits == 1) return;
-
-  // ---- split-K fix-up: the last CTA of this output tile applies the epilogue ----
-  __threadfence();
-  const int tile_id = blockIdx.y * gridDim.x + blockIdx.x;
-  if (threadIdx.x == 0) s_last = atomicAdd(p.counters + tile_id, 1) == p.splits - 1;
-  __syncthreads();
-  if (!s_last) return;
-  __threadfence();
-  const int64_t ldw = kSwap ? p.rows_a : p.rows_b;
-  const int64_t plane = p.rows_a * p.rows_b;
-  for (int e = threadIdx.x; e < kTileM * BN; e += kTcThreads) {
-    // consecutive threads -> consecutive output columns (n)
-    const int64_t arow = kSwap ? a0 + e % kTileM : a0 + e / BN;
-    const int64_t brow = kSwap ? b0 + e / kTileM : b0 + e % BN;
-    if (arow >= p.rows_a || brow >= p.rows_b) continue;
-    const int64_t i = kSwap ? brow : arow, jn = kSwap ? arow : brow;
-    int32_t* w0 = p.ws + i * ldw + jn;
-    const int32_t v = __ldcg(w0);
-    *w0 = 0;
-    if constexpr (KIND != 0) {
-      float_epilogue_store<T>(p.fl, __int_as_float(v), i, jn);
-    } else if constexpr (NB == 2) {
-      int32_t* w1 = w0 + plane;
-      const int32_t v2 = __ldcg(w1);
-      *w1 = 0;
-      glu_epilogue_store<T>(p.glu, v, v2, i, jn);
-    } else {
-      dense_epilogue_store<T>(p.dense, v, i, jn);
-    }
-  }
-  if (threadIdx.x == 0) p.counters[tile_id] = 0;
 }
 
 // ---- host side ----
@@ -406,14 +464,20 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   p.rows_a = kSwap ? n : m;
   p.rows_b = kSwap ? m : n;
   p.k = k;
-  const int tiles_a = div_up(p.rows_a, kTileM), tiles_b = div_up(p.rows_b, BN);
-  const int kb_total = div_up(k, kSwizzleBytes / elem);
+  p.tiles_a = div_up(p.rows_a, kTileM);
+  p.tiles_b = div_up(p.rows_b, BN);
+  p.kb_total = div_up(k, kSwizzleBytes / elem);
   SplitKWorkspace& wsp = SplitKWorkspace::get(st);
-  p.splits = choose_splits(tiles_a * tiles_b, kb_total, m * n * NB, wsp);
+  const int64_t tiles = static_cast<int64_t>(p.tiles_a) * p.tiles_b;
+  const int64_t units = tiles * p.kb_total;
+  int64_t ctas = std::min<int64_t>(wsp.sm_count, units);
+  // tiles shared between CTAs go through the scratch: fall back to whole tiles per CTA when it cannot hold them
+  const bool scratch_ok = static_cast<size_t>(m) * n * NB <= wsp.accum_elems && static_cast<size_t>(tiles) <= wsp.num_counters;
+  p.whole_tiles = scratch_ok ? 0 : 1;
+  if (!scratch_ok) ctas = std::min<int64_t>(wsp.sm_count, tiles);   // tile-aligned CTA ranges
   p.ws = wsp.accum;
   p.counters = wsp.counters;
-  dim3 grid(tiles_a, tiles_b, p.splits);
-  kernel<<<grid, kTcThreads, S::kBytes, st>>>(tmx, tmw, tmw2, p);
+  kernel<<<static_cast<unsigned>(ctas), kTcThreads, S::kBytes, st>>>(tmx, tmw, tmw2, p);
   check_launch();
 }
 
@@ -423,7 +487,7 @@ void launch_tc_shape(const void* x, const void* w, const void* w2, int64_t m, in
   if (m <= 16) launch_tc<T, KIND, 16, NB, true>(x, w, w2, m, n, k, p, st);
   else if (m <= 32) launch_tc<T, KIND, 32, NB, true>(x, w, w2, m, n, k, p, st);
   else if (m <= 64) launch_tc<T, KIND, 64, NB, true>(x, w, w2, m, n, k, p, st);
-  else if (NB == 2) launch_tc<T, KIND, 128, NB, false>(x, w, w2, m, n, k, p, st);
+  else if constexpr (NB == 2) launch_tc<T, KIND, 128, NB, false>(x, w, w2, m, n, k, p, st);
   else launch_tc<T, KIND, 256, NB, false>(x, w, w2, m, n, k, p, st);
 }
 

@@ -61,6 +61,15 @@ void launch_attention_prefill_simple(const void* qkv, const void* kc, const void
                                      int64_t batch, int64_t time, int64_t offset, int H, int Hkv, int D,
                                      int64_t max_len, float scale, void* out, int dtype, cudaStream_t st);
 
+// attention_mma.cu — tensor-core prefill attention (fp16/bf16, head_dim 64/128); false = shape not covered
+bool launch_attention_prefill_mma(const void* qkv, const void* kc, const void* vc, int64_t batch, int64_t time,
+                                  int64_t offset, int H, int Hkv, int D, int64_t max_len, float scale, void* out,
+                                  int dtype, cudaStream_t st);
+// picks the tensor-core kernel when it covers the shape (CT2B200_ATTN_PREFILL=simple forces the generic one)
+void launch_attention_prefill(const void* qkv, const void* kc, const void* vc, const int32_t* lengths, int64_t batch,
+                              int64_t time, int64_t offset, int H, int Hkv, int D, int64_t max_len, float scale,
+                              void* out, int dtype, cudaStream_t st);
+
 // decode_loop.cu
 void launch_sample_greedy(const void* logits, int64_t batch, int64_t vocab, const int32_t* gen, const int32_t* end_ids,
                           const int32_t* forced, int32_t* next_ids, int32_t* out_ids, int32_t* lens, int dtype,
