@@ -133,6 +133,9 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
     model where generating 8e9 gaussians on the host would dominate the run.
     """
     rng = np.random.default_rng(seed)
+    awq_layout = {"awq_gemm": 1, "awq_gemv": 2}.get(quantization, 0)
+    if awq_layout:
+        return _write_llama_awq(model_dir, cfg, awq_layout, seed, init_std, fast_int8)
     is_int8 = quantization.startswith("int8")
     ftype = {"int8": "float32", "int8_float32": "float32", "int8_float16": "float16",
              "int8_bfloat16": "bfloat16"}.get(quantization, quantization)
@@ -213,4 +216,93 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
     w.add("decoder/start_from_zero_embedding", np.int8(0))
     config = {"bos_token": "<t1>", "eos_token": "<t2>", "unk_token": "<t0>",
               "layer_norm_epsilon": cfg.rms_eps, "multi_query_attention": cfg.num_heads_kv != cfg.num_heads}
+    w.close(config, (f"<t{i}>" for i in range(cfg.vocab_size)))
+
+
+AWQ_ORDER = np.array([0, 4, 1, 5, 2, 6, 3, 7])
+
+
+def _pack_nibbles(m: np.ndarray, order) -> np.ndarray:
+    """[rows, cols] values 0..15 -> int32 [rows, cols/8]; element 8c+i goes to nibble order[i]."""
+    r, c = m.shape
+    m = m.reshape(r, c // 8, 8).astype(np.uint32)
+    out = np.zeros((r, c // 8), np.uint32)
+    for i in range(8):
+        out |= (m[:, :, i] & 0xF) << np.uint32(4 * order[i])
+    return out.view(np.int32)
+
+
+def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
+    """AWQ-INT4 (group 128) Llama directory as the AutoAWQ -> CTranslate2 converter lays it out
+    (converters/transformers.py:1697-1843 with quant_type AWQ_GEMM / AWQ_GEMV): linear layers carry int32
+    `weight` + float16 `weight_scale` + int32 `weight_zero`; embeddings, norms and lm_head stay float16;
+    config.json records quantization_type / bits / group size (src/models/model.cc:636-637)."""
+    rng = np.random.default_rng(seed)
+    G = 128
+    d, D = cfg.d_model, cfg.head_dim
+    w = ModelWriter(model_dir)
+    base = rng.integers(0, 16, size=1 << 22, dtype=np.uint8)
+    off = [0]
+
+    def nibbles(rows, cols):
+        n = rows * cols
+        reps = -(-(n + off[0]) // base.size)
+        a = np.tile(base, reps)[off[0]:off[0] + n].reshape(rows, cols)
+        off[0] = (off[0] + 7919) % base.size
+        return a
+
+    def linear(prefix, n, k):
+        scales = (rng.uniform(0.6, 1.4, size=(k // G, n)) * (init_std / 2.5)).astype(np.float16)
+        zeros = rng.integers(6, 10, size=(k // G, n))
+        q = nibbles(k, n)                                   # [K, N] values 0..15
+        if layout == 1:
+            w.add(prefix + "/weight", _pack_nibbles(q, AWQ_ORDER), "int32")
+            w.add(prefix + "/weight_scale", scales, "float16")
+            w.add(prefix + "/weight_zero", _pack_nibbles(zeros, AWQ_ORDER), "int32")
+        else:
+            ng = k // G
+            zw = -(-ng // 8)
+            zp = np.zeros((n, zw * 8), np.int64)
+            zp[:, :ng] = zeros.T
+            sp = np.zeros((n, zw * 8), np.float16)
+            sp[:, :ng] = scales.T
+            w.add(prefix + "/weight", _pack_nibbles(np.ascontiguousarray(q.T), np.arange(8)), "int32")
+            w.add(prefix + "/weight_scale", sp, "float16")
+            w.add(prefix + "/weight_zero", _pack_nibbles(zp, np.arange(8)), "int32")
+
+    def dense_f16(prefix, n, k):
+        reps = -(-(n * k) // (1 << 22))
+        vals = (np.tile(base, reps)[:n * k].astype(np.float32) - 7.5) * (init_std / 4.6)
+        w.add(prefix + "/weight", vals.reshape(n, k), "float16")
+
+    w.add("decoder/activation", np.int8(2))
+    w.add("decoder/alibi", np.int8(0))
+    w.add("decoder/alibi_use_positive_positions", np.int8(0))
+    w.add("decoder/alignment_heads", np.int16(1))
+    w.add("decoder/alignment_layer", np.int16(-1))
+    dense_f16("decoder/embeddings", cfg.vocab_size, d)
+    for l in range(cfg.num_layers):
+        p = f"decoder/layer_{l}/"
+        w.add(p + "ffn/layer_norm/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), "float16")
+        linear(p + "ffn/linear_0", cfg.ffn_dim, d)
+        linear(p + "ffn/linear_0_noact", cfg.ffn_dim, d)
+        linear(p + "ffn/linear_1", d, cfg.ffn_dim)
+        w.add(p + "self_attention/layer_norm/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), "float16")
+        linear(p + "self_attention/linear_0", (cfg.num_heads + 2 * cfg.num_heads_kv) * D, d)
+        linear(p + "self_attention/linear_1", d, cfg.num_heads * D)
+        w.add(p + "self_attention/num_heads_kv", np.int32(cfg.num_heads_kv))
+        w.add(p + "self_attention/head_dim", np.int32(cfg.head_dim))
+        w.add(p + "self_attention/rotary_base", np.float32(cfg.rotary_base))
+        w.add(p + "self_attention/rotary_dim", np.int32(0))
+        w.add(p + "self_attention/rotary_interleave", np.int8(0))
+    w.add("decoder/layer_norm/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), "float16")
+    w.add("decoder/num_heads", np.int16(cfg.num_heads))
+    w.add("decoder/pre_norm", np.int8(1))
+    dense_f16("decoder/projection", cfg.vocab_size, d)
+    w.add("decoder/scale_alibi", np.int8(0))
+    w.add("decoder/scale_embeddings", np.int8(0))
+    w.add("decoder/start_from_zero_embedding", np.int8(0))
+    config = {"bos_token": "<t1>", "eos_token": "<t2>", "unk_token": "<t0>", "layer_norm_epsilon": cfg.rms_eps,
+              "multi_query_attention": cfg.num_heads_kv != cfg.num_heads, "quantization_type": layout,
+              "quantization_bits": 4, "quantization_group_size": G}
     w.close(config, (f"<t{i}>" for i in range(cfg.vocab_size)))

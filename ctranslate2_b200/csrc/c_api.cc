@@ -228,14 +228,40 @@ CT2B200_API int ct2b200_attention_prefill(const void* qkv, void* k_cache, void* 
   });
 }
 
-CT2B200_API int ct2b200_dense_awq(const void*, const int32_t*, const void*, const int32_t*, int, int, const void*, const void*,
-                      int, int64_t, int64_t, int64_t, void*, void*) {
-  g_error = "ct2b200_dense_awq: AWQ-INT4 kernels are not built in this revision";
-  return 3;
+CT2B200_API int ct2b200_awq_repack(const int32_t* qweight, const void* scales, const int32_t* qzeros, int layout, int group_size,
+                       int64_t n, int64_t k, int32_t* wp, void* sc, void* zr, void* stream) {
+  return guarded([&] {
+    require_device();
+    awq_repack(qweight, scales, qzeros, layout, group_size, n, k, wp, sc, zr, S(stream));
+  });
 }
-CT2B200_API int ct2b200_dequantize_awq(const int32_t*, const void*, const int32_t*, int, int, int64_t, int64_t, void*, void*) {
-  g_error = "ct2b200_dequantize_awq: AWQ-INT4 kernels are not built in this revision";
-  return 3;
+
+CT2B200_API int ct2b200_dense_awq(const void* x, const int32_t* wp, const void* sc, const void* zr, int group_size,
+                      const void* bias, const void* residual, int act, int64_t m, int64_t n, int64_t k, void* y,
+                      void* scratch_nk, void* stream) {
+  return guarded([&] {
+    require_device();
+    AwqNative w{wp, sc, zr, n, k, group_size};
+    dense_awq(x, w, bias, residual, act, m, y, scratch_nk, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dense_awq_glu(const void* x, const int32_t* wp_gate, const void* sc_gate, const void* zr_gate,
+                          const int32_t* wp_up, const void* sc_up, const void* zr_up, int group_size, int act, int64_t m,
+                          int64_t n, int64_t k, void* h, void* scratch_nk, void* scratch_mn, void* stream) {
+  return guarded([&] {
+    require_device();
+    AwqNative g{wp_gate, sc_gate, zr_gate, n, k, group_size}, u{wp_up, sc_up, zr_up, n, k, group_size};
+    dense_awq_glu(x, g, u, act, m, h, scratch_nk, scratch_mn, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dequantize_awq(const int32_t* qweight, const void* scales, const int32_t* qzeros, int layout,
+                           int group_size, int64_t n, int64_t k, void* w, void* stream) {
+  return guarded([&] {
+    require_device();
+    awq_dequantize_ref_layout(qweight, scales, qzeros, layout, group_size, n, k, w, S(stream));
+  });
 }
 
 // ---- engine ----

@@ -10,6 +10,7 @@
 #include <cstdio>
 #include <stdexcept>
 #include <string>
+#include <utility>
 
 #include "../../include/ct2b200.h"
 
@@ -150,6 +151,31 @@ __device__ __forceinline__ void dense_epilogue_store(const DenseEpilogue& e, int
   float v = dense_epilogue_value<T>(e, acc, i, j);
   if (e.residual) v = v + to_f32(static_cast<const T*>(e.residual)[i * e.ldy + j]);
   static_cast<T*>(e.y)[i * e.ldy + j] = from_f32<T>(v);
+}
+
+// ---- programmatic dependent launch (PDL) ----
+// Every kernel of the decode step is launched with cudaLaunchAttributeProgrammaticStreamSerialization: it may start
+// (be scheduled, run its prologue) while its predecessor is still draining; `griddep_wait()` blocks until all
+// prerequisite grids have completed and their writes are visible, so it must precede the first access to data a
+// previous kernel produced.  `griddep_launch()` lets the NEXT kernel's CTAs be scheduled early.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+bool pdl_enabled();
+
+template <typename... KArgs, typename... Args>
+void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  CT2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, KArgs(std::forward<Args>(args))...));
 }
 
 inline int div_up(int64_t a, int64_t b) { return static_cast<int>((a + b - 1) / b); }

@@ -262,8 +262,39 @@ void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, Den
     const auto bytes = convert_to_dtype(wt, dtype_);
     upload(w.weight, bytes.data(), bytes.size());
     mc_.weight_bytes += bytes.size();
+  } else if (wt.type_id == 3 && f.find(prefix + "/weight_zero")) {
+    // AWQ-INT4 (model.cc:750-757 pins FLOAT16): repack once into the native K-major layout (kernels/awq.cu)
+    CT2_REQUIRE(dtype_ == CT2B200_F16, "AWQ models run with float16 activations (the reference forces ComputeType::FLOAT16)");
+    const int layout = static_cast<int>(f.config_number("quantization_type", 0));
+    CT2_REQUIRE(layout == 1 || layout == 2, "config.json quantization_type must be 1 (AWQ_GEMM) or 2 (AWQ_GEMV)");
+    const HostVariable& sc = f.get(prefix + "/weight_scale");
+    const HostVariable& zr = f.get(prefix + "/weight_zero");
+    CT2_REQUIRE(sc.type_id == 4, "AWQ scales must be float16");
+    w.kind = layout == 1 ? DenseWeights::AWQ_GEMM : DenseWeights::AWQ_GEMV;
+    if (layout == 1) {            // qweight [K, N/8], scales [K/G, N]
+      w.k = wt.shape[0];
+      w.n = wt.shape[1] * 8;
+      w.group_size = static_cast<int>(w.k / sc.shape[0]);
+    } else {                      // qweight [N, K/8], scales [N, K/G (padded)]
+      w.n = wt.shape[0];
+      w.k = wt.shape[1] * 8;
+      const int g = static_cast<int>(f.config_number("quantization_group_size", 128));
+      w.group_size = g > 0 ? g : 128;
+    }
+    DeviceBuffer qw, qs, qz;
+    upload(qw, wt.data, wt.nbytes);
+    upload(qs, sc.data, sc.nbytes);
+    upload(qz, zr.data, zr.nbytes);
+    const int64_t ng = w.k / w.group_size;
+    w.weight.alloc(static_cast<size_t>(w.n) * (w.k / 8) * 4);
+    w.scale.alloc(static_cast<size_t>(w.n) * ng * 2);
+    w.zeros.alloc(static_cast<size_t>(w.n) * ng * 2);
+    awq_repack(qw.as<int32_t>(), qs.ptr, qz.as<int32_t>(), layout, w.group_size, w.n, w.k, w.weight.as<int32_t>(),
+               w.scale.ptr, w.zeros.ptr, stream_);
+    CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    mc_.weight_bytes += w.weight.bytes + w.scale.bytes + w.zeros.bytes;
   } else {
-    throw std::runtime_error("unsupported weight type for " + prefix + " (AWQ models: see ct2b200_dense_awq)");
+    throw std::runtime_error("unsupported weight type for " + prefix);
   }
   if (const HostVariable* b = f.find(prefix + "/bias")) {
     const auto bytes = convert_to_dtype(*b, dtype_);
@@ -386,6 +417,12 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   qkv_.alloc(R * qkv_w * es);
   attn_.alloc(R * mc_.num_heads * mc_.head_dim * es);
   h_.alloc(R * mc_.ffn_dim * es);
+  if (layers_[0].qkv.kind != DenseWeights::INT8 || projection_.kind != DenseWeights::INT8) {
+    xn_.alloc(R * mc_.d_model * es);
+    scratch_mn_.alloc(R * mc_.ffn_dim * es);
+    if (layers_[0].qkv.kind != DenseWeights::FLOAT16)
+      scratch_nk_.alloc(static_cast<size_t>(std::max(mc_.ffn_dim, mc_.d_model)) * std::max<int64_t>(mc_.ffn_dim, qkv_w) * 2);
+  }
   logits_.alloc(max_batch_ * mc_.vocab * es);
   gathered_.alloc(max_batch_ * mc_.d_model * es);
   attn_splits_ = attention_decode_splits(max_batch_, mc_.num_heads_kv, max_len_, sm_count_);
@@ -399,14 +436,17 @@ LlamaDecoder::~LlamaDecoder() {
   if (stream_) cudaStreamDestroy(stream_);
 }
 
-// layers::Dense::operator()
+// layers::Dense::operator() (src/layers/common.cc:339-442): INT8 / AWQ / float arms
 void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* xs, const void* x_float, int64_t m,
                          const void* residual, int act, void* y) {
   if (w.kind == DenseWeights::INT8) {
     DenseEpilogue e{xs, w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
     gemm_s8(xq, w.weight.as<int8_t>(), m, w.n, w.k, e, dtype_, gemm_impl_, stream_);
-  } else {
+  } else if (w.kind == DenseWeights::FLOAT16) {
     gemm_f16_tc(x_float, w.weight.ptr, w.bias.ptr, residual, act, m, w.n, w.k, y, dtype_, stream_);
+  } else {
+    AwqNative a{w.weight.ptr, w.scale.ptr, w.zeros.ptr, w.n, w.k, w.group_size};
+    dense_awq(x_float, a, w.bias.ptr, residual, act, m, y, scratch_nk_.ptr, stream_);
   }
 }
 
@@ -414,13 +454,7 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
   const int H = mc_.num_heads, Hkv = mc_.num_heads_kv, D = mc_.head_dim;
   const float scale = 1.f / std::sqrt(static_cast<float>(D));
   const bool int8 = layers_[0].qkv.kind == DenseWeights::INT8;
-  CT2_REQUIRE(int8, "float-weight decoder layers are not wired yet (INT8 models only)");
-  for (int l = 0; l < mc_.num_layers; ++l) {
-    LayerWeights& lw = layers_[l];
-    // --- self attention (attention.cc:442-615) ---
-    launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
-                    xs_.as<float>(), dtype_, stream_);
-    dense(lw.qkv, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, qkv_.ptr);
+  auto attention = [&](int l) {
     if (lens_d) {
       launch_attention_decode(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, sin_.as<float>(), cos_.as<float>(), lens_d,
                               batch, H, Hkv, D, max_len_, mc_.rotary_interleave, scale, attn_.ptr, attn_ws_.ptr,
@@ -431,6 +465,36 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
       launch_attention_prefill(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, nullptr, batch, time, offset, H, Hkv, D,
                                max_len_, scale, attn_.ptr, dtype_, stream_);
     }
+  };
+  if (!int8) {
+    // float16/bfloat16 weights (Dense float arm, common.cc:440) and AWQ-INT4 (common.cc:402-438): activations stay in T
+    for (int l = 0; l < mc_.num_layers; ++l) {
+      LayerWeights& lw = layers_[l];
+      launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, xn_.ptr, nullptr, nullptr, dtype_, stream_);
+      dense(lw.qkv, nullptr, nullptr, xn_.ptr, rows, nullptr, -1, qkv_.ptr);
+      attention(l);
+      dense(lw.out, nullptr, nullptr, attn_.ptr, rows, x_.ptr, -1, x_.ptr);
+      launch_rms_norm(lw.ffn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, xn_.ptr, nullptr, nullptr, dtype_, stream_);
+      if (lw.gate.kind == DenseWeights::FLOAT16) {
+        dense(lw.gate, nullptr, nullptr, xn_.ptr, rows, nullptr, mc_.activation, h_.ptr);
+        dense(lw.up, nullptr, nullptr, xn_.ptr, rows, nullptr, -1, scratch_mn_.ptr);
+        launch_mul_inplace(h_.ptr, scratch_mn_.ptr, rows * mc_.ffn_dim, dtype_, stream_);
+      } else {
+        AwqNative g{lw.gate.weight.ptr, lw.gate.scale.ptr, lw.gate.zeros.ptr, lw.gate.n, lw.gate.k, lw.gate.group_size};
+        AwqNative u{lw.up.weight.ptr, lw.up.scale.ptr, lw.up.zeros.ptr, lw.up.n, lw.up.k, lw.up.group_size};
+        dense_awq_glu(xn_.ptr, g, u, mc_.activation, rows, h_.ptr, scratch_nk_.ptr, scratch_mn_.ptr, stream_);
+      }
+      dense(lw.down, nullptr, nullptr, h_.ptr, rows, x_.ptr, -1, x_.ptr);
+    }
+    return;
+  }
+  for (int l = 0; l < mc_.num_layers; ++l) {
+    LayerWeights& lw = layers_[l];
+    // --- self attention (attention.cc:442-615) ---
+    launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                    xs_.as<float>(), dtype_, stream_);
+    dense(lw.qkv, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, qkv_.ptr);
+    attention(l);
     launch_quantize_rows(attn_.ptr, dtype_, rows, static_cast<int64_t>(H) * D, true, xq_.as<int8_t>(),
                          xs_.as<float>(), stream_);
     dense(lw.out, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
@@ -445,11 +509,24 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
   }
 }
 
+// layers::Embeddings::operator() (common.cc:64-81)
+void LlamaDecoder::embed(const int32_t* ids_d, int64_t rows) {
+  if (embeddings_.kind == DenseWeights::INT8)
+    launch_embedding_s8(embeddings_.weight.as<int8_t>(), embeddings_.scale.as<float>(), ids_d, rows, mc_.d_model, x_.ptr,
+                        dtype_, stream_);
+  else
+    launch_gather_rows(embeddings_.weight.ptr, ids_d, rows, mc_.d_model * dtype_size(dtype_), x_.ptr, stream_);
+}
+
 void LlamaDecoder::project(const void* x_rows, int64_t rows, void* logits_out) {
-  launch_rms_norm(final_gamma_.ptr, x_rows, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
-                  xs_.as<float>(), dtype_, stream_);
-  CT2_REQUIRE(projection_.kind == DenseWeights::INT8, "float projection is not wired yet");
-  dense(projection_, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, logits_out);
+  if (projection_.kind == DenseWeights::INT8) {
+    launch_rms_norm(final_gamma_.ptr, x_rows, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                    xs_.as<float>(), dtype_, stream_);
+    dense(projection_, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, logits_out);
+  } else {
+    launch_rms_norm(final_gamma_.ptr, x_rows, rows, mc_.d_model, mc_.eps, false, xn_.ptr, nullptr, nullptr, dtype_, stream_);
+    dense(projection_, nullptr, nullptr, xn_.ptr, rows, nullptr, -1, logits_out);
+  }
 }
 
 void LlamaDecoder::forward_prefill(const int32_t* ids_d, int64_t batch, int64_t time, int64_t offset,
@@ -457,9 +534,7 @@ void LlamaDecoder::forward_prefill(const int32_t* ids_d, int64_t batch, int64_t 
   const int64_t rows = batch * time;
   CT2_REQUIRE(rows <= chunk_rows_, "forward_prefill: too many rows for the activation arena");
   CT2_REQUIRE(batch <= max_batch_ && offset + time <= max_len_, "forward_prefill: batch/length exceeds the KV arena");
-  CT2_REQUIRE(embeddings_.kind == DenseWeights::INT8, "float embeddings are not wired yet");
-  launch_embedding_s8(embeddings_.weight.as<int8_t>(), embeddings_.scale.as<float>(), ids_d, rows, mc_.d_model,
-                      x_.ptr, dtype_, stream_);
+  embed(ids_d, rows);
   layers_forward(rows, batch, time, offset, nullptr);
   if (logits_out_d && num_logit_rows > 0) {
     if (logits_rows_d) {
@@ -480,8 +555,7 @@ void LlamaDecoder::project_rows(const int32_t* rows_d, int64_t n, void* logits_o
 
 void LlamaDecoder::forward_step(const int32_t* ids_d, const int32_t* lens_d, int64_t batch, void* logits_out_d) {
   CT2_REQUIRE(batch <= max_batch_, "forward_step: batch exceeds the KV arena");
-  launch_embedding_s8(embeddings_.weight.as<int8_t>(), embeddings_.scale.as<float>(), ids_d, batch, mc_.d_model,
-                      x_.ptr, dtype_, stream_);
+  embed(ids_d, batch);
   layers_forward(batch, batch, 1, 0, lens_d);
   project(x_.ptr, batch, logits_out_d);
 }
@@ -499,6 +573,8 @@ Generator::Generator(const std::string& model_dir, const ct2b200_generator_confi
   forced_d_.alloc(B * L * sizeof(int32_t));
   out_d_.alloc(B * L * sizeof(int32_t));
   end_ids_d_.alloc(64 * sizeof(int32_t));
+  sample_ws_.alloc((B * 65) * sizeof(int32_t));      // part_v [B*32] | part_i [B*32] | tickets [B]
+  CT2_CUDA_CHECK(cudaMemset(sample_ws_.ptr, 0, sample_ws_.bytes));
   prompt_d_.alloc(B * L * sizeof(int32_t));
   host_pinned_elems_ = static_cast<size_t>(B) * L + 64;
   CT2_CUDA_CHECK(cudaMallocHost(&host_pinned_, host_pinned_elems_ * sizeof(int32_t)));
@@ -527,7 +603,8 @@ void Generator::launch_step(int64_t batch, int64_t, int) {
   d.forward_step(ids_d_.as<int32_t>(), lens_d_.as<int32_t>(), batch, d.logits_buffer());
   launch_sample_greedy(d.logits_buffer(), batch, d.config().vocab, step_d_.as<int32_t>(), end_ids_d_.as<int32_t>(),
                        forced_d_.as<int32_t>(), ids_d_.as<int32_t>(), out_d_.as<int32_t>(), lens_d_.as<int32_t>(),
-                       d.dtype(), d.stream());
+                       sample_ws_.as<float>(), sample_ws_.as<int32_t>() + d.max_batch() * 32,
+                       sample_ws_.as<int32_t>() + d.max_batch() * 64, d.dtype(), d.stream());
 }
 
 void Generator::build_step_graph(int64_t batch, int64_t min_length, int num_end_ids) {

@@ -132,6 +132,7 @@ class LlamaDecoder {
              const void* residual, int act, void* y);
   void layers_forward(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d);
   void project(const void* x_rows, int64_t rows, void* logits_out);
+  void embed(const int32_t* ids_d, int64_t rows);
 
   ModelConfig mc_;
   int dtype_ = CT2B200_F16;
@@ -151,6 +152,7 @@ class LlamaDecoder {
 
   // activations (rows = max(chunk_rows, max_batch))
   DeviceBuffer x_, xq_, xs_, qkv_, attn_, h_, logits_, gathered_, attn_ws_;
+  DeviceBuffer xn_, scratch_mn_, scratch_nk_;   // float/AWQ arms: normed activations, up-projection, dequantized weight
 };
 
 struct GenerationRequest {
@@ -181,7 +183,7 @@ class Generator {
   ct2b200_generator_config cfg_;
   std::unique_ptr<LlamaDecoder> decoder_;
   // decode-loop device state
-  DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_;
+  DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_, sample_ws_;
   int32_t* host_pinned_ = nullptr;
   size_t host_pinned_elems_ = 0;
   cudaGraphExec_t graph_ = nullptr;

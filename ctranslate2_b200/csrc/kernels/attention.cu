@@ -50,6 +50,8 @@ __global__ void __launch_bounds__(kDecThreads)
   __shared__ float s_acc[NW][KPW][G][D];
   __shared__ bool s_last;
 
+  griddep_launch();
+  griddep_wait();
   const int split = blockIdx.x, nsplit = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const int pos = lens[b];                     // position of the new token; keys 0..pos are attended
@@ -112,31 +114,46 @@ __global__ void __launch_bounds__(kDecThreads)
       kv[u] = ld16(kc + off);
       vv[u] = ld16(vc + off);
     }
+    float kf[UNROLL][VEC], vf[UNROLL][VEC];
 #pragma unroll
-    for (int u = 0; u < UNROLL; ++u) {
-      float kf[VEC], vf[VEC];
+    for (int u = 0; u < UNROLL; ++u)
 #pragma unroll
       for (int i = 0; i < VEC; ++i) {
-        kf[i] = to_f32(kv[u].v[i]);
-        vf[i] = to_f32(vv[u].v[i]);
+        kf[u][i] = to_f32(kv[u].v[i]);
+        vf[u][i] = to_f32(vv[u].v[i]);
       }
 #pragma unroll
-      for (int h = 0; h < G; ++h) {
+    for (int h = 0; h < G; ++h) {
+      // scores of the UNROLL keys of this lane group, then ONE rescale of the running state per block
+      float sc[UNROLL], mblk = -INFINITY;
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) s = fmaf(q[h][i], kf[i], s);
+        for (int i = 0; i < VEC; ++i) s = fmaf(q[h][i], kf[u][i], s);
 #pragma unroll
         for (int o = LANES / 2; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-        if (ok[u]) {                           // uniform within the LANES group
-          const float mn = fmaxf(m[h], s);
-          const float corr = exp2f(m[h] - mn);
-          const float p = exp2f(s - mn);
-          l[h] = l[h] * corr + p;
-#pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[h][i] = fmaf(p, vf[i], acc[h][i] * corr);
-          m[h] = mn;
-        }
+        sc[u] = ok[u] ? s : -INFINITY;
+        mblk = fmaxf(mblk, sc[u]);
       }
+      const float mn = fmaxf(m[h], mblk);
+      if (mn == -INFINITY) continue;             // nothing valid yet (uniform within the lane group)
+      const float corr = exp2f(m[h] - mn);       // m == -inf -> 0
+      float psum = 0.f, pu[UNROLL];
+#pragma unroll
+      for (int u = 0; u < UNROLL; ++u) {
+        pu[u] = exp2f(sc[u] - mn);               // -inf -> 0
+        psum += pu[u];
+      }
+      l[h] = l[h] * corr + psum;
+#pragma unroll
+      for (int i = 0; i < VEC; ++i) {
+        float a = acc[h][i] * corr;
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) a = fmaf(pu[u], vf[u][i], a);
+        acc[h][i] = a;
+      }
+      m[h] = mn;
     }
   }
 
@@ -186,13 +203,17 @@ __global__ void __launch_bounds__(kDecThreads)
     const int h = e / D, i = e % D;
     const float* ph = part + static_cast<int64_t>(h) * nsplit * partial_stride(D);
     float mm = -INFINITY;
+#pragma unroll 8
     for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, __ldcg(ph + s * partial_stride(D) + D));
     float ll = 0.f, a = 0.f;
+#pragma unroll 8
     for (int s = 0; s < nsplit; ++s) {
       const float ms = __ldcg(ph + s * partial_stride(D) + D);
+      const float ls = __ldcg(ph + s * partial_stride(D) + D + 1);
+      const float as = __ldcg(ph + s * partial_stride(D) + i);
       const float c = ms == -INFINITY ? 0.f : exp2f(ms - mm);
-      ll += __ldcg(ph + s * partial_stride(D) + D + 1) * c;
-      a += __ldcg(ph + s * partial_stride(D) + i) * c;
+      ll += ls * c;
+      a += as * c;
     }
     out[static_cast<int64_t>(b) * H * D + (static_cast<int64_t>(kvh) * G + h) * D + i] = from_f32<T>(a / ll);
   }
@@ -312,9 +333,9 @@ void launch_decode_g(const void* qkv, void* kc, void* vc, const float* sn, const
   dim3 grid(splits, Hkv, static_cast<unsigned>(batch));
   const int G = H / Hkv;
 #define CT2_LAUNCH_G(GV)                                                                                      \
-  attention_decode_kernel<T, D, GV><<<grid, kDecThreads, 0, st>>>(                                            \
-      static_cast<const T*>(qkv), static_cast<T*>(kc), static_cast<T*>(vc), sn, cs, lens, H, Hkv, max_len,    \
-      interleave, scale_log2, static_cast<T*>(out), partials, tickets)
+  launch_pdl(attention_decode_kernel<T, D, GV>, grid, dim3(kDecThreads), 0, st, static_cast<const T*>(qkv),   \
+             static_cast<T*>(kc), static_cast<T*>(vc), sn, cs, lens, H, Hkv, max_len, interleave, scale_log2, \
+             static_cast<T*>(out), partials, tickets)
   switch (G) {
     case 1: CT2_LAUNCH_G(1); break;
     case 2: CT2_LAUNCH_G(2); break;
@@ -333,7 +354,7 @@ int attention_decode_splits(int64_t batch, int Hkv, int64_t max_len, int sm_coun
   int s = static_cast<int>((2 * sm_count + ctas - 1) / ctas);
   const int max_s = static_cast<int>(std::max<int64_t>(1, max_len / 64));
   if (s > max_s) s = max_s;
-  if (s > 64) s = 64;
+  if (s > 32) s = 32;
   if (s < 1) s = 1;
   return s;
 }

@@ -29,11 +29,42 @@ __device__ __forceinline__ void glu_epilogue_store(const GluEpilogue& e, int32_t
   static_cast<T*>(e.h)[i * e.ldh + j] = from_f32<T>(gate * up);
 }
 
+// Float epilogue of the f16/bf16 GEMM (ops::Gemm::apply_bias_and_activation, reference src/ops/gemm.cc:10-25)
+struct FloatEpilogue {
+  const void* bias;
+  const void* residual;
+  void* y;
+  int act;
+  int64_t ldy;
+};
+template <typename T>
+__device__ __forceinline__ void float_epilogue_store(const FloatEpilogue& e, float acc, int64_t i, int64_t j) {
+  float v = round_to<T>(acc);
+  if (e.bias) v = round_to<T>(v + to_f32(static_cast<const T*>(e.bias)[j]));
+  if (e.act >= 0) v = round_to<T>(apply_act(v, e.act));
+  if (e.residual) v = v + to_f32(static_cast<const T*>(e.residual)[i * e.ldy + j]);
+  static_cast<T*>(e.y)[i * e.ldy + j] = from_f32<T>(v);
+}
+
+
+// SwiGLU over float accumulators (AWQ gate/up): h = T(act(T(gate))) * T(up)
+struct FloatGluEpilogue {
+  void* h;
+  int act;
+  int64_t ldh;
+};
+template <typename T>
+__device__ __forceinline__ void float_glu_epilogue_store(const FloatGluEpilogue& e, float gate, float up, int64_t i, int64_t j) {
+  const float g = round_to<T>(apply_act(round_to<T>(gate), e.act));
+  static_cast<T*>(e.h)[i * e.ldh + j] = from_f32<T>(g * round_to<T>(up));
+}
+
 // Per-(device, stream) split-K scratch.  `accum` holds int32 (or fp32) partial sums and is all-zero
 // between kernels; `counters` are per-tile arrival tickets, also zero between kernels.
 struct SplitKWorkspace {
   int32_t* accum = nullptr;
   int32_t* counters = nullptr;
+  int32_t* accum2 = nullptr;        // fully-overwritten partial slots of the float (f16/AWQ) kernels: never needs zeroing
   size_t accum_elems = 0;
   size_t num_counters = 0;
   int sm_count = 148;
@@ -55,6 +86,7 @@ struct SplitKWorkspace {
         throw std::runtime_error("split-K workspace must be created before stream capture (call a GEMM once eagerly)");
       CT2_CUDA_CHECK(cudaMalloc(&w.accum, kAccumElems * sizeof(int32_t)));
       CT2_CUDA_CHECK(cudaMalloc(&w.counters, kCounters * sizeof(int32_t)));
+      CT2_CUDA_CHECK(cudaMalloc(&w.accum2, kAccumElems * sizeof(int32_t)));
       CT2_CUDA_CHECK(cudaMemset(w.accum, 0, kAccumElems * sizeof(int32_t)));
       CT2_CUDA_CHECK(cudaMemset(w.counters, 0, kCounters * sizeof(int32_t)));
       CT2_CUDA_CHECK(cudaDeviceSynchronize());

@@ -20,142 +20,18 @@
 
 #include "../common.cuh"
 #include "gemm_common.cuh"
+#include "tc_common.cuh"
 
 namespace ct2b200 {
 
 namespace {
 
-constexpr int kTcThreads = 192;
-constexpr int kTileM = 128;              // UMMA M
-constexpr int kSwizzleBytes = 128;       // bytes of K per smem row (= one 128B swizzle atom)
-constexpr uint64_t kEvictFirst = 0x12F0000000000000ull;
-constexpr uint64_t kEvictLast = 0x14F0000000000000ull;
-
-// ---- PTX wrappers ----
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "WAIT_LOOP:\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-      "@p bra WAIT_DONE;\n"
-      "bra WAIT_LOOP;\n"
-      "WAIT_DONE:\n"
-      "}\n" ::"r"(smem_u32(bar)),
-      "r"(parity)
-      : "memory");
-}
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, uint64_t* bar, int c0, int c1,
-                                            uint64_t policy) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.L2::cache_hint"
-      " [%0], [%1, {%3, %4}], [%2], %5;"
-      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1), "l"(policy)
-      : "memory");
-}
-__device__ __forceinline__ void tmem_alloc(uint32_t* smem_slot, uint32_t cols) {
-  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_slot)), "r"(cols));
-  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
-}
-__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
-  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols));
-}
-__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-template <int KIND>
-__device__ __forceinline__ void umma(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
-  if constexpr (KIND == 0) {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::i8 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
-  } else {
-    asm volatile(
-        "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n}\n"
-        ::"r"(tmem_d), "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
-  }
-}
-// 32 lanes x 32 columns of 32-bit accumulators -> 32 registers per thread
-__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,"
-      "%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
-        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
-        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
-      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
-
-// K-major, SWIZZLE_128B shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): rows of 128 bytes,
-// 8-row groups 1024 bytes apart (SBO), version 1 (sm_100), layout type 2 (SWIZZLE_128B).
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);        // start address, bits [0,14)
-  d |= static_cast<uint64_t>(1) << 16;                           // leading byte offset (unused for SW128 K-major)
-  d |= static_cast<uint64_t>(1024 >> 4) << 32;                   // stride byte offset, bits [32,46)
-  d |= static_cast<uint64_t>(1) << 46;                           // descriptor version
-  d |= static_cast<uint64_t>(2) << 61;                           // SWIZZLE_128B
-  return d;
-}
-
-// cute::UMMA::InstrDescriptor
-template <int KIND>
-__host__ __device__ constexpr uint32_t make_idesc(int n) {
-  uint32_t d = 0;
-  d |= (KIND == 0 ? 2u : 1u) << 4;                  // c_format: S32 / F32
-  const uint32_t fmt = KIND == 0 ? 1u /*S8*/ : (KIND == 1 ? 0u /*F16*/ : 1u /*BF16*/);
-  d |= fmt << 7;                                    // a_format
-  d |= fmt << 10;                                   // b_format
-  d |= static_cast<uint32_t>(n >> 3) << 17;         // n_dim
-  d |= static_cast<uint32_t>(kTileM >> 4) << 24;    // m_dim
-  return d;                                         // a_major = b_major = K (0), dense, no negate
-}
+using namespace tc;
 
 template <int KIND> struct KindTraits;
 template <> struct KindTraits<0> { using Acc = int32_t; static constexpr int kElem = 1; };
 template <> struct KindTraits<1> { using Acc = float; static constexpr int kElem = 2; };
 template <> struct KindTraits<2> { using Acc = float; static constexpr int kElem = 2; };
-
-// Float epilogue of the f16/bf16 GEMM (ops::Gemm::apply_bias_and_activation, reference src/ops/gemm.cc:10-25)
-struct FloatEpilogue {
-  const void* bias;
-  const void* residual;
-  void* y;
-  int act;
-  int64_t ldy;
-};
-template <typename T>
-__device__ __forceinline__ void float_epilogue_store(const FloatEpilogue& e, float acc, int64_t i, int64_t j) {
-  float v = round_to<T>(acc);
-  if (e.bias) v = round_to<T>(v + to_f32(static_cast<const T*>(e.bias)[j]));
-  if (e.act >= 0) v = round_to<T>(apply_act(v, e.act));
-  if (e.residual) v = v + to_f32(static_cast<const T*>(e.residual)[i * e.ldy + j]);
-  static_cast<T*>(e.y)[i * e.ldy + j] = from_f32<T>(v);
-}
 
 struct TcParams {
   int64_t rows_a;      // rows of the M-side operand (n when swapped, m otherwise)
@@ -169,6 +45,7 @@ struct TcParams {
   GluEpilogue glu;
   FloatEpilogue fl;
   int32_t* ws;
+  float* fslots;       // float kinds: per-CTA partial-tile slots [ctas][2][128*BN] (deterministic reduction)
   int32_t* counters;
 };
 
@@ -181,15 +58,89 @@ struct TcSmem {
   static constexpr size_t kBytes = static_cast<size_t>(kStages) * kStage + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 128;" ::: "memory"); }
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+// Epilogue of one thread over kCols consecutive N-side rows of its M-side row `arow`, accumulators in r[w][j].
+// All global loads (scales, bias, residual) are issued before any arithmetic or store, so they overlap instead
+// of forming a load -> compute -> store chain per element (which made the epilogue latency-bound).
+//   kSwap: arow = output channel n, N-side rows = batch rows m;   !kSwap: arow = batch row m, N-side = channels n.
+template <typename T, int KIND, int NB, bool kSwap, int kCols>
+__device__ __forceinline__ void chunk_epilogue(const TcParams& p, const uint32_t (&r)[NB][32], int64_t arow, int64_t brow0) {
+  if (arow >= p.rows_a) return;
+  const int64_t ncols = min(static_cast<int64_t>(kCols), p.rows_b - brow0);
+  if (ncols <= 0) return;
+  const T* bias = static_cast<const T*>(KIND == 0 ? p.dense.bias : p.fl.bias);
+  const T* residual = static_cast<const T*>(KIND == 0 ? p.dense.residual : p.fl.residual);
+  T* y = static_cast<T*>(KIND == 0 ? (NB == 2 ? p.glu.h : p.dense.y) : p.fl.y);
+  const int64_t ldy = KIND == 0 ? (NB == 2 ? p.glu.ldh : p.dense.ldy) : p.fl.ldy;
+  const int act = KIND == 0 ? (NB == 2 ? p.glu.act : p.dense.act) : p.fl.act;
+  const bool raw = KIND == 0 && NB == 1 && p.dense.a_scale == nullptr;      // int32 output mode
+  if (raw) {
+#pragma unroll
+    for (int j = 0; j < kCols; ++j)
+      if (j < ncols) {
+        const int64_t i = kSwap ? brow0 + j : arow, jn = kSwap ? arow : brow0 + j;
+        p.dense.c_out[i * ldy + jn] = static_cast<int32_t>(r[0][j]);
+      }
+    return;
+  }
+  // ---- phase 1: loads ----
+  const float* x_scale = NB == 2 ? p.glu.a_scale : p.dense.a_scale;
+  const float* w_scale0 = NB == 2 ? p.glu.gate_scale : p.dense.b_scale;
+  const float* w_scale1 = p.glu.up_scale;
+  float st0 = 1.f, st1 = 1.f, bias_t = 0.f;          // per-thread constants
+  float sj0[kCols], sj1[NB == 2 ? kCols : 1], bj[kCols], resj[kCols];
+  if constexpr (KIND == 0) {
+    if constexpr (kSwap) {
+      st0 = __ldg(w_scale0 + arow);
+      if constexpr (NB == 2) st1 = __ldg(w_scale1 + arow);
+    } else {
+      st0 = __ldg(x_scale + arow);
+    }
+  }
+  if (bias && kSwap) bias_t = to_f32(bias[arow]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) {
+    const bool ok = j < ncols;
+    const int64_t i = kSwap ? brow0 + j : arow, jn = kSwap ? arow : brow0 + j;
+    if constexpr (KIND == 0) {
+      if constexpr (kSwap) {
+        sj0[j] = ok ? __ldg(x_scale + brow0 + j) : 1.f;
+      } else {
+        sj0[j] = ok ? __ldg(w_scale0 + brow0 + j) : 1.f;
+        if constexpr (NB == 2) sj1[j] = ok ? __ldg(w_scale1 + brow0 + j) : 1.f;
+      }
+    }
+    bj[j] = (bias && !kSwap && ok) ? to_f32(bias[jn]) : bias_t;
+    resj[j] = (residual && ok) ? to_f32(residual[i * ldy + jn]) : 0.f;
+  }
+  // ---- phase 2: arithmetic + stores (rounding points: see DenseEpilogue / GluEpilogue / FloatEpilogue) ----
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) {
+    if (j >= ncols) break;
+    const int64_t i = kSwap ? brow0 + j : arow, jn = kSwap ? arow : brow0 + j;
+    float v;
+    if constexpr (KIND != 0) {
+      v = round_to<T>(__uint_as_float(r[0][j]));
+      if (bias) v = round_to<T>(v + bj[j]);
+      if (act >= 0) v = round_to<T>(apply_act(v, act));
+      if (residual) v = v + resj[j];
+    } else if constexpr (NB == 2) {
+      const float sx = kSwap ? sj0[j] : st0;
+      const float sg = kSwap ? st0 : sj0[j], su = kSwap ? st1 : sj1[j];
+      float gate = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sg));
+      gate = round_to<T>(apply_act(gate, act));
+      const float up = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[1][j])), sx * su));
+      v = gate * up;
+    } else {
+      const float sx = kSwap ? sj0[j] : st0, sw = kSwap ? st0 : sj0[j];
+      v = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sw));
+      if (bias) v = round_to<T>(v + bj[j]);
+      if (act >= 0) v = round_to<T>(apply_act(v, act));
+      if (residual) v = v + resj[j];
+    }
+    y[i * ldy + jn] = from_f32<T>(v);
+  }
 }
 
-// index of the CTA whose unit range [c*U/P, (c+1)*U/P) contains unit u
-__device__ __forceinline__ int cta_of_unit(int64_t u, int64_t U, int64_t P) {
-  return static_cast<int>(((u + 1) * P + U - 1) / U - 1);
-}
 
 // Persistent "stream-K" GEMM: the work is the list of (output tile, K block) units, tile-major; CTA c of P
 // owns the contiguous unit range [c*U/P, (c+1)*U/P), so every SM streams the same number of bytes and the TMA
@@ -248,6 +199,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();                                 // the next kernel may be scheduled; it waits on our completion
 
   const CUtensorMap* map_a0 = kSwap ? &tm_w : &tm_x;
   const CUtensorMap* map_a1 = &tm_w2;                   // only when kSwap && NB == 2
@@ -263,6 +215,38 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int tile = static_cast<int>(u_begin / KB);
       int kb = static_cast<int>(u_begin - tile * KB);
       int a0 = (tile % p.tiles_a) * kTileM, b0 = (tile / p.tiles_a) * BN;
+      // The weights never depend on the previous kernel: their tiles for the first ring fill are requested BEFORE
+      // griddepcontrol.wait (so the pipeline fills during the predecessor's tail); the activation tiles after it.
+      const int64_t prefill = min(static_cast<int64_t>(kStages), u_end - u_begin);
+      auto issue = [&](int s, int kc, bool weights, bool acts) {
+        uint8_t* sa = smem + s * S::kStage;
+        uint8_t* sb = sa + S::kA;
+        if (kSwap) {
+          if (weights) {
+            tma_load_2d(sa, &tm_w, full_bar + s, kc, a0, kEvictFirst);
+            if (NB == 2) tma_load_2d(sa + kTileM * kSwizzleBytes, &tm_w2, full_bar + s, kc, a0, kEvictFirst);
+          }
+          if (acts) tma_load_2d(sb, &tm_x, full_bar + s, kc, b0, kEvictLast);
+        } else {
+          if (acts) tma_load_2d(sa, &tm_x, full_bar + s, kc, a0, kEvictLast);
+          if (weights) {
+            tma_load_2d(sb, &tm_w, full_bar + s, kc, b0, kEvictFirst);
+            if (NB == 2) tma_load_2d(sb + BN * kSwizzleBytes, &tm_w2, full_bar + s, kc, b0, kEvictFirst);
+          }
+        }
+      };
+      {
+        int t2 = tile, k2 = kb, a2 = a0, b2 = b0;
+        for (int64_t i = 0; i < prefill; ++i, ++k2) {       // ring is empty at kernel start: no empty-wait needed
+          if (k2 == KB) { k2 = 0; ++t2; a2 = (t2 % p.tiles_a) * kTileM; b2 = (t2 / p.tiles_a) * BN; }
+          const int sv_a0 = a0, sv_b0 = b0;
+          a0 = a2; b0 = b2;
+          mbar_expect_tx(full_bar + i, S::kStage);
+          issue(static_cast<int>(i), k2 * BK, true, false);
+          a0 = sv_a0; b0 = sv_b0;
+        }
+      }
+      griddep_wait();
       for (int64_t u = u_begin; u < u_end; ++u, ++it, ++kb) {
         if (kb == KB) {
           kb = 0;
@@ -272,15 +256,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        mbar_expect_tx(full_bar + s, S::kStage);
-        uint8_t* sa = smem + s * S::kStage;
-        uint8_t* sb = sa + S::kA;
-        const int kc = kb * BK;
-        tma_load_2d(sa, map_a0, full_bar + s, kc, a0, pol_a);
-        if (kSwap && NB == 2) tma_load_2d(sa + kTileM * kSwizzleBytes, map_a1, full_bar + s, kc, a0, pol_a);
-        tma_load_2d(sb, map_b0, full_bar + s, kc, b0, pol_b);
-        if (!kSwap && NB == 2) tma_load_2d(sb + BN * kSwizzleBytes, map_b1, full_bar + s, kc, b0, pol_b);
+        if (it < prefill) {
+          issue(s, kb * BK, false, true);                   // weights of this stage are already in flight
+        } else {
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, S::kStage);
+          issue(s, kb * BK, true, true);
+        }
       }
     }
   } else if (warp == 1) {
@@ -321,6 +303,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
   } else {
     // ===== epilogue warps =====
+    griddep_wait();                                 // scales / residual come from the previous kernels
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int et = threadIdx.x - 64;                // 0..127 among the epilogue threads
     const int64_t ldw = kSwap ? p.rows_a : p.rows_b;                 // row pitch of the [m, n] scratch plane
@@ -339,6 +322,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       tc_fence_after();
       const int64_t arow = a0 + q * 32 + lane;      // M-side row owned by this thread
       const uint32_t taddr = tmem_base + buf * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
+      float* my_slot = p.fslots + (static_cast<int64_t>(blockIdx.x) * 2 + (kb0 > 0 ? 0 : 1)) * (kTileM * BN);
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 32) {
         uint32_t r[NB][32];
@@ -353,22 +337,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           if (lane == 0) mbar_arrive(tmem_empty_bar + buf);
         }
         constexpr int kCols = (BN % 32 == 0) ? 32 : 16;
+        if (direct) {
+          chunk_epilogue<T, KIND, NB, kSwap, kCols>(p, r, arow, b0 + c0);
+        } else {
 #pragma unroll
-        for (int j = 0; j < kCols; ++j) {
-          const int64_t brow = b0 + c0 + j;         // N-side row
-          if (arow >= p.rows_a || brow >= p.rows_b) continue;
-          const int64_t i = kSwap ? brow : arow;    // output row (m)
-          const int64_t jn = kSwap ? arow : brow;   // output column (n)
-          if (direct) {
-            if constexpr (KIND != 0) float_epilogue_store<T>(p.fl, __uint_as_float(r[0][j]), i, jn);
-            else if constexpr (NB == 2) glu_epilogue_store<T>(p.glu, static_cast<int32_t>(r[0][j]), static_cast<int32_t>(r[1][j]), i, jn);
-            else dense_epilogue_store<T>(p.dense, static_cast<int32_t>(r[0][j]), i, jn);
-          } else {
+          for (int j = 0; j < kCols; ++j) {
+            const int64_t brow = b0 + c0 + j;       // N-side row
+            if (arow >= p.rows_a || brow >= p.rows_b) continue;
+            const int64_t i = kSwap ? brow : arow;  // output row (m)
+            const int64_t jn = kSwap ? arow : brow; // output column (n)
             if constexpr (KIND == 0) {
               atomicAdd(p.ws + i * ldw + jn, static_cast<int32_t>(r[0][j]));
               if constexpr (NB == 2) atomicAdd(p.ws + plane + i * ldw + jn, static_cast<int32_t>(r[1][j]));
             } else {
-              atomicAdd(reinterpret_cast<float*>(p.ws) + i * ldw + jn, __uint_as_float(r[0][j]));
+              // float accumulators: no atomics (order-dependent rounding) — each CTA parks its partial tile in its
+              // own slot, [N-side row][128 M-side rows] so that a warp writes 128 contiguous bytes
+              my_slot[static_cast<int64_t>(c0 + j) * kTileM + q * 32 + lane] = __uint_as_float(r[0][j]);
             }
           }
         }
@@ -377,32 +361,47 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       // ---- shared tile: ticket; the last of the contributing CTAs finishes it ----
       __threadfence();
       epi_bar_sync();
-      if (et == 0) {
-        const int contributors = cta_of_unit((tile + 1) * KB - 1, U, P) - cta_of_unit(tile * KB, U, P) + 1;
-        s_last = atomicAdd(p.counters + tile, 1) == contributors - 1;
-      }
+      const int c_lo = cta_of_unit(tile * KB, U, P), c_hi = cta_of_unit((tile + 1) * KB - 1, U, P);
+      if (et == 0) s_last = atomicAdd(p.counters + tile, 1) == c_hi - c_lo;
       epi_bar_sync();
       if (s_last) {
         __threadfence();
-        for (int e = et; e < kTileM * BN; e += 128) {
-          // consecutive threads -> consecutive output columns (n)
-          const int64_t arow2 = kSwap ? a0 + e % kTileM : a0 + e / BN;
-          const int64_t brow2 = kSwap ? b0 + e / kTileM : b0 + e % BN;
-          if (arow2 >= p.rows_a || brow2 >= p.rows_b) continue;
-          const int64_t i = kSwap ? brow2 : arow2, jn = kSwap ? arow2 : brow2;
-          int32_t* w0 = p.ws + i * ldw + jn;
-          const int32_t v = __ldcg(w0);
-          *w0 = 0;
-          if constexpr (KIND != 0) {
-            float_epilogue_store<T>(p.fl, __int_as_float(v), i, jn);
-          } else if constexpr (NB == 2) {
-            int32_t* w1 = w0 + plane;
-            const int32_t v2 = __ldcg(w1);
-            *w1 = 0;
-            glu_epilogue_store<T>(p.glu, v, v2, i, jn);
-          } else {
-            dense_epilogue_store<T>(p.dense, v, i, jn);
+        // thread et finishes M-side row a0+et: gather the reduced accumulators (all loads first), clear the
+        // scratch, then the same chunk epilogue as the direct path
+        constexpr int kColsF = (BN % 32 == 0) ? 32 : 16;
+        const int64_t arow2 = a0 + et;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += kColsF) {
+          uint32_t v[NB][32];
+#pragma unroll
+          for (int j = 0; j < kColsF; ++j) {
+            const int64_t brow2 = b0 + c0 + j;
+            const bool ok = arow2 < p.rows_a && brow2 < p.rows_b;
+            if constexpr (KIND != 0) {
+              float acc = 0.f;
+              if (ok)
+                for (int c = c_lo; c <= c_hi; ++c)    // fixed CTA order => run-to-run deterministic
+                  acc += __ldcg(p.fslots + (static_cast<int64_t>(c) * 2 + (c == c_lo ? 1 : 0)) * (kTileM * BN) +
+                                static_cast<int64_t>(c0 + j) * kTileM + et);
+              v[0][j] = __float_as_uint(acc);
+            } else {
+              const int64_t i = kSwap ? brow2 : arow2, jn = kSwap ? arow2 : brow2;
+#pragma unroll
+              for (int w = 0; w < NB; ++w) v[w][j] = ok ? static_cast<uint32_t>(__ldcg(p.ws + w * plane + i * ldw + jn)) : 0u;
+            }
           }
+          if constexpr (KIND == 0) {
+#pragma unroll
+            for (int j = 0; j < kColsF; ++j) {
+              const int64_t brow2 = b0 + c0 + j;
+              if (arow2 < p.rows_a && brow2 < p.rows_b) {
+                const int64_t i = kSwap ? brow2 : arow2, jn = kSwap ? arow2 : brow2;
+#pragma unroll
+                for (int w = 0; w < NB; ++w) p.ws[w * plane + i * ldw + jn] = 0;
+              }
+            }
+          }
+          chunk_epilogue<T, KIND, NB, kSwap, kColsF>(p, v, arow2, b0 + c0);
         }
         if (et == 0) p.counters[tile] = 0;
       }
@@ -419,34 +418,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }
 
 // ---- host side ----
-PFN_cuTensorMapEncodeTiled_v12000 get_encode_fn() {
-  static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
-  if (!fn) {
-    void* ptr = nullptr;
-    cudaDriverEntryPointQueryResult qres;
-    CT2_CUDA_CHECK(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres));
-    if (qres != cudaDriverEntryPointSuccess || !ptr) throw std::runtime_error("cuTensorMapEncodeTiled is unavailable");
-    fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(ptr);
-  }
-  return fn;
-}
-
-// [rows, k] row-major matrix of `elem` bytes; box = box_rows x 128 bytes, 128B swizzle, zero OOB fill.
-CUtensorMap make_map(const void* base, int64_t rows, int64_t k, int elem, int kind, int box_rows) {
-  CUtensorMap m;
-  const CUtensorMapDataType dt = kind == 0 ? CU_TENSOR_MAP_DATA_TYPE_UINT8
-                               : kind == 1 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
-  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k), static_cast<cuuint64_t>(rows)};
-  cuuint64_t strides[1] = {static_cast<cuuint64_t>(k) * elem};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSwizzleBytes / elem), static_cast<cuuint32_t>(box_rows)};
-  cuuint32_t estr[2] = {1, 1};
-  const CUresult r = get_encode_fn()(&m, dt, 2, const_cast<void*>(base), dims, strides, box, estr,
-                                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
-                                     CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled failed with code " + std::to_string(r));
-  return m;
-}
-
 template <typename T, int KIND, int BN, int NB, bool kSwap>
 void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t n, int64_t k, TcParams p,
                cudaStream_t st) {
@@ -458,9 +429,9 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
     CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S::kBytes)));
     configured = true;
   }
-  const CUtensorMap tmx = make_map(x, m, k, elem, KIND, kSwap ? BN : kTileM);
-  const CUtensorMap tmw = make_map(w, n, k, elem, KIND, kSwap ? kTileM : BN);
-  const CUtensorMap tmw2 = make_map(w2 ? w2 : w, n, k, elem, KIND, kSwap ? kTileM : BN);
+  const CUtensorMap tmx = make_operand_map(x, m, k, elem, KIND, kSwap ? BN : kTileM);
+  const CUtensorMap tmw = make_operand_map(w, n, k, elem, KIND, kSwap ? kTileM : BN);
+  const CUtensorMap tmw2 = make_operand_map(w2 ? w2 : w, n, k, elem, KIND, kSwap ? kTileM : BN);
   p.rows_a = kSwap ? n : m;
   p.rows_b = kSwap ? m : n;
   p.k = k;
@@ -472,12 +443,15 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   const int64_t units = tiles * p.kb_total;
   int64_t ctas = std::min<int64_t>(wsp.sm_count, units);
   // tiles shared between CTAs go through the scratch: fall back to whole tiles per CTA when it cannot hold them
-  const bool scratch_ok = static_cast<size_t>(m) * n * NB <= wsp.accum_elems && static_cast<size_t>(tiles) <= wsp.num_counters;
+  const bool scratch_ok = (KIND == 0 ? static_cast<size_t>(m) * n * NB <= wsp.accum_elems
+                                     : static_cast<size_t>(ctas) * 2 * kTileM * BN <= wsp.accum_elems) &&
+                          static_cast<size_t>(tiles) <= wsp.num_counters;
   p.whole_tiles = scratch_ok ? 0 : 1;
   if (!scratch_ok) ctas = std::min<int64_t>(wsp.sm_count, tiles);   // tile-aligned CTA ranges
   p.ws = wsp.accum;
+  p.fslots = reinterpret_cast<float*>(wsp.accum2);
   p.counters = wsp.counters;
-  kernel<<<static_cast<unsigned>(ctas), kTcThreads, S::kBytes, st>>>(tmx, tmw, tmw2, p);
+  launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kTcThreads), S::kBytes, st, tmx, tmw, tmw2, p);
   check_launch();
 }
 

@@ -47,6 +47,25 @@ void gemm_s8(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, 
 void gemm_s8_glu(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
                  const GluEpilogue& glu, int dtype, int impl, cudaStream_t st);
 
+// awq.cu — AWQ-INT4 in the native (repacked, K-major) layout
+struct AwqNative {
+  const void* wp = nullptr;   // int32 [n, k/8]
+  const void* sc = nullptr;   // f16 [n, k/group]
+  const void* zr = nullptr;   // f16 [n, k/group]
+  int64_t n = 0, k = 0;
+  int group = 128;
+};
+void awq_repack(const int32_t* qweight, const void* scales, const int32_t* qzeros, int layout, int group, int64_t n,
+                int64_t k, int32_t* wp, void* sc, void* zr, cudaStream_t st);
+void awq_dequantize_ref_layout(const int32_t* qweight, const void* scales, const int32_t* qzeros, int layout, int group,
+                               int64_t n, int64_t k, void* w_out, cudaStream_t st);
+void awq_dequantize_native(const AwqNative& w, void* w_out, cudaStream_t st);
+void dense_awq(const void* x, const AwqNative& w, const void* bias, const void* residual, int act, int64_t m, void* y,
+               void* scratch_nk_f16, cudaStream_t st);
+void dense_awq_glu(const void* x, const AwqNative& wg, const AwqNative& wu, int act, int64_t m, void* h,
+                   void* scratch_nk_f16, void* scratch_mn_f16, cudaStream_t st);
+void launch_mul_inplace_f16(void* a_inout, const void* b, int64_t n, cudaStream_t st);
+
 // attention.cu
 int attention_decode_splits(int64_t batch, int Hkv, int64_t max_len, int sm_count);
 size_t attention_decode_workspace_bytes(int64_t batch, int H, int D, int splits);
@@ -71,11 +90,13 @@ void launch_attention_prefill(const void* qkv, const void* kc, const void* vc, c
                               void* out, int dtype, cudaStream_t st);
 
 // decode_loop.cu
+int sample_greedy_chunks(int64_t vocab);
 void launch_sample_greedy(const void* logits, int64_t batch, int64_t vocab, const int32_t* gen, const int32_t* end_ids,
-                          const int32_t* forced, int32_t* next_ids, int32_t* out_ids, int32_t* lens, int dtype,
-                          cudaStream_t st);
+                          const int32_t* forced, int32_t* next_ids, int32_t* out_ids, int32_t* lens, float* part_v,
+                          int32_t* part_i, int32_t* tickets, int dtype, cudaStream_t st);
 void launch_convert_to_f32(const void* x, int64_t n, float* y, int dtype, cudaStream_t st);
 void launch_convert_from_f32(const float* x, int64_t n, void* y, int dtype, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t st);
+void launch_mul_inplace(void* a_inout, const void* b, int64_t n, int dtype, cudaStream_t st);
 
 }  // namespace ct2b200

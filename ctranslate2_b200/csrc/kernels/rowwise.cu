@@ -2,11 +2,21 @@
 // Mul+Quantize, Dequantize (both forms), Rotary, SoftMax, TopK, Gather, INT8 Embeddings.
 // One CTA per row (grid = rows); 16-byte vector accesses whenever the row pitch allows it.
 // Reference kernels these replace are cited per launcher (paths relative to the reference tree).
+#include <cstdlib>
+
 #include "../common.cuh"
 
 namespace ct2b200 {
 
 std::atomic<int64_t> g_kernel_launches{0};
+
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* e = std::getenv("CT2B200_PDL");
+    return !(e && e[0] == '0');
+  }();
+  return on;
+}
 
 constexpr int kRowThreads = 256;
 
@@ -114,6 +124,124 @@ __global__ void __launch_bounds__(kRowThreads) mul_quantize_kernel(const T* __re
 }
 
 // ---------------------------------------------------------------------------------------------
+// Register-resident fast path of the three "-> int8 row" producers of the decode step:
+//   MODE 0: Quantize(x)      MODE 1: Quantize(T(RMSNorm(x, gamma)))      MODE 2: Quantize(T(a * b))
+//   MODE 3: T(RMSNorm(x, gamma)) written as T (same summation order as MODE 1, so 1 == Quantize o 3 bit-exactly)
+// One CTA per row; the row is read ONCE with 16-byte loads and kept in registers (NV vectors per thread), so the
+// kernel is one global round trip + two block reductions instead of three passes (bit-identical results).
+// ---------------------------------------------------------------------------------------------
+template <typename T, int MODE, int NV>
+__global__ void __launch_bounds__(kRowThreads) row_to_int8_kernel(const T* __restrict__ x, const T* __restrict__ aux,
+                                                                  int64_t cols, float eps, bool use_residual,
+                                                                  int8_t* __restrict__ q, float* __restrict__ scale,
+                                                                  T* __restrict__ y_out) {
+  constexpr int N = Vec16<T>::N;
+  __shared__ float red[32];
+  griddep_launch();
+  griddep_wait();
+  const int64_t row = blockIdx.x;
+  const T* xr = x + row * cols;
+  const int64_t nv = cols / N;
+  float v[NV][N];
+  bool have[NV];
+#pragma unroll
+  for (int k = 0; k < NV; ++k) {
+    const int64_t vi = threadIdx.x + static_cast<int64_t>(k) * kRowThreads;
+    have[k] = vi < nv;
+    if (have[k]) {
+      const Vec16<T> d = ld16(xr + vi * N);
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[k][i] = to_f32(d.v[i]);
+    } else {
+#pragma unroll
+      for (int i = 0; i < N; ++i) v[k][i] = 0.f;
+    }
+  }
+  if constexpr (MODE == 2) {
+    const T* br = aux + row * cols;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (have[k]) {
+        const Vec16<T> d = ld16(br + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N);
+#pragma unroll
+        for (int i = 0; i < N; ++i) v[k][i] = round_to<T>(v[k][i] * to_f32(d.v[i]));
+      }
+  }
+  if constexpr (MODE == 1 || MODE == 3) {
+    Vec16<T> gv[NV];
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (have[k]) gv[k] = ld16(aux + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N);
+    float ss = 0.f;
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+#pragma unroll
+      for (int i = 0; i < N; ++i) ss += v[k][i] * v[k][i];
+    // NOTE: the summation order differs from the 3-pass kernel, so `inv` may differ in the last ulp from
+    // rms_norm_kernel; both are valid fp32 evaluations of the same reference formula (fp tolerance class).
+    ss = block_reduce<false>(ss, red);
+    const float inv = rsqrtf(ss / static_cast<float>(cols) + eps);
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (have[k]) {
+#pragma unroll
+        for (int i = 0; i < N; ++i) {
+          const float g = to_f32(gv[k].v[i]) + (use_residual ? 1.f : 0.f);
+          v[k][i] = round_to<T>(v[k][i] * inv * g);
+        }
+      }
+  }
+  if constexpr (MODE == 3) {
+#pragma unroll
+    for (int k = 0; k < NV; ++k)
+      if (have[k]) {
+        Vec16<T> o;
+#pragma unroll
+        for (int i = 0; i < N; ++i) o.v[i] = from_f32<T>(v[k][i]);
+        st16(y_out + row * cols + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N, o);
+      }
+    return;
+  }
+  float amax = 0.f;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+#pragma unroll
+    for (int i = 0; i < N; ++i) amax = fmaxf(amax, fabsf(v[k][i]));
+  amax = block_reduce<true>(amax, red);
+  const float s = amax != 0.f ? 127.f / amax : 1.f;
+  int8_t* qr = q + row * cols;
+#pragma unroll
+  for (int k = 0; k < NV; ++k)
+    if (have[k]) {
+      int8_t out[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) out[i] = static_cast<int8_t>(nearbyintf(v[k][i] * s));
+      int8_t* dst = qr + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N;
+      if constexpr (N == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(out);
+      else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(out);
+    }
+  if (threadIdx.x == 0) scale[row] = s;
+}
+
+// returns false when the shape/alignment is not covered (caller falls back to the generic kernels)
+template <typename T, int MODE>
+bool launch_row_to_int8(const T* x, const T* aux, int64_t rows, int64_t cols, float eps, bool use_residual, int8_t* q,
+                        float* scale, cudaStream_t st, T* y_out = nullptr) {
+  constexpr int N = Vec16<T>::N;
+  if (cols % N != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) ||
+      (reinterpret_cast<uintptr_t>(q) & 7) || (reinterpret_cast<uintptr_t>(y_out) & 15))
+    return false;
+  const int64_t nv = cols / N;
+  const int per = static_cast<int>((nv + kRowThreads - 1) / kRowThreads);
+  if (per <= 1) launch_pdl(row_to_int8_kernel<T, MODE, 1>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
+  else if (per <= 2) launch_pdl(row_to_int8_kernel<T, MODE, 2>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
+  else if (per <= 4) launch_pdl(row_to_int8_kernel<T, MODE, 4>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
+  else if (per <= 8) launch_pdl(row_to_int8_kernel<T, MODE, 8>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
+  else return false;
+  return true;
+}
+
+// ---------------------------------------------------------------------------------------------
 // ops::Dequantize  (src/ops/dequantize_gpu.cu:16-27 rows form, :30-144 GEMM-output form)
 // ---------------------------------------------------------------------------------------------
 template <typename T>
@@ -135,6 +263,8 @@ __global__ void dequantize_gemm_output_kernel(const int32_t* __restrict__ c, Den
 template <typename T>
 __global__ void embedding_s8_kernel(const int8_t* __restrict__ w, const float* __restrict__ scale,
                                     const int32_t* __restrict__ ids, int64_t depth, T* __restrict__ y) {
+  griddep_launch();
+  griddep_wait();
   const int64_t i = blockIdx.x;
   const int64_t id = ids[i];
   const float s = scale[id];
@@ -271,8 +401,11 @@ __global__ void __launch_bounds__(1024) topk_kernel(const T* __restrict__ x, int
 void launch_quantize_rows(const void* x, int dtype, int64_t rows, int64_t cols, bool round, int8_t* q,
                           float* scale, cudaStream_t st) {
   if (rows == 0) return;
-  CT2_DISPATCH_DTYPE(dtype, (quantize_rows_kernel<T><<<rows, kRowThreads, 0, st>>>(
-                                static_cast<const T*>(x), cols, round, q, scale)));
+  bool done = false;
+  if (round) CT2_DISPATCH_DTYPE(dtype, (done = launch_row_to_int8<T, 0>(static_cast<const T*>(x), nullptr, rows, cols, 0.f, false, q, scale, st)));
+  if (!done)
+    CT2_DISPATCH_DTYPE(dtype, (quantize_rows_kernel<T><<<rows, kRowThreads, 0, st>>>(
+                                  static_cast<const T*>(x), cols, round, q, scale)));
   check_launch();
 }
 
@@ -280,13 +413,19 @@ void launch_rms_norm(const void* gamma, const void* x, int64_t rows, int64_t col
                      void* y, int8_t* q, float* scale, int dtype, cudaStream_t st) {
   if (rows == 0) return;
   if (q) {
-    CT2_DISPATCH_DTYPE(dtype, (rms_norm_kernel<T, true><<<rows, kRowThreads, 0, st>>>(
-                                  static_cast<const T*>(gamma), static_cast<const T*>(x), cols, eps,
-                                  use_residual, nullptr, q, scale)));
+    bool done = false;
+    CT2_DISPATCH_DTYPE(dtype, (done = launch_row_to_int8<T, 1>(static_cast<const T*>(x), static_cast<const T*>(gamma), rows, cols, eps, use_residual, q, scale, st)));
+    if (!done)
+      CT2_DISPATCH_DTYPE(dtype, (rms_norm_kernel<T, true><<<rows, kRowThreads, 0, st>>>(
+                                    static_cast<const T*>(gamma), static_cast<const T*>(x), cols, eps,
+                                    use_residual, nullptr, q, scale)));
   } else {
-    CT2_DISPATCH_DTYPE(dtype, (rms_norm_kernel<T, false><<<rows, kRowThreads, 0, st>>>(
-                                  static_cast<const T*>(gamma), static_cast<const T*>(x), cols, eps,
-                                  use_residual, static_cast<T*>(y), nullptr, nullptr)));
+    bool done = false;
+    CT2_DISPATCH_DTYPE(dtype, (done = launch_row_to_int8<T, 3>(static_cast<const T*>(x), static_cast<const T*>(gamma), rows, cols, eps, use_residual, nullptr, nullptr, st, static_cast<T*>(y))));
+    if (!done)
+      CT2_DISPATCH_DTYPE(dtype, (rms_norm_kernel<T, false><<<rows, kRowThreads, 0, st>>>(
+                                    static_cast<const T*>(gamma), static_cast<const T*>(x), cols, eps,
+                                    use_residual, static_cast<T*>(y), nullptr, nullptr)));
   }
   check_launch();
 }
@@ -294,8 +433,11 @@ void launch_rms_norm(const void* gamma, const void* x, int64_t rows, int64_t col
 void launch_mul_quantize(const void* a, const void* b, int64_t rows, int64_t cols, int8_t* q, float* scale,
                          int dtype, cudaStream_t st) {
   if (rows == 0) return;
-  CT2_DISPATCH_DTYPE(dtype, (mul_quantize_kernel<T><<<rows, kRowThreads, 0, st>>>(
-                                static_cast<const T*>(a), static_cast<const T*>(b), cols, q, scale)));
+  bool done = false;
+  CT2_DISPATCH_DTYPE(dtype, (done = launch_row_to_int8<T, 2>(static_cast<const T*>(a), static_cast<const T*>(b), rows, cols, 0.f, false, q, scale, st)));
+  if (!done)
+    CT2_DISPATCH_DTYPE(dtype, (mul_quantize_kernel<T><<<rows, kRowThreads, 0, st>>>(
+                                  static_cast<const T*>(a), static_cast<const T*>(b), cols, q, scale)));
   check_launch();
 }
 
@@ -316,8 +458,8 @@ void launch_dequantize_gemm_output(const int32_t* c, const DenseEpilogue& e, int
 void launch_embedding_s8(const int8_t* w, const float* scale, const int32_t* ids, int64_t num_ids, int64_t depth,
                          void* y, int dtype, cudaStream_t st) {
   if (num_ids == 0) return;
-  CT2_DISPATCH_DTYPE(dtype, (embedding_s8_kernel<T><<<num_ids, 256, 0, st>>>(w, scale, ids, depth,
-                                                                           static_cast<T*>(y))));
+  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(embedding_s8_kernel<T>, dim3(num_ids), dim3(256), 0, st, w, scale, ids, depth,
+                                        static_cast<T*>(y))));
   check_launch();
 }
 

@@ -273,3 +273,65 @@ def attention_prefill(qkv, k_cache, v_cache, sin, cos, batch, time, offset, num_
                                           num_heads, num_heads_kv, head_dim, ctypes.c_int64(max_len), int(interleave),
                                           ctypes.c_float(scale), _p(out), _dt(qkv), _stream()))
     return out
+
+
+# ---------------- AWQ-INT4 (ops::GemmAwq / GemvAwq / DequantizeAwq) ----------------
+AWQ_GEMM, AWQ_GEMV = 1, 2
+
+
+class AwqWeight:
+    """AWQ weight of a Dense layer repacked ONCE into the native K-major layout (ct2b200_awq_repack)."""
+    def __init__(self, qweight, scales, qzeros, layout: int, group_size: int):
+        qweight, scales, qzeros = _c(qweight), _c(scales), _c(qzeros)
+        if layout == AWQ_GEMM:
+            self.k, self.n = qweight.shape[0], qweight.shape[1] * 8
+        elif layout == AWQ_GEMV:
+            self.n, self.k = qweight.shape[0], qweight.shape[1] * 8
+        else:
+            raise ValueError("AWQ layout must be 1 (AWQ_GEMM) or 2 (AWQ_GEMV)")
+        self.group_size = group_size
+        ng = self.k // group_size
+        dev = qweight.device
+        self.wp = torch.empty((self.n, self.k // 8), dtype=torch.int32, device=dev)
+        self.sc = torch.empty((self.n, ng), dtype=torch.float16, device=dev)
+        self.zr = torch.empty((self.n, ng), dtype=torch.float16, device=dev)
+        check(lib().ct2b200_awq_repack(_p(qweight), _p(scales), _p(qzeros), layout, group_size, ctypes.c_int64(self.n),
+                                       ctypes.c_int64(self.k), _p(self.wp), _p(self.sc), _p(self.zr), _stream()))
+
+
+def dequantize_awq(qweight, scales, qzeros, layout: int, group_size: int):
+    """ops::DequantizeAwq: reference layout -> W float16 [K, N]."""
+    qweight = _c(qweight)
+    if layout == AWQ_GEMM:
+        k, n = qweight.shape[0], qweight.shape[1] * 8
+    else:
+        n, k = qweight.shape[0], qweight.shape[1] * 8
+    w = torch.empty((k, n), dtype=torch.float16, device=qweight.device)
+    check(lib().ct2b200_dequantize_awq(_p(qweight), _p(_c(scales)), _p(_c(qzeros)), layout, group_size,
+                                       ctypes.c_int64(n), ctypes.c_int64(k), _p(w), _stream()))
+    return w
+
+
+def dense_awq(x, w: AwqWeight, bias=None, residual=None, activation_type=None):
+    """ops::GemmAwq / GemvAwq (+bias, activation, residual) on a repacked weight; x float16 [m, k]."""
+    x = _c(x)
+    m = x.shape[0]
+    y = torch.empty((m, w.n), dtype=torch.float16, device=x.device)
+    scratch = torch.empty((w.n, w.k), dtype=torch.float16, device=x.device) if m > 64 else None
+    act = -1 if activation_type is None else activation_type
+    check(lib().ct2b200_dense_awq(_p(x), _p(w.wp), _p(w.sc), _p(w.zr), w.group_size, _p(bias), _p(residual), act,
+                                  ctypes.c_int64(m), ctypes.c_int64(w.n), ctypes.c_int64(w.k), _p(y), _p(scratch),
+                                  _stream()))
+    return y
+
+
+def dense_awq_glu(x, wg: AwqWeight, wu: AwqWeight, activation_type=ActivationType.Swish):
+    x = _c(x)
+    m = x.shape[0]
+    h = torch.empty((m, wg.n), dtype=torch.float16, device=x.device)
+    s1 = torch.empty((wg.n, wg.k), dtype=torch.float16, device=x.device) if m > 64 else None
+    s2 = torch.empty((m, wg.n), dtype=torch.float16, device=x.device) if m > 64 else None
+    check(lib().ct2b200_dense_awq_glu(_p(x), _p(wg.wp), _p(wg.sc), _p(wg.zr), _p(wu.wp), _p(wu.sc), _p(wu.zr),
+                                      wg.group_size, activation_type, ctypes.c_int64(m), ctypes.c_int64(wg.n),
+                                      ctypes.c_int64(wg.k), _p(h), _p(s1), _p(s2), _stream()))
+    return h

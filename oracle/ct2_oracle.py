@@ -4,9 +4,9 @@ TEST INFRASTRUCTURE — NOT PRODUCT CODE.  Only `tests/`, `__graft_entry__.smoke
 bench.py's `cpu_baseline` / `--impl reference` legs may import this module; the product
 (`ctranslate2_b200`) never does and fails loudly when its CUDA library is missing.
 
-Parity status: PINNED.  Every function below is checked (tests/test_oracle_*.py, `-m "not gpu"`)
+Parity status: PINNED.  Every function below is checked (tests/test_oracle.py, `-m "not gpu"`)
 against (a) the golden vectors the reference's own gtests hold for this path (tests/golden/
-ref_ops_vectors.py, transcribed from /root/reference/tests/ops_test.cc and layers_test.cc) and
+ref_gtest_vectors.json, extracted from /root/reference/tests/ops_test.cc and layers_test.cc) and
 (b) outputs of the UNMODIFIED reference compiled by oracle/Makefile.ref (oracle/_ref), whose
 fixtures are committed under tests/golden/ by tools/make_golden.py.
 
@@ -391,6 +391,8 @@ class DecoderWeights:
     rotary_high_freq_factor: float = 4.0
     original_max_position_embeddings: int = 0
     flavor: str = "cpu"   # dequantize arithmetic flavor
+    awq_layout: int = 0   # config.json quantization_type: 1 = AWQ_GEMM, 2 = AWQ_GEMV (src/models/model.cc:636-637)
+    awq_group: int = 128
 
     @staticmethod
     def from_dir(model_dir: str, flavor: str = "cpu") -> "DecoderWeights":
@@ -419,7 +421,8 @@ class DecoderWeights:
             rotary_low_freq_factor=float(get("rotary_low_freq_factor", 1.0)),
             rotary_high_freq_factor=float(get("rotary_high_freq_factor", 4.0)),
             original_max_position_embeddings=int(get("original_max_position_embeddings", 0)),
-            flavor=flavor)
+            flavor=flavor, awq_layout=int(cfg.get("quantization_type") or 0),
+            awq_group=int(cfg.get("quantization_group_size") or 128))
 
 
 class LlamaOracle:
@@ -455,6 +458,21 @@ class LlamaOracle:
         bias = v.get(prefix + "/bias")
         if wq.dtype == np.int8:
             return dense_int8(x, wq, v[prefix + "/weight_scale"], bias, act, residual, self.w.flavor)
+        if wq.dtype == np.int32:                  # AWQ arms, common.cc:402-438 (weights dequantized to fp16)
+            sc, zr = v[prefix + "/weight_scale"], v[prefix + "/weight_zero"]
+            x2 = x.reshape(-1, x.shape[-1])
+            if self.w.awq_layout == 1:
+                deq = awq_dequantize_gemm(wq, sc, zr).astype(np.float16).astype(f32)          # [K, N]
+                y = x2.astype(f32) @ deq
+            else:
+                y = awq_gemv(x2, wq, sc, zr, self.w.awq_group)
+            y = y.reshape(x.shape[:-1] + (y.shape[-1],))
+            if bias is not None:
+                y = y + bias.astype(f32)
+            y = activation(y, act)
+            if residual is not None:
+                y = y + residual
+            return y.astype(f32)
         y = x.astype(f32) @ wq.astype(f32).T      # float arm, common.cc:440
         if bias is not None:
             y = y + bias.astype(f32)

@@ -125,3 +125,27 @@ def test_errors():
         g.generate_batch([[1, 2, 3]], max_length=64)             # exceeds the KV arena
     with pytest.raises(ValueError):
         g.generate_batch([[1, 2, 3]], max_length=4, beam_size=4)
+
+
+@gpu
+@pytest.mark.parametrize("quant", ["awq_gemm", "awq_gemv", "float16", "bfloat16"])
+def test_awq_and_float_models_vs_oracle(tmp_path, quant):
+    """AWQ-INT4 (both reference layouts) and float16/bfloat16-weight model dirs: logits vs the oracle, greedy
+    tokens stable across prefill/decode splits."""
+    d = str(tmp_path / quant)
+    cfg = LlamaConfig(num_layers=2, num_heads=8, num_heads_kv=2, head_dim=128, ffn_dim=1024, vocab_size=1000)
+    write_llama_model(d, cfg, quant, seed=5, init_std=0.05)
+    w = O.DecoderWeights.from_dir(d, "cuda")
+    m = O.LlamaOracle(w)
+    prompts = np.random.default_rng(4).integers(3, 1000, size=(2, 20))
+    m.reset(2)
+    ref = m.forward(prompts, 0)
+    ctype = "bfloat16" if quant == "bfloat16" else "float16"
+    g = ct2.Generator(d, compute_type=ctype, max_batch_size=2, max_length=128)
+    logits = g.forward_batch(prompts.tolist())
+    tol = 1.5e-1 if quant == "bfloat16" else 4e-2
+    assert rel_rms(logits, ref) <= tol / 3, rel_rms(logits, ref)
+    assert np.abs(logits - ref).max() <= tol * max(1.0, np.abs(ref).max()), np.abs(logits - ref).max()
+    a = g.generate_batch(prompts.tolist(), max_length=8, min_length=8, end_token=[2])
+    b = g.generate_batch(prompts.tolist(), max_length=8, min_length=8, end_token=[2])
+    assert [r.sequences_ids[0] for r in a] == [r.sequences_ids[0] for r in b]      # deterministic
