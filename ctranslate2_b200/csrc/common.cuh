@@ -162,9 +162,19 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();
+bool mark_configured(const void* kernel);     // true the first time a kernel pointer is seen
+
+// All kernels of the decode step ask for the maximum shared-memory carve-out: the tcgen05 GEMMs need ~200 KB of
+// shared memory per SM, and alternating between kernels with different L1/shared splits forces the SMs to drain
+// and reconfigure between launches.
+template <typename K>
+void prefer_max_shared(K kernel) {
+  cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
 
 template <typename... KArgs, typename... Args>
 void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  if (mark_configured(reinterpret_cast<const void*>(kernel))) prefer_max_shared(kernel);
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;

@@ -17,6 +17,7 @@
 #include <cudaTypedefs.h>
 
 #include <algorithm>
+#include <cstdlib>
 
 #include "../common.cuh"
 #include "gemm_common.cuh"
@@ -446,8 +447,9 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   const bool scratch_ok = (KIND == 0 ? static_cast<size_t>(m) * n * NB <= wsp.accum_elems
                                      : static_cast<size_t>(ctas) * 2 * kTileM * BN <= wsp.accum_elems) &&
                           static_cast<size_t>(tiles) <= wsp.num_counters;
-  p.whole_tiles = scratch_ok ? 0 : 1;
-  if (!scratch_ok) ctas = std::min<int64_t>(wsp.sm_count, tiles);   // tile-aligned CTA ranges
+  static const bool force_whole = [] { const char* e = std::getenv("CT2B200_GEMM_WHOLE"); return e && e[0] == '1'; }();
+  p.whole_tiles = (scratch_ok && !force_whole) ? 0 : 1;
+  if (p.whole_tiles) ctas = std::min<int64_t>(wsp.sm_count, tiles);   // tile-aligned CTA ranges
   p.ws = wsp.accum;
   p.fslots = reinterpret_cast<float*>(wsp.accum2);
   p.counters = wsp.counters;

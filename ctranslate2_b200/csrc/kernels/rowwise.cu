@@ -3,12 +3,21 @@
 // One CTA per row (grid = rows); 16-byte vector accesses whenever the row pitch allows it.
 // Reference kernels these replace are cited per launcher (paths relative to the reference tree).
 #include <cstdlib>
+#include <mutex>
+#include <unordered_set>
 
 #include "../common.cuh"
 
 namespace ct2b200 {
 
 std::atomic<int64_t> g_kernel_launches{0};
+
+bool mark_configured(const void* kernel) {
+  static std::mutex mu;
+  static std::unordered_set<const void*> seen;
+  std::lock_guard<std::mutex> lock(mu);
+  return seen.insert(kernel).second;
+}
 
 bool pdl_enabled() {
   static const bool on = [] {
