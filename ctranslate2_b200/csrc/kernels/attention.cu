@@ -12,6 +12,7 @@
 #include <algorithm>
 
 #include "../common.cuh"
+#include "kernels.h"
 
 namespace ct2b200 {
 
@@ -354,7 +355,7 @@ int attention_decode_splits(int64_t batch, int Hkv, int64_t max_len, int sm_coun
   int s = static_cast<int>((2 * sm_count + ctas - 1) / ctas);
   const int max_s = static_cast<int>(std::max<int64_t>(1, max_len / 64));
   if (s > max_s) s = max_s;
-  if (s > 32) s = 32;
+  if (s > 16) s = 16;
   if (s < 1) s = 1;
   return s;
 }
@@ -376,6 +377,9 @@ void launch_attention_decode(const void* qkv, void* kc, void* vc, const float* s
   int32_t* tickets = static_cast<int32_t*>(workspace);
   const size_t toff = ((static_cast<size_t>(batch) * H * sizeof(int32_t) + 255) / 256) * 256;
   float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + toff);
+  if (launch_attention_decode_mma(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, D, max_len, interleave, scale, out, partials,
+                                  tickets, splits, dtype, st))
+    return;
 #define CT2_DEC(DV)                                                                                          \
   CT2_DISPATCH_DTYPE(dtype, (launch_decode_g<T, DV>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len,       \
                                                      interleave, scale, out, partials, tickets, splits, st)))

@@ -9,6 +9,7 @@
 #include <type_traits>
 
 #include <cstdlib>
+#include <string>
 
 #include "../common.cuh"
 #include "kernels.h"
@@ -214,6 +215,247 @@ __global__ void __launch_bounds__(kThreads)
   }
 }
 
+
+// Combine of the split partials by the last CTA of a (batch, kv-head): two batched load phases instead of a
+// per-split dependent chain.  `scratch` = shared floats, at least 2*G*64 + G.
+template <typename T, int D, int G>
+__device__ __forceinline__ void decode_combine(const float* part, int nsplit, T* out_row, float* scratch) {
+  const size_t PS = static_cast<size_t>(D) + 2;
+  float* sm = scratch;                 // [G][nsplit] max
+  float* sl = scratch + G * 64;        // [G][nsplit] sum
+  float* sw = scratch + 2 * G * 64;    // [G] final 1/l
+  __syncthreads();
+  for (int e = threadIdx.x; e < G * nsplit; e += blockDim.x) {
+    const int h = e / nsplit, s = e % nsplit;
+    sm[h * 64 + s] = __ldcg(part + (static_cast<int64_t>(h) * nsplit + s) * PS + D);
+    sl[h * 64 + s] = __ldcg(part + (static_cast<int64_t>(h) * nsplit + s) * PS + D + 1);
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    const int h = threadIdx.x;
+    float mm = -INFINITY;
+    for (int s = 0; s < nsplit; ++s) mm = fmaxf(mm, sm[h * 64 + s]);
+    float ll = 0.f;
+    for (int s = 0; s < nsplit; ++s) {
+      const float c = sm[h * 64 + s] == -INFINITY ? 0.f : exp2f(sm[h * 64 + s] - mm);
+      sm[h * 64 + s] = c;              // weight of split s
+      ll += sl[h * 64 + s] * c;
+    }
+    sw[h] = 1.f / ll;
+  }
+  __syncthreads();
+  for (int e = threadIdx.x; e < G * D; e += blockDim.x) {
+    const int h = e / D, i = e % D;
+    const float* ph = part + static_cast<int64_t>(h) * nsplit * PS + i;
+    float a = 0.f;
+#pragma unroll 8
+    for (int s = 0; s < nsplit; ++s) a += __ldcg(ph + s * PS) * sm[h * 64 + s];
+    out_row[h * D + i] = from_f32<T>(a * sw[h]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Decode attention on tensor cores (one new token per sequence).  Same split-KV scheme and partial/ticket
+// protocol as attention_decode_kernel (attention.cu), but the inner loop is MMA based: the G query heads of a KV
+// head are rows 0..G-1 of a 16-row A tile, a CTA streams 64-key K/V tiles of its slice through shared memory with
+// cp.async (3 stages), warp w owns keys [16w, 16w+16) of every tile: S = Q K^T (16 mma), fp32 online softmax,
+// O += P V (16 mma).  ~2 tensor instructions per key instead of ~60 SIMT instructions, so the kernel is bound by
+// the 16-byte coalesced cache reads, not by issue slots.
+// ---------------------------------------------------------------------------------------------
+constexpr int kDecTile = 64, kDecStages = 3;
+
+__host__ __device__ inline size_t dec_partial_stride(int D) { return static_cast<size_t>(D) + 2; }
+
+template <typename T>
+__device__ __forceinline__ float rope_at_mma(const T* x, const float* sin, const float* cos, int i, int D, bool interleave) {
+  float other;
+  if (interleave) other = (i & 1) ? to_f32(x[i - 1]) : -to_f32(x[i + 1]);
+  else other = (i < D / 2) ? -to_f32(x[i + D / 2]) : to_f32(x[i - D / 2]);
+  return to_f32(x[i]) * cos[i] + other * sin[i];
+}
+
+template <typename T, int D, int G>
+__global__ void __launch_bounds__(kThreads)
+    attention_decode_mma_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
+                                const float* __restrict__ sin_t, const float* __restrict__ cos_t,
+                                const int32_t* __restrict__ lens, int H, int Hkv, int64_t max_len, bool interleave,
+                                float scale_log2, T* __restrict__ out, float* __restrict__ partials,
+                                int32_t* __restrict__ tickets) {
+  constexpr int LD = D + 8, CH = D / 8, NW = kThreads / 32;
+  extern __shared__ __align__(16) uint8_t smem_raw[];
+  T* sK = reinterpret_cast<T*>(smem_raw);                       // [stages][64][LD]
+  T* sV = sK + kDecStages * kDecTile * LD;                      // [stages][64][LD]
+  float* s_q = reinterpret_cast<float*>(sV + kDecStages * kDecTile * LD);   // [G][D]  (reused for the warp merge)
+  __shared__ float s_m[NW][G], s_l[NW][G];
+  __shared__ bool s_last;
+
+  griddep_launch();
+  griddep_wait();
+  const int split = blockIdx.x, nsplit = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t = lane & 3;
+  const int pos = lens[b];
+  const int nkeys = pos + 1;
+  const int64_t row_w = static_cast<int64_t>(H + 2 * Hkv) * D;
+  const T* q_in = qkv + b * row_w + static_cast<int64_t>(kvh) * G * D;
+  const T* k_in = qkv + b * row_w + static_cast<int64_t>(H) * D + static_cast<int64_t>(kvh) * D;
+  const T* v_in = k_in + static_cast<int64_t>(Hkv) * D;
+  T* kc = k_cache + (static_cast<int64_t>(b) * Hkv + kvh) * max_len * D;
+  T* vc = v_cache + (static_cast<int64_t>(b) * Hkv + kvh) * max_len * D;
+  const float* sn = sin_t + static_cast<int64_t>(pos) * D;
+  const float* cs = cos_t + static_cast<int64_t>(pos) * D;
+
+  int per = (nkeys + nsplit - 1) / nsplit;
+  per = ((per + kDecTile - 1) / kDecTile) * kDecTile;           // slices are whole 64-key tiles
+  const int s0 = split * per;
+  const int s1 = min(nkeys, s0 + per);
+  const int ntiles = s1 > s0 ? (s1 - s0 + kDecTile - 1) / kDecTile : 0;
+
+  for (int e = tid; e < G * D; e += kThreads) {
+    const int h = e / D, i = e % D;
+    s_q[e] = rope_at_mma(q_in + h * D, sn, cs, i, D, interleave) * scale_log2;
+  }
+  if (pos >= s0 && pos < s1) {                                  // the owner of position `pos` appends k_new / v_new
+    for (int i = tid; i < D; i += kThreads) {
+      kc[static_cast<int64_t>(pos) * D + i] = from_f32<T>(rope_at_mma(k_in, sn, cs, i, D, interleave));
+      vc[static_cast<int64_t>(pos) * D + i] = v_in[i];
+    }
+  }
+  __syncthreads();
+
+  auto load_tile = [&](int stage, int kt) {
+    const int64_t k0 = s0 + static_cast<int64_t>(kt) * kDecTile;
+    for (int c = tid; c < kDecTile * CH; c += kThreads) {
+      const int r = c / CH, ch = c % CH;
+      const bool ok = k0 + r < s1;
+      const int64_t off = (ok ? k0 + r : s0) * D + ch * 8;
+      cp16(sK + (stage * kDecTile + r) * LD + ch * 8, kc + off, ok);
+      cp16(sV + (stage * kDecTile + r) * LD + ch * 8, vc + off, ok);
+    }
+  };
+#pragma unroll
+  for (int st = 0; st < kDecStages - 1; ++st) {
+    if (st < ntiles) load_tile(st, st);
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+
+  // Q as A fragments: rows 0..G-1 = heads, rows G..15 = 0
+  uint32_t qf[D / 16][4];
+#pragma unroll
+  for (int kk = 0; kk < D / 16; ++kk) {
+    const float* qr = s_q + g * D + kk * 16 + 2 * t;
+    const bool real = g < G;
+    qf[kk][0] = real ? pack2<T>(qr[0], qr[1]) : 0u;
+    qf[kk][1] = 0u;
+    qf[kk][2] = real ? pack2<T>(qr[8], qr[9]) : 0u;
+    qf[kk][3] = 0u;
+  }
+  float o[D / 8][2];                                            // only rows g (< 8) are kept: c0, c1 of each n-tile
+#pragma unroll
+  for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = 0.f;
+  float m_run = -INFINITY, l_run = 0.f;
+
+  for (int kt = 0; kt < ntiles; ++kt) {
+    const int stage = kt % kDecStages;
+    if (kt + kDecStages - 1 < ntiles) load_tile((kt + kDecStages - 1) % kDecStages, kt + kDecStages - 1);
+    asm volatile("cp.async.commit_group;\n" ::);
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kDecStages - 1));
+    __syncthreads();
+    const T* ks = sK + stage * kDecTile * LD + warp * 16 * LD;   // this warp's 16 keys
+    const T* vs = sV + stage * kDecTile * LD + warp * 16 * LD;
+    float s[2][4];
+#pragma unroll
+    for (int j = 0; j < 2; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+    for (int kk = 0; kk < D / 16; ++kk) {
+      uint32_t bf[4];
+      ldsm4(bf, ks + ((lane & 7) + (lane >> 4) * 8) * LD + kk * 16 + ((lane >> 3) & 1) * 8);
+      mma16816<T>(s[0], qf[kk], bf[0], bf[1]);
+      mma16816<T>(s[1], qf[kk], bf[2], bf[3]);
+    }
+    // online softmax over this warp's 16 keys (row g; rows >= G carry zeros and are ignored)
+    const int kbase = s0 + kt * kDecTile + warp * 16;
+    float mx = m_run;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const int key = kbase + j * 8 + 2 * t + r;
+        s[j][r] = key < s1 ? s[j][r] : -INFINITY;
+        mx = fmaxf(mx, s[j][r]);
+      }
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+    const float corr = (mx == -INFINITY) ? 1.f : exp2f(m_run - mx);
+    m_run = mx;
+    float rs = 0.f;
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        const float pv = (s[j][r] == -INFINITY) ? 0.f : exp2f(s[j][r] - mx);
+        s[j][r] = pv;
+        rs += pv;
+      }
+    l_run = l_run * corr + rs;
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
+    uint32_t pa[4] = {pack2<T>(s[0][0], s[0][1]), 0u, pack2<T>(s[1][0], s[1][1]), 0u};
+#pragma unroll
+    for (int j = 0; j < D / 8; j += 2) {
+      uint32_t bf[4];
+      ldsm4_t(bf, vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * LD + j * 8 + (lane >> 4) * 8);
+      float c0[4] = {o[j][0], o[j][1], 0.f, 0.f}, c1[4] = {o[j + 1][0], o[j + 1][1], 0.f, 0.f};
+      mma16816<T>(c0, pa, bf[0], bf[1]);
+      mma16816<T>(c1, pa, bf[2], bf[3]);
+      o[j][0] = c0[0]; o[j][1] = c0[1];
+      o[j + 1][0] = c1[0]; o[j + 1][1] = c1[1];
+    }
+    __syncthreads();
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+
+  // ---- merge the 4 warps (each holds m, l, O for rows g < G over its keys) ----
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
+  l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
+  if (g < G && t == 0) { s_m[warp][g] = m_run; s_l[warp][g] = l_run; }
+  float* s_o = reinterpret_cast<float*>(smem_raw);              // [NW][G][D] fp32, reuses the K/V staging area
+  __syncthreads();                                              // all tiles consumed before the area is reused
+  if (g < G) {
+#pragma unroll
+    for (int j = 0; j < D / 8; ++j) {
+      s_o[(warp * G + g) * D + j * 8 + 2 * t] = o[j][0];
+      s_o[(warp * G + g) * D + j * 8 + 2 * t + 1] = o[j][1];
+    }
+  }
+  __syncthreads();
+  const size_t PS = dec_partial_stride(D);
+  float* part = partials + ((static_cast<int64_t>(b) * H + static_cast<int64_t>(kvh) * G) * nsplit) * PS;
+  for (int e = tid; e < G * D; e += kThreads) {
+    const int h = e / D, i = e % D;
+    float mm = -INFINITY;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) mm = fmaxf(mm, s_m[w][h]);
+    float ll = 0.f, a = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) {
+      const float c = s_m[w][h] == -INFINITY ? 0.f : exp2f(s_m[w][h] - mm);
+      ll += s_l[w][h] * c;
+      a += s_o[(w * G + h) * D + i] * c;
+    }
+    float* ph = part + (static_cast<int64_t>(h) * nsplit + split) * PS;
+    ph[i] = a;
+    if (i == 0) { ph[D] = mm; ph[D + 1] = ll; }
+  }
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = atomicAdd(tickets + b * Hkv + kvh, 1) == nsplit - 1;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  decode_combine<T, D, G>(part, nsplit, out + static_cast<int64_t>(b) * H * D + static_cast<int64_t>(kvh) * G * D, s_o);
+  if (tid == 0) tickets[b * Hkv + kvh] = 0;
+}
+
 template <typename T, int D>
 void launch_mma(const void* qkv, const void* kc, const void* vc, int64_t batch, int64_t time, int64_t offset, int H,
                 int Hkv, int64_t max_len, float scale, void* out, cudaStream_t st) {
@@ -228,6 +470,39 @@ void launch_mma(const void* qkv, const void* kc, const void* vc, int64_t batch, 
   kernel<<<grid, kThreads, smem, st>>>(static_cast<const T*>(qkv), static_cast<const T*>(kc), static_cast<const T*>(vc),
                                        time, offset, H, Hkv, max_len, scale * 1.4426950408889634f, static_cast<T*>(out));
   check_launch();
+}
+
+
+template <typename T, int D>
+bool launch_decode_mma_g(const void* qkv, void* kc, void* vc, const float* sn, const float* cs, const int32_t* lens,
+                         int64_t batch, int H, int Hkv, int64_t max_len, bool interleave, float scale, void* out,
+                         float* partials, int32_t* tickets, int splits, cudaStream_t st) {
+  const int G = H / Hkv;
+  constexpr size_t smem = static_cast<size_t>(2 * kDecStages * kDecTile) * (D + 8) * sizeof(T) + 8 * D * sizeof(float);
+  const float scale_log2 = scale * 1.4426950408889634f;
+  dim3 grid(splits, Hkv, static_cast<unsigned>(batch));
+#define CT2_DEC_MMA(GV)                                                                                           \
+  {                                                                                                               \
+    auto kernel = attention_decode_mma_kernel<T, D, GV>;                                                          \
+    static bool configured = false;                                                                               \
+    if (!configured) {                                                                                            \
+      CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
+      configured = true;                                                                                          \
+    }                                                                                                             \
+    launch_pdl(kernel, grid, dim3(kThreads), smem, st, static_cast<const T*>(qkv), static_cast<T*>(kc),           \
+               static_cast<T*>(vc), sn, cs, lens, H, Hkv, max_len, interleave, scale_log2, static_cast<T*>(out),  \
+               partials, tickets);                                                                                \
+  }
+  switch (G) {
+    case 1: CT2_DEC_MMA(1); break;
+    case 2: CT2_DEC_MMA(2); break;
+    case 4: CT2_DEC_MMA(4); break;
+    case 8: CT2_DEC_MMA(8); break;
+    default: return false;
+  }
+#undef CT2_DEC_MMA
+  check_launch();
+  return true;
 }
 
 }  // namespace
@@ -247,6 +522,21 @@ bool launch_attention_prefill_mma(const void* qkv, const void* kc, const void* v
     else launch_mma<__nv_bfloat16, 64>(qkv, kc, vc, batch, time, offset, H, Hkv, max_len, scale, out, st);
   }
   return true;
+}
+
+// tensor-core decode attention; false = shape not covered (fp32, head_dim other than 64/128)
+bool launch_attention_decode_mma(const void* qkv, void* kc, void* vc, const float* sn, const float* cs,
+                                 const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
+                                 bool interleave, float scale, void* out, float* partials, int32_t* tickets, int splits,
+                                 int dtype, cudaStream_t st) {
+  static const bool off = [] { const char* e = std::getenv("CT2B200_ATTN_DECODE"); return e && std::string(e) == "simt"; }();
+  if (off || dtype == CT2B200_F32 || (D != 128 && D != 64) || splits > 64) return false;
+  if (dtype == CT2B200_F16) {
+    return D == 128 ? launch_decode_mma_g<__half, 128>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, splits, st)
+                    : launch_decode_mma_g<__half, 64>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, splits, st);
+  }
+  return D == 128 ? launch_decode_mma_g<__nv_bfloat16, 128>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, splits, st)
+                  : launch_decode_mma_g<__nv_bfloat16, 64>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, splits, st);
 }
 
 void launch_attention_prefill(const void* qkv, const void* kc, const void* vc, const int32_t* lengths, int64_t batch,

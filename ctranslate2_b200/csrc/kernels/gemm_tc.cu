@@ -59,28 +59,31 @@ struct TcSmem {
   static constexpr size_t kBytes = static_cast<size_t>(kStages) * kStage + 1024 /*align*/ + 256 /*barriers*/;
 };
 
-// Epilogue of one thread over kCols consecutive N-side rows of its M-side row `arow`, accumulators in r[w][j].
-// All global loads (scales, bias, residual) are issued before any arithmetic or store, so they overlap instead
-// of forming a load -> compute -> store chain per element (which made the epilogue latency-bound).
+// Activation out of line: the epilogue is unrolled over the columns of a chunk, and inlining erff/tanhf/expf
+// into every unrolled copy made the kernels 20-30 k SASS instructions (0.3-0.5 MB), i.e. instruction-fetch bound.
+__device__ __noinline__ float apply_act_call(float x, int act) { return apply_act(x, act); }
+
+// Epilogue of one thread over kCols (16) consecutive N-side rows of its M-side row `arow`, accumulators in r[w][j].
+// All global loads of the chunk (scales, bias, residual) are issued before any arithmetic or store, so they
+// overlap instead of forming a load -> compute -> store chain per element.
 //   kSwap: arow = output channel n, N-side rows = batch rows m;   !kSwap: arow = batch row m, N-side = channels n.
 template <typename T, int KIND, int NB, bool kSwap, int kCols>
-__device__ __forceinline__ void chunk_epilogue(const TcParams& p, const uint32_t (&r)[NB][32], int64_t arow, int64_t brow0) {
+__device__ __forceinline__ void chunk_epilogue(const TcParams& p, const uint32_t (&r)[NB][kCols], int64_t arow, int64_t brow0) {
   if (arow >= p.rows_a) return;
-  const int64_t ncols = min(static_cast<int64_t>(kCols), p.rows_b - brow0);
+  const int ncols = static_cast<int>(min(static_cast<int64_t>(kCols), p.rows_b - brow0));
   if (ncols <= 0) return;
   const T* bias = static_cast<const T*>(KIND == 0 ? p.dense.bias : p.fl.bias);
   const T* residual = static_cast<const T*>(KIND == 0 ? p.dense.residual : p.fl.residual);
   T* y = static_cast<T*>(KIND == 0 ? (NB == 2 ? p.glu.h : p.dense.y) : p.fl.y);
   const int64_t ldy = KIND == 0 ? (NB == 2 ? p.glu.ldh : p.dense.ldy) : p.fl.ldy;
   const int act = KIND == 0 ? (NB == 2 ? p.glu.act : p.dense.act) : p.fl.act;
-  const bool raw = KIND == 0 && NB == 1 && p.dense.a_scale == nullptr;      // int32 output mode
-  if (raw) {
+  // element (row arow, N-side row brow0 + j) lives at base + j * step
+  const int64_t base = kSwap ? brow0 * ldy + arow : arow * ldy + brow0;
+  const int64_t step = kSwap ? ldy : 1;
+  if (KIND == 0 && NB == 1 && p.dense.a_scale == nullptr) {      // raw int32 output (ops::Gemm int8)
 #pragma unroll
     for (int j = 0; j < kCols; ++j)
-      if (j < ncols) {
-        const int64_t i = kSwap ? brow0 + j : arow, jn = kSwap ? arow : brow0 + j;
-        p.dense.c_out[i * ldy + jn] = static_cast<int32_t>(r[0][j]);
-      }
+      if (j < ncols) p.dense.c_out[base + j * step] = static_cast<int32_t>(r[0][j]);
     return;
   }
   // ---- phase 1: loads ----
@@ -101,7 +104,6 @@ __device__ __forceinline__ void chunk_epilogue(const TcParams& p, const uint32_t
 #pragma unroll
   for (int j = 0; j < kCols; ++j) {
     const bool ok = j < ncols;
-    const int64_t i = kSwap ? brow0 + j : arow, jn = kSwap ? arow : brow0 + j;
     if constexpr (KIND == 0) {
       if constexpr (kSwap) {
         sj0[j] = ok ? __ldg(x_scale + brow0 + j) : 1.f;
@@ -110,38 +112,47 @@ __device__ __forceinline__ void chunk_epilogue(const TcParams& p, const uint32_t
         if constexpr (NB == 2) sj1[j] = ok ? __ldg(w_scale1 + brow0 + j) : 1.f;
       }
     }
-    bj[j] = (bias && !kSwap && ok) ? to_f32(bias[jn]) : bias_t;
-    resj[j] = (residual && ok) ? to_f32(residual[i * ldy + jn]) : 0.f;
+    bj[j] = (bias && !kSwap && ok) ? to_f32(bias[brow0 + j]) : bias_t;
+    resj[j] = (residual && ok) ? to_f32(residual[base + j * step]) : 0.f;
   }
   // ---- phase 2: arithmetic + stores (rounding points: see DenseEpilogue / GluEpilogue / FloatEpilogue) ----
 #pragma unroll
   for (int j = 0; j < kCols; ++j) {
     if (j >= ncols) break;
-    const int64_t i = kSwap ? brow0 + j : arow, jn = kSwap ? arow : brow0 + j;
     float v;
     if constexpr (KIND != 0) {
       v = round_to<T>(__uint_as_float(r[0][j]));
       if (bias) v = round_to<T>(v + bj[j]);
-      if (act >= 0) v = round_to<T>(apply_act(v, act));
+      if (act >= 0) v = round_to<T>(apply_act_call(v, act));
       if (residual) v = v + resj[j];
     } else if constexpr (NB == 2) {
       const float sx = kSwap ? sj0[j] : st0;
       const float sg = kSwap ? st0 : sj0[j], su = kSwap ? st1 : sj1[j];
       float gate = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sg));
-      gate = round_to<T>(apply_act(gate, act));
+      gate = round_to<T>(apply_act_call(gate, act));
       const float up = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[1][j])), sx * su));
       v = gate * up;
     } else {
       const float sx = kSwap ? sj0[j] : st0, sw = kSwap ? st0 : sj0[j];
       v = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sw));
       if (bias) v = round_to<T>(v + bj[j]);
-      if (act >= 0) v = round_to<T>(apply_act(v, act));
+      if (act >= 0) v = round_to<T>(apply_act_call(v, act));
       if (residual) v = v + resj[j];
     }
-    y[i * ldy + jn] = from_f32<T>(v);
+    y[base + j * step] = from_f32<T>(v);
   }
 }
 
+// 32 lanes x 16 columns of 32-bit accumulators -> 16 registers per thread
+__device__ __forceinline__ void tmem_ld16x(uint32_t taddr, uint32_t (&r)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
 
 // Persistent "stream-K" GEMM: the work is the list of (output tile, K block) units, tile-major; CTA c of P
 // owns the contiguous unit range [c*U/P, (c+1)*U/P), so every SM streams the same number of bytes and the TMA
@@ -306,9 +317,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // ===== epilogue warps =====
     griddep_wait();                                 // scales / residual come from the previous kernels
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
-    const int et = threadIdx.x - 64;                // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 64;                // 0..127 among the epilogue threads (== q * 32 + lane)
     const int64_t ldw = kSwap ? p.rows_a : p.rows_b;                 // row pitch of the [m, n] scratch plane
     const int64_t plane = p.rows_a * p.rows_b;
+    constexpr int kC = 16;                          // columns per chunk (rolled loop over chunks keeps the code small)
     int seg = 0;
     for (int64_t u = u_begin; u < u_end; ++seg) {
       const int64_t tile = u / KB;
@@ -319,94 +331,88 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int64_t b0 = (tile / p.tiles_a) * BN;
       const int buf = seg & 1;
       const bool direct = kb0 == 0 && kb1 == KB;
-      mbar_wait(tmem_full_bar + buf, (seg >> 1) & 1);
-      tc_fence_after();
-      const int64_t arow = a0 + q * 32 + lane;      // M-side row owned by this thread
+      const int64_t arow = a0 + et;                 // M-side row owned by this thread
       const uint32_t taddr = tmem_base + buf * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
       float* my_slot = p.fslots + (static_cast<int64_t>(blockIdx.x) * 2 + (kb0 > 0 ? 0 : 1)) * (kTileM * BN);
+      int c_lo = 0, c_hi = 0;
+      mbar_wait(tmem_full_bar + buf, (seg >> 1) & 1);
+      tc_fence_after();
+      // pass 0: accumulators from TMEM -> epilogue (tile owned by this CTA alone) or -> scratch (shared tile);
+      // pass 1 (last arriver of a shared tile only): reduced accumulators from the scratch -> epilogue.
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        uint32_t r[NB][32];
+      for (int pass = 0; pass < 2; ++pass) {
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += kC) {
+          uint32_t r[NB][kC];
+          if (pass == 0) {
 #pragma unroll
-        for (int w = 0; w < NB; ++w) {
-          if constexpr (BN % 32 == 0) tmem_ld32(taddr + w * BN + c0, r[w]);
-          else tmem_ld16(taddr + w * BN + c0, r[w]);
-        }
-        if (c0 + 32 >= BN) {                        // last chunk is in registers: hand the buffer back
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(tmem_empty_bar + buf);
-        }
-        constexpr int kCols = (BN % 32 == 0) ? 32 : 16;
-        if (direct) {
-          chunk_epilogue<T, KIND, NB, kSwap, kCols>(p, r, arow, b0 + c0);
-        } else {
-#pragma unroll
-          for (int j = 0; j < kCols; ++j) {
-            const int64_t brow = b0 + c0 + j;       // N-side row
-            if (arow >= p.rows_a || brow >= p.rows_b) continue;
-            const int64_t i = kSwap ? brow : arow;  // output row (m)
-            const int64_t jn = kSwap ? arow : brow; // output column (n)
-            if constexpr (KIND == 0) {
-              atomicAdd(p.ws + i * ldw + jn, static_cast<int32_t>(r[0][j]));
-              if constexpr (NB == 2) atomicAdd(p.ws + plane + i * ldw + jn, static_cast<int32_t>(r[1][j]));
-            } else {
-              // float accumulators: no atomics (order-dependent rounding) — each CTA parks its partial tile in its
-              // own slot, [N-side row][128 M-side rows] so that a warp writes 128 contiguous bytes
-              my_slot[static_cast<int64_t>(c0 + j) * kTileM + q * 32 + lane] = __uint_as_float(r[0][j]);
+            for (int w = 0; w < NB; ++w) tmem_ld16x(taddr + w * BN + c0, r[w]);
+            if (c0 + kC >= BN) {                    // everything is in registers: hand the TMEM buffer back
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(tmem_empty_bar + buf);
             }
-          }
-        }
-      }
-      if (direct) continue;
-      // ---- shared tile: ticket; the last of the contributing CTAs finishes it ----
-      __threadfence();
-      epi_bar_sync();
-      const int c_lo = cta_of_unit(tile * KB, U, P), c_hi = cta_of_unit((tile + 1) * KB - 1, U, P);
-      if (et == 0) s_last = atomicAdd(p.counters + tile, 1) == c_hi - c_lo;
-      epi_bar_sync();
-      if (s_last) {
-        __threadfence();
-        // thread et finishes M-side row a0+et: gather the reduced accumulators (all loads first), clear the
-        // scratch, then the same chunk epilogue as the direct path
-        constexpr int kColsF = (BN % 32 == 0) ? 32 : 16;
-        const int64_t arow2 = a0 + et;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += kColsF) {
-          uint32_t v[NB][32];
+          } else if constexpr (KIND != 0) {
 #pragma unroll
-          for (int j = 0; j < kColsF; ++j) {
-            const int64_t brow2 = b0 + c0 + j;
-            const bool ok = arow2 < p.rows_a && brow2 < p.rows_b;
-            if constexpr (KIND != 0) {
+            for (int j = 0; j < kC; ++j) {
               float acc = 0.f;
-              if (ok)
-                for (int c = c_lo; c <= c_hi; ++c)    // fixed CTA order => run-to-run deterministic
-                  acc += __ldcg(p.fslots + (static_cast<int64_t>(c) * 2 + (c == c_lo ? 1 : 0)) * (kTileM * BN) +
-                                static_cast<int64_t>(c0 + j) * kTileM + et);
-              v[0][j] = __float_as_uint(acc);
-            } else {
-              const int64_t i = kSwap ? brow2 : arow2, jn = kSwap ? arow2 : brow2;
-#pragma unroll
-              for (int w = 0; w < NB; ++w) v[w][j] = ok ? static_cast<uint32_t>(__ldcg(p.ws + w * plane + i * ldw + jn)) : 0u;
+              for (int c = c_lo; c <= c_hi; ++c)      // fixed CTA order => run-to-run deterministic
+                acc += __ldcg(p.fslots + (static_cast<int64_t>(c) * 2 + (c == c_lo ? 1 : 0)) * (kTileM * BN) +
+                              static_cast<int64_t>(c0 + j) * kTileM + et);
+              r[0][j] = __float_as_uint(acc);
             }
-          }
-          if constexpr (KIND == 0) {
+          } else {
 #pragma unroll
-            for (int j = 0; j < kColsF; ++j) {
-              const int64_t brow2 = b0 + c0 + j;
-              if (arow2 < p.rows_a && brow2 < p.rows_b) {
-                const int64_t i = kSwap ? brow2 : arow2, jn = kSwap ? arow2 : brow2;
+            for (int j = 0; j < kC; ++j) {
+              const int64_t brow = b0 + c0 + j;
+              const bool ok = arow < p.rows_a && brow < p.rows_b;
+              const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
 #pragma unroll
-                for (int w = 0; w < NB; ++w) p.ws[w * plane + i * ldw + jn] = 0;
+              for (int w = 0; w < NB; ++w) r[w][j] = ok ? static_cast<uint32_t>(__ldcg(p.ws + w * plane + off)) : 0u;
+            }
+#pragma unroll
+            for (int j = 0; j < kC; ++j) {
+              const int64_t brow = b0 + c0 + j;
+              if (arow < p.rows_a && brow < p.rows_b) {
+                const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
+#pragma unroll
+                for (int w = 0; w < NB; ++w) p.ws[w * plane + off] = 0;
               }
             }
           }
-          chunk_epilogue<T, KIND, NB, kSwap, kColsF>(p, v, arow2, b0 + c0);
+          if (direct || pass == 1) {
+            chunk_epilogue<T, KIND, NB, kSwap, kC>(p, r, arow, b0 + c0);
+          } else {
+#pragma unroll
+            for (int j = 0; j < kC; ++j) {
+              const int64_t brow = b0 + c0 + j;
+              if (arow >= p.rows_a || brow >= p.rows_b) continue;
+              if constexpr (KIND == 0) {
+                const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
+                atomicAdd(p.ws + off, static_cast<int32_t>(r[0][j]));
+                if constexpr (NB == 2) atomicAdd(p.ws + plane + off, static_cast<int32_t>(r[1][j]));
+              } else {
+                // float accumulators: no atomics (order-dependent rounding) — each CTA parks its partial tile in
+                // its own slot, [N-side row][128 M-side rows] so that a warp writes 128 contiguous bytes
+                my_slot[static_cast<int64_t>(c0 + j) * kTileM + et] = __uint_as_float(r[0][j]);
+              }
+            }
+          }
         }
+        if (direct || pass == 1) break;
+        // ---- shared tile: ticket; the last of the contributing CTAs finishes it ----
+        __threadfence();
+        epi_bar_sync();
+        c_lo = cta_of_unit(tile * KB, U, P);
+        c_hi = cta_of_unit((tile + 1) * KB - 1, U, P);
+        if (et == 0) s_last = atomicAdd(p.counters + tile, 1) == c_hi - c_lo;
+        epi_bar_sync();
+        const bool last = s_last != 0;
+        epi_bar_sync();                             // s_last is reused by the next shared tile
+        if (!last) break;
+        __threadfence();
         if (et == 0) p.counters[tile] = 0;
       }
-      epi_bar_sync();                               // s_last is reused by the next shared tile
     }
   }
 

@@ -84,6 +84,10 @@ void launch_attention_prefill_simple(const void* qkv, const void* kc, const void
 bool launch_attention_prefill_mma(const void* qkv, const void* kc, const void* vc, int64_t batch, int64_t time,
                                   int64_t offset, int H, int Hkv, int D, int64_t max_len, float scale, void* out,
                                   int dtype, cudaStream_t st);
+bool launch_attention_decode_mma(const void* qkv, void* kc, void* vc, const float* sn, const float* cs,
+                                 const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
+                                 bool interleave, float scale, void* out, float* partials, int32_t* tickets, int splits,
+                                 int dtype, cudaStream_t st);
 // picks the tensor-core kernel when it covers the shape (CT2B200_ATTN_PREFILL=simple forces the generic one)
 void launch_attention_prefill(const void* qkv, const void* kc, const void* vc, const int32_t* lengths, int64_t batch,
                               int64_t time, int64_t offset, int H, int Hkv, int D, int64_t max_len, float scale,
