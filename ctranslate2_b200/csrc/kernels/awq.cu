@@ -135,7 +135,8 @@ __global__ void awq_dequantize_native_kernel(const int32_t* __restrict__ wp, con
 // ---------------------------------------------------------------------------------------------
 // decode GEMM: y[m,n] = x[m,:] . deq(W)[n,:]  (swap-AB: weights on the UMMA M side)
 // ---------------------------------------------------------------------------------------------
-constexpr int kAwqThreads = 320;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-9 dequantize
+constexpr int kAwqThreads = 448;      // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-13 dequantize
+constexpr int kDeqWarps = 8;          // two threads per weight row, 32 channels (4 packed words) each
 constexpr int kBKh = 64;              // fp16 elements of K per stage (one 128-byte swizzle atom)
 constexpr int kPackedTile = kTileM * kBKh / 2;      // 4096 bytes of nibbles per weight tile per stage
 
@@ -223,7 +224,7 @@ __global__ void __launch_bounds__(kAwqThreads, 1)
     for (int s = 0; s < kStages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
-      mbar_init(ready_bar + s, 4);
+      mbar_init(ready_bar + s, kDeqWarps);
     }
     for (int b = 0; b < 2; ++b) {
       mbar_init(tmem_full_bar + b, 1);
@@ -237,6 +238,7 @@ __global__ void __launch_bounds__(kAwqThreads, 1)
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
 
   if (warp == 0) {
     // ===== TMA producer: packed weight tile(s) + activation tile =====
@@ -244,16 +246,36 @@ __global__ void __launch_bounds__(kAwqThreads, 1)
       int it = 0;
       int tile = static_cast<int>(u_begin / KB);
       int kb = static_cast<int>(u_begin - tile * KB);
+      auto issue = [&](int s, int t_, int kb_, bool weights, bool acts) {
+        uint8_t* st = smem + s * S::kStage;
+        if (weights) {
+          tma_load_2d(st + S::kA, &tm_w, full_bar + s, kb_ * (kBKh / 2), t_ * kTileM, kEvictFirst);
+          if (NB == 2) tma_load_2d(st + S::kA + kPackedTile, &tm_w2, full_bar + s, kb_ * (kBKh / 2), t_ * kTileM, kEvictFirst);
+        }
+        if (acts) tma_load_2d(st + S::kA + S::kP, &tm_x, full_bar + s, kb_ * kBKh, 0, kEvictLast);
+      };
+      // weights never depend on the previous kernel: fill the ring with them before griddepcontrol.wait
+      const int64_t prefill = min(static_cast<int64_t>(kStages), u_end - u_begin);
+      {
+        int t2 = tile, k2 = kb;
+        for (int64_t i = 0; i < prefill; ++i, ++k2) {
+          if (k2 == KB) { k2 = 0; ++t2; }
+          mbar_expect_tx(full_bar + i, S::kP + S::kX);
+          issue(static_cast<int>(i), t2, k2, true, false);
+        }
+      }
+      griddep_wait();
       for (int64_t u = u_begin; u < u_end; ++u, ++it, ++kb) {
         if (kb == KB) { kb = 0; ++tile; }
         const int s = it % kStages;
         const uint32_t ph = (it / kStages) & 1;
-        mbar_wait(empty_bar + s, ph ^ 1);
-        mbar_expect_tx(full_bar + s, S::kP + S::kX);
-        uint8_t* st = smem + s * S::kStage;
-        tma_load_2d(st + S::kA, &tm_w, full_bar + s, kb * (kBKh / 2), tile * kTileM, kEvictFirst);
-        if (NB == 2) tma_load_2d(st + S::kA + kPackedTile, &tm_w2, full_bar + s, kb * (kBKh / 2), tile * kTileM, kEvictFirst);
-        tma_load_2d(st + S::kA + S::kP, &tm_x, full_bar + s, kb * kBKh, 0, kEvictLast);
+        if (it < prefill) {
+          issue(s, tile, kb, false, true);
+        } else {
+          mbar_wait(empty_bar + s, ph ^ 1);
+          mbar_expect_tx(full_bar + s, S::kP + S::kX);
+          issue(s, tile, kb, true, true);
+        }
       }
     }
   } else if (warp == 1) {
@@ -292,36 +314,58 @@ __global__ void __launch_bounds__(kAwqThreads, 1)
     }
   } else if (warp >= 6) {
     // ===== dequantize warps: packed nibbles -> fp16 (q - z) * s into the swizzled UMMA A tile =====
-    const int r = threadIdx.x - 192;                    // tile row 0..127 owned by this thread
+    const int d = threadIdx.x - 192;                    // 0..255
+    const int r = d & 127;                              // tile row owned by this thread
+    const int half = d >> 7;                            // which 32-channel half of the 64-channel K block
     const int64_t ng = p.k / p.group;
     int it = 0;
     int tile = static_cast<int>(u_begin / KB);
     int kb = static_cast<int>(u_begin - tile * KB);
+    // group scale / zero are fetched one group ahead (they change every group/64 K blocks), so the global-load
+    // latency is off the per-block critical path
+    int64_t cur_g = -1;
+    int cur_tile = -1;
+    __half zc[NB], sc_[NB], zn[NB], sn_[NB];
+    auto fetch = [&](int64_t row, int64_t g, __half (&z)[NB], __half (&sc)[NB]) {
+#pragma unroll
+      for (int w = 0; w < NB; ++w) {
+        const bool ok = row < p.n && g < ng;
+        z[w] = ok ? p.zr[w][row * ng + g] : __float2half(0.f);
+        sc[w] = ok ? p.sc[w][row * ng + g] : __float2half(0.f);
+      }
+    };
     for (int64_t u = u_begin; u < u_end; ++u, ++it, ++kb) {
       if (kb == KB) { kb = 0; ++tile; }
       const int s = it % kStages;
       const uint32_t ph = (it / kStages) & 1;
       const int64_t row = static_cast<int64_t>(tile) * kTileM + r;
       const int64_t g = (static_cast<int64_t>(kb) * kBKh) / p.group;
+      if (tile != cur_tile || g != cur_g) {
+        if (tile == cur_tile && g == cur_g + 1) {
+#pragma unroll
+          for (int w = 0; w < NB; ++w) { zc[w] = zn[w]; sc_[w] = sn_[w]; }
+        } else {
+          fetch(row, g, zc, sc_);
+        }
+        fetch(row, g + 1, zn, sn_);                     // prefetch the next group of this row
+        cur_tile = tile;
+        cur_g = g;
+      }
       mbar_wait(full_bar + s, ph);
       uint8_t* st = smem + s * S::kStage;
 #pragma unroll
       for (int w = 0; w < NB; ++w) {
-        __half z = __float2half(0.f), sc = __float2half(0.f);
-        if (row < p.n) {
-          z = p.zr[w][row * ng + g];
-          sc = p.sc[w][row * ng + g];
-        }
-        const __half2 zb = __half2half2(__hadd(__float2half(1024.f), z));
-        const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), z)));
-        const __half2 s2 = __half2half2(sc);
-        const uint4* pk = reinterpret_cast<const uint4*>(st + S::kA + w * kPackedTile + r * (kBKh / 2));
-        const uint4 w0 = pk[0], w1 = pk[1];
-        const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
+        const __half2 zb = __half2half2(__hadd(__float2half(1024.f), zc[w]));
+        const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), zc[w])));
+        const __half2 s2 = __half2half2(sc_[w]);
+        const uint4 wv = *reinterpret_cast<const uint4*>(st + S::kA + w * kPackedTile + r * (kBKh / 2) + half * 16);
+        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
         uint8_t* arow = st + w * kTileM * kSwizzleBytes + r * kSwizzleBytes;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)      // 16-byte chunk c of the row lives at chunk (c ^ (r & 7)) under SWIZZLE_128B
-          *reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4)) = awq_dequant_word(words[c], zb, zt, s2);
+        for (int c = 0; c < 4; ++c) {    // 16-byte chunk cc of the row lives at chunk (cc ^ (r & 7)) under SWIZZLE_128B
+          const int cc = half * 4 + c;
+          *reinterpret_cast<uint4*>(arow + ((cc ^ (r & 7)) << 4)) = awq_dequant_word(words[c], zb, zt, s2);
+        }
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
       __syncwarp();
@@ -329,6 +373,7 @@ __global__ void __launch_bounds__(kAwqThreads, 1)
     }
   } else {
     // ===== epilogue warps (2..5) =====
+    griddep_wait();                                     // bias / residual may come from the previous kernel
     const int q = warp & 3;
     const int et = threadIdx.x - 64;
     const int64_t slot_elems = static_cast<int64_t>(NB) * kTileM * BN;
@@ -453,7 +498,7 @@ void launch_awq(const void* x, const AwqNative& w, const AwqNative* w2, int64_t 
               "awq: scratch too small");
   p.ws = reinterpret_cast<float*>(wsp.accum2);
   p.counters = wsp.counters;
-  kernel<<<static_cast<unsigned>(ctas), kAwqThreads, S::kBytes, st>>>(tmx, tmw, tmw2, p);
+  launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kAwqThreads), S::kBytes, st, tmx, tmw, tmw2, p);
   check_launch();
 }
 

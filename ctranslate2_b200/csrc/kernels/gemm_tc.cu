@@ -42,6 +42,8 @@ struct TcParams {
   int tiles_b;         // N-side tiles of BN rows
   int kb_total;        // K blocks (128 bytes of K each) per output tile
   int whole_tiles;     // 1 = CTA ranges are aligned to whole tiles (no scratch needed)
+  int part_lo;         // > 0: tile-partitioned split-K — every tile is owned by part_lo (or part_lo + 1) CTAs and every
+  int part_rem;        //      CTA works on exactly ONE tile (one reduction round); the first part_rem tiles get +1 CTA
   DenseEpilogue dense;
   GluEpilogue glu;
   FloatEpilogue fl;
@@ -63,81 +65,98 @@ struct TcSmem {
 // into every unrolled copy made the kernels 20-30 k SASS instructions (0.3-0.5 MB), i.e. instruction-fetch bound.
 __device__ __noinline__ float apply_act_call(float x, int act) { return apply_act(x, act); }
 
-// Epilogue of one thread over kCols (16) consecutive N-side rows of its M-side row `arow`, accumulators in r[w][j].
-// All global loads of the chunk (scales, bias, residual) are issued before any arithmetic or store, so they
-// overlap instead of forming a load -> compute -> store chain per element.
+// Epilogue of one thread over kCols (16) consecutive N-side rows of its M-side row `arow`.
 //   kSwap: arow = output channel n, N-side rows = batch rows m;   !kSwap: arow = batch row m, N-side = channels n.
+// Split in two so that the global loads (scales, bias, residual) can be issued early — before the accumulators are
+// ready, or together with the scratch reads of the split-K fix-up — instead of adding a memory round trip:
+//   epi_load:   all loads of the chunk, no dependent arithmetic;
+//   epi_finish: arithmetic + stores (rounding points: see DenseEpilogue / GluEpilogue / FloatEpilogue).
+template <int NB, int kCols>
+struct EpiInputs {
+  float st0, st1, bias_t;               // per-thread constants
+  float sj0[kCols], sj1[NB == 2 ? kCols : 1], bj[kCols], resj[kCols];
+  int ncols;                            // valid columns (0 => nothing to do)
+};
+
 template <typename T, int KIND, int NB, bool kSwap, int kCols>
-__device__ __forceinline__ void chunk_epilogue(const TcParams& p, const uint32_t (&r)[NB][kCols], int64_t arow, int64_t brow0) {
-  if (arow >= p.rows_a) return;
-  const int ncols = static_cast<int>(min(static_cast<int64_t>(kCols), p.rows_b - brow0));
-  if (ncols <= 0) return;
+__device__ __forceinline__ void epi_load(const TcParams& p, int64_t arow, int64_t brow0, EpiInputs<NB, kCols>& in) {
+  in.ncols = arow < p.rows_a ? static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kCols), p.rows_b - brow0))) : 0;
+  in.st0 = in.st1 = 1.f;
+  in.bias_t = 0.f;
+  if (in.ncols == 0) return;
+  if (KIND == 0 && NB == 1 && p.dense.a_scale == nullptr) return;      // raw int32 output needs no inputs
   const T* bias = static_cast<const T*>(KIND == 0 ? p.dense.bias : p.fl.bias);
   const T* residual = static_cast<const T*>(KIND == 0 ? p.dense.residual : p.fl.residual);
+  const int64_t ldy = KIND == 0 ? (NB == 2 ? p.glu.ldh : p.dense.ldy) : p.fl.ldy;
+  const int64_t base = kSwap ? brow0 * ldy + arow : arow * ldy + brow0;
+  const int64_t step = kSwap ? ldy : 1;
+  const float* x_scale = NB == 2 ? p.glu.a_scale : p.dense.a_scale;
+  const float* w_scale0 = NB == 2 ? p.glu.gate_scale : p.dense.b_scale;
+  const float* w_scale1 = p.glu.up_scale;
+  if constexpr (KIND == 0) {
+    if constexpr (kSwap) {
+      in.st0 = __ldg(w_scale0 + arow);
+      if constexpr (NB == 2) in.st1 = __ldg(w_scale1 + arow);
+    } else {
+      in.st0 = __ldg(x_scale + arow);
+    }
+  }
+  if (bias && kSwap) in.bias_t = to_f32(bias[arow]);
+#pragma unroll
+  for (int j = 0; j < kCols; ++j) {
+    const bool ok = j < in.ncols;
+    if constexpr (KIND == 0) {
+      if constexpr (kSwap) {
+        in.sj0[j] = ok ? __ldg(x_scale + brow0 + j) : 1.f;
+      } else {
+        in.sj0[j] = ok ? __ldg(w_scale0 + brow0 + j) : 1.f;
+        if constexpr (NB == 2) in.sj1[j] = ok ? __ldg(w_scale1 + brow0 + j) : 1.f;
+      }
+    }
+    in.bj[j] = (bias && !kSwap && ok) ? to_f32(bias[brow0 + j]) : in.bias_t;
+    in.resj[j] = (residual && ok) ? to_f32(residual[base + j * step]) : 0.f;
+  }
+}
+
+template <typename T, int KIND, int NB, bool kSwap, int kCols>
+__device__ __forceinline__ void epi_finish(const TcParams& p, const uint32_t (&r)[NB][kCols], int64_t arow, int64_t brow0,
+                                           const EpiInputs<NB, kCols>& in) {
+  if (in.ncols == 0) return;
+  const bool has_bias = (KIND == 0 ? p.dense.bias : p.fl.bias) != nullptr;
+  const bool has_res = (KIND == 0 ? p.dense.residual : p.fl.residual) != nullptr;
   T* y = static_cast<T*>(KIND == 0 ? (NB == 2 ? p.glu.h : p.dense.y) : p.fl.y);
   const int64_t ldy = KIND == 0 ? (NB == 2 ? p.glu.ldh : p.dense.ldy) : p.fl.ldy;
   const int act = KIND == 0 ? (NB == 2 ? p.glu.act : p.dense.act) : p.fl.act;
-  // element (row arow, N-side row brow0 + j) lives at base + j * step
   const int64_t base = kSwap ? brow0 * ldy + arow : arow * ldy + brow0;
   const int64_t step = kSwap ? ldy : 1;
   if (KIND == 0 && NB == 1 && p.dense.a_scale == nullptr) {      // raw int32 output (ops::Gemm int8)
 #pragma unroll
     for (int j = 0; j < kCols; ++j)
-      if (j < ncols) p.dense.c_out[base + j * step] = static_cast<int32_t>(r[0][j]);
+      if (j < in.ncols) p.dense.c_out[base + j * step] = static_cast<int32_t>(r[0][j]);
     return;
   }
-  // ---- phase 1: loads ----
-  const float* x_scale = NB == 2 ? p.glu.a_scale : p.dense.a_scale;
-  const float* w_scale0 = NB == 2 ? p.glu.gate_scale : p.dense.b_scale;
-  const float* w_scale1 = p.glu.up_scale;
-  float st0 = 1.f, st1 = 1.f, bias_t = 0.f;          // per-thread constants
-  float sj0[kCols], sj1[NB == 2 ? kCols : 1], bj[kCols], resj[kCols];
-  if constexpr (KIND == 0) {
-    if constexpr (kSwap) {
-      st0 = __ldg(w_scale0 + arow);
-      if constexpr (NB == 2) st1 = __ldg(w_scale1 + arow);
-    } else {
-      st0 = __ldg(x_scale + arow);
-    }
-  }
-  if (bias && kSwap) bias_t = to_f32(bias[arow]);
 #pragma unroll
   for (int j = 0; j < kCols; ++j) {
-    const bool ok = j < ncols;
-    if constexpr (KIND == 0) {
-      if constexpr (kSwap) {
-        sj0[j] = ok ? __ldg(x_scale + brow0 + j) : 1.f;
-      } else {
-        sj0[j] = ok ? __ldg(w_scale0 + brow0 + j) : 1.f;
-        if constexpr (NB == 2) sj1[j] = ok ? __ldg(w_scale1 + brow0 + j) : 1.f;
-      }
-    }
-    bj[j] = (bias && !kSwap && ok) ? to_f32(bias[brow0 + j]) : bias_t;
-    resj[j] = (residual && ok) ? to_f32(residual[base + j * step]) : 0.f;
-  }
-  // ---- phase 2: arithmetic + stores (rounding points: see DenseEpilogue / GluEpilogue / FloatEpilogue) ----
-#pragma unroll
-  for (int j = 0; j < kCols; ++j) {
-    if (j >= ncols) break;
+    if (j >= in.ncols) break;
     float v;
     if constexpr (KIND != 0) {
       v = round_to<T>(__uint_as_float(r[0][j]));
-      if (bias) v = round_to<T>(v + bj[j]);
+      if (has_bias) v = round_to<T>(v + in.bj[j]);
       if (act >= 0) v = round_to<T>(apply_act_call(v, act));
-      if (residual) v = v + resj[j];
+      if (has_res) v = v + in.resj[j];
     } else if constexpr (NB == 2) {
-      const float sx = kSwap ? sj0[j] : st0;
-      const float sg = kSwap ? st0 : sj0[j], su = kSwap ? st1 : sj1[j];
+      const float sx = kSwap ? in.sj0[j] : in.st0;
+      const float sg = kSwap ? in.st0 : in.sj0[j], su = kSwap ? in.st1 : in.sj1[j];
       float gate = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sg));
       gate = round_to<T>(apply_act_call(gate, act));
       const float up = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[1][j])), sx * su));
       v = gate * up;
     } else {
-      const float sx = kSwap ? sj0[j] : st0, sw = kSwap ? st0 : sj0[j];
+      const float sx = kSwap ? in.sj0[j] : in.st0, sw = kSwap ? in.st0 : in.sj0[j];
       v = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sw));
-      if (bias) v = round_to<T>(v + bj[j]);
+      if (has_bias) v = round_to<T>(v + in.bj[j]);
       if (act >= 0) v = round_to<T>(apply_act_call(v, act));
-      if (residual) v = v + resj[j];
+      if (has_res) v = v + in.resj[j];
     }
     y[base + j * step] = from_f32<T>(v);
   }
@@ -191,8 +210,32 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int64_t U = static_cast<int64_t>(p.tiles_a) * p.tiles_b * KB;
   const int64_t P = gridDim.x;
   const int64_t T_all = static_cast<int64_t>(p.tiles_a) * p.tiles_b;
-  const int64_t u_begin = p.whole_tiles ? (blockIdx.x * T_all / P) * KB : blockIdx.x * U / P;
-  const int64_t u_end = p.whole_tiles ? ((blockIdx.x + 1) * T_all / P) * KB : (blockIdx.x + 1) * U / P;
+  int64_t u_begin, u_end;
+  int part_first = 0, part_n = 0;      // partition mode: first CTA and number of CTAs of this CTA's tile
+  if (p.part_lo > 0) {
+    const int big = p.part_rem * (p.part_lo + 1);
+    int t, i;
+    if (static_cast<int>(blockIdx.x) < big) {
+      part_n = p.part_lo + 1;
+      t = blockIdx.x / part_n;
+      i = blockIdx.x % part_n;
+      part_first = t * part_n;
+    } else {
+      part_n = p.part_lo;
+      const int c2 = blockIdx.x - big;
+      t = p.part_rem + c2 / part_n;
+      i = c2 % part_n;
+      part_first = big + (c2 / part_n) * part_n;
+    }
+    u_begin = t * KB + i * KB / part_n;
+    u_end = t * KB + (i + 1) * KB / part_n;
+  } else if (p.whole_tiles) {
+    u_begin = (blockIdx.x * T_all / P) * KB;
+    u_end = ((blockIdx.x + 1) * T_all / P) * KB;
+  } else {
+    u_begin = blockIdx.x * U / P;
+    u_end = (blockIdx.x + 1) * U / P;
+  }
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < kStages; ++s) {
@@ -331,10 +374,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int64_t b0 = (tile / p.tiles_a) * BN;
       const int buf = seg & 1;
       const bool direct = kb0 == 0 && kb1 == KB;
-      const int64_t arow = a0 + et;                 // M-side row owned by this thread
+      const int rloc = q * 32 + lane;               // tile row owned by this thread (= its TMEM lane)
+      const int64_t arow = a0 + rloc;
       const uint32_t taddr = tmem_base + buf * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
       float* my_slot = p.fslots + (static_cast<int64_t>(blockIdx.x) * 2 + (kb0 > 0 ? 0 : 1)) * (kTileM * BN);
       int c_lo = 0, c_hi = 0;
+      EpiInputs<NB, kC> ein;
+      if (direct) epi_load<T, KIND, NB, kSwap, kC>(p, arow, b0, ein);   // issued while the MMAs of this segment run
       mbar_wait(tmem_full_bar + buf, (seg >> 1) & 1);
       tc_fence_after();
       // pass 0: accumulators from TMEM -> epilogue (tile owned by this CTA alone) or -> scratch (shared tile);
@@ -345,6 +391,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int c0 = 0; c0 < BN; c0 += kC) {
           uint32_t r[NB][kC];
           if (pass == 0) {
+            if (direct && c0 > 0) epi_load<T, KIND, NB, kSwap, kC>(p, arow, b0 + c0, ein);
 #pragma unroll
             for (int w = 0; w < NB; ++w) tmem_ld16x(taddr + w * BN + c0, r[w]);
             if (c0 + kC >= BN) {                    // everything is in registers: hand the TMEM buffer back
@@ -352,36 +399,40 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               __syncwarp();
               if (lane == 0) mbar_arrive(tmem_empty_bar + buf);
             }
-          } else if constexpr (KIND != 0) {
-#pragma unroll
-            for (int j = 0; j < kC; ++j) {
-              float acc = 0.f;
-              for (int c = c_lo; c <= c_hi; ++c)      // fixed CTA order => run-to-run deterministic
-                acc += __ldcg(p.fslots + (static_cast<int64_t>(c) * 2 + (c == c_lo ? 1 : 0)) * (kTileM * BN) +
-                              static_cast<int64_t>(c0 + j) * kTileM + et);
-              r[0][j] = __float_as_uint(acc);
-            }
           } else {
+            // the epilogue inputs and the reduced accumulators are requested together: one memory round trip
+            epi_load<T, KIND, NB, kSwap, kC>(p, arow, b0 + c0, ein);
+            if constexpr (KIND != 0) {
 #pragma unroll
-            for (int j = 0; j < kC; ++j) {
-              const int64_t brow = b0 + c0 + j;
-              const bool ok = arow < p.rows_a && brow < p.rows_b;
-              const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
+              for (int j = 0; j < kC; ++j) {
+                float acc = 0.f;
+                for (int c = c_lo; c <= c_hi; ++c)      // fixed CTA order => run-to-run deterministic
+                  acc += __ldcg(p.fslots + (static_cast<int64_t>(c) * 2 + (c == c_lo ? 1 : 0)) * (kTileM * BN) +
+                                static_cast<int64_t>(c0 + j) * kTileM + rloc);
+                r[0][j] = __float_as_uint(acc);
+              }
+            } else {
 #pragma unroll
-              for (int w = 0; w < NB; ++w) r[w][j] = ok ? static_cast<uint32_t>(__ldcg(p.ws + w * plane + off)) : 0u;
-            }
-#pragma unroll
-            for (int j = 0; j < kC; ++j) {
-              const int64_t brow = b0 + c0 + j;
-              if (arow < p.rows_a && brow < p.rows_b) {
+              for (int j = 0; j < kC; ++j) {
+                const int64_t brow = b0 + c0 + j;
+                const bool ok = arow < p.rows_a && brow < p.rows_b;
                 const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
 #pragma unroll
-                for (int w = 0; w < NB; ++w) p.ws[w * plane + off] = 0;
+                for (int w = 0; w < NB; ++w) r[w][j] = ok ? static_cast<uint32_t>(__ldcg(p.ws + w * plane + off)) : 0u;
+              }
+#pragma unroll
+              for (int j = 0; j < kC; ++j) {
+                const int64_t brow = b0 + c0 + j;
+                if (arow < p.rows_a && brow < p.rows_b) {
+                  const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
+#pragma unroll
+                  for (int w = 0; w < NB; ++w) p.ws[w * plane + off] = 0;
+                }
               }
             }
           }
           if (direct || pass == 1) {
-            chunk_epilogue<T, KIND, NB, kSwap, kC>(p, r, arow, b0 + c0);
+            epi_finish<T, KIND, NB, kSwap, kC>(p, r, arow, b0 + c0, ein);
           } else {
 #pragma unroll
             for (int j = 0; j < kC; ++j) {
@@ -394,7 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
               } else {
                 // float accumulators: no atomics (order-dependent rounding) — each CTA parks its partial tile in
                 // its own slot, [N-side row][128 M-side rows] so that a warp writes 128 contiguous bytes
-                my_slot[static_cast<int64_t>(c0 + j) * kTileM + et] = __uint_as_float(r[0][j]);
+                my_slot[static_cast<int64_t>(c0 + j) * kTileM + rloc] = __uint_as_float(r[0][j]);
               }
             }
           }
@@ -403,8 +454,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // ---- shared tile: ticket; the last of the contributing CTAs finishes it ----
         __threadfence();
         epi_bar_sync();
-        c_lo = cta_of_unit(tile * KB, U, P);
-        c_hi = cta_of_unit((tile + 1) * KB - 1, U, P);
+        if (p.part_lo > 0) {
+          c_lo = part_first;
+          c_hi = part_first + part_n - 1;
+        } else {
+          c_lo = cta_of_unit(tile * KB, U, P);
+          c_hi = cta_of_unit((tile + 1) * KB - 1, U, P);
+        }
         if (et == 0) s_last = atomicAdd(p.counters + tile, 1) == c_hi - c_lo;
         epi_bar_sync();
         const bool last = s_last != 0;
@@ -456,6 +512,13 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   static const bool force_whole = [] { const char* e = std::getenv("CT2B200_GEMM_WHOLE"); return e && e[0] == '1'; }();
   p.whole_tiles = (scratch_ok && !force_whole) ? 0 : 1;
   if (p.whole_tiles) ctas = std::min<int64_t>(wsp.sm_count, tiles);   // tile-aligned CTA ranges
+  // tile-partitioned split-K when there are at least two CTAs per tile: one reduction round per CTA instead of up
+  // to two with stream-K (the reduction costs ~3 L2 round trips, comparable to streaming a whole small GEMM)
+  p.part_lo = p.part_rem = 0;
+  if (!p.whole_tiles && ctas >= 2 * tiles && p.kb_total >= 2 * ((ctas + tiles - 1) / tiles)) {
+    p.part_lo = static_cast<int>(ctas / tiles);
+    p.part_rem = static_cast<int>(ctas % tiles);
+  }
   p.ws = wsp.accum;
   p.fslots = reinterpret_cast<float*>(wsp.accum2);
   p.counters = wsp.counters;

@@ -80,7 +80,9 @@ def d128_model(tmp_path_factory):
 
 
 @gpu
-@pytest.mark.parametrize("compute_type,tol", [("int8_float32", 1e-3), ("int8_float16", 5e-2)])
+# fp32 activations: everything matches to ~1e-6 except where a product lands within an ulp of an int8 rounding
+# boundary and the two pipelines round it to different sides (1/127 of that row) — hence 5e-3, not 1e-5.
+@pytest.mark.parametrize("compute_type,tol", [("int8_float32", 5e-3), ("int8_float16", 5e-2)])
 def test_d128_model_vs_oracle(d128_model, compute_type, tol):
     """Llama-3 geometry (head_dim 128, GQA 4:1, Llama3 rope scaling) at a size the oracle runs in seconds."""
     w = O.DecoderWeights.from_dir(d128_model, "cuda")
