@@ -488,34 +488,34 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
     }
     return;
   }
+  // step_mask_: bit i enables kernel class i of the decode step (all ones in production; bench.py --ablate times the
+  // step with classes removed, inside the CUDA graph, to attribute in-graph time to each kernel class)
+  const unsigned mk = step_mask_;
   for (int l = 0; l < mc_.num_layers; ++l) {
     LayerWeights& lw = layers_[l];
     // --- self attention (attention.cc:442-615) ---
-    launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
-                    xs_.as<float>(), dtype_, stream_);
-    dense(lw.qkv, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, qkv_.ptr);
-    attention(l);
-    launch_quantize_rows(attn_.ptr, dtype_, rows, static_cast<int64_t>(H) * D, true, xq_.as<int8_t>(),
-                         xs_.as<float>(), stream_);
-    dense(lw.out, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
+    if (mk & 1u)
+      launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                      xs_.as<float>(), dtype_, stream_);
+    if (mk & 2u) dense(lw.qkv, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, qkv_.ptr);
+    if (mk & 4u) attention(l);
+    if (mk & 8u)
+      launch_quantize_rows(attn_.ptr, dtype_, rows, static_cast<int64_t>(H) * D, true, xq_.as<int8_t>(),
+                           xs_.as<float>(), stream_);
+    if (mk & 16u) dense(lw.out, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
     // --- feed forward (transformer.cc:21-51) ---
-    launch_rms_norm(lw.ffn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
-                    xs_.as<float>(), dtype_, stream_);
-    GluEpilogue g{xs_.as<float>(), lw.gate.scale.as<float>(), lw.up.scale.as<float>(), h_.ptr, mc_.activation, lw.gate.n};
-    gemm_s8_glu(xq_.as<int8_t>(), lw.gate.weight.as<int8_t>(), lw.up.weight.as<int8_t>(), rows, lw.gate.n, lw.gate.k,
-                g, dtype_, gemm_impl_, stream_);
-    launch_quantize_rows(h_.ptr, dtype_, rows, mc_.ffn_dim, true, xq_.as<int8_t>(), xs_.as<float>(), stream_);
-    dense(lw.down, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
+    if (mk & 32u)
+      launch_rms_norm(lw.ffn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                      xs_.as<float>(), dtype_, stream_);
+    if (mk & 64u) {
+      GluEpilogue g{xs_.as<float>(), lw.gate.scale.as<float>(), lw.up.scale.as<float>(), h_.ptr, mc_.activation, lw.gate.n};
+      gemm_s8_glu(xq_.as<int8_t>(), lw.gate.weight.as<int8_t>(), lw.up.weight.as<int8_t>(), rows, lw.gate.n, lw.gate.k,
+                  g, dtype_, gemm_impl_, stream_);
+    }
+    if (mk & 128u)
+      launch_quantize_rows(h_.ptr, dtype_, rows, mc_.ffn_dim, true, xq_.as<int8_t>(), xs_.as<float>(), stream_);
+    if (mk & 256u) dense(lw.down, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
   }
-}
-
-// layers::Embeddings::operator() (common.cc:64-81)
-void LlamaDecoder::embed(const int32_t* ids_d, int64_t rows) {
-  if (embeddings_.kind == DenseWeights::INT8)
-    launch_embedding_s8(embeddings_.weight.as<int8_t>(), embeddings_.scale.as<float>(), ids_d, rows, mc_.d_model, x_.ptr,
-                        dtype_, stream_);
-  else
-    launch_gather_rows(embeddings_.weight.ptr, ids_d, rows, mc_.d_model * dtype_size(dtype_), x_.ptr, stream_);
 }
 
 void LlamaDecoder::project(const void* x_rows, int64_t rows, void* logits_out) {
@@ -557,7 +557,7 @@ void LlamaDecoder::forward_step(const int32_t* ids_d, const int32_t* lens_d, int
   CT2_REQUIRE(batch <= max_batch_, "forward_step: batch exceeds the KV arena");
   embed(ids_d, batch);
   layers_forward(batch, batch, 1, 0, lens_d);
-  project(x_.ptr, batch, logits_out_d);
+  if (step_mask_ & 512u) project(x_.ptr, batch, logits_out_d);
 }
 
 // =============================================================================================
@@ -792,6 +792,10 @@ void Generator::bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, i
   CT2_CUDA_CHECK(cudaMemcpy2DAsync(ids_d_.ptr, sizeof(int32_t), prompt_d_.as<int32_t>() + fwd, prompt_len * sizeof(int32_t),
                                    sizeof(int32_t), batch, cudaMemcpyDeviceToDevice, st));
   launch_fill_i32(lens_d_.as<int32_t>(), batch, static_cast<int32_t>(fwd), st);
+  if (const char* e = std::getenv("CT2B200_STEP_MASK")) {
+    d.set_step_mask(static_cast<unsigned>(std::strtoul(e, nullptr, 0)));
+    if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; graph_batch_ = -1; }
+  }
   const bool use_graph = cfg_.use_cuda_graph != 0;
   if (use_graph) build_step_graph(batch, 0, 0);
   auto step = [&]() {

@@ -124,6 +124,7 @@ class LlamaDecoder {
   void* logits_buffer() const { return logits_.ptr; }       // [max_batch, vocab] T
   int64_t prefill_chunk_rows() const { return chunk_rows_; }
   void set_gemm_impl(int impl) { gemm_impl_ = impl; }
+  void set_step_mask(unsigned m) { step_mask_ = m; }
 
  private:
   void load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w);
@@ -142,6 +143,7 @@ class LlamaDecoder {
   cudaStream_t stream_ = nullptr;
   int64_t max_batch_ = 0, max_len_ = 0, chunk_rows_ = 0;
   int attn_splits_ = 1;
+  unsigned step_mask_ = 0xFFFFFFFFu;
 
   DenseWeights embeddings_;       // int8 [V,d] + scale, or T [V,d]
   DenseWeights projection_;
