@@ -60,6 +60,8 @@ def build(force=False, verbose=True):
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError("link failed:\n%s\n%s" % (r.stdout, r.stderr))
+    import ctypes
+    ctypes.CDLL(OUT)          # fails here (undefined symbols) rather than on the GPU box
     if verbose:
         print("built", OUT)
     return OUT

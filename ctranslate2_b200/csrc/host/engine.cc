@@ -518,6 +518,15 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
   }
 }
 
+// layers::Embeddings::operator() (common.cc:64-81)
+void LlamaDecoder::embed(const int32_t* ids_d, int64_t rows) {
+  if (embeddings_.kind == DenseWeights::INT8)
+    launch_embedding_s8(embeddings_.weight.as<int8_t>(), embeddings_.scale.as<float>(), ids_d, rows, mc_.d_model, x_.ptr,
+                        dtype_, stream_);
+  else
+    launch_gather_rows(embeddings_.weight.ptr, ids_d, rows, mc_.d_model * dtype_size(dtype_), x_.ptr, stream_);
+}
+
 void LlamaDecoder::project(const void* x_rows, int64_t rows, void* logits_out) {
   if (projection_.kind == DenseWeights::INT8) {
     launch_rms_norm(final_gamma_.ptr, x_rows, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),

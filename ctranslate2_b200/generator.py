@@ -34,6 +34,9 @@ class Generator:
         if compute_type not in _COMPUTE:
             raise ValueError(f"Invalid compute type: {compute_type}")
         self.model_path = model_path
+        if not os.path.exists(os.path.join(model_path, "model.bin")):
+            # same failure class as models::Model::load (std::runtime_error)
+            raise RuntimeError("Unable to open file 'model.bin' in model '%s'" % model_path)
         vocab_path = os.path.join(model_path, "vocabulary.json")
         if os.path.exists(vocab_path):
             self._tokens = json.load(open(vocab_path))
