@@ -377,7 +377,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int rloc = q * 32 + lane;               // tile row owned by this thread (= its TMEM lane)
       const int64_t arow = a0 + rloc;
       const uint32_t taddr = tmem_base + buf * kAccCols + (static_cast<uint32_t>(q * 32) << 16);
-      float* my_slot = p.fslots + (static_cast<int64_t>(blockIdx.x) * 2 + (kb0 > 0 ? 0 : 1)) * (kTileM * BN);
+      // partial tiles are parked in per-CTA slots (plain coalesced stores: no atomics, nothing to re-zero, no
+      // same-address contention) and summed by the last arriver in CTA order (deterministic for the float kinds)
+      constexpr int64_t kSlot = static_cast<int64_t>(NB) * kTileM * BN;
+      const int nb_valid = static_cast<int>(min(static_cast<int64_t>(BN), p.rows_b - b0));
+      uint32_t* my_slot = reinterpret_cast<uint32_t*>(p.fslots) + (static_cast<int64_t>(blockIdx.x) * 2 + (kb0 > 0 ? 0 : 1)) * kSlot;
       int c_lo = 0, c_hi = 0;
       EpiInputs<NB, kC> ein;
       if (direct) epi_load<T, KIND, NB, kSwap, kC>(p, arow, b0, ein);   // issued while the MMAs of this segment run
@@ -402,52 +406,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           } else {
             // the epilogue inputs and the reduced accumulators are requested together: one memory round trip
             epi_load<T, KIND, NB, kSwap, kC>(p, arow, b0 + c0, ein);
-            if constexpr (KIND != 0) {
 #pragma unroll
-              for (int j = 0; j < kC; ++j) {
-                float acc = 0.f;
-                for (int c = c_lo; c <= c_hi; ++c)      // fixed CTA order => run-to-run deterministic
-                  acc += __ldcg(p.fslots + (static_cast<int64_t>(c) * 2 + (c == c_lo ? 1 : 0)) * (kTileM * BN) +
-                                static_cast<int64_t>(c0 + j) * kTileM + rloc);
-                r[0][j] = __float_as_uint(acc);
-              }
-            } else {
+            for (int w = 0; w < NB; ++w)
 #pragma unroll
-              for (int j = 0; j < kC; ++j) {
-                const int64_t brow = b0 + c0 + j;
-                const bool ok = arow < p.rows_a && brow < p.rows_b;
-                const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
+              for (int j = 0; j < kC; ++j) r[w][j] = 0u;
+            for (int c = c_lo; c <= c_hi; ++c) {        // fixed CTA order => run-to-run deterministic
+              const uint32_t* sl = reinterpret_cast<const uint32_t*>(p.fslots) + (static_cast<int64_t>(c) * 2 + (c == c_lo ? 1 : 0)) * kSlot;
 #pragma unroll
-                for (int w = 0; w < NB; ++w) r[w][j] = ok ? static_cast<uint32_t>(__ldcg(p.ws + w * plane + off)) : 0u;
-              }
+              for (int w = 0; w < NB; ++w)
 #pragma unroll
-              for (int j = 0; j < kC; ++j) {
-                const int64_t brow = b0 + c0 + j;
-                if (arow < p.rows_a && brow < p.rows_b) {
-                  const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
-#pragma unroll
-                  for (int w = 0; w < NB; ++w) p.ws[w * plane + off] = 0;
+                for (int j = 0; j < kC; ++j) {
+                  if (c0 + j >= nb_valid) continue;
+                  const uint32_t v = __ldcg(sl + (static_cast<int64_t>(w) * BN + c0 + j) * kTileM + rloc);
+                  if constexpr (KIND == 0) r[w][j] += v;                                   // int32 (wrap-around add)
+                  else r[w][j] = __float_as_uint(__uint_as_float(r[w][j]) + __uint_as_float(v));
                 }
-              }
             }
           }
           if (direct || pass == 1) {
             epi_finish<T, KIND, NB, kSwap, kC>(p, r, arow, b0 + c0, ein);
           } else {
 #pragma unroll
-            for (int j = 0; j < kC; ++j) {
-              const int64_t brow = b0 + c0 + j;
-              if (arow >= p.rows_a || brow >= p.rows_b) continue;
-              if constexpr (KIND == 0) {
-                const int64_t off = kSwap ? brow * ldw + arow : arow * ldw + brow;
-                atomicAdd(p.ws + off, static_cast<int32_t>(r[0][j]));
-                if constexpr (NB == 2) atomicAdd(p.ws + plane + off, static_cast<int32_t>(r[1][j]));
-              } else {
-                // float accumulators: no atomics (order-dependent rounding) — each CTA parks its partial tile in
-                // its own slot, [N-side row][128 M-side rows] so that a warp writes 128 contiguous bytes
-                my_slot[static_cast<int64_t>(c0 + j) * kTileM + rloc] = __uint_as_float(r[0][j]);
-              }
-            }
+            for (int w = 0; w < NB; ++w)
+#pragma unroll
+              for (int j = 0; j < kC; ++j)       // [plane][N-side row][128 M-side rows]: a warp writes 128 contiguous bytes
+                if (c0 + j < nb_valid) my_slot[(static_cast<int64_t>(w) * BN + c0 + j) * kTileM + rloc] = r[w][j];
           }
         }
         if (direct || pass == 1) break;
@@ -506,8 +489,7 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   const int64_t units = tiles * p.kb_total;
   int64_t ctas = std::min<int64_t>(wsp.sm_count, units);
   // tiles shared between CTAs go through the scratch: fall back to whole tiles per CTA when it cannot hold them
-  const bool scratch_ok = (KIND == 0 ? static_cast<size_t>(m) * n * NB <= wsp.accum_elems
-                                     : static_cast<size_t>(ctas) * 2 * kTileM * BN <= wsp.accum_elems) &&
+  const bool scratch_ok = static_cast<size_t>(ctas) * 2 * NB * kTileM * BN <= wsp.accum_elems &&
                           static_cast<size_t>(tiles) <= wsp.num_counters;
   static const bool force_whole = [] { const char* e = std::getenv("CT2B200_GEMM_WHOLE"); return e && e[0] == '1'; }();
   p.whole_tiles = (scratch_ok && !force_whole) ? 0 : 1;
