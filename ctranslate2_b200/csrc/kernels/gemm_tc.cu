@@ -42,6 +42,8 @@ struct TcParams {
   int tiles_b;         // N-side tiles of BN rows
   int kb_total;        // K blocks (128 bytes of K each) per output tile
   int whole_tiles;     // 1 = CTA ranges are aligned to whole tiles (no scratch needed)
+  int cluster_s;       // >= 2: thread-block cluster of cluster_s CTAs per tile, split-K reduced through DSMEM
+  int stages;          // smem ring depth actually used (<= TcSmem::kStages; smaller when the DSMEM buffer needs room)
   int part_lo;         // > 0: tile-partitioned split-K — every tile is owned by part_lo (or part_lo + 1) CTAs and every
   int part_rem;        //      CTA works on exactly ONE tile (one reduction round); the first part_rem tiles get +1 CTA
   DenseEpilogue dense;
@@ -63,7 +65,10 @@ struct TcSmem {
 
 // Activation out of line: the epilogue is unrolled over the columns of a chunk, and inlining erff/tanhf/expf
 // into every unrolled copy made the kernels 20-30 k SASS instructions (0.3-0.5 MB), i.e. instruction-fetch bound.
-__device__ __noinline__ float apply_act_call(float x, int act) { return apply_act(x, act); }
+__device__ __noinline__ float apply_act_call(float x, int act) {
+  if (act == CT2B200_ACT_SWISH) return __fdividef(x, 1.f + __expf(-x));     // the hot one (SwiGLU)
+  return apply_act(x, act);
+}
 
 // Epilogue of one thread over kCols (16) consecutive N-side rows of its M-side row `arow`.
 //   kSwap: arow = output channel n, N-side rows = batch rows m;   !kSwap: arow = batch row m, N-side = channels n.
@@ -79,8 +84,10 @@ struct EpiInputs {
 };
 
 template <typename T, int KIND, int NB, bool kSwap, int kCols>
-__device__ __forceinline__ void epi_load(const TcParams& p, int64_t arow, int64_t brow0, EpiInputs<NB, kCols>& in) {
-  in.ncols = arow < p.rows_a ? static_cast<int>(max(static_cast<int64_t>(0), min(static_cast<int64_t>(kCols), p.rows_b - brow0))) : 0;
+__device__ __forceinline__ void epi_load(const TcParams& p, int64_t arow, int64_t brow0, EpiInputs<NB, kCols>& in, int bstep = 1) {
+  // N-side rows brow0, brow0 + bstep, ...: how many of the kCols are inside the matrix
+  const int64_t avail = p.rows_b > brow0 ? (p.rows_b - brow0 + bstep - 1) / bstep : 0;
+  in.ncols = arow < p.rows_a ? static_cast<int>(min(static_cast<int64_t>(kCols), avail)) : 0;
   in.st0 = in.st1 = 1.f;
   in.bias_t = 0.f;
   if (in.ncols == 0) return;
@@ -89,7 +96,7 @@ __device__ __forceinline__ void epi_load(const TcParams& p, int64_t arow, int64_
   const T* residual = static_cast<const T*>(KIND == 0 ? p.dense.residual : p.fl.residual);
   const int64_t ldy = KIND == 0 ? (NB == 2 ? p.glu.ldh : p.dense.ldy) : p.fl.ldy;
   const int64_t base = kSwap ? brow0 * ldy + arow : arow * ldy + brow0;
-  const int64_t step = kSwap ? ldy : 1;
+  const int64_t step = (kSwap ? ldy : 1) * bstep;
   const float* x_scale = NB == 2 ? p.glu.a_scale : p.dense.a_scale;
   const float* w_scale0 = NB == 2 ? p.glu.gate_scale : p.dense.b_scale;
   const float* w_scale1 = p.glu.up_scale;
@@ -107,20 +114,20 @@ __device__ __forceinline__ void epi_load(const TcParams& p, int64_t arow, int64_
     const bool ok = j < in.ncols;
     if constexpr (KIND == 0) {
       if constexpr (kSwap) {
-        in.sj0[j] = ok ? __ldg(x_scale + brow0 + j) : 1.f;
+        in.sj0[j] = ok ? __ldg(x_scale + brow0 + j * bstep) : 1.f;
       } else {
-        in.sj0[j] = ok ? __ldg(w_scale0 + brow0 + j) : 1.f;
-        if constexpr (NB == 2) in.sj1[j] = ok ? __ldg(w_scale1 + brow0 + j) : 1.f;
+        in.sj0[j] = ok ? __ldg(w_scale0 + brow0 + j * bstep) : 1.f;
+        if constexpr (NB == 2) in.sj1[j] = ok ? __ldg(w_scale1 + brow0 + j * bstep) : 1.f;
       }
     }
-    in.bj[j] = (bias && !kSwap && ok) ? to_f32(bias[brow0 + j]) : in.bias_t;
+    in.bj[j] = (bias && !kSwap && ok) ? to_f32(bias[brow0 + j * bstep]) : in.bias_t;
     in.resj[j] = (residual && ok) ? to_f32(residual[base + j * step]) : 0.f;
   }
 }
 
 template <typename T, int KIND, int NB, bool kSwap, int kCols>
 __device__ __forceinline__ void epi_finish(const TcParams& p, const uint32_t (&r)[NB][kCols], int64_t arow, int64_t brow0,
-                                           const EpiInputs<NB, kCols>& in) {
+                                           const EpiInputs<NB, kCols>& in, int bstep = 1) {
   if (in.ncols == 0) return;
   const bool has_bias = (KIND == 0 ? p.dense.bias : p.fl.bias) != nullptr;
   const bool has_res = (KIND == 0 ? p.dense.residual : p.fl.residual) != nullptr;
@@ -128,7 +135,7 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const uint32_t (&r
   const int64_t ldy = KIND == 0 ? (NB == 2 ? p.glu.ldh : p.dense.ldy) : p.fl.ldy;
   const int act = KIND == 0 ? (NB == 2 ? p.glu.act : p.dense.act) : p.fl.act;
   const int64_t base = kSwap ? brow0 * ldy + arow : arow * ldy + brow0;
-  const int64_t step = kSwap ? ldy : 1;
+  const int64_t step = (kSwap ? ldy : 1) * bstep;
   if (KIND == 0 && NB == 1 && p.dense.a_scale == nullptr) {      // raw int32 output (ops::Gemm int8)
 #pragma unroll
     for (int j = 0; j < kCols; ++j)
@@ -147,13 +154,13 @@ __device__ __forceinline__ void epi_finish(const TcParams& p, const uint32_t (&r
     } else if constexpr (NB == 2) {
       const float sx = kSwap ? in.sj0[j] : in.st0;
       const float sg = kSwap ? in.st0 : in.sj0[j], su = kSwap ? in.st1 : in.sj1[j];
-      float gate = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sg));
+      float gate = round_to<T>(__fdividef(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sg));
       gate = round_to<T>(apply_act_call(gate, act));
-      const float up = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[1][j])), sx * su));
+      const float up = round_to<T>(__fdividef(static_cast<float>(static_cast<int32_t>(r[1][j])), sx * su));
       v = gate * up;
     } else {
       const float sx = kSwap ? in.sj0[j] : in.st0, sw = kSwap ? in.st0 : in.sj0[j];
-      v = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sw));
+      v = round_to<T>(__fdividef(static_cast<float>(static_cast<int32_t>(r[0][j])), sx * sw));
       if (has_bias) v = round_to<T>(v + in.bj[j]);
       if (act >= 0) v = round_to<T>(apply_act_call(v, act));
       if (has_res) v = v + in.resj[j];
@@ -198,7 +205,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + kStages * S::kStage);
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + p.stages * S::kStage);      // [kStages] (p.stages used)
   uint64_t* empty_bar = full_bar + kStages;
   uint64_t* tmem_full_bar = empty_bar + kStages;       // [2]
   uint64_t* tmem_empty_bar = tmem_full_bar + 2;        // [2]
@@ -212,7 +219,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   const int64_t T_all = static_cast<int64_t>(p.tiles_a) * p.tiles_b;
   int64_t u_begin, u_end;
   int part_first = 0, part_n = 0;      // partition mode: first CTA and number of CTAs of this CTA's tile
-  if (p.part_lo > 0) {
+  const int CS = p.cluster_s;          // cluster mode: CTAs per tile (= cluster size); rank = blockIdx.x % CS
+  const int crank = CS >= 2 ? static_cast<int>(blockIdx.x % CS) : 0;
+  const int nstages = p.stages;
+  if (CS >= 2) {
+    const int64_t t = blockIdx.x / CS;
+    u_begin = t * KB + crank * KB / CS;
+    u_end = t * KB + (crank + 1) * KB / CS;
+  } else if (p.part_lo > 0) {
     const int big = p.part_rem * (p.part_lo + 1);
     int t, i;
     if (static_cast<int>(blockIdx.x) < big) {
@@ -238,7 +252,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   }
 
   if (threadIdx.x == 0) {
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < p.stages; ++s) {
       mbar_init(full_bar + s, 1);
       mbar_init(empty_bar + s, 1);
     }
@@ -255,6 +269,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();                                 // the next kernel may be scheduled; it waits on our completion
+  // cluster mode: reduction buffer behind the barriers; [src rank][plane][owned column][128 rows] of 32-bit partials
+  uint32_t* red = reinterpret_cast<uint32_t*>(smem + nstages * S::kStage + 512);
+  const int cpr = CS >= 2 ? (BN + CS - 1) / CS : 0;   // columns owned per rank (column j belongs to rank j % CS)
+  if (CS >= 2) asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");   // peers are alive before DSMEM traffic
 
   const CUtensorMap* map_a0 = kSwap ? &tm_w : &tm_x;
   const CUtensorMap* map_a1 = &tm_w2;                   // only when kSwap && NB == 2
@@ -272,7 +290,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       int a0 = (tile % p.tiles_a) * kTileM, b0 = (tile / p.tiles_a) * BN;
       // The weights never depend on the previous kernel: their tiles for the first ring fill are requested BEFORE
       // griddepcontrol.wait (so the pipeline fills during the predecessor's tail); the activation tiles after it.
-      const int64_t prefill = min(static_cast<int64_t>(kStages), u_end - u_begin);
+      const int64_t prefill = min(static_cast<int64_t>(nstages), u_end - u_begin);
       auto issue = [&](int s, int kc, bool weights, bool acts) {
         uint8_t* sa = smem + s * S::kStage;
         uint8_t* sb = sa + S::kA;
@@ -309,8 +327,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           a0 = (tile % p.tiles_a) * kTileM;
           b0 = (tile / p.tiles_a) * BN;
         }
-        const int s = it % kStages;
-        const uint32_t ph = (it / kStages) & 1;
+        const int s = it % nstages;
+        const uint32_t ph = (it / nstages) & 1;
         if (it < prefill) {
           issue(s, kb * BK, false, true);                   // weights of this stage are already in flight
         } else {
@@ -334,8 +352,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         tc_fence_after();
         const uint32_t acc = tmem_base + buf * kAccCols;
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
-          const int s = it % kStages;
-          const uint32_t ph = (it / kStages) & 1;
+          const int s = it % nstages;
+          const uint32_t ph = (it / nstages) & 1;
           mbar_wait(full_bar + s, ph);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + s * S::kStage);
@@ -425,6 +443,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
           }
           if (direct || pass == 1) {
             epi_finish<T, KIND, NB, kSwap, kC>(p, r, arow, b0 + c0, ein);
+          } else if (CS >= 2) {
+            // cluster mode: column j goes to the CTA of rank j % CS (DSMEM store; the owner's own share stays local)
+            if (c0 == 0) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");   // start-up barrier
+#pragma unroll
+            for (int j = 0; j < kC; ++j) {
+              const int col = c0 + j;
+              if (col >= nb_valid) continue;
+              const int owner = col % CS;
+#pragma unroll
+              for (int w = 0; w < NB; ++w) {
+                uint32_t* dst = red + ((static_cast<int64_t>(crank) * NB + w) * cpr + col / CS) * kTileM + rloc;
+                uint32_t raddr;
+                asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(raddr) : "r"(smem_u32(dst)), "r"(owner));
+                asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(raddr), "r"(r[w][j]) : "memory");
+              }
+            }
           } else {
 #pragma unroll
             for (int w = 0; w < NB; ++w)
@@ -433,7 +467,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (c0 + j < nb_valid) my_slot[(static_cast<int64_t>(w) * BN + c0 + j) * kTileM + rloc] = r[w][j];
           }
         }
-        if (direct || pass == 1) break;
+        if (direct || pass == 1 || CS >= 2) break;
         // ---- shared tile: ticket; the last of the contributing CTAs finishes it ----
         __threadfence();
         epi_bar_sync();
@@ -455,6 +489,41 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
   }
 
+  if (CS >= 2) {
+    // every thread of the cluster meets here: all partials have landed in their owners' shared memory
+    __syncwarp();
+    if (warp < 2) asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");     // pending start-up phase
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+    if (warp >= 2 && u_end > u_begin) {
+      // each CTA finishes the columns it owns: sum the CS partials in rank order (deterministic), fused epilogue
+      constexpr int kC2 = 16;
+      const int q = warp & 3;
+      const int rloc = q * 32 + lane;
+      const int64_t tile = u_begin / KB;
+      const int64_t a0 = (tile % p.tiles_a) * kTileM, b0 = (tile / p.tiles_a) * BN;
+      const int64_t arow = a0 + rloc;
+      EpiInputs<NB, kC2> ein;
+      epi_load<T, KIND, NB, kSwap, kC2>(p, arow, b0 + crank, ein, CS);
+      uint32_t r[NB][kC2];
+#pragma unroll
+      for (int w = 0; w < NB; ++w)
+#pragma unroll
+        for (int jj = 0; jj < kC2; ++jj) {
+          uint32_t acc = 0u;
+          if (jj < ein.ncols) {
+            for (int src = 0; src < CS; ++src) {
+              const uint32_t v = red[((static_cast<int64_t>(src) * NB + w) * cpr + jj) * kTileM + rloc];
+              if constexpr (KIND == 0) acc += v;
+              else acc = __float_as_uint(__uint_as_float(acc) + __uint_as_float(v));
+            }
+          }
+          r[w][jj] = acc;
+        }
+      epi_finish<T, KIND, NB, kSwap, kC2>(p, r, arow, b0 + crank, ein, CS);
+    }
+  }
+
   __syncthreads();
   if (warp == 1) {
     __syncwarp();
@@ -472,7 +541,7 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   auto kernel = gemm_tc_kernel<T, KIND, BN, NB, kSwap>;
   static bool configured = false;
   if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S::kBytes)));
+    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     configured = true;
   }
   const CUtensorMap tmx = make_operand_map(x, m, k, elem, KIND, kSwap ? BN : kTileM);
@@ -494,16 +563,61 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   static const bool force_whole = [] { const char* e = std::getenv("CT2B200_GEMM_WHOLE"); return e && e[0] == '1'; }();
   p.whole_tiles = (scratch_ok && !force_whole) ? 0 : 1;
   if (p.whole_tiles) ctas = std::min<int64_t>(wsp.sm_count, tiles);   // tile-aligned CTA ranges
-  // tile-partitioned split-K when there are at least two CTAs per tile: one reduction round per CTA instead of up
-  // to two with stream-K (the reduction costs ~3 L2 round trips, comparable to streaming a whole small GEMM)
   p.part_lo = p.part_rem = 0;
-  if (!p.whole_tiles && ctas >= 2 * tiles && p.kb_total >= 2 * ((ctas + tiles - 1) / tiles)) {
+  p.cluster_s = 0;
+  p.stages = S::kStages;
+  size_t smem_bytes = S::kBytes;
+  static const int mode = [] { const char* e = std::getenv("CT2B200_GEMM_SPLIT"); return e ? std::atoi(e) : 0; }();   // 1 = stream-K, 2 = partition
+  if (kSwap && !force_whole && mode == 0 && tiles < wsp.sm_count) {
+    // Decode GEMMs (fewer tiles than SMs).  Split-K through global memory costs several dependent L2 round trips in
+    // the tail of every CTA, which is comparable to streaming a whole small GEMM; so
+    //  * >= 2 CTAs per tile: thread-block clusters of CS CTAs own one tile, K is split inside the cluster and the
+    //    partial accumulators are exchanged through distributed shared memory (no global traffic, one cluster barrier);
+    //  * otherwise whole tiles (no reduction at all) on as many SMs as there are tiles.
+    int cs = static_cast<int>(wsp.sm_count / tiles);
+    if (cs > 4) cs = 4;                                      // clusters of 4 still fill 132 of 148 SMs
+    if (cs == 3 && tiles * 3 > 132) cs = 2;                  // keep every cluster co-resident
+    while (cs >= 2 && p.kb_total < 2 * cs) --cs;
+    if (cs >= 2) {
+      const size_t red_bytes = static_cast<size_t>(cs) * NB * ((BN + cs - 1) / cs) * kTileM * 4;
+      int stages = S::kStages;
+      while (stages > 2 && static_cast<size_t>(stages) * S::kStage + 1024 + 512 + red_bytes > 227 * 1024) --stages;
+      p.cluster_s = cs;
+      p.stages = stages;
+      p.whole_tiles = 0;
+      ctas = tiles * cs;
+      smem_bytes = static_cast<size_t>(stages) * S::kStage + 1024 + 512 + red_bytes;
+    } else {
+      p.whole_tiles = 1;
+      ctas = tiles;
+    }
+  } else if (!p.whole_tiles && mode != 1 && ctas >= 2 * tiles && p.kb_total >= 2 * ((ctas + tiles - 1) / tiles)) {
+    // tile-partitioned split-K through the global slots: one reduction round per CTA
     p.part_lo = static_cast<int>(ctas / tiles);
     p.part_rem = static_cast<int>(ctas % tiles);
   }
   p.ws = wsp.accum;
   p.fslots = reinterpret_cast<float*>(wsp.accum2);
   p.counters = wsp.counters;
+  if (p.cluster_s >= 2) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(static_cast<unsigned>(ctas));
+    cfg.blockDim = dim3(kTcThreads);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute attr[2];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = p.cluster_s;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    attr[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[1].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = pdl_enabled() ? 2 : 1;
+    CT2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmx, tmw, tmw2, p));
+    check_launch();
+    return;
+  }
   launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kTcThreads), S::kBytes, st, tmx, tmw, tmw2, p);
   check_launch();
 }
