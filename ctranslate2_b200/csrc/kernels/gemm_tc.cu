@@ -541,7 +541,7 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   auto kernel = gemm_tc_kernel<T, KIND, BN, NB, kSwap>;
   static bool configured = false;
   if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
     configured = true;
   }
   const CUtensorMap tmx = make_operand_map(x, m, k, elem, KIND, kSwap ? BN : kTileM);
@@ -581,7 +581,7 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
     if (cs >= 2) {
       const size_t red_bytes = static_cast<size_t>(cs) * NB * ((BN + cs - 1) / cs) * kTileM * 4;
       int stages = S::kStages;
-      while (stages > 2 && static_cast<size_t>(stages) * S::kStage + 1024 + 512 + red_bytes > 227 * 1024) --stages;
+      while (stages > 2 && static_cast<size_t>(stages) * S::kStage + 1024 + 512 + red_bytes > 226 * 1024) --stages;
       p.cluster_s = cs;
       p.stages = stages;
       p.whole_tiles = 0;
