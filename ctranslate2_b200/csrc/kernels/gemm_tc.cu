@@ -503,24 +503,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
       const int64_t tile = u_begin / KB;
       const int64_t a0 = (tile % p.tiles_a) * kTileM, b0 = (tile / p.tiles_a) * BN;
       const int64_t arow = a0 + rloc;
-      EpiInputs<NB, kC2> ein;
-      epi_load<T, KIND, NB, kSwap, kC2>(p, arow, b0 + crank, ein, CS);
-      uint32_t r[NB][kC2];
+#pragma unroll 1
+      for (int jj0 = 0; jj0 < cpr; jj0 += kC2) {          // owned columns jj0.. (global column = (jj0 + jj) * CS + crank)
+        EpiInputs<NB, kC2> ein;
+        const int64_t brow0 = b0 + crank + static_cast<int64_t>(jj0) * CS;
+        epi_load<T, KIND, NB, kSwap, kC2>(p, arow, brow0, ein, CS);
+        uint32_t r[NB][kC2];
 #pragma unroll
-      for (int w = 0; w < NB; ++w)
+        for (int w = 0; w < NB; ++w)
 #pragma unroll
-        for (int jj = 0; jj < kC2; ++jj) {
-          uint32_t acc = 0u;
-          if (jj < ein.ncols) {
-            for (int src = 0; src < CS; ++src) {
-              const uint32_t v = red[((static_cast<int64_t>(src) * NB + w) * cpr + jj) * kTileM + rloc];
-              if constexpr (KIND == 0) acc += v;
-              else acc = __float_as_uint(__uint_as_float(acc) + __uint_as_float(v));
+          for (int jj = 0; jj < kC2; ++jj) {
+            uint32_t acc = 0u;
+            if (jj < ein.ncols) {
+              for (int src = 0; src < CS; ++src) {
+                const uint32_t v = red[((static_cast<int64_t>(src) * NB + w) * cpr + jj0 + jj) * kTileM + rloc];
+                if constexpr (KIND == 0) acc += v;
+                else acc = __float_as_uint(__uint_as_float(acc) + __uint_as_float(v));
+              }
             }
+            r[w][jj] = acc;
           }
-          r[w][jj] = acc;
-        }
-      epi_finish<T, KIND, NB, kSwap, kC2>(p, r, arow, b0 + crank, ein, CS);
+        epi_finish<T, KIND, NB, kSwap, kC2>(p, r, arow, brow0, ein, CS);
+      }
     }
   }
 

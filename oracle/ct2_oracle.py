@@ -359,7 +359,10 @@ def read_model_bin(path: str) -> Tuple[str, int, Dict[str, np.ndarray], Dict[str
                 nbytes = rd("I") * item
                 dt = {4: np.float32, 2: np.int16, 1: np.int8}[item]
             buf = f.read(nbytes)
-            variables[name] = np.frombuffer(buf, dtype=dt).reshape(dims).copy()
+            arr = np.frombuffer(buf, dtype=dt).reshape(dims).copy()
+            if version >= 4 and type_id == 5:      # bfloat16 bit patterns -> float32
+                arr = (arr.astype(np.uint32) << np.uint32(16)).view(np.float32)
+            variables[name] = arr
         if version >= 3:
             for _ in range(rd("I")):
                 alias = rd_str()

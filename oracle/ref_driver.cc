@@ -239,3 +239,19 @@ int ref_gather(const float* data, int n, int d, const int32_t* ids, int m, float
 }
 
 }  // extern "C"
+
+// layers::RotaryEmbeddings (src/layers/attention_layer.cc:178-343) applied to x [1,1,T,dim] at `offset`:
+// lets the tests recover the reference's own sin/cos tables (incl. Linear / Llama3 frequency scaling).
+#include <ctranslate2/layers/attention_layer.h>
+extern "C" int ref_rotary_embeddings(const float* x, int t, int dim, int offset, int interleave, int scaling_type,
+                                     float scaling_factor, float base, float low_freq_factor, float high_freq_factor,
+                                     int original_max_position_embeddings, float* y) {
+  return guarded([&] {
+    layers::RotaryEmbeddings rot(dim, interleave != 0, static_cast<layers::RotaryScalingType>(scaling_type),
+                                 scaling_factor, base, /*num_initial_positions=*/2048, nullptr, nullptr,
+                                 low_freq_factor, high_freq_factor, original_max_position_embeddings, 0, true);
+    StorageView X({1, 1, t, dim}, std::vector<float>(x, x + static_cast<size_t>(t) * dim), Device::CPU);
+    rot.apply(X, offset);
+    std::memcpy(y, X.data<float>(), static_cast<size_t>(t) * dim * sizeof(float));
+  });
+}

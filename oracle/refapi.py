@@ -153,3 +153,19 @@ def gather(data, ids):
     out = np.zeros((ids.size, d), np.float32)
     _check(lib().ref_gather(_p(data), n, d, _p(ids), ids.size, _p(out)))
     return out
+
+
+def rotary_tables(num_positions, dim, base=10000.0, interleave=False, scaling_type=-1, scaling_factor=1.0,
+                  low_freq_factor=1.0, high_freq_factor=4.0, original_max_position_embeddings=0):
+    """sin/cos tables of the reference's layers::RotaryEmbeddings, recovered by rotating an all-ones input
+    (non-interleaved: y_lo = cos - sin, y_hi = cos + sin)."""
+    assert not interleave
+    x = np.ones((num_positions, dim), np.float32)
+    y = np.zeros_like(x)
+    _check(lib().ref_rotary_embeddings(_p(x), num_positions, dim, 0, 0, scaling_type, ctypes.c_float(scaling_factor),
+                                       ctypes.c_float(base), ctypes.c_float(low_freq_factor),
+                                       ctypes.c_float(high_freq_factor), original_max_position_embeddings, _p(y)))
+    h = dim // 2
+    cos = (y[:, :h] + y[:, h:]) / 2
+    sin = (y[:, h:] - y[:, :h]) / 2
+    return np.concatenate([sin, sin], 1), np.concatenate([cos, cos], 1)

@@ -190,3 +190,18 @@ def test_live_reference_synthetic_writer_roundtrip(tmp_path):
     m.reset(2)
     np.testing.assert_allclose(m.forward(prompts.astype(np.int64), 0), ref_logits, atol=2e-5)
     assert m.generate(prompts.astype(np.int64), 10, 10, [2]) == ref_gen
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("kw", [dict(), dict(scaling_type=0, scaling_factor=4.0),
+                                dict(scaling_type=2, scaling_factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
+                                     original_max_position_embeddings=8192)])
+def test_live_reference_rotary_tables(kw):
+    """RotaryEmbeddings::initialize incl. Linear and Llama-3 frequency scaling: oracle tables == the reference's."""
+    for dim in (64, 128):
+        rs, rc = refapi.rotary_tables(300, dim, 500000.0, False, **kw)
+        s, c = O.rotary_tables(300, dim, 500000.0, False, **kw)
+        # angles reach 300 rad, where one float ulp is 3e-5: libm pow/sin vs numpy differ by an ulp of the angle
+        np.testing.assert_allclose(s, rs, atol=1e-4)
+        np.testing.assert_allclose(c, rc, atol=1e-4)
+        assert np.abs(s - rs).mean() < 2e-6
