@@ -426,7 +426,7 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   logits_.alloc(max_batch_ * mc_.vocab * es);
   gathered_.alloc(max_batch_ * mc_.d_model * es);
   attn_splits_ = attention_decode_splits(max_batch_, mc_.num_heads_kv, max_len_, sm_count_);
-  attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, mc_.num_heads, mc_.head_dim, attn_splits_));
+  attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, mc_.num_heads, mc_.head_dim, std::max(attn_splits_, 64)));
   CT2_CUDA_CHECK(cudaMemset(attn_ws_.ptr, 0, attn_ws_.bytes));
   SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
   CT2_CUDA_CHECK(cudaDeviceSynchronize());

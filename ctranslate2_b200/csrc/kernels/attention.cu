@@ -9,6 +9,7 @@
 //    (atomic ticket) merges the partials.  Rotary of q and of the new k, and the K/V append, happen in the
 //    same kernel (the CTA whose slice contains position lens[b] appends).
 //  * rope_append_kernel + attention_prefill_kernel: T new tokens, causal.
+#include <cstdlib>
 #include <algorithm>
 
 #include "../common.cuh"
@@ -351,13 +352,24 @@ void launch_decode_g(const void* qkv, void* kc, void* vc, const float* sn, const
 }  // namespace
 
 int attention_decode_splits(int64_t batch, int Hkv, int64_t max_len, int sm_count) {
-  int64_t ctas = batch * Hkv;
-  int s = static_cast<int>((2 * sm_count + ctas - 1) / ctas);
-  const int max_s = static_cast<int>(std::max<int64_t>(1, max_len / 64));
-  if (s > max_s) s = max_s;
-  if (s > 16) s = 16;
-  if (s < 1) s = 1;
-  return s;
+  // Each (batch row, kv head) is cut into `s` slices of whole 64-key tiles.  Cost model: the kernel is bound by the
+  // per-SM streaming rate, so a candidate s costs  ceil(CTAs / SMs) * (tiles per slice + fixed per-CTA overhead);
+  // the smallest cost wins (ties: fewer slices, which also skips the partial/ticket/combine path when s == 1).
+  if (const char* e = std::getenv("CT2B200_ATTN_SPLITS")) {
+    const int s = std::atoi(e);
+    if (s >= 1 && s <= 64) return s;
+  }
+  const int64_t ctas = batch * Hkv;
+  const int64_t tiles = std::max<int64_t>(1, (max_len + 63) / 64);
+  int best = 1;
+  double best_cost = 1e30;
+  for (int s = 1; s <= 16 && s <= tiles; ++s) {
+    const int64_t per = (tiles + s - 1) / s;
+    const int64_t rounds = (ctas * s + sm_count - 1) / sm_count;
+    const double cost = static_cast<double>(rounds) * (static_cast<double>(per) + 1.5);
+    if (cost < best_cost - 1e-9) { best_cost = cost; best = s; }
+  }
+  return best;
 }
 
 size_t attention_decode_workspace_bytes(int64_t batch, int H, int D, int splits) {
@@ -377,6 +389,11 @@ void launch_attention_decode(const void* qkv, void* kc, void* vc, const float* s
   int32_t* tickets = static_cast<int32_t*>(workspace);
   const size_t toff = ((static_cast<size_t>(batch) * H * sizeof(int32_t) + 255) / 256) * 256;
   float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + toff);
+  // persistent work-balanced kernel (attention_decode.cu) when the workspace holds its 64 slots per (row, head)
+  const int slots = static_cast<int>((workspace_bytes - toff) / (static_cast<size_t>(batch) * H * partial_stride(D) * sizeof(float)));
+  if (launch_attention_decode_persistent(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, D, max_len, interleave, scale, out,
+                                         partials, tickets, slots, dtype, st))
+    return;
   if (launch_attention_decode_mma(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, D, max_len, interleave, scale, out, partials,
                                   tickets, splits, dtype, st))
     return;

@@ -1,0 +1,447 @@
+// attention_decode.cu — single-token (decode) attention as ONE persistent, work-balanced kernel.
+//
+// Replaces, per layer and step, the reference chain  Split(q,k,v) -> Rotary(q,k) -> Concat(cache,k/v) -> MatMul(QK^T)
+// -> SoftMax -> MatMul(PV) -> combine_heads  (src/layers/attention.cc:442-615, 178-287; or the FA2 split-KV path
+// src/ops/flash_attention_gpu.cu:195-366) by one launch that reads every cached K/V byte exactly once.
+//
+// Work decomposition.  A unit is one 64-key tile of one (batch row, KV head); units are numbered row-major
+// (row, KV head, tile) and CTA c of P owns the contiguous range [c*U/P, (c+1)*U/P).  So every SM streams the same
+// number of cache bytes whatever the batch size, the ragged lengths or the KV-head count (the split-KV grid of the
+// previous kernel needed B*Hkv*splits to divide the SM count and paid its prologue/combine once per slice), the
+// cp.async ring never drains between (row, head) pairs, and consecutive units of a CTA are consecutive cache lines.
+//   * a pair that lies inside one CTA is normalised and written directly;
+//   * a pair shared by several CTAs goes through fp32 partials (m, l, O) in the workspace, one slot per contributing
+//     CTA, and the last arriver (ticket) combines them in slot order (deterministic).
+// Inner loop (per tile): the G query heads of the KV head are rows 0..G-1 of a 16-row MMA tile; warp w owns keys
+// [16w, 16w+16): S = Q K^T (mma.sync m16n8k16, fp32), online softmax in fp32, O += P V.  K/V tiles are staged with
+// 16-byte cp.async into XOR-swizzled shared memory (no padding: 96 KB per CTA for D = 128, two CTAs per SM).
+// The new token's rotated K and its V are appended to the cache by the CTA that owns the pair's last tile.
+#include <cstdlib>
+#include <string>
+
+#include "../common.cuh"
+#include "kernels.h"
+#include "mma_common.cuh"
+
+namespace ct2b200 {
+namespace {
+
+using namespace mma;
+
+constexpr int kThreads = 128;
+constexpr int kTile = 64;            // keys per unit
+constexpr int kStages = 3;
+constexpr int kMaxBatch = 1024;      // rows whose tile counts fit the shared prefix table
+constexpr int kSlots = 64;           // partial slots per (row, head) = max CTAs sharing one pair
+
+template <typename T>
+__device__ __forceinline__ float rope_elem(const T* x, const float* sin, const float* cos, int i, int D, bool interleave) {
+  float other;
+  if (interleave) other = (i & 1) ? to_f32(x[i - 1]) : -to_f32(x[i + 1]);
+  else other = (i < D / 2) ? -to_f32(x[i + D / 2]) : to_f32(x[i - D / 2]);
+  return to_f32(x[i]) * cos[i] + other * sin[i];
+}
+
+struct UnitCursor {                  // position in the (row, KV head, tile) enumeration
+  int b, kvh, t, tiles;              // tiles = tiles of row b
+};
+
+template <typename T, int D, int G>
+__global__ void __launch_bounds__(kThreads, 2)
+    attention_decode_persistent_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
+                                       const float* __restrict__ sin_t, const float* __restrict__ cos_t,
+                                       const int32_t* __restrict__ lens, int batch, int H, int Hkv, int64_t max_len,
+                                       bool interleave, float scale_log2, T* __restrict__ out,
+                                       float* __restrict__ partials, int32_t* __restrict__ tickets) {
+  constexpr int CH = D / 8;                       // 16-byte chunks per row
+  constexpr int NW = kThreads / 32;
+  constexpr int kTileElems = kTile * D;
+  constexpr size_t PS = static_cast<size_t>(D) + 2;
+  extern __shared__ __align__(128) uint8_t smem_raw[];
+  T* sK = reinterpret_cast<T*>(smem_raw);                           // [stages][64][D], chunk c of row r at c ^ (r & 7)
+  T* sV = sK + kStages * kTileElems;
+  float* s_q = reinterpret_cast<float*>(sV + kStages * kTileElems);  // [G][D]
+  int* s_pref = reinterpret_cast<int*>(s_q + G * D);                 // [batch + 1] tiles before row b
+  __shared__ float s_m[NW][G], s_l[NW][G];
+  __shared__ int s_last;
+
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
+  const int64_t row_w = static_cast<int64_t>(H + 2 * Hkv) * D;
+
+  griddep_launch();
+  griddep_wait();                                 // qkv and lens come from the previous kernels
+
+  // ---- tiles per row and their prefix sums ----
+  if (warp == 0) {
+    int carry = 0;
+    for (int base = 0; base < batch; base += 32) {
+      const int b = base + lane;
+      int v = b < batch ? (lens[b] + 1 + kTile - 1) / kTile : 0;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int n = __shfl_up_sync(0xffffffffu, v, o);
+        if (lane >= o) v += n;
+      }
+      if (b < batch) s_pref[b + 1] = carry + v;
+      carry += __shfl_sync(0xffffffffu, v, 31);
+    }
+    if (lane == 0) s_pref[0] = 0;
+  }
+  __syncthreads();
+  const int64_t U = static_cast<int64_t>(s_pref[batch]) * Hkv;
+  // no pair may be shared by more than kSlots CTAs: with fewer units than CTAs, use fewer CTAs
+  int max_tiles = 0;
+  for (int b = lane; b < batch; b += 32) max_tiles = max(max_tiles, s_pref[b + 1] - s_pref[b]);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) max_tiles = max(max_tiles, __shfl_xor_sync(0xffffffffu, max_tiles, o));
+  const int min_units = (max_tiles + kSlots - 2) / (kSlots - 1);    // units per CTA so that a pair spans < kSlots CTAs
+  int64_t P = gridDim.x;
+  if (min_units > 1) P = min(P, max(static_cast<int64_t>(1), U / min_units));
+  if (static_cast<int64_t>(blockIdx.x) >= P) return;
+  const int64_t u0 = blockIdx.x * U / P, u1 = (blockIdx.x + 1) * U / P;
+  if (u1 <= u0) return;
+
+  auto cursor_at = [&](int64_t u) {
+    // row b with s_pref[b]*Hkv <= u < s_pref[b+1]*Hkv (rows always have >= 1 tile)
+    int lo = 0, hi = batch - 1;
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if (static_cast<int64_t>(s_pref[mid]) * Hkv <= u) lo = mid; else hi = mid - 1;
+    }
+    UnitCursor c;
+    c.b = lo;
+    c.tiles = s_pref[lo + 1] - s_pref[lo];
+    const int r = static_cast<int>(u - static_cast<int64_t>(s_pref[lo]) * Hkv);
+    c.kvh = r / c.tiles;
+    c.t = r - c.kvh * c.tiles;
+    return c;
+  };
+  auto advance = [&](UnitCursor& c) {
+    if (++c.t == c.tiles) {
+      c.t = 0;
+      if (++c.kvh == Hkv) {
+        c.kvh = 0;
+        ++c.b;
+        c.tiles = c.b < batch ? s_pref[c.b + 1] - s_pref[c.b] : 1;
+      }
+    }
+  };
+  // first and last CTA of the pair that contains unit u (pair = units [base, base + tiles))
+  auto cta_of = [&](int64_t u) { return static_cast<int>(((u + 1) * P - 1) / U); };
+
+  // ---- append the new token's K (rotated) and V for every pair whose last tile is ours ----
+  {
+    UnitCursor c = cursor_at(u0);
+    int64_t u = u0;
+    while (u < u1) {
+      const int64_t last = u + (c.tiles - 1 - c.t);               // unit of this pair's last tile
+      if (last < u1) {
+        const int pos = lens[c.b];
+        const T* k_in = qkv + c.b * row_w + static_cast<int64_t>(H) * D + static_cast<int64_t>(c.kvh) * D;
+        const T* v_in = k_in + static_cast<int64_t>(Hkv) * D;
+        const float* sn = sin_t + static_cast<int64_t>(pos) * D;
+        const float* cs = cos_t + static_cast<int64_t>(pos) * D;
+        T* kc = k_cache + ((static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len + pos) * D;
+        T* vc = v_cache + ((static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len + pos) * D;
+        for (int i = tid; i < D; i += kThreads) {
+          kc[i] = from_f32<T>(rope_elem(k_in, sn, cs, i, D, interleave));
+          vc[i] = v_in[i];
+        }
+      }
+      // jump to the first unit of the next pair
+      u = last + 1;
+      c.t = c.tiles - 1;
+      advance(c);
+    }
+  }
+  __syncthreads();
+
+  // ---- K/V tile loads ----
+  auto load_unit = [&](int stage, const UnitCursor& c) {
+    const int nkeys = lens[c.b] + 1;
+    const int k0 = c.t * kTile;
+    const T* kc = k_cache + (static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len * D;
+    const T* vc = v_cache + (static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len * D;
+    T* dk = sK + stage * kTileElems;
+    T* dv = sV + stage * kTileElems;
+#pragma unroll
+    for (int i = 0; i < kTile * CH / kThreads; ++i) {
+      const int cidx = tid + i * kThreads;
+      const int r = cidx / CH, ch = cidx % CH;
+      const bool ok = k0 + r < nkeys;
+      const int64_t off = static_cast<int64_t>(ok ? k0 + r : k0) * D + ch * 8;
+      const int doff = r * D + ((ch ^ (r & 7)) * 8);
+      cp16(dk + doff, kc + off, ok);
+      cp16(dv + doff, vc + off, ok);
+    }
+  };
+  UnitCursor lc = cursor_at(u0);                   // load cursor (runs kStages - 1 units ahead)
+  int64_t lu = u0;
+#pragma unroll
+  for (int s = 0; s < kStages - 1; ++s) {
+    if (lu < u1) {
+      load_unit(s, lc);
+      advance(lc);
+      ++lu;
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+  }
+
+  UnitCursor cc = cursor_at(u0);                   // compute cursor
+  uint32_t qf[D / 16][2];                          // Q as A fragments: rows 0..G-1 = heads (a0, a2); rows 8..15 are zero
+  float o[D / 8][2];
+  float m_run = -INFINITY, l_run = 0.f;
+  bool seg_start = true;
+  int seg_t0 = cc.t;                               // first tile of the current segment
+  int it = 0;
+  for (int64_t u = u0; u < u1; ++u, ++it) {
+    const int stage = it % kStages;
+    if (lu < u1) {
+      load_unit((it + kStages - 1) % kStages, lc);
+      advance(lc);
+      ++lu;
+    }
+    asm volatile("cp.async.commit_group;\n" ::);
+    const int pos = lens[cc.b];
+    const int nkeys = pos + 1;
+    if (seg_start) {
+      // rotated, pre-scaled queries of this (row, KV head)
+      const T* q_in = qkv + cc.b * row_w + static_cast<int64_t>(cc.kvh) * G * D;
+      const float* sn = sin_t + static_cast<int64_t>(pos) * D;
+      const float* cs = cos_t + static_cast<int64_t>(pos) * D;
+      for (int e = tid; e < G * D; e += kThreads) {
+        const int h = e / D, i = e % D;
+        s_q[e] = rope_elem(q_in + h * D, sn, cs, i, D, interleave) * scale_log2;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        const float* qr = s_q + (g < G ? g : 0) * D + kk * 16 + 2 * t4;
+        const bool real = g < G;
+        qf[kk][0] = real ? pack2<T>(qr[0], qr[1]) : 0u;
+        qf[kk][1] = real ? pack2<T>(qr[8], qr[9]) : 0u;
+      }
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = 0.f;
+      m_run = -INFINITY;
+      l_run = 0.f;
+      seg_t0 = cc.t;
+      seg_start = false;
+    }
+    asm volatile("cp.async.wait_group %0;\n" ::"n"(kStages - 1));
+    __syncthreads();
+
+    // ---- this warp's 16 keys of the tile ----
+    {
+      const T* ks = sK + stage * kTileElems + warp * 16 * D;
+      const T* vs = sV + stage * kTileElems + warp * 16 * D;
+      float s[2][4];
+#pragma unroll
+      for (int j = 0; j < 2; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
+#pragma unroll
+      for (int kk = 0; kk < D / 16; ++kk) {
+        uint32_t bf[4];
+        const int rr = (lane & 7) + (lane >> 4) * 8;
+        const int ch = kk * 2 + ((lane >> 3) & 1);
+        ldsm4(bf, ks + rr * D + ((ch ^ (lane & 7)) * 8));
+        const uint32_t a[4] = {qf[kk][0], 0u, qf[kk][1], 0u};
+        mma16816<T>(s[0], a, bf[0], bf[1]);
+        mma16816<T>(s[1], a, bf[2], bf[3]);
+      }
+      const int kbase = cc.t * kTile + warp * 16;
+      float mx = m_run;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const int key = kbase + j * 8 + 2 * t4 + r;
+          s[j][r] = key < nkeys ? s[j][r] : -INFINITY;
+          mx = fmaxf(mx, s[j][r]);
+        }
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
+      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+      const float corr = (mx == -INFINITY) ? 1.f : exp2f(m_run - mx);
+      m_run = mx;
+      float rs = 0.f;
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          const float pv = (s[j][r] == -INFINITY) ? 0.f : exp2f(s[j][r] - mx);
+          s[j][r] = pv;
+          rs += pv;
+        }
+      l_run = l_run * corr + rs;
+#pragma unroll
+      for (int j = 0; j < D / 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
+      const uint32_t pa[4] = {pack2<T>(s[0][0], s[0][1]), 0u, pack2<T>(s[1][0], s[1][1]), 0u};
+#pragma unroll
+      for (int j = 0; j < D / 8; j += 2) {
+        uint32_t bf[4];
+        const int rr = (lane & 7) + ((lane >> 3) & 1) * 8;
+        const int ch = j + (lane >> 4);
+        ldsm4_t(bf, vs + rr * D + ((ch ^ (lane & 7)) * 8));
+        float c0[4] = {o[j][0], o[j][1], 0.f, 0.f}, c1[4] = {o[j + 1][0], o[j + 1][1], 0.f, 0.f};
+        mma16816<T>(c0, pa, bf[0], bf[1]);
+        mma16816<T>(c1, pa, bf[2], bf[3]);
+        o[j][0] = c0[0]; o[j][1] = c0[1];
+        o[j + 1][0] = c1[0]; o[j + 1][1] = c1[1];
+      }
+    }
+    __syncthreads();                               // the stage is free again (and may serve as scratch below)
+
+    const bool pair_end = cc.t == cc.tiles - 1;
+    if (pair_end || u == u1 - 1) {
+      // ---- end of a segment: merge the 4 warps; scratch = the stage just consumed (refilled only after the sync below)
+      float* s_o = reinterpret_cast<float*>(sK + stage * kTileElems);      // [NW][G][D] fp32 <= 16 KB
+      float ls = l_run;
+      ls += __shfl_xor_sync(0xffffffffu, ls, 1);
+      ls += __shfl_xor_sync(0xffffffffu, ls, 2);
+      if (g < G && t4 == 0) { s_m[warp][g] = m_run; s_l[warp][g] = ls; }
+      if (g < G) {
+#pragma unroll
+        for (int j = 0; j < D / 8; ++j)
+          *reinterpret_cast<float2*>(s_o + (warp * G + g) * D + j * 8 + 2 * t4) = make_float2(o[j][0], o[j][1]);
+      }
+      __syncthreads();
+      const bool whole = seg_t0 == 0 && pair_end;
+      const int64_t pair_base = u - cc.t;                                   // first unit of this pair
+      const int c_first = cta_of(pair_base), c_last = cta_of(pair_base + cc.tiles - 1);
+      const int nsplit = c_last - c_first + 1;
+      const int slot = static_cast<int>(blockIdx.x) - c_first;
+      float* part = partials + (static_cast<int64_t>(cc.b) * H + static_cast<int64_t>(cc.kvh) * G) * kSlots * PS;
+      T* out_row = out + static_cast<int64_t>(cc.b) * H * D + static_cast<int64_t>(cc.kvh) * G * D;
+      for (int e = tid; e < G * D; e += kThreads) {
+        const int h = e / D, i = e % D;
+        float mm = -INFINITY;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) mm = fmaxf(mm, s_m[w][h]);
+        float ll = 0.f, a = 0.f;
+#pragma unroll
+        for (int w = 0; w < NW; ++w) {
+          const float c = s_m[w][h] == -INFINITY ? 0.f : exp2f(s_m[w][h] - mm);
+          ll += s_l[w][h] * c;
+          a += s_o[(w * G + h) * D + i] * c;
+        }
+        if (whole) {
+          out_row[e] = from_f32<T>(a * (1.f / ll));
+        } else {
+          float* ph = part + (static_cast<int64_t>(h) * kSlots + slot) * PS;
+          ph[i] = a;
+          if (i == 0) { ph[D] = mm; ph[D + 1] = ll; }
+        }
+      }
+      if (!whole) {
+        __threadfence();
+        __syncthreads();
+        int32_t* ticket = tickets + cc.b * Hkv + cc.kvh;
+        if (tid == 0) s_last = atomicAdd(ticket, 1) == nsplit - 1;
+        __syncthreads();
+        if (s_last) {
+          __threadfence();
+          // combine the nsplit partials in slot order; scratch: weights [G][64], sums, 1/l
+          float* sw = s_o;                         // [G][kSlots] max -> weight
+          float* sl = s_o + G * kSlots;            // [G][kSlots] sum
+          float* sinv = s_o + 2 * G * kSlots;      // [G]
+          __syncthreads();
+          for (int e = tid; e < G * nsplit; e += kThreads) {
+            const int h = e / nsplit, sidx = e % nsplit;
+            const float* ph = part + (static_cast<int64_t>(h) * kSlots + sidx) * PS;
+            sw[h * kSlots + sidx] = __ldcg(ph + D);
+            sl[h * kSlots + sidx] = __ldcg(ph + D + 1);
+          }
+          __syncthreads();
+          if (tid < G) {
+            float mm = -INFINITY;
+            for (int sidx = 0; sidx < nsplit; ++sidx) mm = fmaxf(mm, sw[tid * kSlots + sidx]);
+            float ll = 0.f;
+            for (int sidx = 0; sidx < nsplit; ++sidx) {
+              const float c = sw[tid * kSlots + sidx] == -INFINITY ? 0.f : exp2f(sw[tid * kSlots + sidx] - mm);
+              sw[tid * kSlots + sidx] = c;
+              ll += sl[tid * kSlots + sidx] * c;
+            }
+            sinv[tid] = 1.f / ll;
+          }
+          __syncthreads();
+          for (int e = tid; e < G * D; e += kThreads) {
+            const int h = e / D, i = e % D;
+            const float* ph = part + static_cast<int64_t>(h) * kSlots * PS + i;
+            float a = 0.f;
+#pragma unroll 4
+            for (int sidx = 0; sidx < nsplit; ++sidx) a += __ldcg(ph + sidx * PS) * sw[h * kSlots + sidx];
+            out_row[e] = from_f32<T>(a * sinv[h]);
+          }
+          if (tid == 0) *ticket = 0;
+        }
+      }
+      __syncthreads();                             // scratch stage released before the next iteration refills it
+      seg_start = true;
+    }
+    advance(cc);
+  }
+  asm volatile("cp.async.wait_group 0;\n" ::);
+}
+
+template <typename T, int D, int G>
+void launch_persistent(const void* qkv, void* kc, void* vc, const float* sn, const float* cs, const int32_t* lens,
+                       int64_t batch, int H, int Hkv, int64_t max_len, bool interleave, float scale, void* out,
+                       float* partials, int32_t* tickets, int sm_count, cudaStream_t st) {
+  auto kernel = attention_decode_persistent_kernel<T, D, G>;
+  const size_t smem = static_cast<size_t>(2 * kStages * kTile * D) * sizeof(T) + static_cast<size_t>(G) * D * sizeof(float) +
+                      (static_cast<size_t>(batch) + 1) * sizeof(int);
+  static bool configured = false;
+  if (!configured) {
+    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
+    configured = true;
+  }
+  const int64_t max_units = batch * Hkv * ((max_len + kTile - 1) / kTile);
+  const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(2 * sm_count, max_units));
+  launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kThreads), smem, st, static_cast<const T*>(qkv),
+             static_cast<T*>(kc), static_cast<T*>(vc), sn, cs, lens, static_cast<int>(batch), H, Hkv, max_len, interleave,
+             scale * 1.4426950408889634f, static_cast<T*>(out), partials, tickets);
+  check_launch();
+}
+
+template <typename T, int D>
+bool launch_persistent_g(const void* qkv, void* kc, void* vc, const float* sn, const float* cs, const int32_t* lens,
+                         int64_t batch, int H, int Hkv, int64_t max_len, bool interleave, float scale, void* out,
+                         float* partials, int32_t* tickets, int sm_count, cudaStream_t st) {
+  switch (H / Hkv) {
+    case 1: launch_persistent<T, D, 1>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sm_count, st); return true;
+    case 2: launch_persistent<T, D, 2>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sm_count, st); return true;
+    case 4: launch_persistent<T, D, 4>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sm_count, st); return true;
+    case 8: launch_persistent<T, D, 8>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sm_count, st); return true;
+    default: return false;
+  }
+}
+
+}  // namespace
+
+// fp16 / bf16, head_dim 64 or 128, G = H / Hkv in {1, 2, 4, 8}, batch <= 1024.  The workspace must hold kSlots (64)
+// partial slots per (row, head): attention_decode_workspace_bytes(batch, H, D, 64).  false = shape not covered.
+bool launch_attention_decode_persistent(const void* qkv, void* kc, void* vc, const float* sn, const float* cs,
+                                        const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
+                                        bool interleave, float scale, void* out, float* partials, int32_t* tickets,
+                                        int slots, int dtype, cudaStream_t st) {
+  static const bool off = [] {
+    const char* e = std::getenv("CT2B200_ATTN_DECODE");
+    return e && (std::string(e) == "simt" || std::string(e) == "split");
+  }();
+  if (off || dtype == CT2B200_F32 || (D != 128 && D != 64) || batch > kMaxBatch || slots < kSlots) return false;
+  int dev = 0, sms = 148;
+  cudaGetDevice(&dev);
+  static int cached_dev = -1, cached_sms = 148;
+  if (cached_dev != dev) {
+    cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
+    cached_dev = dev;
+  }
+  sms = cached_sms;
+  if (dtype == CT2B200_F16) {
+    return D == 128 ? launch_persistent_g<__half, 128>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sms, st)
+                    : launch_persistent_g<__half, 64>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sms, st);
+  }
+  return D == 128 ? launch_persistent_g<__nv_bfloat16, 128>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sms, st)
+                  : launch_persistent_g<__nv_bfloat16, 64>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sms, st);
+}
+
+}  // namespace ct2b200

@@ -21,6 +21,7 @@
 
 #include "../common.cuh"
 #include "gemm_common.cuh"
+#include "kernels.h"
 #include "tc_common.cuh"
 
 namespace ct2b200 {
@@ -569,8 +570,13 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   if (p.whole_tiles) ctas = std::min<int64_t>(wsp.sm_count, tiles);   // tile-aligned CTA ranges
   p.part_lo = p.part_rem = 0;
   p.cluster_s = 0;
-  p.stages = S::kStages;
-  size_t smem_bytes = S::kBytes;
+  // CT2B200_GEMM_SMEM_KB caps the operand ring of the decode (swap) kernels so that the CTAs of two consecutive GEMMs
+  // fit on one SM together: the successor then prefetches its weights while the predecessor drains.
+  static const int smem_cap_kb = [] { const char* e = std::getenv("CT2B200_GEMM_SMEM_KB"); return e ? std::atoi(e) : 0; }();
+  int max_stages = S::kStages;
+  if (kSwap && smem_cap_kb > 0) max_stages = std::max(2, std::min<int>(S::kStages, smem_cap_kb * 1024 / S::kStage));
+  p.stages = max_stages;
+  size_t smem_bytes = static_cast<size_t>(max_stages) * S::kStage + 1024 + 256;
   static const int mode = [] { const char* e = std::getenv("CT2B200_GEMM_SPLIT"); return e ? std::atoi(e) : 0; }();   // 1 = stream-K, 2 = partition
   if (kSwap && !force_whole && mode == 0 && tiles < wsp.sm_count) {
     // Decode GEMMs (fewer tiles than SMs).  Split-K through global memory costs several dependent L2 round trips in
@@ -584,7 +590,7 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
     while (cs >= 2 && p.kb_total < 2 * cs) --cs;
     if (cs >= 2) {
       const size_t red_bytes = static_cast<size_t>(cs) * NB * ((BN + cs - 1) / cs) * kTileM * 4;
-      int stages = S::kStages;
+      int stages = max_stages;
       while (stages > 2 && static_cast<size_t>(stages) * S::kStage + 1024 + 512 + red_bytes > 226 * 1024) --stages;
       p.cluster_s = cs;
       p.stages = stages;
@@ -622,7 +628,7 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
     check_launch();
     return;
   }
-  launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kTcThreads), S::kBytes, st, tmx, tmw, tmw2, p);
+  launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kTcThreads), smem_bytes, st, tmx, tmw, tmw2, p);
   check_launch();
 }
 
@@ -642,6 +648,7 @@ void gemm_s8_tc(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t 
                 int dtype, cudaStream_t st) {
   if (M == 0 || N == 0) return;
   CT2_REQUIRE(K % 16 == 0, "gemm_s8: k must be a multiple of 16");
+  if (gemm_s8_decode(A, B, M, N, K, epi, dtype, st)) return;
   TcParams p{};
   p.dense = epi;
   CT2_DISPATCH_DTYPE(dtype, (launch_tc_shape<T, 0, 1>(A, B, nullptr, M, N, K, p, st)));
@@ -651,6 +658,7 @@ void gemm_s8_glu_tc(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int
                     const GluEpilogue& glu, int dtype, cudaStream_t st) {
   if (M == 0 || N == 0) return;
   CT2_REQUIRE(K % 16 == 0, "gemm_s8: k must be a multiple of 16");
+  if (gemm_s8_glu_decode(A, Bgate, Bup, M, N, K, glu, dtype, st)) return;
   TcParams p{};
   p.glu = glu;
   CT2_DISPATCH_DTYPE(dtype, (launch_tc_shape<T, 0, 2>(A, Bgate, Bup, M, N, K, p, st)));
@@ -662,6 +670,7 @@ void gemm_f16_tc(const void* A, const void* B, const void* bias, const void* res
   if (M == 0 || N == 0) return;
   CT2_REQUIRE(K % 8 == 0, "gemm_f16: k must be a multiple of 8");
   CT2_REQUIRE(dtype == CT2B200_F16 || dtype == CT2B200_BF16, "gemm_f16: dtype must be float16 or bfloat16");
+  if (gemm_f16_decode(A, B, bias, residual, act, M, N, K, C, dtype, st)) return;
   TcParams p{};
   p.fl = FloatEpilogue{bias, residual, C, act, N};
   if (dtype == CT2B200_F16) launch_tc_shape<__half, 1, 1>(A, B, nullptr, M, N, K, p, st);

@@ -41,6 +41,14 @@ void gemm_s8_glu_tc(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int
 void gemm_f16_tc(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
                  int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
 
+// gemm_decode.cu (tcgen05, m <= 64): false = shape not covered, use the general kernel
+bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
+                    int dtype, cudaStream_t st);
+bool gemm_s8_glu_decode(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
+                        const GluEpilogue& glu, int dtype, cudaStream_t st);
+bool gemm_f16_decode(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
+                     int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
+
 // dispatch by ct2b200_gemm_impl
 void gemm_s8(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
              int dtype, int impl, cudaStream_t st);
@@ -84,6 +92,11 @@ void launch_attention_prefill_simple(const void* qkv, const void* kc, const void
 bool launch_attention_prefill_mma(const void* qkv, const void* kc, const void* vc, int64_t batch, int64_t time,
                                   int64_t offset, int H, int Hkv, int D, int64_t max_len, float scale, void* out,
                                   int dtype, cudaStream_t st);
+// attention_decode.cu — persistent work-balanced decode attention; false = shape not covered
+bool launch_attention_decode_persistent(const void* qkv, void* kc, void* vc, const float* sn, const float* cs,
+                                        const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
+                                        bool interleave, float scale, void* out, float* partials, int32_t* tickets,
+                                        int slots, int dtype, cudaStream_t st);
 bool launch_attention_decode_mma(const void* qkv, void* kc, void* vc, const float* sn, const float* cs,
                                  const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
                                  bool interleave, float scale, void* out, float* partials, int32_t* tickets, int splits,

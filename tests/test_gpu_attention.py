@@ -26,9 +26,15 @@ def ref_attention(q, k, v, G):
 @pytest.mark.parametrize("dt", ["float32", "float16", "bfloat16"])
 @pytest.mark.parametrize("cfg", [dict(B=1, H=32, Hkv=8, D=128, lens=[700]), dict(B=3, H=8, Hkv=2, D=128, lens=[0, 5, 130]),
                                  dict(B=2, H=4, Hkv=4, D=64, lens=[63, 64]), dict(B=4, H=4, Hkv=2, D=32, lens=[1, 2, 3, 300]),
-                                 dict(B=2, H=8, Hkv=1, D=128, lens=[17, 257])])
+                                 dict(B=2, H=8, Hkv=1, D=128, lens=[17, 257]),
+                                 # many ragged rows: (row, head) pairs start and end in the middle of a CTA's unit range
+                                 dict(B=40, H=32, Hkv=8, D=128, lens="ragged"),
+                                 dict(B=5, H=16, Hkv=2, D=64, lens=[1023, 0, 511, 64, 65]),
+                                 dict(B=33, H=8, Hkv=8, D=128, lens="ragged")])
 def test_attention_decode(dt, cfg):
     B, H, Hkv, D, lens = cfg["B"], cfg["H"], cfg["Hkv"], cfg["D"], cfg["lens"]
+    if lens == "ragged":
+        lens = np.random.default_rng(B).integers(0, 1000, size=B).tolist()
     G, max_len = H // Hkv, 1024
     r = np.random.default_rng(B * 31 + H)
     qkv = round_through(r.standard_normal((B, (H + 2 * Hkv) * D)), dt)

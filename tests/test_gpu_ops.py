@@ -162,6 +162,55 @@ def test_gemm_f16_tcgen05(dt, mnk):
     np.testing.assert_allclose(to_np(c), ref, rtol=TOL[dt], atol=TOL[dt] * float(np.abs(ref).max()))
 
 
+@gpu
+@pytest.mark.parametrize("cs", [1, 2, 3, 4])
+@pytest.mark.parametrize("rows", [128, 104, 64])
+def test_decode_gemm_plans(cs, rows, monkeypatch):
+    """gemm_decode.cu: every cluster size (split-K through DSMEM) and tile height the planner can pick, pinned with
+    CT2B200_GEMM_CS / CT2B200_GEMM_ROWS; fp32 output => any lost or doubled partial shows up at 2e-5."""
+    monkeypatch.setenv("CT2B200_GEMM_CS", str(cs))
+    monkeypatch.setenv("CT2B200_GEMM_ROWS", str(rows))
+    r = np.random.default_rng(cs * 1000 + rows)
+    n, k = 1000, 1536                                    # ragged last tile; 12 K blocks
+    w = (r.standard_normal((n, k)) * 0.05).astype(np.float32)
+    wq, ws = O.quantize_weight(w)
+    wu, su = O.quantize_weight((r.standard_normal((n, k)) * 0.05).astype(np.float32))
+    for m in (1, 16, 17, 33, 64):
+        for dt in ("float32", "float16"):
+            x = round_through(r.standard_normal((m, k)), dt)
+            res = round_through(r.standard_normal((m, n)), dt)
+            xq, xs = ops.Quantize()(dev(x, TDT[dt]))
+            tol = TOL[dt] if dt != "float32" else 2e-5
+            y = ops.dense_int8(xq, xs, dev(wq), dev(ws), None, dev(res, TDT[dt]), None, TDT[dt], ops.GEMM_TCGEN05)
+            ref = O.dense_int8(x, wq, ws, None, -1, res, "cuda")
+            np.testing.assert_allclose(to_np(y), ref, rtol=tol, atol=tol * max(1.0, float(np.abs(ref).max())))
+            h = ops.dense_int8_glu(xq, xs, dev(wq), dev(ws), dev(wu), dev(su), ops.ActivationType.Swish, TDT[dt],
+                                   ops.GEMM_TCGEN05)
+            gate = round_through(O.dense_int8(x, wq, ws, None, O.ACT_SWISH), dt)
+            ref = gate * round_through(O.dense_int8(x, wu, su), dt)
+            np.testing.assert_allclose(to_np(h), ref, rtol=tol, atol=tol * max(1.0, float(np.abs(ref).max())))
+        a = round_through(r.standard_normal((m, k)), "float16")
+        b = round_through(r.standard_normal((n, k)) * 0.05, "float16")
+        c = ops.Gemm()(dev(a, TDT["float16"]), dev(b, TDT["float16"]))
+        ref = a.astype(np.float64) @ b.astype(np.float64).T
+        np.testing.assert_allclose(to_np(c), ref, rtol=TOL["float16"], atol=TOL["float16"] * float(np.abs(ref).max()))
+
+
+@gpu
+def test_decode_gemm_auto_plan_llama_shapes():
+    """The shapes of one Llama-3-8B decode layer through the planner's own choice (no pinning), batch 1 and 32."""
+    r = np.random.default_rng(8)
+    for n, k in ((6144, 4096), (4096, 4096), (4096, 14336)):
+        w = (r.standard_normal((n, k)) * 0.05).astype(np.float32)
+        wq, ws = O.quantize_weight(w)
+        for m in (1, 32):
+            x = r.standard_normal((m, k)).astype(np.float32)
+            xq, xs = ops.Quantize()(dev(x, TDT["float32"]))
+            y = ops.dense_int8(xq, xs, dev(wq), dev(ws), None, None, None, TDT["float32"], ops.GEMM_TCGEN05)
+            ref = O.dense_int8(x, wq, ws, None, -1, None, "cuda")
+            np.testing.assert_allclose(to_np(y), ref, rtol=2e-5, atol=2e-5 * float(np.abs(ref).max()))
+
+
 # ---------------- RMSNorm / Rotary / SoftMax / TopK / Gather / Embeddings ----------------
 @gpu
 @pytest.mark.parametrize("dt", DTYPES)
