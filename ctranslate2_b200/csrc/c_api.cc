@@ -331,13 +331,17 @@ CT2B200_API int ct2b200_bench_decode(ct2b200_generator* g, int64_t batch, int64_
   });
 }
 
-CT2B200_API int ct2b200_nccl_unique_id(void*) {
-  g_error = "tensor parallel is not built in this revision";
-  return 3;
+CT2B200_API int ct2b200_generator_tp_handle(ct2b200_generator* g, void* handle64_h) {
+  return guarded([&] {
+    CT2_REQUIRE(g && handle64_h, "null argument");
+    g->impl->decoder().tp_handle(handle64_h);
+  });
 }
-CT2B200_API int ct2b200_generator_set_nccl(ct2b200_generator*, const void*) {
-  g_error = "tensor parallel is not built in this revision";
-  return 3;
+CT2B200_API int ct2b200_generator_tp_connect(ct2b200_generator* g, const void* handles_h, int num_handles) {
+  return guarded([&] {
+    CT2_REQUIRE(g && handles_h, "null argument");
+    g->impl->decoder().tp_connect(handles_h, num_handles);
+  });
 }
 
 }  // extern "C"

@@ -13,6 +13,7 @@
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
+#include <tuple>
 #include <fstream>
 #include <sstream>
 
@@ -242,8 +243,93 @@ DeviceBuffer LlamaDecoder::load_float_vector(const ModelFile& f, const std::stri
   return b;
 }
 
-void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w) {
+namespace {
+// rows [b, e) of a dimension split evenly over the tensor-parallel ranks
+std::pair<int64_t, int64_t> shard_range(int64_t total, int rank, int world) {
+  CT2_REQUIRE(total % world == 0, "tensor parallel: dimension is not divisible by the number of ranks");
+  const int64_t per = total / world;
+  return {rank * per, (rank + 1) * per};
+}
+}  // namespace
+
+void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w, Shard shard) {
   const HostVariable& wt = f.get(prefix + "/weight");
+  if (tp_.world > 1 && shard != REPLICATED) {
+    // Tensor-parallel partition (model.cc:662-743): column-parallel layers keep a slice of the output channels
+    // (for the fused QKV: this rank's query heads, key heads and value heads), row-parallel layers a slice of K.
+    // The int8 values and the per-channel scales are those of the unsharded matrix (the scale of a row-parallel
+    // weight still spans the whole row), so the shards reproduce the single-GPU arithmetic exactly.
+    CT2_REQUIRE(wt.type_id == 1 || wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5,
+                "tensor parallel supports INT8 and float16/bfloat16 weights (AWQ shards are not implemented)");
+    CT2_REQUIRE(wt.shape.size() == 2, "weight must be a matrix");
+    const int64_t N = wt.shape[0], K = wt.shape[1];
+    const bool int8 = wt.type_id == 1;
+    CT2_REQUIRE(int8 || dtype_ != CT2B200_F32, "float weights need compute type float16 or bfloat16 on this engine");
+    std::vector<uint8_t> conv;
+    const uint8_t* src = wt.data;
+    size_t es = 1;
+    if (!int8) {
+      conv = convert_to_dtype(wt, dtype_);
+      src = conv.data();
+      es = dtype_size(dtype_);
+    }
+    std::vector<std::pair<int64_t, int64_t>> row_ranges;      // output channels kept
+    int64_t k0 = 0, k1 = K;
+    if (shard == ROWS) {
+      row_ranges.push_back(shard_range(N, tp_.rank, tp_.world));
+    } else if (shard == QKV_ROWS) {
+      const int64_t D = mc_.head_dim, hq = static_cast<int64_t>(mc_.num_heads) * D, hk = static_cast<int64_t>(mc_.num_heads_kv) * D;
+      CT2_REQUIRE(N == hq + 2 * hk, "fused QKV weight has an unexpected number of rows");
+      const auto q = shard_range(mc_.num_heads, tp_.rank, tp_.world), kv = shard_range(mc_.num_heads_kv, tp_.rank, tp_.world);
+      row_ranges.push_back({q.first * D, q.second * D});
+      row_ranges.push_back({hq + kv.first * D, hq + kv.second * D});
+      row_ranges.push_back({hq + hk + kv.first * D, hq + hk + kv.second * D});
+    } else {
+      row_ranges.push_back({0, N});
+      std::tie(k0, k1) = shard_range(K, tp_.rank, tp_.world);
+    }
+    int64_t n_local = 0;
+    for (auto& rr : row_ranges) n_local += rr.second - rr.first;
+    const int64_t k_local = k1 - k0;
+    std::vector<uint8_t> host(static_cast<size_t>(n_local) * k_local * es);
+    std::vector<float> host_scale;
+    const HostVariable* sc = int8 ? &f.get(prefix + "/weight_scale") : nullptr;
+    if (int8) CT2_REQUIRE(sc->type_id == 0 && sc->size() == N, "weight_scale must be float32 [n]");
+    int64_t o = 0;
+    for (auto& rr : row_ranges)
+      for (int64_t i = rr.first; i < rr.second; ++i, ++o) {
+        std::memcpy(host.data() + static_cast<size_t>(o) * k_local * es, src + (static_cast<size_t>(i) * K + k0) * es,
+                    static_cast<size_t>(k_local) * es);
+        if (int8) {
+          float sv;
+          std::memcpy(&sv, sc->data + 4 * i, 4);
+          host_scale.push_back(sv);
+        }
+      }
+    w.kind = int8 ? DenseWeights::INT8 : DenseWeights::FLOAT16;
+    w.n = n_local;
+    w.k = k_local;
+    upload(w.weight, host.data(), host.size());
+    if (int8) upload(w.scale, host_scale.data(), host_scale.size() * 4);
+    mc_.weight_bytes += host.size() + host_scale.size() * 4;
+    if (const HostVariable* b = f.find(prefix + "/bias")) {
+      // column-parallel: the bias slice; row-parallel: the whole bias on rank 0 only (common.cc:348-352)
+      const auto bytes = convert_to_dtype(*b, dtype_);
+      const size_t bes = dtype_size(dtype_);
+      if (shard == COLS) {
+        if (tp_.rank == 0) upload(w.bias, bytes.data(), bytes.size());
+      } else {
+        std::vector<uint8_t> hb(static_cast<size_t>(n_local) * bes);
+        int64_t ob = 0;
+        for (auto& rr : row_ranges) {
+          std::memcpy(hb.data() + ob * bes, bytes.data() + rr.first * bes, (rr.second - rr.first) * bes);
+          ob += rr.second - rr.first;
+        }
+        upload(w.bias, hb.data(), hb.size());
+      }
+    }
+    return;
+  }
   if (wt.type_id == 1) {                       // INT8 weights with per-row fp32 scales (model_spec.py:222-243)
     CT2_REQUIRE(wt.shape.size() == 2, "int8 weight must be a matrix");
     w.kind = DenseWeights::INT8;
@@ -316,6 +402,9 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   gemm_impl_ = cfg.gemm_impl;
   max_batch_ = std::max<int64_t>(1, cfg.max_batch);
   max_len_ = std::max<int64_t>(16, cfg.max_length);
+  tp_.world = std::max(1, cfg.tp_size);
+  tp_.rank = cfg.tp_rank;
+  CT2_REQUIRE(tp_.world <= 8 && tp_.rank >= 0 && tp_.rank < tp_.world, "tensor parallel: rank/size out of range (size <= 8)");
 
   if (f.spec_name != "TransformerDecoderSpec")
     throw std::invalid_argument("ct2b200 serves TransformerDecoderSpec models; got " + f.spec_name);
@@ -346,6 +435,11 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   CT2_REQUIRE(f.find("decoder/layer_0/self_attention/layer_norm/beta") == nullptr, "only RMSNorm decoders are supported");
   CT2_REQUIRE(mc_.rotary_scaling_type != 1, "Su rotary scaling is not supported");
   mc_.ffn_dim = f.get("decoder/layer_0/ffn/linear_0/weight").shape[0];
+  CT2_REQUIRE(mc_.num_heads % tp_.world == 0 && mc_.num_heads_kv % tp_.world == 0 && mc_.ffn_dim % tp_.world == 0,
+              "tensor parallel: heads, kv heads and ffn width must be divisible by the number of ranks");
+  heads_ = mc_.num_heads / tp_.world;
+  heads_kv_ = mc_.num_heads_kv / tp_.world;
+  ffn_ = mc_.ffn_dim / tp_.world;
 
   // --- weights ---
   load_dense(f, "decoder/embeddings", embeddings_);
@@ -358,11 +452,11 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
     LayerWeights& lw = layers_[l];
     lw.attn_gamma = load_float_vector(f, p + "self_attention/layer_norm/gamma");
     lw.ffn_gamma = load_float_vector(f, p + "ffn/layer_norm/gamma");
-    load_dense(f, p + "self_attention/linear_0", lw.qkv);
-    load_dense(f, p + "self_attention/linear_1", lw.out);
-    load_dense(f, p + "ffn/linear_0", lw.gate);
-    load_dense(f, p + "ffn/linear_0_noact", lw.up);
-    load_dense(f, p + "ffn/linear_1", lw.down);
+    load_dense(f, p + "self_attention/linear_0", lw.qkv, QKV_ROWS);
+    load_dense(f, p + "self_attention/linear_1", lw.out, COLS);
+    load_dense(f, p + "ffn/linear_0", lw.gate, ROWS);
+    load_dense(f, p + "ffn/linear_0_noact", lw.up, ROWS);
+    load_dense(f, p + "ffn/linear_1", lw.down, COLS);
   }
 
   // --- rotary tables, fp32 (RotaryEmbeddings::initialize, attention_layer.cc:252-343) ---
@@ -401,7 +495,7 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
 
   // --- KV arena + activations ---
   const size_t es = dtype_size(dtype_);
-  const size_t cache_bytes = static_cast<size_t>(max_batch_) * mc_.num_heads_kv * max_len_ * mc_.head_dim * es;
+  const size_t cache_bytes = static_cast<size_t>(max_batch_) * heads_kv_ * max_len_ * mc_.head_dim * es;
   k_cache_.resize(mc_.num_layers);
   v_cache_.resize(mc_.num_layers);
   for (int l = 0; l < mc_.num_layers; ++l) {
@@ -410,13 +504,13 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   }
   chunk_rows_ = std::max<int64_t>(max_batch_, std::min<int64_t>(8192, max_batch_ * max_len_));
   const int64_t R = chunk_rows_;
-  const int64_t qkv_w = static_cast<int64_t>(mc_.num_heads + 2 * mc_.num_heads_kv) * mc_.head_dim;
+  const int64_t qkv_w = static_cast<int64_t>(heads_ + 2 * heads_kv_) * mc_.head_dim;
   x_.alloc(R * mc_.d_model * es);
   xq_.alloc(R * std::max(mc_.d_model, mc_.ffn_dim));
   xs_.alloc(R * sizeof(float));
   qkv_.alloc(R * qkv_w * es);
-  attn_.alloc(R * mc_.num_heads * mc_.head_dim * es);
-  h_.alloc(R * mc_.ffn_dim * es);
+  attn_.alloc(R * heads_ * mc_.head_dim * es);
+  h_.alloc(R * ffn_ * es);
   if (layers_[0].qkv.kind != DenseWeights::INT8 || projection_.kind != DenseWeights::INT8) {
     xn_.alloc(R * mc_.d_model * es);
     scratch_mn_.alloc(R * mc_.ffn_dim * es);
@@ -425,9 +519,24 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   }
   logits_.alloc(max_batch_ * mc_.vocab * es);
   gathered_.alloc(max_batch_ * mc_.d_model * es);
-  attn_splits_ = attention_decode_splits(max_batch_, mc_.num_heads_kv, max_len_, sm_count_);
-  attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, mc_.num_heads, mc_.head_dim, std::max(attn_splits_, 64)));
+  attn_splits_ = attention_decode_splits(max_batch_, heads_kv_, max_len_, sm_count_);
+  attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, heads_, mc_.head_dim, std::max(attn_splits_, 64)));
   CT2_CUDA_CHECK(cudaMemset(attn_ws_.ptr, 0, attn_ws_.bytes));
+  if (tp_.world > 1) {
+    // exchange buffer of this rank: [flags 2x8 u32 | pad to 256] [amax words 2 x 8 x R] [partials 2 x R x d_model]
+    CT2_REQUIRE(layers_[0].qkv.kind != DenseWeights::AWQ_GEMM && layers_[0].qkv.kind != DenseWeights::AWQ_GEMV,
+                "tensor parallel: AWQ models are not sharded yet");
+    tp_.flags_off = 0;
+    tp_.amax_off = 256;
+    const size_t amax_bytes = static_cast<size_t>(2) * 8 * R * sizeof(unsigned long long);
+    const size_t part_bytes = ((static_cast<size_t>(R) * mc_.d_model * es + 255) / 256) * 256;
+    tp_.part_off[0] = tp_.amax_off + ((amax_bytes + 255) / 256) * 256;
+    tp_.part_off[1] = tp_.part_off[0] + part_bytes;
+    tp_.exchange.alloc(tp_.part_off[1] + part_bytes);
+    CT2_CUDA_CHECK(cudaMemset(tp_.exchange.ptr, 0, tp_.exchange.bytes));
+    tp_.tick.alloc(256);
+    CT2_CUDA_CHECK(cudaMemset(tp_.tick.ptr, 0, 256));
+  }
   SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
   CT2_CUDA_CHECK(cudaDeviceSynchronize());
 }
@@ -451,6 +560,10 @@ void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* x
 }
 
 void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d) {
+  if (tp_.world > 1) {
+    layers_forward_tp(rows, batch, time, offset, lens_d);
+    return;
+  }
   const int H = mc_.num_heads, Hkv = mc_.num_heads_kv, D = mc_.head_dim;
   const float scale = 1.f / std::sqrt(static_cast<float>(D));
   const bool int8 = layers_[0].qkv.kind == DenseWeights::INT8;
@@ -516,6 +629,110 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
       launch_quantize_rows(h_.ptr, dtype_, rows, mc_.ffn_dim, true, xq_.as<int8_t>(), xs_.as<float>(), stream_);
     if (mk & 256u) dense(lw.down, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
   }
+}
+
+// Tensor-parallel layer stack (one process per GPU).  Per layer, rank r computes its heads / FFN columns; the two
+// all-reduces of the reference (attention.cc:608-612, transformer.cc:45-48) are fused into the next kernel on the
+// residual stream and the activation all-gather before a row-parallel INT8 Dense (common.cc:360-387) into the
+// quantization kernel (kernels/tp_rows.cu).  Sync point indices of a pass: 4l amax(attention out), 4l+1 sum(out-proj),
+// 4l+2 amax(ffn hidden), 4l+3 sum(down-proj).
+void LlamaDecoder::layers_forward_tp(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d) {
+  CT2_REQUIRE(tp_.connected, "tensor parallel: call ct2b200_generator_tp_connect before running the model");
+  const int H = heads_, Hkv = heads_kv_, D = mc_.head_dim;
+  const float scale = 1.f / std::sqrt(static_cast<float>(D));
+  const bool int8 = layers_[0].qkv.kind == DenseWeights::INT8;
+  const TpLink& tp = tp_.link;
+  void* part[2] = {static_cast<uint8_t*>(tp_.exchange.ptr) + tp_.part_off[0],
+                   static_cast<uint8_t*>(tp_.exchange.ptr) + tp_.part_off[1]};
+  launch_tp_tick(tp_.tick.as<uint32_t>(), stream_);
+  auto attention = [&](int l) {
+    if (lens_d) {
+      launch_attention_decode(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, sin_.as<float>(), cos_.as<float>(), lens_d,
+                              batch, H, Hkv, D, max_len_, mc_.rotary_interleave, scale, attn_.ptr, attn_ws_.ptr,
+                              attn_ws_.bytes, attn_splits_, dtype_, stream_);
+    } else {
+      launch_rope_append(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, sin_.as<float>(), cos_.as<float>(), nullptr,
+                         batch, time, offset, H, Hkv, D, max_len_, mc_.rotary_interleave, dtype_, stream_);
+      launch_attention_prefill(qkv_.ptr, k_cache_[l].ptr, v_cache_[l].ptr, nullptr, batch, time, offset, H, Hkv, D,
+                               max_len_, scale, attn_.ptr, dtype_, stream_);
+    }
+  };
+  for (int l = 0; l < mc_.num_layers; ++l) {
+    LayerWeights& lw = layers_[l];
+    if (int8) {
+      if (l == 0)
+        launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
+                        xs_.as<float>(), dtype_, stream_);
+      else
+        launch_tp_reduce_norm_quantize(tp, 1, 4 * (l - 1) + 3, x_.ptr, lw.attn_gamma.ptr, rows, mc_.d_model, mc_.eps,
+                                       xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
+      dense(lw.qkv, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, qkv_.ptr);
+      attention(l);
+      launch_tp_quantize_rows(tp, 0, 4 * l, attn_.ptr, rows, static_cast<int64_t>(H) * D, xq_.as<int8_t>(),
+                              xs_.as<float>(), dtype_, stream_);
+      dense(lw.out, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, part[0]);
+      launch_tp_reduce_norm_quantize(tp, 0, 4 * l + 1, x_.ptr, lw.ffn_gamma.ptr, rows, mc_.d_model, mc_.eps,
+                                     xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
+      GluEpilogue g{xs_.as<float>(), lw.gate.scale.as<float>(), lw.up.scale.as<float>(), h_.ptr, mc_.activation, lw.gate.n};
+      gemm_s8_glu(xq_.as<int8_t>(), lw.gate.weight.as<int8_t>(), lw.up.weight.as<int8_t>(), rows, lw.gate.n, lw.gate.k, g,
+                  dtype_, gemm_impl_, stream_);
+      launch_tp_quantize_rows(tp, 1, 4 * l + 2, h_.ptr, rows, ffn_, xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
+      dense(lw.down, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, part[1]);
+    } else {
+      if (l == 0)
+        launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, xn_.ptr, nullptr, nullptr, dtype_, stream_);
+      else
+        launch_tp_reduce_norm(tp, 1, 4 * (l - 1) + 3, x_.ptr, lw.attn_gamma.ptr, rows, mc_.d_model, mc_.eps, xn_.ptr, dtype_, stream_);
+      dense(lw.qkv, nullptr, nullptr, xn_.ptr, rows, nullptr, -1, qkv_.ptr);
+      attention(l);
+      dense(lw.out, nullptr, nullptr, attn_.ptr, rows, nullptr, -1, part[0]);
+      launch_tp_reduce_norm(tp, 0, 4 * l + 1, x_.ptr, lw.ffn_gamma.ptr, rows, mc_.d_model, mc_.eps, xn_.ptr, dtype_, stream_);
+      dense(lw.gate, nullptr, nullptr, xn_.ptr, rows, nullptr, mc_.activation, h_.ptr);
+      dense(lw.up, nullptr, nullptr, xn_.ptr, rows, nullptr, -1, scratch_mn_.ptr);
+      launch_mul_inplace(h_.ptr, scratch_mn_.ptr, rows * ffn_, dtype_, stream_);
+      dense(lw.down, nullptr, nullptr, h_.ptr, rows, nullptr, -1, part[1]);
+    }
+  }
+  // the residual stream is complete once the last down-proj partials are summed in
+  launch_tp_reduce(tp, 1, 4 * (mc_.num_layers - 1) + 3, x_.ptr, rows, mc_.d_model, dtype_, stream_);
+}
+
+void LlamaDecoder::tp_handle(void* handle64) const {
+  CT2_REQUIRE(tp_.world > 1 && tp_.exchange.ptr, "tensor parallel is not enabled for this generator (tp_size == 1)");
+  static_assert(sizeof(cudaIpcMemHandle_t) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  cudaIpcMemHandle_t h;
+  CT2_CUDA_CHECK(cudaIpcGetMemHandle(&h, tp_.exchange.ptr));
+  std::memcpy(handle64, &h, sizeof(h));
+}
+
+void LlamaDecoder::tp_connect(const void* handles, int count) {
+  CT2_REQUIRE(tp_.world > 1, "tensor parallel is not enabled for this generator (tp_size == 1)");
+  CT2_REQUIRE(count == tp_.world, "tp_connect: one handle per rank is required");
+  CT2_CUDA_CHECK(cudaSetDevice(device_));
+  for (int r = 0; r < tp_.world; ++r) {
+    if (r == tp_.rank) {
+      tp_.peer[r] = tp_.exchange.ptr;
+      continue;
+    }
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, static_cast<const uint8_t*>(handles) + static_cast<size_t>(r) * sizeof(h), sizeof(h));
+    CT2_CUDA_CHECK(cudaIpcOpenMemHandle(&tp_.peer[r], h, cudaIpcMemLazyEnablePeerAccess));
+  }
+  TpLink& k = tp_.link;
+  k.rank = tp_.rank;
+  k.world = tp_.world;
+  k.tick = tp_.tick.as<uint32_t>();
+  k.amax_rows = chunk_rows_;
+  k.flags_local = reinterpret_cast<uint32_t*>(static_cast<uint8_t*>(tp_.exchange.ptr) + tp_.flags_off);
+  k.amax_local = reinterpret_cast<unsigned long long*>(static_cast<uint8_t*>(tp_.exchange.ptr) + tp_.amax_off);
+  for (int r = 0; r < tp_.world; ++r) {
+    uint8_t* base = static_cast<uint8_t*>(tp_.peer[r]);
+    k.flags_peer[r] = reinterpret_cast<uint32_t*>(base + tp_.flags_off);
+    k.amax_peer[r] = reinterpret_cast<unsigned long long*>(base + tp_.amax_off);
+    k.parts[0][r] = base + tp_.part_off[0];
+    k.parts[1][r] = base + tp_.part_off[1];
+  }
+  tp_.connected = true;
 }
 
 // layers::Embeddings::operator() (common.cc:64-81)

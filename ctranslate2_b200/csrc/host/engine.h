@@ -122,12 +122,20 @@ class LlamaDecoder {
   // project rows (indices into the rows of the last forward_prefill) of the hidden state to the vocabulary
   void project_rows(const int32_t* rows_d, int64_t n, void* logits_out_d);
   void* logits_buffer() const { return logits_.ptr; }       // [max_batch, vocab] T
+  // tensor parallel bootstrap (one process per GPU): this rank's exchange buffer as a cudaIpcMemHandle (64 bytes),
+  // then the handles of all ranks in rank order
+  int tp_size() const { return tp_.world; }
+  void tp_handle(void* handle64) const;
+  void tp_connect(const void* handles, int count);
   int64_t prefill_chunk_rows() const { return chunk_rows_; }
   void set_gemm_impl(int impl) { gemm_impl_ = impl; }
   void set_step_mask(unsigned m) { step_mask_ = m; }
 
  private:
-  void load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w);
+  // how a Dense weight [n, k] is partitioned over the tensor-parallel ranks (models::Model::load, model.cc:662-743)
+  enum Shard { REPLICATED, ROWS, QKV_ROWS, COLS };
+  void load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w, Shard shard = REPLICATED);
+  void layers_forward_tp(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d);
   DeviceBuffer load_float_vector(const ModelFile& f, const std::string& name);
   void dense(const DenseWeights& w, const int8_t* xq, const float* xs, const void* x_float, int64_t m,
              const void* residual, int act, void* y);
@@ -135,7 +143,18 @@ class LlamaDecoder {
   void project(const void* x_rows, int64_t rows, void* logits_out);
   void embed(const int32_t* ids_d, int64_t rows);
 
-  ModelConfig mc_;
+  ModelConfig mc_;            // global (unsharded) geometry
+  int heads_ = 0, heads_kv_ = 0;   // heads held by this rank
+  int64_t ffn_ = 0;                // FFN columns held by this rank
+  struct Tp {
+    int rank = 0, world = 1;
+    bool connected = false;
+    DeviceBuffer exchange;      // flags | amax words | partial buffer 0 | partial buffer 1
+    DeviceBuffer tick;
+    size_t flags_off = 0, amax_off = 0, part_off[2] = {0, 0};
+    void* peer[8] = {};         // mapped exchange buffers (peer[rank] = own)
+    TpLink link;
+  } tp_;
   int dtype_ = CT2B200_F16;
   int device_ = 0;
   int gemm_impl_ = CT2B200_GEMM_AUTO;

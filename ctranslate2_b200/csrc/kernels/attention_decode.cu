@@ -10,8 +10,11 @@
 // previous kernel needed B*Hkv*splits to divide the SM count and paid its prologue/combine once per slice), the
 // cp.async ring never drains between (row, head) pairs, and consecutive units of a CTA are consecutive cache lines.
 //   * a pair that lies inside one CTA is normalised and written directly;
-//   * a pair shared by several CTAs goes through fp32 partials (m, l, O) in the workspace, one slot per contributing
-//     CTA, and the last arriver (ticket) combines them in slot order (deterministic).
+//   * a pair shared by several CTAs: the CTA that holds its HEAD combines.  The others (they meet the pair at the START
+//     of their range) park fp32 partials (O, m, l) in their workspace slot — O and m first, then l with release
+//     semantics, l > 0 doubling as the "ready" flag — and move on without waiting.  The head owner reaches the pair
+//     at the END of its range, when the other parts are normally long done, folds them in slot order (deterministic)
+//     and clears the flags for the next launch.  All CTAs of the grid are co-resident (grid = occupancy x SMs).
 // Inner loop (per tile): the G query heads of the KV head are rows 0..G-1 of a 16-row MMA tile; warp w owns keys
 // [16w, 16w+16): S = Q K^T (mma.sync m16n8k16, fp32), online softmax in fp32, O += P V.  K/V tiles are staged with
 // 16-byte cp.async into XOR-swizzled shared memory (no padding: 96 KB per CTA for D = 128, two CTAs per SM).
@@ -60,10 +63,9 @@ __global__ void __launch_bounds__(kThreads, 2)
   extern __shared__ __align__(128) uint8_t smem_raw[];
   T* sK = reinterpret_cast<T*>(smem_raw);                           // [stages][64][D], chunk c of row r at c ^ (r & 7)
   T* sV = sK + kStages * kTileElems;
-  float* s_q = reinterpret_cast<float*>(sV + kStages * kTileElems);  // [G][D]
-  int* s_pref = reinterpret_cast<int*>(s_q + G * D);                 // [batch + 1] tiles before row b
+  float* s_q = reinterpret_cast<float*>(sV + kStages * kTileElems);  // [2][G][D] (current / next segment)
+  int* s_pref = reinterpret_cast<int*>(s_q + 2 * G * D);             // [batch + 1] tiles before row b
   __shared__ float s_m[NW][G], s_l[NW][G];
-  __shared__ int s_last;
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
   const int64_t row_w = static_cast<int64_t>(H + 2 * Hkv) * D;
@@ -95,8 +97,8 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) max_tiles = max(max_tiles, __shfl_xor_sync(0xffffffffu, max_tiles, o));
   const int min_units = (max_tiles + kSlots - 2) / (kSlots - 1);    // units per CTA so that a pair spans < kSlots CTAs
-  int64_t P = gridDim.x;
-  if (min_units > 1) P = min(P, max(static_cast<int64_t>(1), U / min_units));
+  // every CTA must own at least one unit (the contributors of a pair are then consecutive CTAs)
+  const int64_t P = min(static_cast<int64_t>(gridDim.x), max(static_cast<int64_t>(1), U / max(min_units, 1)));
   if (static_cast<int64_t>(blockIdx.x) >= P) return;
   const int64_t u0 = blockIdx.x * U / P, u1 = (blockIdx.x + 1) * U / P;
   if (u1 <= u0) return;
@@ -188,6 +190,39 @@ __global__ void __launch_bounds__(kThreads, 2)
   }
 
   UnitCursor cc = cursor_at(u0);                   // compute cursor
+  // ---- rotated, pre-scaled queries of a (row, KV head): raw loads first (prefetch), rotation + store later ----
+  constexpr int QE = (G * D + kThreads - 1) / kThreads;            // query elements per thread
+  float q_x[QE], q_o[QE], q_s[QE], q_c[QE];
+  auto q_load = [&](const UnitCursor& c) {
+    const int pos = lens[c.b];
+    const T* q_in = qkv + c.b * row_w + static_cast<int64_t>(c.kvh) * G * D;
+    const float* sn = sin_t + static_cast<int64_t>(pos) * D;
+    const float* cs = cos_t + static_cast<int64_t>(pos) * D;
+#pragma unroll
+    for (int k = 0; k < QE; ++k) {
+      const int e = tid + k * kThreads;
+      if (e < G * D) {
+        const int h = e / D, i = e % D;
+        const T* x = q_in + h * D;
+        q_x[k] = to_f32(x[i]);
+        if (interleave) q_o[k] = (i & 1) ? to_f32(x[i - 1]) : -to_f32(x[i + 1]);
+        else q_o[k] = (i < D / 2) ? -to_f32(x[i + D / 2]) : to_f32(x[i - D / 2]);
+        q_s[k] = sn[i];
+        q_c[k] = cs[i];
+      }
+    }
+  };
+  auto q_store = [&](float* dst) {
+#pragma unroll
+    for (int k = 0; k < QE; ++k) {
+      const int e = tid + k * kThreads;
+      if (e < G * D) dst[e] = (q_x[k] * q_c[k] + q_o[k] * q_s[k]) * scale_log2;
+    }
+  };
+  int qb = 0;                                      // s_q buffer of the current segment
+  q_load(cc);
+  q_store(s_q);
+
   uint32_t qf[D / 16][2];                          // Q as A fragments: rows 0..G-1 = heads (a0, a2); rows 8..15 are zero
   float o[D / 8][2];
   float m_run = -INFINITY, l_run = 0.f;
@@ -202,21 +237,20 @@ __global__ void __launch_bounds__(kThreads, 2)
       ++lu;
     }
     asm volatile("cp.async.commit_group;\n" ::);
-    const int pos = lens[cc.b];
-    const int nkeys = pos + 1;
+    const int nkeys = lens[cc.b] + 1;
+    const bool pair_end = cc.t == cc.tiles - 1;
+    const bool prefetch_q = pair_end && u + 1 < u1;   // the next unit opens a new (row, head): fetch its queries now
+    if (prefetch_q) {
+      UnitCursor nc = cc;
+      advance(nc);
+      q_load(nc);
+    }
     if (seg_start) {
-      // rotated, pre-scaled queries of this (row, KV head)
-      const T* q_in = qkv + cc.b * row_w + static_cast<int64_t>(cc.kvh) * G * D;
-      const float* sn = sin_t + static_cast<int64_t>(pos) * D;
-      const float* cs = cos_t + static_cast<int64_t>(pos) * D;
-      for (int e = tid; e < G * D; e += kThreads) {
-        const int h = e / D, i = e % D;
-        s_q[e] = rope_elem(q_in + h * D, sn, cs, i, D, interleave) * scale_log2;
-      }
-      __syncthreads();
+      __syncthreads();                             // s_q[qb] is complete
+      const float* sq = s_q + qb * G * D;
 #pragma unroll
       for (int kk = 0; kk < D / 16; ++kk) {
-        const float* qr = s_q + (g < G ? g : 0) * D + kk * 16 + 2 * t4;
+        const float* qr = sq + (g < G ? g : 0) * D + kk * 16 + 2 * t4;
         const bool real = g < G;
         qf[kk][0] = real ? pack2<T>(qr[0], qr[1]) : 0u;
         qf[kk][1] = real ? pack2<T>(qr[8], qr[9]) : 0u;
@@ -288,9 +322,9 @@ __global__ void __launch_bounds__(kThreads, 2)
         o[j + 1][0] = c1[0]; o[j + 1][1] = c1[1];
       }
     }
+    if (prefetch_q) q_store(s_q + (qb ^ 1) * G * D);   // read by the next iteration, after its __syncthreads
     __syncthreads();                               // the stage is free again (and may serve as scratch below)
 
-    const bool pair_end = cc.t == cc.tiles - 1;
     if (pair_end || u == u1 - 1) {
       // ---- end of a segment: merge the 4 warps; scratch = the stage just consumed (refilled only after the sync below)
       float* s_o = reinterpret_cast<float*>(sK + stage * kTileElems);      // [NW][G][D] fp32 <= 16 KB
@@ -304,13 +338,25 @@ __global__ void __launch_bounds__(kThreads, 2)
           *reinterpret_cast<float2*>(s_o + (warp * G + g) * D + j * 8 + 2 * t4) = make_float2(o[j][0], o[j][1]);
       }
       __syncthreads();
-      const bool whole = seg_t0 == 0 && pair_end;
-      const int64_t pair_base = u - cc.t;                                   // first unit of this pair
+      const bool head = seg_t0 == 0;               // this CTA holds the first tile of the pair
+      const int64_t pair_base = u - cc.t;          // first unit of this pair
       const int c_first = cta_of(pair_base), c_last = cta_of(pair_base + cc.tiles - 1);
-      const int nsplit = c_last - c_first + 1;
+      const int nsplit = (head && pair_end) ? 1 : c_last - c_first + 1;
       const int slot = static_cast<int>(blockIdx.x) - c_first;
       float* part = partials + (static_cast<int64_t>(cc.b) * H + static_cast<int64_t>(cc.kvh) * G) * kSlots * PS;
       T* out_row = out + static_cast<int64_t>(cc.b) * H * D + static_cast<int64_t>(cc.kvh) * G * D;
+      if (head && nsplit > 1) {
+        // wait for the other parts (normally long complete): their l field turns non-zero
+        for (int e = tid; e < G * (nsplit - 1); e += kThreads) {
+          const int h = e / (nsplit - 1), sidx = 1 + e % (nsplit - 1);
+          const float* lf = part + (static_cast<int64_t>(h) * kSlots + sidx) * PS + D + 1;
+          float lv;
+          do {
+            asm volatile("ld.acquire.gpu.global.f32 %0, [%1];" : "=f"(lv) : "l"(lf) : "memory");
+          } while (lv == 0.f);
+        }
+        __syncthreads();
+      }
       for (int e = tid; e < G * D; e += kThreads) {
         const int h = e / D, i = e % D;
         float mm = -INFINITY;
@@ -323,59 +369,46 @@ __global__ void __launch_bounds__(kThreads, 2)
           ll += s_l[w][h] * c;
           a += s_o[(w * G + h) * D + i] * c;
         }
-        if (whole) {
+        if (head) {
+          for (int sidx = 1; sidx < nsplit; ++sidx) {       // slot order: deterministic
+            const float* ph = part + (static_cast<int64_t>(h) * kSlots + sidx) * PS;
+            const float ms = __ldcg(ph + D), lsv = __ldcg(ph + D + 1), os = __ldcg(ph + i);
+            const float nm = fmaxf(mm, ms);
+            const float c0 = exp2f(mm - nm), c1 = exp2f(ms - nm);
+            a = a * c0 + os * c1;
+            ll = ll * c0 + lsv * c1;
+            mm = nm;
+          }
           out_row[e] = from_f32<T>(a * (1.f / ll));
         } else {
           float* ph = part + (static_cast<int64_t>(h) * kSlots + slot) * PS;
           ph[i] = a;
-          if (i == 0) { ph[D] = mm; ph[D + 1] = ll; }
+          if (i == 0) ph[D] = mm;
         }
       }
-      if (!whole) {
+      if (head && nsplit > 1) {
+        __syncthreads();                           // every thread has read the parts: clear the flags for the next launch
+        for (int e = tid; e < G * (nsplit - 1); e += kThreads) {
+          const int h = e / (nsplit - 1), sidx = 1 + e % (nsplit - 1);
+          part[(static_cast<int64_t>(h) * kSlots + sidx) * PS + D + 1] = 0.f;
+        }
+      } else if (!head) {
         __threadfence();
-        __syncthreads();
-        int32_t* ticket = tickets + cc.b * Hkv + cc.kvh;
-        if (tid == 0) s_last = atomicAdd(ticket, 1) == nsplit - 1;
-        __syncthreads();
-        if (s_last) {
-          __threadfence();
-          // combine the nsplit partials in slot order; scratch: weights [G][64], sums, 1/l
-          float* sw = s_o;                         // [G][kSlots] max -> weight
-          float* sl = s_o + G * kSlots;            // [G][kSlots] sum
-          float* sinv = s_o + 2 * G * kSlots;      // [G]
-          __syncthreads();
-          for (int e = tid; e < G * nsplit; e += kThreads) {
-            const int h = e / nsplit, sidx = e % nsplit;
-            const float* ph = part + (static_cast<int64_t>(h) * kSlots + sidx) * PS;
-            sw[h * kSlots + sidx] = __ldcg(ph + D);
-            sl[h * kSlots + sidx] = __ldcg(ph + D + 1);
-          }
-          __syncthreads();
-          if (tid < G) {
-            float mm = -INFINITY;
-            for (int sidx = 0; sidx < nsplit; ++sidx) mm = fmaxf(mm, sw[tid * kSlots + sidx]);
-            float ll = 0.f;
-            for (int sidx = 0; sidx < nsplit; ++sidx) {
-              const float c = sw[tid * kSlots + sidx] == -INFINITY ? 0.f : exp2f(sw[tid * kSlots + sidx] - mm);
-              sw[tid * kSlots + sidx] = c;
-              ll += sl[tid * kSlots + sidx] * c;
-            }
-            sinv[tid] = 1.f / ll;
-          }
-          __syncthreads();
-          for (int e = tid; e < G * D; e += kThreads) {
-            const int h = e / D, i = e % D;
-            const float* ph = part + static_cast<int64_t>(h) * kSlots * PS + i;
-            float a = 0.f;
-#pragma unroll 4
-            for (int sidx = 0; sidx < nsplit; ++sidx) a += __ldcg(ph + sidx * PS) * sw[h * kSlots + sidx];
-            out_row[e] = from_f32<T>(a * sinv[h]);
-          }
-          if (tid == 0) *ticket = 0;
+        __syncthreads();                           // O and m of every head are written and fenced ...
+        if (tid < G) {                             // ... then l, which publishes the record
+          float mm = -INFINITY;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) mm = fmaxf(mm, s_m[w][tid]);
+          float ll = 0.f;
+#pragma unroll
+          for (int w = 0; w < NW; ++w) ll += s_l[w][tid] * (s_m[w][tid] == -INFINITY ? 0.f : exp2f(s_m[w][tid] - mm));
+          float* lf = part + (static_cast<int64_t>(tid) * kSlots + slot) * PS + D + 1;
+          asm volatile("st.release.gpu.global.f32 [%0], %1;" ::"l"(lf), "f"(ll) : "memory");
         }
       }
       __syncthreads();                             // scratch stage released before the next iteration refills it
       seg_start = true;
+      if (pair_end) qb ^= 1;
     }
     advance(cc);
   }
@@ -387,15 +420,17 @@ void launch_persistent(const void* qkv, void* kc, void* vc, const float* sn, con
                        int64_t batch, int H, int Hkv, int64_t max_len, bool interleave, float scale, void* out,
                        float* partials, int32_t* tickets, int sm_count, cudaStream_t st) {
   auto kernel = attention_decode_persistent_kernel<T, D, G>;
-  const size_t smem = static_cast<size_t>(2 * kStages * kTile * D) * sizeof(T) + static_cast<size_t>(G) * D * sizeof(float) +
+  const size_t smem = static_cast<size_t>(2 * kStages * kTile * D) * sizeof(T) + static_cast<size_t>(2 * G) * D * sizeof(float) +
                       (static_cast<size_t>(batch) + 1) * sizeof(int);
-  static bool configured = false;
-  if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 110 * 1024));
-    configured = true;
+  static int occupancy = 0;                       // CTAs per SM: the grid must be fully co-resident (flag waits)
+  if (occupancy == 0) {
+    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+    int occ = 0;
+    CT2_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 112 * 1024));
+    occupancy = std::max(1, std::min(occ, 2));
   }
   const int64_t max_units = batch * Hkv * ((max_len + kTile - 1) / kTile);
-  const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(2 * sm_count, max_units));
+  const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(static_cast<int64_t>(occupancy) * sm_count, max_units));
   launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kThreads), smem, st, static_cast<const T*>(qkv),
              static_cast<T*>(kc), static_cast<T*>(vc), sn, cs, lens, static_cast<int>(batch), H, Hkv, max_len, interleave,
              scale * 1.4426950408889634f, static_cast<T*>(out), partials, tickets);

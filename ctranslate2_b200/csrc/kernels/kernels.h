@@ -33,6 +33,27 @@ void launch_softmax(const void* x, const int32_t* lengths, int64_t rows, int64_t
 void launch_topk(const void* x, int64_t rows, int64_t cols, int k, void* values, int32_t* indices, int dtype,
                  cudaStream_t st);
 
+// tp_rows.cu — tensor-parallel row kernels (collectives fused into their consumers over NVLink peer memory)
+struct TpLink {
+  int rank = 0, world = 1;
+  const uint32_t* tick = nullptr;             // forward-pass counter of this rank (device)
+  uint32_t* flags_local = nullptr;            // [2][8] epoch flags in this rank's exchange buffer (peers write them)
+  uint32_t* flags_peer[8] = {};               // the same array inside every peer's buffer
+  const void* parts[2][8] = {};               // partial buffer b ([rows, d_model] T) of rank r
+  unsigned long long* amax_local = nullptr;   // [2][8][amax_rows] {epoch, amax} words in this rank's buffer
+  unsigned long long* amax_peer[8] = {};
+  int64_t amax_rows = 0;
+};
+void launch_tp_tick(uint32_t* tick, cudaStream_t st);
+void launch_tp_reduce_norm_quantize(const TpLink& tp, int buf, int sync_idx, void* x, const void* gamma, int64_t rows,
+                                    int64_t cols, float eps, int8_t* q, float* scale, int dtype, cudaStream_t st);
+void launch_tp_reduce_norm(const TpLink& tp, int buf, int sync_idx, void* x, const void* gamma, int64_t rows, int64_t cols,
+                           float eps, void* y, int dtype, cudaStream_t st);
+void launch_tp_reduce(const TpLink& tp, int buf, int sync_idx, void* x, int64_t rows, int64_t cols, int dtype,
+                      cudaStream_t st);
+void launch_tp_quantize_rows(const TpLink& tp, int slot, int sync_idx, const void* x, int64_t rows, int64_t cols, int8_t* q,
+                             float* scale, int dtype, cudaStream_t st);
+
 // gemm_tc.cu (tcgen05) — gemm_s8_mma.cu declarations live in gemm_common.cuh
 void gemm_s8_tc(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
                 int dtype, cudaStream_t st);

@@ -28,7 +28,12 @@ class GenerationResult:
 
 class Generator:
     def __init__(self, model_path: str, device: str = "cuda", device_index: int = 0, compute_type: str = "default",
-                 max_batch_size: int = 32, max_length: int = 4096, use_cuda_graph: bool = True, gemm_impl: int = 0):
+                 max_batch_size: int = 32, max_length: int = 4096, use_cuda_graph: bool = True, gemm_impl: int = 0,
+                 tensor_parallel: bool = False, tp_rank: Optional[int] = None, tp_size: Optional[int] = None,
+                 tp_group=None):
+        """tensor_parallel=True (ctranslate2.Generator(..., tensor_parallel=True)): one process per GPU; rank and
+        size default to torch.distributed's, whose default (or `tp_group`) group also carries the one-time exchange
+        of the CUDA IPC handles.  Every rank must then make the same calls with the same inputs."""
         if device not in ("cuda", "auto"):
             raise ValueError("ctranslate2_b200 runs on device='cuda' only (no CPU fallback)")
         if compute_type not in _COMPUTE:
@@ -46,13 +51,32 @@ class Generator:
         self._token_to_id = None
         cfg_path = os.path.join(model_path, "config.json")
         self._config = json.load(open(cfg_path)) if os.path.exists(cfg_path) else {}
-        cfg = GeneratorConfig(device_index, _COMPUTE[compute_type], max_batch_size, max_length, 0, 1,
-                              int(use_cuda_graph), gemm_impl)
+        self.tp_rank, self.tp_size = 0, 1
+        if tensor_parallel:
+            from .parallel import default_rank_and_size
+            self.tp_rank, self.tp_size = default_rank_and_size(tp_rank, tp_size, tp_group)
+        cfg = GeneratorConfig(device_index, _COMPUTE[compute_type], max_batch_size, max_length, self.tp_rank,
+                              self.tp_size, int(use_cuda_graph), gemm_impl)
         self._h = lib().ct2b200_generator_open(model_path.encode(), ctypes.byref(cfg))
         if not self._h:
             raise RuntimeError(lib().ct2b200_last_error().decode())
         self.max_batch_size, self.max_length = max_batch_size, max_length
         self.vocab_size = lib().ct2b200_generator_vocab_size(ctypes.c_void_p(self._h))
+        if self.tp_size > 1:
+            from .parallel import exchange_handles
+            self.tp_connect(exchange_handles(self.tp_handle(), self.tp_rank, self.tp_size, tp_group))
+
+    # -- tensor parallel bootstrap ------------------------------------------------------
+    def tp_handle(self) -> bytes:
+        buf = ctypes.create_string_buffer(64)
+        check(lib().ct2b200_generator_tp_handle(ctypes.c_void_p(self._h), buf))
+        return buf.raw
+
+    def tp_connect(self, handles: Sequence[bytes]):
+        blob = b"".join(handles)
+        if len(blob) != 64 * self.tp_size:
+            raise ValueError("tp_connect needs one 64-byte handle per rank")
+        check(lib().ct2b200_generator_tp_connect(ctypes.c_void_p(self._h), blob, len(handles)))
 
     def __del__(self):
         self.close()

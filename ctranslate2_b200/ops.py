@@ -244,6 +244,11 @@ def mul_quantize(gate, up):
     return q, s
 
 
+def attention_decode_workspace_bytes(batch, num_heads, head_dim, max_len):
+    """Bytes of the (zero-initialised, reusable) workspace of attention_decode."""
+    return lib().ct2b200_attention_decode_workspace(ctypes.c_int64(batch), num_heads, head_dim, ctypes.c_int64(max_len))
+
+
 def attention_decode(qkv, k_cache, v_cache, sin, cos, lens, num_heads, num_heads_kv, head_dim, interleave=False,
                      scale=None, workspace=None):
     """MultiHeadAttention decode step between the two Dense layers (attention.cc:485-602)."""

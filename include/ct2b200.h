@@ -198,7 +198,7 @@ typedef struct {
   int compute_type;         /* ct2b200_dtype of activations / KV cache; weights keep their stored type */
   int64_t max_batch;        /* batch slots to reserve */
   int64_t max_length;       /* max total positions (prompt + generated) per sequence */
-  int tp_rank, tp_size;     /* tensor-parallel rank/size (1 = off); see ct2b200_generator_set_nccl */
+  int tp_rank, tp_size;     /* tensor-parallel rank/size (1 = off); see ct2b200_generator_tp_connect */
   int use_cuda_graph;       /* capture the decode step in a CUDA graph */
   int gemm_impl;            /* ct2b200_gemm_impl */
 } ct2b200_generator_config;
@@ -231,11 +231,18 @@ CT2B200_API int ct2b200_forward_batch(ct2b200_generator* g, const int32_t* ids_h
 CT2B200_API int ct2b200_bench_decode(ct2b200_generator* g, int64_t batch, int64_t prompt_len, int64_t steps, int64_t warmup,
                          float* prefill_ms, float* decode_ms, int64_t* kernel_launches);
 
-/* Tensor parallel bootstrap: the caller (one process per GPU, torch.distributed for the rendezvous)
- * hands over a 128-byte ncclUniqueId created by rank 0 (ct2b200_nccl_unique_id) — replaces
- * ScopedMPISetter / MPI_Bcast(ncclUniqueId) in src/devices.cc:141-203. */
-CT2B200_API int ct2b200_nccl_unique_id(void* id128_h);
-CT2B200_API int ct2b200_generator_set_nccl(ct2b200_generator* g, const void* id128_h);
+/* Tensor parallel (ct2b200_generator_config.tp_size > 1; one process per GPU; replaces ScopedMPISetter + the NCCL
+ * communicator of src/devices.cc:141-217 and ops::ReduceAll / GatherAll, src/ops/nccl_ops_gpu.cu:52-85).
+ * The collectives of the decoder are fused into its kernels over NVLink peer memory, so the bootstrap only has to
+ * exchange one CUDA IPC handle per rank:
+ *   1. every rank opens the generator with its tp_rank / tp_size (weights are sharded on load as in
+ *      src/models/model.cc:662-743: QKV and gate/up by output channel, out-proj and down-proj by input channel);
+ *   2. ct2b200_generator_tp_handle writes this rank's 64-byte cudaIpcMemHandle_t to handle64_h;
+ *   3. the caller all-gathers the handles (torch.distributed, MPI, files ...) and passes the tp_size handles in rank
+ *      order to ct2b200_generator_tp_connect.
+ * Every rank must then issue the same generate_batch / forward_batch calls with the same inputs. */
+CT2B200_API int ct2b200_generator_tp_handle(ct2b200_generator* g, void* handle64_h);
+CT2B200_API int ct2b200_generator_tp_connect(ct2b200_generator* g, const void* handles_h, int num_handles);
 
 #ifdef __cplusplus
 }

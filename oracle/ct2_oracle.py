@@ -112,6 +112,49 @@ def dense_int8(x: np.ndarray, w_q: np.ndarray, w_scale: np.ndarray, bias: Option
     return y.reshape(shape[:-1] + (w_q.shape[0],))
 
 
+def tp_shard_rows(n_total: int, rank: int, world: int) -> Tuple[int, int]:
+    """[begin, end) of a dimension split evenly over `world` ranks (models::Model::load splits weights with
+    ops::Split into equal parts, src/models/model.cc:662-743; the dimension must be divisible)."""
+    assert n_total % world == 0
+    per = n_total // world
+    return rank * per, (rank + 1) * per
+
+
+def tp_qkv_rows(num_heads: int, num_heads_kv: int, head_dim: int, rank: int, world: int) -> np.ndarray:
+    """Rows of the fused [q; k; v] projection owned by `rank`: its query heads, its key heads, its value heads
+    (model.cc:689-722 splits the three parts separately so that every rank keeps whole heads)."""
+    q0, q1 = tp_shard_rows(num_heads, rank, world)
+    k0, k1 = tp_shard_rows(num_heads_kv, rank, world)
+    hq, hk = num_heads * head_dim, num_heads_kv * head_dim
+    return np.concatenate([np.arange(q0 * head_dim, q1 * head_dim),
+                           hq + np.arange(k0 * head_dim, k1 * head_dim),
+                           hq + hk + np.arange(k0 * head_dim, k1 * head_dim)])
+
+
+def dense_int8_row_parallel(x: np.ndarray, w_q: np.ndarray, w_scale: np.ndarray, world: int,
+                            residual: Optional[np.ndarray] = None, flavor: str = "cuda",
+                            dtype: str = "float32") -> np.ndarray:
+    """Row-parallel (input dimension split) quantized Dense under tensor parallelism, src/layers/common.cc:348-401:
+    the input rows are quantized with the amax of the WHOLE row (the reference all-gathers the activations before
+    Quantize, :360-387), rank r multiplies its K slice, dequantizes its partial to T, the partials are summed
+    (ops::ReduceAll, transformer.cc:45-48 / attention.cc:608-612) and the residual is added once (rank 0, :348-352).
+    `dtype` is the activation type the partials are rounded to before the sum."""
+    shape = x.shape
+    x2 = x.reshape(-1, shape[-1])
+    xq, xs = quantize_rows(x2)
+    k = x2.shape[1]
+    total = np.zeros((x2.shape[0], w_q.shape[0]), f32)
+    for r in range(world):
+        b, e = tp_shard_rows(k, r, world)
+        part = dequantize_gemm_output(gemm_s8(xq[:, b:e], w_q[:, b:e]), xs, w_scale, None, ACT_NONE, flavor)
+        if dtype != "float32":
+            part = part.astype(np.float16).astype(f32) if dtype == "float16" else part
+        total = (total + part).astype(f32)
+    if residual is not None:
+        total = (total + residual.reshape(total.shape).astype(f32)).astype(f32)
+    return total.reshape(shape[:-1] + (w_q.shape[0],))
+
+
 def quantize_weight(w: np.ndarray) -> Tuple[np.ndarray, np.ndarray]:
     """Weight quantization done by the converter / on load: python/ctranslate2/specs/model_spec.py:222-243
     == src/models/model.cc:304-369.  scale[i] = 127/amax(W[i,:]) (amax 0 -> 127), W_q = rint(W*scale)."""

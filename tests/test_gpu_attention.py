@@ -90,3 +90,33 @@ def test_attention_prefill(dt, cfg):
     tol = TOL[dt] if dt != "float32" else 2e-5
     np.testing.assert_allclose(out, ref, rtol=tol, atol=tol * 2)
     np.testing.assert_array_equal(to_np(vc_d[:, :, off:off + T]), v)
+
+
+@gpu
+@pytest.mark.parametrize("dt", ["float16", "bfloat16"])
+def test_attention_decode_workspace_reuse(dt):
+    """Successive launches on ONE workspace (as the 32 layers of a decode step do): the ready flags of the shared
+    (row, head) pairs are cleared by the combining CTA, so later launches see a clean slate; results stay exact
+    when the same cache is attended again at the next position."""
+    B, H, Hkv, D, max_len = 2, 8, 2, 128, 2048
+    G = H // Hkv
+    r = np.random.default_rng(77)
+    kc = round_through(r.standard_normal((B, Hkv, max_len, D)), dt)
+    vc = round_through(r.standard_normal((B, Hkv, max_len, D)), dt)
+    sin, cos = O.rotary_tables(max_len, D, 500000.0, interleave=False)
+    kc_d, vc_d = dev(kc, TDT[dt]), dev(vc, TDT[dt])
+    nbytes = ops.attention_decode_workspace_bytes(B, H, D, max_len)
+    ws = torch.zeros(nbytes, dtype=torch.uint8, device=DEV)
+    lens = np.array([1500, 900], np.int32)
+    for step in range(3):
+        qkv = round_through(r.standard_normal((B, (H + 2 * Hkv) * D)), dt)
+        out = to_np(ops.attention_decode(dev(qkv, TDT[dt]), kc_d, vc_d, dev(sin), dev(cos), dev(lens), H, Hkv, D,
+                                         workspace=ws)).reshape(B, H, D)
+        kc_h, vc_h = to_np(kc_d), to_np(vc_d)                # caches after the append
+        for b in range(B):
+            pos = int(lens[b])
+            q = qkv[b, :H * D].reshape(1, H, 1, D)
+            qr = O.rotary(q, sin[pos:pos + 1], cos[pos:pos + 1], False)
+            ref = ref_attention(qr, kc_h[b:b + 1, :, :pos + 1], vc_h[b:b + 1, :, :pos + 1], G)[0, :, 0]
+            np.testing.assert_allclose(out[b], ref, rtol=TOL[dt], atol=TOL[dt] * 2)
+        lens = lens + 1

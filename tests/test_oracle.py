@@ -205,3 +205,35 @@ def test_live_reference_rotary_tables(kw):
         np.testing.assert_allclose(s, rs, atol=1e-4)
         np.testing.assert_allclose(c, rc, atol=1e-4)
         assert np.abs(s - rs).mean() < 2e-6
+
+
+def test_tensor_parallel_partition_restatement():
+    """Tensor-parallel partition (model.cc:662-743) restated in the oracle: column-parallel shards concatenate to the
+    unsharded output bit for bit; row-parallel INT8 partials (global per-row amax) sum to the unsharded output up to
+    fp32 rounding, because the int32 accumulators of the K slices add up exactly."""
+    r = np.random.default_rng(0)
+    H, Hkv, D, d, F = 8, 4, 16, 128, 256
+    x = r.standard_normal((5, d)).astype(np.float32)
+    wq, ws = O.quantize_weight((r.standard_normal(((H + 2 * Hkv) * D, d)) * 0.05).astype(np.float32))
+    full = O.dense_int8(x, wq, ws)
+    for world in (2, 4):
+        parts = []
+        for rank in range(world):
+            rows = O.tp_qkv_rows(H, Hkv, D, rank, world)
+            parts.append((rows, O.dense_int8(x, wq[rows], ws[rows])))
+        # every rank holds whole heads: H/world query heads followed by Hkv/world key and value heads
+        assert all(p[1].shape[1] == (H + 2 * Hkv) * D // world for p in parts)
+        recon = np.zeros_like(full)
+        for rows, y in parts:
+            recon[:, rows] = y
+        np.testing.assert_array_equal(recon, full)
+        wd, sd = O.quantize_weight((r.standard_normal((d, F)) * 0.05).astype(np.float32))
+        h = r.standard_normal((5, F)).astype(np.float32)
+        res = r.standard_normal((5, d)).astype(np.float32)
+        np.testing.assert_allclose(O.dense_int8_row_parallel(h, wd, sd, world, res), O.dense_int8(h, wd, sd, None, -1, res),
+                                   rtol=0, atol=2e-6 * float(np.abs(res).max() + 1))
+        # the exact statement behind it: sliced int32 GEMMs add up to the full GEMM
+        hq, _ = O.quantize_rows(h)
+        acc = sum(O.gemm_s8(hq[:, slice(*O.tp_shard_rows(F, k, world))], wd[:, slice(*O.tp_shard_rows(F, k, world))])
+                  for k in range(world))
+        np.testing.assert_array_equal(acc, O.gemm_s8(hq, wd))
