@@ -24,12 +24,14 @@
 
 #include "../common.cuh"
 #include "kernels.h"
+#include "attention_tile.cuh"
 #include "mma_common.cuh"
 
 namespace ct2b200 {
 namespace {
 
 using namespace mma;
+using namespace attn;
 
 constexpr int kThreads = 128;
 constexpr int kTile = 64;            // keys per unit
@@ -56,7 +58,6 @@ __global__ void __launch_bounds__(kThreads, 2)
                                        const int32_t* __restrict__ lens, int batch, int H, int Hkv, int64_t max_len,
                                        bool interleave, float scale_log2, T* __restrict__ out,
                                        float* __restrict__ partials, int32_t* __restrict__ tickets) {
-  constexpr int CH = D / 8;                       // 16-byte chunks per row
   constexpr int NW = kThreads / 32;
   constexpr int kTileElems = kTile * D;
   constexpr size_t PS = static_cast<size_t>(D) + 2;
@@ -159,23 +160,16 @@ __global__ void __launch_bounds__(kThreads, 2)
   __syncthreads();
 
   // ---- K/V tile loads ----
+  TileCtx<T, D> cx;
+  cx.init(tid);
+  const uint32_t sK_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t sV_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
   auto load_unit = [&](int stage, const UnitCursor& c) {
     const int nkeys = lens[c.b] + 1;
     const int k0 = c.t * kTile;
-    const T* kc = k_cache + (static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len * D;
-    const T* vc = v_cache + (static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len * D;
-    T* dk = sK + stage * kTileElems;
-    T* dv = sV + stage * kTileElems;
-#pragma unroll
-    for (int i = 0; i < kTile * CH / kThreads; ++i) {
-      const int cidx = tid + i * kThreads;
-      const int r = cidx / CH, ch = cidx % CH;
-      const bool ok = k0 + r < nkeys;
-      const int64_t off = static_cast<int64_t>(ok ? k0 + r : k0) * D + ch * 8;
-      const int doff = r * D + ((ch ^ (r & 7)) * 8);
-      cp16(dk + doff, kc + off, ok);
-      cp16(dv + doff, vc + off, ok);
-    }
+    const int64_t base = ((static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len + k0) * D;
+    cx.load(sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, k_cache + base,
+            v_cache + base, nkeys - k0);
   };
   UnitCursor lc = cursor_at(u0);                   // load cursor (runs kStages - 1 units ahead)
   int64_t lu = u0;
@@ -224,8 +218,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   q_store(s_q);
 
   uint32_t qf[D / 16][2];                          // Q as A fragments: rows 0..G-1 = heads (a0, a2); rows 8..15 are zero
-  float o[D / 8][2];
-  float m_run = -INFINITY, l_run = 0.f;
+  WarpAcc<D> acc;
+  acc.reset();
   bool seg_start = true;
   int seg_t0 = cc.t;                               // first tile of the current segment
   int it = 0;
@@ -255,87 +249,29 @@ __global__ void __launch_bounds__(kThreads, 2)
         qf[kk][0] = real ? pack2<T>(qr[0], qr[1]) : 0u;
         qf[kk][1] = real ? pack2<T>(qr[8], qr[9]) : 0u;
       }
-#pragma unroll
-      for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = 0.f;
-      m_run = -INFINITY;
-      l_run = 0.f;
+      acc.reset();
       seg_t0 = cc.t;
       seg_start = false;
     }
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kStages - 1));
     __syncthreads();
 
-    // ---- this warp's 16 keys of the tile ----
-    {
-      const T* ks = sK + stage * kTileElems + warp * 16 * D;
-      const T* vs = sV + stage * kTileElems + warp * 16 * D;
-      float s[2][4];
-#pragma unroll
-      for (int j = 0; j < 2; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-#pragma unroll
-      for (int kk = 0; kk < D / 16; ++kk) {
-        uint32_t bf[4];
-        const int rr = (lane & 7) + (lane >> 4) * 8;
-        const int ch = kk * 2 + ((lane >> 3) & 1);
-        ldsm4(bf, ks + rr * D + ((ch ^ (lane & 7)) * 8));
-        const uint32_t a[4] = {qf[kk][0], 0u, qf[kk][1], 0u};
-        mma16816<T>(s[0], a, bf[0], bf[1]);
-        mma16816<T>(s[1], a, bf[2], bf[3]);
-      }
-      const int kbase = cc.t * kTile + warp * 16;
-      float mx = m_run;
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const int key = kbase + j * 8 + 2 * t4 + r;
-          s[j][r] = key < nkeys ? s[j][r] : -INFINITY;
-          mx = fmaxf(mx, s[j][r]);
-        }
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-      mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-      const float corr = (mx == -INFINITY) ? 1.f : exp2f(m_run - mx);
-      m_run = mx;
-      float rs = 0.f;
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int r = 0; r < 2; ++r) {
-          const float pv = (s[j][r] == -INFINITY) ? 0.f : exp2f(s[j][r] - mx);
-          s[j][r] = pv;
-          rs += pv;
-        }
-      l_run = l_run * corr + rs;
-#pragma unroll
-      for (int j = 0; j < D / 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
-      const uint32_t pa[4] = {pack2<T>(s[0][0], s[0][1]), 0u, pack2<T>(s[1][0], s[1][1]), 0u};
-#pragma unroll
-      for (int j = 0; j < D / 8; j += 2) {
-        uint32_t bf[4];
-        const int rr = (lane & 7) + ((lane >> 3) & 1) * 8;
-        const int ch = j + (lane >> 4);
-        ldsm4_t(bf, vs + rr * D + ((ch ^ (lane & 7)) * 8));
-        float c0[4] = {o[j][0], o[j][1], 0.f, 0.f}, c1[4] = {o[j + 1][0], o[j + 1][1], 0.f, 0.f};
-        mma16816<T>(c0, pa, bf[0], bf[1]);
-        mma16816<T>(c1, pa, bf[2], bf[3]);
-        o[j][0] = c0[0]; o[j][1] = c0[1];
-        o[j + 1][0] = c1[0]; o[j + 1][1] = c1[1];
-      }
-    }
+    tile_step<T, D>(cx, sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, warp, lane,
+                    qf, acc, nkeys - cc.t * kTile);
     if (prefetch_q) q_store(s_q + (qb ^ 1) * G * D);   // read by the next iteration, after its __syncthreads
     __syncthreads();                               // the stage is free again (and may serve as scratch below)
 
     if (pair_end || u == u1 - 1) {
       // ---- end of a segment: merge the 4 warps; scratch = the stage just consumed (refilled only after the sync below)
       float* s_o = reinterpret_cast<float*>(sK + stage * kTileElems);      // [NW][G][D] fp32 <= 16 KB
-      float ls = l_run;
+      float ls = acc.l;
       ls += __shfl_xor_sync(0xffffffffu, ls, 1);
       ls += __shfl_xor_sync(0xffffffffu, ls, 2);
-      if (g < G && t4 == 0) { s_m[warp][g] = m_run; s_l[warp][g] = ls; }
+      if (g < G && t4 == 0) { s_m[warp][g] = acc.m; s_l[warp][g] = ls; }
       if (g < G) {
 #pragma unroll
         for (int j = 0; j < D / 8; ++j)
-          *reinterpret_cast<float2*>(s_o + (warp * G + g) * D + j * 8 + 2 * t4) = make_float2(o[j][0], o[j][1]);
+          *reinterpret_cast<float2*>(s_o + (warp * G + g) * D + j * 8 + 2 * t4) = make_float2(acc.o[j][0], acc.o[j][1]);
       }
       __syncthreads();
       const bool head = seg_t0 == 0;               // this CTA holds the first tile of the pair

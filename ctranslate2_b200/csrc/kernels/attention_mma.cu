@@ -13,6 +13,7 @@
 
 #include "../common.cuh"
 #include "kernels.h"
+#include "attention_tile.cuh"
 #include "mma_common.cuh"
 
 namespace ct2b200 {
@@ -241,17 +242,19 @@ __device__ __forceinline__ float rope_at_mma(const T* x, const float* sin, const
 }
 
 template <typename T, int D, int G>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, 2)
     attention_decode_mma_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
                                 const float* __restrict__ sin_t, const float* __restrict__ cos_t,
                                 const int32_t* __restrict__ lens, int H, int Hkv, int64_t max_len, bool interleave,
                                 float scale_log2, T* __restrict__ out, float* __restrict__ partials,
                                 int32_t* __restrict__ tickets) {
-  constexpr int LD = D + 8, CH = D / 8, NW = kThreads / 32;
+  using namespace attn;
+  constexpr int NW = kThreads / 32;
+  constexpr int kTileElems = kDecTile * D;
   extern __shared__ __align__(16) uint8_t smem_raw[];
-  T* sK = reinterpret_cast<T*>(smem_raw);                       // [stages][64][LD]
-  T* sV = sK + kDecStages * kDecTile * LD;                      // [stages][64][LD]
-  float* s_q = reinterpret_cast<float*>(sV + kDecStages * kDecTile * LD);   // [G][D]  (reused for the warp merge)
+  T* sK = reinterpret_cast<T*>(smem_raw);                       // [stages][64][D], XOR-swizzled 16-byte chunks
+  T* sV = sK + kDecStages * kTileElems;
+  float* s_q = reinterpret_cast<float*>(sV + kDecStages * kTileElems);   // [G][D]
   __shared__ float s_m[NW][G], s_l[NW][G];
   __shared__ bool s_last;
 
@@ -288,15 +291,14 @@ __global__ void __launch_bounds__(kThreads)
   }
   __syncthreads();
 
+  TileCtx<T, D> cx;
+  cx.init(tid);
+  const uint32_t sK_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
+  const uint32_t sV_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
   auto load_tile = [&](int stage, int kt) {
     const int64_t k0 = s0 + static_cast<int64_t>(kt) * kDecTile;
-    for (int c = tid; c < kDecTile * CH; c += kThreads) {
-      const int r = c / CH, ch = c % CH;
-      const bool ok = k0 + r < s1;
-      const int64_t off = (ok ? k0 + r : s0) * D + ch * 8;
-      cp16(sK + (stage * kDecTile + r) * LD + ch * 8, kc + off, ok);
-      cp16(sV + (stage * kDecTile + r) * LD + ch * 8, vc + off, ok);
-    }
+    cx.load(sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, kc + k0 * D, vc + k0 * D,
+            static_cast<int>(s1 - k0));
   };
 #pragma unroll
   for (int st = 0; st < kDecStages - 1; ++st) {
@@ -305,20 +307,16 @@ __global__ void __launch_bounds__(kThreads)
   }
 
   // Q as A fragments: rows 0..G-1 = heads, rows G..15 = 0
-  uint32_t qf[D / 16][4];
+  uint32_t qf[D / 16][2];
 #pragma unroll
   for (int kk = 0; kk < D / 16; ++kk) {
-    const float* qr = s_q + g * D + kk * 16 + 2 * t;
+    const float* qr = s_q + (g < G ? g : 0) * D + kk * 16 + 2 * t;
     const bool real = g < G;
     qf[kk][0] = real ? pack2<T>(qr[0], qr[1]) : 0u;
-    qf[kk][1] = 0u;
-    qf[kk][2] = real ? pack2<T>(qr[8], qr[9]) : 0u;
-    qf[kk][3] = 0u;
+    qf[kk][1] = real ? pack2<T>(qr[8], qr[9]) : 0u;
   }
-  float o[D / 8][2];                                            // only rows g (< 8) are kept: c0, c1 of each n-tile
-#pragma unroll
-  for (int j = 0; j < D / 8; ++j) o[j][0] = o[j][1] = 0.f;
-  float m_run = -INFINITY, l_run = 0.f;
+  WarpAcc<D> acc;
+  acc.reset();
 
   for (int kt = 0; kt < ntiles; ++kt) {
     const int stage = kt % kDecStages;
@@ -326,71 +324,24 @@ __global__ void __launch_bounds__(kThreads)
     asm volatile("cp.async.commit_group;\n" ::);
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kDecStages - 1));
     __syncthreads();
-    const T* ks = sK + stage * kDecTile * LD + warp * 16 * LD;   // this warp's 16 keys
-    const T* vs = sV + stage * kDecTile * LD + warp * 16 * LD;
-    float s[2][4];
-#pragma unroll
-    for (int j = 0; j < 2; ++j) s[j][0] = s[j][1] = s[j][2] = s[j][3] = 0.f;
-#pragma unroll
-    for (int kk = 0; kk < D / 16; ++kk) {
-      uint32_t bf[4];
-      ldsm4(bf, ks + ((lane & 7) + (lane >> 4) * 8) * LD + kk * 16 + ((lane >> 3) & 1) * 8);
-      mma16816<T>(s[0], qf[kk], bf[0], bf[1]);
-      mma16816<T>(s[1], qf[kk], bf[2], bf[3]);
-    }
-    // online softmax over this warp's 16 keys (row g; rows >= G carry zeros and are ignored)
-    const int kbase = s0 + kt * kDecTile + warp * 16;
-    float mx = m_run;
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const int key = kbase + j * 8 + 2 * t + r;
-        s[j][r] = key < s1 ? s[j][r] : -INFINITY;
-        mx = fmaxf(mx, s[j][r]);
-      }
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));
-    mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-    const float corr = (mx == -INFINITY) ? 1.f : exp2f(m_run - mx);
-    m_run = mx;
-    float rs = 0.f;
-#pragma unroll
-    for (int j = 0; j < 2; ++j)
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        const float pv = (s[j][r] == -INFINITY) ? 0.f : exp2f(s[j][r] - mx);
-        s[j][r] = pv;
-        rs += pv;
-      }
-    l_run = l_run * corr + rs;
-#pragma unroll
-    for (int j = 0; j < D / 8; ++j) { o[j][0] *= corr; o[j][1] *= corr; }
-    uint32_t pa[4] = {pack2<T>(s[0][0], s[0][1]), 0u, pack2<T>(s[1][0], s[1][1]), 0u};
-#pragma unroll
-    for (int j = 0; j < D / 8; j += 2) {
-      uint32_t bf[4];
-      ldsm4_t(bf, vs + ((lane & 7) + ((lane >> 3) & 1) * 8) * LD + j * 8 + (lane >> 4) * 8);
-      float c0[4] = {o[j][0], o[j][1], 0.f, 0.f}, c1[4] = {o[j + 1][0], o[j + 1][1], 0.f, 0.f};
-      mma16816<T>(c0, pa, bf[0], bf[1]);
-      mma16816<T>(c1, pa, bf[2], bf[3]);
-      o[j][0] = c0[0]; o[j][1] = c0[1];
-      o[j + 1][0] = c1[0]; o[j + 1][1] = c1[1];
-    }
+    tile_step<T, D>(cx, sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, warp, lane, qf,
+                    acc, s1 - (s0 + kt * kDecTile));
     __syncthreads();
   }
   asm volatile("cp.async.wait_group 0;\n" ::);
 
   // ---- merge the 4 warps (each holds m, l, O for rows g < G over its keys) ----
+  float l_run = acc.l;
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 1);
   l_run += __shfl_xor_sync(0xffffffffu, l_run, 2);
-  if (g < G && t == 0) { s_m[warp][g] = m_run; s_l[warp][g] = l_run; }
+  if (g < G && t == 0) { s_m[warp][g] = acc.m; s_l[warp][g] = l_run; }
   float* s_o = reinterpret_cast<float*>(smem_raw);              // [NW][G][D] fp32, reuses the K/V staging area
   __syncthreads();                                              // all tiles consumed before the area is reused
   if (g < G) {
 #pragma unroll
     for (int j = 0; j < D / 8; ++j) {
-      s_o[(warp * G + g) * D + j * 8 + 2 * t] = o[j][0];
-      s_o[(warp * G + g) * D + j * 8 + 2 * t + 1] = o[j][1];
+      s_o[(warp * G + g) * D + j * 8 + 2 * t] = acc.o[j][0];
+      s_o[(warp * G + g) * D + j * 8 + 2 * t + 1] = acc.o[j][1];
     }
   }
   __syncthreads();
@@ -449,7 +400,7 @@ bool launch_decode_mma_g(const void* qkv, void* kc, void* vc, const float* sn, c
                          int64_t batch, int H, int Hkv, int64_t max_len, bool interleave, float scale, void* out,
                          float* partials, int32_t* tickets, int splits, cudaStream_t st) {
   const int G = H / Hkv;
-  constexpr size_t smem = static_cast<size_t>(2 * kDecStages * kDecTile) * (D + 8) * sizeof(T) + 8 * D * sizeof(float);
+  constexpr size_t smem = static_cast<size_t>(2 * kDecStages * kDecTile) * D * sizeof(T) + 8 * D * sizeof(float);
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(splits, Hkv, static_cast<unsigned>(batch));
 #define CT2_DEC_MMA(GV)                                                                                           \

@@ -649,6 +649,7 @@ void gemm_s8_tc(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t 
   if (M == 0 || N == 0) return;
   CT2_REQUIRE(K % 16 == 0, "gemm_s8: k must be a multiple of 16");
   if (gemm_s8_decode(A, B, M, N, K, epi, dtype, st)) return;
+  if (gemm_s8_prefill(A, B, M, N, K, epi, dtype, st)) return;
   TcParams p{};
   p.dense = epi;
   CT2_DISPATCH_DTYPE(dtype, (launch_tc_shape<T, 0, 1>(A, B, nullptr, M, N, K, p, st)));
@@ -659,6 +660,7 @@ void gemm_s8_glu_tc(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int
   if (M == 0 || N == 0) return;
   CT2_REQUIRE(K % 16 == 0, "gemm_s8: k must be a multiple of 16");
   if (gemm_s8_glu_decode(A, Bgate, Bup, M, N, K, glu, dtype, st)) return;
+  if (gemm_s8_glu_prefill(A, Bgate, Bup, M, N, K, glu, dtype, st)) return;
   TcParams p{};
   p.glu = glu;
   CT2_DISPATCH_DTYPE(dtype, (launch_tc_shape<T, 0, 2>(A, Bgate, Bup, M, N, K, p, st)));
@@ -671,6 +673,7 @@ void gemm_f16_tc(const void* A, const void* B, const void* bias, const void* res
   CT2_REQUIRE(K % 8 == 0, "gemm_f16: k must be a multiple of 8");
   CT2_REQUIRE(dtype == CT2B200_F16 || dtype == CT2B200_BF16, "gemm_f16: dtype must be float16 or bfloat16");
   if (gemm_f16_decode(A, B, bias, residual, act, M, N, K, C, dtype, st)) return;
+  if (gemm_f16_prefill(A, B, bias, residual, act, M, N, K, C, dtype, st)) return;
   TcParams p{};
   p.fl = FloatEpilogue{bias, residual, C, act, N};
   if (dtype == CT2B200_F16) launch_tc_shape<__half, 1, 1>(A, B, nullptr, M, N, K, p, st);

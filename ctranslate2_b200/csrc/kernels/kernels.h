@@ -70,6 +70,14 @@ bool gemm_s8_glu_decode(const int8_t* A, const int8_t* Bgate, const int8_t* Bup,
 bool gemm_f16_decode(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
                      int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
 
+// gemm_prefill.cu (tcgen05, m > 64, compute bound): false = shape not covered
+bool gemm_s8_prefill(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
+                     int dtype, cudaStream_t st);
+bool gemm_s8_glu_prefill(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
+                         const GluEpilogue& glu, int dtype, cudaStream_t st);
+bool gemm_f16_prefill(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
+                      int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
+
 // dispatch by ct2b200_gemm_impl
 void gemm_s8(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
              int dtype, int impl, cudaStream_t st);

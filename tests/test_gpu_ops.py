@@ -197,6 +197,38 @@ def test_decode_gemm_plans(cs, rows, monkeypatch):
 
 
 @gpu
+@pytest.mark.parametrize("dt", ["float32", "float16", "bfloat16"])
+@pytest.mark.parametrize("mnk", [(65, 256, 128), (1000, 1000, 1024), (640, 776, 2048)])
+def test_prefill_gemm_tiles(dt, mnk):
+    """gemm_prefill.cu (m > 64): ragged tiles in m and n, several tiles per CTA, residual in place, GLU, f16 GEMM."""
+    m, n, k = mnk
+    r = np.random.default_rng(m + k)
+    x = round_through(r.standard_normal((m, k)), dt)
+    wq, ws = O.quantize_weight((r.standard_normal((n, k)) * 0.05).astype(np.float32))
+    wu, su = O.quantize_weight((r.standard_normal((n, k)) * 0.05).astype(np.float32))
+    bias = round_through(r.standard_normal(n) * 0.1, dt)
+    res = round_through(r.standard_normal((m, n)), dt)
+    xq, xs = ops.Quantize()(dev(x, TDT[dt]))
+    tol = TOL[dt] if dt != "float32" else 2e-5
+    for act, use_bias, use_res in ((-1, False, True), (ops.ActivationType.GELU, True, False)):
+        y = ops.dense_int8(xq, xs, dev(wq), dev(ws), dev(bias, TDT[dt]) if use_bias else None,
+                           dev(res, TDT[dt]) if use_res else None, None if act < 0 else act, TDT[dt], ops.GEMM_TCGEN05)
+        ref = O.dense_int8(x, wq, ws, bias if use_bias else None, act, res if use_res else None, "cuda")
+        np.testing.assert_allclose(to_np(y), ref, rtol=tol, atol=tol * max(1.0, float(np.abs(ref).max())))
+    if dt != "bfloat16":
+        h = ops.dense_int8_glu(xq, xs, dev(wq), dev(ws), dev(wu), dev(su), ops.ActivationType.Swish, TDT[dt], ops.GEMM_TCGEN05)
+        gate = round_through(O.dense_int8(x, wq, ws, None, O.ACT_SWISH), dt)
+        ref = gate * round_through(O.dense_int8(x, wu, su), dt)
+        np.testing.assert_allclose(to_np(h), ref, rtol=tol, atol=tol * max(1.0, float(np.abs(ref).max())))
+    if dt != "float32":
+        a = round_through(r.standard_normal((m, k)), dt)
+        b = round_through(r.standard_normal((n, k)) * 0.05, dt)
+        c = ops.Gemm()(dev(a, TDT[dt]), dev(b, TDT[dt]), bias=dev(bias, TDT[dt]))
+        ref = a.astype(np.float64) @ b.astype(np.float64).T + bias
+        np.testing.assert_allclose(to_np(c), ref, rtol=TOL[dt], atol=TOL[dt] * float(np.abs(ref).max()))
+
+
+@gpu
 def test_decode_gemm_auto_plan_llama_shapes():
     """The shapes of one Llama-3-8B decode layer through the planner's own choice (no pinning), batch 1 and 32."""
     r = np.random.default_rng(8)
