@@ -36,16 +36,16 @@ NAMES = {"8b": "Llama-3-8B", "1b": "Llama-3.2-1B-shaped", "tiny": "tiny-llama-d1
 PROMPT_LEN = 1024
 
 
-def model_dir(name):
+def model_dir(name, quant="int8_float16"):
     """Synthetic model directory in the reference's on-disk format (written once per box)."""
     from ctranslate2_b200.converters.synthetic import LlamaConfig, write_llama_model
     base = os.environ.get("CT2B200_BENCH_DIR", os.path.join(tempfile.gettempdir(), "ct2b200_bench"))
-    d = os.path.join(base, "llama_%s_int8_float16" % name)
+    d = os.path.join(base, "llama_%s_%s" % (name, quant))
     done = os.path.join(d, ".complete")
     if not os.path.exists(done):
         os.makedirs(base, exist_ok=True)
         t0 = time.time()
-        write_llama_model(d, LlamaConfig(**MODELS[name]), "int8_float16", seed=1234, fast_int8=True)
+        write_llama_model(d, LlamaConfig(**MODELS[name]), quant, seed=1234, fast_int8=True)
         open(done, "w").write("ok")
         print("[bench] wrote %s in %.1fs" % (d, time.time() - t0), file=sys.stderr)
     return d
@@ -237,6 +237,8 @@ def main():
     ap.add_argument("--prompt-len", type=int, default=PROMPT_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--tp", action="store_true",
+                    help="N > 1: ONE tensor-parallel generator over the N GPUs (strong scaling) instead of N replicas")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -244,7 +246,9 @@ def main():
     K, W, B, P = args.steps, max(3, args.warmup), args.batch, args.prompt_len
     config = {"workload": "%s generate_batch INT8 (int8_float16), greedy, bsz %d, prompt %d + %d generated "
                           "(BASELINE.json configs[2])" % (NAMES[args.model], B, P, K),
-              "global_batch": B * max(1, world), "prompt_len": P, "parallelism": "dp%d (replicas, no collective)" % world,
+              "global_batch": B * (1 if args.tp else max(1, world)), "prompt_len": P,
+              "parallelism": ("tp%d (heads / FFN columns sharded, collectives fused into kernels over NVLink peer memory)" % world)
+              if args.tp and world > 1 else "dp%d (replicas, no collective)" % world,
               "l2": "every step streams %.1f GB of weights (> 126 MB L2) — no flush needed" % (step_bytes(args.model, 0, 0) / 1e9)}
 
     if args.impl == "reference":
@@ -275,8 +279,10 @@ def main():
         torch.distributed.barrier()
         mdir = model_dir(args.model)
     max_len = P + max(K, 8) + W + 8
+    tp = args.tp and world > 1
     gen = ct2.Generator(mdir, device_index=local_rank, compute_type="int8_float16", max_batch_size=B,
-                        max_length=max_len, use_cuda_graph=not args.no_graph)
+                        max_length=max_len, use_cuda_graph=not args.no_graph, tensor_parallel=tp)
+    units = 1 if tp else world             # independent batches processed per step
     info = gen.info()
 
     def sync_all():
@@ -294,10 +300,10 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     dec_ms, pre_ms = float(t[0]), float(t[1])
-    value = B * K * world / (dec_ms * 1e-3)
+    value = B * K * units / (dec_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers ----
-    prompts = prompts_for(args.model, B, P, seed=42 + rank)
+    prompts = prompts_for(args.model, B, P, seed=42 + (0 if tp else rank))
     gen.generate_batch(prompts[:, :8].tolist(), max_length=2, min_length=2, end_token=[0])   # warm the small path
     sync_all()
     t0 = time.perf_counter()
@@ -309,7 +315,7 @@ def main():
     if world > 1:
         torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
     e2e_s = float(t[0])
-    e2e = {"value": round(B * K * world / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": round(B * P * 4 / K, 1),
+    e2e = {"value": round(B * K * units / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": round(B * P * 4 / K, 1),
            "d2h_bytes_per_step": B * 4, "seconds": round(e2e_s, 4), "includes": "prompt H2D + prefill(P-1) + K decode steps + ids D2H"}
 
     if rank != 0:
@@ -322,7 +328,7 @@ def main():
                    "step_roofline_frac": round(step_gbs / peak, 4), "prefill_ms": round(pre_ms, 2),
                    "prefill_tokens_per_s": round(B * (P - 1) / (pre_ms * 1e-3), 1), "weight_bytes": info["weight_bytes"]})
     line = {"metric": "generate_batch tokens/sec", "value": round(value, 2), "unit": "tokens/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": round(dec_ms / K, 4), "higher_is_better": True, "scaling": "weak",
+            "steps": K, "warmup": W, "ms_per_step": round(dec_ms / K, 4), "higher_is_better": True, "scaling": "strong" if tp else "weak",
             "vs_baseline": None, "dtype": "s8 (int8 x int8 -> s32 on tcgen05; f16 activations, f32 epilogue/softmax)",
             "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": int(launches)}

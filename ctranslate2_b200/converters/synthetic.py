@@ -251,14 +251,24 @@ def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
         off[0] = (off[0] + 7919) % base.size
         return a
 
+    packed_cache = {}
+
     def linear(prefix, n, k):
+        if fast and (n, k) in packed_cache:
+            # bench-sized models: layers of the same shape share one set of packed arrays (packing 7e9 nibbles in
+            # numpy takes minutes; the values do not matter for a throughput measurement)
+            for suffix, (arr, dt) in packed_cache[(n, k)].items():
+                w.add(prefix + suffix, arr, dt)
+            return
+        _linear(prefix, n, k)
+
+    def _linear(prefix, n, k):
         scales = (rng.uniform(0.6, 1.4, size=(k // G, n)) * (init_std / 2.5)).astype(np.float16)
         zeros = rng.integers(6, 10, size=(k // G, n))
         q = nibbles(k, n)                                   # [K, N] values 0..15
         if layout == 1:
-            w.add(prefix + "/weight", _pack_nibbles(q, AWQ_ORDER), "int32")
-            w.add(prefix + "/weight_scale", scales, "float16")
-            w.add(prefix + "/weight_zero", _pack_nibbles(zeros, AWQ_ORDER), "int32")
+            arrays = {"/weight": (_pack_nibbles(q, AWQ_ORDER), "int32"), "/weight_scale": (scales, "float16"),
+                      "/weight_zero": (_pack_nibbles(zeros, AWQ_ORDER), "int32")}
         else:
             ng = k // G
             zw = -(-ng // 8)
@@ -266,9 +276,12 @@ def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
             zp[:, :ng] = zeros.T
             sp = np.zeros((n, zw * 8), np.float16)
             sp[:, :ng] = scales.T
-            w.add(prefix + "/weight", _pack_nibbles(np.ascontiguousarray(q.T), np.arange(8)), "int32")
-            w.add(prefix + "/weight_scale", sp, "float16")
-            w.add(prefix + "/weight_zero", _pack_nibbles(zp, np.arange(8)), "int32")
+            arrays = {"/weight": (_pack_nibbles(np.ascontiguousarray(q.T), np.arange(8)), "int32"),
+                      "/weight_scale": (sp, "float16"), "/weight_zero": (_pack_nibbles(zp, np.arange(8)), "int32")}
+        for suffix, (arr, dt) in arrays.items():
+            w.add(prefix + suffix, arr, dt)
+        if fast:
+            packed_cache[(n, k)] = arrays
 
     def dense_f16(prefix, n, k):
         reps = -(-(n * k) // (1 << 22))

@@ -194,9 +194,9 @@ CT2B200_API int ct2b200_mul_quantize(const void* gate, const void* up, int64_t r
 }
 
 CT2B200_API size_t ct2b200_attention_decode_workspace(int64_t batch, int num_heads, int head_dim, int64_t max_len) {
-  // sized for the largest split count the launcher may choose (64)
+  // 16 slots per (row, head) for the split-KV kernel + 64 for the persistent kernel (attention_decode.cu)
   (void)max_len;
-  return attention_decode_workspace_bytes(batch, num_heads, head_dim, 64);
+  return attention_decode_workspace_bytes(batch, num_heads, head_dim, 80);
 }
 
 CT2B200_API int ct2b200_attention_decode(const void* qkv, void* k_cache, void* v_cache, const float* sin, const float* cos,

@@ -520,7 +520,7 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   logits_.alloc(max_batch_ * mc_.vocab * es);
   gathered_.alloc(max_batch_ * mc_.d_model * es);
   attn_splits_ = attention_decode_splits(max_batch_, heads_kv_, max_len_, sm_count_);
-  attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, heads_, mc_.head_dim, std::max(attn_splits_, 64)));
+  attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, heads_, mc_.head_dim, std::max(attn_splits_, 80)));
   CT2_CUDA_CHECK(cudaMemset(attn_ws_.ptr, 0, attn_ws_.bytes));
   if (tp_.world > 1) {
     // exchange buffer of this rank: [flags 2x8 u32 | pad to 256] [amax words 2 x 8 x R] [partials 2 x R x d_model]

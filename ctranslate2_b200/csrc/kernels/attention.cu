@@ -357,7 +357,7 @@ int attention_decode_splits(int64_t batch, int Hkv, int64_t max_len, int sm_coun
   // the smallest cost wins (ties: fewer slices, which also skips the partial/ticket/combine path when s == 1).
   if (const char* e = std::getenv("CT2B200_ATTN_SPLITS")) {
     const int s = std::atoi(e);
-    if (s >= 1 && s <= 64) return s;
+    if (s >= 1 && s <= 16) return s;
   }
   const int64_t ctas = batch * Hkv;
   const int64_t tiles = std::max<int64_t>(1, (max_len + 63) / 64);
@@ -389,7 +389,8 @@ void launch_attention_decode(const void* qkv, void* kc, void* vc, const float* s
   int32_t* tickets = static_cast<int32_t*>(workspace);
   const size_t toff = ((static_cast<size_t>(batch) * H * sizeof(int32_t) + 255) / 256) * 256;
   float* partials = reinterpret_cast<float*>(static_cast<uint8_t*>(workspace) + toff);
-  // persistent work-balanced kernel (attention_decode.cu) when the workspace holds its 64 slots per (row, head)
+  // persistent work-balanced kernel (attention_decode.cu) when the workspace holds its 64 slots per (row, head) behind
+  // the 16 of the split-KV kernel (which therefore never runs with more than 16 slices)
   const int slots = static_cast<int>((workspace_bytes - toff) / (static_cast<size_t>(batch) * H * partial_stride(D) * sizeof(float)));
   if (launch_attention_decode_persistent(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, D, max_len, interleave, scale, out,
                                          partials, tickets, slots, dtype, st))

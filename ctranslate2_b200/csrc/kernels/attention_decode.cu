@@ -389,16 +389,24 @@ bool launch_persistent_g(const void* qkv, void* kc, void* vc, const float* sn, c
 }  // namespace
 
 // fp16 / bf16, head_dim 64 or 128, G = H / Hkv in {1, 2, 4, 8}, batch <= 1024.  The workspace must hold kSlots (64)
-// partial slots per (row, head): attention_decode_workspace_bytes(batch, H, D, 64).  false = shape not covered.
+// partial slots per (row, head) behind the 16 of the split-KV kernel: attention_decode_workspace_bytes(batch, H, D, 80).  false = shape not covered.
 bool launch_attention_decode_persistent(const void* qkv, void* kc, void* vc, const float* sn, const float* cs,
                                         const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
                                         bool interleave, float scale, void* out, float* partials, int32_t* tickets,
                                         int slots, int dtype, cudaStream_t st) {
-  static const bool off = [] {
-    const char* e = std::getenv("CT2B200_ATTN_DECODE");
-    return e && (std::string(e) == "simt" || std::string(e) == "split");
-  }();
-  if (off || dtype == CT2B200_F32 || (D != 128 && D != 64) || batch > kMaxBatch || slots < kSlots) return false;
+  // Policy (measured in the decode graph of Llama-3-8B, tools/ablate.py): while all (row, KV head) pairs fit in ONE wave
+  // of the split-KV grid (attention_mma.cu) that kernel is 2-6 % faster per step (no prefix table, no cursor); beyond one
+  // wave its second, partial wave costs up to 40 %, and the work-balanced persistent kernel wins.
+  // CT2B200_ATTN_DECODE = persistent | split | simt pins the choice.
+  // (read on every call: the tests pin each kernel in turn).  The two kernels never share partial records: the split-KV
+  // kernel owns the first 16 slots' worth of the partial area, this one the next 64.
+  int mode = 0;
+  if (const char* e = std::getenv("CT2B200_ATTN_DECODE")) {
+    const std::string v(e);
+    mode = v == "persistent" ? 1 : (v == "split" || v == "simt") ? 2 : 0;
+  }
+  if (mode == 2 || dtype == CT2B200_F32 || (D != 128 && D != 64) || batch > kMaxBatch || slots < kSlots + 16) return false;
+  partials += static_cast<size_t>(batch) * H * 16 * (static_cast<size_t>(D) + 2);
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
   static int cached_dev = -1, cached_sms = 148;
@@ -407,6 +415,7 @@ bool launch_attention_decode_persistent(const void* qkv, void* kc, void* vc, con
     cached_dev = dev;
   }
   sms = cached_sms;
+  if (mode == 0 && batch * Hkv <= 2 * static_cast<int64_t>(sms)) return false;
   if (dtype == CT2B200_F16) {
     return D == 128 ? launch_persistent_g<__half, 128>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sms, st)
                     : launch_persistent_g<__half, 64>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, sms, st);

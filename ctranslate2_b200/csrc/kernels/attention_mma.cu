@@ -451,8 +451,9 @@ bool launch_attention_decode_mma(const void* qkv, void* kc, void* vc, const floa
                                  const int32_t* lens, int64_t batch, int H, int Hkv, int D, int64_t max_len,
                                  bool interleave, float scale, void* out, float* partials, int32_t* tickets, int splits,
                                  int dtype, cudaStream_t st) {
-  static const bool off = [] { const char* e = std::getenv("CT2B200_ATTN_DECODE"); return e && std::string(e) == "simt"; }();
-  if (off || dtype == CT2B200_F32 || (D != 128 && D != 64) || splits > 64) return false;
+  const char* e = std::getenv("CT2B200_ATTN_DECODE");
+  const bool off = e && std::string(e) == "simt";
+  if (off || dtype == CT2B200_F32 || (D != 128 && D != 64) || splits > 16) return false;
   if (dtype == CT2B200_F16) {
     return D == 128 ? launch_decode_mma_g<__half, 128>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, splits, st)
                     : launch_decode_mma_g<__half, 64>(qkv, kc, vc, sn, cs, lens, batch, H, Hkv, max_len, interleave, scale, out, partials, tickets, splits, st);

@@ -31,7 +31,13 @@ def ref_attention(q, k, v, G):
                                  dict(B=40, H=32, Hkv=8, D=128, lens="ragged"),
                                  dict(B=5, H=16, Hkv=2, D=64, lens=[1023, 0, 511, 64, 65]),
                                  dict(B=33, H=8, Hkv=8, D=128, lens="ragged")])
-def test_attention_decode(dt, cfg):
+@pytest.mark.parametrize("kernel", ["auto", "persistent", "split"])
+def test_attention_decode(dt, cfg, kernel, monkeypatch):
+    """kernel: the launcher's own choice, or CT2B200_ATTN_DECODE pinned to the persistent / the split-KV kernel."""
+    if kernel != "auto":
+        if dt == "float32" or cfg["D"] == 32:
+            pytest.skip("fp32 / head_dim 32 always take the SIMT kernel")
+        monkeypatch.setenv("CT2B200_ATTN_DECODE", kernel)
     B, H, Hkv, D, lens = cfg["B"], cfg["H"], cfg["Hkv"], cfg["D"], cfg["lens"]
     if lens == "ragged":
         lens = np.random.default_rng(B).integers(0, 1000, size=B).tolist()
@@ -94,10 +100,12 @@ def test_attention_prefill(dt, cfg):
 
 @gpu
 @pytest.mark.parametrize("dt", ["float16", "bfloat16"])
-def test_attention_decode_workspace_reuse(dt):
+@pytest.mark.parametrize("kernel", ["persistent", "split"])
+def test_attention_decode_workspace_reuse(dt, kernel, monkeypatch):
     """Successive launches on ONE workspace (as the 32 layers of a decode step do): the ready flags of the shared
     (row, head) pairs are cleared by the combining CTA, so later launches see a clean slate; results stay exact
     when the same cache is attended again at the next position."""
+    monkeypatch.setenv("CT2B200_ATTN_DECODE", kernel)
     B, H, Hkv, D, max_len = 2, 8, 2, 128, 2048
     G = H // Hkv
     r = np.random.default_rng(77)
