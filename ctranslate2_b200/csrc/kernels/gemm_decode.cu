@@ -410,7 +410,7 @@ DecPlan plan_decode(int64_t n, int kb_total, int sm_count) {
   // CT2B200_GEMM_CS / CT2B200_GEMM_ROWS pin the plan (tests sweep every cluster size and tile height with them)
   const int force_cs = env_int("CT2B200_GEMM_CS", 0);
   const int force_rows = env_int("CT2B200_GEMM_ROWS", 0);
-  const bool forced = force_cs != 0 || force_rows != 0;
+  const bool forced = force_cs != 0 || force_rows != 0 || std::getenv("CT2B200_GEMM_ROWSTEP") != nullptr;
   if (!forced) {
     std::lock_guard<std::mutex> lock(mu);
     auto it = cache.find({dev, n, kb_total});
@@ -430,8 +430,9 @@ DecPlan plan_decode(int64_t n, int kb_total, int sm_count) {
       case 3: maxc = clusters_for<T, KIND, BN, NB, 3>(stages, sm_count); break;
       default: maxc = clusters_for<T, KIND, BN, NB, 4>(stages, sm_count); break;
     }
-    for (int rows = 128; rows >= 64; rows -= 8) {
-      if (force_rows && rows != force_rows) continue;
+    // tile heights need not be multiples of the 8-row swizzle atom: the TMA box simply ends inside an atom
+    const int row_step = std::max(1, env_int("CT2B200_GEMM_ROWSTEP", 8));
+    for (int rows = force_rows ? force_rows : 128; rows >= (force_rows ? force_rows : 64); rows -= row_step) {
       const int tiles = static_cast<int>((n + rows - 1) / rows);
       if (tiles > maxc) continue;
       const double cost = static_cast<double>(rows) * NB * nkb * kSwizzleBytes + (cs > 1 ? 48.0 * 1024 : 0.0) +

@@ -164,7 +164,7 @@ def test_gemm_f16_tcgen05(dt, mnk):
 
 @gpu
 @pytest.mark.parametrize("cs", [1, 2, 3, 4])
-@pytest.mark.parametrize("rows", [128, 104, 64])
+@pytest.mark.parametrize("rows", [128, 104, 97, 64])
 def test_decode_gemm_plans(cs, rows, monkeypatch):
     """gemm_decode.cu: every cluster size (split-K through DSMEM) and tile height the planner can pick, pinned with
     CT2B200_GEMM_CS / CT2B200_GEMM_ROWS; fp32 output => any lost or doubled partial shows up at 2e-5."""
