@@ -20,6 +20,7 @@
 #include <algorithm>
 
 #include "../common.cuh"
+#include "awq_common.cuh"
 #include "gemm_common.cuh"
 #include "kernels.h"
 #include "tc_common.cuh"
@@ -89,30 +90,6 @@ __global__ void awq_dequantize_ref_layout_kernel(const int32_t* __restrict__ qwe
     const __half z = __int2half_rn(awq_zero(qzeros, layout, n, k / G, N, zw));
     w_out[idx] = __hmul(__hsub(q, z), awq_scale(scales, layout, n, k / G, N, sw));
   }
-}
-
-// the 8 channels of one native word -> 8 fp16 values in channel order: (q - z) * s
-__device__ __forceinline__ uint4 awq_dequant_word(uint32_t w, __half2 z_bot, __half2 z_top, __half2 s2) {
-  // bottom nibbles come out as 1024 + q, top nibbles as 1024 + 16 q (the reference's I4s_TO_F16s_MAGIC_NUM trick)
-  constexpr uint32_t kLut = (0xf0 & 0xcc) | 0xaa, kBot = 0x000f000f, kTop = 0x00f000f0, kMagic = 0x64006400;
-  const uint32_t t = w >> 8;
-  uint32_t h0, h1, h2, h3;
-  asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h0) : "r"(w), "n"(kBot), "n"(kMagic), "n"(kLut));
-  asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h1) : "r"(w), "n"(kTop), "n"(kMagic), "n"(kLut));
-  asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h2) : "r"(t), "n"(kBot), "n"(kMagic), "n"(kLut));
-  asm volatile("lop3.b32 %0, %1, %2, %3, %4;" : "=r"(h3) : "r"(t), "n"(kTop), "n"(kMagic), "n"(kLut));
-  const __half2 sixteenth = __float2half2_rn(0.0625f);
-  // z_bot = 1024 + z (exact), z_top = -(64 + z) (exact): both subtractions are exact in fp16, then one rounding
-  __half2 v0 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h0), z_bot), s2);
-  __half2 v1 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h1), sixteenth, z_top), s2);
-  __half2 v2 = __hmul2(__hsub2(*reinterpret_cast<__half2*>(&h2), z_bot), s2);
-  __half2 v3 = __hmul2(__hfma2(*reinterpret_cast<__half2*>(&h3), sixteenth, z_top), s2);
-  uint4 r;
-  r.x = *reinterpret_cast<uint32_t*>(&v0);
-  r.y = *reinterpret_cast<uint32_t*>(&v1);
-  r.z = *reinterpret_cast<uint32_t*>(&v2);
-  r.w = *reinterpret_cast<uint32_t*>(&v3);
-  return r;
 }
 
 // native layout -> W^T [N, K] fp16 (K-major, what gemm_f16_tc consumes) for the prefill arm
@@ -544,6 +521,7 @@ void dense_awq(const void* x, const AwqNative& w, const void* bias, const void* 
     gemm_f16_tc(x, scratch_nk_f16, bias, residual, act, m, w.n, w.k, y, CT2B200_F16, st);
     return;
   }
+  if (dense_awq_decode(x, w, bias, residual, act, m, y, st)) return;
   AwqParams p{};
   p.fl = FloatEpilogue{bias, residual, y, act, w.n};
   if (m <= 16) launch_awq<16, 1>(x, w, nullptr, m, p, st);
@@ -564,6 +542,7 @@ void dense_awq_glu(const void* x, const AwqNative& wg, const AwqNative& wu, int 
     launch_mul_inplace_f16(h, scratch_mn_f16, m * wg.n, st);
     return;
   }
+  if (dense_awq_glu_decode(x, wg, wu, act, m, h, st)) return;
   AwqParams p{};
   p.glu = FloatGluEpilogue{h, act, wg.n};
   if (m <= 16) launch_awq<16, 2>(x, wg, &wu, m, p, st);

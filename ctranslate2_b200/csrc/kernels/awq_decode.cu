@@ -1,0 +1,500 @@
+// awq_decode.cu — AWQ-INT4 weight-streaming GEMM of the decode step (m <= 64) on tcgen05.
+//
+// Replaces ops::GemmAwq / ops::GemvAwq (+ ops::Sum over split-K planes, + bias / activation / Mul) of the reference
+// (src/ops/awq/gemm_gpu.cu, gemv_gpu.cu; dispatch src/layers/common.cc:402-438) by one kernel per Dense.
+//
+// Same plan as gemm_decode.cu (one tile per CTA, tile height and DSMEM split-K cluster chosen so that tiles x CS fills
+// the SMs in one wave, weights prefetched before griddepcontrol.wait), plus what 4-bit weights need:
+//   * the bytes that come from HBM are the packed nibbles: 4 KB per 128-row x 64-channel block.  They get their OWN deep
+//     ring (up to 24 blocks = 96 KB in flight per SM), decoupled from the shallow ring (3 stages) of dequantized fp16
+//     operand tiles (16 KB per block).  The first version staged both in one ring of 8 x 22 KB and never had more than
+//     32 KB of HBM traffic in flight per SM (8-22 % of the HBM peak).
+//   * 8 transform warps turn nibbles into fp16 (q - z) * s (exact subtraction, one fp16 rounding: the arithmetic of the
+//     reference's dequantize_s4_to_fp16x2 + sub.f16x2 + fma.rn.f16x2) straight into the 128B-swizzled K-major UMMA
+//     operand layout; group scales / zeros are fetched one group ahead.
+//   * tcgen05.mma kind::f16, fp32 accumulators in TMEM; epilogue = gemm_decode_common.cuh (float arm).
+#include <map>
+#include <mutex>
+#include <tuple>
+
+#include "awq_common.cuh"
+#include "gemm_decode_common.cuh"
+#include "kernels.h"
+
+namespace ct2b200 {
+namespace {
+
+using namespace tc;
+using namespace dec;
+
+constexpr int kThreads = 448;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-13 transform
+constexpr int kDeqWarps = 8;
+constexpr int kBKh = 64;               // fp16 channels per K block (one 128-byte swizzle atom)
+constexpr int kPacked = kTileM * kBKh / 2;      // 4096 bytes of nibbles per weight per block
+constexpr int kAStages = 3;
+constexpr int kMaxP = 24;
+
+struct AwqDecParams {
+  DecParams d;
+  int64_t k;
+  int group;
+  int p_stages;                  // depth of the packed / activation ring
+  const __half* sc[2];           // [n, k/group] group scales (index 1: GLU "up")
+  const __half* zr[2];
+};
+
+template <int BN, int NB>
+struct AwqDecSmem {
+  static constexpr int kP = NB * kPacked + BN * kSwizzleBytes;     // one block of the packed ring: nibbles + activations
+  static constexpr int kA = NB * kTileM * kSwizzleBytes;           // one dequantized operand stage
+  static constexpr int kCtrl = 1024;
+  static size_t red_bytes(int cs) { return cs > 1 ? static_cast<size_t>(cs) * NB * (BN / 16) * ((16 + cs - 1) / cs) * kTileM * 4 : 0; }
+  static size_t bytes(int p_stages, int cs) {
+    return static_cast<size_t>(kAStages) * kA + static_cast<size_t>(p_stages) * kP + kCtrl + red_bytes(cs) + 1024;
+  }
+};
+
+template <int BN, int NB, int CS>
+__global__ void __launch_bounds__(kThreads, 1)
+    awq_decode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
+                      const __grid_constant__ CUtensorMap tm_w2, const AwqDecParams ap) {
+  using S = AwqDecSmem<BN, NB>;
+  using T = __half;
+  const DecParams& p = ap.d;
+  constexpr int kAccCols = BN * NB;
+  constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : 128;
+  constexpr int cp16 = (16 + CS - 1) / CS;
+  constexpr int cpr = (BN / 16) * cp16;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint8_t* a_ring = smem;                                         // [kAStages][NB][128 x 128 B]
+  uint8_t* p_ring = a_ring + kAStages * S::kA;                    // [p_stages][nibbles NB x 4 KB | x BN x 128 B]
+  const int PD = ap.p_stages;
+  uint8_t* ctrl = p_ring + static_cast<size_t>(PD) * S::kP;
+  uint64_t* p_full = reinterpret_cast<uint64_t*>(ctrl);           // [kMaxP] TMA landed
+  uint64_t* p_free = p_full + kMaxP;                              // [kMaxP] 8 transform warps + the MMA commit
+  uint64_t* a_ready = p_free + kMaxP;                             // [kAStages] operand tile written (8 warps)
+  uint64_t* a_free = a_ready + kAStages;                          // [kAStages] MMAs that read it retired
+  uint64_t* acc_bar = a_free + kAStages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint32_t* red = reinterpret_cast<uint32_t*>(ctrl + S::kCtrl);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int tile = blockIdx.x / CS;
+  const int crank = CS > 1 ? static_cast<int>(blockIdx.x % CS) : 0;
+  const int kb_lo = crank * p.kb_total / CS, kb_hi = (crank + 1) * p.kb_total / CS;
+  const int nkb = kb_hi - kb_lo;
+  const int a0 = tile * p.tile_rows;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < PD; ++s) {
+      mbar_init(p_full + s, 1);
+      mbar_init(p_free + s, kDeqWarps + 1);
+    }
+    for (int s = 0; s < kAStages; ++s) {
+      mbar_init(a_ready + s, kDeqWarps);
+      mbar_init(a_free + s, 1);
+    }
+    mbar_init(acc_bar, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  griddep_launch();
+  if (CS > 1) cluster_arrive();
+
+  if (warp == 0) {
+    // ===== TMA producer: packed nibbles (+ second weight) and the activation block =====
+    if (lane == 0) {
+      const uint32_t tx = static_cast<uint32_t>(NB * p.tile_rows * (kBKh / 2) + BN * kSwizzleBytes);
+      auto weights = [&](int s, int kb) {
+        uint8_t* st = p_ring + static_cast<size_t>(s) * S::kP;
+        tma_load_2d(st, &tm_w, p_full + s, kb * (kBKh / 2), a0, kEvictFirst);
+        if (NB == 2) tma_load_2d(st + kPacked, &tm_w2, p_full + s, kb * (kBKh / 2), a0, kEvictFirst);
+      };
+      auto acts = [&](int s, int kb) {
+        tma_load_2d(p_ring + static_cast<size_t>(s) * S::kP + NB * kPacked, &tm_x, p_full + s, kb * kBKh, 0, kEvictLast);
+      };
+      const int pre = min(PD, nkb);
+#pragma unroll 1
+      for (int i = 0; i < pre; ++i) {
+        mbar_expect_tx(p_full + i, tx);
+        weights(i, kb_lo + i);
+      }
+      griddep_wait();
+#pragma unroll 1
+      for (int i = 0; i < pre; ++i) acts(i, kb_lo + i);
+#pragma unroll 1
+      for (int it = pre; it < nkb; ++it) {
+        const int s = it % PD;
+        mbar_wait(p_free + s, ((it / PD) & 1) ^ 1);
+        mbar_expect_tx(p_full + s, tx);
+        weights(s, kb_lo + it);
+        acts(s, kb_lo + it);
+      }
+    }
+  } else if (warp == 1) {
+    // ===== MMA issuer =====
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc<1>(BN);
+#pragma unroll 1
+      for (int it = 0; it < nkb; ++it) {
+        const int sp = it % PD, sa = it % kAStages;
+        mbar_wait(p_full + sp, (it / PD) & 1);                    // activations of this block landed
+        mbar_wait(a_ready + sa, (it / kAStages) & 1);             // weights dequantized
+        tc_fence_after();
+        const uint32_t abase = smem_u32(a_ring + sa * S::kA);
+        const uint64_t db = make_smem_desc(smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * kPacked));
+#pragma unroll
+        for (int w = 0; w < NB; ++w) {
+          const uint64_t da = make_smem_desc(abase + w * kTileM * kSwizzleBytes);
+#pragma unroll
+          for (int k = 0; k < kBKh / 16; ++k)
+            umma<1>(tmem_base + w * BN, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+        }
+        umma_commit(a_free + sa);
+        umma_commit(p_free + sp);
+      }
+      umma_commit(acc_bar);
+    }
+  } else if (warp >= 6) {
+    // ===== transform warps: nibbles -> fp16 (q - z) * s into the swizzled operand tile =====
+    const int d = threadIdx.x - 192;                   // 0..255
+    const int r = d & 127;                             // tile row of this thread
+    const int half = d >> 7;                           // which 32 channels of the 64-channel block
+    const int64_t ng = ap.k / ap.group;
+    const int64_t row = static_cast<int64_t>(a0) + r;
+    const bool row_ok = r < p.tile_rows && row < p.n;
+    int64_t cur_g = -1;
+    __half zc[NB], sc_[NB], zn[NB], sn_[NB];
+    auto fetch = [&](int64_t g, __half (&z)[NB], __half (&sc)[NB]) {
+#pragma unroll
+      for (int w = 0; w < NB; ++w) {
+        const bool ok = row_ok && g < ng;
+        z[w] = ok ? ap.zr[w][row * ng + g] : __float2half(0.f);
+        sc[w] = ok ? ap.sc[w][row * ng + g] : __float2half(0.f);
+      }
+    };
+#pragma unroll 1
+    for (int it = 0; it < nkb; ++it) {
+      const int sp = it % PD, sa = it % kAStages;
+      const int64_t g = (static_cast<int64_t>(kb_lo + it) * kBKh) / ap.group;
+      if (g != cur_g) {
+        if (g == cur_g + 1 && cur_g >= 0) {
+#pragma unroll
+          for (int w = 0; w < NB; ++w) { zc[w] = zn[w]; sc_[w] = sn_[w]; }
+        } else {
+          fetch(g, zc, sc_);
+        }
+        fetch(g + 1, zn, sn_);                         // next group of this row, off the critical path
+        cur_g = g;
+      }
+      mbar_wait(p_full + sp, (it / PD) & 1);
+      if (it >= kAStages) mbar_wait(a_free + sa, ((it / kAStages) & 1) ^ 1);
+      const uint8_t* pk = p_ring + static_cast<size_t>(sp) * S::kP;
+      uint8_t* at = a_ring + sa * S::kA;
+#pragma unroll
+      for (int w = 0; w < NB; ++w) {
+        const __half2 zb = __half2half2(__hadd(__float2half(1024.f), zc[w]));
+        const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), zc[w])));
+        const __half2 s2 = __half2half2(sc_[w]);
+        const uint4 wv = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2) + half * 16);
+        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+        uint8_t* arow = at + w * kTileM * kSwizzleBytes + r * kSwizzleBytes;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {                  // chunk cc of the row lives at chunk cc ^ (r & 7) under SWIZZLE_128B
+          const int cc = half * 4 + c;
+          *reinterpret_cast<uint4*>(arow + ((cc ^ (r & 7)) << 4)) = awq_dequant_word(words[c], zb, zt, s2);
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
+      __syncwarp();
+      if (lane == 0) {
+        mbar_arrive(a_ready + sa);
+        mbar_arrive(p_free + sp);
+      }
+    }
+  } else {
+    // ===== epilogue warps (2..5): thread = output channel =====
+    const int q = warp & 3;
+    const int rloc = q * 32 + lane;
+    const int64_t arow = static_cast<int64_t>(a0) + rloc;
+    const bool row_ok = rloc < p.tile_rows && arow < p.n;
+    const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    griddep_wait();
+    float bias_t = 0.f;
+    if (row_ok && p.bias) bias_t = to_f32(static_cast<const T*>(p.bias)[arow]);
+    mbar_wait(acc_bar, 0);
+    tc_fence_after();
+    if constexpr (CS == 1) {
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[NB][16];
+#pragma unroll
+        for (int w = 0; w < NB; ++w) tmem_ld16x16(taddr + w * BN + c0, r[w]);
+        if (row_ok && c0 < p.m) dec_finish<T, 1, NB, 16>(p, r, arow, c0, 1, 16, 1.f, 1.f, bias_t);
+      }
+    } else {
+      cluster_wait();
+      uint32_t peer[CS];
+#pragma unroll
+      for (int o = 0; o < CS; ++o) {
+        const uint32_t local = smem_u32(red + static_cast<size_t>(crank) * NB * cpr * kTileM + rloc);
+        asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(peer[o]) : "r"(local), "r"(o));
+      }
+#pragma unroll 1
+      for (int c0 = 0; c0 < BN; c0 += 16) {
+        uint32_t r[NB][16];
+#pragma unroll
+        for (int w = 0; w < NB; ++w) tmem_ld16x16(taddr + w * BN + c0, r[w]);
+        const uint32_t chunk_off = static_cast<uint32_t>((c0 / 16) * cp16 * kTileM * 4);
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+#pragma unroll
+          for (int w = 0; w < NB; ++w) {
+            const uint32_t off = static_cast<uint32_t>((w * cpr + j / CS) * kTileM * 4);
+            asm volatile("st.shared::cluster.u32 [%0], %1;" ::"r"(peer[j % CS] + chunk_off + off), "r"(r[w][j]) : "memory");
+          }
+      }
+    }
+  }
+
+  if constexpr (CS > 1) {
+    __syncwarp();
+    if (warp < 2 || warp >= 6) cluster_wait();         // phase 1 (the epilogue warps consumed it above)
+    cluster_arrive();
+    cluster_wait();
+    if (warp >= 2 && warp < 6) {
+      const int q = warp & 3;
+      const int rloc = q * 32 + lane;
+      const int64_t arow = static_cast<int64_t>(a0) + rloc;
+      const bool row_ok = rloc < p.tile_rows && arow < p.n;
+      float bias_t = 0.f;
+      if (row_ok && p.bias) bias_t = to_f32(static_cast<const T*>(p.bias)[arow]);
+      const int nvalid = (16 - crank + CS - 1) / CS;
+#pragma unroll 1
+      for (int ch = 0; ch < BN / 16; ++ch) {
+        uint32_t r[NB][cp16];
+#pragma unroll
+        for (int w = 0; w < NB; ++w)
+#pragma unroll
+          for (int jj = 0; jj < cp16; ++jj) {
+            float acc = 0.f;
+#pragma unroll
+            for (int src = 0; src < CS; ++src)         // fixed rank order: deterministic
+              acc += __uint_as_float(red[(static_cast<size_t>(src * NB + w) * cpr + ch * cp16 + jj) * kTileM + rloc]);
+            r[w][jj] = __float_as_uint(acc);
+          }
+        const int col0 = ch * 16 + crank;
+        if (row_ok && col0 < p.m) dec_finish<T, 1, NB, cp16>(p, r, arow, col0, CS, nvalid, 1.f, 1.f, bias_t);
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+// ---- host side ----
+struct AwqPlan {
+  int cs = 0, tile_rows = 128, tiles = 0, p_stages = 4;
+};
+
+CUtensorMap make_packed_map(const void* wp, int64_t n, int64_t k, int box_rows) {
+  // wp as bytes [n, k/2]; box = box_rows x 32 bytes, no swizzle
+  CUtensorMap m;
+  cuuint64_t dims[2] = {static_cast<cuuint64_t>(k / 2), static_cast<cuuint64_t>(n)};
+  cuuint64_t strides[1] = {static_cast<cuuint64_t>(k / 2)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBKh / 2), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t estr[2] = {1, 1};
+  const CUresult r = get_tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(wp), dims, strides, box,
+                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (awq) failed with code " + std::to_string(r));
+  return m;
+}
+
+template <int BN, int NB>
+int p_stages_for(int cs, int nkb) {
+  using S = AwqDecSmem<BN, NB>;
+  const size_t cap = 220 * 1024;
+  const size_t fixed = static_cast<size_t>(kAStages) * S::kA + S::kCtrl + S::red_bytes(cs) + 1024;
+  if (fixed + 2 * S::kP > cap) return 0;
+  int st = static_cast<int>((cap - fixed) / S::kP);
+  st = std::min(st, kMaxP);
+  return std::max(2, std::min(st, std::max(nkb, 2)));
+}
+
+template <int BN, int NB, int CS>
+void configure_once() {
+  static bool done = false;
+  if (done) return;
+  CT2_CUDA_CHECK(cudaFuncSetAttribute(awq_decode_kernel<BN, NB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
+  done = true;
+}
+
+template <int BN, int NB, int CS>
+int clusters_for(int p_stages, int sm_count) {
+  configure_once<BN, NB, CS>();
+  static std::mutex mu;
+  static std::map<std::pair<int, int>, int> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  std::lock_guard<std::mutex> lock(mu);
+  auto it = cache.find({dev, p_stages});
+  if (it != cache.end()) return it->second;
+  const int n = max_clusters(awq_decode_kernel<BN, NB, CS>, CS, kThreads, AwqDecSmem<BN, NB>::bytes(p_stages, CS), sm_count);
+  cache[{dev, p_stages}] = n;
+  return n;
+}
+
+template <int BN, int NB>
+AwqPlan plan_awq(int64_t n, int kb_total, int sm_count) {
+  static std::mutex mu;
+  static std::map<std::tuple<int, int64_t, int>, AwqPlan> cache;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  const int force_cs = env_int("CT2B200_GEMM_CS", 0);
+  const int force_rows = env_int("CT2B200_GEMM_ROWS", 0);
+  const bool forced = force_cs != 0 || force_rows != 0;
+  if (!forced) {
+    std::lock_guard<std::mutex> lock(mu);
+    auto it = cache.find({dev, n, kb_total});
+    if (it != cache.end()) return it->second;
+  }
+  AwqPlan best;
+  double best_cost = 1e30;
+  for (int cs = 1; cs <= 4; ++cs) {
+    if (force_cs && cs != force_cs) continue;
+    if (cs > 1 && kb_total < 2 * cs) continue;
+    const int nkb = (kb_total + cs - 1) / cs;
+    const int ps = p_stages_for<BN, NB>(cs, nkb);
+    if (ps == 0) continue;
+    int maxc = 0;
+    switch (cs) {
+      case 1: maxc = clusters_for<BN, NB, 1>(ps, sm_count); break;
+      case 2: maxc = clusters_for<BN, NB, 2>(ps, sm_count); break;
+      case 3: maxc = clusters_for<BN, NB, 3>(ps, sm_count); break;
+      default: maxc = clusters_for<BN, NB, 4>(ps, sm_count); break;
+    }
+    for (int rows = force_rows ? force_rows : 128; rows >= (force_rows ? force_rows : 64); rows -= 8) {
+      const int tiles = static_cast<int>((n + rows - 1) / rows);
+      if (tiles > maxc) continue;
+      const double cost = static_cast<double>(rows) * NB * nkb * (kBKh / 2) + (cs > 1 ? 24.0 * 1024 : 0.0) + (128 - rows) * 8.0;
+      if (cost < best_cost) {
+        best_cost = cost;
+        best.cs = cs;
+        best.tile_rows = rows;
+        best.tiles = tiles;
+        best.p_stages = ps;
+      }
+    }
+  }
+  if (!forced) {
+    std::lock_guard<std::mutex> lock(mu);
+    cache[{dev, n, kb_total}] = best;
+  }
+  return best;
+}
+
+template <int BN, int NB, int CS>
+void launch(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tmw2, const AwqDecParams& p, const AwqPlan& plan,
+            cudaStream_t st) {
+  configure_once<BN, NB, CS>();
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3(static_cast<unsigned>(plan.tiles * CS));
+  cfg.blockDim = dim3(kThreads);
+  cfg.dynamicSmemBytes = AwqDecSmem<BN, NB>::bytes(plan.p_stages, CS);
+  cfg.stream = st;
+  cudaLaunchAttribute attr[2];
+  int na = 0;
+  if (CS > 1) {
+    attr[na].id = cudaLaunchAttributeClusterDimension;
+    attr[na].val.clusterDim.x = CS;
+    attr[na].val.clusterDim.y = 1;
+    attr[na].val.clusterDim.z = 1;
+    ++na;
+  }
+  if (pdl_enabled()) {
+    attr[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+  }
+  cfg.attrs = attr;
+  cfg.numAttrs = na;
+  CT2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, awq_decode_kernel<BN, NB, CS>, tmx, tmw, tmw2, p));
+  check_launch();
+}
+
+template <int BN, int NB>
+bool run(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, AwqDecParams p, cudaStream_t st) {
+  const int kb_total = div_up(w.k, kBKh);
+  const AwqPlan plan = plan_awq<BN, NB>(w.n, kb_total, sm_count_of_current_device());
+  if (plan.cs == 0) return false;
+  p.d.n = w.n;
+  p.d.m = m;
+  p.d.kb_total = kb_total;
+  p.d.tile_rows = plan.tile_rows;
+  p.d.stages = plan.p_stages;
+  p.k = w.k;
+  p.group = w.group;
+  p.p_stages = plan.p_stages;
+  p.sc[0] = static_cast<const __half*>(w.sc);
+  p.zr[0] = static_cast<const __half*>(w.zr);
+  p.sc[1] = static_cast<const __half*>(w2 ? w2->sc : w.sc);
+  p.zr[1] = static_cast<const __half*>(w2 ? w2->zr : w.zr);
+  const CUtensorMap tmx = make_operand_map(x, m, w.k, 2, 1, BN);
+  const CUtensorMap tmw = make_packed_map(w.wp, w.n, w.k, plan.tile_rows);
+  const CUtensorMap tmw2 = make_packed_map(w2 ? w2->wp : w.wp, w.n, w.k, plan.tile_rows);
+  switch (plan.cs) {
+    case 1: launch<BN, NB, 1>(tmx, tmw, tmw2, p, plan, st); break;
+    case 2: launch<BN, NB, 2>(tmx, tmw, tmw2, p, plan, st); break;
+    case 3: launch<BN, NB, 3>(tmx, tmw, tmw2, p, plan, st); break;
+    default: launch<BN, NB, 4>(tmx, tmw, tmw2, p, plan, st); break;
+  }
+  return true;
+}
+
+template <int NB>
+bool run_m(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, const AwqDecParams& p, cudaStream_t st) {
+  if (m <= 16) return run<16, NB>(x, w, w2, m, p, st);
+  if (m <= 32) return run<32, NB>(x, w, w2, m, p, st);
+  return run<64, NB>(x, w, w2, m, p, st);
+}
+
+bool enabled() { return env_int("CT2B200_AWQ_DECODE", 1) != 0; }
+
+}  // namespace
+
+// false = shape not covered (more tiles than one wave holds, group not a multiple of 64): caller uses gemm_awq_tc_kernel
+bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const void* residual, int act, int64_t m, void* y,
+                      cudaStream_t st) {
+  if (!enabled() || m < 1 || m > 64 || w.group % kBKh != 0 || w.k % kBKh != 0) return false;
+  AwqDecParams p{};
+  p.d.bias = bias;
+  p.d.residual = residual;
+  p.d.y = y;
+  p.d.act = act;
+  p.d.ldy = w.n;
+  return run_m<1>(x, w, nullptr, m, p, st);
+}
+
+bool dense_awq_glu_decode(const void* x, const AwqNative& wg, const AwqNative& wu, int act, int64_t m, void* h, cudaStream_t st) {
+  if (!enabled() || m < 1 || m > 64 || wg.group % kBKh != 0 || wg.k % kBKh != 0 || wg.group != wu.group) return false;
+  AwqDecParams p{};
+  p.d.y = h;
+  p.d.act = act;
+  p.d.ldy = wg.n;
+  return run_m<2>(x, wg, &wu, m, p, st);
+}
+
+}  // namespace ct2b200

@@ -81,3 +81,36 @@ def test_dense_awq_glu(m):
     up = (x.astype(np.float64) @ wu[3].astype(np.float64)).astype(np.float32)
     ref = gate * up
     np.testing.assert_allclose(to_np(h), ref, rtol=2e-2, atol=2e-2 * np.abs(ref).max())
+
+
+@gpu
+@pytest.mark.parametrize("cs", [1, 2, 3, 4])
+@pytest.mark.parametrize("rows", [128, 96])
+def test_awq_decode_plans(cs, rows, monkeypatch):
+    """awq_decode.cu: every cluster size (split-K through DSMEM) and a reduced tile height, pinned with
+    CT2B200_GEMM_CS / CT2B200_GEMM_ROWS; also against the general kernel (CT2B200_AWQ_DECODE=0)."""
+    n, k, g = 1000 - 1000 % 8, 2048, 128
+    w_int, z_int, scales, deq = make_awq(n, k, g, cs * 10 + rows)
+    qw, sc, qz = pack(w_int, z_int, scales, g, ops.AWQ_GEMM)
+    wt = ops.AwqWeight(dev(qw), dev(sc), dev(qz), ops.AWQ_GEMM, g)
+    wu = make_awq(n, k, g, 3)
+    u_w = ops.AwqWeight(*[dev(a) for a in pack(*wu[:3], g, ops.AWQ_GEMM)], ops.AWQ_GEMM, g)
+    r = np.random.default_rng(cs)
+    for m in (1, 17, 33, 64):
+        x = r.standard_normal((m, k)).astype(np.float16)
+        res = r.standard_normal((m, n)).astype(np.float16)
+        monkeypatch.setenv("CT2B200_AWQ_DECODE", "0")
+        y_general = to_np(ops.dense_awq(dev(x), wt, residual=dev(res)))
+        monkeypatch.setenv("CT2B200_AWQ_DECODE", "1")
+        monkeypatch.setenv("CT2B200_GEMM_CS", str(cs))
+        monkeypatch.setenv("CT2B200_GEMM_ROWS", str(rows))
+        y = to_np(ops.dense_awq(dev(x), wt, residual=dev(res)))
+        h = to_np(ops.dense_awq_glu(dev(x), wt, u_w))
+        monkeypatch.delenv("CT2B200_GEMM_CS")
+        monkeypatch.delenv("CT2B200_GEMM_ROWS")
+        ref = x.astype(np.float64) @ deq.astype(np.float64) + res.astype(np.float64)
+        np.testing.assert_allclose(y, ref, rtol=1e-2, atol=1e-2 * max(1.0, np.abs(ref).max()))
+        np.testing.assert_allclose(y, y_general, rtol=4e-3, atol=4e-3 * max(1.0, np.abs(ref).max()))
+        gate = O.activation((x.astype(np.float64) @ deq.astype(np.float64)).astype(np.float32), O.ACT_SWISH)
+        up = (x.astype(np.float64) @ wu[3].astype(np.float64)).astype(np.float32)
+        np.testing.assert_allclose(h, gate * up, rtol=2e-2, atol=2e-2 * np.abs(gate * up).max())
