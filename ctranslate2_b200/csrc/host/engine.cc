@@ -434,7 +434,13 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   CT2_REQUIRE(f.find("decoder/layer_0/ffn/linear_0_noact/weight") != nullptr, "only gated FFN (ffn_glu) is supported");
   CT2_REQUIRE(f.find("decoder/layer_0/self_attention/layer_norm/beta") == nullptr, "only RMSNorm decoders are supported");
   CT2_REQUIRE(mc_.rotary_scaling_type != 1, "Su rotary scaling is not supported");
-  mc_.ffn_dim = f.get("decoder/layer_0/ffn/linear_0/weight").shape[0];
+  {
+    // output features of the gate projection: rows of an int8 / float weight, columns x 8 of an AWQ_GEMM-packed one
+    // (qweight [K, N/8]), rows of an AWQ_GEMV-packed one (qweight [N, K/8])
+    const HostVariable& gw = f.get("decoder/layer_0/ffn/linear_0/weight");
+    const bool awq = gw.type_id == 3 && f.find("decoder/layer_0/ffn/linear_0/weight_zero");
+    mc_.ffn_dim = (awq && static_cast<int>(f.config_number("quantization_type", 0)) == 1) ? gw.shape[1] * 8 : gw.shape[0];
+  }
   CT2_REQUIRE(mc_.num_heads % tp_.world == 0 && mc_.num_heads_kv % tp_.world == 0 && mc_.ffn_dim % tp_.world == 0,
               "tensor parallel: heads, kv heads and ffn width must be divisible by the number of ranks");
   heads_ = mc_.num_heads / tp_.world;
@@ -501,6 +507,9 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   for (int l = 0; l < mc_.num_layers; ++l) {
     k_cache_[l].alloc(cache_bytes);
     v_cache_[l].alloc(cache_bytes);
+    // the TMA-staged attention reads whole 64-key boxes: keys past the end are masked, but must be finite
+    CT2_CUDA_CHECK(cudaMemsetAsync(k_cache_[l].ptr, 0, cache_bytes, stream_));
+    CT2_CUDA_CHECK(cudaMemsetAsync(v_cache_[l].ptr, 0, cache_bytes, stream_));
   }
   chunk_rows_ = std::max<int64_t>(max_batch_, std::min<int64_t>(8192, max_batch_ * max_len_));
   const int64_t R = chunk_rows_;

@@ -256,7 +256,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     asm volatile("cp.async.wait_group %0;\n" ::"n"(kStages - 1));
     __syncthreads();
 
-    tile_step<T, D>(cx, sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, warp, lane,
+    tile_step<T, D, false>(cx, sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, warp, lane,
                     qf, acc, nkeys - cc.t * kTile);
     if (prefetch_q) q_store(s_q + (qb ^ 1) * G * D);   // read by the next iteration, after its __syncthreads
     __syncthreads();                               // the stage is free again (and may serve as scratch below)

@@ -15,6 +15,7 @@
 #include "kernels.h"
 #include "attention_tile.cuh"
 #include "mma_common.cuh"
+#include "tc_common.cuh"
 
 namespace ct2b200 {
 
@@ -243,21 +244,31 @@ __device__ __forceinline__ float rope_at_mma(const T* x, const float* sin, const
 
 template <typename T, int D, int G>
 __global__ void __launch_bounds__(kThreads, 2)
-    attention_decode_mma_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
+    attention_decode_mma_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                                const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
                                 const float* __restrict__ sin_t, const float* __restrict__ cos_t,
                                 const int32_t* __restrict__ lens, int H, int Hkv, int64_t max_len, bool interleave,
                                 float scale_log2, T* __restrict__ out, float* __restrict__ partials,
                                 int32_t* __restrict__ tickets) {
   using namespace attn;
+  using Ctx = TileCtx<T, D, true>;
   constexpr int NW = kThreads / 32;
   constexpr int kTileElems = kDecTile * D;
-  extern __shared__ __align__(16) uint8_t smem_raw[];
-  T* sK = reinterpret_cast<T*>(smem_raw);                       // [stages][64][D], XOR-swizzled 16-byte chunks
+  extern __shared__ uint8_t smem_dyn[];
+  // the TMA boxes (SWIZZLE_128B) need a 1024-byte aligned base
+  uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  T* sK = reinterpret_cast<T*>(smem_raw);                       // [stages][D/64 boxes][64 keys][128 B]
   T* sV = sK + kDecStages * kTileElems;
   float* s_q = reinterpret_cast<float*>(sV + kDecStages * kTileElems);   // [G][D]
   __shared__ float s_m[NW][G], s_l[NW][G];
   __shared__ bool s_last;
+  __shared__ __align__(8) uint64_t full_bar[kDecStages];
 
+  if (threadIdx.x == 0) {
+    for (int st = 0; st < kDecStages; ++st) tc::mbar_init(full_bar + st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   griddep_launch();
   griddep_wait();
   const int split = blockIdx.x, nsplit = gridDim.x, kvh = blockIdx.y, b = blockIdx.z;
@@ -288,22 +299,30 @@ __global__ void __launch_bounds__(kThreads, 2)
       kc[static_cast<int64_t>(pos) * D + i] = from_f32<T>(rope_at_mma(k_in, sn, cs, i, D, interleave));
       vc[static_cast<int64_t>(pos) * D + i] = v_in[i];
     }
+    asm volatile("fence.proxy.async;" ::: "memory");            // generic-proxy stores before the TMA (async proxy) reads
   }
   __syncthreads();
 
-  TileCtx<T, D> cx;
+  Ctx cx;
   cx.init(tid);
   const uint32_t sK_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
   const uint32_t sV_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
+  // K/V tiles by TMA: D*2/128 boxes of 64 keys x 128 bytes each, one mbarrier per stage (issued by thread 0)
+  const int row0 = static_cast<int>((static_cast<int64_t>(b) * Hkv + kvh) * max_len) + s0;
   auto load_tile = [&](int stage, int kt) {
-    const int64_t k0 = s0 + static_cast<int64_t>(kt) * kDecTile;
-    cx.load(sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, kc + k0 * D, vc + k0 * D,
-            static_cast<int>(s1 - k0));
-  };
+    tc::mbar_expect_tx(full_bar + stage, 2 * Ctx::kTileBytes);
 #pragma unroll
-  for (int st = 0; st < kDecStages - 1; ++st) {
-    if (st < ntiles) load_tile(st, st);
-    asm volatile("cp.async.commit_group;\n" ::);
+    for (int h = 0; h < Ctx::kBoxes; ++h) {
+      tc::tma_load_2d(reinterpret_cast<uint8_t*>(sK) + stage * Ctx::kTileBytes + h * Ctx::kBoxBytes, &tm_k, full_bar + stage,
+                      h * 64, row0 + kt * kDecTile, tc::kEvictFirst);
+      tc::tma_load_2d(reinterpret_cast<uint8_t*>(sV) + stage * Ctx::kTileBytes + h * Ctx::kBoxBytes, &tm_v, full_bar + stage,
+                      h * 64, row0 + kt * kDecTile, tc::kEvictFirst);
+    }
+  };
+  if (tid == 0) {
+#pragma unroll
+    for (int st = 0; st < kDecStages - 1; ++st)
+      if (st < ntiles) load_tile(st, st);
   }
 
   // Q as A fragments: rows 0..G-1 = heads, rows G..15 = 0
@@ -320,15 +339,13 @@ __global__ void __launch_bounds__(kThreads, 2)
 
   for (int kt = 0; kt < ntiles; ++kt) {
     const int stage = kt % kDecStages;
-    if (kt + kDecStages - 1 < ntiles) load_tile((kt + kDecStages - 1) % kDecStages, kt + kDecStages - 1);
-    asm volatile("cp.async.commit_group;\n" ::);
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(kDecStages - 1));
-    __syncthreads();
-    tile_step<T, D>(cx, sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, warp, lane, qf,
-                    acc, s1 - (s0 + kt * kDecTile));
+    // the stage refilled here was consumed in iteration kt - 1 (trailing __syncthreads)
+    if (tid == 0 && kt + kDecStages - 1 < ntiles) load_tile((kt + kDecStages - 1) % kDecStages, kt + kDecStages - 1);
+    tc::mbar_wait(full_bar + stage, (kt / kDecStages) & 1);
+    tile_step<T, D, true>(cx, sK_u32 + stage * Ctx::kTileBytes, sV_u32 + stage * Ctx::kTileBytes, warp, lane, qf, acc,
+                          s1 - (s0 + kt * kDecTile));
     __syncthreads();
   }
-  asm volatile("cp.async.wait_group 0;\n" ::);
 
   // ---- merge the 4 warps (each holds m, l, O for rows g < G over its keys) ----
   float l_run = acc.l;
@@ -400,7 +417,11 @@ bool launch_decode_mma_g(const void* qkv, void* kc, void* vc, const float* sn, c
                          int64_t batch, int H, int Hkv, int64_t max_len, bool interleave, float scale, void* out,
                          float* partials, int32_t* tickets, int splits, cudaStream_t st) {
   const int G = H / Hkv;
-  constexpr size_t smem = static_cast<size_t>(2 * kDecStages * kDecTile) * D * sizeof(T) + 8 * D * sizeof(float);
+  constexpr size_t smem = static_cast<size_t>(2 * kDecStages * kDecTile) * D * sizeof(T) + 8 * D * sizeof(float) + 1024;
+  // the caches as 2-D tensors [rows = batch * Hkv * max_len, D]; box = 64 keys x 128 bytes, 128B swizzle
+  const int kind = std::is_same<T, __half>::value ? 1 : 2;
+  const CUtensorMap tmk = tc::make_operand_map(kc, batch * Hkv * max_len, D, 2, kind, kDecTile);
+  const CUtensorMap tmv = tc::make_operand_map(vc, batch * Hkv * max_len, D, 2, kind, kDecTile);
   const float scale_log2 = scale * 1.4426950408889634f;
   dim3 grid(splits, Hkv, static_cast<unsigned>(batch));
 #define CT2_DEC_MMA(GV)                                                                                           \
@@ -411,7 +432,7 @@ bool launch_decode_mma_g(const void* qkv, void* kc, void* vc, const float* sn, c
       CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
       configured = true;                                                                                          \
     }                                                                                                             \
-    launch_pdl(kernel, grid, dim3(kThreads), smem, st, static_cast<const T*>(qkv), static_cast<T*>(kc),           \
+    launch_pdl(kernel, grid, dim3(kThreads), smem, st, tmk, tmv, static_cast<const T*>(qkv), static_cast<T*>(kc), \
                static_cast<T*>(vc), sn, cs, lens, H, Hkv, max_len, interleave, scale_log2, static_cast<T*>(out),  \
                partials, tickets);                                                                                \
   }

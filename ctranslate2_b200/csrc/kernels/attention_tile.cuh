@@ -52,20 +52,35 @@ __device__ __forceinline__ void ldsm4_t_u32(uint32_t (&r)[4], uint32_t s) {
                : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(s));
 }
 
-// Tile-invariant per-thread state.  Shared-memory tile layout: [64 keys][D] T, 16-byte chunk c of key r stored at
-// chunk c ^ (r & 7) (conflict-free for the row-wise cp.async writes and the 8-row ldmatrix reads).
-template <typename T, int D>
+// Tile-invariant per-thread state.  Two shared-memory tile layouts:
+//   kTma = false (cp.async staging):  [64 keys][D] T, 16-byte chunk c of key r stored at chunk c ^ (r & 7);
+//   kTma = true  (cp.async.bulk.tensor, SWIZZLE_128B boxes of 64 keys x 128 bytes):  [D*2/128 column halves][64 keys][128 B],
+//                chunk c (0..7) of a 128-byte row stored at c ^ (r & 7) — the hardware swizzle; tile base 1024-aligned.
+// Both are conflict-free for the 8-row ldmatrix reads.
+template <typename T, int D, bool kTma = false>
 struct TileCtx {
   static constexpr int CH = D / 8;                                   // 16-byte chunks per key
   static constexpr int kRowsPerPass = kTileThreads / CH;             // keys copied per cp.async pass of the CTA
   static constexpr int kPasses = kTileKeys / kRowsPerPass;
   static constexpr int kPassBytes = kRowsPerPass * D * static_cast<int>(sizeof(T));
   static constexpr int kTileBytes = kTileKeys * D * static_cast<int>(sizeof(T));
+  static constexpr int kBoxBytes = kTileKeys * 128;                  // one TMA box: 64 keys x 128 bytes
+  static constexpr int kBoxes = D * static_cast<int>(sizeof(T)) / 128;
   uint32_t cp_smem;        // byte offset of this thread's first chunk inside a tile
   uint32_t cp_gmem;        // byte offset of the same chunk relative to the tile's first key in the cache
   int cp_row;              // first key this thread copies (the others are cp_row + i * kRowsPerPass)
   uint32_t k_off[D / 16];  // ldmatrix offsets (bytes, relative to the warp's 16-key slab): QK^T, k-step kk
   uint32_t v_off[D / 16];  // ldmatrix.trans offsets: PV, n-tile pair j
+
+  // byte offset of 16-byte chunk `c` of key `rr` (relative to the slab of 16 keys the row belongs to)
+  static __device__ __forceinline__ uint32_t chunk_offset(int rr, int c) {
+    if constexpr (kTma) return static_cast<uint32_t>((c >> 3) * kBoxBytes + rr * 128 + (((c & 7) ^ (rr & 7)) * 16));
+    else return static_cast<uint32_t>(rr * D * sizeof(T) + ((c ^ (rr & 7)) * 16));
+  }
+  // byte offset of the warp's 16-key slab inside a tile
+  static __device__ __forceinline__ uint32_t slab_offset(int warp) {
+    return static_cast<uint32_t>(warp * 16 * (kTma ? 128 : D * static_cast<int>(sizeof(T))));
+  }
 
   __device__ __forceinline__ void init(int tid) {
     const int lane = tid & 31;
@@ -73,15 +88,12 @@ struct TileCtx {
     cp_row = r;
     cp_smem = static_cast<uint32_t>(r * D * sizeof(T) + ((ch ^ (r & 7)) * 16));
     cp_gmem = static_cast<uint32_t>(r * D * sizeof(T) + ch * 16);
-    const int x = lane & 7;
 #pragma unroll
     for (int kk = 0; kk < D / 16; ++kk) {
       const int rr = (lane & 7) + (lane >> 4) * 8;
-      const int c = kk * 2 + ((lane >> 3) & 1);
-      k_off[kk] = static_cast<uint32_t>(rr * D * sizeof(T) + ((c ^ x) * 16));
+      k_off[kk] = chunk_offset(rr, kk * 2 + ((lane >> 3) & 1));
       const int rv = (lane & 7) + ((lane >> 3) & 1) * 8;
-      const int cv = kk * 2 + (lane >> 4);
-      v_off[kk] = static_cast<uint32_t>(rv * D * sizeof(T) + ((cv ^ x) * 16));
+      v_off[kk] = chunk_offset(rv, kk * 2 + (lane >> 4));
     }
   }
 
@@ -123,12 +135,12 @@ struct WarpAcc {
 
 // One tile for one warp: keys [warp*16, warp*16+16) of the staged tile.  qf = Q as A fragments (rows 0..G-1 real,
 // pre-scaled by log2(e)/sqrt(d)); nvalid = valid keys of the tile (64 except on the ragged last tile).
-template <typename T, int D>
-__device__ __forceinline__ void tile_step(const TileCtx<T, D>& cx, uint32_t sk, uint32_t sv, int warp, int lane,
+template <typename T, int D, bool kTma>
+__device__ __forceinline__ void tile_step(const TileCtx<T, D, kTma>& cx, uint32_t sk, uint32_t sv, int warp, int lane,
                                           const uint32_t (&qf)[D / 16][2], WarpAcc<D>& acc, int nvalid) {
   const int t4 = lane & 3;
-  const uint32_t ks = sk + warp * 16 * D * sizeof(T);
-  const uint32_t vs = sv + warp * 16 * D * sizeof(T);
+  const uint32_t ks = sk + TileCtx<T, D, kTma>::slab_offset(warp);
+  const uint32_t vs = sv + TileCtx<T, D, kTma>::slab_offset(warp);
   float z[4][2] = {{0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}, {0.f, 0.f}};      // accumulator rows 8..15: stay zero
   // scores of keys 2*t4 (+1) and 8 + 2*t4 (+1); two partial sums each (even / odd k-steps) halve the HMMA chains
   float s0[2] = {0.f, 0.f}, s1[2] = {0.f, 0.f}, s0b[2] = {0.f, 0.f}, s1b[2] = {0.f, 0.f};

@@ -6,10 +6,10 @@
 // Same plan as gemm_decode.cu (one tile per CTA, tile height and DSMEM split-K cluster chosen so that tiles x CS fills
 // the SMs in one wave, weights prefetched before griddepcontrol.wait), plus what 4-bit weights need:
 //   * the bytes that come from HBM are the packed nibbles: 4 KB per 128-row x 64-channel block.  They get their OWN deep
-//     ring (up to 24 blocks = 96 KB in flight per SM), decoupled from the shallow ring (3 stages) of dequantized fp16
+//     ring (up to 24 blocks = 96 KB in flight per SM), decoupled from the shallow ring (4 stages) of dequantized fp16
 //     operand tiles (16 KB per block).  The first version staged both in one ring of 8 x 22 KB and never had more than
 //     32 KB of HBM traffic in flight per SM (8-22 % of the HBM peak).
-//   * 8 transform warps turn nibbles into fp16 (q - z) * s (exact subtraction, one fp16 rounding: the arithmetic of the
+//   * 16 transform warps (4 per scheduler: the conversion is instruction-bound) turn nibbles into fp16 (q - z) * s (exact subtraction, one fp16 rounding: the arithmetic of the
 //     reference's dequantize_s4_to_fp16x2 + sub.f16x2 + fma.rn.f16x2) straight into the 128B-swizzled K-major UMMA
 //     operand layout; group scales / zeros are fetched one group ahead.
 //   * tcgen05.mma kind::f16, fp32 accumulators in TMEM; epilogue = gemm_decode_common.cuh (float arm).
@@ -27,11 +27,11 @@ namespace {
 using namespace tc;
 using namespace dec;
 
-constexpr int kThreads = 448;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-13 transform
-constexpr int kDeqWarps = 8;
+constexpr int kThreads = 704;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-21 transform
+constexpr int kDeqWarps = 16;         // the int4 -> fp16 transform is the instruction-bound part: 4 warps per scheduler
 constexpr int kBKh = 64;               // fp16 channels per K block (one 128-byte swizzle atom)
 constexpr int kPacked = kTileM * kBKh / 2;      // 4096 bytes of nibbles per weight per block
-constexpr int kAStages = 3;
+constexpr int kAStages = 4;
 constexpr int kMaxP = 24;
 
 struct AwqDecParams {
@@ -73,8 +73,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int PD = ap.p_stages;
   uint8_t* ctrl = p_ring + static_cast<size_t>(PD) * S::kP;
   uint64_t* p_full = reinterpret_cast<uint64_t*>(ctrl);           // [kMaxP] TMA landed
-  uint64_t* p_free = p_full + kMaxP;                              // [kMaxP] 8 transform warps + the MMA commit
-  uint64_t* a_ready = p_free + kMaxP;                             // [kAStages] operand tile written (8 warps)
+  uint64_t* p_free = p_full + kMaxP;                              // [kMaxP] transform warps + the MMA commit
+  uint64_t* a_ready = p_free + kMaxP;                             // [kAStages] operand tile written (all transform warps)
   uint64_t* a_free = a_ready + kAStages;                          // [kAStages] MMAs that read it retired
   uint64_t* acc_bar = a_free + kAStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
@@ -164,9 +164,11 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp >= 6) {
     // ===== transform warps: nibbles -> fp16 (q - z) * s into the swizzled operand tile =====
-    const int d = threadIdx.x - 192;                   // 0..255
-    const int r = d & 127;                             // tile row of this thread
-    const int half = d >> 7;                           // which 32 channels of the 64-channel block
+    // thread -> (tile row, 16-channel quarter of the 64-channel block): the 4 threads of a row are adjacent lanes, so a
+    // warp reads 256 contiguous bytes of nibbles (8 rows x 32 B) and writes 32 distinct 16-byte chunks per store
+    const int d = threadIdx.x - 192;                   // 0..511
+    const int r = d >> 2;                              // tile row of this thread
+    const int quarter = d & 3;
     const int64_t ng = ap.k / ap.group;
     const int64_t row = static_cast<int64_t>(a0) + r;
     const bool row_ok = r < p.tile_rows && row < p.n;
@@ -203,12 +205,12 @@ __global__ void __launch_bounds__(kThreads, 1)
         const __half2 zb = __half2half2(__hadd(__float2half(1024.f), zc[w]));
         const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), zc[w])));
         const __half2 s2 = __half2half2(sc_[w]);
-        const uint4 wv = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2) + half * 16);
-        const uint32_t words[4] = {wv.x, wv.y, wv.z, wv.w};
+        const uint2 wv = *reinterpret_cast<const uint2*>(pk + w * kPacked + r * (kBKh / 2) + quarter * 8);
+        const uint32_t words[2] = {wv.x, wv.y};
         uint8_t* arow = at + w * kTileM * kSwizzleBytes + r * kSwizzleBytes;
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {                  // chunk cc of the row lives at chunk cc ^ (r & 7) under SWIZZLE_128B
-          const int cc = half * 4 + c;
+        for (int c = 0; c < 2; ++c) {                  // chunk cc of the row lives at chunk cc ^ (r & 7) under SWIZZLE_128B
+          const int cc = quarter * 2 + c;
           *reinterpret_cast<uint4*>(arow + ((cc ^ (r & 7)) << 4)) = awq_dequant_word(words[c], zb, zt, s2);
         }
       }

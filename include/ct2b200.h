@@ -146,7 +146,9 @@ CT2B200_API int ct2b200_mul_quantize(const void* gate_d, const void* up_d, int64
 
 /* Decode step (one new token per sequence): rotary(q,k) at position lens[b], append k/v at lens[b],
  * softmax(q k^T / sqrt(d)) v over positions 0..lens[b].  out [batch, H*head_dim] T.
- * lens_d int32 [batch] = tokens already cached per row (not modified).  head_dim must be 128 or 64 or 32. */
+ * lens_d int32 [batch] = tokens already cached per row (not modified).  head_dim must be 128 or 64 or 32.
+ * The caches must hold finite values everywhere (zero-initialise them once): whole 64-key boxes are staged and the
+ * keys past lens_d[b] are masked, not skipped.  workspace_d: ct2b200_attention_decode_workspace bytes, zeroed once. */
 CT2B200_API int ct2b200_attention_decode(const void* qkv_d, void* k_cache_d, void* v_cache_d, const float* sin_d,
                              const float* cos_d, const int32_t* lens_d, int64_t batch, int num_heads,
                              int num_heads_kv, int head_dim, int64_t max_len, int rotary_interleave,

@@ -146,7 +146,8 @@ def test_awq_and_float_models_vs_oracle(tmp_path, quant):
     """AWQ-INT4 (both reference layouts) and float16/bfloat16-weight model dirs: logits vs the oracle, greedy
     tokens stable across prefill/decode splits."""
     d = str(tmp_path / quant)
-    cfg = LlamaConfig(num_layers=2, num_heads=8, num_heads_kv=2, head_dim=128, ffn_dim=1024, vocab_size=1000,
+    # ffn_dim != d_model on purpose: an AWQ_GEMM-packed weight is [K, N/8], so its first dimension is NOT the layer width
+    cfg = LlamaConfig(num_layers=2, num_heads=8, num_heads_kv=2, head_dim=128, ffn_dim=1536, vocab_size=1000,
                       rotary_scaling_type=2, rotary_scaling_factor=8.0, rotary_low_freq_factor=1.0,
                       rotary_high_freq_factor=4.0, original_max_position_embeddings=64)
     write_llama_model(d, cfg, quant, seed=5, init_std=0.05)
