@@ -155,9 +155,12 @@ def gemm_roofline(name, batch, device):
     alg = 2 * f * d + 2 * f * 4 + batch * d + batch * 4 + batch * f * 2    # weights + scales + x + h(out)
     peak, how = measured_peaks()
     ach = alg / (ms * 1e-3) / 1e9
-    return {"bound": "hbm", "kernel": "gemm_tc_kernel<s8, swap-AB, GLU> (ffn gate/up %dx%d, m=%d)" % (2 * f, d, batch),
+    # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed ncu --set full capture
+    # (profiles/r01_ncu_full_b32_v4.md: 117.73 MB + 3.95 MB at m = 32); null for shapes that were not captured
+    traffic = 121676544 if (name == "8b" and batch == 32) else None
+    return {"bound": "hbm", "kernel": "gemm_decode_kernel<s8, NB=2 gate/up + SwiGLU> (ffn gate/up %dx%d, m=%d)" % (2 * f, d, batch),
             "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
-            "traffic": None, "bytes_per_launch": alg, "us_per_launch": round(ms * 1e3, 2), "peak_source": how}
+            "traffic": traffic, "bytes_per_launch": alg, "us_per_launch": round(ms * 1e3, 2), "peak_source": how}
 
 
 def _ref_thread_cache():

@@ -16,8 +16,8 @@
 //     at the END of its range, when the other parts are normally long done, folds them in slot order (deterministic)
 //     and clears the flags for the next launch.  All CTAs of the grid are co-resident (grid = occupancy x SMs).
 // Inner loop (per tile): the G query heads of the KV head are rows 0..G-1 of a 16-row MMA tile; warp w owns keys
-// [16w, 16w+16): S = Q K^T (mma.sync m16n8k16, fp32), online softmax in fp32, O += P V.  K/V tiles are staged with
-// 16-byte cp.async into XOR-swizzled shared memory (no padding: 96 KB per CTA for D = 128, two CTAs per SM).
+// [16w, 16w+16): S = Q K^T (mma.sync m16n8k16, fp32), online softmax in fp32, O += P V.  K/V tiles are staged by TMA
+// (64 keys x 128 B boxes, SWIZZLE_128B, one mbarrier per stage; 96 KB per CTA for D = 128, two CTAs per SM).
 // The new token's rotated K and its V are appended to the cache by the CTA that owns the pair's last tile.
 #include <cstdlib>
 #include <string>
@@ -26,6 +26,7 @@
 #include "kernels.h"
 #include "attention_tile.cuh"
 #include "mma_common.cuh"
+#include "tc_common.cuh"
 
 namespace ct2b200 {
 namespace {
@@ -53,7 +54,8 @@ struct UnitCursor {                  // position in the (row, KV head, tile) enu
 
 template <typename T, int D, int G>
 __global__ void __launch_bounds__(kThreads, 2)
-    attention_decode_persistent_kernel(const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
+    attention_decode_persistent_kernel(const __grid_constant__ CUtensorMap tm_k, const __grid_constant__ CUtensorMap tm_v,
+                                       const T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
                                        const float* __restrict__ sin_t, const float* __restrict__ cos_t,
                                        const int32_t* __restrict__ lens, int batch, int H, int Hkv, int64_t max_len,
                                        bool interleave, float scale_log2, T* __restrict__ out,
@@ -61,16 +63,24 @@ __global__ void __launch_bounds__(kThreads, 2)
   constexpr int NW = kThreads / 32;
   constexpr int kTileElems = kTile * D;
   constexpr size_t PS = static_cast<size_t>(D) + 2;
-  extern __shared__ __align__(128) uint8_t smem_raw[];
-  T* sK = reinterpret_cast<T*>(smem_raw);                           // [stages][64][D], chunk c of row r at c ^ (r & 7)
+  extern __shared__ uint8_t smem_dyn[];
+  // TMA boxes (64 keys x 128 B, SWIZZLE_128B) need a 1024-byte aligned base
+  uint8_t* smem_raw = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_dyn) + 1023) & ~uintptr_t(1023));
+  T* sK = reinterpret_cast<T*>(smem_raw);                           // [stages][D/64 boxes][64 keys][128 B]
   T* sV = sK + kStages * kTileElems;
   float* s_q = reinterpret_cast<float*>(sV + kStages * kTileElems);  // [2][G][D] (current / next segment)
   int* s_pref = reinterpret_cast<int*>(s_q + 2 * G * D);             // [batch + 1] tiles before row b
   __shared__ float s_m[NW][G], s_l[NW][G];
+  __shared__ __align__(8) uint64_t full_bar[kStages];
 
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, g = lane >> 2, t4 = lane & 3;
   const int64_t row_w = static_cast<int64_t>(H + 2 * Hkv) * D;
 
+  if (tid == 0) {
+    for (int st = 0; st < kStages; ++st) tc::mbar_init(full_bar + st, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
   griddep_launch();
   griddep_wait();                                 // qkv and lens come from the previous kernels
 
@@ -157,30 +167,35 @@ __global__ void __launch_bounds__(kThreads, 2)
       advance(c);
     }
   }
+  asm volatile("fence.proxy.async;" ::: "memory");   // the appended rows (generic proxy) before the TMA (async proxy) reads
   __syncthreads();
 
-  // ---- K/V tile loads ----
-  TileCtx<T, D> cx;
+  // ---- K/V tile loads: TMA, one mbarrier per stage, issued by thread 0 ----
+  using Ctx = TileCtx<T, D, true>;
+  Ctx cx;
   cx.init(tid);
   const uint32_t sK_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
   const uint32_t sV_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sV));
   auto load_unit = [&](int stage, const UnitCursor& c) {
-    const int nkeys = lens[c.b] + 1;
-    const int k0 = c.t * kTile;
-    const int64_t base = ((static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len + k0) * D;
-    cx.load(sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, k_cache + base,
-            v_cache + base, nkeys - k0);
+    const int row = static_cast<int>((static_cast<int64_t>(c.b) * Hkv + c.kvh) * max_len) + c.t * kTile;
+    tc::mbar_expect_tx(full_bar + stage, 2 * Ctx::kTileBytes);
+#pragma unroll
+    for (int h = 0; h < Ctx::kBoxes; ++h) {
+      tc::tma_load_2d(reinterpret_cast<uint8_t*>(sK) + stage * Ctx::kTileBytes + h * Ctx::kBoxBytes, &tm_k, full_bar + stage,
+                      h * 64, row, tc::kEvictFirst);
+      tc::tma_load_2d(reinterpret_cast<uint8_t*>(sV) + stage * Ctx::kTileBytes + h * Ctx::kBoxBytes, &tm_v, full_bar + stage,
+                      h * 64, row, tc::kEvictFirst);
+    }
   };
   UnitCursor lc = cursor_at(u0);                   // load cursor (runs kStages - 1 units ahead)
   int64_t lu = u0;
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
     if (lu < u1) {
-      load_unit(s, lc);
+      if (tid == 0) load_unit(s, lc);
       advance(lc);
       ++lu;
     }
-    asm volatile("cp.async.commit_group;\n" ::);
   }
 
   UnitCursor cc = cursor_at(u0);                   // compute cursor
@@ -225,12 +240,11 @@ __global__ void __launch_bounds__(kThreads, 2)
   int it = 0;
   for (int64_t u = u0; u < u1; ++u, ++it) {
     const int stage = it % kStages;
-    if (lu < u1) {
-      load_unit((it + kStages - 1) % kStages, lc);
+    if (lu < u1) {                                 // refills the stage consumed in iteration it - 1 (trailing __syncthreads)
+      if (tid == 0) load_unit((it + kStages - 1) % kStages, lc);
       advance(lc);
       ++lu;
     }
-    asm volatile("cp.async.commit_group;\n" ::);
     const int nkeys = lens[cc.b] + 1;
     const bool pair_end = cc.t == cc.tiles - 1;
     const bool prefetch_q = pair_end && u + 1 < u1;   // the next unit opens a new (row, head): fetch its queries now
@@ -253,11 +267,9 @@ __global__ void __launch_bounds__(kThreads, 2)
       seg_t0 = cc.t;
       seg_start = false;
     }
-    asm volatile("cp.async.wait_group %0;\n" ::"n"(kStages - 1));
-    __syncthreads();
-
-    tile_step<T, D, false>(cx, sK_u32 + stage * TileCtx<T, D>::kTileBytes, sV_u32 + stage * TileCtx<T, D>::kTileBytes, warp, lane,
-                    qf, acc, nkeys - cc.t * kTile);
+    tc::mbar_wait(full_bar + stage, (it / kStages) & 1);
+    tile_step<T, D, true>(cx, sK_u32 + stage * Ctx::kTileBytes, sV_u32 + stage * Ctx::kTileBytes, warp, lane, qf, acc,
+                          nkeys - cc.t * kTile);
     if (prefetch_q) q_store(s_q + (qb ^ 1) * G * D);   // read by the next iteration, after its __syncthreads
     __syncthreads();                               // the stage is free again (and may serve as scratch below)
 
@@ -342,13 +354,14 @@ __global__ void __launch_bounds__(kThreads, 2)
           asm volatile("st.release.gpu.global.f32 [%0], %1;" ::"l"(lf), "f"(ll) : "memory");
         }
       }
+      // the scratch was written through the generic proxy; the next iteration refills this stage through the async proxy
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
       __syncthreads();                             // scratch stage released before the next iteration refills it
       seg_start = true;
       if (pair_end) qb ^= 1;
     }
     advance(cc);
   }
-  asm volatile("cp.async.wait_group 0;\n" ::);
 }
 
 template <typename T, int D, int G>
@@ -357,7 +370,10 @@ void launch_persistent(const void* qkv, void* kc, void* vc, const float* sn, con
                        float* partials, int32_t* tickets, int sm_count, cudaStream_t st) {
   auto kernel = attention_decode_persistent_kernel<T, D, G>;
   const size_t smem = static_cast<size_t>(2 * kStages * kTile * D) * sizeof(T) + static_cast<size_t>(2 * G) * D * sizeof(float) +
-                      (static_cast<size_t>(batch) + 1) * sizeof(int);
+                      (static_cast<size_t>(batch) + 1) * sizeof(int) + 1024;
+  const int kind = std::is_same<T, __half>::value ? 1 : 2;
+  const CUtensorMap tmk = tc::make_operand_map(kc, batch * Hkv * max_len, D, 2, kind, kTile);
+  const CUtensorMap tmv = tc::make_operand_map(vc, batch * Hkv * max_len, D, 2, kind, kTile);
   static int occupancy = 0;                       // CTAs per SM: the grid must be fully co-resident (flag waits)
   if (occupancy == 0) {
     CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
@@ -367,7 +383,7 @@ void launch_persistent(const void* qkv, void* kc, void* vc, const float* sn, con
   }
   const int64_t max_units = batch * Hkv * ((max_len + kTile - 1) / kTile);
   const int64_t ctas = std::max<int64_t>(1, std::min<int64_t>(static_cast<int64_t>(occupancy) * sm_count, max_units));
-  launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kThreads), smem, st, static_cast<const T*>(qkv),
+  launch_pdl(kernel, dim3(static_cast<unsigned>(ctas)), dim3(kThreads), smem, st, tmk, tmv, static_cast<const T*>(qkv),
              static_cast<T*>(kc), static_cast<T*>(vc), sn, cs, lens, static_cast<int>(batch), H, Hkv, max_len, interleave,
              scale * 1.4426950408889634f, static_cast<T*>(out), partials, tickets);
   check_launch();

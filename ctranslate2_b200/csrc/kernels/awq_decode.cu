@@ -473,7 +473,11 @@ bool run_m(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, co
   return run<64, NB>(x, w, w2, m, p, st);
 }
 
-bool enabled() { return env_int("CT2B200_AWQ_DECODE", 1) != 0; }
+// Opt-in (CT2B200_AWQ_DECODE=1).  Measured on B200 (tools/awq_probe.py, Llama-3-8B shapes): the int4 -> fp16 transform,
+// not HBM, bounds both AWQ kernels (~1 TB/s of packed weights), and a transform-bound kernel wants perfectly even work:
+// the persistent stream-K kernel of awq.cu (148 CTAs x 20.7 blocks for QKV) beats one-tile-per-CTA plans (140 x 32),
+// so the deeper packed ring of this kernel buys nothing yet.  Kept as the vehicle for a cheaper transform.
+bool enabled() { return env_int("CT2B200_AWQ_DECODE", 0) != 0; }
 
 }  // namespace
 
