@@ -9,7 +9,7 @@
 //     ring (up to 24 blocks = 96 KB in flight per SM), decoupled from the shallow ring (4 stages) of dequantized fp16
 //     operand tiles (16 KB per block).  The first version staged both in one ring of 8 x 22 KB and never had more than
 //     32 KB of HBM traffic in flight per SM (8-22 % of the HBM peak).
-//   * 16 transform warps (4 per scheduler: the conversion is instruction-bound) turn nibbles into fp16 (q - z) * s (exact subtraction, one fp16 rounding: the arithmetic of the
+//   * 16 transform warps in 4 groups, each group converting its own K block (4 blocks in flight), turn nibbles into fp16 (q - z) * s (exact subtraction, one fp16 rounding: the arithmetic of the
 //     reference's dequantize_s4_to_fp16x2 + sub.f16x2 + fma.rn.f16x2) straight into the 128B-swizzled K-major UMMA
 //     operand layout; group scales / zeros are fetched one group ahead.
 //   * tcgen05.mma kind::f16, fp32 accumulators in TMEM; epilogue = gemm_decode_common.cuh (float arm).
@@ -28,10 +28,12 @@ using namespace tc;
 using namespace dec;
 
 constexpr int kThreads = 704;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-21 transform
-constexpr int kDeqWarps = 16;         // the int4 -> fp16 transform is the instruction-bound part: 4 warps per scheduler
+constexpr int kDeqWarps = 16;          // 4 transform groups of 4 warps; group g owns the K blocks it % 4 == g, so four
+constexpr int kGroups = 4;             // blocks are converted CONCURRENTLY: one block's LDS -> lop3/hfma -> STS -> fence chain is
+constexpr int kGroupWarps = kDeqWarps / kGroups;   // latency-bound (~1 k cycles measured), not issue-bound
 constexpr int kBKh = 64;               // fp16 channels per K block (one 128-byte swizzle atom)
 constexpr int kPacked = kTileM * kBKh / 2;      // 4096 bytes of nibbles per weight per block
-constexpr int kAStages = 4;
+constexpr int kAStages = kGroups;        // operand stage of block `it` is it % 4 = its transform group
 constexpr int kMaxP = 24;
 
 struct AwqDecParams {
@@ -90,10 +92,10 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < PD; ++s) {
       mbar_init(p_full + s, 1);
-      mbar_init(p_free + s, kDeqWarps + 1);
+      mbar_init(p_free + s, kGroupWarps + 1);
     }
     for (int s = 0; s < kAStages; ++s) {
-      mbar_init(a_ready + s, kDeqWarps);
+      mbar_init(a_ready + s, kGroupWarps);
       mbar_init(a_free + s, 1);
     }
     mbar_init(acc_bar, 1);
@@ -164,38 +166,28 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp >= 6) {
     // ===== transform warps: nibbles -> fp16 (q - z) * s into the swizzled operand tile =====
-    // thread -> (tile row, 16-channel quarter of the 64-channel block): the 4 threads of a row are adjacent lanes, so a
-    // warp reads 256 contiguous bytes of nibbles (8 rows x 32 B) and writes 32 distinct 16-byte chunks per store
+    // thread -> (transform group, tile row): a thread converts the 64 channels (8 packed words) of its row
     const int d = threadIdx.x - 192;                   // 0..511
-    const int r = d >> 2;                              // tile row of this thread
-    const int quarter = d & 3;
+    const int grp = d >> 7;
+    const int r = d & 127;
     const int64_t ng = ap.k / ap.group;
     const int64_t row = static_cast<int64_t>(a0) + r;
     const bool row_ok = r < p.tile_rows && row < p.n;
-    int64_t cur_g = -1;
     __half zc[NB], sc_[NB], zn[NB], sn_[NB];
-    auto fetch = [&](int64_t g, __half (&z)[NB], __half (&sc)[NB]) {
+    auto fetch = [&](int it, __half (&z)[NB], __half (&sc)[NB]) {
+      const int64_t g = (static_cast<int64_t>(kb_lo + it) * kBKh) / ap.group;
 #pragma unroll
       for (int w = 0; w < NB; ++w) {
-        const bool ok = row_ok && g < ng;
+        const bool ok = row_ok && it < nkb && g < ng;
         z[w] = ok ? ap.zr[w][row * ng + g] : __float2half(0.f);
         sc[w] = ok ? ap.sc[w][row * ng + g] : __float2half(0.f);
       }
     };
+    fetch(grp, zc, sc_);
 #pragma unroll 1
-    for (int it = 0; it < nkb; ++it) {
+    for (int it = grp; it < nkb; it += kGroups) {
       const int sp = it % PD, sa = it % kAStages;
-      const int64_t g = (static_cast<int64_t>(kb_lo + it) * kBKh) / ap.group;
-      if (g != cur_g) {
-        if (g == cur_g + 1 && cur_g >= 0) {
-#pragma unroll
-          for (int w = 0; w < NB; ++w) { zc[w] = zn[w]; sc_[w] = sn_[w]; }
-        } else {
-          fetch(g, zc, sc_);
-        }
-        fetch(g + 1, zn, sn_);                         // next group of this row, off the critical path
-        cur_g = g;
-      }
+      fetch(it + kGroups, zn, sn_);                    // scales of this thread's next block, off the critical path
       mbar_wait(p_full + sp, (it / PD) & 1);
       if (it >= kAStages) mbar_wait(a_free + sa, ((it / kAStages) & 1) ^ 1);
       const uint8_t* pk = p_ring + static_cast<size_t>(sp) * S::kP;
@@ -205,14 +197,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         const __half2 zb = __half2half2(__hadd(__float2half(1024.f), zc[w]));
         const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), zc[w])));
         const __half2 s2 = __half2half2(sc_[w]);
-        const uint2 wv = *reinterpret_cast<const uint2*>(pk + w * kPacked + r * (kBKh / 2) + quarter * 8);
-        const uint32_t words[2] = {wv.x, wv.y};
+        const uint4 w0 = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2));
+        const uint4 w1 = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2) + 16);
+        const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
         uint8_t* arow = at + w * kTileM * kSwizzleBytes + r * kSwizzleBytes;
 #pragma unroll
-        for (int c = 0; c < 2; ++c) {                  // chunk cc of the row lives at chunk cc ^ (r & 7) under SWIZZLE_128B
-          const int cc = quarter * 2 + c;
-          *reinterpret_cast<uint4*>(arow + ((cc ^ (r & 7)) << 4)) = awq_dequant_word(words[c], zb, zt, s2);
-        }
+        for (int c = 0; c < 8; ++c)                    // chunk c of the row lives at chunk c ^ (r & 7) under SWIZZLE_128B
+          *reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4)) = awq_dequant_word(words[c], zb, zt, s2);
       }
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
       __syncwarp();
@@ -220,6 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(a_ready + sa);
         mbar_arrive(p_free + sp);
       }
+#pragma unroll
+      for (int w = 0; w < NB; ++w) { zc[w] = zn[w]; sc_[w] = sn_[w]; }
     }
   } else {
     // ===== epilogue warps (2..5): thread = output channel =====
@@ -388,10 +381,13 @@ AwqPlan plan_awq(int64_t n, int kb_total, int sm_count) {
       case 3: maxc = clusters_for<BN, NB, 3>(ps, sm_count); break;
       default: maxc = clusters_for<BN, NB, 4>(ps, sm_count); break;
     }
-    for (int rows = force_rows ? force_rows : 128; rows >= (force_rows ? force_rows : 64); rows -= 8) {
+    // the transform converts all 128 rows of a block whatever the tile height, so only full-height tiles make sense
+    // (a pinned CT2B200_GEMM_ROWS is honoured for the tests); cost = K blocks per CTA (+ the cluster exchange)
+    {
+      const int rows = force_rows ? force_rows : 128;
       const int tiles = static_cast<int>((n + rows - 1) / rows);
       if (tiles > maxc) continue;
-      const double cost = static_cast<double>(rows) * NB * nkb * (kBKh / 2) + (cs > 1 ? 24.0 * 1024 : 0.0) + (128 - rows) * 8.0;
+      const double cost = static_cast<double>(nkb) + (cs > 1 ? 3.0 : 0.0);
       if (cost < best_cost) {
         best_cost = cost;
         best.cs = cs;
