@@ -1,0 +1,40 @@
+"""bench.py contract, CPU side: the reference arm (`--impl reference`) runs the unmodified reference build under
+oracle/_ref on the host cores and prints ONE JSON line with the keys the driver reads.  (The CUDA arm needs a GPU and is
+exercised by the driver; its line carries the same keys plus roofline / clocks / gpu_launches.)"""
+import json
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from oracle import refapi  # noqa: E402
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref not built")
+@pytest.mark.timeout(300)
+def test_reference_arm_prints_the_contract_line(tmp_path):
+    env = dict(os.environ, CT2B200_BENCH_DIR=str(tmp_path))
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--model", "tiny", "--batch", "4",
+                        "--steps", "2", "--warmup", "1"], capture_output=True, text=True, env=env, timeout=280)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "generate_batch tokens/sec" and d["unit"] == "tokens/s"
+    for key in ("value", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "cpu_baseline", "e2e"):
+        assert key in d, key
+    assert d["higher_is_better"] is True and d["value"] > 0 and "workload" in d["config"]
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["sample"]
+    assert d["e2e"] == {"value": d["value"], "unit": "tokens/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+
+
+def test_step_bytes_matches_survey_figures():
+    """Llama-3-8B INT8 streams 7,504,658,432 weight bytes per decode step + 131,072 B of KV per cached token."""
+    import bench
+    w = bench.step_bytes("8b", 0, 0)
+    assert abs(w - (7504658432 + 4 * (32 * (6144 + 4096 + 2 * 14336 + 4096) + 128256))) == 0
+    assert bench.step_bytes("8b", 1, 1) - w == 131072
