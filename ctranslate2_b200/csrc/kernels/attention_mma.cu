@@ -290,19 +290,6 @@ __global__ void __launch_bounds__(kThreads, 2)
   const int s1 = min(nkeys, s0 + per);
   const int ntiles = s1 > s0 ? (s1 - s0 + kDecTile - 1) / kDecTile : 0;
 
-  for (int e = tid; e < G * D; e += kThreads) {
-    const int h = e / D, i = e % D;
-    s_q[e] = rope_at_mma(q_in + h * D, sn, cs, i, D, interleave) * scale_log2;
-  }
-  if (pos >= s0 && pos < s1) {                                  // the owner of position `pos` appends k_new / v_new
-    for (int i = tid; i < D; i += kThreads) {
-      kc[static_cast<int64_t>(pos) * D + i] = from_f32<T>(rope_at_mma(k_in, sn, cs, i, D, interleave));
-      vc[static_cast<int64_t>(pos) * D + i] = v_in[i];
-    }
-    asm volatile("fence.proxy.async;" ::: "memory");            // generic-proxy stores before the TMA (async proxy) reads
-  }
-  __syncthreads();
-
   Ctx cx;
   cx.init(tid);
   const uint32_t sK_u32 = static_cast<uint32_t>(__cvta_generic_to_shared(sK));
@@ -319,11 +306,30 @@ __global__ void __launch_bounds__(kThreads, 2)
                       h * 64, row0 + kt * kDecTile, tc::kEvictFirst);
     }
   };
+  // The first tiles are requested right away, so the loads fly while the queries are rotated — except the tile that
+  // contains position `pos`: it is loaded after the new token's K/V have been appended below.
+  const bool owner = pos >= s0 && pos < s1;                     // this slice holds position `pos`
+  const int kt_pos = owner ? (pos - s0) / kDecTile : -1;
+  __syncthreads();                                              // mbarrier inits (thread 0) before anyone may wait on them
   if (tid == 0) {
 #pragma unroll
     for (int st = 0; st < kDecStages - 1; ++st)
-      if (st < ntiles) load_tile(st, st);
+      if (st < ntiles && st != kt_pos) load_tile(st, st);
   }
+
+  for (int e = tid; e < G * D; e += kThreads) {
+    const int h = e / D, i = e % D;
+    s_q[e] = rope_at_mma(q_in + h * D, sn, cs, i, D, interleave) * scale_log2;
+  }
+  if (owner) {                                                  // the owner of position `pos` appends k_new / v_new
+    for (int i = tid; i < D; i += kThreads) {
+      kc[static_cast<int64_t>(pos) * D + i] = from_f32<T>(rope_at_mma(k_in, sn, cs, i, D, interleave));
+      vc[static_cast<int64_t>(pos) * D + i] = v_in[i];
+    }
+    asm volatile("fence.proxy.async;" ::: "memory");            // generic-proxy stores before the TMA (async proxy) reads
+  }
+  __syncthreads();
+  if (tid == 0 && kt_pos >= 0 && kt_pos < kDecStages - 1) load_tile(kt_pos, kt_pos);
 
   // Q as A fragments: rows 0..G-1 = heads, rows G..15 = 0
   uint32_t qf[D / 16][2];
