@@ -254,13 +254,14 @@ std::pair<int64_t, int64_t> shard_range(int64_t total, int rank, int world) {
 
 void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w, Shard shard) {
   const HostVariable& wt = f.get(prefix + "/weight");
-  if (tp_.world > 1 && shard != REPLICATED) {
+  const bool awq_weight = wt.type_id == 3 && f.find(prefix + "/weight_zero") != nullptr;
+  if (tp_.world > 1 && shard != REPLICATED && !awq_weight) {
     // Tensor-parallel partition (model.cc:662-743): column-parallel layers keep a slice of the output channels
     // (for the fused QKV: this rank's query heads, key heads and value heads), row-parallel layers a slice of K.
     // The int8 values and the per-channel scales are those of the unsharded matrix (the scale of a row-parallel
     // weight still spans the whole row), so the shards reproduce the single-GPU arithmetic exactly.
     CT2_REQUIRE(wt.type_id == 1 || wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5,
-                "tensor parallel supports INT8 and float16/bfloat16 weights (AWQ shards are not implemented)");
+                "unsupported weight type for a tensor-parallel shard");
     CT2_REQUIRE(wt.shape.size() == 2, "weight must be a matrix");
     const int64_t N = wt.shape[0], K = wt.shape[1];
     const bool int8 = wt.type_id == 1;
@@ -378,11 +379,58 @@ void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, Den
     awq_repack(qw.as<int32_t>(), qs.ptr, qz.as<int32_t>(), layout, w.group_size, w.n, w.k, w.weight.as<int32_t>(),
                w.scale.ptr, w.zeros.ptr, stream_);
     CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    if (tp_.world > 1 && shard != REPLICATED) {
+      // Tensor-parallel shard, cut from the repacked (channel-major) tensors: output channels are rows of wp / sc / zr,
+      // input channels are columns (8 per packed word, `group` per scale / zero) — model.cc:662-743
+      const int64_t N = w.n, K = w.k, G = w.group_size, ng = K / G;
+      std::vector<std::pair<int64_t, int64_t>> row_ranges;
+      int64_t k0 = 0, k1 = K;
+      if (shard == ROWS) {
+        row_ranges.push_back(shard_range(N, tp_.rank, tp_.world));
+      } else if (shard == QKV_ROWS) {
+        const int64_t D = mc_.head_dim, hq = static_cast<int64_t>(mc_.num_heads) * D, hk = static_cast<int64_t>(mc_.num_heads_kv) * D;
+        CT2_REQUIRE(N == hq + 2 * hk, "fused QKV weight has an unexpected number of rows");
+        const auto q = shard_range(mc_.num_heads, tp_.rank, tp_.world), kv = shard_range(mc_.num_heads_kv, tp_.rank, tp_.world);
+        row_ranges.push_back({q.first * D, q.second * D});
+        row_ranges.push_back({hq + kv.first * D, hq + kv.second * D});
+        row_ranges.push_back({hq + hk + kv.first * D, hq + hk + kv.second * D});
+      } else {
+        row_ranges.push_back({0, N});
+        std::tie(k0, k1) = shard_range(K, tp_.rank, tp_.world);
+        CT2_REQUIRE(k0 % G == 0 && k1 % G == 0, "tensor parallel: the AWQ group size must divide the K slice");
+      }
+      int64_t n_local = 0;
+      for (auto& rr : row_ranges) n_local += rr.second - rr.first;
+      const int64_t k_local = k1 - k0, ng_local = k_local / G;
+      DeviceBuffer nw(static_cast<size_t>(n_local) * (k_local / 8) * 4), ns(static_cast<size_t>(n_local) * ng_local * 2),
+          nz(static_cast<size_t>(n_local) * ng_local * 2);
+      int64_t o = 0;
+      for (auto& rr : row_ranges) {
+        const int64_t rows_ = rr.second - rr.first;
+        CT2_CUDA_CHECK(cudaMemcpy2DAsync(nw.as<uint8_t>() + o * (k_local / 8) * 4, (k_local / 8) * 4,
+                                         w.weight.as<uint8_t>() + (rr.first * (K / 8) + k0 / 8) * 4, (K / 8) * 4,
+                                         (k_local / 8) * 4, rows_, cudaMemcpyDeviceToDevice, stream_));
+        CT2_CUDA_CHECK(cudaMemcpy2DAsync(ns.as<uint8_t>() + o * ng_local * 2, ng_local * 2,
+                                         w.scale.as<uint8_t>() + (rr.first * ng + k0 / G) * 2, ng * 2, ng_local * 2, rows_,
+                                         cudaMemcpyDeviceToDevice, stream_));
+        CT2_CUDA_CHECK(cudaMemcpy2DAsync(nz.as<uint8_t>() + o * ng_local * 2, ng_local * 2,
+                                         w.zeros.as<uint8_t>() + (rr.first * ng + k0 / G) * 2, ng * 2, ng_local * 2, rows_,
+                                         cudaMemcpyDeviceToDevice, stream_));
+        o += rows_;
+      }
+      CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      w.weight = std::move(nw);
+      w.scale = std::move(ns);
+      w.zeros = std::move(nz);
+      w.n = n_local;
+      w.k = k_local;
+    }
     mc_.weight_bytes += w.weight.bytes + w.scale.bytes + w.zeros.bytes;
   } else {
     throw std::runtime_error("unsupported weight type for " + prefix);
   }
   if (const HostVariable* b = f.find(prefix + "/bias")) {
+    CT2_REQUIRE(!(tp_.world > 1 && shard != REPLICATED), "tensor parallel: biased AWQ layers are not sharded");
     const auto bytes = convert_to_dtype(*b, dtype_);
     upload(w.bias, bytes.data(), bytes.size());
   }
@@ -533,8 +581,6 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   CT2_CUDA_CHECK(cudaMemset(attn_ws_.ptr, 0, attn_ws_.bytes));
   if (tp_.world > 1) {
     // exchange buffer of this rank: [flags 2x8 u32 | pad to 256] [amax words 2 x 8 x R] [partials 2 x R x d_model]
-    CT2_REQUIRE(layers_[0].qkv.kind != DenseWeights::AWQ_GEMM && layers_[0].qkv.kind != DenseWeights::AWQ_GEMV,
-                "tensor parallel: AWQ models are not sharded yet");
     tp_.flags_off = 0;
     tp_.amax_off = 256;
     const size_t amax_bytes = static_cast<size_t>(2) * 8 * R * sizeof(unsigned long long);

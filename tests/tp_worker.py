@@ -26,7 +26,8 @@ def main():
     dist.init_process_group("gloo")                      # host-side rendezvous only: the data path is peer memory
     out = {}
     base = os.path.join(tempfile.gettempdir(), "ct2b200_tp_models")
-    for quant, ctype, tol in (("int8_float16", "int8_float16", 6e-2), ("float16", "float16", 2e-2)):
+    for quant, ctype, tol in (("int8_float16", "int8_float16", 6e-2), ("float16", "float16", 2e-2),
+                             ("awq_gemm", "float16", 2e-2)):
         d = os.path.join(base, quant)
         if rank == 0 and not os.path.exists(os.path.join(d, ".complete")):
             cfg = LlamaConfig(num_layers=3, num_heads=8, num_heads_kv=4, head_dim=128, ffn_dim=2048, vocab_size=2000)
