@@ -469,11 +469,12 @@ bool run_m(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, co
   return run<64, NB>(x, w, w2, m, p, st);
 }
 
-// Opt-in (CT2B200_AWQ_DECODE=1).  Measured on B200 (tools/awq_probe.py, Llama-3-8B shapes): the int4 -> fp16 transform,
-// not HBM, bounds both AWQ kernels (~1 TB/s of packed weights), and a transform-bound kernel wants perfectly even work:
-// the persistent stream-K kernel of awq.cu (148 CTAs x 20.7 blocks for QKV) beats one-tile-per-CTA plans (140 x 32),
-// so the deeper packed ring of this kernel buys nothing yet.  Kept as the vehicle for a cheaper transform.
-bool enabled() { return env_int("CT2B200_AWQ_DECODE", 0) != 0; }
+// CT2B200_AWQ_DECODE=0 falls back to the general stream-K kernel of awq.cu (CT2B200_AWQ_DECODE_GLU does the same for the
+// fused gate/up launch only).  Measured in the decode graph of a Llama-3-8B AWQ model (tools/decode_once.py, B200): with the
+// four concurrent transform groups this kernel takes 3.93 ms / step at bsz 1 and 4.84 ms at bsz 32, the general kernel
+// 4.04 / 6.0 ms.  Both are bound by the int4 -> fp16 transform (~1 TB/s of packed weights), not by HBM.
+bool enabled() { return env_int("CT2B200_AWQ_DECODE", 1) != 0; }
+bool glu_enabled() { return env_int("CT2B200_AWQ_DECODE_GLU", env_int("CT2B200_AWQ_DECODE", 1)) != 0; }
 
 }  // namespace
 
@@ -491,7 +492,7 @@ bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const
 }
 
 bool dense_awq_glu_decode(const void* x, const AwqNative& wg, const AwqNative& wu, int act, int64_t m, void* h, cudaStream_t st) {
-  if (!enabled() || m < 1 || m > 64 || wg.group % kBKh != 0 || wg.k % kBKh != 0 || wg.group != wu.group) return false;
+  if (!glu_enabled() || m < 1 || m > 64 || wg.group % kBKh != 0 || wg.k % kBKh != 0 || wg.group != wu.group) return false;
   AwqDecParams p{};
   p.d.y = h;
   p.d.act = act;
