@@ -2,13 +2,14 @@
 // (reference src/layers/attention.cc:485-602: Split -> [replicate_heads] -> Rotary -> Concat(cache) ->
 // MatMul/SoftMax/MatMul), re-designed around an UN-replicated, preallocated GQA cache
 // [slot, Hkv, max_len, D]: nothing is copied or tiled per step, K/V are appended in place.
-//
-//  * attention_decode_kernel: one new token per sequence.  Split-KV "flash decoding": grid =
-//    (splits, Hkv, batch); a CTA serves the G = H/Hkv query heads of one KV head over a slice of the
-//    keys with 16-byte coalesced cache reads, fp32 online softmax, and the last CTA of a (batch, kv-head)
-//    (atomic ticket) merges the partials.  Rotary of q and of the new k, and the K/V append, happen in the
-//    same kernel (the CTA whose slice contains position lens[b] appends).
-//  * rope_append_kernel + attention_prefill_kernel: T new tokens, causal.
+// This file holds the launch policy and the SIMT kernels that cover every shape / dtype (fp32 activations, head_dim 32,
+// ragged prefill); fp16 / bf16 with head_dim 64 / 128 go to the tensor-core kernels:
+//   decode:  attention_mma.cu (split-KV grid, TMA-staged tiles) or attention_decode.cu (persistent, work-balanced);
+//   prefill: attention_mma.cu (causal flash attention on mma.sync) after rope_append_kernel (here).
+//  * attention_decode_kernel: SIMT split-KV "flash decoding": grid = (splits, Hkv, batch); a CTA serves the G = H/Hkv
+//    query heads of one KV head over a slice of the keys, fp32 online softmax, ticketed combine; rotary of q and of the
+//    new k, and the K/V append, happen in the same kernel.
+//  * rope_append_kernel + attention_prefill_simple_kernel: T new tokens, causal.
 #include <cstdlib>
 #include <algorithm>
 

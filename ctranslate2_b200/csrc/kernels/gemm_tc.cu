@@ -1,13 +1,12 @@
-// gemm_tc.cu — sm_100a tensor-core GEMMs: tcgen05.mma (kind::i8 / kind::f16) with TMA-staged,
-// 128B-swizzled operand tiles in shared memory, accumulators in TMEM, and the fused Dense epilogue
-// read back with tcgen05.ld.  One kernel template serves
-//   * decode (m <= 64, weight-streaming, HBM-bound): "swap-AB" — the weight tile [128 x K] is the
-//     UMMA M-side operand and the quantized activations [m x K] the N-side operand, so a 128-row UMMA
-//     is fully used by 128 output channels and the tiny batch rides in the N dimension; split-K across
-//     CTAs keeps all 148 SMs streaming weights;
-//   * prefill (m large, tensor-bound): activations on the M side, weights on the N side (BN up to 256).
-// Optional second weight matrix = SwiGLU gate/up fusion (two accumulators, one pass over x).
-//
+// gemm_tc.cu — the GENERAL tcgen05 GEMM (first tensor-core kernel of this repo, now the fallback of the two
+// specialised ones): tcgen05.mma (kind::i8 / kind::f16) with TMA-staged, 128B-swizzled operand tiles in shared
+// memory, accumulators in TMEM, fused Dense epilogue read back with tcgen05.ld.
+//   * gemm_s8_tc / gemm_s8_glu_tc / gemm_f16_tc first try gemm_decode.cu (m <= 64, one tile per CTA, cluster/DSMEM
+//     split-K) and gemm_prefill.cu (m > 64, double-buffered TMEM, 8 epilogue warps) and only land here for what those
+//     do not cover: raw int32 output (ops::Gemm), N tiles beyond one wave at m <= 64 (the 128256-row lm_head),
+//     unaligned rows.
+//   * persistent stream-K over (tile, K block) units, "swap-AB" for m <= 64, cluster / partition / whole-tile modes,
+//     deterministic slot-based reduction of shared tiles (no float atomics).
 // Replaces cublasGemmEx s8/f16/bf16 (reference src/cuda/primitives.cu:485-597) + Dequantize epilogue
 // (src/ops/dequantize_gpu.cu:30-121) + ops::Add/ops::Mul (src/layers/common.cc:392-401, transformer.cc:31-37).
 //
