@@ -315,6 +315,27 @@ CT2B200_API int ct2b200_generate_batch(ct2b200_generator* g, const int32_t* prom
   });
 }
 
+CT2B200_API int ct2b200_generate_batch_scores(ct2b200_generator* g, const int32_t* prompt_ids, const int32_t* prompt_lens,
+                                              int64_t batch, int64_t max_prompt_len, int64_t max_length, int64_t min_length,
+                                              const int32_t* end_ids, int num_end_ids, int return_end_token,
+                                              float length_penalty, int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  return guarded([&] {
+    CT2_REQUIRE(g && prompt_ids && prompt_lens && out_ids && out_lens && out_scores, "generate_batch_scores: null argument");
+    GenerationRequest r;
+    r.prompt_ids = prompt_ids;
+    r.prompt_lens = prompt_lens;
+    r.batch = batch;
+    r.max_prompt_len = max_prompt_len;
+    r.max_length = max_length;
+    r.min_length = min_length;
+    r.end_ids.assign(end_ids, end_ids + (end_ids ? num_end_ids : 0));
+    r.return_end_token = return_end_token != 0;
+    r.return_scores = true;
+    r.length_penalty = length_penalty;
+    g->impl->generate(r, out_ids, out_lens, out_scores);
+  });
+}
+
 CT2B200_API int ct2b200_forward_batch(ct2b200_generator* g, const int32_t* ids, int64_t batch, int64_t time, int return_log_probs,
                           float* logits) {
   return guarded([&] {

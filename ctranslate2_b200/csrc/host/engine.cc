@@ -854,7 +854,8 @@ Generator::Generator(const std::string& model_dir, const ct2b200_generator_confi
   forced_d_.alloc(B * L * sizeof(int32_t));
   out_d_.alloc(B * L * sizeof(int32_t));
   end_ids_d_.alloc(64 * sizeof(int32_t));
-  sample_ws_.alloc((B * 65) * sizeof(int32_t));      // part_v [B*32] | part_i [B*32] | tickets [B]
+  sample_ws_.alloc((B * 97) * sizeof(int32_t));      // part_v [B*32] | part_i [B*32] | tickets [B] | part_s [B*32]
+  scores_d_.alloc(B * L * sizeof(float));             // per-step log-probabilities (return_scores)
   CT2_CUDA_CHECK(cudaMemset(sample_ws_.ptr, 0, sample_ws_.bytes));
   prompt_d_.alloc(B * L * sizeof(int32_t));
   host_pinned_elems_ = static_cast<size_t>(B) * L + 64;
@@ -885,11 +886,12 @@ void Generator::launch_step(int64_t batch, int64_t, int) {
   launch_sample_greedy(d.logits_buffer(), batch, d.config().vocab, step_d_.as<int32_t>(), end_ids_d_.as<int32_t>(),
                        forced_d_.as<int32_t>(), ids_d_.as<int32_t>(), out_d_.as<int32_t>(), lens_d_.as<int32_t>(),
                        sample_ws_.as<float>(), sample_ws_.as<int32_t>() + d.max_batch() * 32,
-                       sample_ws_.as<int32_t>() + d.max_batch() * 64, d.dtype(), d.stream());
+                       sample_ws_.as<int32_t>() + d.max_batch() * 64, sample_ws_.as<float>() + d.max_batch() * 65,
+                       want_scores_ ? scores_d_.as<float>() : nullptr, d.dtype(), d.stream());
 }
 
 void Generator::build_step_graph(int64_t batch, int64_t min_length, int num_end_ids) {
-  if (graph_ && graph_batch_ == batch) return;
+  if (graph_ && graph_batch_ == batch && graph_scores_ == want_scores_) return;
   if (graph_) {
     cudaGraphExecDestroy(graph_);
     graph_ = nullptr;
@@ -914,9 +916,11 @@ void Generator::build_step_graph(int64_t batch, int64_t min_length, int num_end_
   CT2_CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
   cudaGraphDestroy(g);
   graph_batch_ = batch;
+  graph_scores_ = want_scores_;
 }
 
-void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* out_lens) {
+void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  want_scores_ = r.return_scores && out_scores != nullptr;
   LlamaDecoder& d = *decoder_;
   cudaStream_t st = d.stream();
   const int64_t B = r.batch;
@@ -971,6 +975,9 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
 
   // ---- GreedySearch::search host loop (decoding.cc:844-971) ----
   std::vector<std::vector<int32_t>> results(B);
+  std::vector<double> score_sum(B, 0.0);
+  std::vector<float> hscores;
+  if (want_scores_) hscores.resize(static_cast<size_t>(total_steps) * B);
   std::vector<char> finished(B, 0);
   int64_t num_finished = 0;
   const int64_t check_every = r.end_ids.empty() ? total_steps : 1;
@@ -979,6 +986,9 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   auto consume = [&](int64_t upto) {   // host bookkeeping for steps [copied, upto)
     CT2_CUDA_CHECK(cudaMemcpyAsync(hout + copied * B, out_d_.as<int32_t>() + copied * B,
                                    (upto - copied) * B * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    if (want_scores_)
+      CT2_CUDA_CHECK(cudaMemcpyAsync(hscores.data() + copied * B, scores_d_.as<float>() + copied * B,
+                                     (upto - copied) * B * sizeof(float), cudaMemcpyDeviceToHost, st));
     CT2_CUDA_CHECK(cudaStreamSynchronize(st));
     for (int64_t s = copied; s < upto; ++s) {
       for (int64_t b = 0; b < B; ++b) {
@@ -987,6 +997,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
         // prompt of row b is exhausted, i.e. fwd+s >= prompt_len-1
         if (fwd + s < r.prompt_lens[b] - 1) continue;
         const int32_t tok = hout[s * B + b];
+        if (want_scores_) score_sum[b] += hscores[s * B + b];      // the end token's log-probability counts too
         const bool is_end = std::find(r.end_ids.begin(), r.end_ids.end(), tok) != r.end_ids.end();
         if (is_end) {
           if (r.return_end_token) results[b].push_back(tok);
@@ -1013,6 +1024,11 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
     if ((s + 1) % check_every == 0 || s + 1 == total_steps) consume(s + 1);
   }
   for (int64_t b = 0; b < B; ++b) {
+    if (want_scores_) {
+      // finalize_hypothesis_score (decoding.cc:189-203); an empty hypothesis keeps the raw sum (reference behaviour)
+      const double len = static_cast<double>(results[b].size());
+      out_scores[b] = static_cast<float>(len > 0 ? score_sum[b] / std::pow(len, static_cast<double>(r.length_penalty)) : score_sum[b]);
+    }
     out_lens[b] = static_cast<int32_t>(results[b].size());
     for (int64_t t = 0; t < r.max_length; ++t)
       out_ids[b * r.max_length + t] = t < static_cast<int64_t>(results[b].size()) ? results[b][t] : -1;

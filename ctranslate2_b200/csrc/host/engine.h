@@ -182,6 +182,8 @@ struct GenerationRequest {
   int64_t batch = 0, max_prompt_len = 0, max_length = 0, min_length = 0;
   std::vector<int32_t> end_ids;
   bool return_end_token = false;
+  bool return_scores = false;              // GenerationOptions::return_scores
+  float length_penalty = 1.f;              // score / length^length_penalty (decoding.cc:189-203)
 };
 
 class Generator {
@@ -190,7 +192,7 @@ class Generator {
   ~Generator();
   LlamaDecoder& decoder() { return *decoder_; }
   // Generator::generate_batch (greedy): fills out_ids [batch, max_length] (-1 padded) and out_lens.
-  void generate(const GenerationRequest& req, int32_t* out_ids, int32_t* out_lens);
+  void generate(const GenerationRequest& req, int32_t* out_ids, int32_t* out_lens, float* out_scores = nullptr);
   // Generator::forward_batch
   void forward(const int32_t* ids_h, int64_t batch, int64_t time, bool log_probs, float* logits_h);
   void bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, int64_t warmup, float* prefill_ms,
@@ -204,7 +206,9 @@ class Generator {
   ct2b200_generator_config cfg_;
   std::unique_ptr<LlamaDecoder> decoder_;
   // decode-loop device state
-  DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_, sample_ws_;
+  DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_, sample_ws_, scores_d_;
+  bool want_scores_ = false;               // the step (and its CUDA graph) also writes per-step log-probabilities
+  bool graph_scores_ = false;
   int32_t* host_pinned_ = nullptr;
   size_t host_pinned_elems_ = 0;
   cudaGraphExec_t graph_ = nullptr;

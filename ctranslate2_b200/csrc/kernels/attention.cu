@@ -253,6 +253,66 @@ __global__ void rope_append_kernel(T* __restrict__ qkv, T* __restrict__ k_cache,
   }
 }
 
+// Same operation, one CTA per TOKEN ROW with 16-byte accesses (the per-head grid above launches H+2Hkv tiny blocks per
+// token: 393 k blocks of 64 threads for a 32 x 256-token chunk of Llama-3-8B, i.e. scheduling-bound).  A task is one
+// 16-byte vector of a q/k head together with its rotation partner (non-interleaved: the vector half a head away;
+// interleaved: the pairs sit inside the vector), or one vector of a v head (plain copy).  Same fp32 math and the same
+// single rounding as rope_at, so the results are bit-identical.
+template <typename T>
+__global__ void __launch_bounds__(256)
+    rope_append_rows_kernel(T* __restrict__ qkv, T* __restrict__ k_cache, T* __restrict__ v_cache,
+                            const float* __restrict__ sin_t, const float* __restrict__ cos_t,
+                            const int32_t* __restrict__ lengths, int64_t time, int64_t offset, int H, int Hkv, int D,
+                            int64_t max_len, bool interleave) {
+  constexpr int N = Vec16<T>::N;
+  const int64_t t = blockIdx.x, b = blockIdx.y;
+  if (lengths && t >= lengths[b]) return;
+  const int64_t row_w = static_cast<int64_t>(H + 2 * Hkv) * D;
+  T* row = qkv + (b * time + t) * row_w;
+  const int64_t pos = offset + t;
+  const float* sn = sin_t + pos * D;
+  const float* cs = cos_t + pos * D;
+  const int half = D / 2;
+  const int vec_per_task = interleave ? 1 : 2;
+  const int tasks_per_head = D / (N * vec_per_task);
+  const int rot_tasks = (H + Hkv) * tasks_per_head;
+  const int copy_tasks = Hkv * (D / N);
+  for (int task = threadIdx.x; task < rot_tasks + copy_tasks; task += blockDim.x) {
+    if (task >= rot_tasks) {                         // v head: copy into the cache
+      const int c = task - rot_tasks;
+      const int hv = c / (D / N), i0 = (c % (D / N)) * N;
+      const Vec16<T> v = ld16(row + static_cast<int64_t>(H + Hkv + hv) * D + i0);
+      st16(v_cache + ((b * Hkv + hv) * max_len + pos) * D + i0, v);
+      continue;
+    }
+    const int head = task / tasks_per_head, i0 = (task % tasks_per_head) * N;
+    T* x = row + static_cast<int64_t>(head) * D;
+    T* dst = head < H ? x : k_cache + ((b * Hkv + (head - H)) * max_len + pos) * D;
+    if (interleave) {
+      const Vec16<T> v = ld16(x + i0);
+      Vec16<T> o;
+#pragma unroll
+      for (int j = 0; j < N; j += 2) {
+        const float a = to_f32(v.v[j]), c = to_f32(v.v[j + 1]);
+        o.v[j] = from_f32<T>(a * cs[i0 + j] + (-c) * sn[i0 + j]);
+        o.v[j + 1] = from_f32<T>(c * cs[i0 + j + 1] + a * sn[i0 + j + 1]);
+      }
+      st16(dst + i0, o);
+    } else {
+      const Vec16<T> lo = ld16(x + i0), hi = ld16(x + i0 + half);
+      Vec16<T> olo, ohi;
+#pragma unroll
+      for (int j = 0; j < N; ++j) {
+        const float a = to_f32(lo.v[j]), c = to_f32(hi.v[j]);
+        olo.v[j] = from_f32<T>(a * cs[i0 + j] + (-c) * sn[i0 + j]);
+        ohi.v[j] = from_f32<T>(c * cs[i0 + half + j] + a * sn[i0 + half + j]);
+      }
+      st16(dst + i0, olo);
+      st16(dst + i0 + half, ohi);
+    }
+  }
+}
+
 // ---- prefill attention, generic SIMT version: one warp per (batch, head, query) row ----
 // (kept as the dtype-generic reference path; the tensor-core kernel in attention_mma.cu is the fast one)
 template <typename T, int D>
@@ -415,6 +475,17 @@ void launch_rope_append(void* qkv, void* kc, void* vc, const float* sn, const fl
                         int64_t batch, int64_t time, int64_t offset, int H, int Hkv, int D, int64_t max_len,
                         bool interleave, int dtype, cudaStream_t st) {
   if (batch * time == 0) return;
+  const int vecn = dtype == CT2B200_F32 ? 4 : 8;
+  const bool aligned = (reinterpret_cast<uintptr_t>(qkv) & 15) == 0 && (reinterpret_cast<uintptr_t>(kc) & 15) == 0 &&
+                       (reinterpret_cast<uintptr_t>(vc) & 15) == 0;
+  if (aligned && D % (2 * vecn) == 0 && time <= 2147483647 && batch <= 65535) {
+    dim3 grid_rows(static_cast<unsigned>(time), static_cast<unsigned>(batch));
+    CT2_DISPATCH_DTYPE(dtype, (rope_append_rows_kernel<T><<<grid_rows, 256, 0, st>>>(
+                                  static_cast<T*>(qkv), static_cast<T*>(kc), static_cast<T*>(vc), sn, cs, lengths,
+                                  time, offset, H, Hkv, D, max_len, interleave)));
+    check_launch();
+    return;
+  }
   dim3 grid(H + 2 * Hkv, static_cast<unsigned>(time), static_cast<unsigned>(batch));
   CT2_DISPATCH_DTYPE(dtype, (rope_append_kernel<T><<<grid, 64, D * sizeof(float), st>>>(
                                 static_cast<T*>(qkv), static_cast<T*>(kc), static_cast<T*>(vc), sn, cs, lengths,

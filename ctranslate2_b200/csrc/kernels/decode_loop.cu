@@ -21,12 +21,16 @@ __device__ __forceinline__ void argmax_merge(float& bv, int32_t& bi, float v, in
   if (v > bv || (v == bv && i < bi)) { bv = v; bi = i; }
 }
 
-template <typename T>
+// kScores: also the log-probability of the chosen token under LogSoftMax of the processed logits (return_scores,
+// decoding.cc:875-880, 919-920): every chunk keeps sum exp(v - chunk max); the chunk max IS its argmax value, and the
+// chosen token is the global argmax, so log p = -log(sum over chunks of s_c * exp(m_c - M)).
+template <typename T, bool kScores>
 __global__ void __launch_bounds__(kSampleThreads)
     sample_greedy_kernel(const T* __restrict__ logits, int64_t vocab, const int32_t* __restrict__ gen,
                          const int32_t* __restrict__ end_ids, const int32_t* __restrict__ forced, int64_t batch,
                          int32_t* __restrict__ next_ids, int32_t* __restrict__ out_ids, int32_t* __restrict__ lens,
-                         float* __restrict__ part_v, int32_t* __restrict__ part_i, int32_t* __restrict__ tickets) {
+                         float* __restrict__ part_v, int32_t* __restrict__ part_i, int32_t* __restrict__ tickets,
+                         float* __restrict__ part_s, float* __restrict__ step_scores) {
   constexpr int N = Vec16<T>::N;
   __shared__ float sv[32];
   __shared__ int32_t si[32];
@@ -44,12 +48,21 @@ __global__ void __launch_bounds__(kSampleThreads)
   const int64_t v0 = chunk * nvec / nchunks, v1 = (chunk + 1) * nvec / nchunks;
   float best = -INFINITY;
   int32_t besti = INT32_MAX;
+  float sum_m = -INFINITY, sum_s = 0.f;          // kScores: running max and sum exp(v - max) of this thread
   const bool vec_ok = (reinterpret_cast<uintptr_t>(row) & 15) == 0;
   auto consider = [&](float v, int64_t j) {
     if (disable_end)
       for (int e = 0; e < num_end; ++e)
         if (end_ids[e] == j) v = -INFINITY;
     argmax_merge(best, besti, v, static_cast<int32_t>(j));
+    if constexpr (kScores) {
+      if (v > sum_m) {
+        sum_s = sum_s * __expf(sum_m - v) + 1.f;  // exp(-inf) = 0 on the first finite value
+        sum_m = v;
+      } else if (v != -INFINITY) {
+        sum_s += __expf(v - sum_m);
+      }
+    }
   };
   if (vec_ok) {
     for (int64_t vi = v0 + threadIdx.x; vi < v1; vi += kSampleThreads) {
@@ -64,20 +77,34 @@ __global__ void __launch_bounds__(kSampleThreads)
     for (int64_t j = nvec * N + threadIdx.x; j < vocab; j += kSampleThreads) consider(to_f32(row[j]), j);
 
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = kSampleThreads >> 5;
+  __shared__ float ss[32];
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     argmax_merge(best, besti, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, besti, o));
-  if (lane == 0) { sv[warp] = best; si[warp] = besti; }
+  if constexpr (kScores) {                       // rescale every thread's sum to the warp max (= best after the merge)
+    sum_s = sum_m == -INFINITY ? 0.f : sum_s * __expf(sum_m - best);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) sum_s += __shfl_xor_sync(0xffffffffu, sum_s, o);
+  }
+  if (lane == 0) { sv[warp] = best; si[warp] = besti; ss[warp] = sum_s; }
   __syncthreads();
   if (warp == 0) {
-    best = lane < nw ? sv[lane] : -INFINITY;
+    const float wbest = lane < nw ? sv[lane] : -INFINITY;
+    float wsum = lane < nw ? ss[lane] : 0.f;
+    best = wbest;
     besti = lane < nw ? si[lane] : INT32_MAX;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1)
       argmax_merge(best, besti, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, besti, o));
+    if constexpr (kScores) {
+      wsum = wbest == -INFINITY ? 0.f : wsum * __expf(wbest - best);
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
     if (lane == 0) {
       part_v[b * nchunks + chunk] = best;
       part_i[b * nchunks + chunk] = besti;
+      if constexpr (kScores) part_s[b * nchunks + chunk] = wsum;
       __threadfence();
       s_last = atomicAdd(tickets + b, 1) == nchunks - 1;
     }
@@ -91,6 +118,16 @@ __global__ void __launch_bounds__(kSampleThreads)
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1)
     argmax_merge(best, besti, __shfl_xor_sync(0xffffffffu, best, o), __shfl_xor_sync(0xffffffffu, besti, o));
+  if constexpr (kScores) {
+    float tot = 0.f;
+    for (int c = lane; c < nchunks; c += 32) {
+      const float mc = __ldcg(part_v + b * nchunks + c);
+      tot += mc == -INFINITY ? 0.f : __ldcg(part_s + b * nchunks + c) * __expf(mc - best);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) tot += __shfl_xor_sync(0xffffffffu, tot, o);
+    if (lane == 0) step_scores[static_cast<int64_t>(step) * batch + b] = -logf(tot);
+  }
   if (lane == 0) {
     out_ids[static_cast<int64_t>(step) * batch + b] = besti;
     int32_t nxt = besti;
@@ -128,12 +165,19 @@ int sample_greedy_chunks(int64_t vocab) { return vocab >= 32768 ? 32 : (vocab >=
 // scratch: part_v float [batch*chunks], part_i int32 [batch*chunks], tickets int32 [batch] (zero between launches)
 void launch_sample_greedy(const void* logits, int64_t batch, int64_t vocab, const int32_t* gen, const int32_t* end_ids,
                           const int32_t* forced, int32_t* next_ids, int32_t* out_ids, int32_t* lens, float* part_v,
-                          int32_t* part_i, int32_t* tickets, int dtype, cudaStream_t st) {
+                          int32_t* part_i, int32_t* tickets, float* part_s, float* step_scores, int dtype,
+                          cudaStream_t st) {
   if (batch == 0) return;
   dim3 grid(sample_greedy_chunks(vocab), static_cast<unsigned>(batch));
-  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(sample_greedy_kernel<T>, grid, dim3(kSampleThreads), 0, st,
-                                        static_cast<const T*>(logits), vocab, gen, end_ids, forced, batch, next_ids,
-                                        out_ids, lens, part_v, part_i, tickets)));
+  if (step_scores) {
+    CT2_DISPATCH_DTYPE(dtype, (launch_pdl(sample_greedy_kernel<T, true>, grid, dim3(kSampleThreads), 0, st,
+                                          static_cast<const T*>(logits), vocab, gen, end_ids, forced, batch, next_ids,
+                                          out_ids, lens, part_v, part_i, tickets, part_s, step_scores)));
+  } else {
+    CT2_DISPATCH_DTYPE(dtype, (launch_pdl(sample_greedy_kernel<T, false>, grid, dim3(kSampleThreads), 0, st,
+                                          static_cast<const T*>(logits), vocab, gen, end_ids, forced, batch, next_ids,
+                                          out_ids, lens, part_v, part_i, tickets, part_s, step_scores)));
+  }
   check_launch();
 }
 

@@ -106,7 +106,8 @@ class Generator:
     def generate_batch(self, start_tokens, max_length: int = 512, min_length: int = 0, beam_size: int = 1,
                        sampling_topk: int = 1, include_prompt_in_result: bool = False,
                        end_token: Union[None, str, Sequence[str], Sequence[int]] = None,
-                       return_end_token: bool = False, **unsupported) -> List[GenerationResult]:
+                       return_end_token: bool = False, return_scores: bool = False, length_penalty: float = 1.0,
+                       **unsupported) -> List[GenerationResult]:
         """start_tokens: list of token-string lists, or list of id lists / int array [batch, len]."""
         if beam_size != 1 or sampling_topk != 1:
             raise ValueError("this engine implements greedy search (beam_size=1, sampling_topk=1)")
@@ -128,16 +129,26 @@ class Generator:
         end_ids = np.array(self._end_ids(end_token), np.int32)
         out = np.empty((B, max_length), np.int32)
         out_lens = np.empty(B, np.int32)
-        check(lib().ct2b200_generate_batch(ctypes.c_void_p(self._h), ids.ctypes.data_as(ctypes.c_void_p),
-                                           lens.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(B), ctypes.c_int64(P),
-                                           ctypes.c_int64(max_length), ctypes.c_int64(min_length),
-                                           end_ids.ctypes.data_as(ctypes.c_void_p), int(end_ids.size),
-                                           int(return_end_token), out.ctypes.data_as(ctypes.c_void_p),
-                                           out_lens.ctypes.data_as(ctypes.c_void_p)))
+        scores = np.zeros(B, np.float32)
+        if return_scores:
+            check(lib().ct2b200_generate_batch_scores(
+                ctypes.c_void_p(self._h), ids.ctypes.data_as(ctypes.c_void_p), lens.ctypes.data_as(ctypes.c_void_p),
+                ctypes.c_int64(B), ctypes.c_int64(P), ctypes.c_int64(max_length), ctypes.c_int64(min_length),
+                end_ids.ctypes.data_as(ctypes.c_void_p), int(end_ids.size), int(return_end_token),
+                ctypes.c_float(length_penalty), out.ctypes.data_as(ctypes.c_void_p),
+                out_lens.ctypes.data_as(ctypes.c_void_p), scores.ctypes.data_as(ctypes.c_void_p)))
+        else:
+            check(lib().ct2b200_generate_batch(ctypes.c_void_p(self._h), ids.ctypes.data_as(ctypes.c_void_p),
+                                               lens.ctypes.data_as(ctypes.c_void_p), ctypes.c_int64(B), ctypes.c_int64(P),
+                                               ctypes.c_int64(max_length), ctypes.c_int64(min_length),
+                                               end_ids.ctypes.data_as(ctypes.c_void_p), int(end_ids.size),
+                                               int(return_end_token), out.ctypes.data_as(ctypes.c_void_p),
+                                               out_lens.ctypes.data_as(ctypes.c_void_p)))
         results = []
         for b in range(B):
             seq = out[b, :out_lens[b]].tolist()
-            results.append(GenerationResult([[self._tokens[i] for i in seq]], [seq]))
+            results.append(GenerationResult([[self._tokens[i] for i in seq]], [seq],
+                                            [float(scores[b])] if return_scores else []))
         return results
 
     def forward_batch(self, tokens, return_log_probs: bool = False) -> np.ndarray:

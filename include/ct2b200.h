@@ -223,6 +223,14 @@ CT2B200_API int ct2b200_generate_batch(ct2b200_generator* g, const int32_t* prom
                            const int32_t* end_ids_h, int num_end_ids, int return_end_token,
                            int32_t* out_ids_h, int32_t* out_lens_h);
 
+/* The same with GenerationOptions::return_scores = true: out_scores_h [batch] = sum of the log-probabilities of the
+ * generated tokens (LogSoftMax of the processed logits, the end token's included) / length^length_penalty
+ * (src/decoding.cc:875-923, 189-203; include/ctranslate2/generation.h:22-23, 55). */
+CT2B200_API int ct2b200_generate_batch_scores(ct2b200_generator* g, const int32_t* prompt_ids_h, const int32_t* prompt_lens_h,
+                           int64_t batch, int64_t max_prompt_len, int64_t max_length, int64_t min_length,
+                           const int32_t* end_ids_h, int num_end_ids, int return_end_token, float length_penalty,
+                           int32_t* out_ids_h, int32_t* out_lens_h, float* out_scores_h);
+
 /* Generator::forward_batch_async(ids, return_log_probs) — full-sequence forward from position 0.
  * ids_h [batch, time] int32 host; logits_h [batch, time, vocab] f32 host. */
 CT2B200_API int ct2b200_forward_batch(ct2b200_generator* g, const int32_t* ids_h, int64_t batch, int64_t time,

@@ -582,7 +582,7 @@ class LlamaOracle:
 
     # -- greedy search ----------------------------------------------------------------
     def generate(self, prompts: np.ndarray, max_length: int, min_length: int = 0,
-                 end_ids: Sequence[int] = ()) -> List[List[int]]:
+                 end_ids: Sequence[int] = (), return_scores: bool = False, length_penalty: float = 1.0):
         """Generator::generate_batch, greedy, include_prompt_in_result=false.
         src/models/language_model.cc:217-238 (prefill of P-1 tokens) + GreedySearch::search
         (src/decoding.cc:732-974): argmax = TopK k=1 lowest-index ties; EOS forbidden until min_length;
@@ -594,6 +594,7 @@ class LlamaOracle:
         cur = prompts[:, P - 1:P].copy()
         out: List[List[int]] = [[] for _ in range(B)]
         done = [False] * B
+        scores = np.zeros(B, np.float64)
         for step in range(max_length):
             logits = self.forward(cur, P - 1 + step, all_logits=False)[:, 0, :]
             if step < min_length:
@@ -601,10 +602,16 @@ class LlamaOracle:
                     logits[:, e] = np.finfo(f32).min     # DisableTokens, decoding.cc:852-856
             _, idx = topk(logits, 1)
             nxt = idx[:, 0]
+            if return_scores:
+                # decoding.cc:875-880: LogSoftMax over the processed logits, score += log-prob of the sampled token
+                # (the end token's too: the addition precedes the is_finished test, :919-923)
+                lp = softmax(logits, log=True)
             for b in range(B):
                 if done[b]:
                     continue
                 tok = int(nxt[b])
+                if return_scores:
+                    scores[b] += float(lp[b, tok])
                 if tok in end_ids:
                     done[b] = True
                 else:
@@ -614,4 +621,9 @@ class LlamaOracle:
             cur = nxt.reshape(B, 1).astype(np.int64)
             if all(done):
                 break
+        if return_scores:
+            # finalize_hypothesis_score, decoding.cc:189-203: score / length^length_penalty (length = returned tokens)
+            final = [float(scores[b] / (max(len(out[b]), 1) ** length_penalty)) if len(out[b]) else float(scores[b])
+                     for b in range(B)]
+            return out, np.array(final, np.float32)
         return out

@@ -75,6 +75,18 @@ class RefGenerator:
                                   end_id, _p(out), _p(lens)))
         return [out[b, :lens[b]].tolist() for b in range(B)]
 
+    def generate_with_scores(self, prompts: np.ndarray, max_length: int, min_length: int = 0, end_id: int = 2,
+                             length_penalty: float = 1.0):
+        """(tokens, scores) with GenerationOptions::return_scores = true."""
+        prompts = _c(prompts, np.int32)
+        B, P = prompts.shape
+        out = np.zeros((B, max_length), np.int32)
+        lens = np.zeros(B, np.int32)
+        scores = np.zeros(B, np.float32)
+        _check(lib().ref_generate_scores(ctypes.c_void_p(self.h), _p(prompts), B, P, max_length, min_length, end_id,
+                                         ctypes.c_float(length_penalty), _p(out), _p(lens), _p(scores)))
+        return [out[b, :lens[b]].tolist() for b in range(B)], scores
+
 
 def quantize(x, round_before_cast=True):
     x = _c(x, np.float32)

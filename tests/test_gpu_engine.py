@@ -190,3 +190,23 @@ def test_full_size_llama8b_properties():
     # fp16 activations + int8 rounding: the two schedules agree on the first tokens and mostly afterwards
     same = sum(int(a == b) for a, b in zip(alone, mixed[0].sequences_ids[0]))
     assert alone[0] == mixed[0].sequences_ids[0][0] or same >= 8, (alone, mixed[0].sequences_ids[0])
+
+
+@gpu
+@pytest.mark.parametrize("graph", [False, True])
+def test_generate_scores_match_reference(graph):
+    """return_scores: cumulative log-probabilities / length^penalty against the unmodified reference's
+    GenerationResult.scores (tests/golden/tiny_llama_int8_scores.json, made by tools/make_golden.py --scores-only),
+    incl. min_length (DisableTokens before LogSoftMax) and rows that stop on the end token."""
+    import json
+    fx = json.load(open(os.path.join(GOLDEN, "tiny_llama_int8_scores.json")))
+    g = ct2.Generator(TINY, compute_type="int8_float32", max_batch_size=4, max_length=64, use_cuda_graph=graph)
+    for c in fx["cases"]:
+        res = g.generate_batch(fx["prompts"], max_length=c["max_length"], min_length=c["min_length"],
+                               end_token=[c["end_id"]], return_scores=True, length_penalty=c["length_penalty"])
+        assert [r.sequences_ids[0] for r in res] == c["tokens"]
+        got = np.array([r.scores[0] for r in res], np.float32)
+        np.testing.assert_allclose(got, np.array(c["scores"], np.float32), rtol=0, atol=2e-4 * (1 + np.abs(c["scores"]).max()))
+    # without return_scores the result carries no scores and the tokens are the same
+    res = g.generate_batch(fx["prompts"], max_length=12, min_length=12, end_token=[2])
+    assert all(r.scores == [] for r in res)

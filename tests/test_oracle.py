@@ -237,3 +237,18 @@ def test_tensor_parallel_partition_restatement():
         acc = sum(O.gemm_s8(hq[:, slice(*O.tp_shard_rows(F, k, world))], wd[:, slice(*O.tp_shard_rows(F, k, world))])
                   for k in range(world))
         np.testing.assert_array_equal(acc, O.gemm_s8(hq, wd))
+
+
+def test_generate_scores_match_reference_fixture():
+    """GenerationOptions::return_scores (decoding.cc:875-923, 189-203): the oracle's cumulative log-probabilities,
+    length-normalised, against the unmodified reference's GenerationResult.scores on the committed tiny model —
+    incl. rows that stop on the end token (its log-probability is part of the score, the token is not returned)."""
+    fx = json.load(open(os.path.join(GOLDEN, "tiny_llama_int8_scores.json")))
+    w = O.DecoderWeights.from_dir(os.path.join(GOLDEN, "tiny_llama_int8"), "cpu")
+    m = O.LlamaOracle(w)
+    prompts = np.array(fx["prompts"])
+    for c in fx["cases"]:
+        toks, scores = m.generate(prompts, c["max_length"], c["min_length"], [c["end_id"]], return_scores=True,
+                                  length_penalty=c["length_penalty"])
+        assert toks == c["tokens"]
+        np.testing.assert_allclose(scores, np.array(c["scores"], np.float32), rtol=0, atol=2e-5)

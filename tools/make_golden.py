@@ -105,8 +105,33 @@ def make_tiny_model(model_dir):
     return V
 
 
+def make_scores_fixture():
+    """GenerationResult.scores of the unmodified reference on the committed tiny model (return_scores=true): sum of the
+    chosen tokens' log-probabilities / length^length_penalty, incl. rows that end on the end token."""
+    from oracle import refapi
+    assert refapi.available(), "build oracle/_ref first: make -f oracle/Makefile.ref -j8"
+    mdir = os.path.join(OUT, "tiny_llama_int8")
+    fx = np.load(os.path.join(OUT, "tiny_llama_int8_ref.npz"), allow_pickle=True)
+    prompts = fx["prompts"]
+    g = refapi.RefGenerator(mdir, "int8", 4)
+    early_end = int(fx["generated_min12"][0][3])         # a token row 0 emits, used as end token below
+    cases = []
+    for lp in (1.0, 0.0, 0.6):
+        for (mx, mn, end) in ((12, 12, 2), (12, 0, 2), (12, 0, early_end), (12, 3, early_end)):
+            toks, scores = g.generate_with_scores(prompts, mx, mn, end, lp)
+            cases.append({"max_length": mx, "min_length": mn, "end_id": end, "length_penalty": lp, "tokens": toks,
+                          "scores": [float(x) for x in scores]})
+    g.close()
+    with open(os.path.join(OUT, "tiny_llama_int8_scores.json"), "w") as f:
+        json.dump({"prompts": prompts.tolist(), "cases": cases}, f)
+    print("wrote tiny_llama_int8_scores.json (%d cases)" % len(cases))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
+    if "--scores-only" in sys.argv:
+        make_scores_fixture()
+        return
     print("extracting gtest golden vectors")
     with open(os.path.join(OUT, "ref_gtest_vectors.json"), "w") as f:
         json.dump(extract_gtest_vectors(), f)
@@ -166,6 +191,7 @@ def main():
     gi = r.integers(0, 50, 9).astype(np.int32)
     d["ga_d"], d["ga_i"], d["ga_y"] = gd, gi, refapi.gather(gd, gi)
     np.savez(os.path.join(OUT, "ref_ops_random.npz"), **d)
+    make_scores_fixture()
     print("done")
 
 
