@@ -425,6 +425,14 @@ void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, Den
       w.n = n_local;
       w.k = k_local;
     }
+    {
+      // group-major {scale, zero} pairs for the decode kernel (coalesced fetches); the row-major arrays stay for the
+      // general kernel, the prompt-pass dequantisation and the op-level API
+      w.scale_zero.alloc(static_cast<size_t>(w.n) * (w.k / w.group_size) * 4);
+      AwqNative a{w.weight.ptr, w.scale.ptr, w.zeros.ptr, w.n, w.k, w.group_size};
+      awq_build_group_major(a, w.scale_zero.ptr, stream_);
+      CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+    }
     mc_.weight_bytes += w.weight.bytes + w.scale.bytes + w.zeros.bytes;
   } else {
     throw std::runtime_error("unsupported weight type for " + prefix);
@@ -609,7 +617,7 @@ void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* x
   } else if (w.kind == DenseWeights::FLOAT16) {
     gemm_f16_tc(x_float, w.weight.ptr, w.bias.ptr, residual, act, m, w.n, w.k, y, dtype_, stream_);
   } else {
-    AwqNative a{w.weight.ptr, w.scale.ptr, w.zeros.ptr, w.n, w.k, w.group_size};
+    AwqNative a{w.weight.ptr, w.scale.ptr, w.zeros.ptr, w.n, w.k, w.group_size, w.scale_zero.ptr};
     dense_awq(x_float, a, w.bias.ptr, residual, act, m, y, scratch_nk_.ptr, stream_);
   }
 }
@@ -648,8 +656,10 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
         dense(lw.up, nullptr, nullptr, xn_.ptr, rows, nullptr, -1, scratch_mn_.ptr);
         launch_mul_inplace(h_.ptr, scratch_mn_.ptr, rows * mc_.ffn_dim, dtype_, stream_);
       } else {
-        AwqNative g{lw.gate.weight.ptr, lw.gate.scale.ptr, lw.gate.zeros.ptr, lw.gate.n, lw.gate.k, lw.gate.group_size};
-        AwqNative u{lw.up.weight.ptr, lw.up.scale.ptr, lw.up.zeros.ptr, lw.up.n, lw.up.k, lw.up.group_size};
+        AwqNative g{lw.gate.weight.ptr, lw.gate.scale.ptr, lw.gate.zeros.ptr, lw.gate.n, lw.gate.k, lw.gate.group_size,
+                    lw.gate.scale_zero.ptr};
+        AwqNative u{lw.up.weight.ptr, lw.up.scale.ptr, lw.up.zeros.ptr, lw.up.n, lw.up.k, lw.up.group_size,
+                    lw.up.scale_zero.ptr};
         dense_awq_glu(xn_.ptr, g, u, mc_.activation, rows, h_.ptr, scratch_nk_.ptr, scratch_mn_.ptr, stream_);
       }
       dense(lw.down, nullptr, nullptr, h_.ptr, rows, x_.ptr, -1, x_.ptr);

@@ -75,6 +75,7 @@ struct DenseWeights {
   DeviceBuffer weight;          // int8 [n,k] | T [n,k] | packed int32
   DeviceBuffer scale;           // f32 [n] (INT8) | f16 scales (AWQ)
   DeviceBuffer zeros;           // AWQ qzeros
+  DeviceBuffer scale_zero;      // AWQ: {scale, zero} pairs in group-major order [k/group, n] (awq_decode.cu)
   DeviceBuffer bias;            // T [n] or empty
   int group_size = 128;
 };

@@ -504,6 +504,23 @@ void awq_dequantize_ref_layout(const int32_t* qweight, const void* scales, const
   check_launch();
 }
 
+namespace {
+__global__ void awq_group_major_kernel(const __half* __restrict__ sc, const __half* __restrict__ zr, int64_t n, int64_t ng,
+                                       __half2* __restrict__ sz) {
+  for (int64_t idx = blockIdx.x * static_cast<int64_t>(blockDim.x) + threadIdx.x; idx < n * ng;
+       idx += static_cast<int64_t>(gridDim.x) * blockDim.x) {
+    const int64_t g = idx / n, row = idx % n;
+    sz[idx] = __halves2half2(sc[row * ng + g], zr[row * ng + g]);
+  }
+}
+}  // namespace
+
+void awq_build_group_major(const AwqNative& w, void* sz_out, cudaStream_t st) {
+  awq_group_major_kernel<<<148 * 4, 256, 0, st>>>(static_cast<const __half*>(w.sc), static_cast<const __half*>(w.zr), w.n,
+                                                  w.k / w.group, static_cast<__half2*>(sz_out));
+  check_launch();
+}
+
 void awq_dequantize_native(const AwqNative& w, void* w_out /* f16 [n,k] */, cudaStream_t st) {
   awq_dequantize_native_kernel<<<148 * 8, 256, 0, st>>>(static_cast<const int32_t*>(w.wp), static_cast<const __half*>(w.sc),
                                                         static_cast<const __half*>(w.zr), w.group, w.n, w.k,

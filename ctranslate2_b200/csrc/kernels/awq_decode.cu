@@ -43,6 +43,7 @@ struct AwqDecParams {
   int p_stages;                  // depth of the packed / activation ring
   const __half* sc[2];           // [n, k/group] group scales (index 1: GLU "up")
   const __half* zr[2];
+  const __half2* sz[2];          // optional {scale, zero} [k/group, n]: one coalesced 4-byte load per row and group
 };
 
 template <int BN, int NB>
@@ -179,8 +180,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
       for (int w = 0; w < NB; ++w) {
         const bool ok = row_ok && it < nkb && g < ng;
-        z[w] = ok ? ap.zr[w][row * ng + g] : __float2half(0.f);
-        sc[w] = ok ? ap.sc[w][row * ng + g] : __float2half(0.f);
+        if (ap.sz[w] != nullptr) {
+          // group-major pairs: the 32 rows of a warp read 128 contiguous bytes (the row-major arrays cost one 32-byte
+          // sector per row and per array, i.e. 16x the traffic of the packed weights they belong to)
+          const __half2 v = ok ? ap.sz[w][g * p.n + row] : __float2half2_rn(0.f);
+          sc[w] = __low2half(v);
+          z[w] = __high2half(v);
+        } else {
+          z[w] = ok ? ap.zr[w][row * ng + g] : __float2half(0.f);
+          sc[w] = ok ? ap.sc[w][row * ng + g] : __float2half(0.f);
+        }
       }
     };
     fetch(grp, zc, sc_);
@@ -450,6 +459,8 @@ bool run(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, AwqD
   p.zr[0] = static_cast<const __half*>(w.zr);
   p.sc[1] = static_cast<const __half*>(w2 ? w2->sc : w.sc);
   p.zr[1] = static_cast<const __half*>(w2 ? w2->zr : w.zr);
+  p.sz[0] = static_cast<const __half2*>(w.sz);
+  p.sz[1] = static_cast<const __half2*>(w2 ? w2->sz : w.sz);
   const CUtensorMap tmx = make_operand_map(x, m, w.k, 2, 1, BN);
   const CUtensorMap tmw = make_packed_map(w.wp, w.n, w.k, plan.tile_rows);
   const CUtensorMap tmw2 = make_packed_map(w2 ? w2->wp : w.wp, w.n, w.k, plan.tile_rows);

@@ -91,7 +91,10 @@ struct AwqNative {
   const void* zr = nullptr;   // f16 [n, k/group]
   int64_t n = 0, k = 0;
   int group = 128;
+  const void* sz = nullptr;   // optional: half2 {scale, zero} [k/group, n] (group-major: coalesced per-row fetches)
 };
+// {scale, zero} pairs of a repacked weight in group-major order (built once at load; awq_decode.cu reads it)
+void awq_build_group_major(const AwqNative& w, void* sz_out /* half2 [k/group, n] */, cudaStream_t st);
 // awq_decode.cu — lean decode kernel (m <= 64); false = shape not covered
 bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const void* residual, int act, int64_t m, void* y,
                       cudaStream_t st);
