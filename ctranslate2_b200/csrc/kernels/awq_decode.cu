@@ -33,7 +33,11 @@ constexpr int kGroups = 4;             // blocks are converted CONCURRENTLY: one
 constexpr int kGroupWarps = kDeqWarps / kGroups;   // latency-bound (~1 k cycles measured), not issue-bound
 constexpr int kBKh = 64;               // fp16 channels per K block (one 128-byte swizzle atom)
 constexpr int kPacked = kTileM * kBKh / 2;      // 4096 bytes of nibbles per weight per block
-constexpr int kAStages = kGroups;        // operand stage of block `it` is it % 4 = its transform group
+// Operand (dequantized fp16) ring: block `it` uses stage it % stages and is converted by group it % 4.  With one stage per
+// group a group cannot start block it + 4 before the MMAs of block it have retired (ncu: 24 % of the transform warps' samples
+// sit on that wait), so a single weight matrix gets two stages per group; the fused gate/up pair (32 KB per stage) keeps one.
+template <int NB> struct AStages { static constexpr int value = NB == 1 ? 2 * kGroups : kGroups; };
+constexpr int kMaxAStages = 2 * kGroups;
 constexpr int kMaxP = 24;
 
 struct AwqDecParams {
@@ -53,7 +57,7 @@ struct AwqDecSmem {
   static constexpr int kCtrl = 1024;
   static size_t red_bytes(int cs) { return cs > 1 ? static_cast<size_t>(cs) * NB * (BN / 16) * ((16 + cs - 1) / cs) * kTileM * 4 : 0; }
   static size_t bytes(int p_stages, int cs) {
-    return static_cast<size_t>(kAStages) * kA + static_cast<size_t>(p_stages) * kP + kCtrl + red_bytes(cs) + 1024;
+    return static_cast<size_t>(AStages<NB>::value) * kA + static_cast<size_t>(p_stages) * kP + kCtrl + red_bytes(cs) + 1024;
   }
 };
 
@@ -68,6 +72,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : 128;
   constexpr int cp16 = (16 + CS - 1) / CS;
   constexpr int cpr = (BN / 16) * cp16;
+  constexpr int kAStages = AStages<NB>::value;
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -78,8 +83,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* p_full = reinterpret_cast<uint64_t*>(ctrl);           // [kMaxP] TMA landed
   uint64_t* p_free = p_full + kMaxP;                              // [kMaxP] transform warps + the MMA commit
   uint64_t* a_ready = p_free + kMaxP;                             // [kAStages] operand tile written (all transform warps)
-  uint64_t* a_free = a_ready + kAStages;                          // [kAStages] MMAs that read it retired
-  uint64_t* acc_bar = a_free + kAStages;
+  uint64_t* a_free = a_ready + kMaxAStages;                       // [kAStages] MMAs that read it retired
+  uint64_t* acc_bar = a_free + kMaxAStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
   uint32_t* red = reinterpret_cast<uint32_t*>(ctrl + S::kCtrl);
 
@@ -192,11 +197,13 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     };
+    __half z2[NB], s2n[NB];
     fetch(grp, zc, sc_);
+    fetch(grp + kGroups, zn, sn_);
 #pragma unroll 1
     for (int it = grp; it < nkb; it += kGroups) {
       const int sp = it % PD, sa = it % kAStages;
-      fetch(it + kGroups, zn, sn_);                    // scales of this thread's next block, off the critical path
+      fetch(it + 2 * kGroups, z2, s2n);                // {scale, zero} two blocks ahead: covers the L2 latency
       mbar_wait(p_full + sp, (it / PD) & 1);
       if (it >= kAStages) mbar_wait(a_free + sa, ((it / kAStages) & 1) ^ 1);
       const uint8_t* pk = p_ring + static_cast<size_t>(sp) * S::kP;
@@ -221,7 +228,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         mbar_arrive(p_free + sp);
       }
 #pragma unroll
-      for (int w = 0; w < NB; ++w) { zc[w] = zn[w]; sc_[w] = sn_[w]; }
+      for (int w = 0; w < NB; ++w) { zc[w] = zn[w]; sc_[w] = sn_[w]; zn[w] = z2[w]; sn_[w] = s2n[w]; }
     }
   } else {
     // ===== epilogue warps (2..5): thread = output channel =====
@@ -331,7 +338,7 @@ template <int BN, int NB>
 int p_stages_for(int cs, int nkb) {
   using S = AwqDecSmem<BN, NB>;
   const size_t cap = 220 * 1024;
-  const size_t fixed = static_cast<size_t>(kAStages) * S::kA + S::kCtrl + S::red_bytes(cs) + 1024;
+  const size_t fixed = static_cast<size_t>(AStages<NB>::value) * S::kA + S::kCtrl + S::red_bytes(cs) + 1024;
   if (fixed + 2 * S::kP > cap) return 0;
   int st = static_cast<int>((cap - fixed) / S::kP);
   st = std::min(st, kMaxP);
