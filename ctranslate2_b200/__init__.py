@@ -4,6 +4,6 @@ There is no CPU or PyTorch fallback: importing works anywhere, every compute cal
 B200."""
 from . import ops  # noqa: F401
 from ._lib import Ct2B200Error, kernel_launch_count, lib  # noqa: F401
-from .generator import GenerationResult, Generator  # noqa: F401
+from .generator import GenerationResult, Generator, model_summary  # noqa: F401
 
 __version__ = "0.1.0"

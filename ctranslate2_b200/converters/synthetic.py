@@ -308,6 +308,13 @@ def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
         w.add(p + "self_attention/rotary_base", np.float32(cfg.rotary_base))
         w.add(p + "self_attention/rotary_dim", np.int32(0))
         w.add(p + "self_attention/rotary_interleave", np.int8(0))
+        if cfg.rotary_scaling_type >= 0:
+            w.add(p + "self_attention/rotary_scaling_type", np.int8(cfg.rotary_scaling_type))
+            w.add(p + "self_attention/rotary_scaling_factor", np.float32(cfg.rotary_scaling_factor))
+            w.add(p + "self_attention/rotary_low_freq_factor", np.float32(cfg.rotary_low_freq_factor))
+            w.add(p + "self_attention/rotary_high_freq_factor", np.float32(cfg.rotary_high_freq_factor))
+            w.add(p + "self_attention/original_max_position_embeddings",
+                  np.int32(cfg.original_max_position_embeddings))
     w.add("decoder/layer_norm/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), "float16")
     w.add("decoder/num_heads", np.int16(cfg.num_heads))
     w.add("decoder/pre_norm", np.int8(1))

@@ -352,6 +352,27 @@ CT2B200_API int ct2b200_bench_decode(ct2b200_generator* g, int64_t batch, int64_
   });
 }
 
+CT2B200_API int ct2b200_model_summary(const char* model_dir, char* json_out, size_t capacity) {
+  return guarded([&] {
+    CT2_REQUIRE(model_dir && json_out && capacity > 0, "model_summary: null argument");
+    ModelFile file(model_dir);
+    const ModelConfig mc = parse_model_config(file);
+    char buf[1024];
+    const int n = std::snprintf(
+        buf, sizeof(buf),
+        "{\"spec\": \"%s\", \"binary_version\": %u, \"revision\": %u, \"num_layers\": %d, \"num_heads\": %d, "
+        "\"num_heads_kv\": %d, \"head_dim\": %d, \"d_model\": %lld, \"ffn_dim\": %lld, \"vocab_size\": %lld, "
+        "\"weights\": \"%s\", \"rotary_interleave\": %s, \"rotary_base\": %.9g, \"rotary_scaling_type\": %d, "
+        "\"layer_norm_epsilon\": %.9g, \"activation\": %d}",
+        file.spec_name.c_str(), file.binary_version, file.revision, mc.num_layers, mc.num_heads, mc.num_heads_kv, mc.head_dim,
+        static_cast<long long>(mc.d_model), static_cast<long long>(mc.ffn_dim), static_cast<long long>(mc.vocab),
+        mc.weights.c_str(), mc.rotary_interleave ? "true" : "false", static_cast<double>(mc.rotary_base),
+        mc.rotary_scaling_type, static_cast<double>(mc.eps), mc.activation);
+    CT2_REQUIRE(n > 0 && static_cast<size_t>(n) < capacity, "model_summary: output buffer too small");
+    std::memcpy(json_out, buf, static_cast<size_t>(n) + 1);
+  });
+}
+
 CT2B200_API int ct2b200_generator_tp_handle(ct2b200_generator* g, void* handle64_h) {
   return guarded([&] {
     CT2_REQUIRE(g && handle64_h, "null argument");

@@ -444,6 +444,54 @@ void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, Den
   }
 }
 
+// Geometry and attributes of a TransformerDecoderSpec model directory (host only: no device is touched), with the checks
+// for what this engine serves.  Attributes: models/model.h get_attribute_with_default; attention_layer.cc:112-142.
+ModelConfig parse_model_config(const ModelFile& f) {
+  ModelConfig mc;
+  if (f.spec_name != "TransformerDecoderSpec")
+    throw std::invalid_argument("ct2b200 serves TransformerDecoderSpec models; got " + f.spec_name);
+  // --- configuration (attributes: models/model.h get_attribute_with_default; attention_layer.cc:112-142) ---
+  while (f.find("decoder/layer_" + std::to_string(mc.num_layers) + "/self_attention/linear_0/weight")) ++mc.num_layers;
+  CT2_REQUIRE(mc.num_layers > 0, "model has no decoder layers");
+  const std::string a0 = "decoder/layer_0/self_attention/";
+  mc.num_heads = static_cast<int>(f.get("decoder/num_heads").scalar());
+  mc.num_heads_kv = static_cast<int>(f.attribute(a0 + "num_heads_kv", mc.num_heads));
+  const HostVariable& emb = f.get("decoder/embeddings/weight");
+  mc.vocab = emb.shape[0];
+  mc.d_model = emb.shape[1];
+  mc.head_dim = static_cast<int>(f.attribute(a0 + "head_dim", static_cast<double>(mc.d_model / mc.num_heads)));
+  mc.eps = static_cast<float>(f.config_number("layer_norm_epsilon", 1e-6));
+  mc.rotary_base = static_cast<float>(f.attribute(a0 + "rotary_base", 10000.0));
+  mc.rotary_interleave = f.attribute(a0 + "rotary_interleave", 1.0) != 0.0;
+  mc.rotary_scaling_type = static_cast<int>(f.attribute(a0 + "rotary_scaling_type", -1.0));
+  mc.rotary_scaling_factor = static_cast<float>(f.attribute(a0 + "rotary_scaling_factor", 1.0));
+  mc.rotary_low_freq = static_cast<float>(f.attribute(a0 + "rotary_low_freq_factor", 1.0));
+  mc.rotary_high_freq = static_cast<float>(f.attribute(a0 + "rotary_high_freq_factor", 4.0));
+  mc.original_max_positions = static_cast<int>(f.attribute(a0 + "original_max_position_embeddings", 0.0));
+  mc.activation = static_cast<int>(f.attribute("decoder/activation", 0.0));
+  CT2_REQUIRE(f.attribute("decoder/pre_norm", 1.0) != 0.0, "only pre-norm decoders are supported");
+  CT2_REQUIRE(f.find(a0 + "rotary_dim") != nullptr, "only rotary-position decoders are supported");
+  CT2_REQUIRE(f.attribute(a0 + "rotary_dim", 0.0) == 0.0 ||
+                  f.attribute(a0 + "rotary_dim", 0.0) == mc.head_dim, "partial rotary_dim is not supported");
+  CT2_REQUIRE(f.find("decoder/layer_0/ffn/linear_0_noact/weight") != nullptr, "only gated FFN (ffn_glu) is supported");
+  CT2_REQUIRE(f.find("decoder/layer_0/self_attention/layer_norm/beta") == nullptr, "only RMSNorm decoders are supported");
+  CT2_REQUIRE(mc.rotary_scaling_type != 1, "Su rotary scaling is not supported");
+  {
+    // output features of the gate projection: rows of an int8 / float weight, columns x 8 of an AWQ_GEMM-packed one
+    // (qweight [K, N/8]), rows of an AWQ_GEMV-packed one (qweight [N, K/8])
+    const HostVariable& gw = f.get("decoder/layer_0/ffn/linear_0/weight");
+    const bool awq = gw.type_id == 3 && f.find("decoder/layer_0/ffn/linear_0/weight_zero");
+    mc.ffn_dim = (awq && static_cast<int>(f.config_number("quantization_type", 0)) == 1) ? gw.shape[1] * 8 : gw.shape[0];
+  }
+  {
+    const HostVariable& qkv = f.get("decoder/layer_0/self_attention/linear_0/weight");
+    const bool awq = qkv.type_id == 3 && f.find("decoder/layer_0/self_attention/linear_0/weight_zero");
+    mc.weights = qkv.type_id == 1 ? "int8" : awq ? (static_cast<int>(f.config_number("quantization_type", 0)) == 1 ? "awq_gemm" : "awq_gemv")
+               : qkv.type_id == 4 ? "float16" : qkv.type_id == 5 ? "bfloat16" : qkv.type_id == 0 ? "float32" : "unsupported";
+  }
+  return mc;
+}
+
 LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& cfg) {
   device_ = cfg.device;
   CT2_CUDA_CHECK(cudaSetDevice(device_));
@@ -462,41 +510,7 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   tp_.rank = cfg.tp_rank;
   CT2_REQUIRE(tp_.world <= 8 && tp_.rank >= 0 && tp_.rank < tp_.world, "tensor parallel: rank/size out of range (size <= 8)");
 
-  if (f.spec_name != "TransformerDecoderSpec")
-    throw std::invalid_argument("ct2b200 serves TransformerDecoderSpec models; got " + f.spec_name);
-  // --- configuration (attributes: models/model.h get_attribute_with_default; attention_layer.cc:112-142) ---
-  while (f.find("decoder/layer_" + std::to_string(mc_.num_layers) + "/self_attention/linear_0/weight")) ++mc_.num_layers;
-  CT2_REQUIRE(mc_.num_layers > 0, "model has no decoder layers");
-  const std::string a0 = "decoder/layer_0/self_attention/";
-  mc_.num_heads = static_cast<int>(f.get("decoder/num_heads").scalar());
-  mc_.num_heads_kv = static_cast<int>(f.attribute(a0 + "num_heads_kv", mc_.num_heads));
-  const HostVariable& emb = f.get("decoder/embeddings/weight");
-  mc_.vocab = emb.shape[0];
-  mc_.d_model = emb.shape[1];
-  mc_.head_dim = static_cast<int>(f.attribute(a0 + "head_dim", static_cast<double>(mc_.d_model / mc_.num_heads)));
-  mc_.eps = static_cast<float>(f.config_number("layer_norm_epsilon", 1e-6));
-  mc_.rotary_base = static_cast<float>(f.attribute(a0 + "rotary_base", 10000.0));
-  mc_.rotary_interleave = f.attribute(a0 + "rotary_interleave", 1.0) != 0.0;
-  mc_.rotary_scaling_type = static_cast<int>(f.attribute(a0 + "rotary_scaling_type", -1.0));
-  mc_.rotary_scaling_factor = static_cast<float>(f.attribute(a0 + "rotary_scaling_factor", 1.0));
-  mc_.rotary_low_freq = static_cast<float>(f.attribute(a0 + "rotary_low_freq_factor", 1.0));
-  mc_.rotary_high_freq = static_cast<float>(f.attribute(a0 + "rotary_high_freq_factor", 4.0));
-  mc_.original_max_positions = static_cast<int>(f.attribute(a0 + "original_max_position_embeddings", 0.0));
-  mc_.activation = static_cast<int>(f.attribute("decoder/activation", 0.0));
-  CT2_REQUIRE(f.attribute("decoder/pre_norm", 1.0) != 0.0, "only pre-norm decoders are supported");
-  CT2_REQUIRE(f.find(a0 + "rotary_dim") != nullptr, "only rotary-position decoders are supported");
-  CT2_REQUIRE(f.attribute(a0 + "rotary_dim", 0.0) == 0.0 ||
-                  f.attribute(a0 + "rotary_dim", 0.0) == mc_.head_dim, "partial rotary_dim is not supported");
-  CT2_REQUIRE(f.find("decoder/layer_0/ffn/linear_0_noact/weight") != nullptr, "only gated FFN (ffn_glu) is supported");
-  CT2_REQUIRE(f.find("decoder/layer_0/self_attention/layer_norm/beta") == nullptr, "only RMSNorm decoders are supported");
-  CT2_REQUIRE(mc_.rotary_scaling_type != 1, "Su rotary scaling is not supported");
-  {
-    // output features of the gate projection: rows of an int8 / float weight, columns x 8 of an AWQ_GEMM-packed one
-    // (qweight [K, N/8]), rows of an AWQ_GEMV-packed one (qweight [N, K/8])
-    const HostVariable& gw = f.get("decoder/layer_0/ffn/linear_0/weight");
-    const bool awq = gw.type_id == 3 && f.find("decoder/layer_0/ffn/linear_0/weight_zero");
-    mc_.ffn_dim = (awq && static_cast<int>(f.config_number("quantization_type", 0)) == 1) ? gw.shape[1] * 8 : gw.shape[0];
-  }
+  mc_ = parse_model_config(f);
   CT2_REQUIRE(mc_.num_heads % tp_.world == 0 && mc_.num_heads_kv % tp_.world == 0 && mc_.ffn_dim % tp_.world == 0,
               "tensor parallel: heads, kv heads and ffn width must be divisible by the number of ranks");
   heads_ = mc_.num_heads / tp_.world;

@@ -97,7 +97,11 @@ struct ModelConfig {
   int activation = CT2B200_ACT_SWISH;
   bool embeddings_int8 = true;
   int64_t weight_bytes = 0;
+  std::string weights;           // storage type of the linear layers: int8 | awq_gemm | awq_gemv | float16 | bfloat16 | float32
 };
+
+class ModelFile;
+ModelConfig parse_model_config(const ModelFile& file);   // host only
 
 // TransformerDecoder for pre-norm / RMSNorm / gated-FFN / rotary decoders (Llama family).
 class LlamaDecoder {

@@ -26,6 +26,14 @@ class GenerationResult:
     scores: List[float] = field(default_factory=list)
 
 
+def model_summary(model_path: str) -> dict:
+    """What the engine finds in a CTranslate2 model directory (host only, no GPU needed): spec, binary version, decoder
+    geometry and the storage type of the linear layers (ct2b200_model_summary)."""
+    buf = ctypes.create_string_buffer(2048)
+    check(lib().ct2b200_model_summary(model_path.encode(), buf, ctypes.c_size_t(len(buf))))
+    return json.loads(buf.value.decode())
+
+
 class Generator:
     def __init__(self, model_path: str, device: str = "cuda", device_index: int = 0, compute_type: str = "default",
                  max_batch_size: int = 32, max_length: int = 4096, use_cuda_graph: bool = True, gemm_impl: int = 0,

@@ -213,6 +213,11 @@ CT2B200_API int ct2b200_generator_vocab_size(const ct2b200_generator* g);
 CT2B200_API int ct2b200_generator_info(const ct2b200_generator* g, int* num_layers, int* num_heads, int* num_heads_kv,
                            int* head_dim, int* d_model, int64_t* weight_bytes);
 
+/* Host only (no device needed): what models::Model::load would find in `model_dir` — spec, binary version, decoder geometry
+ * (layers, heads, kv heads, head_dim, d_model, ffn_dim, vocabulary) and the storage type of the linear layers, as a JSON
+ * object written to json_out.  The same parser configures ct2b200_generator_open. */
+CT2B200_API int ct2b200_model_summary(const char* model_dir, char* json_out, size_t capacity);
+
 /* Generator::generate_batch_async(...).get(), greedy (beam_size 1, sampling_topk 1),
  * include_prompt_in_result=false.  HOST buffers:
  *   prompt_ids_h [batch, max_prompt_len] int32 (right-padded), prompt_lens_h [batch];

@@ -1,0 +1,56 @@
+"""Host logic of the model loader on CPU (no GPU, no compute): ct2b200_model_summary parses model.bin / config.json exactly
+as ct2b200_generator_open does (same C++ function) — binary format v6 of the reference (src/models/model.cc:561-660,
+python/ctranslate2/specs/model_spec.py:382-414), attribute lookup with defaults, and the geometry of every storage type."""
+import os
+import sys
+
+import pytest
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import ctranslate2_b200 as ct2  # noqa: E402
+from ctranslate2_b200.converters.synthetic import LlamaConfig, write_llama_model  # noqa: E402
+
+GOLDEN = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def test_summary_of_the_model_written_by_the_reference_spec_writer():
+    """tests/golden/tiny_llama_int8 was produced by the REFERENCE's own TransformerDecoderModelSpec.save (tools/make_golden.py)."""
+    s = ct2.model_summary(os.path.join(GOLDEN, "tiny_llama_int8"))
+    assert s["spec"] == "TransformerDecoderSpec" and s["binary_version"] == 6 and s["weights"] == "int8"
+    assert s["num_layers"] >= 1 and s["num_heads"] % s["num_heads_kv"] == 0
+    assert s["d_model"] == s["num_heads"] * s["head_dim"] and s["rotary_interleave"] is False
+
+
+@pytest.mark.parametrize("quant,weights", [("int8_float16", "int8"), ("int8", "int8"), ("float16", "float16"),
+                                            ("bfloat16", "bfloat16"), ("awq_gemm", "awq_gemm"), ("awq_gemv", "awq_gemv")])
+def test_geometry_of_every_storage_type(tmp_path, quant, weights):
+    """ffn_dim != d_model and num_heads_kv != num_heads on purpose: an AWQ_GEMM-packed weight is [K, N/8] (the output width is
+    NOT its first dimension), an AWQ_GEMV-packed one [N, K/8]."""
+    cfg = LlamaConfig(num_layers=3, num_heads=8, num_heads_kv=2, head_dim=64, ffn_dim=1280, vocab_size=320,
+                      rotary_scaling_type=2, rotary_scaling_factor=8.0, original_max_position_embeddings=64)
+    d = str(tmp_path / quant)
+    write_llama_model(d, cfg, quant, seed=3, init_std=0.05)
+    s = ct2.model_summary(d)
+    assert s["weights"] == weights
+    assert (s["num_layers"], s["num_heads"], s["num_heads_kv"], s["head_dim"]) == (3, 8, 2, 64)
+    assert (s["d_model"], s["ffn_dim"], s["vocab_size"]) == (512, 1280, 320)
+    assert s["rotary_scaling_type"] == 2 and s["rotary_interleave"] is False and s["activation"] == 2
+    assert abs(s["rotary_base"] - cfg.rotary_base) < 1e-3 and abs(s["layer_norm_epsilon"] - cfg.rms_eps) < 1e-12
+
+
+def test_errors(tmp_path):
+    with pytest.raises(RuntimeError):
+        ct2.model_summary(str(tmp_path / "missing"))
+    # a non-decoder spec is rejected with the reference's exception class for bad arguments (std::invalid_argument)
+    bad = tmp_path / "bad"
+    bad.mkdir()
+    import struct
+    with open(bad / "model.bin", "wb") as f:
+        f.write(struct.pack("I", 6))
+        name = b"TransformerSpec\x00"
+        f.write(struct.pack("H", len(name)) + name)
+        f.write(struct.pack("I", 1))      # revision
+        f.write(struct.pack("I", 0))      # no variables
+        f.write(struct.pack("I", 0))      # no aliases
+    with pytest.raises(ValueError):
+        ct2.model_summary(str(bad))
