@@ -115,15 +115,19 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
-def step_bytes(name, batch, ctx):
-    """Algorithmic bytes of one decode step: int8 linear weights + fp32 row scales + KV read."""
+def step_bytes(name, batch, ctx, weights="int8"):
+    """Algorithmic bytes of one decode step: linear weights + their scales + KV read.
+    int8: 1 B per weight + fp32 row scales; awq: 0.5 B per weight + fp16 scale and zero per group of 128, fp16 lm_head."""
     m = MODELS[name]
     d = m["num_heads"] * m["head_dim"]
     qkv = (m["num_heads"] + 2 * m["num_heads_kv"]) * m["head_dim"]
     per_layer = qkv * d + d * d + 3 * m["ffn_dim"] * d
+    kv = 2 * m["num_heads_kv"] * m["head_dim"] * 2 * m["num_layers"]
+    if weights == "awq":
+        w = m["num_layers"] * per_layer // 2 + m["num_layers"] * per_layer // 128 * 4 + 2 * m["vocab_size"] * d
+        return w + batch * ctx * kv
     w = m["num_layers"] * per_layer + m["vocab_size"] * d
     scales = 4 * (m["num_layers"] * (qkv + d + 2 * m["ffn_dim"] + d) + m["vocab_size"])
-    kv = 2 * m["num_heads_kv"] * m["head_dim"] * 2 * m["num_layers"]
     return w + scales + batch * ctx * kv
 
 
@@ -161,6 +165,42 @@ def gemm_roofline(name, batch, device):
     return {"bound": "hbm", "kernel": "gemm_decode_kernel<s8, NB=2 gate/up + SwiGLU> (ffn gate/up %dx%d, m=%d)" % (2 * f, d, batch),
             "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
             "traffic": traffic, "bytes_per_launch": alg, "us_per_launch": round(ms * 1e3, 2), "peak_source": how}
+
+
+def awq_roofline(name, batch, device):
+    """The dominant kernel of the AWQ variant: fused gate/up AWQ-INT4 GEMM (awq_decode.cu), timed alone like gemm_roofline."""
+    import torch
+    from ctranslate2_b200 import ops
+    m = MODELS[name]
+    d, f, G = m["num_heads"] * m["head_dim"], m["ffn_dim"], 128
+    copies = max(3, int(400e6 // (f * d)) + 1)
+
+    def weight():
+        qw = torch.randint(-2 ** 31, 2 ** 31 - 1, (d, f // 8), dtype=torch.int32, device=device)
+        sc = (torch.rand((d // G, f), device=device) * 0.01 + 0.005).to(torch.float16)
+        qz = torch.randint(-2 ** 31, 2 ** 31 - 1, (d // G, f // 8), dtype=torch.int32, device=device)
+        return ops.AwqWeight(qw, sc, qz, ops.AWQ_GEMM, G)
+
+    wg, wu = [weight() for _ in range(copies)], [weight() for _ in range(copies)]
+    x = torch.randn((batch, d), device=device, dtype=torch.float16)
+    for i in range(copies):
+        ops.dense_awq_glu(x, wg[i], wu[i])
+    torch.cuda.synchronize()
+    iters = 4 * copies
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(iters):
+        ops.dense_awq_glu(x, wg[i % copies], wu[i % copies])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / iters
+    alg = 2 * (f * d // 2 + f * d // G * 4) + batch * d * 2 + batch * f * 2     # nibbles + scales/zeros + x + h
+    peak, how = measured_peaks()
+    ach = alg / (ms * 1e-3) / 1e9
+    return {"bound": "hbm", "kernel": "awq_decode_kernel<NB=2 gate/up + SwiGLU> (ffn gate/up %dx%d int4 g128, m=%d)" % (2 * f, d, batch),
+            "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4), "traffic": None,
+            "bytes_per_launch": alg, "us_per_launch": round(ms * 1e3, 2), "peak_source": how,
+            "note": "transform (int4 -> fp16) bound, not HBM bound: see profiles/r01_ncu_awq_and_prefill.md"}
 
 
 def _ref_thread_cache():
@@ -240,6 +280,8 @@ def main():
     ap.add_argument("--prompt-len", type=int, default=PROMPT_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--weights", default="int8", choices=["int8", "awq"],
+                    help="int8 = the headline INT8 configuration; awq = the AWQ-INT4 (group 128, AWQ_GEMM layout) variant")
     ap.add_argument("--tp", action="store_true",
                     help="N > 1: ONE tensor-parallel generator over the N GPUs (strong scaling) instead of N replicas")
     args = ap.parse_args()
@@ -247,12 +289,14 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     K, W, B, P = args.steps, max(3, args.warmup), args.batch, args.prompt_len
-    config = {"workload": "%s generate_batch INT8 (int8_float16), greedy, bsz %d, prompt %d + %d generated "
-                          "(BASELINE.json configs[2])" % (NAMES[args.model], B, P, K),
+    awq = args.weights == "awq"
+    config = {"workload": "%s generate_batch %s, greedy, bsz %d, prompt %d + %d generated "
+                          "(BASELINE.json configs[2])" % (NAMES[args.model], "AWQ-INT4 g128 (float16)" if awq else
+                                                          "INT8 (int8_float16)", B, P, K),
               "global_batch": B * (1 if args.tp else max(1, world)), "prompt_len": P,
               "parallelism": ("tp%d (heads / FFN columns sharded, collectives fused into kernels over NVLink peer memory)" % world)
               if args.tp and world > 1 else "dp%d (replicas, no collective)" % world,
-              "l2": "every step streams %.1f GB of weights (> 126 MB L2) — no flush needed" % (step_bytes(args.model, 0, 0) / 1e9)}
+              "l2": "every step streams %.1f GB of weights (> 126 MB L2) — no flush needed" % (step_bytes(args.model, 0, 0, args.weights) / 1e9)}
 
     if args.impl == "reference":
         if rank != 0:
@@ -277,13 +321,14 @@ def main():
         import torch.distributed as dist
         dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
     torch.cuda.set_device(local_rank)
-    mdir = model_dir(args.model) if local_rank == 0 else None
+    quant = "awq_gemm" if awq else "int8_float16"
+    mdir = model_dir(args.model, quant) if local_rank == 0 else None
     if world > 1:
         torch.distributed.barrier()
-        mdir = model_dir(args.model)
+        mdir = model_dir(args.model, quant)
     max_len = P + max(K, 8) + W + 8
     tp = args.tp and world > 1
-    gen = ct2.Generator(mdir, device_index=local_rank, compute_type="int8_float16", max_batch_size=B,
+    gen = ct2.Generator(mdir, device_index=local_rank, compute_type="float16" if awq else "int8_float16", max_batch_size=B,
                         max_length=max_len, use_cuda_graph=not args.no_graph, tensor_parallel=tp)
     units = 1 if tp else world             # independent batches processed per step
     info = gen.info()
@@ -325,21 +370,27 @@ def main():
         return
     peak, how = measured_peaks()
     ctx_mean = P + K / 2.0
-    sb = step_bytes(args.model, B, ctx_mean)
+    sb = step_bytes(args.model, B, ctx_mean, args.weights)
     step_gbs = sb / (dec_ms / K * 1e-3) / 1e9
     config.update({"step_bytes_algorithmic": int(sb), "step_GBps": round(step_gbs, 1),
                    "step_roofline_frac": round(step_gbs / peak, 4), "prefill_ms": round(pre_ms, 2),
                    "prefill_tokens_per_s": round(B * (P - 1) / (pre_ms * 1e-3), 1), "weight_bytes": info["weight_bytes"]})
     line = {"metric": "generate_batch tokens/sec", "value": round(value, 2), "unit": "tokens/s", "n_gpus": world,
             "steps": K, "warmup": W, "ms_per_step": round(dec_ms / K, 4), "higher_is_better": True, "scaling": "strong" if tp else "weak",
-            "vs_baseline": None, "dtype": "s8 (int8 x int8 -> s32 on tcgen05; f16 activations, f32 epilogue/softmax)",
+            "vs_baseline": None,
+            "dtype": ("s4 weights -> f16 (tcgen05 kind::f16, f32 accumulate)" if awq else
+                      "s8 (int8 x int8 -> s32 on tcgen05; f16 activations, f32 epilogue/softmax)"),
             "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": int(launches)}
     try:
-        line["roofline"] = gemm_roofline(args.model, B, "cuda")
+        line["roofline"] = awq_roofline(args.model, B, "cuda") if awq else gemm_roofline(args.model, B, "cuda")
     except Exception as ex:  # keep the headline even if the side measurement fails
         line["roofline"] = {"error": str(ex)}
-    if world == 1 and not args.no_cpu_baseline:
+    if awq:
+        line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference",
+                                "sample": "none: the reference has no CPU implementation of the AWQ ops "
+                                          "(src/ops/awq/gemm_cpu.cc, gemv_cpu.cc, dequantize_cpu.cc throw)"}
+    elif world == 1 and not args.no_cpu_baseline:
         gen.close()
         del gen
         torch.cuda.empty_cache()
