@@ -880,9 +880,11 @@ Generator::Generator(const std::string& model_dir, const ct2b200_generator_confi
   end_ids_d_.alloc(64 * sizeof(int32_t));
   sample_ws_.alloc((B * 97) * sizeof(int32_t));      // part_v [B*32] | part_i [B*32] | tickets [B] | part_s [B*32]
   scores_d_.alloc(B * L * sizeof(float));             // per-step log-probabilities (return_scores)
+  row_start_d_.alloc(B * sizeof(int32_t));            // first loop step whose sample is a generated token, per row
+  CT2_CUDA_CHECK(cudaMemset(row_start_d_.ptr, 0, row_start_d_.bytes));
   CT2_CUDA_CHECK(cudaMemset(sample_ws_.ptr, 0, sample_ws_.bytes));
   prompt_d_.alloc(B * L * sizeof(int32_t));
-  host_pinned_elems_ = static_cast<size_t>(B) * L + 64;
+  host_pinned_elems_ = static_cast<size_t>(B) * (L + 2) + 256;   // prompt block | forced inputs | gen[4] | end ids[64] | row starts[B]
   CT2_CUDA_CHECK(cudaMallocHost(&host_pinned_, host_pinned_elems_ * sizeof(int32_t)));
 }
 
@@ -911,7 +913,7 @@ void Generator::launch_step(int64_t batch, int64_t, int) {
                        forced_d_.as<int32_t>(), ids_d_.as<int32_t>(), out_d_.as<int32_t>(), lens_d_.as<int32_t>(),
                        sample_ws_.as<float>(), sample_ws_.as<int32_t>() + d.max_batch() * 32,
                        sample_ws_.as<int32_t>() + d.max_batch() * 64, sample_ws_.as<float>() + d.max_batch() * 65,
-                       want_scores_ ? scores_d_.as<float>() : nullptr, d.dtype(), d.stream());
+                       want_scores_ ? scores_d_.as<float>() : nullptr, row_start_d_.as<int32_t>(), d.dtype(), d.stream());
 }
 
 void Generator::build_step_graph(int64_t batch, int64_t min_length, int num_end_ids) {
@@ -974,14 +976,16 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
     }
   int32_t* hgen = hforced + forced_steps * B;
   hgen[0] = static_cast<int32_t>(fwd);
-  hgen[1] = 0;    // DisableTokens is applied on the host view below (per-row generated count); see note
+  hgen[1] = 0;
   hgen[2] = static_cast<int32_t>(r.end_ids.size());
   hgen[3] = static_cast<int32_t>(forced_steps);
-  // min_length counts GENERATED tokens; with equal-length prompts (the benchmark case) generated count ==
-  // step, so the device-side test `step < min_length` is exact.  Ragged batches use the smallest offset.
-  hgen[1] = static_cast<int32_t>(r.min_length + (max_p - min_p == 0 ? 0 : 0));
+  // min_length counts GENERATED tokens per row: the kernel compares step - row_start[b] with it
+  hgen[1] = static_cast<int32_t>(r.min_length);
   int32_t* hend = hgen + 4;
   for (size_t i = 0; i < r.end_ids.size(); ++i) hend[i] = r.end_ids[i];
+  // step s consumes prompt token fwd + s; row b's first generated token is the sample of step prompt_len - 1 - fwd
+  int32_t* hstart = hend + 64;
+  for (int64_t b = 0; b < B; ++b) hstart[b] = static_cast<int32_t>(r.prompt_lens[b] - 1 - fwd);
 
   if (fwd > 0)
     CT2_CUDA_CHECK(cudaMemcpyAsync(prompt_d_.ptr, hp, B * fwd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -989,6 +993,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   CT2_CUDA_CHECK(cudaMemcpyAsync(step_d_.ptr, hgen, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (!r.end_ids.empty())
     CT2_CUDA_CHECK(cudaMemcpyAsync(end_ids_d_.ptr, hend, r.end_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(row_start_d_.ptr, hstart, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (fwd > 0) run_prefill(prompt_d_.as<int32_t>(), B, fwd);
   // first decode input = forced[0] (the last common prompt token); positions = fwd
   CT2_CUDA_CHECK(cudaMemcpyAsync(ids_d_.ptr, forced_d_.ptr, B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));

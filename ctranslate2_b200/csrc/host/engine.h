@@ -211,7 +211,7 @@ class Generator {
   ct2b200_generator_config cfg_;
   std::unique_ptr<LlamaDecoder> decoder_;
   // decode-loop device state
-  DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_, sample_ws_, scores_d_;
+  DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_, sample_ws_, scores_d_, row_start_d_;
   bool want_scores_ = false;               // the step (and its CUDA graph) also writes per-step log-probabilities
   bool graph_scores_ = false;
   int32_t* host_pinned_ = nullptr;

@@ -147,8 +147,8 @@ void launch_attention_prefill(const void* qkv, const void* kc, const void* vc, c
 int sample_greedy_chunks(int64_t vocab);
 void launch_sample_greedy(const void* logits, int64_t batch, int64_t vocab, const int32_t* gen, const int32_t* end_ids,
                           const int32_t* forced, int32_t* next_ids, int32_t* out_ids, int32_t* lens, float* part_v,
-                          int32_t* part_i, int32_t* tickets, float* part_s, float* step_scores, int dtype,
-                          cudaStream_t st);
+                          int32_t* part_i, int32_t* tickets, float* part_s, float* step_scores,
+                          const int32_t* row_start, int dtype, cudaStream_t st);
 void launch_convert_to_f32(const void* x, int64_t n, float* y, int dtype, cudaStream_t st);
 void launch_convert_from_f32(const float* x, int64_t n, void* y, int dtype, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t st);
