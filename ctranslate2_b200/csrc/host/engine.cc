@@ -1005,6 +1005,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   // ---- GreedySearch::search host loop (decoding.cc:844-971) ----
   std::vector<std::vector<int32_t>> results(B);
   std::vector<double> score_sum(B, 0.0);
+  std::vector<char> ended_by_eos(B, 0);
   std::vector<float> hscores;
   if (want_scores_) hscores.resize(static_cast<size_t>(total_steps) * B);
   std::vector<char> finished(B, 0);
@@ -1030,6 +1031,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
         const bool is_end = std::find(r.end_ids.begin(), r.end_ids.end(), tok) != r.end_ids.end();
         if (is_end) {
           if (r.return_end_token) results[b].push_back(tok);
+          ended_by_eos[b] = 1;
           finished[b] = 1;
           ++num_finished;
         } else {
@@ -1054,8 +1056,9 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   }
   for (int64_t b = 0; b < B; ++b) {
     if (want_scores_) {
-      // finalize_hypothesis_score (decoding.cc:189-203); an empty hypothesis keeps the raw sum (reference behaviour)
-      const double len = static_cast<double>(results[b].size());
+      // finalize_hypothesis_score (decoding.cc:189-203).  The reference decodes with include_eos_in_hypotheses = true
+      // (decoding.h:154) and strips the end token afterwards (language_model.cc:253-257): the normalising length counts it.
+      const double len = static_cast<double>(results[b].size()) + ((ended_by_eos[b] && !r.return_end_token) ? 1.0 : 0.0);
       out_scores[b] = static_cast<float>(len > 0 ? score_sum[b] / std::pow(len, static_cast<double>(r.length_penalty)) : score_sum[b]);
     }
     out_lens[b] = static_cast<int32_t>(results[b].size());

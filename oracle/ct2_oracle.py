@@ -580,6 +580,96 @@ class LlamaOracle:
         x = rms_norm(x, w.v["decoder/layer_norm/gamma"], w.eps)
         return self._dense("decoder/projection", x)
 
+    # -- beam search ------------------------------------------------------------------
+    def generate_beam(self, prompts: np.ndarray, beam_size: int, max_length: int, min_length: int = 0,
+                      end_ids: Sequence[int] = (), length_penalty: float = 1.0, num_hypotheses: int = 1,
+                      patience: float = 1.0):
+        """Generator::generate_batch with beam_size > 1: BeamSearch::search (src/decoding.cc:425-720) after the prompt pass
+        of language_model.cc:217-238.  No prefix bias, no coverage penalty; hypotheses keep their end token while scored.
+        Returns per prompt a list of (tokens, score), best first (finalize_result / sort_hypotheses, :189-254).
+          * 2 * beam_size candidates per step from TopK over the flattened [beam * vocab] cumulative log-probabilities;
+          * only beam 0 is live at step 0 (initialize_beam_scores: the others start at the lowest float, :84-93);
+          * a candidate among the first beam_size that ends (end token, or last step) is registered as a hypothesis and its
+            slot is refilled with the next non-end candidate of the secondary list (:617-655);
+          * a prompt is finished at the last step, or — with no length penalty — when its top beam ended and it has
+            num_hypotheses hypotheses, or else when it has round(beam_size * patience) hypotheses (:657-663)."""
+        B, P = prompts.shape
+        V = self.w.v["decoder/projection/weight"].shape[0]
+        end_ids = list(end_ids)
+        self.reset(B)
+        if P > 1:
+            self.forward(prompts[:, :P - 1], 0, all_logits=False)
+        self.k_cache = [np.repeat(k, beam_size, axis=0) for k in self.k_cache]        # replicate_state
+        self.v_cache = [np.repeat(v, beam_size, axis=0) for v in self.v_cache]
+        ids = np.repeat(prompts[:, P - 1], beam_size).astype(np.int64)               # [B * beam]
+        lowest = np.finfo(f32).min
+        scores = np.tile(np.array([0.0] + [lowest] * (beam_size - 1), f32), B)       # initialize_beam_scores
+        alive = [[[] for _ in range(beam_size)] for _ in range(B)]
+        hyps: List[List[Tuple[List[int], float]]] = [[] for _ in range(B)]
+        finished = [False] * B
+        top_done = [False] * B
+        ncand = 2 * beam_size
+        max_candidates = int(round(beam_size * patience))
+        early_exit = length_penalty == 0
+        for step in range(max_length):
+            logits = self.forward(ids.reshape(-1, 1), P - 1 + step, all_logits=False)[:, 0, :]      # [B*beam, V]
+            if step < min_length:
+                for e in end_ids:
+                    logits[:, e] = lowest                                             # apply_min_length + DisableTokens
+            lp = (softmax(logits, log=True) + scores[:, None]).astype(f32).reshape(B, beam_size * V)
+            cand_scores, cand_ids = topk(lp, ncand)
+            origin, word = cand_ids // V, cand_ids % V
+            is_last = step + 1 == max_length
+            new_ids = np.zeros((B, beam_size), np.int64)
+            new_scores = np.zeros((B, beam_size), f32)
+            gather = np.zeros((B, beam_size), np.int64)
+            for i in range(B):
+                seqs = [alive[i][int(origin[i, j])] + [int(word[i, j])] for j in range(ncand)]
+                secondary = beam_size
+                active = []
+                for k in range(beam_size):
+                    nxt = k
+                    if not finished[i] and (int(word[i, k]) in end_ids or is_last):
+                        if k == 0:
+                            top_done[i] = True
+                        # the hypothesis keeps its end token while it is scored (include_eos_in_hypotheses = true);
+                        # language_model.cc:253-257 strips it from the returned tokens
+                        hyps[i].append((seqs[k][:step + 1], float(cand_scores[i, k])))
+                        for j in range(secondary, ncand):
+                            if int(word[i, j]) not in end_ids:
+                                nxt, secondary = j, j + 1
+                                break
+                    active.append(nxt)
+                if not finished[i]:
+                    if is_last:
+                        finished[i] = True
+                    elif early_exit:
+                        finished[i] = top_done[i] and len(hyps[i]) >= num_hypotheses
+                    else:
+                        finished[i] = len(hyps[i]) >= max_candidates
+                alive[i] = [seqs[a] for a in active]
+                new_ids[i] = word[i, active]
+                new_scores[i] = cand_scores[i, active]
+                gather[i] = i * beam_size + origin[i, active]
+            if all(finished):
+                break
+            g = gather.reshape(-1)                                                    # Decoder::update_state (beam reorder)
+            self.k_cache = [k[g] for k in self.k_cache]
+            self.v_cache = [v[g] for v in self.v_cache]
+            ids, scores = new_ids.reshape(-1), new_scores.reshape(-1).astype(f32)
+        out = []
+        for i in range(B):
+            final = [(t, float(sc / (len(t) ** length_penalty))) for t, sc in hyps[i]]
+            order = sorted(range(len(final)), key=lambda j: -final[j][1])              # std::sort, descending score
+            best = []
+            for j in order[:num_hypotheses]:
+                t = list(final[j][0])
+                while t and t[-1] in end_ids:
+                    t.pop()
+                best.append((t, final[j][1]))
+            out.append(best)
+        return out
+
     # -- greedy search ----------------------------------------------------------------
     def generate(self, prompts: np.ndarray, max_length: int, min_length: int = 0,
                  end_ids: Sequence[int] = (), return_scores: bool = False, length_penalty: float = 1.0):
@@ -594,6 +684,7 @@ class LlamaOracle:
         cur = prompts[:, P - 1:P].copy()
         out: List[List[int]] = [[] for _ in range(B)]
         done = [False] * B
+        ended_by_eos = [False] * B
         scores = np.zeros(B, np.float64)
         for step in range(max_length):
             logits = self.forward(cur, P - 1 + step, all_logits=False)[:, 0, :]
@@ -614,6 +705,7 @@ class LlamaOracle:
                     scores[b] += float(lp[b, tok])
                 if tok in end_ids:
                     done[b] = True
+                    ended_by_eos[b] = True
                 else:
                     out[b].append(tok)
                     if len(out[b]) >= max_length:
@@ -622,8 +714,10 @@ class LlamaOracle:
             if all(done):
                 break
         if return_scores:
-            # finalize_hypothesis_score, decoding.cc:189-203: score / length^length_penalty (length = returned tokens)
-            final = [float(scores[b] / (max(len(out[b]), 1) ** length_penalty)) if len(out[b]) else float(scores[b])
+            # finalize_hypothesis_score, decoding.cc:189-203: score / length^length_penalty.  The Generator decodes with
+            # include_eos_in_hypotheses = true (decoding.h:154) and strips the end token afterwards
+            # (language_model.cc:253-257), so the length that normalises the score counts the end token.
+            final = [float(scores[b] / ((len(out[b]) + (1 if ended_by_eos[b] else 0)) ** length_penalty))
                      for b in range(B)]
             return out, np.array(final, np.float32)
         return out

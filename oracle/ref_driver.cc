@@ -134,6 +134,43 @@ int ref_generate_scores(void* handle, const int32_t* prompt_ids, int B, int P, i
   });
 }
 
+// Beam search (GenerationOptions::beam_size > 1, BeamSearch::search, decoding.cc:425-720): the first `num_hyp` hypotheses per
+// prompt, best first.  out_ids [B, num_hyp, max_len] (-1 padded), out_lens / out_scores [B, num_hyp].
+int ref_generate_beam(void* handle, const int32_t* prompt_ids, int B, int P, int beam_size, int num_hyp, int max_len,
+                      int min_len, int end_id, float length_penalty, float patience, int32_t* out_ids, int32_t* out_lens,
+                      float* out_scores) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> prompts(B);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < P; ++t)
+        prompts[b].push_back(g->vocab->to_token(prompt_ids[b * P + t]));
+    GenerationOptions opt;
+    opt.beam_size = beam_size;
+    opt.patience = patience;
+    opt.num_hypotheses = num_hyp;
+    opt.sampling_topk = 1;
+    opt.max_length = max_len;
+    opt.min_length = min_len;
+    opt.include_prompt_in_result = false;
+    opt.return_scores = true;
+    opt.length_penalty = length_penalty;
+    opt.end_token = std::vector<size_t>{static_cast<size_t>(end_id)};
+    auto futures = g->generator->generate_batch_async(prompts, opt);
+    for (int b = 0; b < B; ++b) {
+      auto result = futures[b].get();
+      for (int h = 0; h < num_hyp; ++h) {
+        const bool have = h < static_cast<int>(result.sequences_ids.size());
+        const int64_t o = (static_cast<int64_t>(b) * num_hyp + h);
+        out_lens[o] = have ? static_cast<int32_t>(result.sequences_ids[h].size()) : -1;
+        out_scores[o] = have ? result.scores.at(h) : 0.f;
+        for (int t = 0; t < max_len; ++t)
+          out_ids[o * max_len + t] = (have && t < out_lens[o]) ? static_cast<int32_t>(result.sequences_ids[h][t]) : -1;
+      }
+    }
+  });
+}
+
 // Full-sequence forward: ids [B,T] -> logits (or log-probs) [B,T,V] fp32.
 int ref_forward(void* handle, const int32_t* ids, int B, int T, int return_log_probs,
                 float* out, int64_t out_capacity) {

@@ -75,6 +75,20 @@ class RefGenerator:
                                   end_id, _p(out), _p(lens)))
         return [out[b, :lens[b]].tolist() for b in range(B)]
 
+    def generate_beam(self, prompts: np.ndarray, beam_size: int, max_length: int, min_length: int = 0, end_id: int = 2,
+                      length_penalty: float = 1.0, num_hypotheses: int = 1, patience: float = 1.0):
+        """Beam search: per prompt a list of (tokens, score), best first."""
+        prompts = _c(prompts, np.int32)
+        B, P = prompts.shape
+        out = np.zeros((B, num_hypotheses, max_length), np.int32)
+        lens = np.zeros((B, num_hypotheses), np.int32)
+        scores = np.zeros((B, num_hypotheses), np.float32)
+        _check(lib().ref_generate_beam(ctypes.c_void_p(self.h), _p(prompts), B, P, beam_size, num_hypotheses, max_length,
+                                       min_length, end_id, ctypes.c_float(length_penalty), ctypes.c_float(patience),
+                                       _p(out), _p(lens), _p(scores)))
+        return [[(out[b, h, :lens[b, h]].tolist(), float(scores[b, h])) for h in range(num_hypotheses) if lens[b, h] >= 0]
+                for b in range(B)]
+
     def generate_with_scores(self, prompts: np.ndarray, max_length: int, min_length: int = 0, end_id: int = 2,
                              length_penalty: float = 1.0):
         """(tokens, scores) with GenerationOptions::return_scores = true."""

@@ -252,3 +252,19 @@ def test_generate_scores_match_reference_fixture():
                                   length_penalty=c["length_penalty"])
         assert toks == c["tokens"]
         np.testing.assert_allclose(scores, np.array(c["scores"], np.float32), rtol=0, atol=2e-5)
+
+
+def test_beam_search_matches_reference_fixture():
+    """BeamSearch::search (decoding.cc:425-720) restated in the oracle (SURVEY §8 f1, the next row): hypotheses and scores of
+    the unmodified reference's Generator with beam_size 2 / 4, several end tokens (rows finishing at step 0, mid-sequence,
+    never), min_length, num_hypotheses, patience, with and without length penalty."""
+    fx = json.load(open(os.path.join(GOLDEN, "tiny_llama_int8_scores.json")))
+    w = O.DecoderWeights.from_dir(os.path.join(GOLDEN, "tiny_llama_int8"), "cpu")
+    m = O.LlamaOracle(w)
+    prompts = np.array(fx["prompts"])
+    for c in fx["beam_cases"]:
+        got = m.generate_beam(prompts, c["beam_size"], c["max_length"], c["min_length"], [c["end_id"]], c["length_penalty"],
+                              c["num_hypotheses"], c["patience"])
+        for row_got, row_ref in zip(got, c["hypotheses"]):
+            assert [t for t, _ in row_got] == [t for t, _ in row_ref], c
+            np.testing.assert_allclose([s for _, s in row_got], [s for _, s in row_ref], rtol=0, atol=5e-5)

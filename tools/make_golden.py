@@ -114,17 +114,29 @@ def make_scores_fixture():
     fx = np.load(os.path.join(OUT, "tiny_llama_int8_ref.npz"), allow_pickle=True)
     prompts = fx["prompts"]
     g = refapi.RefGenerator(mdir, "int8", 4)
-    early_end = int(fx["generated_min12"][0][3])         # a token row 0 emits, used as end token below
+    gm = fx["generated_min12"]
+    # end tokens that rows emit at different positions: rows then stop at step 0, mid-sequence, or never
+    ends = [2, int(gm[0][3]), int(gm[1][2]), int(gm[2][5])]
     cases = []
     for lp in (1.0, 0.0, 0.6):
-        for (mx, mn, end) in ((12, 12, 2), (12, 0, 2), (12, 0, early_end), (12, 3, early_end)):
-            toks, scores = g.generate_with_scores(prompts, mx, mn, end, lp)
-            cases.append({"max_length": mx, "min_length": mn, "end_id": end, "length_penalty": lp, "tokens": toks,
-                          "scores": [float(x) for x in scores]})
+        for end in ends:
+            for (mx, mn) in ((12, 12), (12, 0), (12, 3)):
+                toks, scores = g.generate_with_scores(prompts, mx, mn, end, lp)
+                cases.append({"max_length": mx, "min_length": mn, "end_id": end, "length_penalty": lp, "tokens": toks,
+                              "scores": [float(x) for x in scores]})
+    beams = []
+    for beam in (2, 4):
+        for lp in (1.0, 0.0):
+            for end in ends[:3]:
+                for (mx, mn, nh, pat) in ((10, 0, 2, 1.0), (10, 3, 2, 2.0), (6, 6, 1, 1.0)):
+                    r = g.generate_beam(prompts, beam, mx, mn, end, lp, nh, pat)
+                    beams.append({"beam_size": beam, "max_length": mx, "min_length": mn, "end_id": end,
+                                  "length_penalty": lp, "num_hypotheses": nh, "patience": pat,
+                                  "hypotheses": [[[t, sc] for t, sc in row] for row in r]})
     g.close()
     with open(os.path.join(OUT, "tiny_llama_int8_scores.json"), "w") as f:
-        json.dump({"prompts": prompts.tolist(), "cases": cases}, f)
-    print("wrote tiny_llama_int8_scores.json (%d cases)" % len(cases))
+        json.dump({"prompts": prompts.tolist(), "cases": cases, "beam_cases": beams}, f)
+    print("wrote tiny_llama_int8_scores.json (%d greedy cases, %d beam cases)" % (len(cases), len(beams)))
 
 
 def main():
