@@ -38,3 +38,20 @@ def test_step_bytes_matches_survey_figures():
     w = bench.step_bytes("8b", 0, 0)
     assert abs(w - (7504658432 + 4 * (32 * (6144 + 4096 + 2 * 14336 + 4096) + 128256))) == 0
     assert bench.step_bytes("8b", 1, 1) - w == 131072
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref not built")
+@pytest.mark.timeout(400)
+def test_reference_arm_under_torchrun_prints_one_line(tmp_path):
+    """Launched like the driver launches N > 1 (`python -m torch.distributed.run --nproc-per-node N bench.py --impl reference
+    --gpus N ...`): rank 0 alone runs the reference and prints the line, the other ranks exit 0 without work."""
+    env = dict(os.environ, CT2B200_BENCH_DIR=str(tmp_path))
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+           "--master-port", "29931", os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--model", "tiny",
+           "--batch", "2", "--steps", "2", "--warmup", "1"]
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=380)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["value"] > 0
