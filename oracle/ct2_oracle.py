@@ -16,6 +16,7 @@ All arithmetic is float32 unless stated; integer paths are exact.
 from __future__ import annotations
 
 import math
+import struct
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
 
@@ -100,12 +101,14 @@ def dequantize_gemm_output(c: np.ndarray, a_scale: np.ndarray, b_scale: np.ndarr
 
 
 def dense_int8(x: np.ndarray, w_q: np.ndarray, w_scale: np.ndarray, bias: Optional[np.ndarray] = None,
-               act: int = ACT_NONE, residual: Optional[np.ndarray] = None, flavor: str = "cuda") -> np.ndarray:
+               act: int = ACT_NONE, residual: Optional[np.ndarray] = None, flavor: str = "cuda",
+               round_before_cast: bool = True) -> np.ndarray:
     """layers::Dense::operator(), quantized arm.  src/layers/common.cc:353-401:
-    Quantize(x) -> Gemm s8 -> Dequantize(+bias, activation) -> Add(residual)."""
+    Quantize(x) -> Gemm s8 -> Dequantize(+bias, activation) -> Add(residual).  round_before_cast is
+    Model::round_before_cast_in_quantization(): binary_version >= 5 (include/ctranslate2/models/model.h:87-89)."""
     shape = x.shape
     x2 = x.reshape(-1, shape[-1])
-    xq, xs = quantize_rows(x2)
+    xq, xs = quantize_rows(x2, round_before_cast)
     y = dequantize_gemm_output(gemm_s8(xq, w_q), xs, w_scale, bias, act, flavor)
     if residual is not None:
         y = (y + residual.reshape(y.shape).astype(f32)).astype(f32)
@@ -471,6 +474,260 @@ class DecoderWeights:
             awq_group=int(cfg.get("quantization_group_size") or 128))
 
 
+def layer_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5) -> np.ndarray:
+    """ops::LayerNorm over the last axis.  src/cpu/kernels.cc:463-495: mean = sum/n, var = max(sum(x^2)/n - mean^2, 0),
+    y = (x - mean) / sqrt(var + eps) * gamma + beta  (eps 1e-5 when the layer has a beta, layers/common.cc:449-453)."""
+    x = x.astype(f32)
+    n = f32(x.shape[-1])
+    mean = (x.sum(-1, dtype=f32) / n).astype(f32)
+    var = np.maximum((x * x).sum(-1, dtype=f32) / n - mean * mean, f32(0)).astype(f32)
+    rstd = (f32(1) / np.sqrt(var + f32(eps), dtype=f32)).astype(f32)
+    return ((x - mean[..., None]) * rstd[..., None] * gamma.astype(f32) + beta.astype(f32)).astype(f32)
+
+
+def sinusoidal_position_encoding(max_time: int, depth: int) -> np.ndarray:
+    """layers::SinusoidalPositionEncoder.  src/layers/common.cc:204-229: positions start at 1, [sin | cos] halves,
+    timescale_j = exp(-j * log(10000) / (depth/2 - 1))."""
+    inc = f32(math.log(10000.0)) / f32(depth // 2 - 1)
+    timescales = np.exp(np.arange(depth // 2, dtype=f32) * -inc, dtype=f32)
+    scaled = (np.arange(1, max_time + 1, dtype=f32)[:, None] * timescales[None, :]).astype(f32)
+    return np.concatenate([np.sin(scaled, dtype=f32), np.cos(scaled, dtype=f32)], axis=1)
+
+
+class Seq2SeqOracle:
+    """fp32 restatement of the encoder-decoder Transformer behind ctranslate2::Translator (SURVEY §8 f1, the golden model of
+    tests/translator_test.cc:53-96): TransformerEncoder (src/layers/transformer.cc:405-471), TransformerDecoder with
+    cross-attention (:621-871, attention.cc:371-440), pre-norm LayerNorm, ReLU FFN, sinusoidal positions, embeddings scaled by
+    sqrt(d) (:382-402), INT8 Dense with bias, beam search (beam_search above).  `v` = variables of model.bin."""
+
+    def __init__(self, variables: Dict[str, np.ndarray], num_heads: int = 8, flavor: str = "cpu",
+                 binary_version: int = 6, compute_type: str = "int8"):
+        self.v = variables
+        self.flavor = flavor
+        self.round_before_cast = binary_version >= 5
+        # compute_type "float32": Model::ensure_dtype dequantizes the saved int8 weights (q / scale, model.cc:330-341) and
+        # layers::Dense runs its float arm -- no activation quantization, hence no rounding flips: the strict structural pin
+        self.compute_type = compute_type
+        self._float_w: Dict[str, np.ndarray] = {}
+        self.num_heads = int(variables.get("encoder/num_heads", np.int16(num_heads)))
+        self.d = variables["encoder/embeddings/weight"].shape[1]
+        self.enc_layers = 0
+        while f"encoder/layer_{self.enc_layers}/ffn/linear_0/weight" in variables:
+            self.enc_layers += 1
+        self.dec_layers = 0
+        while f"decoder/layer_{self.dec_layers}/ffn/linear_0/weight" in variables:
+            self.dec_layers += 1
+        self.pos = sinusoidal_position_encoding(512, self.d)
+
+    @classmethod
+    def from_dir(cls, model_dir: str, flavor: str = "cpu", compute_type: str = "int8") -> "Seq2SeqOracle":
+        _, _, variables, _ = read_model_bin(model_dir + "/model.bin")
+        with open(model_dir + "/model.bin", "rb") as f:
+            binary_version = struct.unpack("<I", f.read(4))[0]
+        return cls(variables, flavor=flavor, binary_version=binary_version, compute_type=compute_type)
+
+    # -- layers -----------------------------------------------------------------------
+    def _dense(self, prefix, x, act=ACT_NONE, residual=None):
+        v = self.v
+        if self.compute_type == "float32":
+            w = self._float_w.get(prefix)
+            if w is None:
+                w = (v[prefix + "/weight"].astype(f32) / v[prefix + "/weight_scale"].astype(f32)[:, None]).astype(f32)
+                self._float_w[prefix] = w
+            y = (x.astype(f32) @ w.T).astype(f32)
+            if prefix + "/bias" in v:
+                y = (y + v[prefix + "/bias"].astype(f32)).astype(f32)
+            y = activation(y, act)
+            return y if residual is None else (y + residual).astype(f32)
+        return dense_int8(x, v[prefix + "/weight"], v[prefix + "/weight_scale"], v.get(prefix + "/bias"), act, residual,
+                          self.flavor, self.round_before_cast)
+
+    def _embed(self, scope, ids):
+        v = self.v
+        rows = gather_rows(v[scope + "/embeddings/weight"], ids).astype(f32)
+        sc = gather_rows(v[scope + "/embeddings/weight_scale"], ids).astype(f32)
+        x = (rows / sc[..., None]).astype(f32)
+        return (x * f32(math.sqrt(self.d))).astype(f32)          # build_embeddings_scale: sqrt(depth)
+
+    def _ln(self, prefix, x):
+        return layer_norm(x, self.v[prefix + "/gamma"], self.v[prefix + "/beta"], 1e-5)
+
+    def _attend(self, q, k, v_, lens_rows):
+        """q [B,T,d], k/v [B,S,d] -> context [B,T,d]; softmax over the first lens_rows keys of each (b, h, t) row."""
+        B, T, _ = q.shape
+        S = k.shape[1]
+        H, D = self.num_heads, self.d // self.num_heads
+        qh = q.reshape(B, T, H, D).transpose(0, 2, 1, 3)
+        kh = k.reshape(B, S, H, D).transpose(0, 2, 1, 3)
+        vh = v_.reshape(B, S, H, D).transpose(0, 2, 1, 3)
+        scores = (np.einsum("bhtd,bhsd->bhts", qh, kh) * f32(1.0 / math.sqrt(D))).astype(f32)
+        probs = softmax(scores.reshape(-1, S), lens_rows).reshape(B, H, T, S)
+        ctx = np.einsum("bhts,bhsd->bhtd", probs, vh).astype(f32)
+        return ctx.transpose(0, 2, 1, 3).reshape(B, T, self.d)
+
+    # -- encoder ----------------------------------------------------------------------
+    def encode(self, src: np.ndarray, lengths: np.ndarray) -> np.ndarray:
+        """src [B,S] ids (padding ignored through `lengths`) -> memory [B,S,d]."""
+        B, S = src.shape
+        x = (self._embed("encoder", src) + self.pos[:S][None]).astype(f32)
+        lens_rows = np.repeat(lengths, self.num_heads * S)
+        for l in range(self.enc_layers):
+            p = f"encoder/layer_{l}/"
+            h = self._ln(p + "self_attention/layer_norm", x)
+            qkv = self._dense(p + "self_attention/linear_0", h)
+            q, k, v_ = np.split(qkv, 3, axis=-1)
+            x = self._dense(p + "self_attention/linear_1", self._attend(q, k, v_, lens_rows), residual=x)
+            h = self._ln(p + "ffn/layer_norm", x)
+            h = self._dense(p + "ffn/linear_0", h, act=ACT_RELU)
+            x = self._dense(p + "ffn/linear_1", h, residual=x)
+        return self._ln("encoder/layer_norm", x)
+
+    # -- decoder ----------------------------------------------------------------------
+    def start(self, memory: np.ndarray, lengths: np.ndarray, beam_size: int):
+        """Decoder state for B * beam_size rows: empty self-attention caches, projected memory keys / values per layer."""
+        memory = np.repeat(memory, beam_size, axis=0)
+        self.mem_lengths = np.repeat(lengths, beam_size)
+        self.self_k = [np.zeros((memory.shape[0], 0, self.d), f32) for _ in range(self.dec_layers)]
+        self.self_v = [np.zeros((memory.shape[0], 0, self.d), f32) for _ in range(self.dec_layers)]
+        self.mem_k, self.mem_v = [], []
+        for l in range(self.dec_layers):
+            kv = self._dense(f"decoder/layer_{l}/attention/linear_1", memory)
+            k, v_ = np.split(kv, 2, axis=-1)
+            self.mem_k.append(k)
+            self.mem_v.append(v_)
+
+    def reorder(self, index: np.ndarray):
+        self.self_k = [k[index] for k in self.self_k]
+        self.self_v = [v_[index] for v_ in self.self_v]
+        self.mem_k = [k[index] for k in self.mem_k]
+        self.mem_v = [v_[index] for v_ in self.mem_v]
+        self.mem_lengths = self.mem_lengths[index]
+
+    def step(self, ids: np.ndarray, step: int) -> np.ndarray:
+        """One target position for every row: ids [N] at position `step` -> logits [N, V]."""
+        N = ids.shape[0]
+        H = self.num_heads
+        x = (self._embed("decoder", ids.reshape(N, 1)) + self.pos[step:step + 1][None]).astype(f32)
+        for l in range(self.dec_layers):
+            p = f"decoder/layer_{l}/"
+            h = self._ln(p + "self_attention/layer_norm", x)
+            qkv = self._dense(p + "self_attention/linear_0", h)
+            q, k, v_ = np.split(qkv, 3, axis=-1)
+            self.self_k[l] = np.concatenate([self.self_k[l], k], axis=1)
+            self.self_v[l] = np.concatenate([self.self_v[l], v_], axis=1)
+            S = self.self_k[l].shape[1]
+            ctx = self._attend(q, self.self_k[l], self.self_v[l], np.full(N * H, S))
+            x = self._dense(p + "self_attention/linear_1", ctx, residual=x)
+            h = self._ln(p + "attention/layer_norm", x)
+            q = self._dense(p + "attention/linear_0", h)
+            ctx = self._attend(q, self.mem_k[l], self.mem_v[l], np.repeat(self.mem_lengths, H))
+            x = self._dense(p + "attention/linear_2", ctx, residual=x)
+            h = self._ln(p + "ffn/layer_norm", x)
+            h = self._dense(p + "ffn/linear_0", h, act=ACT_RELU)
+            x = self._dense(p + "ffn/linear_1", h, residual=x)
+        x = self._ln("decoder/layer_norm", x)
+        return self._dense("decoder/projection", x)[:, 0, :]
+
+    # -- Translator::translate_batch ---------------------------------------------------
+    def translate(self, source_ids: Sequence[Sequence[int]], beam_size: int = 2, num_hypotheses: int = 1,
+                  max_length: int = 256, min_length: int = 1, length_penalty: float = 1.0, bos: int = 1, eos: int = 2):
+        """TranslationOptions defaults (include/ctranslate2/translation.h): beam 2, length_penalty 1, min_decoding_length 1."""
+        B = len(source_ids)
+        lengths = np.array([len(r) for r in source_ids])
+        S = int(lengths.max())
+        src = np.zeros((B, S), np.int64)
+        for b, r in enumerate(source_ids):
+            src[b, :len(r)] = r
+        memory = self.encode(src, lengths)
+        self.start(memory, lengths, beam_size)
+        V = self.v["decoder/projection/weight"].shape[0]
+        return beam_search(self.step, self.reorder, np.full(B, bos), V, beam_size, max_length, min_length, [eos],
+                           length_penalty, num_hypotheses)
+
+
+def beam_search(step_fn, reorder_fn, start_ids: np.ndarray, vocab: int, beam_size: int, max_length: int,
+                min_length: int = 0, end_ids: Sequence[int] = (), length_penalty: float = 1.0, num_hypotheses: int = 1,
+                patience: float = 1.0):
+    """BeamSearch::search (src/decoding.cc:425-720).  No prefix bias, no coverage penalty; hypotheses keep their end token
+    while they are scored (include_eos_in_hypotheses = true, decoding.h:154) and lose it in the returned tokens.
+    step_fn(ids [B*beam], step) -> logits [B*beam, vocab] (advances the decoder state); reorder_fn(index [B*beam]) gathers the
+    state rows (Decoder::update_state).  Returns per batch entry a list of (tokens, score), best first
+    (finalize_result / sort_hypotheses, :189-254).
+      * 2 * beam_size candidates per step from TopK over the flattened [beam * vocab] cumulative log-probabilities;
+      * only beam 0 is live at step 0 (initialize_beam_scores: the others start at the lowest float, :84-93);
+      * a candidate among the first beam_size that ends (end token, or last step) is registered as a hypothesis and its
+        slot is refilled with the next non-end candidate of the secondary list (:617-655);
+      * an entry is finished at the last step, or — with no length penalty — when its top beam ended and it has
+        num_hypotheses hypotheses, or else when it has round(beam_size * patience) hypotheses (:657-663)."""
+    B, V = len(start_ids), vocab
+    end_ids = list(end_ids)
+    ids = np.repeat(np.asarray(start_ids), beam_size).astype(np.int64)               # [B * beam]
+    lowest = np.finfo(f32).min
+    scores = np.tile(np.array([0.0] + [lowest] * (beam_size - 1), f32), B)           # initialize_beam_scores
+    alive = [[[] for _ in range(beam_size)] for _ in range(B)]
+    hyps: List[List[Tuple[List[int], float]]] = [[] for _ in range(B)]
+    finished = [False] * B
+    top_done = [False] * B
+    ncand = 2 * beam_size
+    max_candidates = int(round(beam_size * patience))
+    early_exit = length_penalty == 0
+    for step in range(max_length):
+        logits = np.array(step_fn(ids, step), f32)                                    # [B*beam, V]
+        if step < min_length:
+            for e in end_ids:
+                logits[:, e] = lowest                                                 # apply_min_length + DisableTokens
+        with np.errstate(over="ignore"):
+            lp = (softmax(logits, log=True) + scores[:, None]).astype(f32).reshape(B, beam_size * V)
+        cand_scores, cand_ids = topk(lp, ncand)
+        origin, word = cand_ids // V, cand_ids % V
+        is_last = step + 1 == max_length
+        new_ids = np.zeros((B, beam_size), np.int64)
+        new_scores = np.zeros((B, beam_size), f32)
+        gather = np.zeros((B, beam_size), np.int64)
+        for i in range(B):
+            seqs = [alive[i][int(origin[i, j])] + [int(word[i, j])] for j in range(ncand)]
+            secondary = beam_size
+            active = []
+            for k in range(beam_size):
+                nxt = k
+                if not finished[i] and (int(word[i, k]) in end_ids or is_last):
+                    if k == 0:
+                        top_done[i] = True
+                    hyps[i].append((seqs[k][:step + 1], float(cand_scores[i, k])))
+                    for j in range(secondary, ncand):
+                        if int(word[i, j]) not in end_ids:
+                            nxt, secondary = j, j + 1
+                            break
+                active.append(nxt)
+            if not finished[i]:
+                if is_last:
+                    finished[i] = True
+                elif early_exit:
+                    finished[i] = top_done[i] and len(hyps[i]) >= num_hypotheses
+                else:
+                    finished[i] = len(hyps[i]) >= max_candidates
+            alive[i] = [seqs[a] for a in active]
+            new_ids[i] = word[i, active]
+            new_scores[i] = cand_scores[i, active]
+            gather[i] = i * beam_size + origin[i, active]
+        if all(finished):
+            break
+        reorder_fn(gather.reshape(-1))
+        ids, scores = new_ids.reshape(-1), new_scores.reshape(-1).astype(f32)
+    out = []
+    for i in range(B):
+        final = [(t, float(sc / (len(t) ** length_penalty))) for t, sc in hyps[i]]
+        order = sorted(range(len(final)), key=lambda j: -final[j][1])                  # std::sort, descending score
+        best = []
+        for j in order[:num_hypotheses]:
+            t = list(final[j][0])
+            while t and t[-1] in end_ids:
+                t.pop()
+            best.append((t, final[j][1]))
+        out.append(best)
+    return out
+
+
 class LlamaOracle:
     """fp32 restatement of TransformerDecoder::decode (src/layers/transformer.cc:621-871) for the
     Llama family: Embeddings (common.cc:64-81) -> L x [MultiHeadAttention (attention.cc:442-615) ->
@@ -584,91 +841,25 @@ class LlamaOracle:
     def generate_beam(self, prompts: np.ndarray, beam_size: int, max_length: int, min_length: int = 0,
                       end_ids: Sequence[int] = (), length_penalty: float = 1.0, num_hypotheses: int = 1,
                       patience: float = 1.0):
-        """Generator::generate_batch with beam_size > 1: BeamSearch::search (src/decoding.cc:425-720) after the prompt pass
-        of language_model.cc:217-238.  No prefix bias, no coverage penalty; hypotheses keep their end token while scored.
-        Returns per prompt a list of (tokens, score), best first (finalize_result / sort_hypotheses, :189-254).
-          * 2 * beam_size candidates per step from TopK over the flattened [beam * vocab] cumulative log-probabilities;
-          * only beam 0 is live at step 0 (initialize_beam_scores: the others start at the lowest float, :84-93);
-          * a candidate among the first beam_size that ends (end token, or last step) is registered as a hypothesis and its
-            slot is refilled with the next non-end candidate of the secondary list (:617-655);
-          * a prompt is finished at the last step, or — with no length penalty — when its top beam ended and it has
-            num_hypotheses hypotheses, or else when it has round(beam_size * patience) hypotheses (:657-663)."""
+        """Generator::generate_batch with beam_size > 1: the prompt pass of language_model.cc:217-238 (all but the last prompt
+        token), state replicated beam_size times, then beam_search() below from the last prompt token."""
         B, P = prompts.shape
         V = self.w.v["decoder/projection/weight"].shape[0]
-        end_ids = list(end_ids)
         self.reset(B)
         if P > 1:
             self.forward(prompts[:, :P - 1], 0, all_logits=False)
         self.k_cache = [np.repeat(k, beam_size, axis=0) for k in self.k_cache]        # replicate_state
         self.v_cache = [np.repeat(v, beam_size, axis=0) for v in self.v_cache]
-        ids = np.repeat(prompts[:, P - 1], beam_size).astype(np.int64)               # [B * beam]
-        lowest = np.finfo(f32).min
-        scores = np.tile(np.array([0.0] + [lowest] * (beam_size - 1), f32), B)       # initialize_beam_scores
-        alive = [[[] for _ in range(beam_size)] for _ in range(B)]
-        hyps: List[List[Tuple[List[int], float]]] = [[] for _ in range(B)]
-        finished = [False] * B
-        top_done = [False] * B
-        ncand = 2 * beam_size
-        max_candidates = int(round(beam_size * patience))
-        early_exit = length_penalty == 0
-        for step in range(max_length):
-            logits = self.forward(ids.reshape(-1, 1), P - 1 + step, all_logits=False)[:, 0, :]      # [B*beam, V]
-            if step < min_length:
-                for e in end_ids:
-                    logits[:, e] = lowest                                             # apply_min_length + DisableTokens
-            lp = (softmax(logits, log=True) + scores[:, None]).astype(f32).reshape(B, beam_size * V)
-            cand_scores, cand_ids = topk(lp, ncand)
-            origin, word = cand_ids // V, cand_ids % V
-            is_last = step + 1 == max_length
-            new_ids = np.zeros((B, beam_size), np.int64)
-            new_scores = np.zeros((B, beam_size), f32)
-            gather = np.zeros((B, beam_size), np.int64)
-            for i in range(B):
-                seqs = [alive[i][int(origin[i, j])] + [int(word[i, j])] for j in range(ncand)]
-                secondary = beam_size
-                active = []
-                for k in range(beam_size):
-                    nxt = k
-                    if not finished[i] and (int(word[i, k]) in end_ids or is_last):
-                        if k == 0:
-                            top_done[i] = True
-                        # the hypothesis keeps its end token while it is scored (include_eos_in_hypotheses = true);
-                        # language_model.cc:253-257 strips it from the returned tokens
-                        hyps[i].append((seqs[k][:step + 1], float(cand_scores[i, k])))
-                        for j in range(secondary, ncand):
-                            if int(word[i, j]) not in end_ids:
-                                nxt, secondary = j, j + 1
-                                break
-                    active.append(nxt)
-                if not finished[i]:
-                    if is_last:
-                        finished[i] = True
-                    elif early_exit:
-                        finished[i] = top_done[i] and len(hyps[i]) >= num_hypotheses
-                    else:
-                        finished[i] = len(hyps[i]) >= max_candidates
-                alive[i] = [seqs[a] for a in active]
-                new_ids[i] = word[i, active]
-                new_scores[i] = cand_scores[i, active]
-                gather[i] = i * beam_size + origin[i, active]
-            if all(finished):
-                break
-            g = gather.reshape(-1)                                                    # Decoder::update_state (beam reorder)
+
+        def step_fn(ids, step):
+            return self.forward(ids.reshape(-1, 1), P - 1 + step, all_logits=False)[:, 0, :]
+
+        def reorder_fn(g):                                                            # Decoder::update_state
             self.k_cache = [k[g] for k in self.k_cache]
             self.v_cache = [v[g] for v in self.v_cache]
-            ids, scores = new_ids.reshape(-1), new_scores.reshape(-1).astype(f32)
-        out = []
-        for i in range(B):
-            final = [(t, float(sc / (len(t) ** length_penalty))) for t, sc in hyps[i]]
-            order = sorted(range(len(final)), key=lambda j: -final[j][1])              # std::sort, descending score
-            best = []
-            for j in order[:num_hypotheses]:
-                t = list(final[j][0])
-                while t and t[-1] in end_ids:
-                    t.pop()
-                best.append((t, final[j][1]))
-            out.append(best)
-        return out
+
+        return beam_search(step_fn, reorder_fn, prompts[:, P - 1], V, beam_size, max_length, min_length, end_ids,
+                           length_penalty, num_hypotheses, patience)
 
     # -- greedy search ----------------------------------------------------------------
     def generate(self, prompts: np.ndarray, max_length: int, min_length: int = 0,

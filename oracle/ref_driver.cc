@@ -17,6 +17,8 @@
 
 #include <ctranslate2/generator.h>
 #include <ctranslate2/models/language_model.h>
+#include <ctranslate2/models/sequence_to_sequence.h>
+#include <ctranslate2/translator.h>
 #include <ctranslate2/ops/ops.h>
 #include <ctranslate2/utils.h>
 
@@ -166,6 +168,73 @@ int ref_generate_beam(void* handle, const int32_t* prompt_ids, int B, int P, int
         out_scores[o] = have ? result.scores.at(h) : 0.f;
         for (int t = 0; t < max_len; ++t)
           out_ids[o * max_len + t] = (have && t < out_lens[o]) ? static_cast<int32_t>(result.sequences_ids[h][t]) : -1;
+      }
+    }
+  });
+}
+
+// ---- Translator (encoder-decoder) over token ids: the golden case of tests/translator_test.cc:53-96 --------------------
+struct RefTranslator {
+  std::shared_ptr<const models::Model> model;
+  std::unique_ptr<Translator> translator;
+  const Vocabulary* source = nullptr;
+  const Vocabulary* target = nullptr;
+};
+
+void* ref_translator_open(const char* model_dir, const char* compute_type, int intra_threads) {
+  RefTranslator* t = nullptr;
+  int rc = guarded([&] {
+    auto holder = std::make_unique<RefTranslator>();
+    holder->model = models::Model::load(model_dir, Device::CPU, 0, str_to_compute_type(compute_type));
+    ReplicaPoolConfig config;
+    config.num_threads_per_replica = intra_threads > 0 ? intra_threads : 0;
+    holder->translator = std::make_unique<Translator>(holder->model, config);
+    auto s2s = dynamic_cast<const models::SequenceToSequenceModel*>(holder->model.get());
+    if (!s2s)
+      throw std::runtime_error("model is not a sequence-to-sequence model");
+    holder->source = &s2s->get_source_vocabulary();
+    holder->target = &s2s->get_target_vocabulary();
+    t = holder.release();
+  });
+  return rc == 0 ? t : nullptr;
+}
+
+void ref_translator_close(void* handle) { delete static_cast<RefTranslator*>(handle); }
+
+int ref_translator_vocab_sizes(void* handle, int* source, int* target) {
+  auto* t = static_cast<RefTranslator*>(handle);
+  return guarded([&] {
+    *source = static_cast<int>(t->source->size());
+    *target = static_cast<int>(t->target->size());
+  });
+}
+
+// source_ids [B, S] (rows right-padded with -1), beam search with TranslationOptions defaults except the given ones.
+// out_ids [B, num_hyp, max_len] (-1 padded), out_lens / out_scores [B, num_hyp].
+int ref_translate(void* handle, const int32_t* source_ids, int B, int S, int beam_size, int num_hyp, int max_len,
+                  int min_len, float length_penalty, int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  auto* t = static_cast<RefTranslator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> source(B);
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < S && source_ids[b * S + i] >= 0; ++i)
+        source[b].push_back(t->source->to_token(source_ids[b * S + i]));
+    TranslationOptions opt;
+    opt.beam_size = beam_size;
+    opt.num_hypotheses = num_hyp;
+    opt.max_decoding_length = max_len;
+    opt.min_decoding_length = min_len;
+    opt.length_penalty = length_penalty;
+    opt.return_scores = true;
+    auto results = t->translator->translate_batch(source, opt);
+    for (int b = 0; b < B; ++b) {
+      for (int h = 0; h < num_hyp; ++h) {
+        const bool have = h < static_cast<int>(results[b].hypotheses.size());
+        const int64_t o = static_cast<int64_t>(b) * num_hyp + h;
+        out_lens[o] = have ? static_cast<int32_t>(results[b].hypotheses[h].size()) : -1;
+        out_scores[o] = have ? results[b].scores.at(h) : 0.f;
+        for (int i = 0; i < max_len; ++i)
+          out_ids[o * max_len + i] = (have && i < out_lens[o]) ? static_cast<int32_t>(t->target->to_id(results[b].hypotheses[h][i])) : -1;
       }
     }
   });
@@ -321,5 +390,34 @@ extern "C" int ref_rotary_embeddings(const float* x, int t, int dim, int offset,
     StorageView X({1, 1, t, dim}, std::vector<float>(x, x + static_cast<size_t>(t) * dim), Device::CPU);
     rot.apply(X, offset);
     std::memcpy(y, X.data<float>(), static_cast<size_t>(t) * dim * sizeof(float));
+  });
+}
+
+// ops::LayerNorm (src/ops/layer_norm.cc) over the last axis
+extern "C" int ref_layer_norm(const float* gamma, const float* beta, const float* x, int rows, int cols, float eps,
+                              float* y) {
+  return guarded([&] {
+    StorageView G = view_f32(gamma, {cols}), Bt = view_f32(beta, {cols}), X = view_f32(x, {rows, cols});
+    StorageView Y(DataType::FLOAT32);
+    ops::LayerNorm(-1, eps)(Bt, G, X, Y);
+    std::memcpy(y, Y.data<float>(), (size_t)rows * cols * sizeof(float));
+  });
+}
+
+// layers::TransformerEncoder of the translator's model: ids [B,S] (padded with any id), lengths [B] -> out [B,S,d] fp32
+#include <ctranslate2/layers/transformer.h>
+extern "C" int ref_encoder_forward(void* handle, const int32_t* ids, const int32_t* lengths, int B, int S, float* out,
+                                   int64_t out_capacity) {
+  auto* t = static_cast<RefTranslator*>(handle);
+  return guarded([&] {
+    layers::TransformerEncoder encoder(*t->model, "encoder");
+    StorageView I({B, S}, DataType::INT32), L({B}, DataType::INT32);
+    std::memcpy(I.data<int32_t>(), ids, sizeof(int32_t) * B * S);
+    std::memcpy(L.data<int32_t>(), lengths, sizeof(int32_t) * B);
+    StorageView O(DataType::FLOAT32);
+    encoder({I}, &L, O);
+    if (O.size() > out_capacity)
+      throw std::runtime_error("ref_encoder_forward: output buffer too small");
+    std::memcpy(out, O.data<float>(), sizeof(float) * O.size());
   });
 }

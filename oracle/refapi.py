@@ -102,6 +102,62 @@ class RefGenerator:
         return [out[b, :lens[b]].tolist() for b in range(B)], scores
 
 
+class RefTranslator:
+    """The unmodified reference's Translator (encoder-decoder models) over token ids."""
+
+    def __init__(self, model_dir: str, compute_type: str = "int8", threads: int = 0):
+        lib().ref_translator_open.restype = ctypes.c_void_p
+        self.h = lib().ref_translator_open(model_dir.encode(), compute_type.encode(), threads)
+        if not self.h:
+            raise RuntimeError(lib().ref_last_error().decode())
+        s, t = ctypes.c_int(), ctypes.c_int()
+        _check(lib().ref_translator_vocab_sizes(ctypes.c_void_p(self.h), ctypes.byref(s), ctypes.byref(t)))
+        self.source_vocab_size, self.target_vocab_size = s.value, t.value
+
+    def close(self):
+        if self.h:
+            lib().ref_translator_close(ctypes.c_void_p(self.h))
+            self.h = None
+
+    def __del__(self):
+        self.close()
+
+    def encode(self, source_ids):
+        """layers::TransformerEncoder over the padded batch -> memory [B, S, d] fp32 and the lengths."""
+        B = len(source_ids)
+        S = max(len(r) for r in source_ids)
+        src = np.zeros((B, S), np.int32)
+        for b, r in enumerate(source_ids):
+            src[b, :len(r)] = r
+        lens = np.array([len(r) for r in source_ids], np.int32)
+        out = np.zeros((B, S, 4096), np.float32)
+        _check(lib().ref_encoder_forward(ctypes.c_void_p(self.h), _p(src), _p(lens), B, S, _p(out), ctypes.c_int64(out.size)))
+        return out, lens
+
+    def translate(self, source_ids, beam_size=2, num_hypotheses=1, max_length=256, min_length=1, length_penalty=1.0):
+        """source_ids: list of id lists.  Returns per sentence a list of (target ids, score), best first."""
+        B = len(source_ids)
+        S = max(len(r) for r in source_ids)
+        src = np.full((B, S), -1, np.int32)
+        for b, r in enumerate(source_ids):
+            src[b, :len(r)] = r
+        out = np.zeros((B, num_hypotheses, max_length), np.int32)
+        lens = np.zeros((B, num_hypotheses), np.int32)
+        scores = np.zeros((B, num_hypotheses), np.float32)
+        _check(lib().ref_translate(ctypes.c_void_p(self.h), _p(src), B, S, beam_size, num_hypotheses, max_length, min_length,
+                                   ctypes.c_float(length_penalty), _p(out), _p(lens), _p(scores)))
+        return [[(out[b, h, :lens[b, h]].tolist(), float(scores[b, h])) for h in range(num_hypotheses) if lens[b, h] >= 0]
+                for b in range(B)]
+
+
+def layer_norm(gamma, beta, x, eps=1e-5):
+    x = _c(x, np.float32)
+    r, c = x.shape
+    y = np.zeros((r, c), np.float32)
+    _check(lib().ref_layer_norm(_p(_c(gamma, np.float32)), _p(_c(beta, np.float32)), _p(x), r, c, ctypes.c_float(eps), _p(y)))
+    return y
+
+
 def quantize(x, round_before_cast=True):
     x = _c(x, np.float32)
     r, c = x.shape
