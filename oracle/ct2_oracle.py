@@ -115,6 +115,36 @@ def dense_int8(x: np.ndarray, w_q: np.ndarray, w_scale: np.ndarray, bias: Option
     return y.reshape(shape[:-1] + (w_q.shape[0],))
 
 
+def bias_add(value: np.ndarray, bias: np.ndarray, act: int = ACT_NONE, residual: Optional[np.ndarray] = None,
+             axis: int = -1) -> np.ndarray:
+    """ops::BiasAdd: act(value + bias [+ residual]), bias broadcast along `axis`.  src/ops/bias_add.cc,
+    src/cpu/kernels.cc add_bias_and_activation; goldens tests/ops_test.cc:1398-1432."""
+    shape = [1] * value.ndim
+    shape[axis] = bias.shape[0]
+    y = (value.astype(f32) + bias.astype(f32).reshape(shape)).astype(f32)
+    if residual is not None:
+        y = (y + residual.astype(f32)).astype(f32)
+    return activation(y, act)
+
+
+def gemm_float(a: np.ndarray, b: np.ndarray, c: Optional[np.ndarray] = None, alpha: float = 1.0, beta: float = 0.0,
+               trans_a: bool = False, trans_b: bool = False, bias: Optional[np.ndarray] = None,
+               residual: Optional[np.ndarray] = None, act: int = ACT_NONE) -> np.ndarray:
+    """ops::Gemm, float arm: C = act(alpha * op(A) op(B) + beta * C + bias + residual).  src/ops/gemm.cc:10-25 (the
+    activation comes AFTER bias and residual) and :45-107; goldens tests/ops_test.cc:516-681.  layers::Dense uses
+    alpha=1, beta=0, trans_b=true (common.cc:440)."""
+    A = a.astype(f32).T if trans_a else a.astype(f32)
+    B = b.astype(f32).T if trans_b else b.astype(f32)
+    y = (f32(alpha) * (A @ B)).astype(f32)
+    if c is not None and beta != 0.0:
+        y = (y + f32(beta) * c.astype(f32)).astype(f32)
+    if bias is not None:
+        return bias_add(y, bias, act, residual)
+    if residual is not None:
+        y = (y + residual.astype(f32)).astype(f32)
+    return activation(y, act)
+
+
 def tp_shard_rows(n_total: int, rank: int, world: int) -> Tuple[int, int]:
     """[begin, end) of a dimension split evenly over `world` ranks (models::Model::load splits weights with
     ops::Split into equal parts, src/models/model.cc:662-743; the dimension must be divisible)."""
@@ -534,11 +564,9 @@ class Seq2SeqOracle:
             if w is None:
                 w = (v[prefix + "/weight"].astype(f32) / v[prefix + "/weight_scale"].astype(f32)[:, None]).astype(f32)
                 self._float_w[prefix] = w
-            y = (x.astype(f32) @ w.T).astype(f32)
-            if prefix + "/bias" in v:
-                y = (y + v[prefix + "/bias"].astype(f32)).astype(f32)
-            y = activation(y, act)
-            return y if residual is None else (y + residual).astype(f32)
+            return gemm_float(x.reshape(-1, x.shape[-1]), w, trans_b=True, bias=v.get(prefix + "/bias"),
+                              residual=None if residual is None else residual.reshape(-1, w.shape[0]),
+                              act=act).reshape(x.shape[:-1] + (w.shape[0],))
         return dense_int8(x, v[prefix + "/weight"], v[prefix + "/weight_scale"], v.get(prefix + "/bias"), act, residual,
                           self.flavor, self.round_before_cast)
 
@@ -770,19 +798,16 @@ class LlamaOracle:
             else:
                 y = awq_gemv(x2, wq, sc, zr, self.w.awq_group)
             y = y.reshape(x.shape[:-1] + (y.shape[-1],))
+            # apply_bias_and_activation (gemm.cc:10-25): act(y + bias + residual).  No layer of the decoder passes an
+            # activation together with a residual, so this equals the product's fused epilogue (activation, then residual).
             if bias is not None:
                 y = y + bias.astype(f32)
-            y = activation(y, act)
             if residual is not None:
                 y = y + residual
-            return y.astype(f32)
-        y = x.astype(f32) @ wq.astype(f32).T      # float arm, common.cc:440
-        if bias is not None:
-            y = y + bias.astype(f32)
-        y = activation(y, act)
-        if residual is not None:
-            y = y + residual
-        return y.astype(f32)
+            return activation(y.astype(f32), act)
+        return gemm_float(x.reshape(-1, x.shape[-1]), wq, trans_b=True, bias=bias,          # float arm, common.cc:440
+                          residual=None if residual is None else residual.reshape(-1, wq.shape[0]),
+                          act=act).reshape(x.shape[:-1] + (wq.shape[0],))
 
     def _embed(self, ids: np.ndarray) -> np.ndarray:
         v = self.w.v

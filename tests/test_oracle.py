@@ -66,6 +66,37 @@ def test_gtest_activations(test, act):
     np.testing.assert_allclose(O.activation(vec(test, "input"), act), vec(test, "expected"), atol=1e-5)
 
 
+def static_vec(name):
+    it = next(i for i in GT["_static"] if i["name"] == name)
+    return np.array(it["values"], np.float32).reshape(it["shape"])
+
+
+def test_gtest_gemm_float_bias_residual_gelu():
+    """tests/ops_test.cc:516-681 — the float Gemm arm with beta * C, bias, residual and the GELU epilogue (act after both)."""
+    a, b, y = static_vec("gemm_a"), static_vec("gemm_b"), static_vec("gemm_y")
+    tol = dict(atol=1e-5, rtol=1e-5)
+    np.testing.assert_allclose(O.gemm_float(a, b, y, 1.0, 1.0), vec("Gemm", "expected"), **tol)
+    np.testing.assert_allclose(O.gemm_float(a.T.copy(), b, y, 1.0, 1.0, trans_a=True), vec("Gemm", "expected"), **tol)
+    np.testing.assert_allclose(O.gemm_float(a, b.T.copy(), y, 1.0, 1.0, trans_b=True), vec("Gemm", "expected"), **tol)
+    np.testing.assert_allclose(O.gemm_float(a, b, y, 1.0, 1.0, bias=vec("GemmBias", "bias")), vec("GemmBias", "expected"), **tol)
+    res = vec("GemmResidual", "residual")
+    np.testing.assert_allclose(O.gemm_float(a, b, y, 1.0, 1.0, bias=vec("GemmResidual", "bias"), residual=res),
+                               vec("GemmResidual", "expected", nth=0), **tol)
+    np.testing.assert_allclose(O.gemm_float(a, b, y, 1.0, 1.0, residual=res), vec("GemmResidual", "expected", nth=1), **tol)
+    bias, res = vec("GemmGELU", "bias"), vec("GemmGELU", "residual")
+    np.testing.assert_allclose(O.gemm_float(a, b, bias=bias, residual=res, act=O.ACT_GELU),
+                               vec("GemmGELU", "expected", nth=0), **tol)
+    np.testing.assert_allclose(O.gemm_float(a, b, bias=bias, act=O.ACT_GELU), vec("GemmGELU", "expected", nth=1), **tol)
+    np.testing.assert_allclose(O.gemm_float(a, b, act=O.ACT_GELU), vec("GemmGELU", "expected", nth=2), **tol)
+
+
+def test_gtest_bias_add():
+    """tests/ops_test.cc:1398-1432 — BiasAdd with the GELU epilogue, last axis and axis -2."""
+    value, bias = static_vec("bias_value"), static_vec("bias_bias")
+    np.testing.assert_allclose(O.bias_add(value, bias, O.ACT_GELU), vec("BiasAddGELU", "expected"), atol=1e-5)
+    np.testing.assert_allclose(O.bias_add(value, bias, O.ACT_GELU, axis=-2), vec("BiasAddAxisGELU", "expected"), atol=1e-5)
+
+
 def test_gtest_rotary_embedding():
     x, exp = vec("RotaryEmbedding", "input"), vec("RotaryEmbedding", "expected")
     # default RotaryEmbeddings(): dim 0 (= depth), interleave, base 10000, applied at offset 2

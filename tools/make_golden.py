@@ -35,9 +35,12 @@ GTESTS = {
                     "MaskedSoftMax", "RMSNorm", "QuantizeINT8", "QuantizeINT8ZeroRow", "Swish", "ReLU",
                     "GELU", "GELUTanh", "GELUSigmoid", "Gemm", "GemmBias", "GemmResidual", "GemmGELU",
                     "GatherData1D", "GatherData1DIndex2D", "GatherData2D", "GatherData3D",
-                    "GatherData2DIndex2D", "BiasAdd", "BiasAddResidual"],
+                    "GatherData2DIndex2D", "BiasAddGELU", "BiasAddAxisGELU"],
     "layers_test.cc": ["RotaryEmbedding"],
 }
+
+
+STATICS = ("gemm_a", "gemm_b", "gemm_y", "bias_value", "bias_bias")
 
 
 def extract_gtest_vectors():
@@ -63,6 +66,14 @@ def extract_gtest_vectors():
                 items.append({"name": v.group(1), "shape": shape, "ctype": v.group(3), "values": vals})
             out[name] = items
             print("  %-24s %d vectors" % (name, len(items)))
+        # file-scope inputs shared by several tests (`static const StorageView gemm_a(...)`)
+        static = re.compile(r"static const StorageView\s+(\w+)\((\{[^}]*\}),\s*std::vector<(\w+)>\s*\{([^}]*)\}", re.S)
+        for v in static.finditer(text):
+            if v.group(1) in STATICS:
+                shape = [int(t) for t in v.group(2).strip("{}").split(",") if t.strip()]
+                vals = [float(t.rstrip("f")) for t in re.split(r"[,\s]+", v.group(4).strip()) if t]
+                out.setdefault("_static", []).append({"name": v.group(1), "shape": shape, "ctype": v.group(3), "values": vals})
+                print("  static %-17s %s" % (v.group(1), shape))
     return out
 
 
@@ -143,6 +154,10 @@ def main():
     os.makedirs(OUT, exist_ok=True)
     if "--scores-only" in sys.argv:
         make_scores_fixture()
+        return
+    if "--gtest-only" in sys.argv:
+        with open(os.path.join(OUT, "ref_gtest_vectors.json"), "w") as f:
+            json.dump(extract_gtest_vectors(), f)
         return
     print("extracting gtest golden vectors")
     with open(os.path.join(OUT, "ref_gtest_vectors.json"), "w") as f:
