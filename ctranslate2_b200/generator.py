@@ -34,6 +34,16 @@ def model_summary(model_path: str) -> dict:
     return json.loads(buf.value.decode())
 
 
+def _validate_ids(rows, vocab_size: int) -> None:
+    """Token ids index the embedding table on the device (layers::Embeddings gathers rows, common.cc:64-81): the C-ABI takes
+    them as given, so the range check lives here, where ids can come from the caller instead of the vocabulary."""
+    for b, row in enumerate(rows):
+        a = np.asarray(row, dtype=np.int64)
+        if a.size and (int(a.min()) < 0 or int(a.max()) >= vocab_size):
+            bad = int(a[(a < 0) | (a >= vocab_size)][0])
+            raise ValueError(f"token id {bad} of row {b} is outside the vocabulary [0, {vocab_size})")
+
+
 class Generator:
     def __init__(self, model_path: str, device: str = "cuda", device_index: int = 0, compute_type: str = "default",
                  max_batch_size: int = 32, max_length: int = 4096, use_cuda_graph: bool = True, gemm_impl: int = 0,
@@ -128,6 +138,7 @@ class Generator:
         rows = [list(r) for r in start_tokens]
         if rows and rows[0] and isinstance(rows[0][0], str):
             rows = [self._ids(r) for r in rows]
+        _validate_ids(rows, self.vocab_size)
         B = len(rows)
         lens = np.array([len(r) for r in rows], np.int32)
         P = int(lens.max())
@@ -164,6 +175,7 @@ class Generator:
         rows = [list(r) for r in tokens]
         if rows and rows[0] and isinstance(rows[0][0], str):
             rows = [self._ids(r) for r in rows]
+        _validate_ids(rows, self.vocab_size)
         ids = np.ascontiguousarray(np.array(rows, np.int32))
         B, T = ids.shape
         logits = np.empty((B, T, self.vocab_size), np.float32)

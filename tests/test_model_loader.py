@@ -54,3 +54,12 @@ def test_errors(tmp_path):
         f.write(struct.pack("I", 0))      # no aliases
     with pytest.raises(ValueError):
         ct2.model_summary(str(bad))
+
+
+def test_token_ids_are_range_checked_before_they_reach_the_device():
+    from ctranslate2_b200.generator import _validate_ids
+    _validate_ids([[0, 5, 199], []], 200)
+    with pytest.raises(ValueError, match="row 1"):
+        _validate_ids([[1, 2], [3, 200]], 200)
+    with pytest.raises(ValueError, match="-1"):
+        _validate_ids([[1, -1]], 200)
