@@ -136,7 +136,9 @@ class Generator:
             if v not in (None, False, 0, 1, 1.0):
                 raise ValueError(f"unsupported generation option: {k}")
         rows = [list(r) for r in start_tokens]
-        if rows and rows[0] and isinstance(rows[0][0], str):
+        if not rows:
+            return []                       # an empty batch is an empty result (replica_pool.h: no job is posted)
+        if rows[0] and isinstance(rows[0][0], str):
             rows = [self._ids(r) for r in rows]
         _validate_ids(rows, self.vocab_size)
         B = len(rows)

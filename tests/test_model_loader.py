@@ -63,3 +63,10 @@ def test_token_ids_are_range_checked_before_they_reach_the_device():
         _validate_ids([[1, 2], [3, 200]], 200)
     with pytest.raises(ValueError, match="-1"):
         _validate_ids([[1, -1]], 200)
+
+
+def test_empty_batch_is_an_empty_result_without_touching_the_device():
+    from ctranslate2_b200.generator import Generator
+    g = Generator.__new__(Generator)        # no model, no device: the empty batch must return before either is needed
+    g._h = None
+    assert g.generate_batch([]) == []
