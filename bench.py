@@ -272,7 +272,8 @@ def reference_cpu(name, batch, steps, warmup, budget_s=100.0, calibrate=True):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=256)
+    # default = the named workload: 1024 generated tokens after the 1024-token prompt ("seq 2048"); a few seconds on a B200
+    ap.add_argument("--steps", type=int, default=1024)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--impl", default="ours")
