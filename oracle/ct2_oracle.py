@@ -673,6 +673,43 @@ class Seq2SeqOracle:
                            length_penalty, num_hypotheses)
 
 
+def apply_logits_processors(logits: np.ndarray, sampled: Sequence[int], repetition_penalty: float = 1.0,
+                            no_repeat_ngram_size: int = 0, suppress_sequences: Sequence[Sequence[int]] = (),
+                            disable_ids: Sequence[int] = ()) -> None:
+    """The LogitsProcessor chain of one row, in the order decoding.cc:1099-1112 builds it, on `logits` [V] in place.
+    `sampled` = the row of alive_seq: every token chosen by the loop so far (empty at step 0).  src/decoding_utils.cc:
+      RepetitionPenalty (:45-67, cpu/primitives.cc:411-428): scores of previous tokens are gathered FIRST, then each is
+        rewritten from its gathered value (score < 0 ? score * p : score / p) — a token seen twice is penalised once;
+      NoRepeatNgram (:75-107): every token that completed an earlier occurrence of the current (n-1)-gram suffix is disabled;
+      SuppressTokens (:170-177, disable_unk) and SuppressSequences (:110-150): single tokens always, the last token of a
+        longer sequence when the row ends with the rest.
+    Disabled entries become the lowest float (DisableTokens, decoding_utils.h:39) after all processors ran."""
+    lowest = np.finfo(f32).min
+    disabled = set()
+    if repetition_penalty != 1.0 and len(sampled) > 0:
+        ids = np.asarray(sampled, np.int64)
+        prev = logits[ids].copy()
+        logits[ids] = np.where(prev < 0, prev * f32(repetition_penalty), prev / f32(repetition_penalty)).astype(f32)
+    n = int(no_repeat_ngram_size)
+    if n > 0 and len(sampled) >= n:
+        suffix = list(sampled[len(sampled) - n + 1:]) if n > 1 else []
+        for p in range(0, len(sampled) - n + 1):
+            if list(sampled[p:p + n - 1]) == suffix:
+                disabled.add(int(sampled[p + n - 1]))
+    for t in disable_ids:
+        disabled.add(int(t))
+    for seq in suppress_sequences:
+        seq = [int(t) for t in seq]
+        if len(seq) == 0:
+            continue
+        if len(seq) == 1:
+            disabled.add(seq[0])
+        elif len(sampled) >= len(seq) - 1 and len(sampled) > 0 and list(sampled[len(sampled) - (len(seq) - 1):]) == seq[:-1]:
+            disabled.add(seq[-1])
+    for t in disabled:
+        logits[t] = lowest
+
+
 def beam_search(step_fn, reorder_fn, start_ids: np.ndarray, vocab: int, beam_size: int, max_length: int,
                 min_length: int = 0, end_ids: Sequence[int] = (), length_penalty: float = 1.0, num_hypotheses: int = 1,
                 patience: float = 1.0):
@@ -888,12 +925,17 @@ class LlamaOracle:
 
     # -- greedy search ----------------------------------------------------------------
     def generate(self, prompts: np.ndarray, max_length: int, min_length: int = 0,
-                 end_ids: Sequence[int] = (), return_scores: bool = False, length_penalty: float = 1.0):
+                 end_ids: Sequence[int] = (), return_scores: bool = False, length_penalty: float = 1.0,
+                 repetition_penalty: float = 1.0, no_repeat_ngram_size: int = 0,
+                 suppress_sequences: Sequence[Sequence[int]] = (), disable_ids: Sequence[int] = ()):
         """Generator::generate_batch, greedy, include_prompt_in_result=false.
         src/models/language_model.cc:217-238 (prefill of P-1 tokens) + GreedySearch::search
         (src/decoding.cc:732-974): argmax = TopK k=1 lowest-index ties; EOS forbidden until min_length;
-        a finished row stops (its tokens are not reported further)."""
+        a finished row stops (its tokens are not reported further).  The logits processors of GenerationOptions
+        (decoding.cc:1099-1112, apply_logits_processors below) see the tokens sampled so far in the loop — NOT the prompt."""
         B, P = prompts.shape
+        processors = repetition_penalty != 1.0 or no_repeat_ngram_size > 0 or len(suppress_sequences) > 0 or len(disable_ids) > 0
+        sampled: List[List[int]] = [[] for _ in range(B)]      # alive_seq, decoding.cc:886-893 (includes an end token)
         self.reset(B)
         if P > 1:
             self.forward(prompts[:, :P - 1], 0, all_logits=False)
@@ -907,6 +949,11 @@ class LlamaOracle:
             if step < min_length:
                 for e in end_ids:
                     logits[:, e] = np.finfo(f32).min     # DisableTokens, decoding.cc:852-856
+            if processors:
+                for b in range(B):
+                    if not done[b]:
+                        apply_logits_processors(logits[b], sampled[b], repetition_penalty, no_repeat_ngram_size,
+                                                suppress_sequences, disable_ids)
             _, idx = topk(logits, 1)
             nxt = idx[:, 0]
             if return_scores:
@@ -917,6 +964,7 @@ class LlamaOracle:
                 if done[b]:
                     continue
                 tok = int(nxt[b])
+                sampled[b].append(tok)
                 if return_scores:
                     scores[b] += float(lp[b, tok])
                 if tok in end_ids:

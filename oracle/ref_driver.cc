@@ -421,3 +421,52 @@ extern "C" int ref_encoder_forward(void* handle, const int32_t* ids, const int32
     std::memcpy(out, O.data<float>(), sizeof(float) * O.size());
   });
 }
+
+// Greedy generate_batch with the logits processors of GenerationOptions (decoding.cc:1099-1112, decoding_utils.cc):
+// repetition_penalty, no_repeat_ngram_size, disable_unk, suppress_sequences.  `suppress` is a flat list of token ids in which
+// -1 ends a sequence (n_suppress entries).  Scores are returned too (return_scores = true, length_penalty 1).
+extern "C" int ref_generate_processors(void* handle, const int32_t* prompt_ids, int B, int P, int max_len, int min_len,
+                                       int end_id, float repetition_penalty, int no_repeat_ngram_size, int disable_unk,
+                                       const int32_t* suppress, int n_suppress, int32_t* out_ids, int32_t* out_lens,
+                                       float* out_scores) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> prompts(B);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < P; ++t)
+        prompts[b].push_back(g->vocab->to_token(prompt_ids[b * P + t]));
+    GenerationOptions opt;
+    opt.beam_size = 1;
+    opt.sampling_topk = 1;
+    opt.max_length = max_len;
+    opt.min_length = min_len;
+    opt.include_prompt_in_result = false;
+    opt.return_scores = true;
+    opt.length_penalty = 1.f;
+    opt.repetition_penalty = repetition_penalty;
+    opt.no_repeat_ngram_size = static_cast<size_t>(no_repeat_ngram_size);
+    opt.disable_unk = disable_unk != 0;
+    std::vector<std::string> current;
+    for (int i = 0; i < n_suppress; ++i) {
+      if (suppress[i] < 0) {
+        if (!current.empty())
+          opt.suppress_sequences.push_back(std::move(current));
+        current.clear();
+      } else {
+        current.push_back(g->vocab->to_token(suppress[i]));
+      }
+    }
+    if (!current.empty())
+      opt.suppress_sequences.push_back(std::move(current));
+    opt.end_token = std::vector<size_t>{static_cast<size_t>(end_id)};
+    auto futures = g->generator->generate_batch_async(prompts, opt);
+    for (int b = 0; b < B; ++b) {
+      auto result = futures[b].get();
+      const auto& ids = result.sequences_ids.at(0);
+      out_lens[b] = static_cast<int32_t>(ids.size());
+      out_scores[b] = result.scores.at(0);
+      for (int t = 0; t < max_len; ++t)
+        out_ids[b * max_len + t] = t < (int)ids.size() ? (int32_t)ids[t] : -1;
+    }
+  });
+}

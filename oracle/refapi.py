@@ -102,6 +102,28 @@ class RefGenerator:
         return [out[b, :lens[b]].tolist() for b in range(B)], scores
 
 
+def _generate_processors(self, prompts, max_length, min_length=0, end_id=2, repetition_penalty=1.0, no_repeat_ngram_size=0,
+                         disable_unk=False, suppress_sequences=()):
+    """(tokens, scores) of greedy generate_batch with the logits processors of GenerationOptions."""
+    prompts = _c(prompts, np.int32)
+    B, P = prompts.shape
+    flat = []
+    for seq in suppress_sequences:
+        flat.extend(int(t) for t in seq)
+        flat.append(-1)
+    sup = np.array(flat if flat else [-1], np.int32)
+    out = np.zeros((B, max_length), np.int32)
+    lens = np.zeros(B, np.int32)
+    scores = np.zeros(B, np.float32)
+    _check(lib().ref_generate_processors(ctypes.c_void_p(self.h), _p(prompts), B, P, max_length, min_length, end_id,
+                                         ctypes.c_float(repetition_penalty), int(no_repeat_ngram_size), int(bool(disable_unk)),
+                                         _p(sup), int(len(flat)), _p(out), _p(lens), _p(scores)))
+    return [out[b, :lens[b]].tolist() for b in range(B)], scores
+
+
+RefGenerator.generate_processors = _generate_processors
+
+
 class RefTranslator:
     """The unmodified reference's Translator (encoder-decoder models) over token ids."""
 

@@ -285,6 +285,49 @@ def test_generate_scores_match_reference_fixture():
         np.testing.assert_allclose(scores, np.array(c["scores"], np.float32), rtol=0, atol=2e-5)
 
 
+def test_logits_processors_match_reference_fixture():
+    """GenerationOptions::repetition_penalty / no_repeat_ngram_size / disable_unk / suppress_sequences through the greedy loop
+    (decoding.cc:845-850, decoding_utils.cc): tokens identical, scores to fp32 round-off, incl. end tokens and min_length."""
+    fx = json.load(open(os.path.join(GOLDEN, "tiny_llama_int8_processors.json")))
+    w = O.DecoderWeights.from_dir(os.path.join(GOLDEN, "tiny_llama_int8"), "cpu")
+    m = O.LlamaOracle(w)
+    prompts = np.array(fx["prompts"])
+    changed = 0
+    plain = {}
+    for c in fx["cases"]:
+        opt = dict(c["options"])
+        if opt.pop("disable_unk", False):
+            opt["disable_ids"] = [0]                   # <t0> is the unknown token of the tiny model
+        key = (c["max_length"], c["min_length"], c["end_id"])
+        if key not in plain:
+            plain[key] = m.generate(prompts, c["max_length"], c["min_length"], [c["end_id"]])
+        toks, scores = m.generate(prompts, c["max_length"], c["min_length"], [c["end_id"]], return_scores=True, **opt)
+        assert toks == c["tokens"], c["options"]
+        np.testing.assert_allclose(scores, c["scores"], rtol=0, atol=2e-5)
+        changed += int(toks != plain[key])
+    assert changed >= len(fx["cases"]) // 2          # the options really alter what is generated
+
+
+def test_logits_processor_rules():
+    lowest = np.finfo(np.float32).min
+    base = np.array([1.0, -2.0, 3.0, 0.5, -0.5], np.float32)
+    x = base.copy()
+    O.apply_logits_processors(x, [2, 1, 2], repetition_penalty=2.0)          # a token seen twice is penalised once
+    np.testing.assert_array_equal(x, np.array([1.0, -4.0, 1.5, 0.5, -0.5], np.float32))
+    x = base.copy()
+    O.apply_logits_processors(x, [3, 4, 0, 3], no_repeat_ngram_size=2)         # "3 4" happened: after 3, token 4 is banned
+    assert x[4] == lowest and (x[:4] == base[:4]).all()
+    x = base.copy()
+    O.apply_logits_processors(x, [3, 4], no_repeat_ngram_size=3)               # shorter than the n-gram: nothing to ban
+    np.testing.assert_array_equal(x, base)
+    x = base.copy()
+    O.apply_logits_processors(x, [], suppress_sequences=[[1], [0, 2]])          # step 0: single tokens only
+    assert x[1] == lowest and x[2] == base[2]
+    x = base.copy()
+    O.apply_logits_processors(x, [4, 0], suppress_sequences=[[1], [0, 2]])
+    assert x[1] == lowest and x[2] == lowest
+
+
 def test_beam_search_matches_reference_fixture():
     """BeamSearch::search (decoding.cc:425-720) restated in the oracle (SURVEY §8 f1, the next row): hypotheses and scores of
     the unmodified reference's Generator with beam_size 2 / 4, several end tokens (rows finishing at step 0, mid-sequence,

@@ -150,10 +150,41 @@ def make_scores_fixture():
     print("wrote tiny_llama_int8_scores.json (%d greedy cases, %d beam cases)" % (len(cases), len(beams)))
 
 
+def make_processors_fixture():
+    """Greedy generate_batch of the unmodified reference with the logits processors of GenerationOptions (repetition_penalty,
+    no_repeat_ngram_size, disable_unk, suppress_sequences) on the committed tiny model — it repeats tokens a lot, which is
+    exactly what these options act on."""
+    from oracle import refapi
+    assert refapi.available(), "build oracle/_ref first: make -f oracle/Makefile.ref -j8"
+    mdir = os.path.join(OUT, "tiny_llama_int8")
+    fx = np.load(os.path.join(OUT, "tiny_llama_int8_ref.npz"), allow_pickle=True)
+    prompts = fx["prompts"]
+    gm = fx["generated_min12"]
+    g = refapi.RefGenerator(mdir, "int8", 4)
+    options = [dict(repetition_penalty=1.3), dict(repetition_penalty=0.7), dict(repetition_penalty=2.0, no_repeat_ngram_size=3),
+               dict(no_repeat_ngram_size=1), dict(no_repeat_ngram_size=2), dict(no_repeat_ngram_size=4), dict(disable_unk=True),
+               dict(suppress_sequences=[[int(gm[0][0])]]),
+               dict(suppress_sequences=[[int(gm[0][0])], [int(gm[1][0]), int(gm[1][1])], [int(gm[2][1]), int(gm[2][2]), int(gm[2][3])]]),
+               dict(suppress_sequences=[[int(gm[1][4]), int(gm[1][5])]], repetition_penalty=1.2, no_repeat_ngram_size=2)]
+    cases = []
+    for opt in options:
+        for (mx, mn, end) in ((12, 12, 2), (12, 0, int(gm[0][4])), (10, 3, int(gm[1][2]))):
+            toks, scores = g.generate_processors(prompts, mx, mn, end, **opt)
+            cases.append({"max_length": mx, "min_length": mn, "end_id": end, "options": opt, "tokens": toks,
+                          "scores": [float(x) for x in scores]})
+    g.close()
+    with open(os.path.join(OUT, "tiny_llama_int8_processors.json"), "w") as f:
+        json.dump({"prompts": prompts.tolist(), "cases": cases}, f)
+    print("wrote tiny_llama_int8_processors.json (%d cases)" % len(cases))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--scores-only" in sys.argv:
         make_scores_fixture()
+        return
+    if "--processors-only" in sys.argv:
+        make_processors_fixture()
         return
     if "--gtest-only" in sys.argv:
         with open(os.path.join(OUT, "ref_gtest_vectors.json"), "w") as f:
@@ -219,6 +250,7 @@ def main():
     d["ga_d"], d["ga_i"], d["ga_y"] = gd, gi, refapi.gather(gd, gi)
     np.savez(os.path.join(OUT, "ref_ops_random.npz"), **d)
     make_scores_fixture()
+    make_processors_fixture()
     print("done")
 
 
