@@ -164,7 +164,7 @@ CT2B200_API int ct2b200_attention_prefill(const void* qkv_d, void* k_cache_d, vo
                               int rotary_interleave, float scale, void* out_d, int dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
- * AWQ-INT4: ops::GemmAwq / GemvAwq / DequantizeAwq — include/ctranslate2/ops/awq/*.h,
+ * AWQ-INT4: ops::GemmAwq / GemvAwq / DequantizeAwq — include/ctranslate2/ops/awq/{gemm,gemv,dequantize}.h,
  * src/ops/awq/{gemm,gemv,dequantize}_gpu.cu.  x [m,k] f16 -> y [m,n] f16.
  * layout 1 = AWQ_GEMM: qweight int32 [k, n/8], scales f16 [k/g, n], qzeros int32 [k/g, n/8]
  * layout 2 = AWQ_GEMV: qweight int32 [n, k/8], scales f16 [n, sf_w], qzeros int32 [n, zeros_w]
