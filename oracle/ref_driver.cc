@@ -470,3 +470,32 @@ extern "C" int ref_generate_processors(void* handle, const int32_t* prompt_ids, 
     }
   });
 }
+
+// Greedy generate_batch over prompts of DIFFERENT lengths: prompt_ids [B,P] right-padded with -1.  return_scores = true.
+extern "C" int ref_generate_ragged(void* handle, const int32_t* prompt_ids, int B, int P, int max_len, int min_len,
+                                   int end_id, int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> prompts(B);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < P && prompt_ids[b * P + t] >= 0; ++t)
+        prompts[b].push_back(g->vocab->to_token(prompt_ids[b * P + t]));
+    GenerationOptions opt;
+    opt.beam_size = 1;
+    opt.sampling_topk = 1;
+    opt.max_length = max_len;
+    opt.min_length = min_len;
+    opt.include_prompt_in_result = false;
+    opt.return_scores = true;
+    opt.end_token = std::vector<size_t>{static_cast<size_t>(end_id)};
+    auto futures = g->generator->generate_batch_async(prompts, opt);
+    for (int b = 0; b < B; ++b) {
+      auto result = futures[b].get();
+      const auto& ids = result.sequences_ids.at(0);
+      out_lens[b] = static_cast<int32_t>(ids.size());
+      out_scores[b] = result.scores.at(0);
+      for (int t = 0; t < max_len + P; ++t)
+        out_ids[b * (max_len + P) + t] = t < (int)ids.size() ? (int32_t)ids[t] : -1;
+    }
+  });
+}

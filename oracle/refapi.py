@@ -124,6 +124,25 @@ def _generate_processors(self, prompts, max_length, min_length=0, end_id=2, repe
 RefGenerator.generate_processors = _generate_processors
 
 
+def _generate_ragged(self, prompts, max_length, min_length=0, end_id=2):
+    """(tokens, scores) of greedy generate_batch over prompts of different lengths (list of id lists)."""
+    B = len(prompts)
+    P = max(len(r) for r in prompts)
+    ids = np.full((B, P), -1, np.int32)
+    for b, r in enumerate(prompts):
+        ids[b, :len(r)] = r
+    width = max_length + P
+    out = np.zeros((B, width), np.int32)
+    lens = np.zeros(B, np.int32)
+    scores = np.zeros(B, np.float32)
+    _check(lib().ref_generate_ragged(ctypes.c_void_p(self.h), _p(ids), B, P, max_length, min_length, end_id, _p(out), _p(lens),
+                                     _p(scores)))
+    return [out[b, :lens[b]].tolist() for b in range(B)], scores
+
+
+RefGenerator.generate_ragged = _generate_ragged
+
+
 class RefTranslator:
     """The unmodified reference's Translator (encoder-decoder models) over token ids."""
 

@@ -178,10 +178,37 @@ def make_processors_fixture():
     print("wrote tiny_llama_int8_processors.json (%d cases)" % len(cases))
 
 
+def make_ragged_fixture():
+    """Greedy generate_batch of the unmodified reference over prompts of different lengths (include_prompt_in_result=false):
+    the shortest prompt decides how much is forwarded at once, the rest of each prompt is forced through the loop
+    (language_model.cc:217-238).  Also records the reference's behaviour when the shortest prompt is ONE token: it then keeps
+    return_prefix = true and returns the forced prompt tokens as part of the result."""
+    from oracle import refapi
+    assert refapi.available(), "build oracle/_ref first: make -f oracle/Makefile.ref -j8"
+    g = refapi.RefGenerator(os.path.join(OUT, "tiny_llama_int8"), "int8", 4)
+    batches = [[[5, 9, 11, 40, 7], [8, 3, 77], [100, 23, 45, 67]],
+               [[17, 4], [9, 9, 9, 9, 9, 9, 9], [150, 3, 8]],
+               [[5, 9, 11, 40, 7], [8], [100, 23]],
+               [[5], [8], [100]]]
+    cases = []
+    for prompts in batches:
+        for (mx, mn, end) in ((6, 6, 2), (6, 0, 164), (5, 2, 18), (8, 3, 143)):
+            toks, scores = g.generate_ragged(prompts, mx, mn, end)
+            cases.append({"prompts": prompts, "max_length": mx, "min_length": mn, "end_id": end, "tokens": toks,
+                          "scores": [float(x) for x in scores]})
+    g.close()
+    with open(os.path.join(OUT, "tiny_llama_int8_ragged.json"), "w") as f:
+        json.dump({"cases": cases}, f)
+    print("wrote tiny_llama_int8_ragged.json (%d cases)" % len(cases))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--scores-only" in sys.argv:
         make_scores_fixture()
+        return
+    if "--ragged-only" in sys.argv:
+        make_ragged_fixture()
         return
     if "--processors-only" in sys.argv:
         make_processors_fixture()
@@ -251,6 +278,7 @@ def main():
     np.savez(os.path.join(OUT, "ref_ops_random.npz"), **d)
     make_scores_fixture()
     make_processors_fixture()
+    make_ragged_fixture()
     print("done")
 
 
