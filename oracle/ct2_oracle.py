@@ -924,6 +924,23 @@ class LlamaOracle:
                            length_penalty, num_hypotheses, patience)
 
     # -- greedy search ----------------------------------------------------------------
+    def score(self, sequences: Sequence[Sequence[int]], offset: int = 0) -> List[List[float]]:
+        """Generator::score_batch.  src/scoring.cc:6-66: inputs = sequence[:-1], outputs = sequence[1:], one full-sequence
+        forward, LogSoftMax, Gather of the output ids; results start at `offset`; sequences of fewer than two tokens score
+        nothing (language_model.cc:136-140).  Rows are scored one by one here (padding never reaches a valid position of a
+        causal decoder, so the batch composition does not matter)."""
+        out: List[List[float]] = []
+        for seq in sequences:
+            seq = [int(t) for t in seq]
+            if len(seq) < 2:
+                out.append([])
+                continue
+            self.reset(1)
+            logits = self.forward(np.array([seq[:-1]]), 0)[0]                  # [T, V]
+            lp = softmax(logits, log=True)
+            out.append([float(lp[t, seq[t + 1]]) for t in range(offset, len(seq) - 1)])
+        return out
+
     def generate(self, prompts: np.ndarray, max_length: int, min_length: int = 0,
                  end_ids: Sequence[int] = (), return_scores: bool = False, length_penalty: float = 1.0,
                  repetition_penalty: float = 1.0, no_repeat_ngram_size: int = 0,

@@ -499,3 +499,25 @@ extern "C" int ref_generate_ragged(void* handle, const int32_t* prompt_ids, int 
     }
   });
 }
+
+// Generator::score_batch (ScoringOptions defaults except `offset`): ids [B,P] right-padded with -1; out_scores [B, P-1] holds
+// the log-probability of ids[b][t+1] given ids[b][:t+1] for t + 1 < length (0 elsewhere); out_lens[b] = number of scores.
+#include <ctranslate2/scoring.h>
+extern "C" int ref_score(void* handle, const int32_t* ids, int B, int P, int offset, float* out_scores, int32_t* out_lens) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> tokens(B);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < P && ids[b * P + t] >= 0; ++t)
+        tokens[b].push_back(g->vocab->to_token(ids[b * P + t]));
+    ScoringOptions opt;
+    opt.offset = offset;
+    auto futures = g->generator->score_batch_async(tokens, opt);
+    for (int b = 0; b < B; ++b) {
+      auto result = futures[b].get();
+      out_lens[b] = static_cast<int32_t>(result.tokens_score.size());
+      for (int t = 0; t < P - 1; ++t)
+        out_scores[b * (P - 1) + t] = t < out_lens[b] ? result.tokens_score[t] : 0.f;
+    }
+  });
+}

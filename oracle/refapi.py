@@ -143,6 +143,22 @@ def _generate_ragged(self, prompts, max_length, min_length=0, end_id=2):
 RefGenerator.generate_ragged = _generate_ragged
 
 
+def _score(self, sequences, offset=0):
+    """Generator::score_batch over id lists: per sequence the log-probabilities of tokens[offset + 1:] (list of float lists)."""
+    B = len(sequences)
+    P = max(2, max(len(r) for r in sequences))
+    ids = np.full((B, P), -1, np.int32)
+    for b, r in enumerate(sequences):
+        ids[b, :len(r)] = r
+    out = np.zeros((B, P - 1), np.float32)
+    lens = np.zeros(B, np.int32)
+    _check(lib().ref_score(ctypes.c_void_p(self.h), _p(ids), B, P, int(offset), _p(out), _p(lens)))
+    return [out[b, :lens[b]].tolist() for b in range(B)]
+
+
+RefGenerator.score = _score
+
+
 class RefTranslator:
     """The unmodified reference's Translator (encoder-decoder models) over token ids."""
 

@@ -309,6 +309,19 @@ def test_ragged_prompts_match_reference_fixture():
     assert regular >= 30 and quirk >= 4
 
 
+def test_score_batch_matches_reference_fixture():
+    """Generator::score_batch (src/scoring.cc:6-66): log-probability of every token given its prefix — ragged batch, sequences
+    too short to score, ScoringOptions::offset."""
+    fx = json.load(open(os.path.join(GOLDEN, "tiny_llama_int8_score_batch.json")))
+    w = O.DecoderWeights.from_dir(os.path.join(GOLDEN, "tiny_llama_int8"), "cpu")
+    m = O.LlamaOracle(w)
+    for c in fx["cases"]:
+        got = m.score(c["sequences"], c["offset"])
+        assert [len(x) for x in got] == [len(x) for x in c["log_probs"]]
+        for a, b in zip(got, c["log_probs"]):
+            np.testing.assert_allclose(a, b, rtol=0, atol=2e-5)
+
+
 def test_logits_processors_match_reference_fixture():
     """GenerationOptions::repetition_penalty / no_repeat_ngram_size / disable_unk / suppress_sequences through the greedy loop
     (decoding.cc:845-850, decoding_utils.cc): tokens identical, scores to fp32 round-off, incl. end tokens and min_length."""

@@ -202,10 +202,28 @@ def make_ragged_fixture():
     print("wrote tiny_llama_int8_ragged.json (%d cases)" % len(cases))
 
 
+def make_score_fixture():
+    """Generator::score_batch of the unmodified reference on the tiny model: log-probability of every token given its prefix,
+    ragged batch, sequences too short to score, ScoringOptions::offset."""
+    from oracle import refapi
+    assert refapi.available(), "build oracle/_ref first: make -f oracle/Makefile.ref -j8"
+    g = refapi.RefGenerator(os.path.join(OUT, "tiny_llama_int8"), "int8", 4)
+    rng = np.random.default_rng(11)
+    seqs = [[int(t) for t in rng.integers(3, 200, size=n)] for n in (12, 2, 1, 30, 7, 19)]
+    cases = [{"sequences": seqs, "offset": off, "log_probs": g.score(seqs, off)} for off in (0, 1, 5)]
+    g.close()
+    with open(os.path.join(OUT, "tiny_llama_int8_score_batch.json"), "w") as f:
+        json.dump({"cases": cases}, f)
+    print("wrote tiny_llama_int8_score_batch.json (%d cases)" % len(cases))
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--scores-only" in sys.argv:
         make_scores_fixture()
+        return
+    if "--score-only" in sys.argv:
+        make_score_fixture()
         return
     if "--ragged-only" in sys.argv:
         make_ragged_fixture()
@@ -279,6 +297,7 @@ def main():
     make_scores_fixture()
     make_processors_fixture()
     make_ragged_fixture()
+    make_score_fixture()
     print("done")
 
 
