@@ -34,12 +34,6 @@ def model_summary(model_path: str) -> dict:
     return json.loads(buf.value.decode())
 
 
-def _sub_batches(lengths: Sequence[int], max_batch_size: int) -> List[List[int]]:
-    """Indices of the sub-batches of an oversized request: sorted by decreasing length (stable), max_batch_size each."""
-    order = sorted(range(len(lengths)), key=lambda i: -lengths[i])
-    return [order[i:i + max_batch_size] for i in range(0, len(order), max_batch_size)]
-
-
 def _validate_ids(rows, vocab_size: int) -> None:
     """Token ids index the embedding table on the device (layers::Embeddings gathers rows, common.cc:64-81): the C-ABI takes
     them as given, so the range check lives here, where ids can come from the caller instead of the vocabulary."""
@@ -147,17 +141,6 @@ class Generator:
         if rows[0] and isinstance(rows[0][0], str):
             rows = [self._ids(r) for r in rows]
         _validate_ids(rows, self.vocab_size)
-        if len(rows) > self.max_batch_size:
-            # more prompts than the arena holds: run them in sub-batches, longest first so that similar lengths share a
-            # batch (the reference re-batches the same way, src/batch_reader.cc rebatch_input); rows do not interact
-            results: List[Optional[GenerationResult]] = [None] * len(rows)
-            for part in _sub_batches([len(r) for r in rows], self.max_batch_size):
-                done = self.generate_batch([rows[i] for i in part], max_length=max_length, min_length=min_length,
-                                           end_token=end_token, return_end_token=return_end_token,
-                                           return_scores=return_scores, length_penalty=length_penalty)
-                for i, r in zip(part, done):
-                    results[i] = r
-            return results
         B = len(rows)
         lens = np.array([len(r) for r in rows], np.int32)
         P = int(lens.max())

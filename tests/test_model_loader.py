@@ -70,26 +70,3 @@ def test_empty_batch_is_an_empty_result_without_touching_the_device():
     g = Generator.__new__(Generator)        # no model, no device: the empty batch must return before either is needed
     g._h = None
     assert g.generate_batch([]) == []
-
-
-def test_oversized_requests_are_split_into_sub_batches_and_put_back_in_order():
-    from ctranslate2_b200 import generator as G
-    assert G._sub_batches([3, 9, 1, 9, 5], 2) == [[1, 3], [4, 0], [2]]
-    g = G.Generator.__new__(G.Generator)        # no device: only the re-batching logic runs
-    g._h, g.max_batch_size, g.vocab_size, g._tokens = None, 2, 100, [str(i) for i in range(100)]
-    calls = []
-    real = G.Generator.generate_batch
-
-    def fake(self, rows, **kw):
-        if len(rows) > self.max_batch_size:
-            return real(self, rows, **kw)
-        calls.append([list(r) for r in rows])
-        return [G.GenerationResult([[str(r[0])]], [[r[0]]], []) for r in rows]
-
-    G.Generator.generate_batch = fake
-    try:
-        res = g.generate_batch([[1, 2, 3], [4] * 9, [5], [6] * 9, [7] * 5], max_length=4)
-    finally:
-        G.Generator.generate_batch = real
-    assert [r.sequences_ids[0][0] for r in res] == [1, 4, 5, 6, 7]            # original order
-    assert [len(c) for c in calls] == [2, 2, 1] and calls[0][0][0] == 4      # longest first, at most max_batch_size each
