@@ -90,6 +90,12 @@ def test_gtest_gemm_float_bias_residual_gelu():
     np.testing.assert_allclose(O.gemm_float(a, b, act=O.ACT_GELU), vec("GemmGELU", "expected", nth=2), **tol)
 
 
+def test_gtest_layer_norm():
+    """tests/ops_test.cc:880-895 — LayerNorm with gamma and beta (the encoder-decoder restatement uses it)."""
+    y = O.layer_norm(vec("LayerNorm", "x"), vec("LayerNorm", "gamma"), vec("LayerNorm", "beta"), 1e-5)
+    np.testing.assert_allclose(y, vec("LayerNorm", "expected"), atol=1e-5)
+
+
 def test_gtest_bias_add():
     """tests/ops_test.cc:1398-1432 — BiasAdd with the GELU epilogue, last axis and axis -2."""
     value, bias = static_vec("bias_value"), static_vec("bias_bias")

@@ -32,7 +32,7 @@ sys.path.insert(0, ROOT)
 
 GTESTS = {
     "ops_test.cc": ["GemmInt8", "TopK", "TopKVariableDepth", "TopKChangeK", "SoftMax", "LogSoftMax",
-                    "MaskedSoftMax", "RMSNorm", "QuantizeINT8", "QuantizeINT8ZeroRow", "Swish", "ReLU",
+                    "MaskedSoftMax", "RMSNorm", "LayerNorm", "QuantizeINT8", "QuantizeINT8ZeroRow", "Swish", "ReLU",
                     "GELU", "GELUTanh", "GELUSigmoid", "Gemm", "GemmBias", "GemmResidual", "GemmGELU",
                     "GatherData1D", "GatherData1DIndex2D", "GatherData2D", "GatherData3D",
                     "GatherData2DIndex2D", "BiasAddGELU", "BiasAddAxisGELU"],
