@@ -351,6 +351,19 @@ def test_logits_processors_match_reference_fixture():
     assert changed >= len(fx["cases"]) // 2          # the options really alter what is generated
 
 
+def test_gtest_penalize_previous_tokens():
+    """tests/primitives_test.cc:33-52 (PenalizePreviousTokens): penalty 1.2; row 0 saw token 2 twice (penalised once), row 1
+    saw tokens 1 and 2."""
+    scores = np.array([[0.6, 0.2, -1.2, 0.1], [0.3, 0.5, -1.3, 0.2]], np.float32)
+    expected = scores.copy()
+    expected[0, 2] *= np.float32(1.2)
+    expected[1, 1] /= np.float32(1.2)
+    expected[1, 2] *= np.float32(1.2)
+    for row, prev in zip(scores, ([2, 2], [1, 2])):
+        O.apply_logits_processors(row, prev, repetition_penalty=1.2)
+    np.testing.assert_array_equal(scores, expected)
+
+
 def test_logits_processor_rules():
     lowest = np.finfo(np.float32).min
     base = np.array([1.0, -2.0, 3.0, 0.5, -0.5], np.float32)
