@@ -562,7 +562,10 @@ class Seq2SeqOracle:
         if self.compute_type == "float32":
             w = self._float_w.get(prefix)
             if w is None:
-                w = (v[prefix + "/weight"].astype(f32) / v[prefix + "/weight_scale"].astype(f32)[:, None]).astype(f32)
+                w = v[prefix + "/weight"].astype(f32)
+                if prefix + "/weight_scale" in v:                      # int8: per-row scales; int16: one scale per layer
+                    sc = v[prefix + "/weight_scale"].astype(f32)
+                    w = (w / (sc[:, None] if sc.ndim == 1 else sc)).astype(f32)
                 self._float_w[prefix] = w
             return gemm_float(x.reshape(-1, x.shape[-1]), w, trans_b=True, bias=v.get(prefix + "/bias"),
                               residual=None if residual is None else residual.reshape(-1, w.shape[0]),
@@ -572,9 +575,10 @@ class Seq2SeqOracle:
 
     def _embed(self, scope, ids):
         v = self.v
-        rows = gather_rows(v[scope + "/embeddings/weight"], ids).astype(f32)
-        sc = gather_rows(v[scope + "/embeddings/weight_scale"], ids).astype(f32)
-        x = (rows / sc[..., None]).astype(f32)
+        x = gather_rows(v[scope + "/embeddings/weight"], ids).astype(f32)
+        if scope + "/embeddings/weight_scale" in v:              # Embeddings::operator(), common.cc:64-81
+            sc = v[scope + "/embeddings/weight_scale"].astype(f32)
+            x = (x / (gather_rows(sc, ids)[..., None] if sc.ndim == 1 else sc)).astype(f32)
         return (x * f32(math.sqrt(self.d))).astype(f32)          # build_embeddings_scale: sqrt(depth)
 
     def _ln(self, prefix, x):

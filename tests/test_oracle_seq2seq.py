@@ -87,6 +87,26 @@ def test_float32_translations_match_reference(beam, num_hyp, length_penalty):
 
 
 @needs_reference
+@pytest.mark.parametrize("variant", ["aren-transliteration", "aren-transliteration-i16", "aren-transliteration-i8"])
+def test_model_variants_translate_the_golden_sentence(variant):
+    """tests/translator_test.cc:53-96 (ModelVariantTest): the float32, int16 and int8 storage variants of the toy model all
+    translate the golden sentence to "a t z m o n"; computed in float32 the oracle agrees with the reference on every
+    hypothesis of a few random batches as well."""
+    model = os.path.join(os.path.dirname(MODEL), variant)
+    src, tgt = _vocab("source_vocabulary.txt"), _vocab("target_vocabulary.txt")
+    ids = [src.index(w) for w in ["آ", "ت", "ز", "م", "و", "ن"]]
+    oracle = O.Seq2SeqOracle.from_dir(model, compute_type="float32")
+    ref = refapi.RefTranslator(model, "float32")
+    assert [tgt[i] for i in oracle.translate([ids], beam_size=2)[0][0][0]] == ["a", "t", "z", "m", "o", "n"]
+    for srcs in [[ids]] + _random_sources(3, 4):
+        got = oracle.translate(srcs, beam_size=2, num_hypotheses=2, max_length=16)
+        want = ref.translate(srcs, beam_size=2, num_hypotheses=2, max_length=16)
+        for g, w in zip(got, want):
+            assert [h[0] for h in g] == [h[0] for h in w]
+            np.testing.assert_allclose([h[1] for h in g], [h[1] for h in w], atol=1e-4)
+
+
+@needs_reference
 def test_float32_min_length_and_encoder_memory():
     oracle = O.Seq2SeqOracle.from_dir(MODEL, compute_type="float32")
     ref = refapi.RefTranslator(MODEL, "float32")
