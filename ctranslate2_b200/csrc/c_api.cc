@@ -229,29 +229,34 @@ CT2B200_API int ct2b200_attention_prefill(const void* qkv, void* k_cache, void* 
 }
 
 CT2B200_API int ct2b200_awq_repack(const int32_t* qweight, const void* scales, const int32_t* qzeros, int layout, int group_size,
-                       int64_t n, int64_t k, int32_t* wp, void* sc, void* zr, void* stream) {
+                       int64_t n, int64_t k, int32_t* wp, void* sc, void* zr, void* sz, void* stream) {
   return guarded([&] {
     require_device();
     awq_repack(qweight, scales, qzeros, layout, group_size, n, k, wp, sc, zr, S(stream));
+    if (sz) {
+      AwqNative w{wp, sc, zr, n, k, group_size};
+      awq_build_group_major(w, sz, S(stream));
+    }
   });
 }
 
-CT2B200_API int ct2b200_dense_awq(const void* x, const int32_t* wp, const void* sc, const void* zr, int group_size,
-                      const void* bias, const void* residual, int act, int64_t m, int64_t n, int64_t k, void* y,
-                      void* scratch_nk, void* stream) {
+CT2B200_API int ct2b200_dense_awq(const void* x, const int32_t* wp, const void* sc, const void* zr, const void* sz,
+                      int group_size, const void* bias, const void* residual, int act, int64_t m, int64_t n, int64_t k,
+                      void* y, void* scratch_nk, void* stream) {
   return guarded([&] {
     require_device();
-    AwqNative w{wp, sc, zr, n, k, group_size};
+    AwqNative w{wp, sc, zr, n, k, group_size, sz};
     dense_awq(x, w, bias, residual, act, m, y, scratch_nk, S(stream));
   });
 }
 
 CT2B200_API int ct2b200_dense_awq_glu(const void* x, const int32_t* wp_gate, const void* sc_gate, const void* zr_gate,
-                          const int32_t* wp_up, const void* sc_up, const void* zr_up, int group_size, int act, int64_t m,
-                          int64_t n, int64_t k, void* h, void* scratch_nk, void* scratch_mn, void* stream) {
+                          const void* sz_gate, const int32_t* wp_up, const void* sc_up, const void* zr_up,
+                          const void* sz_up, int group_size, int act, int64_t m, int64_t n, int64_t k, void* h,
+                          void* scratch_nk, void* scratch_mn, void* stream) {
   return guarded([&] {
     require_device();
-    AwqNative g{wp_gate, sc_gate, zr_gate, n, k, group_size}, u{wp_up, sc_up, zr_up, n, k, group_size};
+    AwqNative g{wp_gate, sc_gate, zr_gate, n, k, group_size, sz_gate}, u{wp_up, sc_up, zr_up, n, k, group_size, sz_up};
     dense_awq_glu(x, g, u, act, m, h, scratch_nk, scratch_mn, S(stream));
   });
 }

@@ -1,18 +1,24 @@
-// awq_decode.cu — AWQ-INT4 weight-streaming GEMM of the decode step (m <= 64) on tcgen05.
+// awq_decode.cu — AWQ-INT4 weight-streaming GEMM of the decode step (m <= 64) on tcgen05, A operand in TENSOR MEMORY.
 //
 // Replaces ops::GemmAwq / ops::GemvAwq (+ ops::Sum over split-K planes, + bias / activation / Mul) of the reference
 // (src/ops/awq/gemm_gpu.cu, gemv_gpu.cu; dispatch src/layers/common.cc:402-438) by one kernel per Dense.
 //
-// Same plan as gemm_decode.cu (one tile per CTA, tile height and DSMEM split-K cluster chosen so that tiles x CS fills
-// the SMs in one wave, weights prefetched before griddepcontrol.wait), plus what 4-bit weights need:
-//   * the bytes that come from HBM are the packed nibbles: 4 KB per 128-row x 64-channel block.  They get their OWN deep
-//     ring (up to 24 blocks = 96 KB in flight per SM), decoupled from the shallow ring (4 stages) of dequantized fp16
-//     operand tiles (16 KB per block).  The first version staged both in one ring of 8 x 22 KB and never had more than
-//     32 KB of HBM traffic in flight per SM (8-22 % of the HBM peak).
-//   * 16 transform warps in 4 groups, each group converting its own K block (4 blocks in flight), turn nibbles into fp16 (q - z) * s (exact subtraction, one fp16 rounding: the arithmetic of the
-//     reference's dequantize_s4_to_fp16x2 + sub.f16x2 + fma.rn.f16x2) straight into the 128B-swizzled K-major UMMA
-//     operand layout; group scales / zeros are fetched one group ahead.
-//   * tcgen05.mma kind::f16, fp32 accumulators in TMEM; epilogue = gemm_decode_common.cuh (float arm).
+// Same plan as gemm_decode.cu (one tile per CTA, "swap AB": 128 output channels = the UMMA M side, activations = N side;
+// DSMEM split-K cluster chosen so that tiles x CS fills the SMs in one wave; weights prefetched before griddepcontrol.wait),
+// plus what 4-bit weights need:
+//   * the only bytes that come from HBM are the packed nibbles: 4 KB per 128-row x 64-channel block.  They get a deep TMA
+//     ring (up to 24 blocks in flight per SM); each ring slot also carries the block's 128 {scale, zero} pairs (512 B, one
+//     cp.async.bulk from the group-major array) and the activation block, so the transform warps never touch global memory.
+//     (Round 1 fetched the pairs with per-thread global loads inside the loop: ncu showed 64 % of the transform warps'
+//     samples on long_scoreboard and the kernel at 0.2 of the HBM peak.)
+//   * the dequantized fp16 operand never goes back to shared memory.  int4 -> fp16 at HBM speed is 5.8 TB/s of nibbles =
+//     23 TB/s of fp16, i.e. 82 B/clk/SM written + 82 B/clk/SM read by the tensor core: more than the 128 B/clk of the shared
+//     memory port.  Instead the thread that owns output channel r converts the 64 channels of its row in registers
+//     ((q - z) * s: exact subtraction, one fp16 rounding — the arithmetic of the reference's dequantize_s4_to_fp16x2 +
+//     sub.f16x2 + fma.rn.f16x2) and writes them with ONE tcgen05.st.32x32b.x32 into TMEM lane r, columns [32 x stage): the
+//     K-major A layout tcgen05.mma reads directly (cute::UMMA::tmem_frg, M = 128: lane = row, two fp16 per 32-bit column).
+//   * tcgen05.mma.kind::f16 with A from TMEM, B (activations) from 128B-swizzled smem, fp32 accumulators in TMEM;
+//     epilogue = gemm_decode_common.cuh (float arm).
 #include <map>
 #include <mutex>
 #include <tuple>
@@ -29,37 +35,62 @@ using namespace dec;
 
 constexpr int kThreads = 704;          // warp 0 TMA, warp 1 MMA, warps 2-5 epilogue, warps 6-21 transform
 constexpr int kDeqWarps = 16;          // 4 transform groups of 4 warps; group g owns the K blocks it % 4 == g, so four
-constexpr int kGroups = 4;             // blocks are converted CONCURRENTLY: one block's LDS -> lop3/hfma -> STS -> fence chain is
-constexpr int kGroupWarps = kDeqWarps / kGroups;   // latency-bound (~1 k cycles measured), not issue-bound
-constexpr int kBKh = 64;               // fp16 channels per K block (one 128-byte swizzle atom)
+constexpr int kGroups = 4;             // blocks are converted CONCURRENTLY (LDS -> lop3/hfma -> tcgen05.st is a latency chain)
+constexpr int kGroupWarps = kDeqWarps / kGroups;
+constexpr int kBKh = 64;               // fp16 channels per K block (one 128-byte swizzle atom of the activation operand)
 constexpr int kPacked = kTileM * kBKh / 2;      // 4096 bytes of nibbles per weight per block
-// Operand (dequantized fp16) ring: block `it` uses stage it % stages and is converted by group it % 4.  With one stage per
-// group a group cannot start block it + 4 before the MMAs of block it have retired (ncu: 24 % of the transform warps' samples
-// sit on that wait), so a single weight matrix gets two stages per group; the fused gate/up pair (32 KB per stage) keeps one.
-template <int NB> struct AStages { static constexpr int value = NB == 1 ? 2 * kGroups : kGroups; };
-constexpr int kMaxAStages = 2 * kGroups;
+constexpr int kPairs = 1024;                    // slot of the 128 {scale, zero} pairs (512 B) of a weight; 1 KB keeps the
+                                                // 128B-swizzled activation operand behind it 1024-byte aligned
+constexpr int kAColsPerBlock = kBKh / 2;        // 32 TMEM columns hold the 64 fp16 channels of a block
+// TMEM: accumulators in columns [0, 128), dequantized A stages above.  Block `it` uses A stage it % kAStages.
+constexpr int kAccColsMax = 128;
+template <int NB> struct AStages { static constexpr int value = (512 - kAccColsMax) / (NB * kAColsPerBlock); };   // 12 / 6
+constexpr int kMaxAStages = 12;
 constexpr int kMaxP = 24;
 
 struct AwqDecParams {
   DecParams d;
   int64_t k;
   int group;
-  int p_stages;                  // depth of the packed / activation ring
-  const __half* sc[2];           // [n, k/group] group scales (index 1: GLU "up")
-  const __half* zr[2];
-  const __half2* sz[2];          // optional {scale, zero} [k/group, n]: one coalesced 4-byte load per row and group
+  int p_stages;                  // depth of the packed / pairs / activation ring
+  const __half2* sz[2];          // {scale, zero} [k/group, n] (group-major): 512 contiguous bytes per tile and group
 };
 
 template <int BN, int NB>
 struct AwqDecSmem {
-  static constexpr int kP = NB * kPacked + BN * kSwizzleBytes;     // one block of the packed ring: nibbles + activations
-  static constexpr int kA = NB * kTileM * kSwizzleBytes;           // one dequantized operand stage
+  static constexpr int kP = NB * (kPacked + kPairs) + BN * kSwizzleBytes;   // one ring slot: nibbles | pairs | activations
   static constexpr int kCtrl = 1024;
   static size_t red_bytes(int cs) { return cs > 1 ? static_cast<size_t>(cs) * NB * (BN / 16) * ((16 + cs - 1) / cs) * kTileM * 4 : 0; }
   static size_t bytes(int p_stages, int cs) {
-    return static_cast<size_t>(AStages<NB>::value) * kA + static_cast<size_t>(p_stages) * kP + kCtrl + red_bytes(cs) + 1024;
+    return static_cast<size_t>(p_stages) * kP + kCtrl + red_bytes(cs) + 1024;
   }
 };
+
+// D[tmem] (+)= A[tmem] * B[smem descriptor]
+__device__ __forceinline__ void umma_ts_f16(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n.reg .pred p;\nsetp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n}\n"
+      ::"r"(tmem_d), "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate));
+}
+// 32 lanes x 32 columns: thread t of the warp writes r[0..31] to its lane, columns taddr.col + [0, 32)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,"
+      "%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31,%32};"
+      ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+        "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+        "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+        "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+// global -> shared bulk copy (bytes % 16 == 0, both addresses 16-byte aligned), completion on an mbarrier
+__device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
 
 template <int BN, int NB, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
@@ -68,21 +99,20 @@ __global__ void __launch_bounds__(kThreads, 1)
   using S = AwqDecSmem<BN, NB>;
   using T = __half;
   const DecParams& p = ap.d;
-  constexpr int kAccCols = BN * NB;
-  constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : 128;
+  constexpr uint32_t kTmemCols = 512;
   constexpr int cp16 = (16 + CS - 1) / CS;
   constexpr int cpr = (BN / 16) * cp16;
   constexpr int kAStages = AStages<NB>::value;
+  static_assert(BN * NB <= kAccColsMax, "accumulators exceed their TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  uint8_t* a_ring = smem;                                         // [kAStages][NB][128 x 128 B]
-  uint8_t* p_ring = a_ring + kAStages * S::kA;                    // [p_stages][nibbles NB x 4 KB | x BN x 128 B]
+  uint8_t* p_ring = smem;                                         // [p_stages][nibbles NB x 4 KB | pairs NB x 512 B | x BN x 128 B]
   const int PD = ap.p_stages;
   uint8_t* ctrl = p_ring + static_cast<size_t>(PD) * S::kP;
   uint64_t* p_full = reinterpret_cast<uint64_t*>(ctrl);           // [kMaxP] TMA landed
   uint64_t* p_free = p_full + kMaxP;                              // [kMaxP] transform warps + the MMA commit
-  uint64_t* a_ready = p_free + kMaxP;                             // [kAStages] operand tile written (all transform warps)
+  uint64_t* a_ready = p_free + kMaxP;                             // [kAStages] A stage written to TMEM (the group's warps)
   uint64_t* a_free = a_ready + kMaxAStages;                       // [kAStages] MMAs that read it retired
   uint64_t* acc_bar = a_free + kMaxAStages;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
@@ -117,16 +147,25 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (CS > 1) cluster_arrive();
 
   if (warp == 0) {
-    // ===== TMA producer: packed nibbles (+ second weight) and the activation block =====
+    // ===== TMA producer: packed nibbles, {scale, zero} pairs (both weights are constants: issued before the grid
+    // dependency resolves) and the activation block =====
     if (lane == 0) {
-      const uint32_t tx = static_cast<uint32_t>(NB * p.tile_rows * (kBKh / 2) + BN * kSwizzleBytes);
+      const int rows_here = static_cast<int>(min(static_cast<int64_t>(p.tile_rows), p.n - a0));
+      const uint32_t pair_bytes = static_cast<uint32_t>(rows_here) * 4u;
+      const uint32_t tx = static_cast<uint32_t>(NB * p.tile_rows * (kBKh / 2)) + NB * pair_bytes + BN * kSwizzleBytes;
       auto weights = [&](int s, int kb) {
         uint8_t* st = p_ring + static_cast<size_t>(s) * S::kP;
+        const int64_t g = (static_cast<int64_t>(kb) * kBKh) / ap.group;
         tma_load_2d(st, &tm_w, p_full + s, kb * (kBKh / 2), a0, kEvictFirst);
-        if (NB == 2) tma_load_2d(st + kPacked, &tm_w2, p_full + s, kb * (kBKh / 2), a0, kEvictFirst);
+        bulk_load(st + NB * kPacked, ap.sz[0] + g * p.n + a0, pair_bytes, p_full + s);
+        if (NB == 2) {
+          tma_load_2d(st + kPacked, &tm_w2, p_full + s, kb * (kBKh / 2), a0, kEvictFirst);
+          bulk_load(st + NB * kPacked + kPairs, ap.sz[1] + g * p.n + a0, pair_bytes, p_full + s);
+        }
       };
       auto acts = [&](int s, int kb) {
-        tma_load_2d(p_ring + static_cast<size_t>(s) * S::kP + NB * kPacked, &tm_x, p_full + s, kb * kBKh, 0, kEvictLast);
+        tma_load_2d(p_ring + static_cast<size_t>(s) * S::kP + NB * (kPacked + kPairs), &tm_x, p_full + s, kb * kBKh, 0,
+                    kEvictLast);
       };
       const int pre = min(PD, nkb);
 #pragma unroll 1
@@ -154,81 +193,67 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int it = 0; it < nkb; ++it) {
         const int sp = it % PD, sa = it % kAStages;
         mbar_wait(p_full + sp, (it / PD) & 1);                    // activations of this block landed
-        mbar_wait(a_ready + sa, (it / kAStages) & 1);             // weights dequantized
+        mbar_wait(a_ready + sa, (it / kAStages) & 1);             // weights dequantized into TMEM
         tc_fence_after();
-        const uint32_t abase = smem_u32(a_ring + sa * S::kA);
-        const uint64_t db = make_smem_desc(smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * kPacked));
+        const uint32_t ta = tmem_base + kAccColsMax + sa * (NB * kAColsPerBlock);
+        const uint64_t db = make_smem_desc(smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * (kPacked + kPairs)));
 #pragma unroll
-        for (int w = 0; w < NB; ++w) {
-          const uint64_t da = make_smem_desc(abase + w * kTileM * kSwizzleBytes);
+        for (int w = 0; w < NB; ++w)
 #pragma unroll
-          for (int k = 0; k < kBKh / 16; ++k)
-            umma<1>(tmem_base + w * BN, da + 2 * k, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        }
+          for (int k = 0; k < kBKh / 16; ++k)                     // K = 16 per instruction = 8 TMEM columns of A
+            umma_ts_f16(tmem_base + w * BN, ta + w * kAColsPerBlock + k * 8, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
         umma_commit(a_free + sa);
         umma_commit(p_free + sp);
       }
       umma_commit(acc_bar);
     }
   } else if (warp >= 6) {
-    // ===== transform warps: nibbles -> fp16 (q - z) * s into the swizzled operand tile =====
-    // thread -> (transform group, tile row): a thread converts the 64 channels (8 packed words) of its row
-    const int d = threadIdx.x - 192;                   // 0..511
-    const int grp = d >> 7;
-    const int r = d & 127;
-    const int64_t ng = ap.k / ap.group;
-    const int64_t row = static_cast<int64_t>(a0) + r;
-    const bool row_ok = r < p.tile_rows && row < p.n;
-    __half zc[NB], sc_[NB], zn[NB], sn_[NB];
-    auto fetch = [&](int it, __half (&z)[NB], __half (&sc)[NB]) {
-      const int64_t g = (static_cast<int64_t>(kb_lo + it) * kBKh) / ap.group;
-#pragma unroll
-      for (int w = 0; w < NB; ++w) {
-        const bool ok = row_ok && it < nkb && g < ng;
-        if (ap.sz[w] != nullptr) {
-          // group-major pairs: the 32 rows of a warp read 128 contiguous bytes (the row-major arrays cost one 32-byte
-          // sector per row and per array, i.e. 16x the traffic of the packed weights they belong to)
-          const __half2 v = ok ? ap.sz[w][g * p.n + row] : __float2half2_rn(0.f);
-          sc[w] = __low2half(v);
-          z[w] = __high2half(v);
-        } else {
-          z[w] = ok ? ap.zr[w][row * ng + g] : __float2half(0.f);
-          sc[w] = ok ? ap.sc[w][row * ng + g] : __float2half(0.f);
-        }
-      }
-    };
-    __half z2[NB], s2n[NB];
-    fetch(grp, zc, sc_);
-    fetch(grp + kGroups, zn, sn_);
+    // ===== transform warps: nibbles -> fp16 (q - z) * s, registers -> TMEM =====
+    // thread -> (transform group, tile row).  A warp may only touch TMEM lanes [32 * (warp % 4), +32): the row quadrant of a
+    // warp is warp % 4 (any bijection inside the group of four consecutive warps works).
+    const int grp = (warp - 6) >> 2;
+    const int quad = warp & 3;
+    const int r = quad * 32 + lane;
+    const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
 #pragma unroll 1
     for (int it = grp; it < nkb; it += kGroups) {
       const int sp = it % PD, sa = it % kAStages;
-      fetch(it + 2 * kGroups, z2, s2n);                // {scale, zero} two blocks ahead: covers the L2 latency
       mbar_wait(p_full + sp, (it / PD) & 1);
-      if (it >= kAStages) mbar_wait(a_free + sa, ((it / kAStages) & 1) ^ 1);
       const uint8_t* pk = p_ring + static_cast<size_t>(sp) * S::kP;
-      uint8_t* at = a_ring + sa * S::kA;
+      const uint32_t ta = tmem_base + lane_base + kAccColsMax + sa * (NB * kAColsPerBlock);
 #pragma unroll
       for (int w = 0; w < NB; ++w) {
-        const __half2 zb = __half2half2(__hadd(__float2half(1024.f), zc[w]));
-        const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), zc[w])));
-        const __half2 s2 = __half2half2(sc_[w]);
+        uint32_t v[32];
+        const __half2 sz = *reinterpret_cast<const __half2*>(pk + NB * kPacked + w * kPairs + r * 4);
+        const __half sc = __low2half(sz), zp = __high2half(sz);
+        const __half2 zb = __half2half2(__hadd(__float2half(1024.f), zp));
+        const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), zp)));
+        const __half2 s2 = __half2half2(sc);
         const uint4 w0 = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2));
         const uint4 w1 = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2) + 16);
         const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
-        uint8_t* arow = at + w * kTileM * kSwizzleBytes + r * kSwizzleBytes;
 #pragma unroll
-        for (int c = 0; c < 8; ++c)                    // chunk c of the row lives at chunk c ^ (r & 7) under SWIZZLE_128B
-          *reinterpret_cast<uint4*>(arow + ((c ^ (r & 7)) << 4)) = awq_dequant_word(words[c], zb, zt, s2);
+        for (int c = 0; c < 8; ++c) {                  // word c = channels 8c .. 8c+7 = TMEM columns 4c .. 4c+3
+          const uint4 d = awq_dequant_word(words[c], zb, zt, s2);
+          v[4 * c + 0] = d.x;
+          v[4 * c + 1] = d.y;
+          v[4 * c + 2] = d.z;
+          v[4 * c + 3] = d.w;
+        }
+        // the A stage is free once the MMAs of block it - kAStages have retired (waited for AFTER the first conversion)
+        if (w == 0 && it >= kAStages) {
+          mbar_wait(a_free + sa, ((it / kAStages) & 1) ^ 1);
+          tc_fence_after();
+        }
+        tmem_st32(ta + w * kAColsPerBlock, v);
       }
-      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy stores -> visible to tcgen05
+      tmem_st_wait();
+      tc_fence_before();
       __syncwarp();
       if (lane == 0) {
         mbar_arrive(a_ready + sa);
         mbar_arrive(p_free + sp);
       }
-#pragma unroll
-      for (int w = 0; w < NB; ++w) { zc[w] = zn[w]; sc_[w] = sn_[w]; zn[w] = z2[w]; sn_[w] = s2n[w]; }
     }
   } else {
     // ===== epilogue warps (2..5): thread = output channel =====
@@ -338,7 +363,7 @@ template <int BN, int NB>
 int p_stages_for(int cs, int nkb) {
   using S = AwqDecSmem<BN, NB>;
   const size_t cap = 220 * 1024;
-  const size_t fixed = static_cast<size_t>(AStages<NB>::value) * S::kA + S::kCtrl + S::red_bytes(cs) + 1024;
+  const size_t fixed = S::kCtrl + S::red_bytes(cs) + 1024;
   if (fixed + 2 * S::kP > cap) return 0;
   int st = static_cast<int>((cap - fixed) / S::kP);
   st = std::min(st, kMaxP);
@@ -462,10 +487,6 @@ bool run(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, AwqD
   p.k = w.k;
   p.group = w.group;
   p.p_stages = plan.p_stages;
-  p.sc[0] = static_cast<const __half*>(w.sc);
-  p.zr[0] = static_cast<const __half*>(w.zr);
-  p.sc[1] = static_cast<const __half*>(w2 ? w2->sc : w.sc);
-  p.zr[1] = static_cast<const __half*>(w2 ? w2->zr : w.zr);
   p.sz[0] = static_cast<const __half2*>(w.sz);
   p.sz[1] = static_cast<const __half2*>(w2 ? w2->sz : w.sz);
   const CUtensorMap tmx = make_operand_map(x, m, w.k, 2, 1, BN);
@@ -499,7 +520,7 @@ bool glu_enabled() { return env_int("CT2B200_AWQ_DECODE_GLU", env_int("CT2B200_A
 // false = shape not covered (more tiles than one wave holds, group not a multiple of 64): caller uses gemm_awq_tc_kernel
 bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const void* residual, int act, int64_t m, void* y,
                       cudaStream_t st) {
-  if (!enabled() || m < 1 || m > 64 || w.group % kBKh != 0 || w.k % kBKh != 0) return false;
+  if (!enabled() || m < 1 || m > 64 || w.group % kBKh != 0 || w.k % kBKh != 0 || w.sz == nullptr || w.n % 8 != 0) return false;
   AwqDecParams p{};
   p.d.bias = bias;
   p.d.residual = residual;
@@ -510,7 +531,9 @@ bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const
 }
 
 bool dense_awq_glu_decode(const void* x, const AwqNative& wg, const AwqNative& wu, int act, int64_t m, void* h, cudaStream_t st) {
-  if (!glu_enabled() || m < 1 || m > 64 || wg.group % kBKh != 0 || wg.k % kBKh != 0 || wg.group != wu.group) return false;
+  if (!glu_enabled() || m < 1 || m > 64 || wg.group % kBKh != 0 || wg.k % kBKh != 0 || wg.group != wu.group ||
+      wg.sz == nullptr || wu.sz == nullptr || wg.n % 8 != 0)
+    return false;
   AwqDecParams p{};
   p.d.y = h;
   p.d.act = act;

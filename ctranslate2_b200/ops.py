@@ -300,8 +300,9 @@ class AwqWeight:
         self.wp = torch.empty((self.n, self.k // 8), dtype=torch.int32, device=dev)
         self.sc = torch.empty((self.n, ng), dtype=torch.float16, device=dev)
         self.zr = torch.empty((self.n, ng), dtype=torch.float16, device=dev)
+        self.sz = torch.empty((ng, self.n, 2), dtype=torch.float16, device=dev)     # {scale, zero} pairs, group-major
         check(lib().ct2b200_awq_repack(_p(qweight), _p(scales), _p(qzeros), layout, group_size, ctypes.c_int64(self.n),
-                                       ctypes.c_int64(self.k), _p(self.wp), _p(self.sc), _p(self.zr), _stream()))
+                                       ctypes.c_int64(self.k), _p(self.wp), _p(self.sc), _p(self.zr), _p(self.sz), _stream()))
 
 
 def dequantize_awq(qweight, scales, qzeros, layout: int, group_size: int):
@@ -324,7 +325,7 @@ def dense_awq(x, w: AwqWeight, bias=None, residual=None, activation_type=None):
     y = torch.empty((m, w.n), dtype=torch.float16, device=x.device)
     scratch = torch.empty((w.n, w.k), dtype=torch.float16, device=x.device) if m > 64 else None
     act = -1 if activation_type is None else activation_type
-    check(lib().ct2b200_dense_awq(_p(x), _p(w.wp), _p(w.sc), _p(w.zr), w.group_size, _p(bias), _p(residual), act,
+    check(lib().ct2b200_dense_awq(_p(x), _p(w.wp), _p(w.sc), _p(w.zr), _p(w.sz), w.group_size, _p(bias), _p(residual), act,
                                   ctypes.c_int64(m), ctypes.c_int64(w.n), ctypes.c_int64(w.k), _p(y), _p(scratch),
                                   _stream()))
     return y
@@ -336,7 +337,7 @@ def dense_awq_glu(x, wg: AwqWeight, wu: AwqWeight, activation_type=ActivationTyp
     h = torch.empty((m, wg.n), dtype=torch.float16, device=x.device)
     s1 = torch.empty((wg.n, wg.k), dtype=torch.float16, device=x.device) if m > 64 else None
     s2 = torch.empty((m, wg.n), dtype=torch.float16, device=x.device) if m > 64 else None
-    check(lib().ct2b200_dense_awq_glu(_p(x), _p(wg.wp), _p(wg.sc), _p(wg.zr), _p(wu.wp), _p(wu.sc), _p(wu.zr),
+    check(lib().ct2b200_dense_awq_glu(_p(x), _p(wg.wp), _p(wg.sc), _p(wg.zr), _p(wg.sz), _p(wu.wp), _p(wu.sc), _p(wu.zr), _p(wu.sz),
                                       wg.group_size, activation_type, ctypes.c_int64(m), ctypes.c_int64(wg.n),
                                       ctypes.c_int64(wg.k), _p(h), _p(s1), _p(s2), _stream()))
     return h

@@ -170,20 +170,25 @@ CT2B200_API int ct2b200_attention_prefill(const void* qkv_d, void* k_cache_d, vo
  * layout 2 = AWQ_GEMV: qweight int32 [n, k/8], scales f16 [n, sf_w], qzeros int32 [n, zeros_w]
  * ------------------------------------------------------------------------------------------- */
 /* One-time repack (Dense ctor / model load) of either reference layout into the native K-major layout:
- * wp int32 [n, k/8] (channel 8w+i of row n in nibble {0,4,1,5,2,6,3,7}[i] of word w), sc f16 [n, k/g], zr f16 [n, k/g]. */
+ * wp int32 [n, k/8] (channel 8w+i of row n in nibble {0,4,1,5,2,6,3,7}[i] of word w), sc f16 [n, k/g], zr f16 [n, k/g],
+ * and (sz_d non-NULL) the same {scale, zero} values as f16 pairs in group-major order sz [k/g, n][2]: the decode kernel
+ * (m <= 64) stages the 128 pairs of a tile and group with one bulk copy and needs it; NULL = not produced. */
 CT2B200_API int ct2b200_awq_repack(const int32_t* qweight_d, const void* scales_d, const int32_t* qzeros_d, int layout,
-                       int group_size, int64_t n, int64_t k, int32_t* wp_d, void* sc_d, void* zr_d, void* stream);
+                       int group_size, int64_t n, int64_t k, int32_t* wp_d, void* sc_d, void* zr_d, void* sz_d,
+                       void* stream);
 
 /* ops::GemmAwq / GemvAwq + apply_bias_and_activation — src/ops/awq/gemm.cc:8-33, gemv.cc:9-37, on the native layout:
- * y = act(x . deq(W)^T + bias) + residual.  m <= 64: fused dequantize + tcgen05 GEMM.  m > 64 (the reference's
+ * y = act(x . deq(W)^T + bias) + residual.  m <= 64: fused dequantize + tcgen05 GEMM (weight-streaming kernel with the
+ * operand in tensor memory when sz_d is given, the general kernel otherwise).  m > 64 (the reference's
  * DequantizeAwq + cuBLAS arm, src/layers/common.cc:409-420): needs scratch_nk_d, an fp16 [n,k] buffer. */
-CT2B200_API int ct2b200_dense_awq(const void* x_d, const int32_t* wp_d, const void* sc_d, const void* zr_d, int group_size,
-                      const void* bias_d, const void* residual_d, int act, int64_t m, int64_t n, int64_t k, void* y_d,
-                      void* scratch_nk_d, void* stream);
+CT2B200_API int ct2b200_dense_awq(const void* x_d, const int32_t* wp_d, const void* sc_d, const void* zr_d, const void* sz_d,
+                      int group_size, const void* bias_d, const void* residual_d, int act, int64_t m, int64_t n, int64_t k,
+                      void* y_d, void* scratch_nk_d, void* stream);
 /* gate/up pair of the gated FFN in one pass: h = act(x . deq(Wg)^T) * (x . deq(Wu)^T).  m > 64 also needs scratch_mn_d. */
 CT2B200_API int ct2b200_dense_awq_glu(const void* x_d, const int32_t* wp_gate_d, const void* sc_gate_d, const void* zr_gate_d,
-                          const int32_t* wp_up_d, const void* sc_up_d, const void* zr_up_d, int group_size, int act,
-                          int64_t m, int64_t n, int64_t k, void* h_d, void* scratch_nk_d, void* scratch_mn_d, void* stream);
+                          const void* sz_gate_d, const int32_t* wp_up_d, const void* sc_up_d, const void* zr_up_d,
+                          const void* sz_up_d, int group_size, int act, int64_t m, int64_t n, int64_t k, void* h_d,
+                          void* scratch_nk_d, void* scratch_mn_d, void* stream);
 /* ops::DequantizeAwq — src/ops/awq/dequantize_gpu.cu:8-62: reference layout (1 or 2) -> W f16 [k, n]. */
 CT2B200_API int ct2b200_dequantize_awq(const int32_t* qweight_d, const void* scales_d, const int32_t* qzeros_d, int layout,
                            int group_size, int64_t n, int64_t k, void* w_d /* f16 [k,n] */, void* stream);

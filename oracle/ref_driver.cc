@@ -8,6 +8,12 @@
 //   ctranslate2::Generator::forward_batch_async    include/ctranslate2/generator.h:30-32
 //   ctranslate2::ops::{Quantize,Gemm,Dequantize,RMSNorm,Rotary,SoftMax,TopK,Gather}
 // Only `tests/`, `__graft_entry__.smoke()` and bench.py's CPU legs may load this.
+//
+// Built twice: against oracle/_ref (CPU-only reference) and, with -DREF_DRIVER_CUDA, against
+// oracle/_ref_cuda (the reference WITH its CUDA backend, oracle/Makefile.ref_cuda).  In the second
+// build `ref_set_device(1, flash)` makes the generator / translator entry points load the model on
+// Device::CUDA, and the `ref_cuda_*` entry points run the reference's GPU-only ops (AWQ) and its
+// CUDA specialisations of the row ops on device buffers staged from host arrays.
 
 #include <cstdint>
 #include <cstring>
@@ -26,6 +32,8 @@ using namespace ctranslate2;
 
 namespace {
   thread_local std::string g_error;
+  Device g_device = Device::CPU;
+  bool g_flash_attention = false;
 
   struct RefGenerator {
     std::shared_ptr<const models::Model> model;
@@ -53,12 +61,28 @@ extern "C" {
 
 const char* ref_last_error() { return g_error.c_str(); }
 
+// 0 = Device::CPU (default), 1 = Device::CUDA (only in the -DREF_DRIVER_CUDA build); flash_attention selects
+// layers::FlashMultiHeadAttention (models::ModelLoader::use_flash_attention, transformer.cc:157-169)
+int ref_set_device(int cuda, int flash_attention) {
+  return guarded([&] {
+#ifndef REF_DRIVER_CUDA
+    if (cuda) throw std::runtime_error("this driver was built against the CPU-only reference");
+#endif
+    g_device = cuda ? Device::CUDA : Device::CPU;
+    g_flash_attention = flash_attention != 0;
+  });
+}
+
 void* ref_generator_open(const char* model_dir, const char* compute_type, int intra_threads) {
   RefGenerator* g = nullptr;
   int rc = guarded([&] {
     auto holder = std::make_unique<RefGenerator>();
-    holder->model = models::Model::load(model_dir, Device::CPU, 0,
-                                        str_to_compute_type(compute_type));
+    models::ModelLoader loader(model_dir);
+    loader.device = g_device;
+    loader.device_indices = {0};
+    loader.compute_type = str_to_compute_type(compute_type);
+    loader.use_flash_attention = g_flash_attention;
+    holder->model = loader.load().at(0);
     ReplicaPoolConfig config;
     config.num_threads_per_replica = intra_threads > 0 ? intra_threads : 0;
     holder->generator = std::make_unique<Generator>(holder->model, config);
@@ -185,7 +209,11 @@ void* ref_translator_open(const char* model_dir, const char* compute_type, int i
   RefTranslator* t = nullptr;
   int rc = guarded([&] {
     auto holder = std::make_unique<RefTranslator>();
-    holder->model = models::Model::load(model_dir, Device::CPU, 0, str_to_compute_type(compute_type));
+    models::ModelLoader loader(model_dir);
+    loader.device = g_device;
+    loader.device_indices = {0};
+    loader.compute_type = str_to_compute_type(compute_type);
+    holder->model = loader.load().at(0);
     ReplicaPoolConfig config;
     config.num_threads_per_replica = intra_threads > 0 ? intra_threads : 0;
     holder->translator = std::make_unique<Translator>(holder->model, config);
@@ -521,3 +549,126 @@ extern "C" int ref_score(void* handle, const int32_t* ids, int B, int P, int off
     }
   });
 }
+
+#ifdef REF_DRIVER_CUDA
+// ---- the reference's CUDA specialisations, run on device buffers staged from host arrays ------------------------------
+// (GPU-side oracle: tools/make_golden_cuda.py turns their outputs into fixtures under tests/golden/, tests compare live
+// when the library is present on the GPU box.)
+#include <ctranslate2/ops/awq/gemm.h>
+#include <ctranslate2/ops/awq/gemv.h>
+#include <ctranslate2/ops/awq/dequantize_awq.h>
+#include <cuda_runtime.h>
+#include <chrono>
+
+namespace {
+  StorageView to_cuda(const void* host, Shape shape, DataType dt) {
+    StorageView h(dt, Device::CPU);
+    h.resize(shape);
+    std::memcpy(h.buffer(), host, h.size() * h.item_size());
+    return h.to(Device::CUDA);
+  }
+  void to_host(const StorageView& d, void* out) {
+    StorageView h = d.to(Device::CPU);
+    std::memcpy(out, h.buffer(), h.size() * h.item_size());
+  }
+}
+
+extern "C" {
+
+// ops::GemmAwq (src/ops/awq/gemm.cc:8-33): x f16 [m,k], qweight int32 [k, n/8], scales f16 [k/g, n], qzeros int32 [k/g, n/8]
+// -> y f16 [m, n]
+int ref_cuda_gemm_awq(const uint16_t* x, const int32_t* qweight, const uint16_t* scales, const int32_t* qzeros, int m, int n,
+                      int k, int group, uint16_t* y) {
+  return guarded([&] {
+    StorageView X = to_cuda(x, {m, k}, DataType::FLOAT16);
+    StorageView W = to_cuda(qweight, {k, n / 8}, DataType::INT32);
+    StorageView S = to_cuda(scales, {k / group, n}, DataType::FLOAT16);
+    StorageView Z = to_cuda(qzeros, {k / group, n / 8}, DataType::INT32);
+    StorageView Y(DataType::FLOAT16, Device::CUDA);
+    ops::GemmAwq op(1.f, 0.f, false, false, false, false, nullptr);
+    op(X, W, S, Z, Y);
+    to_host(Y, y);
+  });
+}
+
+// ops::GemvAwq (src/ops/awq/gemv.cc:9-37; m <= 8: gemv kernel, else gemv2): x f16 [m,k], qweight int32 [n, k/8],
+// scales f16 [n, sw], qzeros int32 [n, zw] (padded widths of the AWQ_GEMV layout) -> y f16 [m, n]
+int ref_cuda_gemv_awq(const uint16_t* x, const int32_t* qweight, const uint16_t* scales, const int32_t* qzeros, int m, int n,
+                      int k, int sw, int zw, uint16_t* y) {
+  return guarded([&] {
+    StorageView X = to_cuda(x, {m, k}, DataType::FLOAT16);
+    StorageView W = to_cuda(qweight, {n, k / 8}, DataType::INT32);
+    StorageView S = to_cuda(scales, {n, sw}, DataType::FLOAT16);
+    StorageView Z = to_cuda(qzeros, {n, zw}, DataType::INT32);
+    StorageView Y(DataType::FLOAT16, Device::CUDA);
+    ops::GemvAwq op(1.f, 0.f, false, false, false, false, nullptr);
+    op(X, W, S, Z, Y);
+    to_host(Y, y);
+  });
+}
+
+// ops::DequantizeAwq (src/ops/awq/dequantize.cc): qweight int32 [k, n/8] (AWQ_GEMM layout) -> f16 [k, n]
+int ref_cuda_dequantize_awq(const int32_t* qweight, const uint16_t* scales, const int32_t* qzeros, int n, int k, int group,
+                            uint16_t* w) {
+  return guarded([&] {
+    StorageView W = to_cuda(qweight, {k, n / 8}, DataType::INT32);
+    StorageView S = to_cuda(scales, {k / group, n}, DataType::FLOAT16);
+    StorageView Z = to_cuda(qzeros, {k / group, n / 8}, DataType::INT32);
+    StorageView Y(DataType::FLOAT16, Device::CUDA);
+    ops::DequantizeAwq()(W, S, Z, Y);
+    to_host(Y, w);
+  });
+}
+
+// layers::Dense INT8 arm on the GPU (common.cc:353-401): Quantize -> cublasGemmEx s8 -> Dequantize(+bias, act), x f16 [m,k]
+int ref_cuda_dense_s8(const uint16_t* x, const int8_t* w, const float* w_scale, int act, int m, int n, int k, uint16_t* y) {
+  return guarded([&] {
+    StorageView X = to_cuda(x, {m, k}, DataType::FLOAT16);
+    StorageView W = to_cuda(w, {n, k}, DataType::INT8);
+    StorageView WS = to_cuda(w_scale, {n}, DataType::FLOAT32);
+    StorageView Q(DataType::INT8, Device::CUDA), QS(DataType::FLOAT32, Device::CUDA), C(DataType::INT32, Device::CUDA),
+        Y(DataType::FLOAT16, Device::CUDA);
+    ops::Quantize(ops::Quantize::ScaleType::GLOBAL, false, true)(X, Q, QS);
+    ops::Gemm(1.f, 0.f, false, true)(Q, W, C);
+    ops::ActivationType at = static_cast<ops::ActivationType>(act < 0 ? 0 : act);
+    ops::Dequantize(act >= 0 ? &at : nullptr)(C, QS, WS, false, true, Y, nullptr);
+    to_host(Y, y);
+  });
+}
+
+// Wall time (seconds) of one greedy generate_batch of exactly max_len tokens per row on the current device, after a
+// cudaDeviceSynchronize on both sides; out_ids as ref_generate.
+int ref_generate_timed(void* handle, const int32_t* prompt_ids, int B, int P, int max_len, int end_id, int32_t* out_ids,
+                       double* seconds) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> prompts(B);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < P; ++t)
+        prompts[b].push_back(g->vocab->to_token(prompt_ids[b * P + t]));
+    GenerationOptions opt;
+    opt.beam_size = 1;
+    opt.sampling_topk = 1;
+    opt.max_length = max_len;
+    opt.min_length = max_len;
+    opt.include_prompt_in_result = false;
+    opt.return_scores = false;
+    opt.end_token = std::vector<size_t>{static_cast<size_t>(end_id)};
+    cudaDeviceSynchronize();
+    const auto t0 = std::chrono::steady_clock::now();
+    auto futures = g->generator->generate_batch_async(prompts, opt, /*max_batch_size=*/0);
+    std::vector<GenerationResult> results;
+    for (auto& f : futures) results.push_back(f.get());
+    cudaDeviceSynchronize();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    if (out_ids)
+      for (int b = 0; b < B; ++b) {
+        const auto& ids = results[b].sequences_ids.at(0);
+        for (int t = 0; t < max_len; ++t)
+          out_ids[b * max_len + t] = t < (int)ids.size() ? (int32_t)ids[t] : -1;
+      }
+  });
+}
+
+}  // extern "C"
+#endif  // REF_DRIVER_CUDA

@@ -1,8 +1,12 @@
-"""ctypes binding of oracle/_ref/libct2ref_driver.so (the UNMODIFIED reference, CPU build).
+"""ctypes binding of oracle/_ref/libct2ref_driver.so (the UNMODIFIED reference, CPU build) and of
+oracle/_ref_cuda/libct2ref_cuda_driver.so (the UNMODIFIED reference WITH its CUDA backend: cuBLAS GEMM,
+its own AWQ / FlashAttention-2 kernels, compiled for sm_100 by oracle/Makefile.ref_cuda).
 
-TEST INFRASTRUCTURE: only tests/, tools/make_golden.py, __graft_entry__.smoke() and bench.py's
-CPU legs import this.  `available()` is False when oracle/_ref was not built (run
-`make -f oracle/Makefile.ref -j8` in a container that has /root/reference).
+TEST INFRASTRUCTURE: only tests/, tools/make_golden*.py, __graft_entry__.smoke() and bench.py's
+reference legs import this.  `available()` / `cuda_available()` are False when the library was not built
+(run `make -f oracle/Makefile.ref -j8` / `make -f oracle/Makefile.ref_cuda -j8` in a container that has
+/root/reference).  `use_cuda(True)` switches the process to the CUDA build BEFORE the first call: the two
+libraries define the same symbols and are never loaded together.
 """
 from __future__ import annotations
 
@@ -14,17 +18,36 @@ import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _PATH = os.path.join(_HERE, "_ref", "libct2ref_driver.so")
+_PATH_CUDA = os.path.join(_HERE, "_ref_cuda", "libct2ref_cuda_driver.so")
 _lib = None
+_cuda = False
 
 
 def available() -> bool:
     return os.path.exists(_PATH)
 
 
+def cuda_available() -> bool:
+    return os.path.exists(_PATH_CUDA)
+
+
+def use_cuda(flash_attention: bool = False):
+    """Route this process to the reference's CUDA build: generators / translators load on Device::CUDA (device 0)."""
+    global _cuda
+    if _lib is not None and not _cuda:
+        raise RuntimeError("the CPU reference library is already loaded in this process")
+    _cuda = True
+    _check(lib().ref_set_device(1, int(flash_attention)))
+
+
+def is_cuda() -> bool:
+    return _cuda
+
+
 def lib():
     global _lib
     if _lib is None:
-        _lib = ctypes.CDLL(_PATH)
+        _lib = ctypes.CDLL(_PATH_CUDA if _cuda else _PATH)
         _lib.ref_last_error.restype = ctypes.c_char_p
         _lib.ref_generator_open.restype = ctypes.c_void_p
         _lib.ref_generator_open.argtypes = [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int]
@@ -308,3 +331,64 @@ def rotary_tables(num_positions, dim, base=10000.0, interleave=False, scaling_ty
     cos = (y[:, :h] + y[:, h:]) / 2
     sin = (y[:, h:] - y[:, :h]) / 2
     return np.concatenate([sin, sin], 1), np.concatenate([cos, cos], 1)
+
+
+# ---- CUDA build only: the reference's GPU-only ops (AWQ) and its INT8 Dense chain, host arrays in and out ----
+def _f16(a):
+    return None if a is None else np.ascontiguousarray(a, dtype=np.float16)
+
+
+def cuda_gemm_awq(x, qweight, scales, qzeros, group):
+    """ops::GemmAwq (AWQ_GEMM layout): x f16 [m,k], qweight int32 [k,n/8], scales f16 [k/g,n], qzeros int32 [k/g,n/8]."""
+    x, scales = _f16(x), _f16(scales)
+    qweight, qzeros = _c(qweight, np.int32), _c(qzeros, np.int32)
+    m, k = x.shape
+    n = qweight.shape[1] * 8
+    y = np.zeros((m, n), np.float16)
+    _check(lib().ref_cuda_gemm_awq(_p(x), _p(qweight), _p(scales), _p(qzeros), m, n, k, group, _p(y)))
+    return y
+
+
+def cuda_gemv_awq(x, qweight, scales, qzeros):
+    """ops::GemvAwq (AWQ_GEMV layout): qweight int32 [n,k/8], scales f16 [n,sw], qzeros int32 [n,zw]."""
+    x, scales = _f16(x), _f16(scales)
+    qweight, qzeros = _c(qweight, np.int32), _c(qzeros, np.int32)
+    m, k = x.shape
+    n = qweight.shape[0]
+    y = np.zeros((m, n), np.float16)
+    _check(lib().ref_cuda_gemv_awq(_p(x), _p(qweight), _p(scales), _p(qzeros), m, n, k, scales.shape[1], qzeros.shape[1], _p(y)))
+    return y
+
+
+def cuda_dequantize_awq(qweight, scales, qzeros, group):
+    """ops::DequantizeAwq (AWQ_GEMM layout) -> W f16 [k, n]."""
+    scales = _f16(scales)
+    qweight, qzeros = _c(qweight, np.int32), _c(qzeros, np.int32)
+    k, n = qweight.shape[0], qweight.shape[1] * 8
+    w = np.zeros((k, n), np.float16)
+    _check(lib().ref_cuda_dequantize_awq(_p(qweight), _p(scales), _p(qzeros), n, k, group, _p(w)))
+    return w
+
+
+def cuda_dense_s8(x, w, w_scale, act=-1):
+    """layers::Dense INT8 arm on the GPU: Quantize -> cublasGemmEx(s8) -> Dequantize(+act); x f16 [m,k], w int8 [n,k]."""
+    x = _f16(x)
+    w, w_scale = _c(w, np.int8), _c(w_scale, np.float32)
+    m, k = x.shape
+    n = w.shape[0]
+    y = np.zeros((m, n), np.float16)
+    _check(lib().ref_cuda_dense_s8(_p(x), _p(w), _p(w_scale), act, m, n, k, _p(y)))
+    return y
+
+
+def _generate_timed(self, prompts, max_length, end_id=2):
+    """(tokens [B, max_length], seconds) of one greedy generate_batch of exactly max_length tokens (device-synchronised)."""
+    prompts = _c(prompts, np.int32)
+    B, P = prompts.shape
+    out = np.zeros((B, max_length), np.int32)
+    sec = ctypes.c_double()
+    _check(lib().ref_generate_timed(ctypes.c_void_p(self.h), _p(prompts), B, P, max_length, end_id, _p(out), ctypes.byref(sec)))
+    return out, sec.value
+
+
+RefGenerator.generate_timed = _generate_timed
