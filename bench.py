@@ -6,12 +6,18 @@
 A "step" is one decode step of the whole batch (B generated tokens) of BASELINE.json configs[2]
 ("Llama-3-8B generate_batch INT8, seq 2048, bsz 1 and 32, on 1xB200"): prompt P=1024 then K generated
 tokens per sequence.  One JSON line on stdout (rank 0):
-  value  = B*K*N / device time of K decode steps, inputs already resident in HBM (CUDA events, max over ranks)
-  e2e    = the same tokens/s through ctranslate2_b200.Generator.generate_batch with HOST prompt ids and HOST
-           result ids (prefill + decode + host<->device copies inside the timed region)
+  value    = B*K*N / device time of K decode steps, inputs already resident in HBM (CUDA events, max over ranks)
+  e2e      = the same tokens/s through ctranslate2_b200.Generator.generate_batch with HOST prompt ids and HOST
+             result ids (prefill + decode + host<->device copies inside the timed region)
+  e2e_full = e2e at the NAMED workload (1024 generated tokens after the 1024-token prompt) whatever --steps is
+  variants = the four points of BASELINE.json's metric — INT8 and AWQ-INT4 at bsz 1 and 32 — device-timed decode
+             (ms/step, tokens/s, fraction of the HBM roofline of the step), each beside `ref_cuda`: the UNMODIFIED
+             reference's own CUDA build (oracle/_ref_cuda: cuBLAS INT8 GEMM / its AWQ kernels) on the same GPU
   roofline = the weight-streaming tcgen05 GEMM timed alone with CUDA events over buffers larger than L2
   cpu_baseline = the unmodified reference (oracle/_ref, Ruy INT8) on the host cores, bounded sample
-N>1: independent data-parallel replicas (one process per GPU, no data-path collective): scaling "weak".
+N>1: independent data-parallel replicas (one process per GPU, no data-path collective): scaling "weak"; the same line
+also carries `tp`: ONE tensor-parallel generator over the N GPUs (heads / FFN columns sharded, collectives fused into
+kernels over NVLink peer memory), strong scaling of the same step.
 `--impl reference` times the reference's own CPU implementation (oracle/_ref) on the host cores.
 """
 import argparse
@@ -269,6 +275,48 @@ def reference_cpu(name, batch, steps, warmup, budget_s=100.0, calibrate=True):
             "seconds": dt}
 
 
+def ref_cuda_bench(name, quant, compute, batch, plen, g1=8, g2=40, flash=False, timeout=900):
+    """The unmodified reference's CUDA build (oracle/_ref_cuda) on the same GPU, in its own process: decode tokens/s from
+    two generations of g1 and g2 tokens (the difference isolates the decode steps), e2e tokens/s of the longer one."""
+    lib = os.path.join(ROOT, "oracle", "_ref_cuda", "libct2ref_cuda_driver.so")
+    if not os.path.exists(lib):
+        return {"unavailable": "oracle/_ref_cuda is not built (make -f oracle/Makefile.ref_cuda)"}
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_cuda_worker.py"), "bench", model_dir(name, quant), compute,
+           str(batch), str(plen), str(g1), str(g2)] + (["--flash"] if flash else [])
+    try:
+        r = subprocess.run(cmd, capture_output=True, text=True, timeout=timeout)
+        line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+        if r.returncode != 0 or not line:
+            return {"error": (r.stderr or r.stdout)[-300:]}
+        return json.loads(line[-1])
+    except Exception as ex:
+        return {"error": str(ex)[-300:]}
+
+
+def measure_variant(ct2, torch, name, weights, batch, plen, steps, warmup, device_index, peak, with_ref_cuda):
+    """One point of the metric: device-timed decode of `steps` steps after the `plen`-token prompt."""
+    awq = weights == "awq"
+    quant = "awq_gemm" if awq else "int8_float16"
+    gen = ct2.Generator(model_dir(name, quant), device_index=device_index, compute_type="float16" if awq else "int8_float16",
+                        max_batch_size=batch, max_length=plen + steps + warmup + 16)
+    pre_ms, dec_ms, launches = gen.bench_decode(batch, plen, steps, warmup)
+    gen.close()
+    del gen
+    torch.cuda.empty_cache()
+    ms = dec_ms / steps
+    sb = step_bytes(name, batch, plen + steps / 2.0, weights)
+    rec = {"ms_per_step": round(ms, 4), "tokens_per_s": round(batch / (ms * 1e-3), 1), "steps": steps,
+           "context": "%d -> %d" % (plen, plen + steps), "prefill_ms": round(pre_ms, 2),
+           "launches_per_step": int(launches // steps), "step_bytes_algorithmic": int(sb),
+           "step_roofline_frac": round(sb / (ms * 1e-3) / 1e9 / peak, 4)}
+    if with_ref_cuda:
+        r = ref_cuda_bench(name, quant, "float16" if awq else "int8_float16", batch, plen)
+        rec["ref_cuda"] = r
+        if "decode_tokens_per_s" in r:
+            rec["vs_ref_cuda"] = round(rec["tokens_per_s"] / r["decode_tokens_per_s"], 2)
+    return rec
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -281,10 +329,12 @@ def main():
     ap.add_argument("--prompt-len", type=int, default=PROMPT_LEN)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-graph", action="store_true")
+    ap.add_argument("--no-variants", action="store_true", help="skip the INT8/AWQ x bsz 1/32 sub-records and ref_cuda")
+    ap.add_argument("--no-tp", action="store_true", help="N > 1: skip the tensor-parallel record")
     ap.add_argument("--weights", default="int8", choices=["int8", "awq"],
                     help="int8 = the headline INT8 configuration; awq = the AWQ-INT4 (group 128, AWQ_GEMM layout) variant")
     ap.add_argument("--tp", action="store_true",
-                    help="N > 1: ONE tensor-parallel generator over the N GPUs (strong scaling) instead of N replicas")
+                    help="N > 1: ONE tensor-parallel generator over the N GPUs (strong scaling) as the headline instead of N replicas")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -306,6 +356,11 @@ def main():
         if r is None:
             print(json.dumps({"impl": "reference", "unavailable": "oracle/_ref is not built (make -f oracle/Makefile.ref)"}))
             return
+        # the CPU arm runs a BOUNDED sample of the workload: say so in the label the driver compares
+        config["workload"] = ("%s generate_batch INT8 (int8, Ruy), greedy, bsz %d, bounded sample: prompt 8 + %d generated "
+                              "(BASELINE.json configs[2] has prompt %d + %d generated)" % (NAMES[args.model], B, r["steps"], P, K))
+        config["prompt_len"] = 8
+        config["parallelism"] = "host cores (%d threads)" % r["cores"]
         line = {"impl": "reference", "metric": "generate_batch tokens/sec", "value": round(r["value"], 3),
                 "unit": "tokens/s", "n_gpus": 0, "steps": r["steps"], "warmup": W,
                 "ms_per_step": round(1e3 * r["seconds"] / r["steps"], 3), "higher_is_better": True, "scaling": "weak",
@@ -330,7 +385,8 @@ def main():
     max_len = P + max(K, 8) + W + 8
     tp = args.tp and world > 1
     gen = ct2.Generator(mdir, device_index=local_rank, compute_type="float16" if awq else "int8_float16", max_batch_size=B,
-                        max_length=max_len, use_cuda_graph=not args.no_graph, tensor_parallel=tp)
+                        max_length=max(max_len, P + 1024 + 16) if not tp else max_len, use_cuda_graph=not args.no_graph,
+                        tensor_parallel=tp)
     units = 1 if tp else world             # independent batches processed per step
     info = gen.info()
 
@@ -340,32 +396,65 @@ def main():
             torch.distributed.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(*vals):
+        t = torch.tensor(list(vals), device="cuda", dtype=torch.float64)
+        if world > 1:
+            torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
+        return [float(v) for v in t]
+
     # ---- device-timed decode (inputs resident), K steps after W warm-up steps ----
     sync_all()
     with ClockSampler(local_rank) as clocks:
         pre_ms, dec_ms, launches = gen.bench_decode(B, P, K, W)
         sync_all()
-    t = torch.tensor([dec_ms, pre_ms], device="cuda", dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    dec_ms, pre_ms = float(t[0]), float(t[1])
+    dec_ms, pre_ms = max_over_ranks(dec_ms, pre_ms)
     value = B * K * units / (dec_ms * 1e-3)
 
     # ---- end to end through the public API with host buffers ----
     prompts = prompts_for(args.model, B, P, seed=42 + (0 if tp else rank))
     gen.generate_batch(prompts[:, :8].tolist(), max_length=2, min_length=2, end_token=[0])   # warm the small path
-    sync_all()
-    t0 = time.perf_counter()
-    res = gen.generate_batch(prompts, max_length=K, min_length=K, end_token=[1])
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    assert all(len(r.sequences_ids[0]) == K for r in res)
-    t = torch.tensor([e2e_s], device="cuda", dtype=torch.float64)
-    if world > 1:
-        torch.distributed.all_reduce(t, op=torch.distributed.ReduceOp.MAX)
-    e2e_s = float(t[0])
-    e2e = {"value": round(B * K * units / e2e_s, 2), "unit": "tokens/s", "h2d_bytes_per_step": round(B * P * 4 / K, 1),
-           "d2h_bytes_per_step": B * 4, "seconds": round(e2e_s, 4), "includes": "prompt H2D + prefill(P-1) + K decode steps + ids D2H"}
+
+    def e2e_run(tokens):
+        sync_all()
+        t0 = time.perf_counter()
+        res = gen.generate_batch(prompts, max_length=tokens, min_length=tokens, end_token=[1])
+        torch.cuda.synchronize()
+        sec = time.perf_counter() - t0
+        assert all(len(r.sequences_ids[0]) == tokens for r in res)
+        sec, = max_over_ranks(sec)
+        return {"value": round(B * tokens * units / sec, 2), "unit": "tokens/s", "h2d_bytes_per_step": round(B * P * 4 / tokens, 1),
+                "d2h_bytes_per_step": B * 4, "seconds": round(sec, 4), "generated_tokens_per_sequence": tokens,
+                "includes": "prompt H2D + prefill(P-1) + %d decode steps + ids D2H" % tokens}
+
+    e2e = e2e_run(K)
+    e2e_full = e2e if K == 1024 else (e2e_run(1024) if not tp else None)
+
+    # ---- N > 1: ONE tensor-parallel generator over the same GPUs (strong scaling of the same step) ----
+    tp_rec = None
+    if world > 1 and not tp and not args.no_tp:
+        gen.close()
+        del gen
+        torch.cuda.empty_cache()
+        torch.distributed.barrier()
+        try:
+            tgen = ct2.Generator(mdir, device_index=local_rank, compute_type="float16" if awq else "int8_float16",
+                                 max_batch_size=B, max_length=max_len, use_cuda_graph=not args.no_graph, tensor_parallel=True)
+            sync_all()
+            tpre, tdec, tl = tgen.bench_decode(B, P, K, W)
+            sync_all()
+            tdec, tpre = max_over_ranks(tdec, tpre)
+            m = MODELS[args.model]
+            d = m["num_heads"] * m["head_dim"]
+            # per layer two reduced [B, d] tensors pulled from world-1 peers, plus two 8-byte {epoch, amax} words per row
+            nvl = m["num_layers"] * 2 * (world - 1) * B * (d * 2 + 8)
+            tp_rec = {"parallelism": "tp%d" % world, "scaling": "strong", "ms_per_step": round(tdec / K, 4),
+                      "tokens_per_s": round(B * K / (tdec * 1e-3), 1), "prefill_ms": round(tpre, 2),
+                      "speedup_vs_one_gpu_step": round((dec_ms / K) / (tdec / K), 3),
+                      "nvlink_bytes_per_step_per_gpu": int(nvl), "launches_per_step": int(tl // K)}
+            tgen.close()
+        except Exception as ex:
+            tp_rec = {"error": str(ex)[-300:]}
+        gen = None
 
     if rank != 0:
         return
@@ -383,18 +472,34 @@ def main():
                       "s8 (int8 x int8 -> s32 on tcgen05; f16 activations, f32 epilogue/softmax)"),
             "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
             "gpu_launches": int(launches)}
+    if e2e_full is not None:
+        line["e2e_full"] = e2e_full
+    if tp_rec is not None:
+        line["tp"] = tp_rec
+    if gen is not None:
+        gen.close()
+        del gen
+    torch.cuda.empty_cache()
     try:
         line["roofline"] = awq_roofline(args.model, B, "cuda") if awq else gemm_roofline(args.model, B, "cuda")
     except Exception as ex:  # keep the headline even if the side measurement fails
         line["roofline"] = {"error": str(ex)}
+    if world == 1 and not args.no_variants:
+        # the four points BASELINE.json's metric names, each beside the reference's own CUDA build on this GPU
+        variants = {}
+        for wname in ("int8", "awq"):
+            for b in (1, 32):
+                key = "%s_b%d" % (wname, b)
+                try:
+                    variants[key] = measure_variant(ct2, torch, args.model, wname, b, P, 64, W, local_rank, peak, True)
+                except Exception as ex:
+                    variants[key] = {"error": str(ex)[-300:]}
+        line["variants"] = variants
     if awq:
         line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference",
                                 "sample": "none: the reference has no CPU implementation of the AWQ ops "
                                           "(src/ops/awq/gemm_cpu.cc, gemv_cpu.cc, dequantize_cpu.cc throw)"}
     elif world == 1 and not args.no_cpu_baseline:
-        gen.close()
-        del gen
-        torch.cuda.empty_cache()
         r = reference_cpu(args.model, B, 64, 1, budget_s=25.0, calibrate=False)
         line["cpu_baseline"] = ({k: r[k] for k in ("value", "unit", "cores", "kind", "sample")} if r else
                                 {"value": None, "kind": "reference", "sample": "oracle/_ref not built"})

@@ -48,7 +48,7 @@ def check(rc: int):
 class GeneratorConfig(ctypes.Structure):
     _fields_ = [("device", ctypes.c_int), ("compute_type", ctypes.c_int), ("max_batch", ctypes.c_int64),
                 ("max_length", ctypes.c_int64), ("tp_rank", ctypes.c_int), ("tp_size", ctypes.c_int),
-                ("use_cuda_graph", ctypes.c_int), ("gemm_impl", ctypes.c_int)]
+                ("use_cuda_graph", ctypes.c_int), ("gemm_impl", ctypes.c_int), ("weight_type", ctypes.c_int)]
 
 
 def kernel_launch_count() -> int:

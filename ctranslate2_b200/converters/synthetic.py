@@ -123,11 +123,14 @@ class ModelWriter:
 
 
 def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int8_float16",
-                      seed: int = 1234, init_std: float = 0.02, fast_int8: bool = False) -> None:
+                      seed: int = 1234, init_std: float = 0.02, fast_int8: bool = False,
+                      extra: Optional[Dict] = None, omit=()) -> None:
     """Writes a random-init Llama-class model directory.
 
     quantization: "int8" / "int8_float32" / "int8_float16" / "int8_bfloat16" (int8 linear + embedding
     weights with fp32 row scales, norms in the float type), or "float32" / "float16" / "bfloat16".
+    extra / omit: additional variables {name: numpy value} written after the standard ones / names left out (loader tests
+    build model directories with features the engine must refuse).
     fast_int8: draw int8 weights and scales directly (same distribution as quantizing N(0, std^2)
     rows whose amax sits near 4 sigma) instead of quantizing an fp32 draw — used for the 8B bench
     model where generating 8e9 gaussians on the host would dominate the run.
@@ -141,6 +144,9 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
              "int8_bfloat16": "bfloat16"}.get(quantization, quantization)
     d, D = cfg.d_model, cfg.head_dim
     w = ModelWriter(model_dir)
+    _add = w.add
+    if omit:
+        w.add = lambda name, value, dtype=None: None if name in omit else _add(name, value, dtype)
 
     base = rng.integers(-127, 128, size=1 << 24, dtype=np.int8) if fast_int8 else None
     state = {"off": 0}
@@ -214,6 +220,8 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
     w.add("decoder/scale_alibi", np.int8(0))
     w.add("decoder/scale_embeddings", np.int8(0))
     w.add("decoder/start_from_zero_embedding", np.int8(0))
+    for name, value in (extra or {}).items():
+        _add(name, value)
     config = {"bos_token": "<t1>", "eos_token": "<t2>", "unk_token": "<t0>",
               "layer_norm_epsilon": cfg.rms_eps, "multi_query_attention": cfg.num_heads_kv != cfg.num_heads}
     w.close(config, (f"<t{i}>" for i in range(cfg.vocab_size)))

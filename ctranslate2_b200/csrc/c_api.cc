@@ -118,6 +118,43 @@ CT2B200_API int ct2b200_dense_s8_glu(const int8_t* xq, const float* x_scale, con
   });
 }
 
+namespace {
+void rows_to_int8(const void* x, const void* gamma, float eps, int64_t m, int64_t k, int dtype, int8_t* xq, float* xs,
+                  cudaStream_t st) {
+  if (gamma) launch_rms_norm(gamma, x, m, k, eps, false, nullptr, xq, xs, dtype, st);
+  else launch_quantize_rows(x, dtype, m, k, true, xq, xs, st);
+}
+}  // namespace
+
+CT2B200_API int ct2b200_dense_s8_rows(const void* x, const void* gamma, float eps, const int8_t* w, const float* w_scale,
+                          const void* bias, const void* residual, int act, int64_t m, int64_t n, int64_t k, void* y,
+                          int dtype, int8_t* xq, float* x_scale, unsigned* barrier, void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(x && w && w_scale && xq && x_scale && barrier, "dense_s8_rows: null argument");
+    DenseEpilogue e{x_scale, w_scale, bias, residual, y, nullptr, act, n};
+    RowPre pre{gamma ? 2 : 1, x, gamma, eps, barrier};
+    if (m <= 64 && gemm_s8_decode(xq, w, m, n, k, e, dtype, S(stream), &pre)) return;
+    rows_to_int8(x, gamma, eps, m, k, dtype, xq, x_scale, S(stream));
+    gemm_s8(xq, w, m, n, k, e, dtype, CT2B200_GEMM_AUTO, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_dense_s8_glu_rows(const void* x, const void* gamma, float eps, const int8_t* w_gate,
+                              const float* w_gate_scale, const int8_t* w_up, const float* w_up_scale, int act, int64_t m,
+                              int64_t n, int64_t k, void* h, int dtype, int8_t* xq, float* x_scale, unsigned* barrier,
+                              void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(x && w_gate && w_up && xq && x_scale && barrier, "dense_s8_glu_rows: null argument");
+    GluEpilogue g{x_scale, w_gate_scale, w_up_scale, h, act, n};
+    RowPre pre{gamma ? 2 : 1, x, gamma, eps, barrier};
+    if (m <= 64 && gemm_s8_glu_decode(xq, w_gate, w_up, m, n, k, g, dtype, S(stream), &pre)) return;
+    rows_to_int8(x, gamma, eps, m, k, dtype, xq, x_scale, S(stream));
+    gemm_s8_glu(xq, w_gate, w_up, m, n, k, g, dtype, CT2B200_GEMM_AUTO, S(stream));
+  });
+}
+
 CT2B200_API int ct2b200_gemm_f16(const void* a, const void* b, const void* bias, const void* residual, int act, int64_t m,
                      int64_t n, int64_t k, void* c, int dtype, void* stream) {
   return guarded([&] {
@@ -367,11 +404,11 @@ CT2B200_API int ct2b200_model_summary(const char* model_dir, char* json_out, siz
         buf, sizeof(buf),
         "{\"spec\": \"%s\", \"binary_version\": %u, \"revision\": %u, \"num_layers\": %d, \"num_heads\": %d, "
         "\"num_heads_kv\": %d, \"head_dim\": %d, \"d_model\": %lld, \"ffn_dim\": %lld, \"vocab_size\": %lld, "
-        "\"weights\": \"%s\", \"rotary_interleave\": %s, \"rotary_base\": %.9g, \"rotary_scaling_type\": %d, "
+        "\"weights\": \"%s\", \"float_type\": \"%s\", \"rotary_interleave\": %s, \"rotary_base\": %.9g, \"rotary_scaling_type\": %d, "
         "\"layer_norm_epsilon\": %.9g, \"activation\": %d}",
         file.spec_name.c_str(), file.binary_version, file.revision, mc.num_layers, mc.num_heads, mc.num_heads_kv, mc.head_dim,
         static_cast<long long>(mc.d_model), static_cast<long long>(mc.ffn_dim), static_cast<long long>(mc.vocab),
-        mc.weights.c_str(), mc.rotary_interleave ? "true" : "false", static_cast<double>(mc.rotary_base),
+        mc.weights.c_str(), mc.float_type.c_str(), mc.rotary_interleave ? "true" : "false", static_cast<double>(mc.rotary_base),
         mc.rotary_scaling_type, static_cast<double>(mc.eps), mc.activation);
     CT2_REQUIRE(n > 0 && static_cast<size_t>(n) < capacity, "model_summary: output buffer too small");
     std::memcpy(json_out, buf, static_cast<size_t>(n) + 1);

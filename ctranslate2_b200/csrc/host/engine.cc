@@ -255,72 +255,110 @@ std::pair<int64_t, int64_t> shard_range(int64_t total, int rank, int world) {
 void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w, Shard shard) {
   const HostVariable& wt = f.get(prefix + "/weight");
   const bool awq_weight = wt.type_id == 3 && f.find(prefix + "/weight_zero") != nullptr;
-  if (tp_.world > 1 && shard != REPLICATED && !awq_weight) {
-    // Tensor-parallel partition (model.cc:662-743): column-parallel layers keep a slice of the output channels
-    // (for the fused QKV: this rank's query heads, key heads and value heads), row-parallel layers a slice of K.
-    // The int8 values and the per-channel scales are those of the unsharded matrix (the scale of a row-parallel
-    // weight still spans the whole row), so the shards reproduce the single-GPU arithmetic exactly.
-    CT2_REQUIRE(wt.type_id == 1 || wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5,
-                "unsupported weight type for a tensor-parallel shard");
+  if (!awq_weight) {
+    // ---- INT8 / float weights: Model::set_compute_type + ensure_dtype (src/models/model.cc:178-234, 304-369) on the GPU ----
+    // The stored matrix goes to the device as it is; when the requested compute type asks for another weight type it is
+    // converted there with the converter's own arithmetic (model_spec.py:222-243 = ops::Quantize on fp32: scale = 127 / amax
+    // per row, q = rint(w * scale); back: w = T(float(q) * (1 / scale)), dequantize_cpu.cc:12-21).  Tensor-parallel shards
+    // (model.cc:662-743) are cut afterwards, device to device: column-parallel layers keep a slice of the output channels
+    // (fused QKV: this rank's query, key and value heads), row-parallel layers a slice of K.  The int8 values and the
+    // per-channel scales are those of the unsharded matrix, so the shards reproduce the single-GPU arithmetic exactly.
+    CT2_REQUIRE(wt.type_id == 1 || wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5, "unsupported weight type for " + prefix);
     CT2_REQUIRE(wt.shape.size() == 2, "weight must be a matrix");
     const int64_t N = wt.shape[0], K = wt.shape[1];
-    const bool int8 = wt.type_id == 1;
-    CT2_REQUIRE(int8 || dtype_ != CT2B200_F32, "float weights need compute type float16 or bfloat16 on this engine");
-    std::vector<uint8_t> conv;
-    const uint8_t* src = wt.data;
-    size_t es = 1;
-    if (!int8) {
-      conv = convert_to_dtype(wt, dtype_);
-      src = conv.data();
-      es = dtype_size(dtype_);
-    }
-    std::vector<std::pair<int64_t, int64_t>> row_ranges;      // output channels kept
-    int64_t k0 = 0, k1 = K;
-    if (shard == ROWS) {
-      row_ranges.push_back(shard_range(N, tp_.rank, tp_.world));
-    } else if (shard == QKV_ROWS) {
-      const int64_t D = mc_.head_dim, hq = static_cast<int64_t>(mc_.num_heads) * D, hk = static_cast<int64_t>(mc_.num_heads_kv) * D;
-      CT2_REQUIRE(N == hq + 2 * hk, "fused QKV weight has an unexpected number of rows");
-      const auto q = shard_range(mc_.num_heads, tp_.rank, tp_.world), kv = shard_range(mc_.num_heads_kv, tp_.rank, tp_.world);
-      row_ranges.push_back({q.first * D, q.second * D});
-      row_ranges.push_back({hq + kv.first * D, hq + kv.second * D});
-      row_ranges.push_back({hq + hk + kv.first * D, hq + hk + kv.second * D});
+    const bool stored_int8 = wt.type_id == 1;
+    const bool want_int8 = weight_type_ == CT2B200_WEIGHTS_INT8 || (weight_type_ == CT2B200_WEIGHTS_STORED && stored_int8);
+    CT2_REQUIRE(want_int8 || dtype_ != CT2B200_F32, "float weights need compute type float16 or bfloat16 on this engine");
+    DeviceBuffer full_w, full_s;
+    if (stored_int8) {
+      const HostVariable& sc = f.get(prefix + "/weight_scale");
+      CT2_REQUIRE(sc.type_id == 0 && sc.size() == N, "weight_scale must be float32 [n]");
+      upload(full_w, wt.data, wt.nbytes);
+      upload(full_s, sc.data, sc.nbytes);
+      if (!want_int8) {                            // int8 -> float (compute types float16 / bfloat16 on an int8 model)
+        DeviceBuffer deq(static_cast<size_t>(N) * K * dtype_size(dtype_));
+        launch_dequantize_rows(full_w.as<int8_t>(), full_s.as<float>(), N, K, deq.ptr, dtype_, stream_, /*reciprocal=*/true);
+        CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        full_w = std::move(deq);
+        full_s.release();
+      }
     } else {
-      row_ranges.push_back({0, N});
-      std::tie(k0, k1) = shard_range(K, tp_.rank, tp_.world);
-    }
-    int64_t n_local = 0;
-    for (auto& rr : row_ranges) n_local += rr.second - rr.first;
-    const int64_t k_local = k1 - k0;
-    std::vector<uint8_t> host(static_cast<size_t>(n_local) * k_local * es);
-    std::vector<float> host_scale;
-    const HostVariable* sc = int8 ? &f.get(prefix + "/weight_scale") : nullptr;
-    if (int8) CT2_REQUIRE(sc->type_id == 0 && sc->size() == N, "weight_scale must be float32 [n]");
-    int64_t o = 0;
-    for (auto& rr : row_ranges)
-      for (int64_t i = rr.first; i < rr.second; ++i, ++o) {
-        std::memcpy(host.data() + static_cast<size_t>(o) * k_local * es, src + (static_cast<size_t>(i) * K + k0) * es,
-                    static_cast<size_t>(k_local) * es);
-        if (int8) {
-          float sv;
-          std::memcpy(&sv, sc->data + 4 * i, 4);
-          host_scale.push_back(sv);
+      const int stored = wt.type_id == 0 ? CT2B200_F32 : wt.type_id == 4 ? CT2B200_F16 : CT2B200_BF16;
+      upload(full_w, wt.data, wt.nbytes);
+      if (want_int8 || stored != dtype_) {
+        DeviceBuffer f32;
+        const float* src32 = full_w.as<float>();
+        if (stored != CT2B200_F32) {
+          f32.alloc(static_cast<size_t>(N) * K * 4);
+          launch_convert_to_f32(full_w.ptr, N * K, f32.as<float>(), stored, stream_);
+          src32 = f32.as<float>();
+        }
+        if (want_int8) {                           // float -> int8 (e.g. a float16 model served as int8_float16)
+          DeviceBuffer q(static_cast<size_t>(N) * K);
+          full_s.alloc(static_cast<size_t>(N) * 4);
+          launch_quantize_rows(src32, CT2B200_F32, N, K, true, q.as<int8_t>(), full_s.as<float>(), stream_);
+          CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+          full_w = std::move(q);
+        } else {                                   // float -> the compute float type
+          DeviceBuffer t(static_cast<size_t>(N) * K * dtype_size(dtype_));
+          launch_convert_from_f32(src32, N * K, t.ptr, dtype_, stream_);
+          CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+          full_w = std::move(t);
         }
       }
-    w.kind = int8 ? DenseWeights::INT8 : DenseWeights::FLOAT16;
-    w.n = n_local;
-    w.k = k_local;
-    upload(w.weight, host.data(), host.size());
-    if (int8) upload(w.scale, host_scale.data(), host_scale.size() * 4);
-    mc_.weight_bytes += host.size() + host_scale.size() * 4;
-    if (const HostVariable* b = f.find(prefix + "/bias")) {
+    }
+    const size_t es = want_int8 ? 1 : dtype_size(dtype_);
+    w.kind = want_int8 ? DenseWeights::INT8 : DenseWeights::FLOAT16;
+    std::vector<std::pair<int64_t, int64_t>> row_ranges = {{0, N}};
+    int64_t k0 = 0, k1 = K;
+    if (tp_.world > 1 && shard != REPLICATED) {
+      if (shard == ROWS) {
+        row_ranges = {shard_range(N, tp_.rank, tp_.world)};
+      } else if (shard == QKV_ROWS) {
+        const int64_t D = mc_.head_dim, hq = static_cast<int64_t>(mc_.num_heads) * D, hk = static_cast<int64_t>(mc_.num_heads_kv) * D;
+        CT2_REQUIRE(N == hq + 2 * hk, "fused QKV weight has an unexpected number of rows");
+        const auto q = shard_range(mc_.num_heads, tp_.rank, tp_.world), kv = shard_range(mc_.num_heads_kv, tp_.rank, tp_.world);
+        row_ranges = {{q.first * D, q.second * D}, {hq + kv.first * D, hq + kv.second * D},
+                      {hq + hk + kv.first * D, hq + hk + kv.second * D}};
+      } else {
+        std::tie(k0, k1) = shard_range(K, tp_.rank, tp_.world);
+      }
+      int64_t n_local = 0;
+      for (auto& rr : row_ranges) n_local += rr.second - rr.first;
+      const int64_t k_local = k1 - k0;
+      DeviceBuffer nw(static_cast<size_t>(n_local) * k_local * es), ns;
+      if (want_int8) ns.alloc(static_cast<size_t>(n_local) * 4);
+      int64_t o = 0;
+      for (auto& rr : row_ranges) {
+        const int64_t rows_ = rr.second - rr.first;
+        CT2_CUDA_CHECK(cudaMemcpy2DAsync(nw.as<uint8_t>() + o * k_local * es, k_local * es,
+                                         full_w.as<uint8_t>() + (rr.first * K + k0) * es, K * es, k_local * es, rows_,
+                                         cudaMemcpyDeviceToDevice, stream_));
+        if (want_int8)
+          CT2_CUDA_CHECK(cudaMemcpyAsync(ns.as<float>() + o, full_s.as<float>() + rr.first, rows_ * 4, cudaMemcpyDeviceToDevice,
+                                         stream_));
+        o += rows_;
+      }
+      CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      full_w = std::move(nw);
+      full_s = std::move(ns);
+      w.n = n_local;
+      w.k = k_local;
+    } else {
+      w.n = N;
+      w.k = K;
+    }
+    w.weight = std::move(full_w);
+    w.scale = std::move(full_s);
+    mc_.weight_bytes += w.weight.bytes + w.scale.bytes;
+    if (const HostVariable* bv = f.find(prefix + "/bias")) {
       // column-parallel: the bias slice; row-parallel: the whole bias on rank 0 only (common.cc:348-352)
-      const auto bytes = convert_to_dtype(*b, dtype_);
+      const auto bytes = convert_to_dtype(*bv, dtype_);
       const size_t bes = dtype_size(dtype_);
-      if (shard == COLS) {
+      if (tp_.world > 1 && shard == COLS) {
         if (tp_.rank == 0) upload(w.bias, bytes.data(), bytes.size());
       } else {
-        std::vector<uint8_t> hb(static_cast<size_t>(n_local) * bes);
+        std::vector<uint8_t> hb(static_cast<size_t>(w.n) * bes);
         int64_t ob = 0;
         for (auto& rr : row_ranges) {
           std::memcpy(hb.data() + ob * bes, bytes.data() + rr.first * bes, (rr.second - rr.first) * bes);
@@ -331,25 +369,7 @@ void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, Den
     }
     return;
   }
-  if (wt.type_id == 1) {                       // INT8 weights with per-row fp32 scales (model_spec.py:222-243)
-    CT2_REQUIRE(wt.shape.size() == 2, "int8 weight must be a matrix");
-    w.kind = DenseWeights::INT8;
-    w.n = wt.shape[0];
-    w.k = wt.shape[1];
-    upload(w.weight, wt.data, wt.nbytes);
-    const HostVariable& sc = f.get(prefix + "/weight_scale");
-    CT2_REQUIRE(sc.type_id == 0 && sc.size() == w.n, "weight_scale must be float32 [n]");
-    upload(w.scale, sc.data, sc.nbytes);
-    mc_.weight_bytes += wt.nbytes + sc.nbytes;
-  } else if (wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5) {
-    CT2_REQUIRE(dtype_ != CT2B200_F32, "float weights need compute type float16 or bfloat16 on this engine");
-    w.kind = DenseWeights::FLOAT16;
-    w.n = wt.shape[0];
-    w.k = wt.shape[1];
-    const auto bytes = convert_to_dtype(wt, dtype_);
-    upload(w.weight, bytes.data(), bytes.size());
-    mc_.weight_bytes += bytes.size();
-  } else if (wt.type_id == 3 && f.find(prefix + "/weight_zero")) {
+  if (wt.type_id == 3 && f.find(prefix + "/weight_zero")) {
     // AWQ-INT4 (model.cc:750-757 pins FLOAT16): repack once into the native K-major layout (kernels/awq.cu)
     CT2_REQUIRE(dtype_ == CT2B200_F16, "AWQ models run with float16 activations (the reference forces ComputeType::FLOAT16)");
     const int layout = static_cast<int>(f.config_number("quantization_type", 0));
@@ -476,6 +496,51 @@ ModelConfig parse_model_config(const ModelFile& f) {
   CT2_REQUIRE(f.find("decoder/layer_0/ffn/linear_0_noact/weight") != nullptr, "only gated FFN (ffn_glu) is supported");
   CT2_REQUIRE(f.find("decoder/layer_0/self_attention/layer_norm/beta") == nullptr, "only RMSNorm decoders are supported");
   CT2_REQUIRE(mc.rotary_scaling_type != 1, "Su rotary scaling is not supported");
+  // Features of TransformerDecoderSpec the reference honours and this engine does not implement: refuse the model instead
+  // of silently computing something else (transformer.cc:380-400, 475-530; attention_layer.cc:112-142; common.cc:448).
+  {
+    // scale_embeddings: absent or a true int8 flag => embeddings * sqrt(d_model); a float => that factor (transformer.cc:385-396)
+    const HostVariable* se = f.find("decoder/scale_embeddings");
+    if (!se) se = f.find("decoder/embeddings/multiply_by_sqrt_depth");
+    CT2_REQUIRE(se != nullptr, "decoder/scale_embeddings is absent: the reference would scale the embeddings by sqrt(d_model), "
+                               "which this engine does not implement");
+    CT2_REQUIRE((se->type_id == 1 && se->scalar() == 0.0) || (se->type_id != 1 && se->scalar() == 1.0),
+                "scaled embeddings (decoder/scale_embeddings) are not supported");
+    auto flag_off = [&](const std::string& name, const char* what) {
+      if (f.attribute(name, 0.0) != 0.0) throw std::invalid_argument(std::string(what) + " (" + name + ") is not supported");
+    };
+    auto absent = [&](const std::string& name, const char* what) {
+      if (f.find(name)) throw std::invalid_argument(std::string(what) + " (" + name + ") is not supported");
+    };
+    flag_off("decoder/alibi", "ALiBi positions");
+    flag_off("decoder/sliding_window", "sliding-window attention");
+    flag_off(a0 + "sliding_window", "sliding-window attention");
+    flag_off(a0 + "multi_query", "the multi_query attention flag (use num_heads_kv)");
+    flag_off("decoder/final_logit_softcapping", "final logit soft-capping");
+    absent("decoder/scale_outputs", "scaled outputs");
+    absent("decoder/layernorm_embedding/gamma", "layernorm_embedding");
+    absent("decoder/project_in/weight", "project_in");
+    absent("decoder/project_out/weight", "project_out");
+    absent("decoder/position_encodings/encodings", "learned / sinusoidal position encodings");
+    CT2_REQUIRE(f.attribute("decoder/layer_0/layer_scalar", 1.0) == 1.0, "layer_scalar is not supported");
+    const double qs = f.attribute(a0 + "queries_scale", 0.0);
+    CT2_REQUIRE(qs == 0.0 || std::fabs(qs - 1.0 / std::sqrt(static_cast<double>(mc.head_dim))) < 1e-6,
+                "a queries_scale other than 1/sqrt(head_dim) is not supported");
+    for (int l = 0; l < mc.num_layers; ++l) {
+      const std::string p = "decoder/layer_" + std::to_string(l) + "/";
+      absent(p + "self_attention/q_norm/gamma", "q_norm");
+      absent(p + "self_attention/k_norm/gamma", "k_norm");
+      absent(p + "self_attention/relative_position_keys", "relative positions");
+      absent(p + "self_attention/relative_attention_bias", "relative attention bias");
+      absent(p + "attention/linear_0/weight", "cross attention (encoder-decoder models)");
+      for (const char* n : {"input_layer_norm", "post_attention_layer_norm", "pre_feedforward_layer_norm",
+                            "post_feedforward_layer_norm", "shared_layer_norm"})
+        absent(p + n + "/gamma", "an extra layer norm");
+      flag_off(p + "self_attention/layer_norm/layer_norm_use_residual", "layer_norm_use_residual (1 + gamma)");
+      flag_off(p + "ffn/layer_norm/layer_norm_use_residual", "layer_norm_use_residual (1 + gamma)");
+    }
+    flag_off("decoder/layer_norm/layer_norm_use_residual", "layer_norm_use_residual (1 + gamma)");
+  }
   {
     // output features of the gate projection: rows of an int8 / float weight, columns x 8 of an AWQ_GEMM-packed one
     // (qweight [K, N/8]), rows of an AWQ_GEMV-packed one (qweight [N, K/8])
@@ -488,6 +553,10 @@ ModelConfig parse_model_config(const ModelFile& f) {
     const bool awq = qkv.type_id == 3 && f.find("decoder/layer_0/self_attention/linear_0/weight_zero");
     mc.weights = qkv.type_id == 1 ? "int8" : awq ? (static_cast<int>(f.config_number("quantization_type", 0)) == 1 ? "awq_gemm" : "awq_gemv")
                : qkv.type_id == 4 ? "float16" : qkv.type_id == 5 ? "bfloat16" : qkv.type_id == 0 ? "float32" : "unsupported";
+  }
+  {
+    const HostVariable* g = f.find("decoder/layer_norm/gamma");
+    mc.float_type = !g ? "float32" : g->type_id == 4 ? "float16" : g->type_id == 5 ? "bfloat16" : "float32";
   }
   return mc;
 }
@@ -504,6 +573,8 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   CT2_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
   dtype_ = cfg.compute_type;
   gemm_impl_ = cfg.gemm_impl;
+  weight_type_ = cfg.weight_type;
+  CT2_REQUIRE(weight_type_ >= 0 && weight_type_ <= 2, "weight_type must be a ct2b200_weight_type");
   max_batch_ = std::max<int64_t>(1, cfg.max_batch);
   max_len_ = std::max<int64_t>(16, cfg.max_length);
   tp_.world = std::max(1, cfg.tp_size);
@@ -614,6 +685,9 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
     tp_.tick.alloc(256);
     CT2_CUDA_CHECK(cudaMemset(tp_.tick.ptr, 0, 256));
   }
+  grid_bar_.alloc(256);
+  CT2_CUDA_CHECK(cudaMemset(grid_bar_.ptr, 0, 256));
+  if (const char* e = std::getenv("CT2B200_FUSE_ROWS")) fuse_rows_ = e[0] != '0';
   SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
   CT2_CUDA_CHECK(cudaDeviceSynchronize());
 }
@@ -634,6 +708,39 @@ void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* x
     AwqNative a{w.weight.ptr, w.scale.ptr, w.zeros.ptr, w.n, w.k, w.group_size, w.scale_zero.ptr};
     dense_awq(x_float, a, w.bias.ptr, residual, act, m, y, scratch_nk_.ptr, stream_);
   }
+}
+
+void LlamaDecoder::dense_from_rows(const DenseWeights& w, const void* x_rows, const void* gamma, int64_t cols, int64_t m,
+                                   const void* residual, int act, void* y) {
+  const bool tc = gemm_impl_ == CT2B200_GEMM_TCGEN05 || (gemm_impl_ == CT2B200_GEMM_AUTO && env_gemm_impl() != CT2B200_GEMM_MMA_SYNC);
+  if (fuse_rows_ && tc && m <= 64) {
+    RowPre pre{gamma ? 2 : 1, x_rows, gamma, mc_.eps, grid_bar_.as<unsigned>()};
+    DenseEpilogue e{xs_.as<float>(), w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
+    if (gemm_s8_decode(xq_.as<int8_t>(), w.weight.as<int8_t>(), m, w.n, w.k, e, dtype_, stream_, &pre)) return;
+  }
+  if (gamma)
+    launch_rms_norm(gamma, x_rows, m, cols, mc_.eps, false, nullptr, xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
+  else
+    launch_quantize_rows(x_rows, dtype_, m, cols, true, xq_.as<int8_t>(), xs_.as<float>(), stream_);
+  dense(w, xq_.as<int8_t>(), xs_.as<float>(), nullptr, m, residual, act, y);
+}
+
+void LlamaDecoder::glu_from_rows(const DenseWeights& gate, const DenseWeights& up, const void* x_rows, const void* gamma,
+                                 int64_t m, void* h) {
+  GluEpilogue g{xs_.as<float>(), gate.scale.as<float>(), up.scale.as<float>(), h, mc_.activation, gate.n};
+  const bool tc = gemm_impl_ == CT2B200_GEMM_TCGEN05 || (gemm_impl_ == CT2B200_GEMM_AUTO && env_gemm_impl() != CT2B200_GEMM_MMA_SYNC);
+  if (fuse_rows_ && tc && m <= 64) {
+    RowPre pre{gamma ? 2 : 1, x_rows, gamma, mc_.eps, grid_bar_.as<unsigned>()};
+    if (gemm_s8_glu_decode(xq_.as<int8_t>(), gate.weight.as<int8_t>(), up.weight.as<int8_t>(), m, gate.n, gate.k, g, dtype_,
+                           stream_, &pre))
+      return;
+  }
+  if (gamma)
+    launch_rms_norm(gamma, x_rows, m, gate.k, mc_.eps, false, nullptr, xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
+  else
+    launch_quantize_rows(x_rows, dtype_, m, gate.k, true, xq_.as<int8_t>(), xs_.as<float>(), stream_);
+  gemm_s8_glu(xq_.as<int8_t>(), gate.weight.as<int8_t>(), up.weight.as<int8_t>(), m, gate.n, gate.k, g, dtype_, gemm_impl_,
+              stream_);
 }
 
 void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d) {
@@ -680,33 +787,18 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
     }
     return;
   }
-  // step_mask_: bit i enables kernel class i of the decode step (all ones in production; bench.py --ablate times the
-  // step with classes removed, inside the CUDA graph, to attribute in-graph time to each kernel class)
-  const unsigned mk = step_mask_;
+  // Per layer: [RMSNorm + Quantize +] QKV Dense, attention, [Quantize +] out Dense (+ residual), [RMSNorm + Quantize +] gate/up
+  // Dense with SwiGLU, [Quantize +] down Dense (+ residual).  At decode (rows <= 64) the bracketed row ops run as the
+  // pre-phase of the following GEMM: 5 launches per layer.
   for (int l = 0; l < mc_.num_layers; ++l) {
     LayerWeights& lw = layers_[l];
     // --- self attention (attention.cc:442-615) ---
-    if (mk & 1u)
-      launch_rms_norm(lw.attn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
-                      xs_.as<float>(), dtype_, stream_);
-    if (mk & 2u) dense(lw.qkv, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, nullptr, -1, qkv_.ptr);
-    if (mk & 4u) attention(l);
-    if (mk & 8u)
-      launch_quantize_rows(attn_.ptr, dtype_, rows, static_cast<int64_t>(H) * D, true, xq_.as<int8_t>(),
-                           xs_.as<float>(), stream_);
-    if (mk & 16u) dense(lw.out, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
+    dense_from_rows(lw.qkv, x_.ptr, lw.attn_gamma.ptr, mc_.d_model, rows, nullptr, -1, qkv_.ptr);
+    attention(l);
+    dense_from_rows(lw.out, attn_.ptr, nullptr, static_cast<int64_t>(H) * D, rows, x_.ptr, -1, x_.ptr);
     // --- feed forward (transformer.cc:21-51) ---
-    if (mk & 32u)
-      launch_rms_norm(lw.ffn_gamma.ptr, x_.ptr, rows, mc_.d_model, mc_.eps, false, nullptr, xq_.as<int8_t>(),
-                      xs_.as<float>(), dtype_, stream_);
-    if (mk & 64u) {
-      GluEpilogue g{xs_.as<float>(), lw.gate.scale.as<float>(), lw.up.scale.as<float>(), h_.ptr, mc_.activation, lw.gate.n};
-      gemm_s8_glu(xq_.as<int8_t>(), lw.gate.weight.as<int8_t>(), lw.up.weight.as<int8_t>(), rows, lw.gate.n, lw.gate.k,
-                  g, dtype_, gemm_impl_, stream_);
-    }
-    if (mk & 128u)
-      launch_quantize_rows(h_.ptr, dtype_, rows, mc_.ffn_dim, true, xq_.as<int8_t>(), xs_.as<float>(), stream_);
-    if (mk & 256u) dense(lw.down, xq_.as<int8_t>(), xs_.as<float>(), nullptr, rows, x_.ptr, -1, x_.ptr);
+    glu_from_rows(lw.gate, lw.up, x_.ptr, lw.ffn_gamma.ptr, rows, h_.ptr);
+    dense_from_rows(lw.down, h_.ptr, nullptr, mc_.ffn_dim, rows, x_.ptr, -1, x_.ptr);
   }
 }
 
@@ -862,7 +954,7 @@ void LlamaDecoder::forward_step(const int32_t* ids_d, const int32_t* lens_d, int
   CT2_REQUIRE(batch <= max_batch_, "forward_step: batch exceeds the KV arena");
   embed(ids_d, batch);
   layers_forward(batch, batch, 1, 0, lens_d);
-  if (step_mask_ & 512u) project(x_.ptr, batch, logits_out_d);
+  project(x_.ptr, batch, logits_out_d);
 }
 
 // =============================================================================================
@@ -874,7 +966,9 @@ Generator::Generator(const std::string& model_dir, const ct2b200_generator_confi
   const int64_t B = decoder_->max_batch(), L = decoder_->max_length();
   ids_d_.alloc(std::max<int64_t>(B, decoder_->prefill_chunk_rows()) * sizeof(int32_t));
   lens_d_.alloc(B * sizeof(int32_t));
-  step_d_.alloc(4 * sizeof(int32_t));
+  step_d_.alloc(8 * sizeof(int32_t));
+  attn_lens_d_.alloc(B * sizeof(int32_t));
+  finished_d_.alloc(B * sizeof(int32_t));
   forced_d_.alloc(B * L * sizeof(int32_t));
   out_d_.alloc(B * L * sizeof(int32_t));
   end_ids_d_.alloc(64 * sizeof(int32_t));
@@ -908,12 +1002,13 @@ void Generator::run_prefill(const int32_t* ids_d, int64_t batch, int64_t time) {
 
 void Generator::launch_step(int64_t batch, int64_t, int) {
   LlamaDecoder& d = *decoder_;
-  d.forward_step(ids_d_.as<int32_t>(), lens_d_.as<int32_t>(), batch, d.logits_buffer());
+  d.forward_step(ids_d_.as<int32_t>(), attn_lens_d_.as<int32_t>(), batch, d.logits_buffer());
   launch_sample_greedy(d.logits_buffer(), batch, d.config().vocab, step_d_.as<int32_t>(), end_ids_d_.as<int32_t>(),
                        forced_d_.as<int32_t>(), ids_d_.as<int32_t>(), out_d_.as<int32_t>(), lens_d_.as<int32_t>(),
                        sample_ws_.as<float>(), sample_ws_.as<int32_t>() + d.max_batch() * 32,
                        sample_ws_.as<int32_t>() + d.max_batch() * 64, sample_ws_.as<float>() + d.max_batch() * 65,
-                       want_scores_ ? scores_d_.as<float>() : nullptr, row_start_d_.as<int32_t>(), d.dtype(), d.stream());
+                       want_scores_ ? scores_d_.as<float>() : nullptr, row_start_d_.as<int32_t>(), attn_lens_d_.as<int32_t>(),
+                       finished_d_.as<int32_t>(), d.dtype(), d.stream());
 }
 
 void Generator::build_step_graph(int64_t batch, int64_t min_length, int num_end_ids) {
@@ -981,7 +1076,9 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   hgen[3] = static_cast<int32_t>(forced_steps);
   // min_length counts GENERATED tokens per row: the kernel compares step - row_start[b] with it
   hgen[1] = static_cast<int32_t>(r.min_length);
-  int32_t* hend = hgen + 4;
+  hgen[4] = static_cast<int32_t>(r.max_length);
+  hgen[5] = hgen[6] = hgen[7] = 0;
+  int32_t* hend = hgen + 8;
   for (size_t i = 0; i < r.end_ids.size(); ++i) hend[i] = r.end_ids[i];
   // step s consumes prompt token fwd + s; row b's first generated token is the sample of step prompt_len - 1 - fwd
   int32_t* hstart = hend + 64;
@@ -990,7 +1087,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   if (fwd > 0)
     CT2_CUDA_CHECK(cudaMemcpyAsync(prompt_d_.ptr, hp, B * fwd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CT2_CUDA_CHECK(cudaMemcpyAsync(forced_d_.ptr, hforced, forced_steps * B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(step_d_.ptr, hgen, 4 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(step_d_.ptr, hgen, 8 * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   if (!r.end_ids.empty())
     CT2_CUDA_CHECK(cudaMemcpyAsync(end_ids_d_.ptr, hend, r.end_ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
   CT2_CUDA_CHECK(cudaMemcpyAsync(row_start_d_.ptr, hstart, B * sizeof(int32_t), cudaMemcpyHostToDevice, st));
@@ -998,6 +1095,8 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   // first decode input = forced[0] (the last common prompt token); positions = fwd
   CT2_CUDA_CHECK(cudaMemcpyAsync(ids_d_.ptr, forced_d_.ptr, B * sizeof(int32_t), cudaMemcpyDeviceToDevice, st));
   launch_fill_i32(lens_d_.as<int32_t>(), B, static_cast<int32_t>(fwd), st);
+  launch_fill_i32(attn_lens_d_.as<int32_t>(), B, static_cast<int32_t>(fwd), st);
+  launch_fill_i32(finished_d_.as<int32_t>(), B, 0, st);
 
   const bool use_graph = cfg_.use_cuda_graph != 0;
   if (use_graph) build_step_graph(B, r.min_length, static_cast<int>(r.end_ids.size()));
@@ -1010,7 +1109,16 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
   if (want_scores_) hscores.resize(static_cast<size_t>(total_steps) * B);
   std::vector<char> finished(B, 0);
   int64_t num_finished = 0;
-  const int64_t check_every = r.end_ids.empty() ? total_steps : 1;
+  // The host looks at the sampled ids only where a row can finish: never without end tokens (the step count is known),
+  // not before the first step at which some row is past min_length (DisableTokens masks the end ids until then,
+  // decoding.cc:852-856), and from there every `poll` steps — the device marks finished rows itself (their K/V stream
+  // stops), so a late look only costs a few steps of a shrinking batch.
+  int64_t first_eos_step = total_steps;
+  if (!r.end_ids.empty())
+    for (int64_t b = 0; b < B; ++b)
+      first_eos_step = std::min<int64_t>(first_eos_step, hstart[b] + std::max<int64_t>(0, r.min_length));
+  const char* poll_env = std::getenv("CT2B200_EOS_POLL");
+  const int64_t poll = std::max<int64_t>(1, poll_env ? std::atoll(poll_env) : 4);
   int32_t* hout = host_pinned_;     // reuse: [steps, B] sampled ids
   int64_t copied = 0;
   auto consume = [&](int64_t upto) {   // host bookkeeping for steps [copied, upto)
@@ -1052,7 +1160,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
     } else {
       launch_step(B, r.min_length, static_cast<int>(r.end_ids.size()));
     }
-    if ((s + 1) % check_every == 0 || s + 1 == total_steps) consume(s + 1);
+    if (s + 1 == total_steps || (s >= first_eos_step && (s - first_eos_step) % poll == poll - 1)) consume(s + 1);
   }
   for (int64_t b = 0; b < B; ++b) {
     if (want_scores_) {
@@ -1104,7 +1212,7 @@ void Generator::bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, i
   std::vector<int32_t> ids(batch * prompt_len);
   for (size_t i = 0; i < ids.size(); ++i) ids[i] = static_cast<int32_t>((7919ull * i + 3) % V);
   CT2_CUDA_CHECK(cudaMemcpy(prompt_d_.ptr, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
-  int32_t gen[4] = {static_cast<int32_t>(prompt_len - 1), 0, 0, 0};
+  int32_t gen[8] = {static_cast<int32_t>(prompt_len - 1), 0, 0, 0, INT32_MAX, 0, 0, 0};
   CT2_CUDA_CHECK(cudaMemcpy(step_d_.ptr, gen, sizeof(gen), cudaMemcpyHostToDevice));
   cudaEvent_t e0, e1, e2, e3;
   cudaEventCreate(&e0);
@@ -1121,10 +1229,8 @@ void Generator::bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, i
   CT2_CUDA_CHECK(cudaMemcpy2DAsync(ids_d_.ptr, sizeof(int32_t), prompt_d_.as<int32_t>() + fwd, prompt_len * sizeof(int32_t),
                                    sizeof(int32_t), batch, cudaMemcpyDeviceToDevice, st));
   launch_fill_i32(lens_d_.as<int32_t>(), batch, static_cast<int32_t>(fwd), st);
-  if (const char* e = std::getenv("CT2B200_STEP_MASK")) {
-    d.set_step_mask(static_cast<unsigned>(std::strtoul(e, nullptr, 0)));
-    if (graph_) { cudaGraphExecDestroy(graph_); graph_ = nullptr; graph_batch_ = -1; }
-  }
+  launch_fill_i32(attn_lens_d_.as<int32_t>(), batch, static_cast<int32_t>(fwd), st);
+  launch_fill_i32(finished_d_.as<int32_t>(), batch, 0, st);
   const bool use_graph = cfg_.use_cuda_graph != 0;
   if (use_graph) build_step_graph(batch, 0, 0);
   auto step = [&]() {

@@ -97,6 +97,7 @@ struct ModelConfig {
   int activation = CT2B200_ACT_SWISH;
   bool embeddings_int8 = true;
   int64_t weight_bytes = 0;
+  std::string float_type;        // stored type of the non-weight float variables (decoder/layer_norm/gamma): what "default" keeps
   std::string weights;           // storage type of the linear layers: int8 | awq_gemm | awq_gemv | float16 | bfloat16 | float32
 };
 
@@ -134,7 +135,6 @@ class LlamaDecoder {
   void tp_connect(const void* handles, int count);
   int64_t prefill_chunk_rows() const { return chunk_rows_; }
   void set_gemm_impl(int impl) { gemm_impl_ = impl; }
-  void set_step_mask(unsigned m) { step_mask_ = m; }
 
  private:
   // how a Dense weight [n, k] is partitioned over the tensor-parallel ranks (models::Model::load, model.cc:662-743)
@@ -144,6 +144,12 @@ class LlamaDecoder {
   DeviceBuffer load_float_vector(const ModelFile& f, const std::string& name);
   void dense(const DenseWeights& w, const int8_t* xq, const float* xs, const void* x_float, int64_t m,
              const void* residual, int act, void* y);
+  // INT8 Dense whose input rows are still in T: [RMSNorm +] Quantize + Dense.  Decode steps (m <= 64) run it as ONE launch
+  // (row pre-phase of gemm_decode.cu); otherwise the row kernel and the GEMM are launched separately (same bits).
+  void dense_from_rows(const DenseWeights& w, const void* x_rows, const void* gamma, int64_t cols, int64_t m,
+                       const void* residual, int act, void* y);
+  void glu_from_rows(const DenseWeights& gate, const DenseWeights& up, const void* x_rows, const void* gamma, int64_t m,
+                     void* h);
   void layers_forward(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d);
   void project(const void* x_rows, int64_t rows, void* logits_out);
   void embed(const int32_t* ids_d, int64_t rows);
@@ -163,11 +169,13 @@ class LlamaDecoder {
   int dtype_ = CT2B200_F16;
   int device_ = 0;
   int gemm_impl_ = CT2B200_GEMM_AUTO;
+  int weight_type_ = CT2B200_WEIGHTS_STORED;
   int sm_count_ = 148;
   cudaStream_t stream_ = nullptr;
   int64_t max_batch_ = 0, max_len_ = 0, chunk_rows_ = 0;
   int attn_splits_ = 1;
-  unsigned step_mask_ = 0xFFFFFFFFu;
+  bool fuse_rows_ = true;          // CT2B200_FUSE_ROWS=0: always launch the row kernels separately
+  DeviceBuffer grid_bar_;          // grid barrier words of the row pre-phase
 
   DenseWeights embeddings_;       // int8 [V,d] + scale, or T [V,d]
   DenseWeights projection_;
@@ -212,6 +220,7 @@ class Generator {
   std::unique_ptr<LlamaDecoder> decoder_;
   // decode-loop device state
   DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_, sample_ws_, scores_d_, row_start_d_;
+  DeviceBuffer attn_lens_d_, finished_d_;    // per row: cache length the attention kernel sees (0 once finished), finished flag
   bool want_scores_ = false;               // the step (and its CUDA graph) also writes per-step log-probabilities
   bool graph_scores_ = false;
   int32_t* host_pinned_ = nullptr;

@@ -28,6 +28,7 @@
 #include "gemm_common.cuh"
 #include "gemm_decode_common.cuh"
 #include "kernels.h"
+#include "row_ops.cuh"
 #include "tc_common.cuh"
 
 namespace ct2b200 {
@@ -69,7 +70,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);               // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                           // [kMaxStages]
   uint64_t* acc_bar = empty_bar + kMaxStages;                            // accumulators complete
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
+  uint64_t* pre_done = acc_bar + 1;                                      // row pre-phase: int8 rows of every CTA are visible
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pre_done + 1);
+  float* pre_red = reinterpret_cast<float*>(ctrl + 256);                 // 4 floats (row_ops.cuh reductions)
   uint32_t* red = reinterpret_cast<uint32_t*>(ctrl + S::kCtrl);          // [CS src][NB][cpr][128] (CS > 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -85,6 +88,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       mbar_init(empty_bar + s, 1);
     }
     mbar_init(acc_bar, 1);
+    mbar_init(pre_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -115,6 +119,12 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         weights(i, kb_lo + i);
       }
       griddep_wait();
+      if constexpr (KIND == 0) {
+        if (p.pre_mode != 0) {                         // the int8 rows are written by this grid: wait for the grid barrier
+          mbar_wait(pre_done, 0);
+          asm volatile("fence.proxy.async.global;" ::: "memory");
+        }
+      }
 #pragma unroll 1
       for (int i = 0; i < pre; ++i) acts(i, kb_lo + i);
 #pragma unroll 1
@@ -156,6 +166,34 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     const bool row_ok = rloc < p.tile_rows && arow < p.n;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     griddep_wait();                                    // a_scale / residual come from the previous kernels
+    if constexpr (KIND == 0) {
+      if (p.pre_mode != 0) {
+        // ===== row pre-phase: these 128 threads quantize row blockIdx.x (+ gridDim.x ...) of the activations =====
+        const int t = static_cast<int>(threadIdx.x) - 64;
+        const T* px = static_cast<const T*>(p.pre_x);
+        const T* pg = static_cast<const T*>(p.pre_gamma);
+        const bool wide = rowop::nv_for<T>(p.pre_cols) != 4;
+#pragma unroll 1
+        for (int64_t r = blockIdx.x; r < p.m; r += gridDim.x) {
+          const T* xr = px + r * p.pre_cols;
+          int8_t* qr = p.pre_q + r * p.pre_cols;
+          if (p.pre_mode == 2) {
+            if (wide) rowop::row_op_128<T, 1, rowop::kMaxNV>(xr, pg, p.pre_cols, p.pre_eps, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
+            else rowop::row_op_128<T, 1, 4>(xr, pg, p.pre_cols, p.pre_eps, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
+          } else {
+            if (wide) rowop::row_op_128<T, 0, rowop::kMaxNV>(xr, nullptr, p.pre_cols, 0.f, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
+            else rowop::row_op_128<T, 0, 4>(xr, nullptr, p.pre_cols, 0.f, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
+          }
+        }
+        __threadfence();                               // this thread's row bytes are visible at gpu scope
+        rowop::bar128(1);
+        if (t == 0) {
+          grid_barrier(p.pre_bar, gridDim.x);
+          mbar_arrive(pre_done);                       // releases the TMA producer's activation loads
+        }
+        rowop::bar128(1);                              // the epilogue reads a_scale of every row: after the grid barrier
+      }
+    }
     float sw0 = 1.f, sw1 = 1.f, bias_t = 0.f;
     if (row_ok) {
       if constexpr (KIND == 0) {
@@ -429,10 +467,32 @@ bool decode_kernel_enabled() {
 
 // The three entry points return false when the shape is not covered (m > 64, raw int32 output, more tiles than one
 // wave holds): the caller then uses the general persistent kernel of gemm_tc.cu.
+namespace {
+// fills the pre-phase fields; false = the row shape / alignment is not covered by row_ops.cuh
+bool set_row_pre(DecParams& p, const RowPre* pre, const int8_t* A, const float* a_scale, int64_t K, int dtype) {
+  if (!pre || pre->mode == 0) return true;
+  bool ok = false;
+  CT2_DISPATCH_DTYPE(dtype, (ok = rowop::covers<T>(K)));
+  if (!ok || (reinterpret_cast<uintptr_t>(pre->x) & 15) || (reinterpret_cast<uintptr_t>(pre->gamma) & 15) ||
+      (reinterpret_cast<uintptr_t>(A) & 7) || pre->bar == nullptr || (pre->mode == 2 && pre->gamma == nullptr))
+    return false;
+  p.pre_mode = pre->mode;
+  p.pre_x = pre->x;
+  p.pre_gamma = pre->gamma;
+  p.pre_eps = pre->eps;
+  p.pre_q = const_cast<int8_t*>(A);
+  p.pre_s = const_cast<float*>(a_scale);
+  p.pre_cols = K;
+  p.pre_bar = pre->bar;
+  return true;
+}
+}  // namespace
+
 bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& e, int dtype,
-                    cudaStream_t st) {
+                    cudaStream_t st, const RowPre* pre) {
   if (!decode_kernel_enabled() || M > 64 || M < 1 || e.a_scale == nullptr || K % 16 != 0) return false;
   DecParams p{};
+  if (!set_row_pre(p, pre, A, e.a_scale, K, dtype)) return false;
   p.a_scale = e.a_scale;
   p.w_scale0 = e.b_scale;
   p.bias = e.bias;
@@ -446,9 +506,10 @@ bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int6
 }
 
 bool gemm_s8_glu_decode(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
-                        const GluEpilogue& g, int dtype, cudaStream_t st) {
+                        const GluEpilogue& g, int dtype, cudaStream_t st, const RowPre* pre) {
   if (!decode_kernel_enabled() || M > 64 || M < 1 || K % 16 != 0) return false;
   DecParams p{};
+  if (!set_row_pre(p, pre, A, g.a_scale, K, dtype)) return false;
   p.a_scale = g.a_scale;
   p.w_scale0 = g.gate_scale;
   p.w_scale1 = g.up_scale;

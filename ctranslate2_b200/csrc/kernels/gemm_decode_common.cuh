@@ -30,7 +30,38 @@ struct DecParams {
   void* y;                  // [m, n] T
   int act;
   int64_t ldy;
+  // Row pre-phase (INT8 kernels): the activations arrive as T rows and are quantized INSIDE this kernel — CTA r < m runs
+  // ops::Quantize (pre_mode 1) or ops::RMSNorm + ops::Quantize (pre_mode 2) for row r (row_ops.cuh, bit-identical to the
+  // standalone row kernel), all CTAs meet at a grid barrier, then the int8 rows are staged by TMA as before.  The weight ring
+  // was filled before that, so HBM keeps streaming under it.  0 = the int8 rows / scales were produced by an earlier kernel.
+  int pre_mode;
+  const void* pre_x;        // [m, k] T
+  const void* pre_gamma;    // [k] T (pre_mode 2)
+  float pre_eps;
+  int8_t* pre_q;            // [m, k] (the tensor tm_x maps)
+  float* pre_s;             // [m] (= a_scale)
+  int64_t pre_cols;         // k
+  unsigned* pre_bar;        // grid barrier: {arrivals, generation}, zero-initialised, owned by the caller
 };
+
+// One thread per CTA: all `nctas` CTAs of the (co-resident, single-wave) grid meet here.  bar[0] counts arrivals, bar[1] is
+// the generation; the last arriver resets the count and bumps the generation (release), the others spin on it (acquire).
+__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas) {
+  unsigned gen;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
+  __threadfence();
+  const unsigned prev = atomicAdd(bar, 1u);
+  if (prev == nctas - 1) {
+    bar[0] = 0u;
+    __threadfence();
+    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
+  } else {
+    unsigned now;
+    do {
+      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
+    } while (now == gen);
+  }
+}
 
 template <int KIND> struct Elem { static constexpr int bytes = KIND == 0 ? 1 : 2; };
 
@@ -68,7 +99,7 @@ __device__ __forceinline__ void dec_finish(const DecParams& p, const uint32_t (&
   for (int j = 0; j < NC; ++j) {                       // all loads first: one memory round trip
     const bool ok = j < nvalid && col0 + j * cstep < p.m;
     res[j] = (rp && ok) ? to_f32(rp[j * step]) : 0.f;
-    if constexpr (KIND == 0) sx[j] = ok ? __ldg(p.a_scale + col0 + j * cstep) : 1.f;
+    if constexpr (KIND == 0) sx[j] = ok ? p.a_scale[col0 + j * cstep] : 1.f;   // plain load: may be written by this grid (pre-phase)
   }
 #pragma unroll
   for (int j = 0; j < NC; ++j) {

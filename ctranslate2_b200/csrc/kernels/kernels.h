@@ -19,7 +19,7 @@ void launch_rms_norm(const void* gamma, const void* x, int64_t rows, int64_t col
 void launch_mul_quantize(const void* a, const void* b, int64_t rows, int64_t cols, int8_t* q, float* scale,
                          int dtype, cudaStream_t st);
 void launch_dequantize_rows(const int8_t* x, const float* scale, int64_t rows, int64_t cols, void* y, int dtype,
-                            cudaStream_t st);
+                            cudaStream_t st, bool reciprocal = false);
 void launch_dequantize_gemm_output(const int32_t* c, const DenseEpilogue& e, int64_t m, int64_t n, int dtype,
                                    cudaStream_t st);
 void launch_embedding_s8(const int8_t* w, const float* scale, const int32_t* ids, int64_t num_ids, int64_t depth,
@@ -62,11 +62,21 @@ void gemm_s8_glu_tc(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int
 void gemm_f16_tc(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
                  int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
 
-// gemm_decode.cu (tcgen05, m <= 64): false = shape not covered, use the general kernel
+// Row pre-phase of the decode GEMM: the kernel quantizes its own activations (ops::Quantize or ops::RMSNorm + ops::Quantize
+// of x [M, K] in the GEMM's dtype, bit-identical to launch_quantize_rows / launch_rms_norm) into q / s before it stages them,
+// behind a grid barrier.  q must be the `A` pointer of the call and s the epilogue's a_scale; bar = 2 zero-initialised words.
+struct RowPre {
+  int mode = 0;                 // 1 Quantize, 2 RMSNorm + Quantize
+  const void* x = nullptr;      // [M, K] T
+  const void* gamma = nullptr;  // [K] T (mode 2)
+  float eps = 0.f;
+  unsigned* bar = nullptr;
+};
+// gemm_decode.cu (tcgen05, m <= 64): false = shape (or pre-phase) not covered, use the general kernel (+ separate row kernel)
 bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
-                    int dtype, cudaStream_t st);
+                    int dtype, cudaStream_t st, const RowPre* pre = nullptr);
 bool gemm_s8_glu_decode(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
-                        const GluEpilogue& glu, int dtype, cudaStream_t st);
+                        const GluEpilogue& glu, int dtype, cudaStream_t st, const RowPre* pre = nullptr);
 bool gemm_f16_decode(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
                      int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
 
@@ -148,7 +158,7 @@ int sample_greedy_chunks(int64_t vocab);
 void launch_sample_greedy(const void* logits, int64_t batch, int64_t vocab, const int32_t* gen, const int32_t* end_ids,
                           const int32_t* forced, int32_t* next_ids, int32_t* out_ids, int32_t* lens, float* part_v,
                           int32_t* part_i, int32_t* tickets, float* part_s, float* step_scores,
-                          const int32_t* row_start, int dtype, cudaStream_t st);
+                          const int32_t* row_start, int32_t* attn_lens, int32_t* finished, int dtype, cudaStream_t st);
 void launch_convert_to_f32(const void* x, int64_t n, float* y, int dtype, cudaStream_t st);
 void launch_convert_from_f32(const float* x, int64_t n, void* y, int dtype, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t st);

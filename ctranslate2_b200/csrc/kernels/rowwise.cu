@@ -7,6 +7,7 @@
 #include <unordered_set>
 
 #include "../common.cuh"
+#include "row_ops.cuh"
 
 namespace ct2b200 {
 
@@ -133,133 +134,56 @@ __global__ void __launch_bounds__(kRowThreads) mul_quantize_kernel(const T* __re
 }
 
 // ---------------------------------------------------------------------------------------------
-// Register-resident fast path of the three "-> int8 row" producers of the decode step:
-//   MODE 0: Quantize(x)      MODE 1: Quantize(T(RMSNorm(x, gamma)))      MODE 2: Quantize(T(a * b))
-//   MODE 3: T(RMSNorm(x, gamma)) written as T (same summation order as MODE 1, so 1 == Quantize o 3 bit-exactly)
-// One CTA per row; the row is read ONCE with 16-byte loads and kept in registers (NV vectors per thread), so the
-// kernel is one global round trip + two block reductions instead of three passes (bit-identical results).
+// Register-resident fast path of the "-> int8 row" producers of the decode step (row_ops.cuh: MODE 0 Quantize, 1 RMSNorm +
+// Quantize, 2 Mul + Quantize, 3 RMSNorm written as T).  One CTA of 128 threads per row, one global round trip; the same
+// device function runs as the row pre-phase of the decode GEMM (gemm_decode.cu), bit-identically.
 // ---------------------------------------------------------------------------------------------
 template <typename T, int MODE, int NV>
-__global__ void __launch_bounds__(kRowThreads) row_to_int8_kernel(const T* __restrict__ x, const T* __restrict__ aux,
-                                                                  int64_t cols, float eps, bool use_residual,
-                                                                  int8_t* __restrict__ q, float* __restrict__ scale,
-                                                                  T* __restrict__ y_out) {
-  constexpr int N = Vec16<T>::N;
-  __shared__ float red[32];
+__global__ void __launch_bounds__(rowop::kThreads) row_to_int8_kernel(const T* __restrict__ x, const T* __restrict__ aux,
+                                                                      int64_t cols, float eps, bool use_residual,
+                                                                      int8_t* __restrict__ q, float* __restrict__ scale,
+                                                                      T* __restrict__ y_out) {
+  __shared__ float red[4];
   griddep_launch();
   griddep_wait();
   const int64_t row = blockIdx.x;
-  const T* xr = x + row * cols;
-  const int64_t nv = cols / N;
-  float v[NV][N];
-  bool have[NV];
-#pragma unroll
-  for (int k = 0; k < NV; ++k) {
-    const int64_t vi = threadIdx.x + static_cast<int64_t>(k) * kRowThreads;
-    have[k] = vi < nv;
-    if (have[k]) {
-      const Vec16<T> d = ld16(xr + vi * N);
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[k][i] = to_f32(d.v[i]);
-    } else {
-#pragma unroll
-      for (int i = 0; i < N; ++i) v[k][i] = 0.f;
-    }
-  }
-  if constexpr (MODE == 2) {
-    const T* br = aux + row * cols;
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-      if (have[k]) {
-        const Vec16<T> d = ld16(br + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N);
-#pragma unroll
-        for (int i = 0; i < N; ++i) v[k][i] = round_to<T>(v[k][i] * to_f32(d.v[i]));
-      }
-  }
-  if constexpr (MODE == 1 || MODE == 3) {
-    Vec16<T> gv[NV];
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-      if (have[k]) gv[k] = ld16(aux + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N);
-    float ss = 0.f;
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-#pragma unroll
-      for (int i = 0; i < N; ++i) ss += v[k][i] * v[k][i];
-    // NOTE: the summation order differs from the 3-pass kernel, so `inv` may differ in the last ulp from
-    // rms_norm_kernel; both are valid fp32 evaluations of the same reference formula (fp tolerance class).
-    ss = block_reduce<false>(ss, red);
-    const float inv = rsqrtf(ss / static_cast<float>(cols) + eps);
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-      if (have[k]) {
-#pragma unroll
-        for (int i = 0; i < N; ++i) {
-          const float g = to_f32(gv[k].v[i]) + (use_residual ? 1.f : 0.f);
-          v[k][i] = round_to<T>(v[k][i] * inv * g);
-        }
-      }
-  }
-  if constexpr (MODE == 3) {
-#pragma unroll
-    for (int k = 0; k < NV; ++k)
-      if (have[k]) {
-        Vec16<T> o;
-#pragma unroll
-        for (int i = 0; i < N; ++i) o.v[i] = from_f32<T>(v[k][i]);
-        st16(y_out + row * cols + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N, o);
-      }
-    return;
-  }
-  float amax = 0.f;
-#pragma unroll
-  for (int k = 0; k < NV; ++k)
-#pragma unroll
-    for (int i = 0; i < N; ++i) amax = fmaxf(amax, fabsf(v[k][i]));
-  amax = block_reduce<true>(amax, red);
-  const float s = amax != 0.f ? 127.f / amax : 1.f;
-  int8_t* qr = q + row * cols;
-#pragma unroll
-  for (int k = 0; k < NV; ++k)
-    if (have[k]) {
-      int8_t out[N];
-#pragma unroll
-      for (int i = 0; i < N; ++i) out[i] = static_cast<int8_t>(nearbyintf(v[k][i] * s));
-      int8_t* dst = qr + (threadIdx.x + static_cast<int64_t>(k) * kRowThreads) * N;
-      if constexpr (N == 8) *reinterpret_cast<uint2*>(dst) = *reinterpret_cast<uint2*>(out);
-      else *reinterpret_cast<uint32_t*>(dst) = *reinterpret_cast<uint32_t*>(out);
-    }
-  if (threadIdx.x == 0) scale[row] = s;
+  const T* auxr = MODE == 2 ? aux + row * cols : aux;
+  rowop::row_op_128<T, MODE, NV>(x + row * cols, auxr, cols, eps, use_residual, q ? q + row * cols : nullptr,
+                             scale ? scale + row : nullptr, y_out ? y_out + row * cols : nullptr, red,
+                             static_cast<int>(threadIdx.x), 1);
 }
 
 // returns false when the shape/alignment is not covered (caller falls back to the generic kernels)
 template <typename T, int MODE>
 bool launch_row_to_int8(const T* x, const T* aux, int64_t rows, int64_t cols, float eps, bool use_residual, int8_t* q,
                         float* scale, cudaStream_t st, T* y_out = nullptr) {
-  constexpr int N = Vec16<T>::N;
-  if (cols % N != 0 || (reinterpret_cast<uintptr_t>(x) & 15) || (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) ||
+  if (!rowop::covers<T>(cols) || (reinterpret_cast<uintptr_t>(x) & 15) || (aux && (reinterpret_cast<uintptr_t>(aux) & 15)) ||
       (reinterpret_cast<uintptr_t>(q) & 7) || (reinterpret_cast<uintptr_t>(y_out) & 15))
     return false;
-  const int64_t nv = cols / N;
-  const int per = static_cast<int>((nv + kRowThreads - 1) / kRowThreads);
-  if (per <= 1) launch_pdl(row_to_int8_kernel<T, MODE, 1>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
-  else if (per <= 2) launch_pdl(row_to_int8_kernel<T, MODE, 2>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
-  else if (per <= 4) launch_pdl(row_to_int8_kernel<T, MODE, 4>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
-  else if (per <= 8) launch_pdl(row_to_int8_kernel<T, MODE, 8>, dim3(rows), dim3(kRowThreads), 0, st, x, aux, cols, eps, use_residual, q, scale, y_out);
-  else return false;
+  if (rowop::nv_for<T>(cols) == 4)
+    launch_pdl(row_to_int8_kernel<T, MODE, 4>, dim3(rows), dim3(rowop::kThreads), 0, st, x, aux, cols, eps, use_residual, q,
+               scale, y_out);
+  else
+    launch_pdl(row_to_int8_kernel<T, MODE, rowop::kMaxNV>, dim3(rows), dim3(rowop::kThreads), 0, st, x, aux, cols, eps,
+               use_residual, q, scale, y_out);
   return true;
 }
 
 // ---------------------------------------------------------------------------------------------
 // ops::Dequantize  (src/ops/dequantize_gpu.cu:16-27 rows form, :30-144 GEMM-output form)
 // ---------------------------------------------------------------------------------------------
+// reciprocal = false: y = x / scale (the CUDA kernel of the reference, dequantize_gpu.cu:16-27); true: y = x * (1 / scale), the
+// reference's CPU kernel (dequantize_cpu.cc:12-21), which is what converts int8 weights to float at load (model.cc:331-341)
 template <typename T>
 __global__ void dequantize_rows_kernel(const int8_t* __restrict__ x, const float* __restrict__ scale, int64_t cols,
-                                       T* __restrict__ y) {
+                                       T* __restrict__ y, bool reciprocal) {
   const int64_t row = blockIdx.x;
   const float s = scale[row];
-  for (int64_t j = threadIdx.x; j < cols; j += blockDim.x)
-    y[row * cols + j] = from_f32<T>(__fdiv_rn(static_cast<float>(x[row * cols + j]), s));
+  const float r = __fdiv_rn(1.f, s);
+  for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float v = static_cast<float>(x[row * cols + j]);
+    y[row * cols + j] = from_f32<T>(reciprocal ? __fmul_rn(v, r) : __fdiv_rn(v, s));
+  }
 }
 
 template <typename T>
@@ -451,9 +375,9 @@ void launch_mul_quantize(const void* a, const void* b, int64_t rows, int64_t col
 }
 
 void launch_dequantize_rows(const int8_t* x, const float* scale, int64_t rows, int64_t cols, void* y, int dtype,
-                            cudaStream_t st) {
+                            cudaStream_t st, bool reciprocal) {
   if (rows == 0) return;
-  CT2_DISPATCH_DTYPE(dtype, (dequantize_rows_kernel<T><<<rows, 256, 0, st>>>(x, scale, cols, static_cast<T*>(y))));
+  CT2_DISPATCH_DTYPE(dtype, (dequantize_rows_kernel<T><<<rows, 256, 0, st>>>(x, scale, cols, static_cast<T*>(y), reciprocal)));
   check_launch();
 }
 

@@ -15,8 +15,16 @@ import numpy as np
 
 from ._lib import GeneratorConfig, check, lib
 
-_COMPUTE = {"float32": 0, "int8_float32": 0, "float16": 1, "int8_float16": 1, "int8": 1, "default": 1, "auto": 1,
-            "bfloat16": 2, "int8_bfloat16": 2}
+_F32, _F16, _BF16 = 0, 1, 2
+_STORED, _INT8, _FLOAT = 0, 1, 2
+# compute type -> (ct2b200_dtype of the activations or None = the model's stored float type, ct2b200_weight_type), following
+# compute_type_to_data_type / resolve_compute_type of the reference (src/types.cc): "default" keeps what the model stores (an
+# int8 model with float32 norms runs as int8_float32), "int8" means int8 weights with float32 activations, "auto" keeps the
+# stored weights and runs float32 models in float16 (the fastest supported type).  Weights are converted at load, on the GPU.
+_COMPUTE = {"default": (None, _STORED), "auto": (None, _STORED), "int8": (_F32, _INT8), "int8_float32": (_F32, _INT8),
+            "int8_float16": (_F16, _INT8), "int8_bfloat16": (_BF16, _INT8), "float16": (_F16, _FLOAT),
+            "bfloat16": (_BF16, _FLOAT), "float32": (_F32, _FLOAT)}
+_FLOAT_IDS = {"float32": _F32, "float16": _F16, "bfloat16": _BF16}
 
 
 @dataclass
@@ -32,6 +40,40 @@ def model_summary(model_path: str) -> dict:
     buf = ctypes.create_string_buffer(2048)
     check(lib().ct2b200_model_summary(model_path.encode(), buf, ctypes.c_size_t(len(buf))))
     return json.loads(buf.value.decode())
+
+
+# GenerationOptions (include/ctranslate2/generation.h:14-78) this engine does not implement, with the only value of each it
+# accepts (the reference's default, under which the option is a no-op); everything else raises instead of being ignored.
+_NEUTRAL_OPTIONS = {
+    "patience": 1, "repetition_penalty": 1, "no_repeat_ngram_size": 0, "disable_unk": False, "suppress_sequences": None,
+    "sampling_topp": 1, "sampling_temperature": 1, "num_hypotheses": 1, "return_logits_vocab": False,
+    "return_alternatives": False, "min_alternative_expansion_prob": 0, "static_prompt": None, "cache_static_prompt": True,
+    "callback": None, "asynchronous": False, "max_batch_size": 0, "batch_type": "examples",
+}
+
+
+def _is_neutral(name, value) -> bool:
+    neutral = _NEUTRAL_OPTIONS[name]
+    if neutral is None:                       # list-valued options: None or empty
+        return value is None or (hasattr(value, "__len__") and len(value) == 0)
+    if isinstance(neutral, bool):             # True == 1 in Python: compare flags as flags, not as numbers
+        return isinstance(value, (bool, np.bool_)) and bool(value) == neutral
+    if isinstance(neutral, str):
+        return value == neutral
+    return not isinstance(value, (bool, np.bool_)) and isinstance(value, (int, float, np.integer, np.floating)) \
+        and float(value) == float(neutral)
+
+
+def _check_options(options: dict, max_length: int, min_length: int) -> None:
+    for k, v in options.items():
+        if k not in _NEUTRAL_OPTIONS:
+            raise ValueError(f"unknown generation option: {k}")
+        if not _is_neutral(k, v):
+            raise ValueError(f"unsupported generation option: {k}={v!r} (this engine implements the default "
+                             f"{_NEUTRAL_OPTIONS[k]!r} only)")
+    if max_length == 0 or min_length > max_length:
+        # decoding.cc:1035-1040
+        raise ValueError("max_length must be > 0 and min_length must be <= max_length")
 
 
 def _validate_ids(rows, vocab_size: int) -> None:
@@ -73,8 +115,15 @@ class Generator:
         if tensor_parallel:
             from .parallel import default_rank_and_size
             self.tp_rank, self.tp_size = default_rank_and_size(tp_rank, tp_size, tp_group)
-        cfg = GeneratorConfig(device_index, _COMPUTE[compute_type], max_batch_size, max_length, self.tp_rank,
-                              self.tp_size, int(use_cuda_graph), gemm_impl)
+        dtype, weight_type = _COMPUTE[compute_type]
+        if dtype is None:
+            summary = model_summary(model_path)
+            dtype = _F16 if summary["weights"].startswith("awq") else _FLOAT_IDS[summary["float_type"]]
+            if compute_type == "auto" and dtype == _F32:
+                dtype = _F16
+        self.compute_type = compute_type
+        cfg = GeneratorConfig(device_index, dtype, max_batch_size, max_length, self.tp_rank,
+                              self.tp_size, int(use_cuda_graph), gemm_impl, weight_type)
         self._h = lib().ct2b200_generator_open(model_path.encode(), ctypes.byref(cfg))
         if not self._h:
             raise RuntimeError(lib().ct2b200_last_error().decode())
@@ -132,9 +181,7 @@ class Generator:
         if include_prompt_in_result:
             raise ValueError("include_prompt_in_result=True forces the prompt through the decode loop token by "
                              "token (decoding.cc:21-67); pass False (docs/performance.md)")
-        for k, v in unsupported.items():
-            if v not in (None, False, 0, 1, 1.0):
-                raise ValueError(f"unsupported generation option: {k}")
+        _check_options(unsupported, max_length, min_length)
         rows = [list(r) for r in start_tokens]
         if not rows:
             return []                       # an empty batch is an empty result (replica_pool.h: no job is posted)

@@ -119,6 +119,45 @@ def dense_int8(xq, x_scale, w, w_scale, bias=None, residual=None, activation_typ
     return y
 
 
+_barrier_words = {}
+
+
+def _barrier(device):
+    """Grid-barrier words of the row pre-phase (two zero-initialised uint32), one buffer per device."""
+    key = str(device)
+    if key not in _barrier_words:
+        _barrier_words[key] = torch.zeros(64, dtype=torch.int32, device=device)
+    return _barrier_words[key]
+
+
+def dense_int8_rows(x, w, w_scale, gamma=None, eps=1e-5, bias=None, residual=None, activation_type=None):
+    """[RMSNorm +] Quantize + layers::Dense (INT8 arm) from rows in T: ONE launch for m <= 64.  Returns (y, xq, x_scale)."""
+    x, w = _c(x), _c(w)
+    m, k = x.shape
+    n = w.shape[0]
+    y = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    xq = torch.empty((m, k), dtype=torch.int8, device=x.device)
+    xs = torch.empty((m,), dtype=torch.float32, device=x.device)
+    act = -1 if activation_type is None else activation_type
+    check(lib().ct2b200_dense_s8_rows(_p(x), _p(gamma), ctypes.c_float(eps), _p(w), _p(w_scale), _p(bias), _p(residual), act,
+                                      ctypes.c_int64(m), ctypes.c_int64(n), ctypes.c_int64(k), _p(y), _dt(x), _p(xq), _p(xs),
+                                      _p(_barrier(x.device)), _stream()))
+    return y, xq, xs
+
+
+def dense_int8_glu_rows(x, w_gate, gate_scale, w_up, up_scale, gamma=None, eps=1e-5, activation_type=ActivationType.Swish):
+    x = _c(x)
+    m, k = x.shape
+    n = w_gate.shape[0]
+    h = torch.empty((m, n), dtype=x.dtype, device=x.device)
+    xq = torch.empty((m, k), dtype=torch.int8, device=x.device)
+    xs = torch.empty((m,), dtype=torch.float32, device=x.device)
+    check(lib().ct2b200_dense_s8_glu_rows(_p(x), _p(gamma), ctypes.c_float(eps), _p(_c(w_gate)), _p(gate_scale), _p(_c(w_up)),
+                                          _p(up_scale), activation_type, ctypes.c_int64(m), ctypes.c_int64(n),
+                                          ctypes.c_int64(k), _p(h), _dt(x), _p(xq), _p(xs), _p(_barrier(x.device)), _stream()))
+    return h, xq, xs
+
+
 def dense_int8_glu(xq, x_scale, w_gate, gate_scale, w_up, up_scale, activation_type=ActivationType.Swish,
                    dtype=torch.float16, impl=GEMM_AUTO):
     """FeedForwardNetwork gate/up pair fused (src/layers/transformer.cc:21-51)."""

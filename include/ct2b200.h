@@ -92,6 +92,21 @@ CT2B200_API int ct2b200_dense_s8_glu(const int8_t* xq_d, const float* x_scale_d,
                          const float* w_gate_scale_d, const int8_t* w_up_d, const float* w_up_scale_d, int act,
                          int64_t m, int64_t n, int64_t k, void* h_d, int dtype, int impl, void* stream);
 
+/* The whole quantized arm of layers::Dense::operator() INCLUDING its input side, as ONE launch when m <= 64 —
+ * src/layers/common.cc:353-401 preceded by ops::Quantize (quantize.cc:21-50) or, with gamma_d, by the layer's pre-norm
+ * ops::RMSNorm (rms_norm_gpu.cu:19-63):  xq, x_scale = Quantize([RMSNorm(x, gamma, eps)]);  y = dense_s8(xq, x_scale, ...).
+ * x [m,k] T; xq_d [m,k] int8 and x_scale_d [m] are OUTPUTS (the same bits ct2b200_quantize_rows / ct2b200_rms_norm_quantize
+ * produce); barrier_d = two zero-initialised uint32 owned by the caller (grid barrier of the row pre-phase, reusable by
+ * later calls on the same stream).  m > 64 or uncovered shapes run the row kernel and the GEMM as two launches. */
+CT2B200_API int ct2b200_dense_s8_rows(const void* x_d, const void* gamma_d, float eps, const int8_t* w_d, const float* w_scale_d,
+                          const void* bias_d, const void* residual_d, int act, int64_t m, int64_t n, int64_t k,
+                          void* y_d, int dtype, int8_t* xq_d, float* x_scale_d, unsigned* barrier_d, void* stream);
+/* same for the gate/up pair: h = act(dense(xq, w_gate)) * dense(xq, w_up) */
+CT2B200_API int ct2b200_dense_s8_glu_rows(const void* x_d, const void* gamma_d, float eps, const int8_t* w_gate_d,
+                              const float* w_gate_scale_d, const int8_t* w_up_d, const float* w_up_scale_d, int act,
+                              int64_t m, int64_t n, int64_t k, void* h_d, int dtype, int8_t* xq_d, float* x_scale_d,
+                              unsigned* barrier_d, void* stream);
+
 /* primitives<Device::CUDA>::gemm<float16_t|bfloat16_t> (trans_b, alpha 1, beta 0) + ops::Gemm's
  * apply_bias_and_activation — src/cuda/primitives.cu:485-569, src/ops/gemm.cc:10-25.
  * a [m,k] T, b [n,k] T -> c [m,n] T, fp32 accumulation; dtype F16 or BF16. */
@@ -200,14 +215,21 @@ CT2B200_API int ct2b200_dequantize_awq(const int32_t* qweight_d, const void* sca
  * ------------------------------------------------------------------------------------------- */
 typedef struct ct2b200_generator ct2b200_generator;
 
+/* Weight type requested by the compute type (models::Model::set_compute_type / ensure_dtype, src/models/model.cc:178-234,
+ * 304-369): STORED = "default" (keep what model.bin holds), INT8 = the int8* compute types (float weights are quantized at
+ * load: scale = 127 / amax per row, q = rint(w * scale)), FLOAT = float16 / bfloat16 (int8 weights are dequantized at load).
+ * The conversion runs on the GPU.  AWQ-INT4 models ignore it (the reference pins ComputeType::FLOAT16, model.cc:750-757). */
+typedef enum { CT2B200_WEIGHTS_STORED = 0, CT2B200_WEIGHTS_INT8 = 1, CT2B200_WEIGHTS_FLOAT = 2 } ct2b200_weight_type;
+
 typedef struct {
   int device;               /* CUDA device ordinal */
-  int compute_type;         /* ct2b200_dtype of activations / KV cache; weights keep their stored type */
+  int compute_type;         /* ct2b200_dtype of activations / KV cache */
   int64_t max_batch;        /* batch slots to reserve */
   int64_t max_length;       /* max total positions (prompt + generated) per sequence */
   int tp_rank, tp_size;     /* tensor-parallel rank/size (1 = off); see ct2b200_generator_tp_connect */
   int use_cuda_graph;       /* capture the decode step in a CUDA graph */
   int gemm_impl;            /* ct2b200_gemm_impl */
+  int weight_type;          /* ct2b200_weight_type: what Model::set_compute_type asks of the Dense / embedding weights */
 } ct2b200_generator_config;
 
 /* models::Model::load(model_dir, Device::CUDA, device, compute_type) + Generator ctor.

@@ -504,6 +504,31 @@ class DecoderWeights:
             awq_group=int(cfg.get("quantization_group_size") or 128))
 
 
+def ensure_compute_type(w: "DecoderWeights", weights: str, float_dtype=np.float32) -> "DecoderWeights":
+    """Model::set_compute_type + ensure_dtype (src/models/model.cc:178-234, 304-369) for the variables of a decoder:
+    every variable whose name ends in "weight" (is_quantizable, :288-290) is brought to the weight type of the requested
+    compute type — weights="int8": a float matrix is quantized row-wise on its float32 value with ops::Quantize
+    (scale = 127/amax or 1, q = rint(w*scale)) and "<name>_scale" is registered; weights="float": an int8 matrix becomes
+    float_dtype(float32(q) * (1/scale)) (the CPU Dequantize, dequantize_cpu.cc:12-21, the load happens on the CPU) and its
+    scale is removed.  AWQ variables (int32) are left alone (model.cc:750-757)."""
+    import dataclasses
+    v = dict(w.v)
+    for name in list(v):
+        if name not in v:
+            continue
+        a = v[name]
+        if not name.endswith("weight") or a.ndim != 2 or a.dtype == np.int32:
+            continue
+        if weights == "int8" and a.dtype != np.int8:
+            q, sc = quantize_rows(a.astype(f32))
+            v[name], v[name + "_scale"] = q, sc
+        elif weights == "float" and a.dtype == np.int8:
+            r = (f32(1) / v[name + "_scale"].astype(f32)).astype(f32)
+            v[name] = (a.astype(f32) * r[:, None]).astype(f32).astype(float_dtype)
+            del v[name + "_scale"]
+    return dataclasses.replace(w, v=v)
+
+
 def layer_norm(x: np.ndarray, gamma: np.ndarray, beta: np.ndarray, eps: float = 1e-5) -> np.ndarray:
     """ops::LayerNorm over the last axis.  src/cpu/kernels.cc:463-495: mean = sum/n, var = max(sum(x^2)/n - mean^2, 0),
     y = (x - mean) / sqrt(var + eps) * gamma + beta  (eps 1e-5 when the layer has a beta, layers/common.cc:449-453)."""

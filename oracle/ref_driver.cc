@@ -278,7 +278,7 @@ int ref_forward(void* handle, const int32_t* ids, int B, int T, int return_log_p
       for (int t = 0; t < T; ++t)
         v[b][t] = ids[b * T + t];
     StorageView logits = g->generator->forward_batch_async(v, return_log_probs != 0).get();
-    StorageView f = logits.to_float32();
+    StorageView f = logits.to_float32().to(Device::CPU);      // the CUDA build returns device memory
     if (f.size() > out_capacity)
       throw std::runtime_error("ref_forward: output buffer too small");
     std::memcpy(out, f.data<float>(), f.size() * sizeof(float));

@@ -341,3 +341,34 @@ def test_invalid_arguments_raise():
         ops.TopK(100)(torch.zeros((2, 8), device=DEV))
     with pytest.raises(ValueError):
         ops.Quantize()(torch.zeros((2, 8)))   # CPU tensor: no CPU path
+
+
+@gpu
+@pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
+@pytest.mark.parametrize("mnk", [(1, 512, 1024), (5, 6144, 4096), (32, 4096, 4096), (64, 4096, 14336), (33, 1000, 2048)])
+def test_dense_int8_rows_fused_is_bit_identical(dtype, mnk):
+    """Row pre-phase of the decode GEMM (gemm_decode.cu + row_ops.cuh): [RMSNorm +] Quantize + Dense in ONE launch gives
+    exactly the bits of the separate ops::Quantize / RMSNorm + Quantize kernels followed by the fused Dense — int8 rows,
+    scales and outputs; repeated calls reuse the grid-barrier words."""
+    m, n, k = mnk
+    r = np.random.default_rng(m + n)
+    x = dev(r.standard_normal((m, k)).astype(np.float32) * 3, TDT[dtype])
+    gamma = dev(r.uniform(0.5, 1.5, size=k).astype(np.float32), TDT[dtype])
+    res = dev(r.standard_normal((m, n)).astype(np.float32), TDT[dtype])
+    w = dev(r.integers(-127, 128, size=(n, k)).astype(np.int8))
+    ws = dev(r.uniform(500, 4000, size=n).astype(np.float32))
+    w2 = dev(r.integers(-127, 128, size=(n, k)).astype(np.int8))
+    for rep in range(3):
+        for g in (None, gamma):
+            if g is None:
+                xq0, xs0 = ops.Quantize()(x)
+            else:
+                xq0, xs0 = ops.RMSNorm(1e-5).quantize(g, x)
+            y0 = ops.dense_int8(xq0, xs0, w, ws, residual=res, dtype=TDT[dtype])
+            y1, xq1, xs1 = ops.dense_int8_rows(x, w, ws, gamma=g, eps=1e-5, residual=res)
+            assert torch.equal(xq0, xq1) and torch.equal(xs0, xs1)
+            assert torch.equal(y0, y1)
+            h0 = ops.dense_int8_glu(xq0, xs0, w, ws, w2, ws, dtype=TDT[dtype])
+            h1, xq2, xs2 = ops.dense_int8_glu_rows(x, w, ws, w2, ws, gamma=g, eps=1e-5)
+            assert torch.equal(xq0, xq2) and torch.equal(xs0, xs2)
+            assert torch.equal(h0, h1)

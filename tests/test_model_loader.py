@@ -70,3 +70,56 @@ def test_empty_batch_is_an_empty_result_without_touching_the_device():
     g = Generator.__new__(Generator)        # no model, no device: the empty batch must return before either is needed
     g._h = None
     assert g.generate_batch([]) == []
+
+
+@pytest.mark.parametrize("extra,omit", [
+    ({"decoder/scale_embeddings": __import__("numpy").int8(1)}, ("decoder/scale_embeddings",)),      # sqrt(d_model) scaling on
+    ({}, ("decoder/scale_embeddings",)),                                                             # absent = on in the reference
+    ({"decoder/scale_embeddings": __import__("numpy").float32(2.5)}, ("decoder/scale_embeddings",)),
+    ({"decoder/alibi": __import__("numpy").int8(1)}, ("decoder/alibi",)),
+    ({"decoder/sliding_window": __import__("numpy").int32(128)}, ()),
+    ({"decoder/layer_0/self_attention/sliding_window": __import__("numpy").int32(128)}, ()),
+    ({"decoder/layer_1/self_attention/q_norm/gamma": __import__("numpy").ones(64, "float32")}, ()),
+    ({"decoder/layer_1/self_attention/k_norm/gamma": __import__("numpy").ones(64, "float32")}, ()),
+    ({"decoder/layer_0/self_attention/layer_norm/layer_norm_use_residual": __import__("numpy").int8(1)}, ()),
+    ({"decoder/layer_norm/layer_norm_use_residual": __import__("numpy").int8(1)}, ()),
+    ({"decoder/layernorm_embedding/gamma": __import__("numpy").ones(512, "float32")}, ()),
+    ({"decoder/project_in/weight": __import__("numpy").ones((512, 512), "float32")}, ()),
+    ({"decoder/project_out/weight": __import__("numpy").ones((512, 512), "float32")}, ()),
+    ({"decoder/layer_0/input_layer_norm/gamma": __import__("numpy").ones(512, "float32")}, ()),
+    ({"decoder/layer_0/post_attention_layer_norm/gamma": __import__("numpy").ones(512, "float32")}, ()),
+    ({"decoder/layer_1/pre_feedforward_layer_norm/gamma": __import__("numpy").ones(512, "float32")}, ()),
+    ({"decoder/layer_1/post_feedforward_layer_norm/gamma": __import__("numpy").ones(512, "float32")}, ()),
+    ({"decoder/layer_2/shared_layer_norm/gamma": __import__("numpy").ones(512, "float32")}, ()),
+    ({"decoder/final_logit_softcapping": __import__("numpy").float32(30.0)}, ()),
+    ({"decoder/layer_0/self_attention/queries_scale": __import__("numpy").float32(0.5)}, ()),
+])
+def test_decoder_features_the_engine_does_not_implement_are_refused(tmp_path, extra, omit):
+    """The reference honours these TransformerDecoderSpec attributes (transformer.cc:380-400, 475-530, attention.cc:314-315,
+    common.cc:448); a model that uses one must not load and silently produce other tokens (Gemma: scaled embeddings + 1 + gamma
+    norms, Mistral: sliding window, Qwen3: q/k norms, Falcon / GPT-J: shared / parallel norms)."""
+    cfg = LlamaConfig(num_layers=3, num_heads=8, num_heads_kv=2, head_dim=64, ffn_dim=1280, vocab_size=320)
+    d = str(tmp_path / "m")
+    write_llama_model(d, cfg, "float16", seed=3, init_std=0.05, extra=extra, omit=omit)
+    with pytest.raises(ValueError):
+        ct2.model_summary(d)
+
+
+def test_generation_options_are_rejected_unless_neutral():
+    """GenerationOptions the engine does not implement raise unless they hold the reference's default — flags are compared
+    as flags (True == 1 in Python: disable_unk=True must not pass as "1")."""
+    from ctranslate2_b200.generator import _check_options
+    _check_options({}, 8, 0)
+    _check_options({"repetition_penalty": 1.0, "no_repeat_ngram_size": 0, "disable_unk": False, "suppress_sequences": [],
+                    "static_prompt": None, "sampling_temperature": 1, "num_hypotheses": 1, "asynchronous": False,
+                    "cache_static_prompt": True, "callback": None}, 8, 8)
+    for bad in ({"disable_unk": True}, {"return_logits_vocab": True}, {"return_alternatives": True}, {"asynchronous": True},
+                {"no_repeat_ngram_size": 1}, {"repetition_penalty": 1.2}, {"sampling_temperature": 0.7}, {"num_hypotheses": 2},
+                {"suppress_sequences": [["a"]]}, {"static_prompt": ["a"]}, {"sampling_topp": 0.9}, {"patience": 2},
+                {"cache_static_prompt": False}, {"not_an_option": 0}, {"num_hypotheses": True}):
+        with pytest.raises(ValueError):
+            _check_options(bad, 8, 0)
+    with pytest.raises(ValueError):
+        _check_options({}, 0, 0)            # max_length == 0 (decoding.cc:1035-1040)
+    with pytest.raises(ValueError):
+        _check_options({}, 4, 5)            # min_length > max_length

@@ -230,6 +230,27 @@ def test_live_reference_synthetic_writer_roundtrip(tmp_path):
 
 
 @pytest.mark.skipif(not refapi.available(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("stored,requested", [("float32", "int8"), ("float16", "int8"), ("int8", "float32")])
+def test_live_reference_on_load_compute_type_conversion(tmp_path, stored, requested):
+    """Model::set_compute_type / ensure_dtype (model.cc:178-234, 304-369): a float model requested as int8 is quantized at
+    load, an int8 model requested as float32 is dequantized — the oracle's restatement against the unmodified reference."""
+    from ctranslate2_b200.converters.synthetic import LlamaConfig, write_llama_model
+    cfg = LlamaConfig(num_layers=2, num_heads=4, num_heads_kv=2, head_dim=32, ffn_dim=192, vocab_size=150)
+    mdir = str(tmp_path / "m")
+    write_llama_model(mdir, cfg, stored, seed=6, init_std=0.05)
+    g = refapi.RefGenerator(mdir, requested, 2)
+    prompts = np.random.default_rng(1).integers(3, 150, size=(2, 7), dtype=np.int32)
+    ref_logits = g.forward(prompts)
+    g.close()
+    w = O.ensure_compute_type(O.DecoderWeights.from_dir(mdir, "cpu"), "int8" if requested == "int8" else "float")
+    if stored == "float16":      # non-weight variables (norms) are converted to float32 on the CPU (is_convertible branch)
+        w.v.update({k: a.astype(np.float32) for k, a in w.v.items() if a.dtype == np.float16})
+    m = O.LlamaOracle(w)
+    m.reset(2)
+    np.testing.assert_allclose(m.forward(prompts.astype(np.int64), 0), ref_logits, atol=5e-5)
+
+
+@pytest.mark.skipif(not refapi.available(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("kw", [dict(), dict(scaling_type=0, scaling_factor=4.0),
                                 dict(scaling_type=2, scaling_factor=8.0, low_freq_factor=1.0, high_freq_factor=4.0,
                                      original_max_position_embeddings=8192)])
