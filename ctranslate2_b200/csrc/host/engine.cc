@@ -710,13 +710,28 @@ void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* x
   }
 }
 
+namespace {
+NextWeights successor(const DenseWeights* next, const DenseWeights* next_up) {
+  NextWeights nw;
+  if (next && next->kind == DenseWeights::INT8) {
+    nw.w = next->weight.ptr;
+    nw.w2 = next_up ? next_up->weight.ptr : nullptr;
+    nw.n = next->n;
+    nw.k = next->k;
+  }
+  return nw;
+}
+}  // namespace
+
 void LlamaDecoder::dense_from_rows(const DenseWeights& w, const void* x_rows, const void* gamma, int64_t cols, int64_t m,
-                                   const void* residual, int act, void* y) {
+                                   const void* residual, int act, void* y, const DenseWeights* next,
+                                   const DenseWeights* next_up) {
   const bool tc = gemm_impl_ == CT2B200_GEMM_TCGEN05 || (gemm_impl_ == CT2B200_GEMM_AUTO && env_gemm_impl() != CT2B200_GEMM_MMA_SYNC);
   if (fuse_rows_ && tc && m <= 64) {
     RowPre pre{gamma ? 2 : 1, x_rows, gamma, mc_.eps, grid_bar_.as<unsigned>()};
     DenseEpilogue e{xs_.as<float>(), w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
-    if (gemm_s8_decode(xq_.as<int8_t>(), w.weight.as<int8_t>(), m, w.n, w.k, e, dtype_, stream_, &pre)) return;
+    const NextWeights nw = successor(next, next_up);
+    if (gemm_s8_decode(xq_.as<int8_t>(), w.weight.as<int8_t>(), m, w.n, w.k, e, dtype_, stream_, &pre, &nw)) return;
   }
   if (gamma)
     launch_rms_norm(gamma, x_rows, m, cols, mc_.eps, false, nullptr, xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
@@ -726,13 +741,14 @@ void LlamaDecoder::dense_from_rows(const DenseWeights& w, const void* x_rows, co
 }
 
 void LlamaDecoder::glu_from_rows(const DenseWeights& gate, const DenseWeights& up, const void* x_rows, const void* gamma,
-                                 int64_t m, void* h) {
+                                 int64_t m, void* h, const DenseWeights* next) {
   GluEpilogue g{xs_.as<float>(), gate.scale.as<float>(), up.scale.as<float>(), h, mc_.activation, gate.n};
   const bool tc = gemm_impl_ == CT2B200_GEMM_TCGEN05 || (gemm_impl_ == CT2B200_GEMM_AUTO && env_gemm_impl() != CT2B200_GEMM_MMA_SYNC);
   if (fuse_rows_ && tc && m <= 64) {
     RowPre pre{gamma ? 2 : 1, x_rows, gamma, mc_.eps, grid_bar_.as<unsigned>()};
+    const NextWeights nw = successor(next, nullptr);
     if (gemm_s8_glu_decode(xq_.as<int8_t>(), gate.weight.as<int8_t>(), up.weight.as<int8_t>(), m, gate.n, gate.k, g, dtype_,
-                           stream_, &pre))
+                           stream_, &pre, &nw))
       return;
   }
   if (gamma)
@@ -793,12 +809,13 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
   for (int l = 0; l < mc_.num_layers; ++l) {
     LayerWeights& lw = layers_[l];
     // --- self attention (attention.cc:442-615) ---
-    dense_from_rows(lw.qkv, x_.ptr, lw.attn_gamma.ptr, mc_.d_model, rows, nullptr, -1, qkv_.ptr);
+    dense_from_rows(lw.qkv, x_.ptr, lw.attn_gamma.ptr, mc_.d_model, rows, nullptr, -1, qkv_.ptr, &lw.out);
     attention(l);
-    dense_from_rows(lw.out, attn_.ptr, nullptr, static_cast<int64_t>(H) * D, rows, x_.ptr, -1, x_.ptr);
+    dense_from_rows(lw.out, attn_.ptr, nullptr, static_cast<int64_t>(H) * D, rows, x_.ptr, -1, x_.ptr, &lw.gate, &lw.up);
     // --- feed forward (transformer.cc:21-51) ---
-    glu_from_rows(lw.gate, lw.up, x_.ptr, lw.ffn_gamma.ptr, rows, h_.ptr);
-    dense_from_rows(lw.down, h_.ptr, nullptr, mc_.ffn_dim, rows, x_.ptr, -1, x_.ptr);
+    glu_from_rows(lw.gate, lw.up, x_.ptr, lw.ffn_gamma.ptr, rows, h_.ptr, &lw.down);
+    dense_from_rows(lw.down, h_.ptr, nullptr, mc_.ffn_dim, rows, x_.ptr, -1, x_.ptr,
+                    l + 1 < mc_.num_layers ? &layers_[l + 1].qkv : nullptr);
   }
 }
 

@@ -146,10 +146,12 @@ class LlamaDecoder {
              const void* residual, int act, void* y);
   // INT8 Dense whose input rows are still in T: [RMSNorm +] Quantize + Dense.  Decode steps (m <= 64) run it as ONE launch
   // (row pre-phase of gemm_decode.cu); otherwise the row kernel and the GEMM are launched separately (same bits).
+  // next / next_up: the Dense (pair) that follows in the step; its weights are prefetched into L2 (successor prefetch)
   void dense_from_rows(const DenseWeights& w, const void* x_rows, const void* gamma, int64_t cols, int64_t m,
-                       const void* residual, int act, void* y);
+                       const void* residual, int act, void* y, const DenseWeights* next = nullptr,
+                       const DenseWeights* next_up = nullptr);
   void glu_from_rows(const DenseWeights& gate, const DenseWeights& up, const void* x_rows, const void* gamma, int64_t m,
-                     void* h);
+                     void* h, const DenseWeights* next = nullptr);
   void layers_forward(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d);
   void project(const void* x_rows, int64_t rows, void* logits_out);
   void embed(const int32_t* ids_d, int64_t rows);

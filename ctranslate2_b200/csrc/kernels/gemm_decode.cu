@@ -53,7 +53,8 @@ struct DecSmem {
 template <typename T, int KIND, int BN, int NB, int CS>
 __global__ void __launch_bounds__(kTcThreads, 2)
     gemm_decode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                       const __grid_constant__ CUtensorMap tm_w2, const DecParams p) {
+                       const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_n,
+                       const __grid_constant__ CUtensorMap tm_n2, const DecParams p) {
   using S = DecSmem<BN, NB>;
   constexpr int kElem = Elem<KIND>::bytes;
   constexpr int BK = kSwizzleBytes / kElem;
@@ -112,12 +113,24 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       auto acts = [&](int s, int kb) {
         tma_load_2d(smem + s * S::kStage + S::kA, &tm_x, full_bar + s, kb * BK, 0, kEvictLast);
       };
+      // successor prefetch: box j of the next kernel = (matrix j % nb, tile (j / nb) % tiles, K block (j / nb) / tiles)
+      int pf_j = static_cast<int>(blockIdx.x);
+      auto prefetch_one = [&]() {
+        if (pf_j < p.pf_boxes) {
+          const int which = pf_j % p.pf_nb, rest = pf_j / p.pf_nb;
+          const int t2 = rest % p.pf_tiles, kb2 = rest / p.pf_tiles;
+          tma_prefetch_2d(which == 0 ? &tm_n : &tm_n2, kb2 * p.pf_bk, t2 * p.pf_rows);
+          pf_j += static_cast<int>(gridDim.x);
+        }
+      };
       const int pre = min(nstages, nkb);
 #pragma unroll 1
       for (int i = 0; i < pre; ++i) {                  // weights of the first ring fill: before the dependency wait
         mbar_expect_tx(full_bar + i, stage_tx);
         weights(i, kb_lo + i);
       }
+#pragma unroll 1
+      for (int i = 0; i < pre; ++i) prefetch_one();
       griddep_wait();
       if constexpr (KIND == 0) {
         if (p.pre_mode != 0) {                         // the int8 rows are written by this grid: wait for the grid barrier
@@ -134,7 +147,10 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         mbar_expect_tx(full_bar + s, stage_tx);
         weights(s, kb_lo + it);
         acts(s, kb_lo + it);
+        prefetch_one();
       }
+#pragma unroll 1
+      while (pf_j < p.pf_boxes) prefetch_one();         // what the cap allows beyond one box per own K block
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -383,8 +399,8 @@ DecPlan plan_decode(int64_t n, int kb_total, int sm_count) {
 }
 
 template <typename T, int KIND, int BN, int NB, int CS>
-void launch_decode(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tmw2, const DecParams& p,
-                   const DecPlan& plan, cudaStream_t st) {
+void launch_decode(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tmw2, const CUtensorMap& tmn,
+                   const CUtensorMap& tmn2, const DecParams& p, const DecPlan& plan, cudaStream_t st) {
   configure_once<T, KIND, BN, NB, CS>();
   auto kernel = gemm_decode_kernel<T, KIND, BN, NB, CS>;
   cudaLaunchConfig_t cfg{};
@@ -408,13 +424,13 @@ void launch_decode(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtenso
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  CT2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmx, tmw, tmw2, p));
+  CT2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmx, tmw, tmw2, tmn, tmn2, p));
   check_launch();
 }
 
 template <typename T, int KIND, int BN, int NB>
 bool run_decode(const void* x, const void* w, const void* w2, int64_t m, int64_t n, int64_t k, DecParams p,
-                cudaStream_t st) {
+                cudaStream_t st, const NextWeights* next = nullptr) {
   constexpr int elem = Elem<KIND>::bytes;
   int dev = 0, sms = 148;
   cudaGetDevice(&dev);
@@ -441,21 +457,41 @@ bool run_decode(const void* x, const void* w, const void* w2, int64_t m, int64_t
   const CUtensorMap tmx = make_operand_map(x, m, k, elem, KIND, BN);
   const CUtensorMap tmw = make_operand_map(w, n, k, elem, KIND, plan.tile_rows);
   const CUtensorMap tmw2 = make_operand_map(w2 ? w2 : w, n, k, elem, KIND, plan.tile_rows);
+  // successor prefetch: the next Dense's plan gives the boxes its CTAs will load first
+  CUtensorMap tmn = tmw, tmn2 = tmw2;
+  p.pf_boxes = 0;
+  p.pf_tiles = p.pf_nb = p.pf_rows = 1;
+  p.pf_bk = kSwizzleBytes / elem;
+  static const int pf_mb = std::max(0, env_int("CT2B200_L2_PREFETCH_MB", 24));
+  if (next && next->w && pf_mb > 0 && KIND == 0) {
+    const int kb2 = div_up(next->k, kSwizzleBytes / elem);
+    const DecPlan np = next->w2 ? plan_decode<T, KIND, BN, 2>(next->n, kb2, sms) : plan_decode<T, KIND, BN, 1>(next->n, kb2, sms);
+    if (np.cs != 0) {
+      tmn = make_operand_map(next->w, next->n, next->k, elem, KIND, np.tile_rows);
+      tmn2 = make_operand_map(next->w2 ? next->w2 : next->w, next->n, next->k, elem, KIND, np.tile_rows);
+      p.pf_nb = next->w2 ? 2 : 1;
+      p.pf_tiles = np.tiles;
+      p.pf_rows = np.tile_rows;
+      const int64_t total = static_cast<int64_t>(np.tiles) * kb2 * p.pf_nb;
+      const int64_t cap = static_cast<int64_t>(pf_mb) * 1024 * 1024 / (static_cast<int64_t>(np.tile_rows) * kSwizzleBytes);
+      p.pf_boxes = static_cast<int>(std::min(total, cap));
+    }
+  }
   switch (plan.cs) {
-    case 1: launch_decode<T, KIND, BN, NB, 1>(tmx, tmw, tmw2, p, plan, st); break;
-    case 2: launch_decode<T, KIND, BN, NB, 2>(tmx, tmw, tmw2, p, plan, st); break;
-    case 3: launch_decode<T, KIND, BN, NB, 3>(tmx, tmw, tmw2, p, plan, st); break;
-    default: launch_decode<T, KIND, BN, NB, 4>(tmx, tmw, tmw2, p, plan, st); break;
+    case 1: launch_decode<T, KIND, BN, NB, 1>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
+    case 2: launch_decode<T, KIND, BN, NB, 2>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
+    case 3: launch_decode<T, KIND, BN, NB, 3>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
+    default: launch_decode<T, KIND, BN, NB, 4>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
   }
   return true;
 }
 
 template <typename T, int KIND, int NB>
 bool run_decode_m(const void* x, const void* w, const void* w2, int64_t m, int64_t n, int64_t k, const DecParams& p,
-                  cudaStream_t st) {
-  if (m <= 16) return run_decode<T, KIND, 16, NB>(x, w, w2, m, n, k, p, st);
-  if (m <= 32) return run_decode<T, KIND, 32, NB>(x, w, w2, m, n, k, p, st);
-  return run_decode<T, KIND, 64, NB>(x, w, w2, m, n, k, p, st);
+                  cudaStream_t st, const NextWeights* next = nullptr) {
+  if (m <= 16) return run_decode<T, KIND, 16, NB>(x, w, w2, m, n, k, p, st, next);
+  if (m <= 32) return run_decode<T, KIND, 32, NB>(x, w, w2, m, n, k, p, st, next);
+  return run_decode<T, KIND, 64, NB>(x, w, w2, m, n, k, p, st, next);
 }
 
 bool decode_kernel_enabled() {
@@ -489,7 +525,7 @@ bool set_row_pre(DecParams& p, const RowPre* pre, const int8_t* A, const float* 
 }  // namespace
 
 bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& e, int dtype,
-                    cudaStream_t st, const RowPre* pre) {
+                    cudaStream_t st, const RowPre* pre, const NextWeights* next) {
   if (!decode_kernel_enabled() || M > 64 || M < 1 || e.a_scale == nullptr || K % 16 != 0) return false;
   DecParams p{};
   if (!set_row_pre(p, pre, A, e.a_scale, K, dtype)) return false;
@@ -501,12 +537,12 @@ bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int6
   p.act = e.act;
   p.ldy = e.ldy;
   bool ok = false;
-  CT2_DISPATCH_DTYPE(dtype, (ok = run_decode_m<T, 0, 1>(A, B, nullptr, M, N, K, p, st)));
+  CT2_DISPATCH_DTYPE(dtype, (ok = run_decode_m<T, 0, 1>(A, B, nullptr, M, N, K, p, st, next)));
   return ok;
 }
 
 bool gemm_s8_glu_decode(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
-                        const GluEpilogue& g, int dtype, cudaStream_t st, const RowPre* pre) {
+                        const GluEpilogue& g, int dtype, cudaStream_t st, const RowPre* pre, const NextWeights* next) {
   if (!decode_kernel_enabled() || M > 64 || M < 1 || K % 16 != 0) return false;
   DecParams p{};
   if (!set_row_pre(p, pre, A, g.a_scale, K, dtype)) return false;
@@ -517,7 +553,7 @@ bool gemm_s8_glu_decode(const int8_t* A, const int8_t* Bgate, const int8_t* Bup,
   p.act = g.act;
   p.ldy = g.ldh;
   bool ok = false;
-  CT2_DISPATCH_DTYPE(dtype, (ok = run_decode_m<T, 0, 2>(A, Bgate, Bup, M, N, K, p, st)));
+  CT2_DISPATCH_DTYPE(dtype, (ok = run_decode_m<T, 0, 2>(A, Bgate, Bup, M, N, K, p, st, next)));
   return ok;
 }
 

@@ -42,7 +42,20 @@ struct DecParams {
   float* pre_s;             // [m] (= a_scale)
   int64_t pre_cols;         // k
   unsigned* pre_bar;        // grid barrier: {arrivals, generation}, zero-initialised, owned by the caller
+  // Successor prefetch: the weights of the NEXT Dense of the step are constants, so while this kernel streams its own tiles
+  // its TMA thread also asks for the boxes the next kernel will load first (cp.async.bulk.prefetch.tensor -> L2), one box
+  // per own K block, k-block-major over the next kernel's tiles so that every one of its CTAs finds the head of its stream
+  // in L2.  HBM then keeps streaming through this kernel's epilogue and the next kernel's prologue.  pf_boxes = 0: off.
+  int pf_boxes;             // boxes to prefetch in total (capped by CT2B200_L2_PREFETCH_MB)
+  int pf_tiles;             // tiles of the next kernel
+  int pf_rows;              // its tile height (box rows)
+  int pf_nb;                // 1, or 2 when it streams a gate/up pair (tm_n and tm_n2)
+  int pf_bk;                // elements per 128-byte K block of its weights
 };
+
+__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
+  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
+}
 
 // One thread per CTA: all `nctas` CTAs of the (co-resident, single-wave) grid meet here.  bar[0] counts arrivals, bar[1] is
 // the generation; the last arriver resets the count and bumps the generation (release), the others spin on it (acquire).

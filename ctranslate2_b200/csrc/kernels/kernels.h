@@ -72,11 +72,19 @@ struct RowPre {
   float eps = 0.f;
   unsigned* bar = nullptr;
 };
+// The Dense that follows in the decode step (same m): its int8 weights are prefetched into L2 while this one streams
+// (successor prefetch, gemm_decode_common.cuh).  w2 = the "up" matrix when the successor is a gate/up pair.
+struct NextWeights {
+  const void* w = nullptr;
+  const void* w2 = nullptr;
+  int64_t n = 0, k = 0;
+};
 // gemm_decode.cu (tcgen05, m <= 64): false = shape (or pre-phase) not covered, use the general kernel (+ separate row kernel)
 bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& epi,
-                    int dtype, cudaStream_t st, const RowPre* pre = nullptr);
+                    int dtype, cudaStream_t st, const RowPre* pre = nullptr, const NextWeights* next = nullptr);
 bool gemm_s8_glu_decode(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
-                        const GluEpilogue& glu, int dtype, cudaStream_t st, const RowPre* pre = nullptr);
+                        const GluEpilogue& glu, int dtype, cudaStream_t st, const RowPre* pre = nullptr,
+                        const NextWeights* next = nullptr);
 bool gemm_f16_decode(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M,
                      int64_t N, int64_t K, void* C, int dtype, cudaStream_t st);
 

@@ -1,5 +1,5 @@
 #!/bin/bash
-# tools/gpu_call.sh — the command list of ONE gpurun call (edited per call; the log of what each call measured is
+# tools/gpu_call.sh — the command list of ONE gpurun call (edited per call; what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/gpu_call.sh'
 set -u
@@ -13,8 +13,14 @@ timeout 600 python tools/ref_cuda_worker.py awq-golden $OUT/awq_ref_cuda.npz > $
 timeout 600 python tools/ref_cuda_worker.py dense-s8 $OUT/dense_s8_ref_cuda.npz >> $OUT/ref_golden.log 2>&1
 cp $OUT/awq_ref_cuda.npz $OUT/dense_s8_ref_cuda.npz tests/golden/ 2>/dev/null
 
-# 2. the new AWQ decode kernel first, bounded: a hang must not take the box
-timeout 600 python -m pytest tests/test_gpu_awq.py tests/test_gpu_ref_cuda.py -q -k "awq" > $OUT/pytest_awq.log 2>&1
+# 2. new kernels first, bounded: a hang (grid barrier, mbarrier protocol) must not take the box
+timeout 300 python -m pytest tests/test_gpu_ops.py -q -k "rows_fused" > $OUT/pytest_fused.log 2>&1
+echo "fused rows exit $?" >> $OUT/pytest_fused.log
+if ! grep -q " passed" $OUT/pytest_fused.log || grep -q "failed\|exit 124" $OUT/pytest_fused.log; then
+  echo "row pre-phase disabled for the rest of the call" >> $OUT/pytest_fused.log
+  export CT2B200_FUSE_ROWS=0
+fi
+timeout 600 python -m pytest tests/test_gpu_awq.py -q > $OUT/pytest_awq.log 2>&1
 echo "awq tests exit $?" >> $OUT/pytest_awq.log
 if ! grep -q " passed" $OUT/pytest_awq.log || grep -q "failed\|exit 124" $OUT/pytest_awq.log; then
   echo "AWQ decode kernel disabled for the rest of the call" >> $OUT/pytest_awq.log
@@ -25,26 +31,38 @@ fi
 timeout 3000 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
 echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
 
-# 4. decode step sweeps (8B): shared-memory cap of the weight-streaming GEMM (2 CTAs/SM overlap epilogue and prefetch)
-for kb in 200 110 96; do for b in 1 32; do
-  echo "SMEM_KB=$kb batch=$b" >> $OUT/sweep.log
-  CT2B200_GEMM_SMEM_KB=$kb timeout 600 python tools/decode_once.py $b 64 int8_float16 8b int8_float16 >> $OUT/sweep.log 2>&1
-done; done
-for b in 1 32; do
-  echo "AWQ batch=$b" >> $OUT/sweep.log
-  timeout 900 python tools/decode_once.py $b 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
+# 4. decode step sweeps (8B, 64 steps after the 1024-token prompt)
+run() { echo "== $*" >> $OUT/sweep.log; env "$@" timeout 600 python tools/decode_once.py $B 64 int8_float16 8b int8_float16 >> $OUT/sweep.log 2>&1; }
+for B in 1 32; do
+  run CT2B200_FUSE_ROWS=0 CT2B200_L2_PREFETCH_MB=0
+  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=0
+  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=8
+  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24
+  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=48
+  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24 CT2B200_GEMM_ROWSTEP=1
+done
+for B in 1 32; do
+  echo "== AWQ batch=$B" >> $OUT/sweep.log
+  timeout 900 python tools/decode_once.py $B 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
 done
 
 # 5. the reference's CUDA build on the same workload (bounded: G2 generated tokens)
 M8=/tmp/ct2b200_bench/llama_8b_int8_float16
 MA=/tmp/ct2b200_bench/llama_8b_awq_gemm
 for b in 1 32; do
-  timeout 900 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 8 40 >> $OUT/ref_cuda_bench.log 2>&1
-  timeout 900 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 8 40 --flash >> $OUT/ref_cuda_bench.log 2>&1
-  timeout 900 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 8 40 >> $OUT/ref_cuda_bench.log 2>&1
+  timeout 900 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 16 80 >> $OUT/ref_cuda_bench.log 2>&1
+  timeout 900 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 16 80 --flash >> $OUT/ref_cuda_bench.log 2>&1
+  timeout 900 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 16 80 >> $OUT/ref_cuda_bench.log 2>&1
+  timeout 900 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 16 80 --flash >> $OUT/ref_cuda_bench.log 2>&1
 done
 
-# 6. ncu: the AWQ gate/up kernel and the INT8 gate/up kernel (2 launches each)
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 4 \
+# 6. ncu: launch list of the INT8 bsz-32 step (2 steps), full capture of the AWQ gate/up kernel and of the INT8 one
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file $OUT/r02_launches_b32.csv python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_list.log 2>&1
+timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+  --log-file $OUT/r02_launches_b1.csv python tools/decode_once.py 1 2 int8_float16 8b int8_float16 >> $OUT/ncu_list.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 5 \
   -o $OUT/r02_awq_decode python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
+timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_decode_kernel -c 5 \
+  -o $OUT/r02_gemm_decode python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
 tail -3 $OUT/sweep.log
