@@ -33,6 +33,7 @@ def lib() -> ctypes.CDLL:
         _lib.ct2b200_version.restype = ctypes.c_char_p
         _lib.ct2b200_kernel_launch_count.restype = ctypes.c_int64
         _lib.ct2b200_generator_open.restype = ctypes.c_void_p
+        _lib.ct2b200_translator_open.restype = ctypes.c_void_p
         _lib.ct2b200_attention_decode_workspace.restype = ctypes.c_size_t
     return _lib
 

@@ -334,3 +334,104 @@ def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
               "multi_query_attention": cfg.num_heads_kv != cfg.num_heads, "quantization_type": layout,
               "quantization_bits": 4, "quantization_group_size": G}
     w.close(config, (f"<t{i}>" for i in range(cfg.vocab_size)))
+
+
+# ---------------------------------------------------------------------------------------------
+# Encoder-decoder Transformer directories (TransformerSpec revision 7, python/ctranslate2/specs/transformer_spec.py:477-560):
+# the variable set the OpenNMT-py / Marian (OPUS-MT) converters emit — LayerNorm with beta, biased Dense layers, ReLU or
+# Swish FFN, sinusoidal positions (no stored encodings), embeddings scaled by sqrt(d), optional shared vocabulary.
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class TransformerConfig:
+    encoder_layers: int = 6
+    decoder_layers: int = 6
+    num_heads: int = 8
+    d_model: int = 512
+    ffn_dim: int = 2048
+    source_vocab: int = 58101
+    target_vocab: int = 58101
+    pre_norm: bool = False                 # Marian / OPUS-MT transformers are post-norm (converters/marian.py:41)
+    activation: int = 0                    # common_spec.Activation: RELU = 0, SWISH = 2
+    start_from_zero_embedding: bool = False
+    add_source_eos: bool = False
+    layer_norm_epsilon: Optional[float] = None
+
+
+OPUS_MT_BASE = TransformerConfig(pre_norm=False, activation=2, start_from_zero_embedding=True, add_source_eos=True)
+
+
+def write_transformer_model(model_dir: str, cfg: TransformerConfig, quantization: str = "int8", seed: int = 1234,
+                            init_std: float = 0.05, emb_std: float = 0.3) -> None:
+    """Writes a random-init encoder-decoder Transformer directory (model.bin v6 + config.json + vocabularies)."""
+    rng = np.random.default_rng(seed)
+    is_int8 = quantization.startswith("int8")
+    ftype = {"int8": "float32", "int8_float32": "float32", "int8_float16": "float16",
+             "int8_bfloat16": "bfloat16"}.get(quantization, quantization)
+    d = cfg.d_model
+    w = ModelWriter(model_dir, spec="TransformerSpec", revision=7)
+
+    def linear(prefix, n, k, std=init_std, bias=True):
+        wt = (rng.standard_normal((n, k), dtype=np.float32) * np.float32(std))
+        if is_int8:
+            q, scale = quantize_int8(wt)
+            w.add(prefix + "/weight", q, "int8")
+            w.add(prefix + "/weight_scale", scale, "float32")
+        else:
+            w.add(prefix + "/weight", wt, ftype)
+        if bias:
+            w.add(prefix + "/bias", (0.02 * rng.standard_normal(n)).astype(np.float32), ftype)
+
+    def norm(prefix):
+        w.add(prefix + "/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), ftype)
+        w.add(prefix + "/beta", (0.05 * rng.standard_normal(d)).astype(np.float32), ftype)
+
+    def attention(prefix, cross):
+        norm(prefix + "/layer_norm")
+        if cross:
+            linear(prefix + "/linear_0", d, d)
+            linear(prefix + "/linear_1", 2 * d, d)
+            linear(prefix + "/linear_2", d, d)
+        else:
+            linear(prefix + "/linear_0", 3 * d, d)
+            linear(prefix + "/linear_1", d, d)
+
+    def ffn(prefix):
+        norm(prefix + "/layer_norm")
+        linear(prefix + "/linear_0", cfg.ffn_dim, d)
+        linear(prefix + "/linear_1", d, cfg.ffn_dim)
+
+    for scope, layers in (("encoder", cfg.encoder_layers), ("decoder", cfg.decoder_layers)):
+        w.add(scope + "/num_heads", np.int16(cfg.num_heads))
+        w.add(scope + "/pre_norm", np.int8(cfg.pre_norm))
+        w.add(scope + "/activation", np.int8(cfg.activation))
+        w.add(scope + "/scale_embeddings", np.int8(1))
+        if scope == "encoder":
+            w.add("encoder/embeddings_merge", np.int8(0))
+            linear("encoder/embeddings_0", cfg.source_vocab, d, std=emb_std, bias=False)
+        else:
+            w.add("decoder/alignment_layer", np.int16(-1))
+            w.add("decoder/alignment_heads", np.int16(1))
+            w.add("decoder/alibi", np.int8(0))
+            w.add("decoder/alibi_use_positive_positions", np.int8(0))
+            w.add("decoder/scale_alibi", np.int8(0))
+            w.add("decoder/start_from_zero_embedding", np.int8(cfg.start_from_zero_embedding))
+            linear("decoder/embeddings", cfg.target_vocab, d, std=emb_std, bias=False)
+            linear("decoder/projection", cfg.target_vocab, d, std=emb_std / 4)
+        if cfg.pre_norm:
+            norm(scope + "/layer_norm")
+        for l in range(layers):
+            p = f"{scope}/layer_{l}"
+            attention(p + "/self_attention", False)
+            if scope == "decoder":
+                attention(p + "/attention", True)
+            ffn(p + "/ffn")
+    config = {"bos_token": "<s>", "eos_token": "</s>", "unk_token": "<unk>", "add_source_bos": False,
+              "add_source_eos": cfg.add_source_eos, "decoder_start_token": "<s>"}
+    if cfg.layer_norm_epsilon is not None:
+        config["layer_norm_epsilon"] = cfg.layer_norm_epsilon
+    specials = ["<unk>", "<s>", "</s>"]
+    w.close(config, [])
+    os.remove(os.path.join(model_dir, "vocabulary.json"))
+    for name, n in (("source_vocabulary", cfg.source_vocab), ("target_vocabulary", cfg.target_vocab)):
+        with open(os.path.join(model_dir, name + ".json"), "w") as f:
+            json.dump(specials + [f"<t{i}>" for i in range(3, n)], f)

@@ -8,6 +8,7 @@
 
 #include "common.cuh"
 #include "host/engine.h"
+#include "host/translator.h"
 #include "kernels/kernels.h"
 
 using namespace ct2b200;
@@ -43,6 +44,9 @@ void require_device() {
 
 struct ct2b200_generator {
   std::unique_ptr<Generator> impl;
+};
+struct ct2b200_translator {
+  std::unique_ptr<Translator> impl;
 };
 
 extern "C" {
@@ -425,6 +429,125 @@ CT2B200_API int ct2b200_generator_tp_connect(ct2b200_generator* g, const void* h
   return guarded([&] {
     CT2_REQUIRE(g && handles_h, "null argument");
     g->impl->decoder().tp_connect(handles_h, num_handles);
+  });
+}
+
+// ---- encoder-decoder path ----
+CT2B200_API int ct2b200_gemm_f32(const float* a, const float* b, const float* bias, const float* residual, int act, int64_t m,
+                     int64_t n, int64_t k, float* c, void* stream) {
+  return guarded([&] {
+    require_device();
+    gemm_f32(a, b, bias, residual, act, m, n, k, c, S(stream));
+  });
+}
+
+CT2B200_API int ct2b200_layer_norm(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t cols, float eps, void* y,
+                       int8_t* q, float* scale, int round_before_cast, int dtype, void* stream) {
+  return guarded([&] {
+    require_device();
+    CT2_REQUIRE(y || q, "layer_norm: no output requested");
+    CT2_REQUIRE(!q || scale, "layer_norm: scale_d is required with q_d");
+    launch_layer_norm(x, gamma, beta, rows, cols, eps, y, q, scale, round_before_cast != 0, dtype, S(stream));
+  });
+}
+
+CT2B200_API ct2b200_translator* ct2b200_translator_open(const char* model_dir, const ct2b200_generator_config* config) {
+  ct2b200_translator* t = nullptr;
+  const int rc = guarded([&] {
+    require_device();
+    CT2_REQUIRE(model_dir && config, "translator_open: null argument");
+    auto holder = std::make_unique<ct2b200_translator>();
+    holder->impl = std::make_unique<Translator>(model_dir, *config);
+    t = holder.release();
+  });
+  return rc == 0 ? t : nullptr;
+}
+
+CT2B200_API void ct2b200_translator_close(ct2b200_translator* t) { delete t; }
+
+CT2B200_API int ct2b200_translator_info(const ct2b200_translator* t, int* encoder_layers, int* decoder_layers, int* num_heads,
+                            int* d_model, int* source_vocab, int* target_vocab, int64_t* weight_bytes) {
+  return guarded([&] {
+    CT2_REQUIRE(t, "null translator");
+    const Seq2SeqConfig& c = t->impl->config();
+    if (encoder_layers) *encoder_layers = c.enc_layers;
+    if (decoder_layers) *decoder_layers = c.dec_layers;
+    if (num_heads) *num_heads = c.num_heads;
+    if (d_model) *d_model = static_cast<int>(c.d_model);
+    if (source_vocab) *source_vocab = static_cast<int>(c.src_vocab);
+    if (target_vocab) *target_vocab = static_cast<int>(c.tgt_vocab);
+    if (weight_bytes) *weight_bytes = c.weight_bytes;
+  });
+}
+
+CT2B200_API int ct2b200_translator_summary(const char* model_dir, char* json_out, size_t capacity) {
+  return guarded([&] {
+    CT2_REQUIRE(model_dir && json_out && capacity > 0, "translator_summary: null argument");
+    ModelFile file(model_dir);
+    const Seq2SeqConfig mc = parse_seq2seq_config(file);
+    char buf[1024];
+    const int n = std::snprintf(
+        buf, sizeof(buf),
+        "{\"spec\": \"%s\", \"binary_version\": %u, \"revision\": %u, \"encoder_layers\": %d, \"decoder_layers\": %d, "
+        "\"num_heads\": %d, \"head_dim\": %d, \"d_model\": %lld, \"ffn_dim\": %lld, \"source_vocab\": %lld, "
+        "\"target_vocab\": %lld, \"weights\": \"%s\", \"pre_norm\": %s, \"activation\": %d, \"embeddings_scale\": %.9g, "
+        "\"layer_norm_epsilon\": %.9g, \"round_before_cast\": %s}",
+        file.spec_name.c_str(), file.binary_version, file.revision, mc.enc_layers, mc.dec_layers, mc.num_heads, mc.head_dim,
+        static_cast<long long>(mc.d_model), static_cast<long long>(mc.ffn_dim), static_cast<long long>(mc.src_vocab),
+        static_cast<long long>(mc.tgt_vocab), mc.weights.c_str(), mc.dec_pre_norm ? "true" : "false", mc.dec_activation,
+        static_cast<double>(mc.dec_emb_scale), static_cast<double>(mc.eps), mc.round_before_cast ? "true" : "false");
+    CT2_REQUIRE(n > 0 && static_cast<size_t>(n) < capacity, "translator_summary: output buffer too small");
+    std::memcpy(json_out, buf, static_cast<size_t>(n) + 1);
+  });
+}
+
+CT2B200_API int ct2b200_translate_batch(ct2b200_translator* t, const int32_t* source_ids, const int32_t* source_lens, int64_t batch,
+                            int64_t max_source_len, int beam_size, float patience, float length_penalty,
+                            int64_t max_decoding_length, int64_t min_decoding_length, int num_hypotheses, int32_t start_id,
+                            const int32_t* end_ids, int num_end_ids, int return_end_token, int32_t* out_ids, int32_t* out_lens,
+                            float* out_scores) {
+  return guarded([&] {
+    CT2_REQUIRE(t && source_ids && source_lens && out_ids && out_lens && out_scores, "translate_batch: null argument");
+    TranslationRequest r;
+    r.source_ids = source_ids;
+    r.source_lens = source_lens;
+    r.batch = batch;
+    r.max_source_len = max_source_len;
+    r.beam_size = beam_size;
+    r.patience = patience;
+    r.length_penalty = length_penalty;
+    r.max_decoding_length = max_decoding_length;
+    r.min_decoding_length = min_decoding_length;
+    r.num_hypotheses = num_hypotheses;
+    r.start_id = start_id;
+    r.end_ids.assign(end_ids, end_ids + (end_ids ? num_end_ids : 0));
+    r.return_end_token = return_end_token != 0;
+    const std::vector<TranslationHypotheses> res = t->impl->translate(r);
+    for (int64_t b = 0; b < batch; ++b)
+      for (int h = 0; h < num_hypotheses; ++h) {
+        int32_t* dst = out_ids + (b * num_hypotheses + h) * max_decoding_length;
+        const bool have = h < static_cast<int>(res[b].tokens.size());
+        const int64_t len = have ? static_cast<int64_t>(res[b].tokens[h].size()) : 0;
+        for (int64_t i = 0; i < max_decoding_length; ++i) dst[i] = i < len ? res[b].tokens[h][i] : -1;
+        out_lens[b * num_hypotheses + h] = have ? static_cast<int32_t>(len) : -1;
+        out_scores[b * num_hypotheses + h] = have ? res[b].scores[h] : 0.f;
+      }
+  });
+}
+
+CT2B200_API int ct2b200_translator_encode(ct2b200_translator* t, const int32_t* source_ids, const int32_t* source_lens, int64_t batch,
+                              int64_t max_source_len, float* memory) {
+  return guarded([&] {
+    CT2_REQUIRE(t && source_ids && source_lens && memory, "translator_encode: null argument");
+    t->impl->encode(source_ids, source_lens, batch, max_source_len, memory);
+  });
+}
+
+CT2B200_API int ct2b200_bench_translate(ct2b200_translator* t, int64_t batch, int64_t source_len, int beam_size, int64_t steps,
+                            int64_t warmup, float* encode_ms, float* decode_ms, int64_t* kernel_launches) {
+  return guarded([&] {
+    CT2_REQUIRE(t && encode_ms && decode_ms && kernel_launches, "bench_translate: null argument");
+    t->impl->bench(batch, source_len, beam_size, steps, warmup, encode_ms, decode_ms, kernel_launches);
   });
 }
 

@@ -91,9 +91,9 @@ ModelFile::ModelFile(const std::string& model_dir) {
   if (map_ == MAP_FAILED) throw std::runtime_error("mmap failed for " + path);
   Cursor c{static_cast<const uint8_t*>(map_), static_cast<const uint8_t*>(map_) + map_size_};
   binary_version = c.read<uint32_t>();
-  if (binary_version < 4 || binary_version > 6)
+  if (binary_version < 2 || binary_version > 6)
     throw std::runtime_error("Unsupported model binary version " + std::to_string(binary_version) +
-                             " (this engine reads versions 4 to 6)");
+                             " (this engine reads versions 2 to 6)");
   spec_name = c.read_string();
   revision = c.read<uint32_t>();
   const uint32_t nvars = c.read<uint32_t>();
@@ -102,8 +102,16 @@ ModelFile::ModelFile(const std::string& model_dir) {
     HostVariable v;
     const uint8_t rank = c.read<uint8_t>();
     for (int r = 0; r < rank; ++r) v.shape.push_back(c.read<uint32_t>());
-    v.type_id = c.read<uint8_t>();
-    v.nbytes = c.read<uint32_t>();
+    if (binary_version >= 4) {
+      v.type_id = c.read<uint8_t>();
+      v.nbytes = c.read<uint32_t>();
+    } else {
+      // versions 2-3 store the item size and the item count (model.cc:653-657, get_dtype_from_item_size)
+      const uint8_t item_size = c.read<uint8_t>();
+      v.type_id = item_size == 4 ? 0 : item_size == 2 ? 2 : item_size == 1 ? 1 : -1;
+      if (v.type_id < 0) throw std::runtime_error("model.bin: unknown item size " + std::to_string(item_size));
+      v.nbytes = static_cast<size_t>(c.read<uint32_t>()) * item_size;
+    }
     if (static_cast<size_t>(v.size()) * type_size(v.type_id) != v.nbytes)
       throw std::runtime_error("model.bin: variable " + name + " has inconsistent size");
     if (c.p + v.nbytes > c.end) throw std::runtime_error("model.bin: unexpected end of file");
@@ -111,13 +119,18 @@ ModelFile::ModelFile(const std::string& model_dir) {
     c.p += v.nbytes;
     vars_.emplace(name, v);
   }
-  const uint32_t naliases = c.read<uint32_t>();
+  const uint32_t naliases = binary_version >= 3 ? c.read<uint32_t>() : 0;
   for (uint32_t i = 0; i < naliases; ++i) {
     const std::string alias = c.read_string();
     const std::string target = c.read_string();
     auto it = vars_.find(target);
     if (it == vars_.end()) throw std::runtime_error("model.bin: alias target not found: " + target);
     vars_.emplace(alias, it->second);
+    // the quantization scale / zero of the target follows its alias (model.cc:772-774)
+    for (const char* suffix : {"_scale", "_zero"}) {
+      auto sit = vars_.find(target + suffix);
+      if (sit != vars_.end()) vars_.emplace(alias + suffix, sit->second);
+    }
   }
   std::ifstream cf(model_dir + "/config.json");
   if (cf) {
@@ -171,8 +184,6 @@ void DeviceBuffer::release() {
   bytes = 0;
 }
 
-namespace {
-
 // host-side conversion of a float-ish variable to the compute dtype
 std::vector<uint8_t> convert_to_dtype(const HostVariable& v, int dtype) {
   const int64_t n = v.size();
@@ -207,6 +218,8 @@ void upload(DeviceBuffer& dst, const void* src, size_t n) {
   if (n) CT2_CUDA_CHECK(cudaMemcpy(dst.ptr, src, n, cudaMemcpyHostToDevice));
 }
 
+namespace {
+
 int env_gemm_impl() {
   const char* e = std::getenv("CT2B200_GEMM_IMPL");
   if (!e) return CT2B200_GEMM_AUTO;
@@ -223,6 +236,15 @@ void gemm_s8(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, 
   if (impl == CT2B200_GEMM_AUTO) impl = env_gemm_impl();
   if (impl == CT2B200_GEMM_MMA_SYNC) gemm_s8_mma(A, B, M, N, K, epi, dtype, st);
   else gemm_s8_tc(A, B, M, N, K, epi, dtype, st);
+}
+// float Dense (ops::Gemm float arms, primitives.cu:485-569): f16 / bf16 on tcgen05 kind::f16, f32 as true fp32 FMAs
+void gemm_float(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M, int64_t N,
+                int64_t K, void* C, int dtype, cudaStream_t st) {
+  if (dtype == CT2B200_F32)
+    gemm_f32(static_cast<const float*>(A), static_cast<const float*>(B), static_cast<const float*>(bias),
+             static_cast<const float*>(residual), act, M, N, K, static_cast<float*>(C), st);
+  else
+    gemm_f16_tc(A, B, bias, residual, act, M, N, K, C, dtype, st);
 }
 void gemm_s8_glu(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
                  const GluEpilogue& glu, int dtype, int impl, cudaStream_t st) {
@@ -252,6 +274,60 @@ std::pair<int64_t, int64_t> shard_range(int64_t total, int rank, int world) {
 }
 }  // namespace
 
+// The matrix of a Dense layer as the requested arithmetic wants it: Model::set_compute_type + ensure_dtype
+// (src/models/model.cc:178-234, 304-369) on the GPU.  The stored matrix goes to the device as it is; when the compute type
+// asks for another weight type it is converted there with the converter's own arithmetic (model_spec.py:222-243 =
+// ops::Quantize on fp32: scale = 127 / amax per row, q = rint(w * scale); back: w = T(float(q) * (1 / scale)),
+// dequantize_cpu.cc:12-21).  Returns true when the result is int8 (+ fp32 row scales in full_s), false for T [N, K].
+bool load_dense_matrix(const ModelFile& f, const std::string& prefix, int dtype_, int weight_type_, cudaStream_t stream_,
+                     DeviceBuffer& full_w, DeviceBuffer& full_s, int64_t& N, int64_t& K) {
+  const HostVariable& wt = f.get(prefix + "/weight");
+  CT2_REQUIRE(wt.type_id == 1 || wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5, "unsupported weight type for " + prefix);
+  CT2_REQUIRE(wt.shape.size() == 2, "weight must be a matrix");
+  N = wt.shape[0];
+  K = wt.shape[1];
+  const bool stored_int8 = wt.type_id == 1;
+  const bool want_int8 = weight_type_ == CT2B200_WEIGHTS_INT8 || (weight_type_ == CT2B200_WEIGHTS_STORED && stored_int8);
+  if (stored_int8) {
+    const HostVariable& sc = f.get(prefix + "/weight_scale");
+    CT2_REQUIRE(sc.type_id == 0 && sc.size() == N, "weight_scale must be float32 [n]");
+    upload(full_w, wt.data, wt.nbytes);
+    upload(full_s, sc.data, sc.nbytes);
+    if (!want_int8) {                            // int8 -> float (compute types float16 / bfloat16 on an int8 model)
+      DeviceBuffer deq(static_cast<size_t>(N) * K * dtype_size(dtype_));
+      launch_dequantize_rows(full_w.as<int8_t>(), full_s.as<float>(), N, K, deq.ptr, dtype_, stream_, /*reciprocal=*/true);
+      CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      full_w = std::move(deq);
+      full_s.release();
+    }
+  } else {
+    const int stored = wt.type_id == 0 ? CT2B200_F32 : wt.type_id == 4 ? CT2B200_F16 : CT2B200_BF16;
+    upload(full_w, wt.data, wt.nbytes);
+    if (want_int8 || stored != dtype_) {
+      DeviceBuffer f32;
+      const float* src32 = full_w.as<float>();
+      if (stored != CT2B200_F32) {
+        f32.alloc(static_cast<size_t>(N) * K * 4);
+        launch_convert_to_f32(full_w.ptr, N * K, f32.as<float>(), stored, stream_);
+        src32 = f32.as<float>();
+      }
+      if (want_int8) {                           // float -> int8 (e.g. a float16 model served as int8_float16)
+        DeviceBuffer q(static_cast<size_t>(N) * K);
+        full_s.alloc(static_cast<size_t>(N) * 4);
+        launch_quantize_rows(src32, CT2B200_F32, N, K, true, q.as<int8_t>(), full_s.as<float>(), stream_);
+        CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        full_w = std::move(q);
+      } else {                                   // float -> the compute float type
+        DeviceBuffer t(static_cast<size_t>(N) * K * dtype_size(dtype_));
+        launch_convert_from_f32(src32, N * K, t.ptr, dtype_, stream_);
+        CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+        full_w = std::move(t);
+      }
+    }
+  }
+  return want_int8;
+}
+
 void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w, Shard shard) {
   const HostVariable& wt = f.get(prefix + "/weight");
   const bool awq_weight = wt.type_id == 3 && f.find(prefix + "/weight_zero") != nullptr;
@@ -263,50 +339,9 @@ void LlamaDecoder::load_dense(const ModelFile& f, const std::string& prefix, Den
     // (model.cc:662-743) are cut afterwards, device to device: column-parallel layers keep a slice of the output channels
     // (fused QKV: this rank's query, key and value heads), row-parallel layers a slice of K.  The int8 values and the
     // per-channel scales are those of the unsharded matrix, so the shards reproduce the single-GPU arithmetic exactly.
-    CT2_REQUIRE(wt.type_id == 1 || wt.type_id == 0 || wt.type_id == 4 || wt.type_id == 5, "unsupported weight type for " + prefix);
-    CT2_REQUIRE(wt.shape.size() == 2, "weight must be a matrix");
-    const int64_t N = wt.shape[0], K = wt.shape[1];
-    const bool stored_int8 = wt.type_id == 1;
-    const bool want_int8 = weight_type_ == CT2B200_WEIGHTS_INT8 || (weight_type_ == CT2B200_WEIGHTS_STORED && stored_int8);
-    CT2_REQUIRE(want_int8 || dtype_ != CT2B200_F32, "float weights need compute type float16 or bfloat16 on this engine");
     DeviceBuffer full_w, full_s;
-    if (stored_int8) {
-      const HostVariable& sc = f.get(prefix + "/weight_scale");
-      CT2_REQUIRE(sc.type_id == 0 && sc.size() == N, "weight_scale must be float32 [n]");
-      upload(full_w, wt.data, wt.nbytes);
-      upload(full_s, sc.data, sc.nbytes);
-      if (!want_int8) {                            // int8 -> float (compute types float16 / bfloat16 on an int8 model)
-        DeviceBuffer deq(static_cast<size_t>(N) * K * dtype_size(dtype_));
-        launch_dequantize_rows(full_w.as<int8_t>(), full_s.as<float>(), N, K, deq.ptr, dtype_, stream_, /*reciprocal=*/true);
-        CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
-        full_w = std::move(deq);
-        full_s.release();
-      }
-    } else {
-      const int stored = wt.type_id == 0 ? CT2B200_F32 : wt.type_id == 4 ? CT2B200_F16 : CT2B200_BF16;
-      upload(full_w, wt.data, wt.nbytes);
-      if (want_int8 || stored != dtype_) {
-        DeviceBuffer f32;
-        const float* src32 = full_w.as<float>();
-        if (stored != CT2B200_F32) {
-          f32.alloc(static_cast<size_t>(N) * K * 4);
-          launch_convert_to_f32(full_w.ptr, N * K, f32.as<float>(), stored, stream_);
-          src32 = f32.as<float>();
-        }
-        if (want_int8) {                           // float -> int8 (e.g. a float16 model served as int8_float16)
-          DeviceBuffer q(static_cast<size_t>(N) * K);
-          full_s.alloc(static_cast<size_t>(N) * 4);
-          launch_quantize_rows(src32, CT2B200_F32, N, K, true, q.as<int8_t>(), full_s.as<float>(), stream_);
-          CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
-          full_w = std::move(q);
-        } else {                                   // float -> the compute float type
-          DeviceBuffer t(static_cast<size_t>(N) * K * dtype_size(dtype_));
-          launch_convert_from_f32(src32, N * K, t.ptr, dtype_, stream_);
-          CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
-          full_w = std::move(t);
-        }
-      }
-    }
+    int64_t N = 0, K = 0;
+    const bool want_int8 = load_dense_matrix(f, prefix, dtype_, weight_type_, stream_, full_w, full_s, N, K);
     const size_t es = want_int8 ? 1 : dtype_size(dtype_);
     w.kind = want_int8 ? DenseWeights::INT8 : DenseWeights::FLOAT16;
     std::vector<std::pair<int64_t, int64_t>> row_ranges = {{0, N}};
@@ -703,7 +738,7 @@ void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* x
     DenseEpilogue e{xs, w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
     gemm_s8(xq, w.weight.as<int8_t>(), m, w.n, w.k, e, dtype_, gemm_impl_, stream_);
   } else if (w.kind == DenseWeights::FLOAT16) {
-    gemm_f16_tc(x_float, w.weight.ptr, w.bias.ptr, residual, act, m, w.n, w.k, y, dtype_, stream_);
+    gemm_float(x_float, w.weight.ptr, w.bias.ptr, residual, act, m, w.n, w.k, y, dtype_, stream_);
   } else {
     AwqNative a{w.weight.ptr, w.scale.ptr, w.zeros.ptr, w.n, w.k, w.group_size, w.scale_zero.ptr};
     dense_awq(x_float, a, w.bias.ptr, residual, act, m, y, scratch_nk_.ptr, stream_);

@@ -80,6 +80,14 @@ struct DenseWeights {
   int group_size = 128;
 };
 
+class ModelFile;
+// Dense matrix of `prefix` converted on the GPU to what the compute type asks for (Model::set_compute_type); true = int8
+bool load_dense_matrix(const ModelFile& f, const std::string& prefix, int dtype, int weight_type, cudaStream_t st,
+                       DeviceBuffer& full_w, DeviceBuffer& full_s, int64_t& n, int64_t& k);
+// host-side conversion of a float variable to the compute dtype (gammas, biases, position encodings)
+std::vector<uint8_t> convert_to_dtype(const HostVariable& v, int dtype);
+void upload(DeviceBuffer& dst, const void* src, size_t n);
+
 struct LayerWeights {
   DeviceBuffer attn_gamma, ffn_gamma;
   DenseWeights qkv, out, gate, up, down;

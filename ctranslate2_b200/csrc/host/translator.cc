@@ -1,0 +1,646 @@
+// translator.cc — see translator.h.  Reference counterparts: src/models/transformer.cc, src/models/sequence_to_sequence.cc
+// (EncoderDecoderReplica::run_translation), src/layers/transformer.cc (TransformerEncoder / TransformerDecoder),
+// src/layers/attention.cc, src/layers/common.cc (Embeddings, position encoders, LayerNorm, Dense), src/decoding.cc (BeamSearch).
+#include "translator.h"
+
+#include <cuda_profiler_api.h>
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+#include <numeric>
+
+namespace ct2b200 {
+
+// =============================================================================================
+// configuration
+// =============================================================================================
+namespace {
+
+const HostVariable* find_any(const ModelFile& f, std::initializer_list<std::string> names) {
+  for (const auto& n : names)
+    if (const HostVariable* v = f.find(n)) return v;
+  return nullptr;
+}
+
+std::string embeddings_scope(const ModelFile& f, const std::string& scope) {
+  if (f.find(scope + "/embeddings_0/weight")) {
+    if (f.find(scope + "/embeddings_1/weight"))
+      throw std::invalid_argument("models with several input features (embeddings_1) are not supported");
+    return scope + "/embeddings_0";
+  }
+  return scope + "/embeddings";
+}
+
+// build_embeddings_scale (transformer.cc:380-402): the attribute is a flag or the scale itself
+float embeddings_scale(const ModelFile& f, const std::string& scope, int64_t depth) {
+  const HostVariable* s = find_any(f, {scope + "/scale_embeddings", scope + "/embeddings/multiply_by_sqrt_depth"});
+  if (!s || (s->type_id == 1 && s->scalar() != 0.0)) return std::sqrt(static_cast<float>(depth));
+  if (s->type_id != 1 && s->scalar() != 1.0) return static_cast<float>(s->scalar());
+  return 0.f;
+}
+
+double scoped_attribute(const ModelFile& f, const std::string& scope, const std::string& name, double fallback) {
+  // spec revisions < 5 keep the attribute at the top level (models/transformer.cc:67-79)
+  const HostVariable* v = find_any(f, {scope + "/" + name, name});
+  return v ? v->scalar() : fallback;
+}
+
+}  // namespace
+
+Seq2SeqConfig parse_seq2seq_config(const ModelFile& f) {
+  Seq2SeqConfig mc;
+  if (!f.find("encoder/layer_0/self_attention/linear_0/weight") || !f.find("decoder/layer_0/attention/linear_0/weight"))
+    throw std::invalid_argument("ct2b200 Translator serves encoder-decoder Transformer models (TransformerSpec); got " + f.spec_name);
+  while (f.find("encoder/layer_" + std::to_string(mc.enc_layers) + "/self_attention/linear_0/weight")) ++mc.enc_layers;
+  while (f.find("decoder/layer_" + std::to_string(mc.dec_layers) + "/self_attention/linear_0/weight")) ++mc.dec_layers;
+  const HostVariable& semb = f.get(embeddings_scope(f, "encoder") + "/weight");
+  const HostVariable& temb = f.get("decoder/embeddings/weight");
+  mc.src_vocab = semb.shape[0];
+  mc.tgt_vocab = temb.shape[0];
+  mc.d_model = semb.shape[1];
+  CT2_REQUIRE(temb.shape[1] == mc.d_model, "encoder and decoder depths differ");
+  // num_heads: attribute since revision 3; TransformerBase / TransformerBig imply 8 / 16 before (models/transformer.cc:62-65)
+  mc.num_heads = static_cast<int>(scoped_attribute(f, "encoder", "num_heads", f.spec_name == "TransformerBig" ? 16 : 8));
+  CT2_REQUIRE(static_cast<int>(scoped_attribute(f, "decoder", "num_heads", mc.num_heads)) == mc.num_heads,
+              "encoder and decoder head counts differ");
+  CT2_REQUIRE(mc.d_model % mc.num_heads == 0, "d_model must be divisible by num_heads");
+  mc.head_dim = static_cast<int>(mc.d_model / mc.num_heads);
+  mc.enc_pre_norm = scoped_attribute(f, "encoder", "pre_norm", 1.0) != 0.0;
+  mc.dec_pre_norm = scoped_attribute(f, "decoder", "pre_norm", 1.0) != 0.0;
+  mc.enc_activation = static_cast<int>(scoped_attribute(f, "encoder", "activation", 0.0));
+  mc.dec_activation = static_cast<int>(scoped_attribute(f, "decoder", "activation", 0.0));
+  mc.enc_emb_scale = embeddings_scale(f, "encoder", mc.d_model);
+  mc.dec_emb_scale = embeddings_scale(f, "decoder", mc.d_model);
+  mc.ffn_dim = f.get("encoder/layer_0/ffn/linear_0/weight").shape[0];
+  mc.round_before_cast = f.binary_version >= 5;
+  mc.has_enc_final_norm = f.find("encoder/layer_norm/gamma") != nullptr;
+  mc.has_dec_final_norm = f.find("decoder/layer_norm/gamma") != nullptr;
+  const bool has_beta = f.find("encoder/layer_0/self_attention/layer_norm/beta") != nullptr;
+  mc.eps = static_cast<float>(f.config_number("layer_norm_epsilon", has_beta ? 1e-5 : 1e-6));
+  // what TransformerSpec can express and this engine does not compute: refuse instead of translating something else
+  auto absent = [&](const std::string& name, const char* what) {
+    if (f.find(name)) throw std::invalid_argument(std::string(what) + " (" + name + ") is not supported by the Translator engine");
+  };
+  CT2_REQUIRE(has_beta, "RMSNorm encoder-decoder models are not supported (LayerNorm with beta is)");
+  for (const char* scope : {"encoder", "decoder"}) {
+    const std::string s(scope);
+    absent(s + "/layernorm_embedding/gamma", "layernorm_embedding");
+    absent(s + "/layer_0/self_attention/relative_position_keys", "relative position representations");
+    absent(s + "/layer_0/self_attention/relative_attention_bias", "relative attention bias");
+    absent(s + "/layer_0/self_attention/rotary_dim", "rotary embeddings");
+    absent(s + "/layer_0/self_attention/num_heads_kv", "grouped-query attention");
+    absent(s + "/layer_0/ffn/linear_0_noact/weight", "gated feed-forward layers");
+    absent(s + "/project_in/weight", "project_in");
+    absent(s + "/project_out/weight", "project_out");
+    if (scoped_attribute(f, s, "alibi", 0.0) != 0.0) throw std::invalid_argument("ALiBi is not supported by the Translator engine");
+    if (scoped_attribute(f, s, "embeddings_merge", 0.0) != 0.0)
+      throw std::invalid_argument("embeddings_merge other than CONCAT of one feature is not supported");
+  }
+  mc.start_from_zero_embedding = f.attribute("decoder/start_from_zero_embedding", 0.0) != 0.0;
+  absent("decoder/scale_outputs", "scaled outputs");
+  absent("decoder/layer_0/layer_scalar", "layer_scalar");
+  absent("decoder/layer_0/self_attention/queries_scale", "a custom queries_scale");
+  if (f.attribute("decoder/final_logit_softcapping", 0.0) != 0.0)
+    throw std::invalid_argument("final logit soft-capping is not supported by the Translator engine");
+  CT2_REQUIRE(f.revision != 1, "spec revision 1 (OpenNMT-tf variable names) is not supported");
+  const HostVariable& w = f.get("encoder/layer_0/self_attention/linear_0/weight");
+  mc.weights = w.type_id == 1 ? "int8" : w.type_id == 2 ? "int16" : w.type_id == 4 ? "float16" : w.type_id == 5 ? "bfloat16" : "float32";
+  CT2_REQUIRE(w.type_id != 2, "int16 models are not supported (convert with int8 or a float type)");
+  return mc;
+}
+
+// =============================================================================================
+// loading
+// =============================================================================================
+void Translator::load_dense(const ModelFile& f, const std::string& prefix, DenseWeights& w) {
+  const bool int8 = load_dense_matrix(f, prefix, dtype_, weight_type_, stream_, w.weight, w.scale, w.n, w.k);
+  w.kind = int8 ? DenseWeights::INT8 : DenseWeights::FLOAT16;
+  CT2_REQUIRE(!int8 || w.k % 16 == 0, "int8 Dense layers need an input size that is a multiple of 16");
+  mc_.weight_bytes += w.weight.bytes + w.scale.bytes;
+  if (const HostVariable* b = f.find(prefix + "/bias")) {
+    const auto bytes = convert_to_dtype(*b, dtype_);
+    upload(w.bias, bytes.data(), bytes.size());
+  }
+}
+
+void Translator::load_norm(const ModelFile& f, const std::string& prefix, NormWeights& n) {
+  const auto g = convert_to_dtype(f.get(prefix + "/gamma"), dtype_);
+  const auto b = convert_to_dtype(f.get(prefix + "/beta"), dtype_);
+  upload(n.gamma, g.data(), g.size());
+  upload(n.beta, b.data(), b.size());
+}
+
+namespace {
+// generate_sinusoidal_position_encoding (common.cc:204-229): positions start at 1, [sin | cos] halves, fp32 then cast
+std::vector<float> sinusoidal_positions(int64_t max_time, int64_t depth) {
+  const float inc = std::log(10000.f) / static_cast<float>(depth / 2 - 1);
+  std::vector<float> ts(depth / 2);
+  for (int64_t i = 0; i < depth / 2; ++i) ts[i] = std::exp(-inc * static_cast<float>(i));
+  std::vector<float> e(max_time * depth);
+  for (int64_t t = 0; t < max_time; ++t)
+    for (int64_t j = 0; j < depth / 2; ++j) {
+      const float a = static_cast<float>(t + 1) * ts[j];
+      e[t * depth + j] = std::sin(a);
+      e[t * depth + depth / 2 + j] = std::cos(a);
+    }
+  return e;
+}
+}  // namespace
+
+Translator::Translator(const std::string& model_dir, const ct2b200_generator_config& cfg) {
+  device_ = cfg.device;
+  CT2_CUDA_CHECK(cudaSetDevice(device_));
+  int major = 0;
+  CT2_CUDA_CHECK(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, device_));
+  if (major != 10)
+    throw std::runtime_error("ct2b200 needs an sm_100 (B200) device; found compute capability major " + std::to_string(major));
+  CT2_CUDA_CHECK(cudaDeviceGetAttribute(&sm_count_, cudaDevAttrMultiProcessorCount, device_));
+  CT2_CUDA_CHECK(cudaStreamCreateWithFlags(&stream_, cudaStreamNonBlocking));
+  dtype_ = cfg.compute_type;
+  weight_type_ = cfg.weight_type;
+  use_graph_ = cfg.use_cuda_graph != 0;
+  CT2_REQUIRE(cfg.tp_size <= 1, "the Translator engine does not run tensor parallel");
+
+  ModelFile f(model_dir);
+  mc_ = parse_seq2seq_config(f);
+  load_dense(f, embeddings_scope(f, "encoder"), enc_emb_);
+  load_dense(f, "decoder/embeddings", dec_emb_);
+  load_dense(f, "decoder/projection", projection_);
+  if (mc_.has_enc_final_norm) load_norm(f, "encoder/layer_norm", enc_norm_);
+  if (mc_.has_dec_final_norm) load_norm(f, "decoder/layer_norm", dec_norm_);
+  enc_.resize(mc_.enc_layers);
+  for (int l = 0; l < mc_.enc_layers; ++l) {
+    const std::string p = "encoder/layer_" + std::to_string(l) + "/";
+    load_norm(f, p + "self_attention/layer_norm", enc_[l].self.norm);
+    load_dense(f, p + "self_attention/linear_0", enc_[l].self.in);
+    load_dense(f, p + "self_attention/linear_1", enc_[l].self.out);
+    load_norm(f, p + "ffn/layer_norm", enc_[l].ffn.norm);
+    load_dense(f, p + "ffn/linear_0", enc_[l].ffn.ff1);
+    load_dense(f, p + "ffn/linear_1", enc_[l].ffn.ff2);
+  }
+  dec_.resize(mc_.dec_layers);
+  for (int l = 0; l < mc_.dec_layers; ++l) {
+    const std::string p = "decoder/layer_" + std::to_string(l) + "/";
+    load_norm(f, p + "self_attention/layer_norm", dec_[l].self.norm);
+    load_dense(f, p + "self_attention/linear_0", dec_[l].self.in);
+    load_dense(f, p + "self_attention/linear_1", dec_[l].self.out);
+    load_norm(f, p + "attention/layer_norm", dec_[l].cross.norm);
+    load_dense(f, p + "attention/linear_0", dec_[l].cross.in);
+    load_dense(f, p + "attention/linear_1", dec_[l].cross.kv);
+    load_dense(f, p + "attention/linear_2", dec_[l].cross.out);
+    load_norm(f, p + "ffn/layer_norm", dec_[l].ffn.norm);
+    load_dense(f, p + "ffn/linear_0", dec_[l].ffn.ff1);
+    load_dense(f, p + "ffn/linear_1", dec_[l].ffn.ff2);
+  }
+  // position encodings: stored table (PositionEmbedding) or sinusoidal (SinusoidalPositionEncoder, 500 positions or more)
+  num_positions_ = std::max<int64_t>(500, cfg.max_length);
+  auto load_positions = [&](const std::string& scope, DeviceBuffer& dst) {
+    if (const HostVariable* e = f.find(scope + "/position_encodings/encodings")) {
+      const auto bytes = convert_to_dtype(*e, dtype_);
+      upload(dst, bytes.data(), bytes.size());
+      num_positions_ = std::min<int64_t>(num_positions_, e->shape[0]);
+      return;
+    }
+    const std::vector<float> enc = sinusoidal_positions(num_positions_, mc_.d_model);
+    HostVariable v;
+    v.shape = {num_positions_, mc_.d_model};
+    v.type_id = 0;
+    v.data = reinterpret_cast<const uint8_t*>(enc.data());
+    v.nbytes = enc.size() * 4;
+    const auto bytes = convert_to_dtype(v, dtype_);
+    upload(dst, bytes.data(), bytes.size());
+  };
+  load_positions("encoder", enc_pos_);
+  load_positions("decoder", dec_pos_);
+  end_ids_d_.alloc(64 * sizeof(int32_t));
+  counters_.alloc(64);
+  CT2_CUDA_CHECK(cudaMemset(counters_.ptr, 0, 64));
+  SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());
+}
+
+Translator::~Translator() {
+  if (graph_) cudaGraphExecDestroy(graph_);
+  if (host_pinned_) cudaFreeHost(host_pinned_);
+  if (stream_) cudaStreamDestroy(stream_);
+}
+
+void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t max_steps) {
+  CT2_REQUIRE(src_len <= num_positions_ && max_steps <= num_positions_, "sequence longer than the position encodings");
+  if (batch <= cap_batch_ && src_len <= cap_src_ && beam <= cap_beam_ && max_steps <= cap_steps_) return;
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  if (graph_) {
+    cudaGraphExecDestroy(graph_);
+    graph_ = nullptr;
+    graph_key_.clear();
+  }
+  cap_batch_ = std::max(cap_batch_, batch);
+  cap_src_ = std::max(cap_src_, src_len);
+  cap_beam_ = std::max(cap_beam_, beam);
+  cap_steps_ = std::max(cap_steps_, max_steps);
+  const int64_t B = cap_batch_, S = cap_src_, L = cap_steps_, N = B * cap_beam_;
+  const int64_t R = std::max(B * S, N), d = mc_.d_model, F = mc_.ffn_dim, V = mc_.tgt_vocab;
+  cap_rows_ = R;
+  const size_t es = dtype_size(dtype_);
+  src_ids_.alloc(B * S * 4);
+  src_lens_.alloc(B * 4);
+  x_.alloc(R * d * es);
+  xn_.alloc(R * d * es);
+  xq_.alloc(R * std::max(d, F));
+  xs_.alloc(R * 4);
+  qkv_.alloc(R * 3 * d * es);
+  ctx_.alloc(R * d * es);
+  h_.alloc(R * F * es);
+  q_.alloc(R * d * es);
+  memory_.alloc(B * S * d * es);
+  mem_kv_.resize(mc_.dec_layers);
+  self_k_.resize(mc_.dec_layers);
+  self_v_.resize(mc_.dec_layers);
+  for (int l = 0; l < mc_.dec_layers; ++l) {
+    mem_kv_[l].alloc(B * S * 2 * d * es);
+    self_k_[l].alloc(N * L * d * es);
+    self_v_[l].alloc(N * L * d * es);
+  }
+  logits_.alloc(N * V * es);
+  cum_.alloc(N * es);
+  cand_scores_.alloc(B * 2 * cap_beam_ * es);
+  cand_ids_.alloc(B * 2 * cap_beam_ * 4);
+  ids_.alloc(N * 4);
+  finished_.alloc(B * 4);
+  top_done_.alloc(B * 4);
+  num_hyp_.alloc(B * 4);
+  alive_.alloc(2 * N * L * 4);
+  anc_.alloc(2 * N * L * 4);
+  CT2_CUDA_CHECK(cudaMemset(anc_.ptr, 0, anc_.bytes));
+  const int64_t maxh = 3 * cap_beam_;      // round(beam * patience) + beam with patience <= 2
+  hyp_tokens_.alloc(B * maxh * L * 4);
+  hyp_len_.alloc(B * maxh * 4);
+  hyp_score_.alloc(B * maxh * 4);
+  const size_t need = static_cast<size_t>(B) * S + B + static_cast<size_t>(B) * maxh * (L + 2) + B + 256;
+  if (need > host_pinned_elems_) {
+    if (host_pinned_) cudaFreeHost(host_pinned_);
+    CT2_CUDA_CHECK(cudaMallocHost(&host_pinned_, need * sizeof(int32_t)));
+    host_pinned_elems_ = need;
+  }
+}
+
+// =============================================================================================
+// layers
+// =============================================================================================
+void Translator::dense(const DenseWeights& w, const NormWeights* pre, const void* x, int64_t rows, const void* residual,
+                       int act, void* y) {
+  if (w.kind == DenseWeights::INT8) {
+    if (pre)
+      launch_layer_norm(x, pre->gamma.ptr, pre->beta.ptr, rows, w.k, mc_.eps, nullptr, xq_.as<int8_t>(), xs_.as<float>(),
+                        mc_.round_before_cast, dtype_, stream_);
+    else
+      launch_quantize_rows(x, dtype_, rows, w.k, mc_.round_before_cast, xq_.as<int8_t>(), xs_.as<float>(), stream_);
+    DenseEpilogue e{xs_.as<float>(), w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
+    gemm_s8(xq_.as<int8_t>(), w.weight.as<int8_t>(), rows, w.n, w.k, e, dtype_, CT2B200_GEMM_AUTO, stream_);
+  } else {
+    const void* src = x;
+    if (pre) {
+      launch_layer_norm(x, pre->gamma.ptr, pre->beta.ptr, rows, w.k, mc_.eps, xn_.ptr, nullptr, nullptr, true, dtype_, stream_);
+      src = xn_.ptr;
+    }
+    gemm_float(src, w.weight.ptr, w.bias.ptr, residual, act, rows, w.n, w.k, y, dtype_, stream_);
+  }
+}
+
+void Translator::post_norm(const NormWeights& n, void* x, int64_t rows) {
+  launch_layer_norm(x, n.gamma.ptr, n.beta.ptr, rows, mc_.d_model, mc_.eps, x, nullptr, nullptr, true, dtype_, stream_);
+}
+
+// TransformerEncoder::operator() (transformer.cc:427-471); rows = batch * S, padded positions are computed and ignored
+void Translator::run_encoder(int64_t batch, int64_t S) {
+  const int64_t rows = batch * S, d = mc_.d_model;
+  const float scale = 1.f / std::sqrt(static_cast<float>(mc_.head_dim));
+  const bool pre = mc_.enc_pre_norm;
+  launch_embed_pos(enc_emb_.weight.ptr, enc_emb_.kind == DenseWeights::INT8 ? enc_emb_.scale.as<float>() : nullptr,
+                   src_ids_.as<int32_t>(), rows, d, mc_.enc_emb_scale, enc_pos_.ptr, S, nullptr, false, x_.ptr, dtype_, stream_);
+  for (int l = 0; l < mc_.enc_layers; ++l) {
+    EncoderLayerWeights& w = enc_[l];
+    dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr);
+    launch_attention_encoder(qkv_.ptr, src_lens_.as<int32_t>(), batch, static_cast<int>(S), mc_.num_heads, mc_.head_dim, scale,
+                             ctx_.ptr, dtype_, stream_);
+    dense(w.self.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
+    if (!pre) post_norm(w.self.norm, x_.ptr, rows);
+    dense(w.ffn.ff1, pre ? &w.ffn.norm : nullptr, x_.ptr, rows, nullptr, mc_.enc_activation, h_.ptr);
+    dense(w.ffn.ff2, nullptr, h_.ptr, rows, x_.ptr, -1, x_.ptr);
+    if (!pre) post_norm(w.ffn.norm, x_.ptr, rows);
+  }
+  if (mc_.has_enc_final_norm)
+    launch_layer_norm(x_.ptr, enc_norm_.gamma.ptr, enc_norm_.beta.ptr, rows, d, mc_.eps, memory_.ptr, nullptr, nullptr, true, dtype_,
+                      stream_);
+  else
+    CT2_CUDA_CHECK(cudaMemcpyAsync(memory_.ptr, x_.ptr, rows * d * dtype_size(dtype_), cudaMemcpyDeviceToDevice, stream_));
+}
+
+// the memory keys / values of every decoder layer, once per batch (cached_attn_keys / values, attention.cc:385-428)
+void Translator::project_memory(int64_t batch, int64_t S) {
+  for (int l = 0; l < mc_.dec_layers; ++l)
+    dense(dec_[l].cross.kv, nullptr, memory_.ptr, batch * S, nullptr, -1, mem_kv_[l].ptr);
+}
+
+// TransformerDecoder::decode for one target position of every beam row (transformer.cc:621-871)
+void Translator::decoder_step(int64_t rows, int beam, int64_t batch, int64_t S) {
+  (void)batch;
+  const int64_t d = mc_.d_model;
+  const float scale = 1.f / std::sqrt(static_cast<float>(mc_.head_dim));
+  const bool pre = mc_.dec_pre_norm;
+  const int32_t* step_ptr = counters_.as<int32_t>();
+  launch_embed_pos(dec_emb_.weight.ptr, dec_emb_.kind == DenseWeights::INT8 ? dec_emb_.scale.as<float>() : nullptr,
+                   ids_.as<int32_t>(), rows, d, mc_.dec_emb_scale, dec_pos_.ptr, 1, step_ptr, mc_.start_from_zero_embedding, x_.ptr, dtype_,
+                   stream_);
+  for (int l = 0; l < mc_.dec_layers; ++l) {
+    DecoderLayerWeights& w = dec_[l];
+    dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr);
+    launch_attention_beam_self(qkv_.ptr, self_k_[l].ptr, self_v_[l].ptr, anc_.as<int32_t>(), step_ptr, rows,
+                               static_cast<int>(cap_steps_), mc_.num_heads, mc_.head_dim, scale, ctx_.ptr, dtype_, stream_);
+    dense(w.self.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
+    if (!pre) post_norm(w.self.norm, x_.ptr, rows);
+    dense(w.cross.in, pre ? &w.cross.norm : nullptr, x_.ptr, rows, nullptr, -1, q_.ptr);
+    launch_attention_cross(q_.ptr, mem_kv_[l].ptr, src_lens_.as<int32_t>(), rows, beam, static_cast<int>(S), mc_.num_heads,
+                           mc_.head_dim, scale, ctx_.ptr, dtype_, stream_);
+    dense(w.cross.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
+    if (!pre) post_norm(w.cross.norm, x_.ptr, rows);
+    dense(w.ffn.ff1, pre ? &w.ffn.norm : nullptr, x_.ptr, rows, nullptr, mc_.dec_activation, h_.ptr);
+    dense(w.ffn.ff2, nullptr, h_.ptr, rows, x_.ptr, -1, x_.ptr);
+    if (!pre) post_norm(w.ffn.norm, x_.ptr, rows);
+  }
+  dense(projection_, mc_.has_dec_final_norm ? &dec_norm_ : nullptr, x_.ptr, rows, nullptr, -1, logits_.ptr);
+}
+
+// log-probabilities + cumulative scores, TopK of 2 * beam candidates per entry, bookkeeping (decoding.cc:536-700)
+void Translator::beam_step(const BeamState& bs) {
+  const int64_t rows = static_cast<int64_t>(bs.batch) * bs.beam;
+  launch_beam_logprobs(logits_.ptr, rows, bs.vocab, cum_.ptr, bs.step, bs.min_length,
+                       bs.end_ids, bs.num_end, dtype_, stream_);
+  launch_topk(logits_.ptr, bs.batch, static_cast<int64_t>(bs.beam) * bs.vocab, 2 * bs.beam, cand_scores_.ptr,
+              cand_ids_.as<int32_t>(), dtype_, stream_);
+  launch_beam_update(bs, cand_scores_.ptr, cand_ids_.as<int32_t>(), cum_.ptr, dtype_, stream_);
+}
+
+void Translator::launch_or_capture_step(const BeamState& bs, int64_t S) {
+  const int64_t rows = static_cast<int64_t>(bs.batch) * bs.beam;
+  if (!use_graph_) {
+    decoder_step(rows, bs.beam, bs.batch, S);
+    beam_step(bs);
+    return;
+  }
+  if (!graph_) {
+    cudaGraph_t g = nullptr;
+    const int64_t before = g_kernel_launches.load();
+    CT2_CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
+    try {
+      decoder_step(rows, bs.beam, bs.batch, S);
+      beam_step(bs);
+    } catch (...) {
+      cudaStreamEndCapture(stream_, &g);
+      if (g) cudaGraphDestroy(g);
+      throw;
+    }
+    CT2_CUDA_CHECK(cudaStreamEndCapture(stream_, &g));
+    g_kernel_launches.store(before);
+    size_t n = 0;
+    cudaGraphGetNodes(g, nullptr, &n);
+    graph_nodes_ = static_cast<int64_t>(n);
+    CT2_CUDA_CHECK(cudaGraphInstantiate(&graph_, g, 0));
+    cudaGraphDestroy(g);
+  }
+  CT2_CUDA_CHECK(cudaGraphLaunch(graph_, stream_));
+  count_launch(static_cast<int>(graph_nodes_));
+}
+
+// =============================================================================================
+// Translator::translate_batch
+// =============================================================================================
+namespace {
+BeamState make_beam_state(const TranslationRequest& r, int64_t vocab, int64_t stride, int64_t max_hyp) {
+  BeamState bs;
+  bs.batch = static_cast<int>(r.batch);
+  bs.beam = r.beam_size;
+  bs.vocab = static_cast<int>(vocab);
+  bs.stride = static_cast<int>(stride);
+  bs.max_steps = static_cast<int>(r.max_decoding_length);
+  bs.max_hyp = static_cast<int>(max_hyp);
+  bs.min_length = static_cast<int>(r.min_decoding_length);
+  bs.max_candidates = std::max(1, static_cast<int>(std::lround(r.beam_size * r.patience)));   // decoding.cc:415-418
+  bs.num_hypotheses = r.num_hypotheses;
+  bs.early_exit = r.length_penalty == 0.f ? 1 : 0;
+  bs.num_end = static_cast<int>(r.end_ids.size());
+  return bs;
+}
+}  // namespace
+
+std::vector<TranslationHypotheses> Translator::translate(const TranslationRequest& r) {
+  const int64_t B = r.batch, S = r.max_source_len, L = r.max_decoding_length;
+  const int beam = r.beam_size;
+  CT2_REQUIRE(B > 0 && S > 0, "translate_batch: empty batch");
+  CT2_REQUIRE(beam >= 1 && beam <= 32, "beam_size must be in [1, 32]");
+  CT2_REQUIRE(r.num_hypotheses >= 1 && r.num_hypotheses <= beam, "num_hypotheses must be in [1, beam_size]");   // decoding.cc:1046-1048
+  CT2_REQUIRE(L >= 1 && r.min_decoding_length <= L, "min_decoding_length is greater than max_decoding_length");
+  CT2_REQUIRE(r.patience > 0.f && r.patience <= 2.f, "patience must be in (0, 2]");
+  CT2_REQUIRE(r.end_ids.size() <= 64, "at most 64 end tokens");
+  CT2_REQUIRE(static_cast<int64_t>(2) * beam <= static_cast<int64_t>(beam) * mc_.tgt_vocab, "beam_size exceeds the vocabulary");
+  for (int64_t b = 0; b < B; ++b) {
+    CT2_REQUIRE(r.source_lens[b] >= 1 && r.source_lens[b] <= S, "translate_batch: source lengths must be in [1, max_source_len]");
+    for (int64_t t = 0; t < r.source_lens[b]; ++t) {
+      const int32_t id = r.source_ids[b * S + t];
+      CT2_REQUIRE(id >= 0 && id < mc_.src_vocab, "translate_batch: source id out of range");
+    }
+  }
+  ensure_arena(B, S, beam, L);
+  const int64_t N = B * beam, stride = cap_steps_, maxh = 3 * cap_beam_;
+
+  // ---- inputs ----
+  int32_t* hp = host_pinned_;
+  for (int64_t b = 0; b < B; ++b)
+    for (int64_t t = 0; t < S; ++t) hp[b * S + t] = t < r.source_lens[b] ? r.source_ids[b * S + t] : 0;
+  int32_t* hl = hp + B * S;
+  for (int64_t b = 0; b < B; ++b) hl[b] = r.source_lens[b];
+  int32_t* hend = hl + B;
+  for (size_t i = 0; i < r.end_ids.size(); ++i) hend[i] = r.end_ids[i];
+  CT2_CUDA_CHECK(cudaMemcpyAsync(src_ids_.ptr, hp, B * S * 4, cudaMemcpyHostToDevice, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(src_lens_.ptr, hl, B * 4, cudaMemcpyHostToDevice, stream_));
+  if (!r.end_ids.empty())
+    CT2_CUDA_CHECK(cudaMemcpyAsync(end_ids_d_.ptr, hend, r.end_ids.size() * 4, cudaMemcpyHostToDevice, stream_));
+
+  // ---- encoder + memory projections ----
+  run_encoder(B, S);
+  project_memory(B, S);
+
+  // ---- beam search ----
+  BeamState bs = make_beam_state(r, mc_.tgt_vocab, stride, maxh);
+  bs.end_ids = end_ids_d_.as<int32_t>();
+  bs.step = counters_.as<int32_t>();
+  bs.ticket = bs.step + 1;
+  bs.num_finished = bs.step + 2;
+  bs.finished = finished_.as<int32_t>();
+  bs.top_done = top_done_.as<int32_t>();
+  bs.num_hyp = num_hyp_.as<int32_t>();
+  bs.alive = alive_.as<int32_t>();
+  bs.anc = anc_.as<int32_t>();
+  bs.next_ids = ids_.as<int32_t>();
+  bs.hyp_tokens = hyp_tokens_.as<int32_t>();
+  bs.hyp_len = hyp_len_.as<int32_t>();
+  bs.hyp_score = hyp_score_.as<float>();
+  // everything the captured step bakes in (kernel arguments are values)
+  std::vector<int64_t> key = {B, beam, S, stride, L, r.min_decoding_length, maxh, bs.max_candidates, bs.num_hypotheses,
+                              bs.early_exit, bs.num_end, N};
+  if (key != graph_key_) {
+    if (graph_) {
+      cudaGraphExecDestroy(graph_);
+      graph_ = nullptr;
+    }
+    graph_key_ = key;
+  }
+  CT2_CUDA_CHECK(cudaMemsetAsync(counters_.ptr, 0, 64, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(finished_.ptr, 0, B * 4, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(top_done_.ptr, 0, B * 4, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(num_hyp_.ptr, 0, B * 4, stream_));
+  launch_beam_init(cum_.ptr, ids_.as<int32_t>(), N, beam, r.start_id, dtype_, stream_);
+
+  const char* poll_env = std::getenv("CT2B200_EOS_POLL");
+  const int64_t poll = std::max<int64_t>(1, poll_env ? std::atoll(poll_env) : 4);
+  // the earliest step at which an entry can be complete: min_decoding_length (end tokens are masked before)
+  const int64_t first_check = std::max<int64_t>(0, r.min_decoding_length);
+  int32_t* hfin = hend + 64;
+  for (int64_t s = 0; s < L; ++s) {
+    launch_or_capture_step(bs, S);
+    if (s + 1 == L) break;
+    if (s >= first_check && (s - first_check) % poll == poll - 1) {
+      CT2_CUDA_CHECK(cudaMemcpyAsync(hfin, bs.num_finished, 4, cudaMemcpyDeviceToHost, stream_));
+      CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      if (*hfin >= B) break;
+    }
+  }
+
+  // ---- results: finalize_result (decoding.cc:189-254) on the host ----
+  int32_t* h_nh = hfin + 64;
+  int32_t* h_len = h_nh + B;
+  float* h_score = reinterpret_cast<float*>(h_len + B * maxh);
+  int32_t* h_tok = h_len + 2 * B * maxh;
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_nh, num_hyp_.ptr, B * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_len, hyp_len_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_score, hyp_score_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_tok, hyp_tokens_.ptr, B * maxh * stride * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  std::vector<TranslationHypotheses> out(B);
+  for (int64_t b = 0; b < B; ++b) {
+    const int nh = h_nh[b];
+    std::vector<float> sc(nh);
+    for (int j = 0; j < nh; ++j) {
+      const float len = static_cast<float>(h_len[b * maxh + j]);
+      sc[j] = h_score[b * maxh + j] / std::pow(len, r.length_penalty);
+    }
+    std::vector<int> order(nh);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return sc[a] > sc[c]; });
+    if (static_cast<int>(order.size()) > r.num_hypotheses) order.resize(r.num_hypotheses);
+    for (int j : order) {
+      const int32_t* t = h_tok + (b * maxh + j) * stride;
+      std::vector<int32_t> toks(t, t + h_len[b * maxh + j]);
+      if (!r.return_end_token)
+        while (!toks.empty() && std::find(r.end_ids.begin(), r.end_ids.end(), toks.back()) != r.end_ids.end()) toks.pop_back();
+      out[b].tokens.push_back(std::move(toks));
+      out[b].scores.push_back(sc[j]);
+    }
+  }
+  return out;
+}
+
+void Translator::encode(const int32_t* ids_h, const int32_t* lens_h, int64_t batch, int64_t S, float* memory_h) {
+  CT2_REQUIRE(batch > 0 && S > 0, "encode: empty batch");
+  ensure_arena(batch, S, 1, 1);
+  int32_t* hp = host_pinned_;
+  for (int64_t b = 0; b < batch; ++b) {
+    CT2_REQUIRE(lens_h[b] >= 1 && lens_h[b] <= S, "encode: source lengths must be in [1, max_source_len]");
+    for (int64_t t = 0; t < S; ++t) hp[b * S + t] = t < lens_h[b] ? ids_h[b * S + t] : 0;
+  }
+  CT2_CUDA_CHECK(cudaMemcpyAsync(src_ids_.ptr, hp, batch * S * 4, cudaMemcpyHostToDevice, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(src_lens_.ptr, lens_h, batch * 4, cudaMemcpyHostToDevice, stream_));
+  run_encoder(batch, S);
+  DeviceBuffer f32(static_cast<size_t>(batch) * S * mc_.d_model * 4);
+  launch_convert_to_f32(memory_.ptr, batch * S * mc_.d_model, f32.as<float>(), dtype_, stream_);
+  CT2_CUDA_CHECK(cudaMemcpyAsync(memory_h, f32.ptr, f32.bytes, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t steps, int64_t warmup, float* encode_ms,
+                       float* decode_ms, int64_t* launches) {
+  const int64_t L = steps + warmup;
+  ensure_arena(batch, source_len, beam, L);
+  std::vector<int32_t> ids(batch * source_len), lens(batch, static_cast<int32_t>(source_len));
+  for (size_t i = 0; i < ids.size(); ++i) ids[i] = static_cast<int32_t>((7919ull * i + 3) % mc_.src_vocab);
+  CT2_CUDA_CHECK(cudaMemcpy(src_ids_.ptr, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
+  CT2_CUDA_CHECK(cudaMemcpy(src_lens_.ptr, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice));
+  TranslationRequest r;
+  r.batch = batch;
+  r.max_source_len = source_len;
+  r.beam_size = beam;
+  r.max_decoding_length = L;
+  r.min_decoding_length = 0;
+  r.num_hypotheses = 1;
+  const int64_t stride = cap_steps_, maxh = 3 * cap_beam_, N = batch * beam;
+  BeamState bs = make_beam_state(r, mc_.tgt_vocab, stride, maxh);
+  bs.end_ids = end_ids_d_.as<int32_t>();
+  bs.step = counters_.as<int32_t>();
+  bs.ticket = bs.step + 1;
+  bs.num_finished = bs.step + 2;
+  bs.finished = finished_.as<int32_t>();
+  bs.top_done = top_done_.as<int32_t>();
+  bs.num_hyp = num_hyp_.as<int32_t>();
+  bs.alive = alive_.as<int32_t>();
+  bs.anc = anc_.as<int32_t>();
+  bs.next_ids = ids_.as<int32_t>();
+  bs.hyp_tokens = hyp_tokens_.as<int32_t>();
+  bs.hyp_len = hyp_len_.as<int32_t>();
+  bs.hyp_score = hyp_score_.as<float>();
+  std::vector<int64_t> key = {batch, beam, source_len, stride, L, 0, maxh, bs.max_candidates, bs.num_hypotheses, bs.early_exit,
+                              bs.num_end, N};
+  if (key != graph_key_) {
+    if (graph_) {
+      cudaGraphExecDestroy(graph_);
+      graph_ = nullptr;
+    }
+    graph_key_ = key;
+  }
+  cudaEvent_t e0, e1, e2, e3;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  cudaEventCreate(&e2);
+  cudaEventCreate(&e3);
+  run_encoder(batch, source_len);      // warm-up (first-use kernel configuration)
+  project_memory(batch, source_len);
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  cudaEventRecord(e0, stream_);
+  run_encoder(batch, source_len);
+  project_memory(batch, source_len);
+  cudaEventRecord(e1, stream_);
+  CT2_CUDA_CHECK(cudaMemsetAsync(counters_.ptr, 0, 64, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(finished_.ptr, 0, batch * 4, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(top_done_.ptr, 0, batch * 4, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(num_hyp_.ptr, 0, batch * 4, stream_));
+  launch_beam_init(cum_.ptr, ids_.as<int32_t>(), N, beam, 1, dtype_, stream_);
+  for (int64_t s = 0; s < warmup; ++s) launch_or_capture_step(bs, source_len);
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  const int64_t l0 = g_kernel_launches.load();
+  cudaProfilerStart();
+  cudaEventRecord(e2, stream_);
+  for (int64_t s = 0; s < steps; ++s) launch_or_capture_step(bs, source_len);
+  cudaEventRecord(e3, stream_);
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  cudaProfilerStop();
+  *launches = g_kernel_launches.load() - l0;
+  cudaEventElapsedTime(encode_ms, e0, e1);
+  cudaEventElapsedTime(decode_ms, e2, e3);
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaEventDestroy(e2);
+  cudaEventDestroy(e3);
+}
+
+}  // namespace ct2b200

@@ -101,6 +101,8 @@ void gemm_s8(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, 
              int dtype, int impl, cudaStream_t st);
 void gemm_s8_glu(const int8_t* A, const int8_t* Bgate, const int8_t* Bup, int64_t M, int64_t N, int64_t K,
                  const GluEpilogue& glu, int dtype, int impl, cudaStream_t st);
+void gemm_float(const void* A, const void* B, const void* bias, const void* residual, int act, int64_t M, int64_t N,
+                int64_t K, void* C, int dtype, cudaStream_t st);
 
 // awq.cu — AWQ-INT4 in the native (repacked, K-major) layout
 struct AwqNative {
@@ -171,5 +173,44 @@ void launch_convert_to_f32(const void* x, int64_t n, float* y, int dtype, cudaSt
 void launch_convert_from_f32(const float* x, int64_t n, void* y, int dtype, cudaStream_t st);
 void launch_fill_i32(int32_t* p, int64_t n, int32_t v, cudaStream_t st);
 void launch_mul_inplace(void* a_inout, const void* b, int64_t n, int dtype, cudaStream_t st);
+
+// seq2seq.cu — encoder-decoder path (Translator): embeddings + positions, LayerNorm, head_dim-agnostic attention, beam search
+void launch_embed_pos(const void* w, const float* w_scale, const int32_t* ids, int64_t rows, int64_t depth, float emb_scale,
+                      const void* pos, int64_t time, const int32_t* step_ptr, bool zero_first, void* y, int dtype,
+                      cudaStream_t st);
+void launch_layer_norm(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t cols, float eps, void* y,
+                       int8_t* q, float* scale, bool round, int dtype, cudaStream_t st);
+void launch_attention_encoder(const void* qkv, const int32_t* lengths, int64_t batch, int S, int H, int D, float scale,
+                              void* out, int dtype, cudaStream_t st);
+void launch_attention_beam_self(const void* qkv, void* k_cache, void* v_cache, const int32_t* anc, const int32_t* step_ptr,
+                                int64_t rows, int max_len, int H, int D, float scale, void* out, int dtype, cudaStream_t st);
+void launch_attention_cross(const void* q, const void* kv, const int32_t* lengths, int64_t rows, int beam, int S, int H, int D,
+                            float scale, void* out, int dtype, cudaStream_t st);
+// device state of BeamSearch::search (decoding.cc:425-720); N = batch * beam rows, `stride` = allocated steps per row
+struct BeamState {
+  int batch = 0, beam = 1, vocab = 0, stride = 0, max_steps = 0, max_hyp = 0, max_candidates = 1, num_hypotheses = 1;
+  int early_exit = 0, num_end = 0, min_length = 0;
+  const int32_t* end_ids = nullptr;
+  int32_t* step = nullptr;          // [1] current step, advanced by the update kernel
+  int32_t* ticket = nullptr;        // [1]
+  int32_t* num_finished = nullptr;  // [1] entries whose result is final (the host polls it)
+  int32_t* finished = nullptr;      // [batch]
+  int32_t* top_done = nullptr;      // [batch]
+  int32_t* num_hyp = nullptr;       // [batch]
+  int32_t* alive = nullptr;         // [2][N, stride] token history of the live beams (double-buffered by step parity)
+  int32_t* anc = nullptr;           // [2][N, stride] cache slot holding position t of the row's history
+  int32_t* next_ids = nullptr;      // [N] input ids of the next step
+  int32_t* hyp_tokens = nullptr;    // [batch, max_hyp, stride]
+  int32_t* hyp_len = nullptr;       // [batch, max_hyp]
+  float* hyp_score = nullptr;       // [batch, max_hyp] cumulative log-probability (not normalised)
+};
+void launch_beam_init(void* cum, int32_t* ids, int64_t rows, int beam, int start_id, int dtype, cudaStream_t st);
+void launch_beam_logprobs(void* logits, int64_t rows, int64_t vocab, const void* cum, const int32_t* step_ptr, int min_length,
+                          const int32_t* end_ids, int num_end, int dtype, cudaStream_t st);
+void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, int dtype,
+                        cudaStream_t st);
+// float32 Dense (true fp32 FMAs): c [m,n] = a [m,k] . b [n,k]^T with bias / activation / residual
+void gemm_f32(const float* A, const float* B, const float* bias, const float* residual, int act, int64_t M, int64_t N,
+              int64_t K, float* C, cudaStream_t st);
 
 }  // namespace ct2b200

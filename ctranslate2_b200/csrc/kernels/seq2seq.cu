@@ -1,0 +1,560 @@
+// seq2seq.cu — kernels of the encoder-decoder path (ctranslate2::Translator): embeddings with scale and
+// position encodings, LayerNorm (+ Quantize), a head_dim-agnostic attention (encoder self-attention with padding mask,
+// single-token decoder self-attention over a beam-REMAPPED cache, cross-attention over the memory keys / values of the
+// batch entry), and the device side of BeamSearch::search: log-softmax + cumulative scores, candidate bookkeeping,
+// hypothesis registration and the beam reindex as an index remap (no K/V bytes move when beams are reordered).
+// Reference kernels / functions these replace are cited per kernel (paths relative to the reference tree).
+#include <cfloat>
+
+#include "../common.cuh"
+#include "kernels.h"
+
+namespace ct2b200 {
+
+namespace {
+
+template <typename T> __device__ __forceinline__ float lowest_of();
+template <> __device__ __forceinline__ float lowest_of<float>() { return -FLT_MAX; }
+template <> __device__ __forceinline__ float lowest_of<__half>() { return -65504.f; }
+template <> __device__ __forceinline__ float lowest_of<__nv_bfloat16>() { return -3.3895313892515355e38f; }
+
+// ---------------------------------------------------------------------------------------------
+// layers::Embeddings (+ int8 dequantization, common.cc:64-81) * embeddings scale (transformer.cc:382-402, ops::Mul in T)
+// + PositionEncoder (common.cc:170-229, ops::Add in T).  Row r of [batch, time]: position = r % time, or *step_ptr for the
+// single-token decoder step (device-resident so that the step is CUDA-graph capturable).
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void embed_pos_kernel(const void* __restrict__ w, const float* __restrict__ w_scale, const int32_t* __restrict__ ids,
+                                 int64_t depth, float emb_scale, const T* __restrict__ pos, int64_t time,
+                                 const int32_t* __restrict__ step_ptr, bool zero_first, T* __restrict__ y) {
+  griddep_launch();
+  griddep_wait();
+  const int64_t r = blockIdx.x;
+  const int64_t id = ids[r];
+  const int64_t t = step_ptr ? static_cast<int64_t>(*step_ptr) : (r % time);
+  const float es = round_to<T>(emb_scale);
+  const bool zero = zero_first && t == 0;      // start_from_zero_embedding (transformer.cc:637-640): no token at step 0
+  for (int64_t j = threadIdx.x; j < depth; j += blockDim.x) {
+    float v;
+    if (zero) v = 0.f;
+    else if (w_scale) v = round_to<T>(__fdiv_rn(static_cast<float>(static_cast<const int8_t*>(w)[id * depth + j]), w_scale[id]));
+    else v = to_f32(static_cast<const T*>(w)[id * depth + j]);
+    if (emb_scale != 0.f && !zero) v = round_to<T>(v * es);
+    if (pos) v = round_to<T>(v + to_f32(pos[t * depth + j]));
+    y[r * depth + j] = from_f32<T>(v);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// ops::LayerNorm (src/ops/layer_norm_gpu.cu:169-206): mean = sum/n, var = max(sum(x^2)/n - mean^2, 0),
+// y = T((x - mean) * rsqrt(var + eps) * gamma + beta); optionally followed by ops::Quantize of T(y) (quantize_gpu.cu:57-105;
+// `round` = false reproduces models of binary version < 5, model.h:87-89).  y and (q, scale) may both be requested.
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                         const T* __restrict__ beta, int64_t cols, float eps,
+                                                         T* __restrict__ y, int8_t* __restrict__ q, float* __restrict__ scale,
+                                                         bool round) {
+  __shared__ float red[32];
+  griddep_launch();
+  griddep_wait();
+  const int64_t row = blockIdx.x;
+  const T* xr = x + row * cols;
+  float s1 = 0.f, s2 = 0.f;
+  for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+    const float v = to_f32(xr[j]);
+    s1 += v;
+    s2 += v * v;
+  }
+  s1 = block_reduce<false>(s1, red);
+  s2 = block_reduce<false>(s2, red);
+  const float inv_n = 1.f / static_cast<float>(cols);
+  const float mean = s1 * inv_n;
+  const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
+  auto normed = [&](int64_t j) {
+    const float g = gamma ? to_f32(gamma[j]) : 1.f, b = beta ? to_f32(beta[j]) : 0.f;
+    return round_to<T>((to_f32(xr[j]) - mean) * rstd * g + b);
+  };
+  if (q) {
+    float amax = 0.f;
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) amax = fmaxf(amax, fabsf(normed(j)));
+    amax = block_reduce<true>(amax, red);
+    const float s = amax != 0.f ? 127.f / amax : 1.f;
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) {
+      const float v = normed(j) * s;
+      q[row * cols + j] = static_cast<int8_t>(round ? nearbyintf(v) : v);
+    }
+    if (threadIdx.x == 0) scale[row] = s;
+  }
+  if (y) {
+    T* yr = y + row * cols;   // y may alias x: every thread rewrites only the elements it read last
+    __syncthreads();
+    for (int64_t j = threadIdx.x; j < cols; j += blockDim.x) yr[j] = from_f32<T>(normed(j));
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Attention for any head_dim (layers::MultiHeadAttention, attention.cc:178-287 dot_product_attention; the fused
+// decode kernels of attention_mma.cu cover head_dim 64 / 128 with rotary positions — this one serves the
+// encoder-decoder models: absolute positions, padding masks, beams).  One warp per (query row, head):
+//   scores_j = T(scale * q . k_j)  (fp32 accumulate), probs = T(softmax over the valid keys) (fp32), out = T(sum_j p_j v_j).
+// MODE 0  encoder self-attention: q, k, v = column blocks of qkv [B*S, 3d]; keys of row (b, t) = rows (b, j), j < lengths[b]
+// MODE 1  decoder self-attention of ONE new token per row: the row's k / v (columns d.. / 2d.. of qkv [N, 3d]) are written to
+//         the cache [N, max_len, d] at (row, step); key j < step lives in slot anc[row][j] — the beam ancestry table — so
+//         reordering beams never copies K/V (Decoder::update_state, decoder.cc:33-55, gathers the whole state instead)
+// MODE 2  cross-attention (attention.cc:371-440): q [N, d]; keys / values = column blocks of kv [B*S, 2d] of batch entry
+//         row / beam, j < lengths[row / beam] (the beams of an entry share the memory: replicate_state copies it instead)
+// ---------------------------------------------------------------------------------------------
+struct AttnGeneric {
+  const void* q;
+  int64_t q_stride;
+  const void* k;
+  const void* v;
+  int64_t kv_stride;
+  void* out;
+  int64_t out_stride;
+  const int32_t* lengths;
+  const int32_t* anc;        // MODE 1: [2][N, max_len] ancestry tables (read buffer = step & 1)
+  const int32_t* step_ptr;   // MODE 1
+  void* k_cache;             // MODE 1: [N, max_len, d]
+  void* v_cache;
+  int64_t rows;              // query rows
+  int S;                     // keys per batch entry (MODE 0 / 2) or max_len (MODE 1)
+  int beam;
+  int H, D;
+  float scale;
+  int max_keys;              // capacity of the per-warp score buffer
+};
+
+constexpr int kAttnWarps = 4;
+
+template <typename T, int MODE>
+__global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(AttnGeneric a) {
+  extern __shared__ float smem_f[];
+  griddep_launch();
+  griddep_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t unit = static_cast<int64_t>(blockIdx.x) * kAttnWarps + warp;
+  if (unit >= a.rows * a.H) return;
+  const int64_t n = unit / a.H;
+  const int h = static_cast<int>(unit % a.H);
+  const int D = a.D, d_model = a.H * a.D;
+  float* qs = smem_f + static_cast<size_t>(warp) * (a.max_keys + D);
+  float* sc = qs + D;
+  const T* qrow = static_cast<const T*>(a.q) + n * a.q_stride + h * D;
+  for (int i = lane; i < D; i += 32) qs[i] = to_f32(qrow[i]);
+
+  int nkeys;
+  int64_t base = 0;          // first key row (MODE 0 / 2)
+  const int32_t* anc = nullptr;
+  int step = 0;
+  const T* kb = static_cast<const T*>(a.k);
+  const T* vb = static_cast<const T*>(a.v);
+  if constexpr (MODE == 0) {
+    const int64_t b = n / a.S;
+    nkeys = a.lengths ? min(a.lengths[b], a.S) : a.S;
+    base = b * a.S;
+  } else if constexpr (MODE == 2) {
+    const int64_t b = n / a.beam;
+    nkeys = a.lengths ? min(a.lengths[b], a.S) : a.S;
+    base = b * a.S;
+  } else {
+    step = *a.step_ptr;
+    nkeys = step + 1;
+    anc = a.anc + static_cast<int64_t>(step & 1) * a.rows * a.S + n * a.S;
+    // append this row's key / value at (row, step)
+    T* kc = static_cast<T*>(a.k_cache) + (n * a.S + step) * d_model + h * D;
+    T* vc = static_cast<T*>(a.v_cache) + (n * a.S + step) * d_model + h * D;
+    const T* knew = static_cast<const T*>(a.q) + n * a.q_stride + d_model + h * D;
+    const T* vnew = knew + d_model;
+    for (int i = lane; i < D; i += 32) {
+      kc[i] = knew[i];
+      vc[i] = vnew[i];
+    }
+    kb = static_cast<const T*>(a.k_cache);
+    vb = static_cast<const T*>(a.v_cache);
+  }
+  __syncwarp();
+  auto key_row = [&](int j) -> int64_t {
+    if constexpr (MODE == 1) return (j == step ? n : static_cast<int64_t>(anc[j])) * a.S + j;
+    else return base + j;
+  };
+  // scores: one key per lane
+  float m = -INFINITY;
+  for (int j = lane; j < nkeys; j += 32) {
+    const T* kr = kb + key_row(j) * a.kv_stride + h * D;
+    float dot = 0.f;
+    if constexpr (MODE == 1) {
+      if (j == step) {          // own key: not necessarily visible through the cache pointer yet
+        const T* knew = static_cast<const T*>(a.q) + n * a.q_stride + d_model + h * D;
+        for (int i = 0; i < D; ++i) dot += qs[i] * to_f32(knew[i]);
+      } else {
+        for (int i = 0; i < D; ++i) dot += qs[i] * to_f32(kr[i]);
+      }
+    } else {
+      for (int i = 0; i < D; ++i) dot += qs[i] * to_f32(kr[i]);
+    }
+    const float s = round_to<T>(dot * a.scale);
+    sc[j] = s;
+    m = fmaxf(m, s);
+  }
+  m = warp_max(m);
+  float sum = 0.f;
+  for (int j = lane; j < nkeys; j += 32) sum += expf(sc[j] - m);
+  sum = warp_sum(sum);
+  for (int j = lane; j < nkeys; j += 32) sc[j] = round_to<T>(expf(sc[j] - m) / sum);
+  __syncwarp();
+  // context: one output dimension per lane
+  T* orow = static_cast<T*>(a.out) + n * a.out_stride + h * D;
+  for (int i = lane; i < D; i += 32) {
+    float acc = 0.f;
+    for (int j = 0; j < nkeys; ++j) {
+      const T* vr;
+      if constexpr (MODE == 1) {
+        vr = (j == step) ? static_cast<const T*>(a.q) + n * a.q_stride + 2 * d_model + h * D
+                         : vb + key_row(j) * a.kv_stride + h * D;
+      } else {
+        vr = vb + key_row(j) * a.kv_stride + h * D;
+      }
+      acc += sc[j] * to_f32(vr[i]);
+    }
+    orow[i] = from_f32<T>(acc);
+  }
+}
+
+// ---------------------------------------------------------------------------------------------
+// BeamSearch::search, device side (src/decoding.cc:425-720).
+// ---------------------------------------------------------------------------------------------
+// Step 1 per row of [B*beam, V]: DisableTokens of the end ids while step < min_length (apply_min_length, decoding.cc:60-81),
+// ops::LogSoftMax in fp32 -> T, then primitives::add_depth_broadcast of the beam's cumulative score IN T (decoding.cc:548-553).
+template <typename T>
+__global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logits, int64_t vocab, const T* __restrict__ cum,
+                                                            const int32_t* __restrict__ step_ptr, int min_length,
+                                                            const int32_t* __restrict__ end_ids, int num_end) {
+  __shared__ float red[32];
+  griddep_launch();
+  griddep_wait();
+  const int64_t row = blockIdx.x;
+  T* xr = logits + row * vocab;
+  const int step = *step_ptr;
+  if (step < min_length) {
+    for (int e = threadIdx.x; e < num_end; e += blockDim.x)
+      if (end_ids[e] >= 0 && end_ids[e] < vocab) xr[end_ids[e]] = from_f32<T>(lowest_of<T>());
+    __syncthreads();
+  }
+  float m = -INFINITY;
+  for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) m = fmaxf(m, to_f32(xr[j]));
+  m = block_reduce<true>(m, red);
+  float s = 0.f;
+  for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) s += expf(to_f32(xr[j]) - m);
+  s = block_reduce<false>(s, red);
+  const float logs = logf(s);
+  const float c = to_f32(cum[row]);
+  for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x)
+    xr[j] = from_f32<T>(round_to<T>(to_f32(xr[j]) - m - logs) + c);
+}
+
+// Step 3 (step 2 = ops::TopK of 2 * beam candidates over the flattened [beam * vocab] scores, rowwise.cu): one CTA per batch
+// entry walks the candidates exactly like decoding.cc:595-663 — a candidate among the first `beam` that ends (end token, or
+// last step) is registered as a hypothesis and its slot refilled from the secondary list — then rebuilds the beam state:
+// next ids, cumulative scores, token history (alive_seq) and the K/V ancestry table, both double-buffered by step parity.
+// Finished entries keep decoding (their results are frozen); the last CTA to finish advances the step counter.
+template <typename T>
+__global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T* __restrict__ cand_scores,
+                                                          const int32_t* __restrict__ cand_ids, T* __restrict__ cum) {
+  __shared__ int s_origin[64], s_word[64], s_active[32], s_hyp[32];
+  __shared__ float s_score[64];
+  __shared__ int s_last;
+  griddep_launch();
+  griddep_wait();
+  const int i = blockIdx.x;
+  const int beam = st.beam, nc = 2 * beam, L = st.stride;
+  const int step = *st.step;
+  const int N = st.batch * beam;
+  auto is_end = [&](int w) {
+    for (int e = 0; e < st.num_end; ++e)
+      if (st.end_ids[e] == w) return true;
+    return false;
+  };
+  if (threadIdx.x < nc) {
+    const int flat = cand_ids[i * nc + threadIdx.x];
+    s_origin[threadIdx.x] = flat / st.vocab;
+    s_word[threadIdx.x] = flat % st.vocab;
+    s_score[threadIdx.x] = to_f32(cand_scores[i * nc + threadIdx.x]);
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool was_finished = st.finished[i] != 0;
+    const bool is_last = step + 1 >= st.max_steps;
+    int secondary = beam, nh = st.num_hyp[i];
+    bool top_done = st.top_done[i] != 0;
+    for (int k = 0; k < beam; ++k) {
+      int next = k;
+      s_hyp[k] = -1;
+      if (!was_finished && (is_end(s_word[k]) || is_last)) {
+        if (k == 0) top_done = true;
+        if (nh < st.max_hyp) {
+          s_hyp[k] = nh;
+          st.hyp_len[i * st.max_hyp + nh] = step + 1;
+          st.hyp_score[i * st.max_hyp + nh] = s_score[k];
+          ++nh;
+        }
+        for (int j = secondary; j < nc; ++j)
+          if (!is_end(s_word[j])) {
+            next = j;
+            secondary = j + 1;
+            break;
+          }
+      }
+      s_active[k] = next;
+    }
+    if (!was_finished) {
+      bool fin;
+      if (is_last) fin = true;
+      else if (st.early_exit) fin = top_done && nh >= st.num_hypotheses;
+      else fin = nh >= st.max_candidates;
+      st.num_hyp[i] = nh;
+      st.top_done[i] = top_done ? 1 : 0;
+      if (fin) {
+        st.finished[i] = 1;
+        atomicAdd(st.num_finished, 1);
+      }
+    }
+  }
+  __syncthreads();
+  const int32_t* alive_r = st.alive + static_cast<int64_t>(step & 1) * N * L;
+  int32_t* alive_w = st.alive + static_cast<int64_t>((step + 1) & 1) * N * L;
+  const int32_t* anc_r = st.anc + static_cast<int64_t>(step & 1) * N * L;
+  int32_t* anc_w = st.anc + static_cast<int64_t>((step + 1) & 1) * N * L;
+  // hypotheses registered this step: history of the candidate's origin beam + its word
+  for (int k = 0; k < beam; ++k) {
+    const int slot = s_hyp[k];
+    if (slot < 0) continue;
+    int32_t* dst = st.hyp_tokens + (static_cast<int64_t>(i) * st.max_hyp + slot) * L;
+    const int32_t* src = alive_r + static_cast<int64_t>(i * beam + s_origin[k]) * L;
+    for (int t = threadIdx.x; t < step; t += blockDim.x) dst[t] = src[t];
+    if (threadIdx.x == 0) dst[step] = s_word[k];
+  }
+  // the next beams
+  for (int k = 0; k < beam; ++k) {
+    const int c = s_active[k];
+    const int64_t row = static_cast<int64_t>(i) * beam + k, parent = static_cast<int64_t>(i) * beam + s_origin[c];
+    for (int t = threadIdx.x; t < step; t += blockDim.x) {
+      alive_w[row * L + t] = alive_r[parent * L + t];
+      anc_w[row * L + t] = anc_r[parent * L + t];
+    }
+    if (threadIdx.x == 0) {
+      alive_w[row * L + step] = s_word[c];
+      anc_w[row * L + step] = static_cast<int32_t>(parent);
+      st.next_ids[row] = s_word[c];
+      cum[row] = from_f32<T>(s_score[c]);
+    }
+  }
+  // the last CTA advances the step (every CTA has read it by then)
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();
+    s_last = atomicAdd(st.ticket, 1) == static_cast<int>(gridDim.x) - 1;
+    if (s_last) {
+      *st.ticket = 0;
+      *st.step = step + 1;
+    }
+  }
+}
+
+// initialize_beam_scores (decoding.cc:84-93): beam 0 of every entry starts at 0, the others at the lowest T
+template <typename T>
+__global__ void beam_init_kernel(T* cum, int32_t* ids, int n, int beam, int start_id) {
+  const int r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= n) return;
+  cum[r] = from_f32<T>((r % beam) == 0 ? 0.f : lowest_of<T>());
+  ids[r] = start_id;
+}
+
+// ---------------------------------------------------------------------------------------------
+// float32 Dense (primitives<CUDA>::gemm<float, float>, src/cuda/primitives.cu:485-505: cublasSgemm) — C[m,n] = A[m,k] . B[n,k]^T
+// with the float epilogue of ops::Gemm (gemm.cc:10-25).  True fp32 FMAs on the CUDA cores (tcgen05 has no fp32 kind; TF32 would
+// not meet the reference's 1e-5 class): 64 x 64 tiles, 16-deep K slices in shared memory, 4 x 4 outputs per thread.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t M, int64_t N,
+                                                      int64_t K, FloatEpilogue e) {
+  __shared__ float As[16][64 + 4], Bs[16][64 + 4];
+  griddep_launch();
+  griddep_wait();
+  const int tx = threadIdx.x % 16, ty = threadIdx.x / 16;
+  const int64_t m0 = static_cast<int64_t>(blockIdx.y) * 64, n0 = static_cast<int64_t>(blockIdx.x) * 64;
+  float acc[4][4] = {};
+  for (int64_t k0 = 0; k0 < K; k0 += 16) {
+    for (int idx = threadIdx.x; idx < 64 * 16; idx += 256) {
+      const int r = idx / 16, c = idx % 16;
+      As[c][r] = (m0 + r < M && k0 + c < K) ? A[(m0 + r) * K + k0 + c] : 0.f;
+      Bs[c][r] = (n0 + r < N && k0 + c < K) ? B[(n0 + r) * K + k0 + c] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        a[i] = As[kk][ty * 4 + i];
+        b[i] = Bs[kk][tx * 4 + i];
+      }
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int64_t r = m0 + ty * 4 + i, c = n0 + tx * 4 + j;
+      if (r < M && c < N) float_epilogue_store<float>(e, acc[i][j], r, c);
+    }
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------
+// launchers
+// ---------------------------------------------------------------------------------------------
+void launch_embed_pos(const void* w, const float* w_scale, const int32_t* ids, int64_t rows, int64_t depth, float emb_scale,
+                      const void* pos, int64_t time, const int32_t* step_ptr, bool zero_first, void* y, int dtype,
+                      cudaStream_t st) {
+  if (rows == 0) return;
+  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(embed_pos_kernel<T>, dim3(rows), dim3(128), 0, st, w, w_scale, ids, depth, emb_scale,
+                                        static_cast<const T*>(pos), time, step_ptr, zero_first, static_cast<T*>(y))));
+  check_launch();
+}
+
+void launch_layer_norm(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t cols, float eps, void* y,
+                       int8_t* q, float* scale, bool round, int dtype, cudaStream_t st) {
+  if (rows == 0) return;
+  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(layer_norm_kernel<T>, dim3(rows), dim3(256), 0, st, static_cast<const T*>(x),
+                                        static_cast<const T*>(gamma), static_cast<const T*>(beta), cols, eps,
+                                        static_cast<T*>(y), q, scale, round)));
+  check_launch();
+}
+
+namespace {
+template <typename T, int MODE>
+void launch_attn_mode(const AttnGeneric& a, cudaStream_t st) {
+  const size_t smem = static_cast<size_t>(kAttnWarps) * (a.max_keys + a.D) * sizeof(float);
+  CT2_REQUIRE(smem <= 200 * 1024, "attention: too many keys for the generic kernel");
+  auto kernel = attention_generic_kernel<T, MODE>;
+  if (smem > 48 * 1024) {
+    // the attribute is per device: set it whenever the request grows (cheap, idempotent)
+    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
+  }
+  const int64_t units = a.rows * a.H;
+  launch_pdl(kernel, dim3(static_cast<unsigned>((units + kAttnWarps - 1) / kAttnWarps)), dim3(kAttnWarps * 32), smem, st, a);
+  check_launch();
+}
+}  // namespace
+
+void launch_attention_encoder(const void* qkv, const int32_t* lengths, int64_t batch, int S, int H, int D, float scale,
+                              void* out, int dtype, cudaStream_t st) {
+  if (batch * S == 0) return;
+  const int64_t d = static_cast<int64_t>(H) * D;
+  const size_t es = dtype_size(dtype);
+  AttnGeneric a{};
+  a.q = qkv;
+  a.q_stride = 3 * d;
+  a.k = static_cast<const uint8_t*>(qkv) + d * es;
+  a.v = static_cast<const uint8_t*>(qkv) + 2 * d * es;
+  a.kv_stride = 3 * d;
+  a.out = out;
+  a.out_stride = d;
+  a.lengths = lengths;
+  a.rows = batch * S;
+  a.S = S;
+  a.beam = 1;
+  a.H = H;
+  a.D = D;
+  a.scale = scale;
+  a.max_keys = S;
+  CT2_DISPATCH_DTYPE(dtype, (launch_attn_mode<T, 0>(a, st)));
+}
+
+void launch_attention_beam_self(const void* qkv, void* k_cache, void* v_cache, const int32_t* anc, const int32_t* step_ptr,
+                                int64_t rows, int max_len, int H, int D, float scale, void* out, int dtype, cudaStream_t st) {
+  if (rows == 0) return;
+  const int64_t d = static_cast<int64_t>(H) * D;
+  AttnGeneric a{};
+  a.q = qkv;
+  a.q_stride = 3 * d;
+  a.kv_stride = d;
+  a.out = out;
+  a.out_stride = d;
+  a.anc = anc;
+  a.step_ptr = step_ptr;
+  a.k_cache = k_cache;
+  a.v_cache = v_cache;
+  a.rows = rows;
+  a.S = max_len;
+  a.beam = 1;
+  a.H = H;
+  a.D = D;
+  a.scale = scale;
+  a.max_keys = max_len;
+  CT2_DISPATCH_DTYPE(dtype, (launch_attn_mode<T, 1>(a, st)));
+}
+
+void launch_attention_cross(const void* q, const void* kv, const int32_t* lengths, int64_t rows, int beam, int S, int H, int D,
+                            float scale, void* out, int dtype, cudaStream_t st) {
+  if (rows == 0) return;
+  const int64_t d = static_cast<int64_t>(H) * D;
+  const size_t es = dtype_size(dtype);
+  AttnGeneric a{};
+  a.q = q;
+  a.q_stride = d;
+  a.k = kv;
+  a.v = static_cast<const uint8_t*>(kv) + d * es;
+  a.kv_stride = 2 * d;
+  a.out = out;
+  a.out_stride = d;
+  a.lengths = lengths;
+  a.rows = rows;
+  a.S = S;
+  a.beam = beam;
+  a.H = H;
+  a.D = D;
+  a.scale = scale;
+  a.max_keys = S;
+  CT2_DISPATCH_DTYPE(dtype, (launch_attn_mode<T, 2>(a, st)));
+}
+
+void launch_beam_init(void* cum, int32_t* ids, int64_t rows, int beam, int start_id, int dtype, cudaStream_t st) {
+  if (rows == 0) return;
+  CT2_DISPATCH_DTYPE(dtype, (beam_init_kernel<T><<<div_up(rows, 128), 128, 0, st>>>(static_cast<T*>(cum), ids,
+                                                                                      static_cast<int>(rows), beam, start_id)));
+  check_launch();
+}
+
+void launch_beam_logprobs(void* logits, int64_t rows, int64_t vocab, const void* cum, const int32_t* step_ptr, int min_length,
+                          const int32_t* end_ids, int num_end, int dtype, cudaStream_t st) {
+  if (rows == 0) return;
+  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_logprobs_kernel<T>, dim3(rows), dim3(256), 0, st, static_cast<T*>(logits), vocab,
+                                        static_cast<const T*>(cum), step_ptr, min_length, end_ids, num_end)));
+  check_launch();
+}
+
+void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, int dtype,
+                        cudaStream_t st) {
+  CT2_REQUIRE(s.beam >= 1 && s.beam <= 32, "beam_size must be in [1, 32]");
+  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_update_kernel<T>, dim3(s.batch), dim3(128), 0, st, s,
+                                        static_cast<const T*>(cand_scores), cand_ids, static_cast<T*>(cum))));
+  check_launch();
+}
+
+void gemm_f32(const float* A, const float* B, const float* bias, const float* residual, int act, int64_t M, int64_t N,
+              int64_t K, float* C, cudaStream_t st) {
+  if (M == 0 || N == 0) return;
+  FloatEpilogue e{bias, residual, C, act, N};
+  launch_pdl(gemm_f32_kernel, dim3(div_up(N, 64), div_up(M, 64)), dim3(256), 0, st, A, B, M, N, K, e);
+  check_launch();
+}
+
+}  // namespace ct2b200

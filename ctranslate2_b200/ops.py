@@ -60,7 +60,7 @@ class Quantize:
 
 class Gemm:
     """ops::Gemm for the form layers::Dense uses: alpha=1, beta=0, trans_a=False, trans_b=True.
-    int8 x int8 -> int32 (exact) or float16/bfloat16 -> same type (fp32 accumulate, + bias/activation/residual)."""
+    int8 x int8 -> int32 (exact) or float32/float16/bfloat16 -> same type (fp32 accumulate, + bias/activation/residual)."""
     def __init__(self, alpha=1.0, beta=0.0, trans_a=False, trans_b=True, activation_type: Optional[int] = None,
                  impl: int = GEMM_AUTO):
         if alpha != 1.0 or beta != 0.0 or trans_a or not trans_b:
@@ -80,6 +80,10 @@ class Gemm:
                                         self.impl, _stream()))
             return c
         c = torch.empty((m, n), dtype=a.dtype, device=a.device)
+        if a.dtype == torch.float32:      # primitives<CUDA>::gemm<float, float>: true fp32 FMAs
+            check(lib().ct2b200_gemm_f32(_p(a), _p(b), _p(bias), _p(residual), self.act, ctypes.c_int64(m), ctypes.c_int64(n),
+                                         ctypes.c_int64(k), _p(c), _stream()))
+            return c
         check(lib().ct2b200_gemm_f16(_p(a), _p(b), _p(bias), _p(residual), self.act, ctypes.c_int64(m),
                                      ctypes.c_int64(n), ctypes.c_int64(k), _p(c), _dt(a), _stream()))
         return c
@@ -380,3 +384,24 @@ def dense_awq_glu(x, wg: AwqWeight, wu: AwqWeight, activation_type=ActivationTyp
                                       wg.group_size, activation_type, ctypes.c_int64(m), ctypes.c_int64(wg.n),
                                       ctypes.c_int64(wg.k), _p(h), _p(s1), _p(s2), _stream()))
     return h
+
+
+class LayerNorm:
+    """ops::LayerNorm over the last axis (include/ctranslate2/ops/layer_norm.h): y = LayerNorm(axis=-1, epsilon)(beta, gamma, x).
+    quantize=True also returns ops::Quantize of the normalised row from the same launch: (y, q, scale)."""
+    def __init__(self, axis: int = -1, epsilon: float = 1e-5):
+        if axis != -1:
+            raise ValueError("LayerNorm: only the last axis is on the hot path")
+        self.epsilon = epsilon
+
+    def __call__(self, beta, gamma, x, quantize: bool = False, round_before_cast: bool = True):
+        x = _c(x)
+        cols = x.shape[-1]
+        rows = x.numel() // cols if cols else 0
+        y = torch.empty_like(x)
+        q = torch.empty(x.shape, dtype=torch.int8, device=x.device) if quantize else None
+        s = torch.empty(x.shape[:-1], dtype=torch.float32, device=x.device) if quantize else None
+        check(lib().ct2b200_layer_norm(_p(x), _p(gamma), _p(beta), ctypes.c_int64(rows), ctypes.c_int64(cols),
+                                       ctypes.c_float(self.epsilon), _p(y), _p(q), _p(s), int(round_before_cast), _dt(x),
+                                       _stream()))
+        return (y, q, s) if quantize else y

@@ -113,6 +113,17 @@ CT2B200_API int ct2b200_dense_s8_glu_rows(const void* x_d, const void* gamma_d, 
 CT2B200_API int ct2b200_gemm_f16(const void* a_d, const void* b_d, const void* bias_d, const void* residual_d, int act,
                      int64_t m, int64_t n, int64_t k, void* c_d, int dtype, void* stream);
 
+/* primitives<Device::CUDA>::gemm<float,float> (trans_b, alpha 1, beta 0) + apply_bias_and_activation —
+ * src/cuda/primitives.cu:485-505 (cublasSgemm), src/ops/gemm.cc:10-25.  True fp32 FMAs (no TF32). */
+CT2B200_API int ct2b200_gemm_f32(const float* a_d, const float* b_d, const float* bias_d, const float* residual_d, int act,
+                     int64_t m, int64_t n, int64_t k, float* c_d, void* stream);
+
+/* ops::LayerNorm::compute<Device::CUDA,T> (last axis) — include/ctranslate2/ops/layer_norm.h, src/ops/layer_norm_gpu.cu:33-66,
+ * 169-206: y = (x - mean) * rsqrt(var + eps) * gamma + beta.  y_d may be NULL when only the quantized row is wanted;
+ * q_d / scale_d non-NULL adds ops::Quantize of T(y) in the same launch (layers::LayerNorm + Dense's Quantize). */
+CT2B200_API int ct2b200_layer_norm(const void* x_d, const void* gamma_d, const void* beta_d, int64_t rows, int64_t cols, float eps,
+                       void* y_d, int8_t* q_d, float* scale_d, int round_before_cast, int dtype, void* stream);
+
 /* ops::RMSNorm::compute<Device::CUDA,T> — include/ctranslate2/ops/rms_norm.h, src/ops/rms_norm_gpu.cu:19-63. */
 CT2B200_API int ct2b200_rms_norm(const void* gamma_d, const void* x_d, int64_t rows, int64_t cols, float eps,
                      int use_residual, void* y_d, int dtype, void* stream);
@@ -233,7 +244,7 @@ typedef struct {
 } ct2b200_generator_config;
 
 /* models::Model::load(model_dir, Device::CUDA, device, compute_type) + Generator ctor.
- * Reads model.bin (binary versions 4..6), config.json. */
+ * Reads model.bin (binary versions 2..6), config.json. */
 CT2B200_API ct2b200_generator* ct2b200_generator_open(const char* model_dir, const ct2b200_generator_config* config);
 CT2B200_API void ct2b200_generator_close(ct2b200_generator* g);
 CT2B200_API int ct2b200_generator_vocab_size(const ct2b200_generator* g);
@@ -285,6 +296,41 @@ CT2B200_API int ct2b200_bench_decode(ct2b200_generator* g, int64_t batch, int64_
  * Every rank must then issue the same generate_batch / forward_batch calls with the same inputs. */
 CT2B200_API int ct2b200_generator_tp_handle(ct2b200_generator* g, void* handle64_h);
 CT2B200_API int ct2b200_generator_tp_connect(ct2b200_generator* g, const void* handles_h, int num_handles);
+
+/* ---------------------------------------------------------------------------------------------
+ * Encoder-decoder path: ctranslate2::Translator — include/ctranslate2/translator.h:20-60,
+ * TranslationOptions include/ctranslate2/translation.h:14-98; models::TransformerModel (src/models/transformer.cc),
+ * EncoderDecoderReplica::run_translation (src/models/sequence_to_sequence.cc:305-420), TransformerEncoder /
+ * TransformerDecoder with cross-attention (src/layers/transformer.cc), BeamSearch::search (src/decoding.cc:425-720).
+ * Serves pre- and post-norm LayerNorm Transformers with absolute (sinusoidal or stored) positions; model.bin versions 2..6.
+ * ct2b200_generator_config: compute_type / weight_type / device / use_cuda_graph are honoured; max_length bounds the
+ * positions reserved for sinusoidal encodings (>= 500); max_batch is a hint (arenas grow on demand).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct ct2b200_translator ct2b200_translator;
+CT2B200_API ct2b200_translator* ct2b200_translator_open(const char* model_dir, const ct2b200_generator_config* config);
+CT2B200_API void ct2b200_translator_close(ct2b200_translator* t);
+CT2B200_API int ct2b200_translator_info(const ct2b200_translator* t, int* encoder_layers, int* decoder_layers, int* num_heads,
+                            int* d_model, int* source_vocab, int* target_vocab, int64_t* weight_bytes);
+/* Host only: the geometry parse_seq2seq_config reads from `model_dir`, as JSON. */
+CT2B200_API int ct2b200_translator_summary(const char* model_dir, char* json_out, size_t capacity);
+
+/* Translator::translate_batch on ids (Vocabulary lookups stay on the caller's side).  HOST buffers:
+ *   source_ids_h [batch, max_source_len] int32 right-padded (with_source_bos / eos already applied), source_lens_h [batch];
+ *   out_ids_h [batch, num_hypotheses, max_decoding_length] (-1 padded), out_lens_h / out_scores_h [batch, num_hypotheses]
+ *   (length -1 = fewer hypotheses than asked).  beam_size 1 = GreedySearch (identical results to the beam-of-one search).
+ *   Scores are cumulative log-probabilities / length^length_penalty (finalize_result, decoding.cc:189-254). */
+CT2B200_API int ct2b200_translate_batch(ct2b200_translator* t, const int32_t* source_ids_h, const int32_t* source_lens_h,
+                            int64_t batch, int64_t max_source_len, int beam_size, float patience, float length_penalty,
+                            int64_t max_decoding_length, int64_t min_decoding_length, int num_hypotheses, int32_t start_id,
+                            const int32_t* end_ids_h, int num_end_ids, int return_end_token, int32_t* out_ids_h,
+                            int32_t* out_lens_h, float* out_scores_h);
+/* TransformerEncoder::operator() — memory_h [batch, max_source_len, d_model] f32 host (padded positions are unspecified). */
+CT2B200_API int ct2b200_translator_encode(ct2b200_translator* t, const int32_t* source_ids_h, const int32_t* source_lens_h,
+                              int64_t batch, int64_t max_source_len, float* memory_h);
+/* Device-timed phases for bench.py: one encoder pass of [batch, source_len], then `steps` beam-search steps of
+ * batch * beam_size rows with inputs resident in HBM. */
+CT2B200_API int ct2b200_bench_translate(ct2b200_translator* t, int64_t batch, int64_t source_len, int beam_size, int64_t steps,
+                            int64_t warmup, float* encode_ms, float* decode_ms, int64_t* kernel_launches);
 
 #ifdef __cplusplus
 }

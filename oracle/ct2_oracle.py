@@ -15,7 +15,9 @@ All arithmetic is float32 unless stated; integer paths are exact.
 """
 from __future__ import annotations
 
+import json
 import math
+import os
 import struct
 from dataclasses import dataclass, field
 from typing import Dict, List, Optional, Sequence, Tuple
@@ -556,7 +558,7 @@ class Seq2SeqOracle:
     sqrt(d) (:382-402), INT8 Dense with bias, beam search (beam_search above).  `v` = variables of model.bin."""
 
     def __init__(self, variables: Dict[str, np.ndarray], num_heads: int = 8, flavor: str = "cpu",
-                 binary_version: int = 6, compute_type: str = "int8"):
+                 binary_version: int = 6, compute_type: str = "int8", eps: float = 1e-5):
         self.v = variables
         self.flavor = flavor
         self.round_before_cast = binary_version >= 5
@@ -565,7 +567,8 @@ class Seq2SeqOracle:
         self.compute_type = compute_type
         self._float_w: Dict[str, np.ndarray] = {}
         self.num_heads = int(variables.get("encoder/num_heads", np.int16(num_heads)))
-        self.d = variables["encoder/embeddings/weight"].shape[1]
+        self.enc_emb = "encoder/embeddings_0" if "encoder/embeddings_0/weight" in variables else "encoder/embeddings"
+        self.d = variables[self.enc_emb + "/weight"].shape[1]
         self.enc_layers = 0
         while f"encoder/layer_{self.enc_layers}/ffn/linear_0/weight" in variables:
             self.enc_layers += 1
@@ -573,13 +576,29 @@ class Seq2SeqOracle:
         while f"decoder/layer_{self.dec_layers}/ffn/linear_0/weight" in variables:
             self.dec_layers += 1
         self.pos = sinusoidal_position_encoding(512, self.d)
+        # attributes of TransformerSpec (scoped since spec revision 5, models/transformer.cc:67-79)
+        def attr(scope, name, default):
+            for key in (f"{scope}/{name}", name):
+                if key in variables:
+                    return variables[key]
+            return default
+        self.pre_norm = {s: bool(attr(s, "pre_norm", True)) for s in ("encoder", "decoder")}
+        self.act = {s: int(attr(s, "activation", ACT_RELU)) for s in ("encoder", "decoder")}
+        self.zero_first = bool(variables.get("decoder/start_from_zero_embedding", False))
+        self.eps = eps
 
     @classmethod
     def from_dir(cls, model_dir: str, flavor: str = "cpu", compute_type: str = "int8") -> "Seq2SeqOracle":
         _, _, variables, _ = read_model_bin(model_dir + "/model.bin")
         with open(model_dir + "/model.bin", "rb") as f:
             binary_version = struct.unpack("<I", f.read(4))[0]
-        return cls(variables, flavor=flavor, binary_version=binary_version, compute_type=compute_type)
+        eps = 1e-5
+        cfg = os.path.join(model_dir, "config.json")
+        if os.path.exists(cfg):
+            with open(cfg) as f:
+                e = json.load(f).get("layer_norm_epsilon")
+            eps = eps if e is None else float(e)
+        return cls(variables, flavor=flavor, binary_version=binary_version, compute_type=compute_type, eps=eps)
 
     # -- layers -----------------------------------------------------------------------
     def _dense(self, prefix, x, act=ACT_NONE, residual=None):
@@ -600,14 +619,21 @@ class Seq2SeqOracle:
 
     def _embed(self, scope, ids):
         v = self.v
-        x = gather_rows(v[scope + "/embeddings/weight"], ids).astype(f32)
-        if scope + "/embeddings/weight_scale" in v:              # Embeddings::operator(), common.cc:64-81
-            sc = v[scope + "/embeddings/weight_scale"].astype(f32)
+        emb = self.enc_emb if scope == "encoder" else "decoder/embeddings"
+        x = gather_rows(v[emb + "/weight"], ids).astype(f32)
+        if emb + "/weight_scale" in v:                           # Embeddings::operator(), common.cc:64-81
+            sc = v[emb + "/weight_scale"].astype(f32)
             x = (x / (gather_rows(sc, ids)[..., None] if sc.ndim == 1 else sc)).astype(f32)
         return (x * f32(math.sqrt(self.d))).astype(f32)          # build_embeddings_scale: sqrt(depth)
 
     def _ln(self, prefix, x):
-        return layer_norm(x, self.v[prefix + "/gamma"], self.v[prefix + "/beta"], 1e-5)
+        return layer_norm(x, self.v[prefix + "/gamma"], self.v[prefix + "/beta"], self.eps)
+
+    def _sublayer(self, scope, prefix, x, fn):
+        """pre-norm: x + f(LN(x)); post-norm: LN(x + f(x)) (attention.cc:497-500, 602-614; transformer.cc:21-51)."""
+        if self.pre_norm[scope]:
+            return fn(self._ln(prefix + "/layer_norm", x), x)
+        return self._ln(prefix + "/layer_norm", fn(x, x))
 
     def _attend(self, q, k, v_, lens_rows):
         """q [B,T,d], k/v [B,S,d] -> context [B,T,d]; softmax over the first lens_rows keys of each (b, h, t) row."""
@@ -630,14 +656,17 @@ class Seq2SeqOracle:
         lens_rows = np.repeat(lengths, self.num_heads * S)
         for l in range(self.enc_layers):
             p = f"encoder/layer_{l}/"
-            h = self._ln(p + "self_attention/layer_norm", x)
-            qkv = self._dense(p + "self_attention/linear_0", h)
-            q, k, v_ = np.split(qkv, 3, axis=-1)
-            x = self._dense(p + "self_attention/linear_1", self._attend(q, k, v_, lens_rows), residual=x)
-            h = self._ln(p + "ffn/layer_norm", x)
-            h = self._dense(p + "ffn/linear_0", h, act=ACT_RELU)
-            x = self._dense(p + "ffn/linear_1", h, residual=x)
-        return self._ln("encoder/layer_norm", x)
+
+            def attn(h, res):
+                q, k, v_ = np.split(self._dense(p + "self_attention/linear_0", h), 3, axis=-1)
+                return self._dense(p + "self_attention/linear_1", self._attend(q, k, v_, lens_rows), residual=res)
+
+            def ffn(h, res):
+                return self._dense(p + "ffn/linear_1", self._dense(p + "ffn/linear_0", h, act=self.act["encoder"]), residual=res)
+
+            x = self._sublayer("encoder", p + "self_attention", x, attn)
+            x = self._sublayer("encoder", p + "ffn", x, ffn)
+        return self._ln("encoder/layer_norm", x) if "encoder/layer_norm/gamma" in self.v else x
 
     # -- decoder ----------------------------------------------------------------------
     def start(self, memory: np.ndarray, lengths: np.ndarray, beam_size: int):
@@ -664,25 +693,34 @@ class Seq2SeqOracle:
         """One target position for every row: ids [N] at position `step` -> logits [N, V]."""
         N = ids.shape[0]
         H = self.num_heads
-        x = (self._embed("decoder", ids.reshape(N, 1)) + self.pos[step:step + 1][None]).astype(f32)
+        x = self._embed("decoder", ids.reshape(N, 1))
+        if self.zero_first and step == 0:                        # start_from_zero_embedding (transformer.cc:637-640)
+            x = np.zeros_like(x)
+        x = (x + self.pos[step:step + 1][None]).astype(f32)
         for l in range(self.dec_layers):
             p = f"decoder/layer_{l}/"
-            h = self._ln(p + "self_attention/layer_norm", x)
-            qkv = self._dense(p + "self_attention/linear_0", h)
-            q, k, v_ = np.split(qkv, 3, axis=-1)
-            self.self_k[l] = np.concatenate([self.self_k[l], k], axis=1)
-            self.self_v[l] = np.concatenate([self.self_v[l], v_], axis=1)
-            S = self.self_k[l].shape[1]
-            ctx = self._attend(q, self.self_k[l], self.self_v[l], np.full(N * H, S))
-            x = self._dense(p + "self_attention/linear_1", ctx, residual=x)
-            h = self._ln(p + "attention/layer_norm", x)
-            q = self._dense(p + "attention/linear_0", h)
-            ctx = self._attend(q, self.mem_k[l], self.mem_v[l], np.repeat(self.mem_lengths, H))
-            x = self._dense(p + "attention/linear_2", ctx, residual=x)
-            h = self._ln(p + "ffn/layer_norm", x)
-            h = self._dense(p + "ffn/linear_0", h, act=ACT_RELU)
-            x = self._dense(p + "ffn/linear_1", h, residual=x)
-        x = self._ln("decoder/layer_norm", x)
+
+            def self_attn(h, res):
+                q, k, v_ = np.split(self._dense(p + "self_attention/linear_0", h), 3, axis=-1)
+                self.self_k[l] = np.concatenate([self.self_k[l], k], axis=1)
+                self.self_v[l] = np.concatenate([self.self_v[l], v_], axis=1)
+                S = self.self_k[l].shape[1]
+                ctx = self._attend(q, self.self_k[l], self.self_v[l], np.full(N * H, S))
+                return self._dense(p + "self_attention/linear_1", ctx, residual=res)
+
+            def cross_attn(h, res):
+                q = self._dense(p + "attention/linear_0", h)
+                ctx = self._attend(q, self.mem_k[l], self.mem_v[l], np.repeat(self.mem_lengths, H))
+                return self._dense(p + "attention/linear_2", ctx, residual=res)
+
+            def ffn(h, res):
+                return self._dense(p + "ffn/linear_1", self._dense(p + "ffn/linear_0", h, act=self.act["decoder"]), residual=res)
+
+            x = self._sublayer("decoder", p + "self_attention", x, self_attn)
+            x = self._sublayer("decoder", p + "attention", x, cross_attn)
+            x = self._sublayer("decoder", p + "ffn", x, ffn)
+        if "decoder/layer_norm/gamma" in self.v:
+            x = self._ln("decoder/layer_norm", x)
         return self._dense("decoder/projection", x)[:, 0, :]
 
     # -- Translator::translate_batch ---------------------------------------------------

@@ -1,68 +1,88 @@
 #!/bin/bash
-# tools/gpu_call.sh — the command list of ONE gpurun call (edited per call; what each call measured is summarised in
+# tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
-#   /usr/local/graft/bin/gpurun --timeout 3000 -- 'bash tools/gpu_call.sh'
+#   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
+# stages: golden tests sweeps awq refbench ncu ncufull bench
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
 mkdir -p $OUT
 nvidia-smi -L > $OUT/box.txt; nproc >> $OUT/box.txt
-
-# 1. the reference's CUDA kernels on seeded inputs -> fixtures
-timeout 600 python tools/ref_cuda_worker.py awq-golden $OUT/awq_ref_cuda.npz > $OUT/ref_golden.log 2>&1
-timeout 600 python tools/ref_cuda_worker.py dense-s8 $OUT/dense_s8_ref_cuda.npz >> $OUT/ref_golden.log 2>&1
-cp $OUT/awq_ref_cuda.npz $OUT/dense_s8_ref_cuda.npz tests/golden/ 2>/dev/null
-
-# 2. new kernels first, bounded: a hang (grid barrier, mbarrier protocol) must not take the box
-timeout 300 python -m pytest tests/test_gpu_ops.py -q -k "rows_fused" > $OUT/pytest_fused.log 2>&1
-echo "fused rows exit $?" >> $OUT/pytest_fused.log
-if ! grep -q " passed" $OUT/pytest_fused.log || grep -q "failed\|exit 124" $OUT/pytest_fused.log; then
-  echo "row pre-phase disabled for the rest of the call" >> $OUT/pytest_fused.log
-  export CT2B200_FUSE_ROWS=0
-fi
-timeout 600 python -m pytest tests/test_gpu_awq.py -q > $OUT/pytest_awq.log 2>&1
-echo "awq tests exit $?" >> $OUT/pytest_awq.log
-if ! grep -q " passed" $OUT/pytest_awq.log || grep -q "failed\|exit 124" $OUT/pytest_awq.log; then
-  echo "AWQ decode kernel disabled for the rest of the call" >> $OUT/pytest_awq.log
-  export CT2B200_AWQ_DECODE=0
-fi
-
-# 3. the whole GPU suite
-timeout 3000 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
-echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
-
-# 4. decode step sweeps (8B, 64 steps after the 1024-token prompt)
-run() { echo "== $*" >> $OUT/sweep.log; env "$@" timeout 600 python tools/decode_once.py $B 64 int8_float16 8b int8_float16 >> $OUT/sweep.log 2>&1; }
-for B in 1 32; do
-  run CT2B200_FUSE_ROWS=0 CT2B200_L2_PREFETCH_MB=0
-  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=0
-  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=8
-  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24
-  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=48
-  run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24 CT2B200_GEMM_ROWSTEP=1
-done
-for B in 1 32; do
-  echo "== AWQ batch=$B" >> $OUT/sweep.log
-  timeout 900 python tools/decode_once.py $B 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
-done
-
-# 5. the reference's CUDA build on the same workload (bounded: G2 generated tokens)
 M8=/tmp/ct2b200_bench/llama_8b_int8_float16
 MA=/tmp/ct2b200_bench/llama_8b_awq_gemm
-for b in 1 32; do
-  timeout 900 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 16 80 >> $OUT/ref_cuda_bench.log 2>&1
-  timeout 900 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 16 80 --flash >> $OUT/ref_cuda_bench.log 2>&1
-  timeout 900 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 16 80 >> $OUT/ref_cuda_bench.log 2>&1
-  timeout 900 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 16 80 --flash >> $OUT/ref_cuda_bench.log 2>&1
-done
 
-# 6. ncu: launch list of the INT8 bsz-32 step (2 steps), full capture of the AWQ gate/up kernel and of the INT8 one
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-  --log-file $OUT/r02_launches_b32.csv python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_list.log 2>&1
-timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-  --log-file $OUT/r02_launches_b1.csv python tools/decode_once.py 1 2 int8_float16 8b int8_float16 >> $OUT/ncu_list.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 5 \
-  -o $OUT/r02_awq_decode python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
-timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_decode_kernel -c 5 \
-  -o $OUT/r02_gemm_decode python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
-tail -3 $OUT/sweep.log
+stage_golden() {   # the reference's CUDA kernels on seeded inputs -> fixtures (needs oracle/_ref_cuda)
+  timeout 600 python tools/ref_cuda_worker.py awq-golden $OUT/awq_ref_cuda.npz > $OUT/ref_golden.log 2>&1
+  timeout 600 python tools/ref_cuda_worker.py dense-s8 $OUT/dense_s8_ref_cuda.npz >> $OUT/ref_golden.log 2>&1
+  cp $OUT/awq_ref_cuda.npz $OUT/dense_s8_ref_cuda.npz tests/golden/ 2>/dev/null
+}
+
+stage_tests() {    # new kernels first, bounded: a hang (grid barrier, mbarrier protocol) must not take the box
+  timeout 300 python -m pytest tests/test_gpu_ops.py -q -x -k "rows_fused" > $OUT/pytest_fused.log 2>&1
+  echo "fused rows exit $?" >> $OUT/pytest_fused.log
+  if ! grep -q " passed" $OUT/pytest_fused.log || grep -q "failed\|exit 124" $OUT/pytest_fused.log; then
+    echo "row pre-phase disabled for the rest of the call" >> $OUT/pytest_fused.log
+    export CT2B200_FUSE_ROWS=0
+  fi
+  timeout 600 python -m pytest tests/test_gpu_awq.py -q > $OUT/pytest_awq.log 2>&1
+  echo "awq tests exit $?" >> $OUT/pytest_awq.log
+  if ! grep -q " passed" $OUT/pytest_awq.log || grep -q "failed\|exit 124" $OUT/pytest_awq.log; then
+    echo "AWQ decode kernel disabled for the rest of the call" >> $OUT/pytest_awq.log
+    export CT2B200_AWQ_DECODE=0
+  fi
+  timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
+  echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
+}
+
+run() { echo "== B=$B $*" >> $OUT/sweep.log; env "$@" timeout 300 python tools/decode_once.py $B 64 int8_float16 8b int8_float16 >> $OUT/sweep.log 2>&1; }
+stage_sweeps() {   # decode step sweeps (8B, 64 steps after the 1024-token prompt)
+  for B in 1 32; do
+    run CT2B200_FUSE_ROWS=0 CT2B200_L2_PREFETCH_MB=0
+    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=0
+    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=8
+    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24
+    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24 CT2B200_GEMM_ROWSTEP=1
+  done
+}
+stage_awq() {
+  for B in 1 32; do
+    echo "== AWQ batch=$B" >> $OUT/sweep.log
+    timeout 600 python tools/decode_once.py $B 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
+  done
+}
+
+stage_refbench() { # the reference's CUDA build on the same workload (bounded: 16 / 80 generated tokens)
+  python -c "import bench; bench.model_dir('8b','int8_float16'); bench.model_dir('8b','awq_gemm')" 2>> $OUT/ref_cuda_bench.log
+  for b in 1 32; do
+    timeout 600 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 16 80 >> $OUT/ref_cuda_bench.log 2>&1
+    timeout 600 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 16 80 --flash >> $OUT/ref_cuda_bench.log 2>&1
+    timeout 600 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 16 80 >> $OUT/ref_cuda_bench.log 2>&1
+    timeout 600 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 16 80 --flash >> $OUT/ref_cuda_bench.log 2>&1
+  done
+}
+
+stage_ncu() {      # launch lists of the INT8 step (2 steps) at bsz 32 and 1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_b32.csv python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_list.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_b1.csv python tools/decode_once.py 1 2 int8_float16 8b int8_float16 >> $OUT/ncu_list.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_awq_b1.csv python tools/decode_once.py 1 2 float16 8b awq_gemm >> $OUT/ncu_list.log 2>&1
+}
+stage_ncufull() {  # full captures of the AWQ gate/up kernel and of the INT8 one
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 5 \
+    -o $OUT/r02_awq_decode python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_decode_kernel -c 5 \
+    -o $OUT/r02_gemm_decode python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
+}
+stage_bench() {
+  timeout 1500 python bench.py > $OUT/bench.json 2> $OUT/bench.err
+  echo "bench exit $?" >> $OUT/bench.err
+}
+
+for s in "$@"; do
+  echo "=== stage $s $(date +%T)" >> $OUT/stages.log
+  stage_$s
+done
+echo "=== done $(date +%T)" >> $OUT/stages.log
+tail -3 $OUT/sweep.log 2>/dev/null; tail -3 $OUT/pytest_gpu.log 2>/dev/null

@@ -217,6 +217,65 @@ def make_score_fixture():
     print("wrote tiny_llama_int8_score_batch.json (%d cases)" % len(cases))
 
 
+SEQ2SEQ_CASES = [  # (beam, num_hypotheses, length_penalty, max_length, min_length)
+    (1, 1, 1.0, 16, 1), (2, 2, 1.0, 16, 1), (4, 2, 0.0, 16, 1), (3, 3, 0.6, 12, 1), (4, 4, 1.0, 14, 9), (2, 1, 1.0, 5, 1)]
+
+
+def seq2seq_sources(seed, cases, lo, hi):
+    rng = np.random.default_rng(seed)
+    out = []
+    for _ in range(cases):
+        batch = int(rng.integers(1, 5))
+        out.append([[int(x) for x in rng.integers(lo, hi, size=int(rng.integers(2, 10)))] for _ in range(batch)])
+    return out
+
+
+def make_seq2seq_fixture():
+    """Encoder-decoder path: outputs of the UNMODIFIED reference's Translator (oracle/_ref, CPU) on
+    (a) the reference's own golden model tests/data/models/v2/aren-transliteration-i8 (tests/translator_test.cc:53-96), copied
+        to tests/golden/ as a data fixture (binary version 2: the activation quantizer truncates), and
+    (b) a post-norm / Swish / start-from-zero-embedding model written by converters/synthetic.py (the OPUS-MT recipe in small),
+    in float32 (no activation quantization: every token must agree) and int8."""
+    from ctranslate2_b200.converters.synthetic import TransformerConfig, write_transformer_model
+    from oracle import refapi
+    src_dir = os.path.join(REF, "tests", "data", "models", "v2", "aren-transliteration-i8")
+    aren = os.path.join(OUT, "aren-transliteration-i8")
+    if os.path.isdir(aren):
+        shutil.rmtree(aren)
+    shutil.copytree(src_dir, aren)
+    for root, _, files in os.walk(aren):          # the reference tree is read-only: the copy must not be
+        os.chmod(root, 0o755)
+        for name in files:
+            os.chmod(os.path.join(root, name), 0o644)
+    post = os.path.join(OUT, "tiny_seq2seq_postnorm")
+    cfg = TransformerConfig(encoder_layers=2, decoder_layers=2, num_heads=4, d_model=64, ffn_dim=128, source_vocab=120,
+                            target_vocab=96, pre_norm=False, activation=2, start_from_zero_embedding=True)
+    write_transformer_model(post, cfg, "int8", seed=7)
+    fixture = {}
+    for name, mdir, lo, hi in (("aren", aren, 4, 51), ("postnorm", post, 3, 120)):
+        entry = {"models": {}}
+        for compute in ("float32", "int8"):
+            t = refapi.RefTranslator(mdir, compute, 2)
+            cases = []
+            for ci, (beam, nh, lp, mx, mn) in enumerate(SEQ2SEQ_CASES):
+                for srcs in seq2seq_sources(100 + ci, 4, lo, hi):
+                    res = t.translate(srcs, beam_size=beam, num_hypotheses=nh, max_length=mx, min_length=mn, length_penalty=lp)
+                    cases.append({"sources": srcs, "beam_size": beam, "num_hypotheses": nh, "length_penalty": lp,
+                                  "max_length": mx, "min_length": mn,
+                                  "hypotheses": [[h[0] for h in r] for r in res], "scores": [[h[1] for h in r] for r in res]})
+            srcs = seq2seq_sources(9, 1, lo, hi)[0] + [[lo + 1, lo + 2, lo + 3, lo + 4, lo + 5, lo + 6, lo + 7]]
+            memory, lens = t.encode(srcs)
+            d = 32 if name == "aren" else 64
+            S = max(len(r) for r in srcs)
+            memory = memory.reshape(-1)[:len(srcs) * S * d].reshape(len(srcs), S, d)
+            entry["models"][compute] = {"cases": cases, "encode_sources": srcs, "memory": memory.tolist()}
+            t.close()
+        fixture[name] = entry
+    with open(os.path.join(OUT, "seq2seq_ref.json"), "w") as f:
+        json.dump(fixture, f)
+    print("seq2seq fixture:", sum(len(m["cases"]) for e in fixture.values() for m in e["models"].values()), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--scores-only" in sys.argv:
@@ -227,6 +286,9 @@ def main():
         return
     if "--ragged-only" in sys.argv:
         make_ragged_fixture()
+        return
+    if "--seq2seq-only" in sys.argv:
+        make_seq2seq_fixture()
         return
     if "--processors-only" in sys.argv:
         make_processors_fixture()
@@ -298,6 +360,7 @@ def main():
     make_processors_fixture()
     make_ragged_fixture()
     make_score_fixture()
+    make_seq2seq_fixture()
     print("done")
 
 
