@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests sweeps awq refbench ncu ncufull bench
+# stages: golden tests shims sweeps awq refbench ncu ncufull bench translate
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -32,6 +32,16 @@ stage_tests() {    # new kernels first, bounded: a hang (grid barrier, mbarrier 
   fi
   timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
   echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
+}
+
+stage_shims() {    # the reference's own gtests with libct2b200 interposed under its ops (oracle/Makefile.shims)
+  CT2B200_SHIM_REPORT=$OUT/shim_report.txt timeout 600 oracle/_ref_cuda/ct2_tests_b200 tests/golden \
+    --gtest_filter='*CUDA*' > $OUT/ref_gtests_on_b200.txt 2>&1
+  echo "shim gtests exit $?" >> $OUT/ref_gtests_on_b200.txt
+}
+stage_translate() {   # encoder-decoder path: tests first, then the OPUS-MT-shaped bench record
+  timeout 900 python -m pytest tests/test_gpu_translator.py -q > $OUT/pytest_translator.log 2>&1
+  echo "translator tests exit $?" >> $OUT/pytest_translator.log
 }
 
 run() { echo "== B=$B $*" >> $OUT/sweep.log; env "$@" timeout 300 python tools/decode_once.py $B 64 int8_float16 8b int8_float16 >> $OUT/sweep.log 2>&1; }
