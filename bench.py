@@ -293,6 +293,58 @@ def ref_cuda_bench(name, quant, compute, batch, plen, g1=8, g2=40, flash=False, 
         return {"error": str(ex)[-300:]}
 
 
+def seq2seq_model_dir():
+    """BASELINE.json configs[1]: OPUS-MT En-De geometry (Transformer-base 6+6, d 512, 8 heads, ffn 2048, V 58101, INT8, post-norm,
+    Swish, zero first decoder embedding, source EOS — what converters/marian.py writes), random-init, written once per box."""
+    from ctranslate2_b200.converters.synthetic import OPUS_MT_BASE, write_transformer_model
+    base = os.environ.get("CT2B200_BENCH_DIR", os.path.join(tempfile.gettempdir(), "ct2b200_bench"))
+    d = os.path.join(base, "opus_mt_base_int8")
+    done = os.path.join(d, ".complete")
+    if not os.path.exists(done):
+        os.makedirs(base, exist_ok=True)
+        write_transformer_model(d, OPUS_MT_BASE, "int8", seed=1234)
+        open(done, "w").write("ok")
+    return d
+
+
+def translate_record(device_index, with_ref_cuda, batch=64, beam=4, max_len=256):
+    """configs[1]: translate_batch of 64 sentences of length U[10,50], beam 4, max_decoding_length 256, INT8
+    weights / fp16 activations: device-timed decoding steps, end-to-end target tokens/s through Translator.translate_batch with
+    HOST ids in and out, and the unmodified reference's CUDA Translator on the same GPU and sentences."""
+    import numpy as np
+    from ctranslate2_b200.translator import Translator
+    mdir = seq2seq_model_dir()
+    rng = np.random.default_rng(42)
+    srcs = [[int(x) for x in rng.integers(3, 58101, size=int(rng.integers(10, 51)))] + [2] for _ in range(batch)]
+    t = Translator(mdir, compute_type="int8_float16")
+    enc_ms, dec_ms, launches = t.bench(batch, 51, beam, 64, 3)
+    t.translate_ids(srcs, beam_size=beam, max_decoding_length=max_len, start_id=1, end_token=[2])      # warm-up at the timed shapes
+    t0 = time.perf_counter()
+    ids, lens, _ = t.translate_ids(srcs, beam_size=beam, max_decoding_length=max_len, start_id=1, end_token=[2])
+    sec = time.perf_counter() - t0
+    toks = int(lens[:, 0].sum())
+    rec = {"workload": "OPUS-MT-shaped Transformer-base INT8 (int8_float16) translate_batch, %d sentences U[10,50], beam %d, "
+                       "max_decoding_length %d (BASELINE.json configs[1])" % (batch, beam, max_len),
+           "decode_ms_per_step": round(dec_ms / 64, 4), "rows_per_step": batch * beam, "encode_ms": round(enc_ms, 3),
+           "launches_per_step": int(launches // 64), "e2e_target_tokens": toks, "e2e_seconds": round(sec, 4),
+           "e2e_tokens_per_s": round(toks / sec, 1), "h2d_bytes": int(sum(len(r) for r in srcs) * 4), "d2h_bytes": toks * 4}
+    t.close()
+    if with_ref_cuda and os.path.exists(os.path.join(ROOT, "oracle", "_ref_cuda", "libct2ref_cuda_driver.so")):
+        src_path = os.path.join(os.path.dirname(mdir), "opus_sources.json")
+        json.dump([r[:-1] for r in srcs], open(src_path, "w"))       # the reference appends </s> itself (add_source_eos)
+        cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_cuda_worker.py"), "translate-bench", mdir, "int8_float16",
+               src_path, str(beam), str(max_len)]
+        try:
+            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+            rec["ref_cuda"] = json.loads(line[-1]) if (r.returncode == 0 and line) else {"error": (r.stderr or r.stdout)[-300:]}
+            if "tokens_per_s" in rec["ref_cuda"]:
+                rec["vs_ref_cuda"] = round(rec["e2e_tokens_per_s"] / rec["ref_cuda"]["tokens_per_s"], 2)
+        except Exception as ex:
+            rec["ref_cuda"] = {"error": str(ex)[-300:]}
+    return rec
+
+
 def measure_variant(ct2, torch, name, weights, batch, plen, steps, warmup, device_index, peak, with_ref_cuda):
     """One point of the metric: device-timed decode of `steps` steps after the `plen`-token prompt."""
     awq = weights == "awq"
@@ -331,6 +383,8 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the INT8/AWQ x bsz 1/32 sub-records and ref_cuda")
     ap.add_argument("--no-tp", action="store_true", help="N > 1: skip the tensor-parallel record")
+    ap.add_argument("--side-budget", type=float, default=420.0,
+                    help="seconds the variants / translate side records may spend before they stop launching reference CUDA runs")
     ap.add_argument("--weights", default="int8", choices=["int8", "awq"],
                     help="int8 = the headline INT8 configuration; awq = the AWQ-INT4 (group 128, AWQ_GEMM layout) variant")
     ap.add_argument("--tp", action="store_true",
@@ -485,16 +539,23 @@ def main():
     except Exception as ex:  # keep the headline even if the side measurement fails
         line["roofline"] = {"error": str(ex)}
     if world == 1 and not args.no_variants:
-        # the four points BASELINE.json's metric names, each beside the reference's own CUDA build on this GPU
+        # the four points BASELINE.json's metric names, each beside the reference's own CUDA build on this GPU; the side
+        # records stop adding reference runs once the run has used its time budget (the headline above is already measured)
+        t_side = time.time()
         variants = {}
         for wname in ("int8", "awq"):
             for b in (1, 32):
                 key = "%s_b%d" % (wname, b)
                 try:
-                    variants[key] = measure_variant(ct2, torch, args.model, wname, b, P, 64, W, local_rank, peak, True)
+                    variants[key] = measure_variant(ct2, torch, args.model, wname, b, P, 64, W, local_rank, peak,
+                                                    time.time() - t_side < args.side_budget)
                 except Exception as ex:
                     variants[key] = {"error": str(ex)[-300:]}
         line["variants"] = variants
+        try:
+            line["translate"] = translate_record(local_rank, time.time() - t_side < args.side_budget)
+        except Exception as ex:
+            line["translate"] = {"error": str(ex)[-300:]}
     if awq:
         line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference",
                                 "sample": "none: the reference has no CPU implementation of the AWQ ops "

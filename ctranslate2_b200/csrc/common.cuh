@@ -162,7 +162,9 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();
-bool mark_configured(const void* kernel);     // true the first time a kernel pointer is seen
+// true the first time (kernel, tag) is seen ON THE CURRENT DEVICE: function attributes (dynamic shared memory limit, carve-out)
+// and occupancy queries are per device, and a process may open generators on several (tag 0 = carve-out, 1 = smem limit)
+bool mark_configured(const void* kernel, int tag = 0);
 
 // All kernels of the decode step ask for the maximum shared-memory carve-out: the tcgen05 GEMMs need ~200 KB of
 // shared memory per SM, and alternating between kernels with different L1/shared splits forces the SMs to drain
@@ -170,6 +172,13 @@ bool mark_configured(const void* kernel);     // true the first time a kernel po
 template <typename K>
 void prefer_max_shared(K kernel) {
   cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+}
+
+// cudaFuncAttributeMaxDynamicSharedMemorySize, once per kernel and device
+template <typename K>
+void allow_dynamic_smem(K kernel, size_t bytes) {
+  if (mark_configured(reinterpret_cast<const void*>(kernel), 1))
+    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(bytes)));
 }
 
 template <typename... KArgs, typename... Args>

@@ -728,7 +728,14 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
 }
 
 LlamaDecoder::~LlamaDecoder() {
-  if (stream_) cudaStreamDestroy(stream_);
+  cudaSetDevice(device_);
+  if (stream_) cudaStreamSynchronize(stream_);
+  for (int r = 0; r < tp_.world; ++r)                 // peer exchange buffers mapped by tp_connect
+    if (tp_.connected && r != tp_.rank && tp_.peer[r]) cudaIpcCloseMemHandle(tp_.peer[r]);
+  if (stream_) {
+    SplitKWorkspace::release(stream_);
+    cudaStreamDestroy(stream_);
+  }
 }
 
 // layers::Dense::operator() (src/layers/common.cc:339-442): INT8 / AWQ / float arms
@@ -1093,6 +1100,7 @@ void Generator::build_step_graph(int64_t batch, int64_t min_length, int num_end_
 }
 
 void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  std::lock_guard<std::mutex> lock(mu_);      // one request at a time per generator (the reference queues them per replica)
   want_scores_ = r.return_scores && out_scores != nullptr;
   LlamaDecoder& d = *decoder_;
   cudaStream_t st = d.stream();
@@ -1228,6 +1236,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
 }
 
 void Generator::forward(const int32_t* ids_h, int64_t batch, int64_t time, bool log_probs, float* logits_h) {
+  std::lock_guard<std::mutex> lock(mu_);
   LlamaDecoder& d = *decoder_;
   cudaStream_t st = d.stream();
   CT2_REQUIRE(batch > 0 && batch <= d.max_batch() && time > 0 && time <= d.max_length(), "forward_batch: shape exceeds the arena");
@@ -1256,6 +1265,7 @@ void Generator::forward(const int32_t* ids_h, int64_t batch, int64_t time, bool 
 
 void Generator::bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, int64_t warmup, float* prefill_ms,
                              float* decode_ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lock(mu_);
   LlamaDecoder& d = *decoder_;
   cudaStream_t st = d.stream();
   CT2_REQUIRE(batch <= d.max_batch() && prompt_len + warmup + steps <= d.max_length(), "bench_decode: exceeds the arena");

@@ -9,6 +9,7 @@
 #include <cstdint>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -227,6 +228,7 @@ class Generator {
   void launch_step(int64_t batch, int64_t min_length, int num_end_ids);
 
   ct2b200_generator_config cfg_;
+  std::mutex mu_;                          // generate / forward / bench_decode are serialised per generator
   std::unique_ptr<LlamaDecoder> decoder_;
   // decode-loop device state
   DeviceBuffer ids_d_, lens_d_, step_d_, forced_d_, out_d_, end_ids_d_, prompt_d_, sample_ws_, scores_d_, row_start_d_;

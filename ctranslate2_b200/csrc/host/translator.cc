@@ -224,7 +224,11 @@ Translator::Translator(const std::string& model_dir, const ct2b200_generator_con
 Translator::~Translator() {
   if (graph_) cudaGraphExecDestroy(graph_);
   if (host_pinned_) cudaFreeHost(host_pinned_);
-  if (stream_) cudaStreamDestroy(stream_);
+  if (stream_) {
+    cudaStreamSynchronize(stream_);
+    SplitKWorkspace::release(stream_);
+    cudaStreamDestroy(stream_);
+  }
 }
 
 void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t max_steps) {
@@ -436,6 +440,7 @@ BeamState make_beam_state(const TranslationRequest& r, int64_t vocab, int64_t st
 }  // namespace
 
 std::vector<TranslationHypotheses> Translator::translate(const TranslationRequest& r) {
+  std::lock_guard<std::mutex> lock(mu_);
   const int64_t B = r.batch, S = r.max_source_len, L = r.max_decoding_length;
   const int beam = r.beam_size;
   CT2_REQUIRE(B > 0 && S > 0, "translate_batch: empty batch");
@@ -553,6 +558,7 @@ std::vector<TranslationHypotheses> Translator::translate(const TranslationReques
 }
 
 void Translator::encode(const int32_t* ids_h, const int32_t* lens_h, int64_t batch, int64_t S, float* memory_h) {
+  std::lock_guard<std::mutex> lock(mu_);
   CT2_REQUIRE(batch > 0 && S > 0, "encode: empty batch");
   ensure_arena(batch, S, 1, 1);
   int32_t* hp = host_pinned_;
@@ -571,6 +577,7 @@ void Translator::encode(const int32_t* ids_h, const int32_t* lens_h, int64_t bat
 
 void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t steps, int64_t warmup, float* encode_ms,
                        float* decode_ms, int64_t* launches) {
+  std::lock_guard<std::mutex> lock(mu_);
   const int64_t L = steps + warmup;
   ensure_arena(batch, source_len, beam, L);
   std::vector<int32_t> ids(batch * source_len), lens(batch, static_cast<int32_t>(source_len));

@@ -98,6 +98,7 @@ class Translator {
   void beam_step(const BeamState& bs);
   void launch_or_capture_step(const BeamState& bs, int64_t S);
 
+  std::mutex mu_;                // translate / encode / bench are serialised per translator
   Seq2SeqConfig mc_;
   int dtype_ = CT2B200_F32, device_ = 0, weight_type_ = CT2B200_WEIGHTS_STORED, sm_count_ = 148;
   bool use_graph_ = true;

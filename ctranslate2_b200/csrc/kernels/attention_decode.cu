@@ -374,9 +374,9 @@ void launch_persistent(const void* qkv, void* kc, void* vc, const float* sn, con
   const int kind = std::is_same<T, __half>::value ? 1 : 2;
   const CUtensorMap tmk = tc::make_operand_map(kc, batch * Hkv * max_len, D, 2, kind, kTile);
   const CUtensorMap tmv = tc::make_operand_map(vc, batch * Hkv * max_len, D, 2, kind, kTile);
-  static int occupancy = 0;                       // CTAs per SM: the grid must be fully co-resident (flag waits)
-  if (occupancy == 0) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 112 * 1024));
+  allow_dynamic_smem(kernel, 112 * 1024);
+  static int occupancy = 0;                       // CTAs per SM: the grid must be fully co-resident (flag waits); the same on
+  if (occupancy == 0) {                           // every sm_100 device of a box
     int occ = 0;
     CT2_CUDA_CHECK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kernel, kThreads, 112 * 1024));
     occupancy = std::max(1, std::min(occ, 2));

@@ -406,11 +406,7 @@ void launch_mma(const void* qkv, const void* kc, const void* vc, int64_t batch, 
                 int Hkv, int64_t max_len, float scale, void* out, cudaStream_t st) {
   constexpr size_t smem = static_cast<size_t>(kQTile + 4 * kKTile) * (D + 8) * sizeof(T);
   auto kernel = attention_prefill_mma_kernel<T, D>;
-  static bool configured = false;
-  if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
-  }
+  allow_dynamic_smem(kernel, smem);
   dim3 grid(div_up(time, kQTile), H, static_cast<unsigned>(batch));
   kernel<<<grid, kThreads, smem, st>>>(static_cast<const T*>(qkv), static_cast<const T*>(kc), static_cast<const T*>(vc),
                                        time, offset, H, Hkv, max_len, scale * 1.4426950408889634f, static_cast<T*>(out));
@@ -433,11 +429,7 @@ bool launch_decode_mma_g(const void* qkv, void* kc, void* vc, const float* sn, c
 #define CT2_DEC_MMA(GV)                                                                                           \
   {                                                                                                               \
     auto kernel = attention_decode_mma_kernel<T, D, GV>;                                                          \
-    static bool configured = false;                                                                               \
-    if (!configured) {                                                                                            \
-      CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem))); \
-      configured = true;                                                                                          \
-    }                                                                                                             \
+    allow_dynamic_smem(kernel, smem);                                                                             \
     launch_pdl(kernel, grid, dim3(kThreads), smem, st, tmk, tmv, static_cast<const T*>(qkv), static_cast<T*>(kc), \
                static_cast<T*>(vc), sn, cs, lens, H, Hkv, max_len, interleave, scale_log2, static_cast<T*>(out),  \
                partials, tickets);                                                                                \

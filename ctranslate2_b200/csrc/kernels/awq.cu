@@ -455,11 +455,7 @@ template <int BN, int NB>
 void launch_awq(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, AwqParams p, cudaStream_t st) {
   using S = AwqSmem<BN, NB>;
   auto kernel = gemm_awq_tc_kernel<BN, NB>;
-  static bool configured = false;
-  if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(S::kBytes)));
-    configured = true;
-  }
+  allow_dynamic_smem(kernel, S::kBytes);
   const CUtensorMap tmx = make_operand_map(x, m, w.k, 2, 1, BN);
   const CUtensorMap tmw = make_packed_map(w.wp, w.n, w.k);
   const CUtensorMap tmw2 = make_packed_map(w2 ? w2->wp : w.wp, w.n, w.k);

@@ -372,10 +372,7 @@ int p_stages_for(int cs, int nkb) {
 
 template <int BN, int NB, int CS>
 void configure_once() {
-  static bool done = false;
-  if (done) return;
-  CT2_CUDA_CHECK(cudaFuncSetAttribute(awq_decode_kernel<BN, NB, CS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  done = true;
+  allow_dynamic_smem(awq_decode_kernel<BN, NB, CS>, 226 * 1024);
 }
 
 template <int BN, int NB, int CS>

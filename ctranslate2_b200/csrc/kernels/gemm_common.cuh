@@ -72,13 +72,32 @@ struct SplitKWorkspace {
   static constexpr size_t kAccumElems = size_t(16) << 20;  // 64 MiB of int32
   static constexpr size_t kCounters = 1 << 16;
 
-  static SplitKWorkspace& get(cudaStream_t st) {
+  static std::mutex& mutex() {
     static std::mutex mu;
+    return mu;
+  }
+  static std::map<std::pair<int, cudaStream_t>, SplitKWorkspace>& registry() {
     static std::map<std::pair<int, cudaStream_t>, SplitKWorkspace> all;
+    return all;
+  }
+  // the owner of a stream (a decoder / translator) returns its scratch when it goes away
+  static void release(cudaStream_t st) {
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess) return;
+    std::lock_guard<std::mutex> lock(mutex());
+    auto it = registry().find({dev, st});
+    if (it == registry().end()) return;
+    cudaFree(it->second.accum);
+    cudaFree(it->second.counters);
+    cudaFree(it->second.accum2);
+    registry().erase(it);
+  }
+
+  static SplitKWorkspace& get(cudaStream_t st) {
     int dev = 0;
     CT2_CUDA_CHECK(cudaGetDevice(&dev));
-    std::lock_guard<std::mutex> lock(mu);
-    auto& w = all[{dev, st}];
+    std::lock_guard<std::mutex> lock(mutex());
+    auto& w = registry()[{dev, st}];
     if (!w.accum) {
       cudaStreamCaptureStatus cs = cudaStreamCaptureStatusNone;
       cudaStreamIsCapturing(st, &cs);

@@ -313,11 +313,7 @@ struct DecPlan {
 
 template <typename T, int KIND, int BN, int NB, int CS>
 void configure_once() {
-  static bool done = false;
-  if (done) return;
-  auto kernel = gemm_decode_kernel<T, KIND, BN, NB, CS>;
-  CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-  done = true;
+  allow_dynamic_smem(gemm_decode_kernel<T, KIND, BN, NB, CS>, 226 * 1024);
 }
 
 template <typename T, int KIND, int BN, int NB, int CS>

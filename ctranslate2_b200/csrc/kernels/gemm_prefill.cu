@@ -270,11 +270,7 @@ void launch_prefill(const void* x, const void* w, const void* w2, int64_t m, int
                     cudaStream_t st) {
   constexpr int elem = Elem<KIND>::bytes;
   auto kernel = gemm_prefill_kernel<T, KIND, NB>;
-  static bool configured = false;
-  if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(kSmemBytes)));
-    configured = true;
-  }
+  allow_dynamic_smem(kernel, kSmemBytes);
   constexpr int out_cols = NB == 2 ? kBN / 2 : kBN;
   p.m = m;
   p.n = n;

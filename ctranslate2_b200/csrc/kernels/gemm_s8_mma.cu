@@ -192,11 +192,7 @@ void launch_cfg(const int8_t* A, const int8_t* B, const int8_t* B2, int64_t M, i
   constexpr int LDS = BK + 16;
   constexpr size_t smem = static_cast<size_t>(STAGES) * (BM + NB * BN) * LDS;
   auto kernel = gemm_s8_mma_kernel<T, BM, BN, BK, WARPS_M, WARPS_N, STAGES, kGlu>;
-  static bool configured = false;
-  if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-    configured = true;
-  }
+  allow_dynamic_smem(kernel, smem);
   const int tiles_m = div_up(M, BM), tiles_n = div_up(N, BN);
   const int kt_total = div_up(K, BK);
   SplitKWorkspace& w = SplitKWorkspace::get(st);

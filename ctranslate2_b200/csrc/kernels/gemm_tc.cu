@@ -543,11 +543,7 @@ void launch_tc(const void* x, const void* w, const void* w2, int64_t m, int64_t 
   using S = TcSmem<BN, NB, kSwap>;
   constexpr int elem = KindTraits<KIND>::kElem;
   auto kernel = gemm_tc_kernel<T, KIND, BN, NB, kSwap>;
-  static bool configured = false;
-  if (!configured) {
-    CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 226 * 1024));
-    configured = true;
-  }
+  allow_dynamic_smem(kernel, 226 * 1024);
   const CUtensorMap tmx = make_operand_map(x, m, k, elem, KIND, kSwap ? BN : kTileM);
   const CUtensorMap tmw = make_operand_map(w, n, k, elem, KIND, kSwap ? kTileM : BN);
   const CUtensorMap tmw2 = make_operand_map(w2 ? w2 : w, n, k, elem, KIND, kSwap ? kTileM : BN);

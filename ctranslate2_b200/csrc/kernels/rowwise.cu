@@ -4,7 +4,8 @@
 // Reference kernels these replace are cited per launcher (paths relative to the reference tree).
 #include <cstdlib>
 #include <mutex>
-#include <unordered_set>
+#include <set>
+#include <tuple>
 
 #include "../common.cuh"
 #include "row_ops.cuh"
@@ -13,11 +14,13 @@ namespace ct2b200 {
 
 std::atomic<int64_t> g_kernel_launches{0};
 
-bool mark_configured(const void* kernel) {
+bool mark_configured(const void* kernel, int tag) {
   static std::mutex mu;
-  static std::unordered_set<const void*> seen;
+  static std::set<std::tuple<const void*, int, int>> seen;
+  int dev = 0;
+  cudaGetDevice(&dev);
   std::lock_guard<std::mutex> lock(mu);
-  return seen.insert(kernel).second;
+  return seen.insert({kernel, tag, dev}).second;
 }
 
 bool pdl_enabled() {

@@ -133,3 +133,35 @@ def test_llama8b_int8_full_size_vs_reference_cuda(tmp_path):
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(report, open(os.path.join(ROOT, "gpurun_out", "llama8b_vs_ref_cuda.json"), "w"), indent=1)
     print(report)
+
+
+@gpu
+@pytest.mark.skipif(not HAVE_REF_CUDA, reason="oracle/_ref_cuda (reference CUDA build) is not on this box")
+def test_opus_mt_shape_translations_vs_reference_cuda(tmp_path):
+    """BASELINE.json configs[1] geometry (Transformer-base 6+6, d 512, 8 heads, ffn 2048, post-norm / Swish / zero first
+    embedding as converters/marian.py writes OPUS-MT; vocabulary cut to 4000 to keep the model small): beam-4 translations of
+    16 sentences against the UNMODIFIED reference's CUDA Translator on the same GPU, float32 compute on both sides."""
+    from ctranslate2_b200.converters.synthetic import TransformerConfig, write_transformer_model
+    from ctranslate2_b200.translator import Translator
+    cfg = TransformerConfig(source_vocab=4000, target_vocab=4000, pre_norm=False, activation=2, start_from_zero_embedding=True)
+    mdir = str(tmp_path / "opus_small")
+    write_transformer_model(mdir, cfg, "int8", seed=3)
+    r = np.random.default_rng(11)
+    srcs = [[int(x) for x in r.integers(3, 4000, size=int(r.integers(10, 50)))] for _ in range(16)]
+    json.dump(srcs, open(tmp_path / "src.json", "w"))
+    worker("translate", mdir, "float32", tmp_path / "src.json", 4, 2, 24, tmp_path / "ref.json")
+    ref = json.load(open(tmp_path / "ref.json"))
+    t = Translator(mdir, compute_type="float32")
+    ids, lens, scores = t.translate_ids(srcs, beam_size=4, num_hypotheses=2, max_decoding_length=24, start_id=1, end_token=[2])
+    same = 0
+    for b in range(len(srcs)):
+        mine = ids[b, 0, :lens[b, 0]].tolist()
+        same += mine == ref[b][0][0]
+        if mine == ref[b][0][0]:
+            assert abs(float(scores[b, 0]) - ref[b][0][1]) < 2e-3
+    report = {"sentences": len(srcs), "best_hypothesis_identical": same}
+    os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+    json.dump(report, open(os.path.join(ROOT, "gpurun_out", "opus_small_vs_ref_cuda.json"), "w"))
+    # random weights give near-uniform output distributions: a 1e-6 logit difference can reorder two candidates, so a
+    # sentence or two may legitimately differ; a structural error would break all of them
+    assert same >= len(srcs) - 2, report

@@ -8,6 +8,8 @@ oracle and the `ref_cuda` performance record; nothing under ctranslate2_b200/ im
     python tools/ref_cuda_worker.py forward MODEL_DIR COMPUTE IDS.npy OUT.npy [--flash]
     python tools/ref_cuda_worker.py generate MODEL_DIR COMPUTE PROMPTS.npy MAXLEN OUT.npy [--flash]
     python tools/ref_cuda_worker.py bench MODEL_DIR COMPUTE BATCH PROMPT_LEN G1 G2 [--flash]   # one JSON line
+    python tools/ref_cuda_worker.py translate MODEL_DIR COMPUTE SOURCES.json BEAM NUM_HYP MAXLEN OUT.json
+    python tools/ref_cuda_worker.py translate-bench MODEL_DIR COMPUTE SOURCES.json BEAM MAXLEN   # one JSON line
 
 The seeded inputs of `awq-golden` are rebuilt by tests/test_gpu_awq.py::make_awq from (n, k, g, seed), so the fixture
 holds only the reference's outputs.
@@ -133,6 +135,24 @@ def main():
                           "prompt_len": P, "generated": [G1, G2], "seconds": [round(t1, 4), round(t2, 4)],
                           "decode_ms_per_step": round(dec * 1e3, 4), "decode_tokens_per_s": round(B / dec, 2),
                           "e2e_tokens_per_s": round(B * G2 / t2, 2), "load_seconds": round(load_s, 1)}))
+    elif task == "translate":
+        t = refapi.RefTranslator(args[1], args[2], 0)
+        srcs = json.load(open(args[3]))
+        res = t.translate(srcs, beam_size=int(args[4]), num_hypotheses=int(args[5]), max_length=int(args[6]))
+        json.dump([[[h[0], h[1]] for h in r] for r in res], open(args[7], "w"))
+    elif task == "translate-bench":
+        t = refapi.RefTranslator(args[1], args[2], 0)
+        srcs = json.load(open(args[3]))
+        beam, maxlen = int(args[4]), int(args[5])
+        t.translate(srcs[:4], beam_size=beam, max_length=8)              # kernel loading, allocator pools
+        t.translate(srcs, beam_size=beam, max_length=maxlen)             # warm-up at the timed shapes
+        t0 = time.time()
+        res = t.translate(srcs, beam_size=beam, max_length=maxlen)
+        dt = time.time() - t0
+        toks = sum(len(r[0][0]) for r in res)
+        print(json.dumps({"impl": "reference-cuda", "compute_type": args[2], "batch": len(srcs), "beam_size": beam,
+                          "max_decoding_length": maxlen, "target_tokens": toks, "seconds": round(dt, 4),
+                          "tokens_per_s": round(toks / dt, 1)}))
     else:
         raise SystemExit("unknown task " + task)
     return 0
