@@ -3,6 +3,8 @@
 // src/decoding.cc, src/models/language_model.cc, src/generator.cc.
 #include "engine.h"
 
+#include "../kernels/gemm_decode_common.cuh"
+
 #include <cuda_profiler_api.h>
 #include <fcntl.h>
 #include <sys/mman.h>
@@ -722,7 +724,7 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   }
   grid_bar_.alloc(256);
   CT2_CUDA_CHECK(cudaMemset(grid_bar_.ptr, 0, 256));
-  if (const char* e = std::getenv("CT2B200_FUSE_ROWS")) fuse_rows_ = e[0] != '0';
+  fuse_rows_ = dec::row_prephase_enabled();            // CT2B200_FUSE_ROWS
   SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
   CT2_CUDA_CHECK(cudaDeviceSynchronize());
 }

@@ -185,7 +185,7 @@ class LlamaDecoder {
   cudaStream_t stream_ = nullptr;
   int64_t max_batch_ = 0, max_len_ = 0, chunk_rows_ = 0;
   int attn_splits_ = 1;
-  bool fuse_rows_ = true;          // CT2B200_FUSE_ROWS=0: always launch the row kernels separately
+  bool fuse_rows_ = false;         // CT2B200_FUSE_ROWS: row pre-phase of the decode GEMM instead of separate row kernels
   DeviceBuffer grid_bar_;          // grid barrier words of the row pre-phase
 
   DenseWeights embeddings_;       // int8 [V,d] + scale, or T [V,d]

@@ -509,8 +509,8 @@ bool run_m(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, co
 // fused gate/up launch only).  Measured in the decode graph of a Llama-3-8B AWQ model (tools/decode_once.py, B200): with the
 // four concurrent transform groups this kernel takes 3.93 ms / step at bsz 1 and 4.84 ms at bsz 32, the general kernel
 // 4.04 / 6.0 ms.  Both are bound by the int4 -> fp16 transform (~1 TB/s of packed weights), not by HBM.
-bool enabled() { return env_int("CT2B200_AWQ_DECODE", 1) != 0; }
-bool glu_enabled() { return env_int("CT2B200_AWQ_DECODE_GLU", env_int("CT2B200_AWQ_DECODE", 1)) != 0; }
+bool enabled() { return env_int("CT2B200_AWQ_DECODE", CT2B200_DEFAULT_AWQ_DECODE) != 0; }
+bool glu_enabled() { return env_int("CT2B200_AWQ_DECODE_GLU", env_int("CT2B200_AWQ_DECODE", CT2B200_DEFAULT_AWQ_DECODE)) != 0; }
 
 }  // namespace
 

@@ -503,6 +503,7 @@ namespace {
 // fills the pre-phase fields; false = the row shape / alignment is not covered by row_ops.cuh
 bool set_row_pre(DecParams& p, const RowPre* pre, const int8_t* A, const float* a_scale, int64_t K, int dtype) {
   if (!pre || pre->mode == 0) return true;
+  if (!row_prephase_enabled()) return false;           // the caller launches the row kernel and the GEMM separately
   bool ok = false;
   CT2_DISPATCH_DTYPE(dtype, (ok = rowop::covers<T>(K)));
   if (!ok || (reinterpret_cast<uintptr_t>(pre->x) & 15) || (reinterpret_cast<uintptr_t>(pre->gamma) & 15) ||

@@ -15,6 +15,10 @@ using namespace tc;
 
 constexpr int kMaxStages = 10;
 
+// defaults of the opt-in features (flipped to 1 once validated on hardware)
+#define CT2B200_DEFAULT_FUSE_ROWS 0
+#define CT2B200_DEFAULT_AWQ_DECODE 0
+
 struct DecParams {
   int64_t n;            // output channels (weight rows)
   int64_t m;            // activation rows
@@ -146,6 +150,11 @@ inline int env_int(const char* name, int fallback) {
   const char* e = std::getenv(name);
   return e ? std::atoi(e) : fallback;
 }
+
+// Features whose hardware validation is recorded in profiles/README.md are on by default; the others stay opt-in until a GPU
+// session has run their bit-identity tests (tools/gpu_call.sh runs them with the switch set):
+//   CT2B200_FUSE_ROWS   row pre-phase of the decode GEMM (grid barrier inside the kernel)
+inline bool row_prephase_enabled() { return env_int("CT2B200_FUSE_ROWS", CT2B200_DEFAULT_FUSE_ROWS) != 0; }
 
 // co-resident clusters of `cs` CTAs of `kernel` (cs == 1: one CTA per SM)
 template <typename K>

@@ -17,21 +17,28 @@ stage_golden() {   # the reference's CUDA kernels on seeded inputs -> fixtures (
   cp $OUT/awq_ref_cuda.npz $OUT/dense_s8_ref_cuda.npz tests/golden/ 2>/dev/null
 }
 
-stage_tests() {    # new kernels first, bounded: a hang (grid barrier, mbarrier protocol) must not take the box
-  timeout 300 python -m pytest tests/test_gpu_ops.py -q -x -k "rows_fused" > $OUT/pytest_fused.log 2>&1
+stage_tests() {    # opt-in kernels first, bounded: a hang (grid barrier, mbarrier protocol) must not take the box
+  CT2B200_FUSE_ROWS=1 timeout 300 python -m pytest tests/test_gpu_ops.py -q -x -k "rows_fused" > $OUT/pytest_fused.log 2>&1
   echo "fused rows exit $?" >> $OUT/pytest_fused.log
+  FUSE=1
   if ! grep -q " passed" $OUT/pytest_fused.log || grep -q "failed\|exit 124" $OUT/pytest_fused.log; then
-    echo "row pre-phase disabled for the rest of the call" >> $OUT/pytest_fused.log
-    export CT2B200_FUSE_ROWS=0
+    echo "row pre-phase NOT validated" >> $OUT/pytest_fused.log
+    FUSE=0
   fi
-  timeout 600 python -m pytest tests/test_gpu_awq.py -q > $OUT/pytest_awq.log 2>&1
+  CT2B200_AWQ_DECODE=1 timeout 600 python -m pytest tests/test_gpu_awq.py tests/test_gpu_ref_cuda.py -q -k "awq" > $OUT/pytest_awq.log 2>&1
   echo "awq tests exit $?" >> $OUT/pytest_awq.log
+  AWQD=1
   if ! grep -q " passed" $OUT/pytest_awq.log || grep -q "failed\|exit 124" $OUT/pytest_awq.log; then
-    echo "AWQ decode kernel disabled for the rest of the call" >> $OUT/pytest_awq.log
-    export CT2B200_AWQ_DECODE=0
+    echo "AWQ decode kernel NOT validated" >> $OUT/pytest_awq.log
+    AWQD=0
   fi
-  timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
+  echo "validated: FUSE_ROWS=$FUSE AWQ_DECODE=$AWQD" > $OUT/validated.txt
+  # the whole GPU suite with the defaults of the tree, then once more with the validated opt-ins switched on
+  timeout 1500 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
   echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
+  CT2B200_FUSE_ROWS=$FUSE CT2B200_AWQ_DECODE=$AWQD timeout 1500 python -m pytest tests/test_gpu_engine.py tests/test_gpu_ops.py tests/test_gpu_awq.py \
+    -m gpu -q > $OUT/pytest_gpu_optin.log 2>&1
+  echo "gpu suite (opt-ins on) exit $?" >> $OUT/pytest_gpu_optin.log
 }
 
 stage_shims() {    # the reference's own gtests with libct2b200 interposed under its ops (oracle/Makefile.shims)
@@ -56,8 +63,10 @@ stage_sweeps() {   # decode step sweeps (8B, 64 steps after the 1024-token promp
 }
 stage_awq() {
   for B in 1 32; do
-    echo "== AWQ batch=$B" >> $OUT/sweep.log
-    timeout 600 python tools/decode_once.py $B 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
+    for D in 0 1; do
+      echo "== AWQ batch=$B CT2B200_AWQ_DECODE=$D" >> $OUT/sweep.log
+      CT2B200_AWQ_DECODE=$D timeout 600 python tools/decode_once.py $B 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
+    done
   done
 }
 
@@ -77,11 +86,11 @@ stage_ncu() {      # launch lists of the INT8 step (2 steps) at bsz 32 and 1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/r02_launches_b1.csv python tools/decode_once.py 1 2 int8_float16 8b int8_float16 >> $OUT/ncu_list.log 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
-    --log-file $OUT/r02_launches_awq_b1.csv python tools/decode_once.py 1 2 float16 8b awq_gemm >> $OUT/ncu_list.log 2>&1
+    --log-file $OUT/r02_launches_awq_b1.csv env CT2B200_AWQ_DECODE=1 python tools/decode_once.py 1 2 float16 8b awq_gemm >> $OUT/ncu_list.log 2>&1
 }
 stage_ncufull() {  # full captures of the AWQ gate/up kernel and of the INT8 one
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 5 \
-    -o $OUT/r02_awq_decode python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
+    -o $OUT/r02_awq_decode env CT2B200_AWQ_DECODE=1 python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_decode_kernel -c 5 \
     -o $OUT/r02_gemm_decode python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
 }
