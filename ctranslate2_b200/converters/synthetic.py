@@ -435,3 +435,116 @@ def write_transformer_model(model_dir: str, cfg: TransformerConfig, quantization
     for name, n in (("source_vocabulary", cfg.source_vocab), ("target_vocabulary", cfg.target_vocab)):
         with open(os.path.join(model_dir, name + ".json"), "w") as f:
             json.dump(specials + [f"<t{i}>" for i in range(3, n)], f)
+
+
+# ---------------------------------------------------------------------------------------------
+# Whisper directories (WhisperSpec revision 3, python/ctranslate2/specs/whisper_spec.py:26-78): Conv1D front-end (weights kept
+# in float, as the reference does on CUDA, src/models/model.cc:204-223), pre-norm GELU encoder with stored positions, a
+# TransformerDecoderSpec decoder with cross-attention, stored positions, unscaled embeddings tied to the output projection.
+# ---------------------------------------------------------------------------------------------
+@dataclass
+class WhisperConfig:
+    encoder_layers: int = 32
+    decoder_layers: int = 32
+    num_heads: int = 20
+    d_model: int = 1280
+    n_mels: int = 128
+    max_source_positions: int = 1500       # frames after the stride-2 convolution (30 s of audio)
+    max_target_positions: int = 448
+    text_tokens: int = 50257               # ids below <|endoftext|>
+    languages: int = 100
+    timestamps: int = 1501
+
+
+WHISPER_LARGE_V3 = WhisperConfig()
+
+
+def whisper_vocabulary(cfg: WhisperConfig):
+    """Token order of the Whisper tokenizers: text, <|endoftext|>, <|startoftranscript|>, languages, <|translate|>,
+    <|transcribe|>, <|startoflm|>, <|startofprev|>, <|nospeech|>, <|notimestamps|>, timestamps (src/models/whisper.cc:75-80)."""
+    toks = [f"<t{i}>" for i in range(cfg.text_tokens)] + ["<|endoftext|>", "<|startoftranscript|>"]
+    toks += [f"<|l{i}|>" for i in range(cfg.languages)]
+    toks += ["<|translate|>", "<|transcribe|>", "<|startoflm|>", "<|startofprev|>", "<|nospeech|>", "<|notimestamps|>"]
+    toks += ["<|%.2f|>" % (0.02 * i) for i in range(cfg.timestamps)]
+    return toks
+
+
+def write_whisper_model(model_dir: str, cfg: WhisperConfig, quantization: str = "int8", seed: int = 1234,
+                        init_std: float = 0.15, emb_std: float = 0.02) -> None:
+    rng = np.random.default_rng(seed)
+    is_int8 = quantization.startswith("int8")
+    ftype = {"int8": "float32", "int8_float32": "float32", "int8_float16": "float16",
+             "int8_bfloat16": "bfloat16"}.get(quantization, quantization)
+    d, F = cfg.d_model, 4 * cfg.d_model
+    vocab = whisper_vocabulary(cfg)
+    V = len(vocab)
+    w = ModelWriter(model_dir, spec="WhisperSpec", revision=3)
+
+    def linear(prefix, n, k, std=init_std, bias=True):
+        wt = (rng.standard_normal((n, k), dtype=np.float32) * np.float32(std))
+        if is_int8:
+            q, scale = quantize_int8(wt)
+            w.add(prefix + "/weight", q, "int8")
+            w.add(prefix + "/weight_scale", scale, "float32")
+        else:
+            w.add(prefix + "/weight", wt, ftype)
+        if bias:
+            w.add(prefix + "/bias", (0.02 * rng.standard_normal(n)).astype(np.float32), ftype)
+
+    def norm(prefix):
+        w.add(prefix + "/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), ftype)
+        w.add(prefix + "/beta", (0.05 * rng.standard_normal(d)).astype(np.float32), ftype)
+
+    def conv(prefix, cout, cin):
+        w.add(prefix + "/weight", (rng.standard_normal((cout, cin, 3), dtype=np.float32) * np.float32(1.0 / np.sqrt(3 * cin))), ftype)
+        w.add(prefix + "/bias", (0.02 * rng.standard_normal(cout)).astype(np.float32), ftype)
+
+    w.add("encoder/num_heads", np.int16(cfg.num_heads))
+    conv("encoder/conv1", d, cfg.n_mels)
+    conv("encoder/conv2", d, d)
+    w.add("encoder/position_encodings/encodings", (0.1 * rng.standard_normal((cfg.max_source_positions, d))).astype(np.float32), ftype)
+    norm("encoder/layer_norm")
+    for l in range(cfg.encoder_layers):
+        p = f"encoder/layer_{l}"
+        norm(p + "/self_attention/layer_norm")
+        linear(p + "/self_attention/linear_0", 3 * d, d)
+        linear(p + "/self_attention/linear_1", d, d)
+        norm(p + "/ffn/layer_norm")
+        linear(p + "/ffn/linear_0", F, d)
+        linear(p + "/ffn/linear_1", d, F)
+    w.add("decoder/num_heads", np.int16(cfg.num_heads))
+    w.add("decoder/pre_norm", np.int8(1))
+    w.add("decoder/activation", np.int8(3))                  # GELU
+    w.add("decoder/alignment_layer", np.int16(-1))
+    w.add("decoder/alignment_heads", np.int16(1))
+    w.add("decoder/scale_embeddings", np.int8(0))
+    w.add("decoder/alibi", np.int8(0))
+    w.add("decoder/alibi_use_positive_positions", np.int8(0))
+    w.add("decoder/scale_alibi", np.int8(0))
+    w.add("decoder/start_from_zero_embedding", np.int8(0))
+    # small embeddings: with the projection tied to them, large ones make every step repeat its input token
+    linear("decoder/embeddings", V, d, std=emb_std, bias=False)
+    w.add("decoder/position_encodings/encodings", (0.1 * rng.standard_normal((cfg.max_target_positions, d))).astype(np.float32), ftype)
+    # a large output-norm gain gives the tied projection logits of order 1 (decisive, input-dependent tokens)
+    w.add("decoder/layer_norm/gamma", (0.25 / emb_std * (1.0 + 0.1 * rng.standard_normal(d))).astype(np.float32), ftype)
+    w.add("decoder/layer_norm/beta", (0.05 * rng.standard_normal(d)).astype(np.float32), ftype)
+    for l in range(cfg.decoder_layers):
+        p = f"decoder/layer_{l}"
+        norm(p + "/self_attention/layer_norm")
+        linear(p + "/self_attention/linear_0", 3 * d, d)
+        linear(p + "/self_attention/linear_1", d, d)
+        norm(p + "/attention/layer_norm")
+        linear(p + "/attention/linear_0", d, d)
+        linear(p + "/attention/linear_1", 2 * d, d)
+        linear(p + "/attention/linear_2", d, d)
+        norm(p + "/ffn/layer_norm")
+        linear(p + "/ffn/linear_0", F, d)
+        linear(p + "/ffn/linear_1", d, F)
+    # the output projection is the embedding matrix (converters/transformers.py WhisperLoader ties them)
+    w.alias("decoder/projection/weight", "decoder/embeddings/weight")
+    eot = cfg.text_tokens
+    config = {"suppress_ids": [1, 2, 7, 8, 9, eot + 1, eot + 2 + cfg.languages, eot + 3 + cfg.languages, eot + 4 + cfg.languages,
+                               eot + 5 + cfg.languages, eot + 6 + cfg.languages],
+              "suppress_ids_begin": [3, eot], "lang_ids": list(range(eot + 2, eot + 2 + cfg.languages)),
+              "alignment_heads": [[cfg.decoder_layers - 1, 0]]}
+    w.close(config, vocab)

@@ -551,4 +551,60 @@ CT2B200_API int ct2b200_bench_translate(ct2b200_translator* t, int64_t batch, in
   });
 }
 
+// ---- Whisper ----
+CT2B200_API int ct2b200_whisper_info(const ct2b200_translator* t, int* n_mels, int* max_frames, int* d_model, int* vocab_size) {
+  return guarded([&] {
+    CT2_REQUIRE(t, "null translator");
+    const Seq2SeqConfig& c = t->impl->config();
+    CT2_REQUIRE(c.whisper, "not a Whisper model");
+    if (n_mels) *n_mels = static_cast<int>(c.n_mels);
+    if (max_frames) *max_frames = static_cast<int>(c.max_frames);
+    if (d_model) *d_model = static_cast<int>(c.d_model);
+    if (vocab_size) *vocab_size = static_cast<int>(c.tgt_vocab);
+  });
+}
+
+CT2B200_API int ct2b200_whisper_encode(ct2b200_translator* t, const float* features, int64_t batch, int64_t frames, float* memory) {
+  return guarded([&] {
+    CT2_REQUIRE(t && features && memory, "whisper_encode: null argument");
+    t->impl->whisper_encode(features, batch, frames, memory);
+  });
+}
+
+CT2B200_API int ct2b200_whisper_generate(ct2b200_translator* t, const float* features, int64_t batch, int64_t frames,
+                             const int32_t* prompts, int64_t prompt_len, int beam_size, float patience, float length_penalty,
+                             int64_t max_length, int num_hypotheses, const int32_t* suppress_ids, int num_suppress,
+                             const int32_t* suppress_begin, int num_begin, int32_t sot_id, int32_t eot_id, int32_t no_speech_id,
+                             int32_t* out_ids, int32_t* out_lens, float* out_scores, float* no_speech) {
+  return guarded([&] {
+    CT2_REQUIRE(t && features && prompts && out_ids && out_lens && out_scores, "whisper_generate: null argument");
+    WhisperRequest r;
+    r.features = features;
+    r.batch = batch;
+    r.frames = frames;
+    r.prompts = prompts;
+    r.prompt_len = prompt_len;
+    r.beam_size = beam_size;
+    r.patience = patience;
+    r.length_penalty = length_penalty;
+    r.max_length = max_length;
+    r.num_hypotheses = num_hypotheses;
+    r.suppress_ids.assign(suppress_ids, suppress_ids + (suppress_ids ? num_suppress : 0));
+    r.suppress_ids_begin.assign(suppress_begin, suppress_begin + (suppress_begin ? num_begin : 0));
+    r.sot_id = sot_id;
+    r.eot_id = eot_id;
+    r.no_speech_id = no_speech_id;
+    const std::vector<TranslationHypotheses> res = t->impl->whisper_generate(r, no_speech);
+    for (int64_t b = 0; b < batch; ++b)
+      for (int h = 0; h < num_hypotheses; ++h) {
+        int32_t* dst = out_ids + (b * num_hypotheses + h) * max_length;
+        const bool have = h < static_cast<int>(res[b].tokens.size());
+        const int64_t len = have ? static_cast<int64_t>(res[b].tokens[h].size()) : 0;
+        for (int64_t i = 0; i < max_length; ++i) dst[i] = i < len ? res[b].tokens[h][i] : -1;
+        out_lens[b * num_hypotheses + h] = have ? static_cast<int32_t>(len) : -1;
+        out_scores[b * num_hypotheses + h] = have ? res[b].scores[h] : 0.f;
+      }
+  });
+}
+
 }  // extern "C"

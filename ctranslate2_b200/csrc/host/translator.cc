@@ -52,15 +52,29 @@ double scoped_attribute(const ModelFile& f, const std::string& scope, const std:
 Seq2SeqConfig parse_seq2seq_config(const ModelFile& f) {
   Seq2SeqConfig mc;
   if (!f.find("encoder/layer_0/self_attention/linear_0/weight") || !f.find("decoder/layer_0/attention/linear_0/weight"))
-    throw std::invalid_argument("ct2b200 Translator serves encoder-decoder Transformer models (TransformerSpec); got " + f.spec_name);
+    throw std::invalid_argument("ct2b200 Translator serves encoder-decoder Transformer models (TransformerSpec, WhisperSpec); got " +
+                                f.spec_name);
   while (f.find("encoder/layer_" + std::to_string(mc.enc_layers) + "/self_attention/linear_0/weight")) ++mc.enc_layers;
   while (f.find("decoder/layer_" + std::to_string(mc.dec_layers) + "/self_attention/linear_0/weight")) ++mc.dec_layers;
-  const HostVariable& semb = f.get(embeddings_scope(f, "encoder") + "/weight");
   const HostVariable& temb = f.get("decoder/embeddings/weight");
-  mc.src_vocab = semb.shape[0];
   mc.tgt_vocab = temb.shape[0];
-  mc.d_model = semb.shape[1];
-  CT2_REQUIRE(temb.shape[1] == mc.d_model, "encoder and decoder depths differ");
+  mc.d_model = temb.shape[1];
+  mc.whisper = f.find("encoder/conv1/weight") != nullptr;
+  if (mc.whisper) {
+    // WhisperEncoder (layers/whisper.cc:8-23): Conv1D(k 3, stride 1, pad 1) + GELU, Conv1D(k 3, stride 2, pad 1) + GELU,
+    // stored positions, pre-norm GELU layers
+    const HostVariable& c1 = f.get("encoder/conv1/weight");
+    const HostVariable& c2 = f.get("encoder/conv2/weight");
+    CT2_REQUIRE(c1.shape.size() == 3 && c1.shape[2] == 3 && c2.shape.size() == 3 && c2.shape[2] == 3, "Whisper convolutions must have kernel size 3");
+    CT2_REQUIRE(c1.shape[0] == mc.d_model && c2.shape[0] == mc.d_model && c2.shape[1] == mc.d_model, "unexpected convolution shapes");
+    mc.n_mels = c1.shape[1];
+    mc.max_frames = f.get("encoder/position_encodings/encodings").shape[0];
+    CT2_REQUIRE(f.find("decoder/position_encodings/encodings") != nullptr, "Whisper decoders store their position encodings");
+  } else {
+    const HostVariable& semb = f.get(embeddings_scope(f, "encoder") + "/weight");
+    mc.src_vocab = semb.shape[0];
+    CT2_REQUIRE(semb.shape[1] == mc.d_model, "encoder and decoder depths differ");
+  }
   // num_heads: attribute since revision 3; TransformerBase / TransformerBig imply 8 / 16 before (models/transformer.cc:62-65)
   mc.num_heads = static_cast<int>(scoped_attribute(f, "encoder", "num_heads", f.spec_name == "TransformerBig" ? 16 : 8));
   CT2_REQUIRE(static_cast<int>(scoped_attribute(f, "decoder", "num_heads", mc.num_heads)) == mc.num_heads,
@@ -71,7 +85,11 @@ Seq2SeqConfig parse_seq2seq_config(const ModelFile& f) {
   mc.dec_pre_norm = scoped_attribute(f, "decoder", "pre_norm", 1.0) != 0.0;
   mc.enc_activation = static_cast<int>(scoped_attribute(f, "encoder", "activation", 0.0));
   mc.dec_activation = static_cast<int>(scoped_attribute(f, "decoder", "activation", 0.0));
-  mc.enc_emb_scale = embeddings_scale(f, "encoder", mc.d_model);
+  if (mc.whisper) {
+    mc.enc_pre_norm = true;
+    mc.enc_activation = CT2B200_ACT_GELU;
+  }
+  mc.enc_emb_scale = mc.whisper ? 0.f : embeddings_scale(f, "encoder", mc.d_model);
   mc.dec_emb_scale = embeddings_scale(f, "decoder", mc.d_model);
   mc.ffn_dim = f.get("encoder/layer_0/ffn/linear_0/weight").shape[0];
   mc.round_before_cast = f.binary_version >= 5;
@@ -165,7 +183,44 @@ Translator::Translator(const std::string& model_dir, const ct2b200_generator_con
 
   ModelFile f(model_dir);
   mc_ = parse_seq2seq_config(f);
-  load_dense(f, embeddings_scope(f, "encoder"), enc_emb_);
+  if (mc_.whisper) {
+    // the convolutions run as im2col + float Dense: weights [d, Cin, 3] flattened to [d, Cin * 3] in T (the reference keeps
+    // them in float on CUDA too, model.cc:204-223; an int8-stored convolution is dequantized here: w = q / scale)
+    auto load_conv = [&](const std::string& prefix, DenseWeights& w) {
+      const HostVariable& wt = f.get(prefix + "/weight");
+      HostVariable flat = wt;
+      std::vector<float> deq;
+      if (wt.type_id == 1) {
+        const HostVariable& sc = f.get(prefix + "/weight_scale");
+        CT2_REQUIRE(sc.type_id == 0 && (sc.size() == wt.shape[0] || sc.size() == 1), "unexpected convolution weight_scale");
+        deq.resize(wt.size());
+        const int64_t per = wt.size() / wt.shape[0];
+        for (int64_t i = 0; i < wt.size(); ++i) {
+          float scale;
+          std::memcpy(&scale, sc.data + 4 * (sc.size() == 1 ? 0 : i / per), 4);
+          deq[i] = static_cast<float>(reinterpret_cast<const int8_t*>(wt.data)[i]) / scale;
+        }
+        flat.type_id = 0;
+        flat.data = reinterpret_cast<const uint8_t*>(deq.data());
+        flat.nbytes = deq.size() * 4;
+      }
+      const auto bytes = convert_to_dtype(flat, dtype_);
+      upload(w.weight, bytes.data(), bytes.size());
+      w.kind = DenseWeights::FLOAT16;
+      w.n = wt.shape[0];
+      w.k = wt.shape[1] * wt.shape[2];
+      mc_.weight_bytes += bytes.size();
+      if (const HostVariable* b = f.find(prefix + "/bias")) {
+        const auto bb = convert_to_dtype(*b, dtype_);
+        upload(w.bias, bb.data(), bb.size());
+      }
+    };
+    CT2_REQUIRE(dtype_ == CT2B200_F32 || (mc_.n_mels * 3) % 8 == 0, "n_mels * 3 must be a multiple of 8 for float16 / bfloat16");
+    load_conv("encoder/conv1", conv1_);
+    load_conv("encoder/conv2", conv2_);
+  } else {
+    load_dense(f, embeddings_scope(f, "encoder"), enc_emb_);
+  }
   load_dense(f, "decoder/embeddings", dec_emb_);
   load_dense(f, "decoder/projection", projection_);
   if (mc_.has_enc_final_norm) load_norm(f, "encoder/layer_norm", enc_norm_);
@@ -195,25 +250,25 @@ Translator::Translator(const std::string& model_dir, const ct2b200_generator_con
     load_dense(f, p + "ffn/linear_1", dec_[l].ffn.ff2);
   }
   // position encodings: stored table (PositionEmbedding) or sinusoidal (SinusoidalPositionEncoder, 500 positions or more)
-  num_positions_ = std::max<int64_t>(500, cfg.max_length);
-  auto load_positions = [&](const std::string& scope, DeviceBuffer& dst) {
+  auto load_positions = [&](const std::string& scope, DeviceBuffer& dst) -> int64_t {
     if (const HostVariable* e = f.find(scope + "/position_encodings/encodings")) {
       const auto bytes = convert_to_dtype(*e, dtype_);
       upload(dst, bytes.data(), bytes.size());
-      num_positions_ = std::min<int64_t>(num_positions_, e->shape[0]);
-      return;
+      return e->shape[0];
     }
-    const std::vector<float> enc = sinusoidal_positions(num_positions_, mc_.d_model);
+    const int64_t count = std::max<int64_t>(500, cfg.max_length);
+    const std::vector<float> enc = sinusoidal_positions(count, mc_.d_model);
     HostVariable v;
-    v.shape = {num_positions_, mc_.d_model};
+    v.shape = {count, mc_.d_model};
     v.type_id = 0;
     v.data = reinterpret_cast<const uint8_t*>(enc.data());
     v.nbytes = enc.size() * 4;
     const auto bytes = convert_to_dtype(v, dtype_);
     upload(dst, bytes.data(), bytes.size());
+    return count;
   };
-  load_positions("encoder", enc_pos_);
-  load_positions("decoder", dec_pos_);
+  enc_positions_ = load_positions("encoder", enc_pos_);
+  dec_positions_ = load_positions("decoder", dec_pos_);
   end_ids_d_.alloc(64 * sizeof(int32_t));
   counters_.alloc(64);
   CT2_CUDA_CHECK(cudaMemset(counters_.ptr, 0, 64));
@@ -232,7 +287,8 @@ Translator::~Translator() {
 }
 
 void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t max_steps) {
-  CT2_REQUIRE(src_len <= num_positions_ && max_steps <= num_positions_, "sequence longer than the position encodings");
+  CT2_REQUIRE(src_len <= enc_positions_ && max_steps <= dec_positions_,
+              "No position encodings are defined for positions this far (common.cc:157-161)");
   if (batch <= cap_batch_ && src_len <= cap_src_ && beam <= cap_beam_ && max_steps <= cap_steps_) return;
   CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
   if (graph_) {
@@ -282,7 +338,14 @@ void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t 
   hyp_tokens_.alloc(B * maxh * L * 4);
   hyp_len_.alloc(B * maxh * 4);
   hyp_score_.alloc(B * maxh * 4);
-  const size_t need = static_cast<size_t>(B) * S + B + static_cast<size_t>(B) * maxh * (L + 2) + B + 256;
+  if (mc_.whisper) {
+    const int64_t frames = 2 * S;                        // conv2 halves the frames
+    features_.alloc(B * mc_.n_mels * frames * 4);
+    cols_.alloc(std::max(B * frames * mc_.n_mels * 3, B * S * d * 3) * es);
+    conv_out_.alloc(B * frames * d * es);
+  }
+  const size_t need = static_cast<size_t>(B) * S + B + static_cast<size_t>(B) * maxh * (L + 2) + B + 256 +
+                      static_cast<size_t>(N) * 16 + 8192;
   if (need > host_pinned_elems_) {
     if (host_pinned_) cudaFreeHost(host_pinned_);
     CT2_CUDA_CHECK(cudaMallocHost(&host_pinned_, need * sizeof(int32_t)));
@@ -319,16 +382,22 @@ void Translator::post_norm(const NormWeights& n, void* x, int64_t rows) {
 
 // TransformerEncoder::operator() (transformer.cc:427-471); rows = batch * S, padded positions are computed and ignored
 void Translator::run_encoder(int64_t batch, int64_t S) {
+  launch_embed_pos(enc_emb_.weight.ptr, enc_emb_.kind == DenseWeights::INT8 ? enc_emb_.scale.as<float>() : nullptr,
+                   src_ids_.as<int32_t>(), batch * S, mc_.d_model, mc_.enc_emb_scale, enc_pos_.ptr, S, nullptr, false, x_.ptr,
+                   dtype_, stream_);
+  run_encoder_layers(batch, S, src_lens_.as<int32_t>());
+}
+
+// the layer stack on x_ -> memory_ (lens_d = null: every position is valid)
+void Translator::run_encoder_layers(int64_t batch, int64_t S, const int32_t* lens_d) {
   const int64_t rows = batch * S, d = mc_.d_model;
   const float scale = 1.f / std::sqrt(static_cast<float>(mc_.head_dim));
   const bool pre = mc_.enc_pre_norm;
-  launch_embed_pos(enc_emb_.weight.ptr, enc_emb_.kind == DenseWeights::INT8 ? enc_emb_.scale.as<float>() : nullptr,
-                   src_ids_.as<int32_t>(), rows, d, mc_.enc_emb_scale, enc_pos_.ptr, S, nullptr, false, x_.ptr, dtype_, stream_);
   for (int l = 0; l < mc_.enc_layers; ++l) {
     EncoderLayerWeights& w = enc_[l];
     dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr);
-    launch_attention_encoder(qkv_.ptr, src_lens_.as<int32_t>(), batch, static_cast<int>(S), mc_.num_heads, mc_.head_dim, scale,
-                             ctx_.ptr, dtype_, stream_);
+    launch_attention_encoder(qkv_.ptr, lens_d, batch, static_cast<int>(S), mc_.num_heads, mc_.head_dim, scale, ctx_.ptr, dtype_,
+                             stream_);
     dense(w.self.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
     if (!pre) post_norm(w.self.norm, x_.ptr, rows);
     dense(w.ffn.ff1, pre ? &w.ffn.norm : nullptr, x_.ptr, rows, nullptr, mc_.enc_activation, h_.ptr);
@@ -379,9 +448,7 @@ void Translator::decoder_step(int64_t rows, int beam, int64_t batch, int64_t S) 
 
 // log-probabilities + cumulative scores, TopK of 2 * beam candidates per entry, bookkeeping (decoding.cc:536-700)
 void Translator::beam_step(const BeamState& bs) {
-  const int64_t rows = static_cast<int64_t>(bs.batch) * bs.beam;
-  launch_beam_logprobs(logits_.ptr, rows, bs.vocab, cum_.ptr, bs.step, bs.min_length,
-                       bs.end_ids, bs.num_end, dtype_, stream_);
+  launch_beam_logprobs(logits_.ptr, cum_.ptr, bs, dtype_, stream_);
   launch_topk(logits_.ptr, bs.batch, static_cast<int64_t>(bs.beam) * bs.vocab, 2 * bs.beam, cand_scores_.ptr,
               cand_ids_.as<int32_t>(), dtype_, stream_);
   launch_beam_update(bs, cand_scores_.ptr, cand_ids_.as<int32_t>(), cum_.ptr, dtype_, stream_);
@@ -419,28 +486,115 @@ void Translator::launch_or_capture_step(const BeamState& bs, int64_t S) {
 }
 
 // =============================================================================================
-// Translator::translate_batch
+// the search (shared by translate_batch and Whisper::generate)
 // =============================================================================================
-namespace {
-BeamState make_beam_state(const TranslationRequest& r, int64_t vocab, int64_t stride, int64_t max_hyp) {
+BeamState Translator::beam_state(int64_t batch, int beam, int64_t max_steps, int64_t min_length, float patience,
+                                 float length_penalty, int num_hypotheses, int num_end) {
   BeamState bs;
-  bs.batch = static_cast<int>(r.batch);
-  bs.beam = r.beam_size;
-  bs.vocab = static_cast<int>(vocab);
-  bs.stride = static_cast<int>(stride);
-  bs.max_steps = static_cast<int>(r.max_decoding_length);
-  bs.max_hyp = static_cast<int>(max_hyp);
-  bs.min_length = static_cast<int>(r.min_decoding_length);
-  bs.max_candidates = std::max(1, static_cast<int>(std::lround(r.beam_size * r.patience)));   // decoding.cc:415-418
-  bs.num_hypotheses = r.num_hypotheses;
-  bs.early_exit = r.length_penalty == 0.f ? 1 : 0;
-  bs.num_end = static_cast<int>(r.end_ids.size());
+  bs.batch = static_cast<int>(batch);
+  bs.beam = beam;
+  bs.vocab = static_cast<int>(mc_.tgt_vocab);
+  bs.stride = static_cast<int>(cap_steps_);
+  bs.max_steps = static_cast<int>(max_steps);
+  bs.max_hyp = static_cast<int>(3 * cap_beam_);
+  bs.min_length = static_cast<int>(min_length);
+  bs.max_candidates = std::max(1, static_cast<int>(std::lround(beam * patience)));   // decoding.cc:415-418
+  bs.num_hypotheses = num_hypotheses;
+  bs.early_exit = length_penalty == 0.f ? 1 : 0;
+  bs.num_end = num_end;
+  bs.end_ids = end_ids_d_.as<int32_t>();
+  bs.step = counters_.as<int32_t>();
+  bs.ticket = bs.step + 1;
+  bs.num_finished = bs.step + 2;
+  bs.finished = finished_.as<int32_t>();
+  bs.top_done = top_done_.as<int32_t>();
+  bs.num_hyp = num_hyp_.as<int32_t>();
+  bs.alive = alive_.as<int32_t>();
+  bs.anc = anc_.as<int32_t>();
+  bs.next_ids = ids_.as<int32_t>();
+  bs.hyp_tokens = hyp_tokens_.as<int32_t>();
+  bs.hyp_len = hyp_len_.as<int32_t>();
+  bs.hyp_score = hyp_score_.as<float>();
   return bs;
 }
-}  // namespace
 
+void Translator::reset_search(const BeamState& bs, int32_t start_id) {
+  CT2_CUDA_CHECK(cudaMemsetAsync(counters_.ptr, 0, 64, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(finished_.ptr, 0, bs.batch * 4, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(top_done_.ptr, 0, bs.batch * 4, stream_));
+  CT2_CUDA_CHECK(cudaMemsetAsync(num_hyp_.ptr, 0, bs.batch * 4, stream_));
+  launch_beam_init(cum_.ptr, ids_.as<int32_t>(), static_cast<int64_t>(bs.batch) * bs.beam, bs.beam, start_id, dtype_, stream_);
+}
+
+// the decoding loop: one captured step per position; the host only polls the "finished entries" counter
+void Translator::run_search(const BeamState& bs, int64_t S, int64_t first_check) {
+  // everything the captured step bakes in (kernel arguments are values)
+  std::vector<int64_t> key = {bs.batch, bs.beam, S, bs.stride, bs.max_steps, bs.min_length, bs.max_hyp, bs.max_candidates,
+                              bs.num_hypotheses, bs.early_exit, bs.num_end, bs.start_step, bs.include_eos, bs.num_disable,
+                              bs.num_begin};
+  if (key != graph_key_) {
+    if (graph_) {
+      cudaGraphExecDestroy(graph_);
+      graph_ = nullptr;
+    }
+    graph_key_ = key;
+  }
+  const char* poll_env = std::getenv("CT2B200_EOS_POLL");
+  const int64_t poll = std::max<int64_t>(1, poll_env ? std::atoll(poll_env) : 4);
+  int32_t* hfin = host_pinned_ + host_pinned_elems_ - 16;
+  for (int64_t s = 0; s < bs.max_steps; ++s) {
+    launch_or_capture_step(bs, S);
+    if (s + 1 == bs.max_steps) break;
+    if (s >= first_check && (s - first_check) % poll == poll - 1) {
+      CT2_CUDA_CHECK(cudaMemcpyAsync(hfin, bs.num_finished, 4, cudaMemcpyDeviceToHost, stream_));
+      CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+      if (*hfin >= bs.batch) break;
+    }
+  }
+}
+
+// finalize_result (decoding.cc:189-254) on the host: normalise, sort, keep num_hypotheses, strip `strip_ids` from the tail
+std::vector<TranslationHypotheses> Translator::collect(const BeamState& bs, float length_penalty, int num_hypotheses,
+                                                       const std::vector<int32_t>& strip_ids) {
+  const int64_t B = bs.batch, maxh = bs.max_hyp, stride = bs.stride;
+  int32_t* h_nh = host_pinned_;
+  int32_t* h_len = h_nh + B;
+  float* h_score = reinterpret_cast<float*>(h_len + B * maxh);
+  int32_t* h_tok = h_len + 2 * B * maxh;
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_nh, num_hyp_.ptr, B * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_len, hyp_len_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_score, hyp_score_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(h_tok, hyp_tokens_.ptr, B * maxh * stride * 4, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  std::vector<TranslationHypotheses> out(B);
+  for (int64_t b = 0; b < B; ++b) {
+    const int nh = h_nh[b];
+    std::vector<float> sc(nh);
+    for (int j = 0; j < nh; ++j) {
+      const float len = static_cast<float>(h_len[b * maxh + j]);
+      sc[j] = h_score[b * maxh + j] / std::pow(len, length_penalty);
+    }
+    std::vector<int> order(nh);
+    std::iota(order.begin(), order.end(), 0);
+    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return sc[a] > sc[c]; });
+    if (static_cast<int>(order.size()) > num_hypotheses) order.resize(num_hypotheses);
+    for (int j : order) {
+      const int32_t* t = h_tok + (b * maxh + j) * stride;
+      std::vector<int32_t> toks(t, t + h_len[b * maxh + j]);
+      while (!toks.empty() && std::find(strip_ids.begin(), strip_ids.end(), toks.back()) != strip_ids.end()) toks.pop_back();
+      out[b].tokens.push_back(std::move(toks));
+      out[b].scores.push_back(sc[j]);
+    }
+  }
+  return out;
+}
+
+// =============================================================================================
+// Translator::translate_batch
+// =============================================================================================
 std::vector<TranslationHypotheses> Translator::translate(const TranslationRequest& r) {
   std::lock_guard<std::mutex> lock(mu_);
+  CT2_REQUIRE(!mc_.whisper, "this is a Whisper model: use whisper_generate");
   const int64_t B = r.batch, S = r.max_source_len, L = r.max_decoding_length;
   const int beam = r.beam_size;
   CT2_REQUIRE(B > 0 && S > 0, "translate_batch: empty batch");
@@ -458,7 +612,6 @@ std::vector<TranslationHypotheses> Translator::translate(const TranslationReques
     }
   }
   ensure_arena(B, S, beam, L);
-  const int64_t N = B * beam, stride = cap_steps_, maxh = 3 * cap_beam_;
 
   // ---- inputs ----
   int32_t* hp = host_pinned_;
@@ -477,88 +630,17 @@ std::vector<TranslationHypotheses> Translator::translate(const TranslationReques
   run_encoder(B, S);
   project_memory(B, S);
 
-  // ---- beam search ----
-  BeamState bs = make_beam_state(r, mc_.tgt_vocab, stride, maxh);
-  bs.end_ids = end_ids_d_.as<int32_t>();
-  bs.step = counters_.as<int32_t>();
-  bs.ticket = bs.step + 1;
-  bs.num_finished = bs.step + 2;
-  bs.finished = finished_.as<int32_t>();
-  bs.top_done = top_done_.as<int32_t>();
-  bs.num_hyp = num_hyp_.as<int32_t>();
-  bs.alive = alive_.as<int32_t>();
-  bs.anc = anc_.as<int32_t>();
-  bs.next_ids = ids_.as<int32_t>();
-  bs.hyp_tokens = hyp_tokens_.as<int32_t>();
-  bs.hyp_len = hyp_len_.as<int32_t>();
-  bs.hyp_score = hyp_score_.as<float>();
-  // everything the captured step bakes in (kernel arguments are values)
-  std::vector<int64_t> key = {B, beam, S, stride, L, r.min_decoding_length, maxh, bs.max_candidates, bs.num_hypotheses,
-                              bs.early_exit, bs.num_end, N};
-  if (key != graph_key_) {
-    if (graph_) {
-      cudaGraphExecDestroy(graph_);
-      graph_ = nullptr;
-    }
-    graph_key_ = key;
-  }
-  CT2_CUDA_CHECK(cudaMemsetAsync(counters_.ptr, 0, 64, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(finished_.ptr, 0, B * 4, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(top_done_.ptr, 0, B * 4, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(num_hyp_.ptr, 0, B * 4, stream_));
-  launch_beam_init(cum_.ptr, ids_.as<int32_t>(), N, beam, r.start_id, dtype_, stream_);
-
-  const char* poll_env = std::getenv("CT2B200_EOS_POLL");
-  const int64_t poll = std::max<int64_t>(1, poll_env ? std::atoll(poll_env) : 4);
-  // the earliest step at which an entry can be complete: min_decoding_length (end tokens are masked before)
-  const int64_t first_check = std::max<int64_t>(0, r.min_decoding_length);
-  int32_t* hfin = hend + 64;
-  for (int64_t s = 0; s < L; ++s) {
-    launch_or_capture_step(bs, S);
-    if (s + 1 == L) break;
-    if (s >= first_check && (s - first_check) % poll == poll - 1) {
-      CT2_CUDA_CHECK(cudaMemcpyAsync(hfin, bs.num_finished, 4, cudaMemcpyDeviceToHost, stream_));
-      CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
-      if (*hfin >= B) break;
-    }
-  }
-
-  // ---- results: finalize_result (decoding.cc:189-254) on the host ----
-  int32_t* h_nh = hfin + 64;
-  int32_t* h_len = h_nh + B;
-  float* h_score = reinterpret_cast<float*>(h_len + B * maxh);
-  int32_t* h_tok = h_len + 2 * B * maxh;
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_nh, num_hyp_.ptr, B * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_len, hyp_len_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_score, hyp_score_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_tok, hyp_tokens_.ptr, B * maxh * stride * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
-  std::vector<TranslationHypotheses> out(B);
-  for (int64_t b = 0; b < B; ++b) {
-    const int nh = h_nh[b];
-    std::vector<float> sc(nh);
-    for (int j = 0; j < nh; ++j) {
-      const float len = static_cast<float>(h_len[b * maxh + j]);
-      sc[j] = h_score[b * maxh + j] / std::pow(len, r.length_penalty);
-    }
-    std::vector<int> order(nh);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return sc[a] > sc[c]; });
-    if (static_cast<int>(order.size()) > r.num_hypotheses) order.resize(r.num_hypotheses);
-    for (int j : order) {
-      const int32_t* t = h_tok + (b * maxh + j) * stride;
-      std::vector<int32_t> toks(t, t + h_len[b * maxh + j]);
-      if (!r.return_end_token)
-        while (!toks.empty() && std::find(r.end_ids.begin(), r.end_ids.end(), toks.back()) != r.end_ids.end()) toks.pop_back();
-      out[b].tokens.push_back(std::move(toks));
-      out[b].scores.push_back(sc[j]);
-    }
-  }
-  return out;
+  // ---- beam search: the earliest step at which an entry can be complete is min_decoding_length ----
+  BeamState bs = beam_state(B, beam, L, r.min_decoding_length, r.patience, r.length_penalty, r.num_hypotheses,
+                            static_cast<int>(r.end_ids.size()));
+  reset_search(bs, r.start_id);
+  run_search(bs, S, std::max<int64_t>(0, r.min_decoding_length));
+  return collect(bs, r.length_penalty, r.num_hypotheses, r.return_end_token ? std::vector<int32_t>{} : r.end_ids);
 }
 
 void Translator::encode(const int32_t* ids_h, const int32_t* lens_h, int64_t batch, int64_t S, float* memory_h) {
   std::lock_guard<std::mutex> lock(mu_);
+  CT2_REQUIRE(!mc_.whisper, "this is a Whisper model: use whisper_encode");
   CT2_REQUIRE(batch > 0 && S > 0, "encode: empty batch");
   ensure_arena(batch, S, 1, 1);
   int32_t* hp = host_pinned_;
@@ -578,36 +660,15 @@ void Translator::encode(const int32_t* ids_h, const int32_t* lens_h, int64_t bat
 void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t steps, int64_t warmup, float* encode_ms,
                        float* decode_ms, int64_t* launches) {
   std::lock_guard<std::mutex> lock(mu_);
+  CT2_REQUIRE(!mc_.whisper, "bench_translate serves Translator models");
   const int64_t L = steps + warmup;
   ensure_arena(batch, source_len, beam, L);
   std::vector<int32_t> ids(batch * source_len), lens(batch, static_cast<int32_t>(source_len));
   for (size_t i = 0; i < ids.size(); ++i) ids[i] = static_cast<int32_t>((7919ull * i + 3) % mc_.src_vocab);
   CT2_CUDA_CHECK(cudaMemcpy(src_ids_.ptr, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
   CT2_CUDA_CHECK(cudaMemcpy(src_lens_.ptr, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice));
-  TranslationRequest r;
-  r.batch = batch;
-  r.max_source_len = source_len;
-  r.beam_size = beam;
-  r.max_decoding_length = L;
-  r.min_decoding_length = 0;
-  r.num_hypotheses = 1;
-  const int64_t stride = cap_steps_, maxh = 3 * cap_beam_, N = batch * beam;
-  BeamState bs = make_beam_state(r, mc_.tgt_vocab, stride, maxh);
-  bs.end_ids = end_ids_d_.as<int32_t>();
-  bs.step = counters_.as<int32_t>();
-  bs.ticket = bs.step + 1;
-  bs.num_finished = bs.step + 2;
-  bs.finished = finished_.as<int32_t>();
-  bs.top_done = top_done_.as<int32_t>();
-  bs.num_hyp = num_hyp_.as<int32_t>();
-  bs.alive = alive_.as<int32_t>();
-  bs.anc = anc_.as<int32_t>();
-  bs.next_ids = ids_.as<int32_t>();
-  bs.hyp_tokens = hyp_tokens_.as<int32_t>();
-  bs.hyp_len = hyp_len_.as<int32_t>();
-  bs.hyp_score = hyp_score_.as<float>();
-  std::vector<int64_t> key = {batch, beam, source_len, stride, L, 0, maxh, bs.max_candidates, bs.num_hypotheses, bs.early_exit,
-                              bs.num_end, N};
+  BeamState bs = beam_state(batch, beam, L, 0, 1.f, 1.f, 1, 0);      // no end token: nothing finishes before the last step
+  std::vector<int64_t> key = {-1, batch, beam, source_len, bs.stride, L};
   if (key != graph_key_) {
     if (graph_) {
       cudaGraphExecDestroy(graph_);
@@ -627,11 +688,7 @@ void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t step
   run_encoder(batch, source_len);
   project_memory(batch, source_len);
   cudaEventRecord(e1, stream_);
-  CT2_CUDA_CHECK(cudaMemsetAsync(counters_.ptr, 0, 64, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(finished_.ptr, 0, batch * 4, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(top_done_.ptr, 0, batch * 4, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(num_hyp_.ptr, 0, batch * 4, stream_));
-  launch_beam_init(cum_.ptr, ids_.as<int32_t>(), N, beam, 1, dtype_, stream_);
+  reset_search(bs, 1);
   for (int64_t s = 0; s < warmup; ++s) launch_or_capture_step(bs, source_len);
   CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
   const int64_t l0 = g_kernel_launches.load();
@@ -648,6 +705,124 @@ void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t step
   cudaEventDestroy(e1);
   cudaEventDestroy(e2);
   cudaEventDestroy(e3);
+}
+
+// =============================================================================================
+// Whisper (src/models/whisper.cc, src/layers/whisper.cc)
+// =============================================================================================
+// WhisperEncoder::operator(): conv1 + GELU, conv2 (stride 2) + GELU as im2col + float Dense (the GEMM output is already the
+// transposed [batch, frames / 2, d] layout), stored positions, pre-norm GELU layers, LayerNorm
+void Translator::run_whisper_encoder(int64_t batch, int64_t frames) {
+  const int64_t d = mc_.d_model, S = (frames + 2 - 3) / 2 + 1;
+  launch_im2col(features_.ptr, true, batch, mc_.n_mels, frames, frames, 3, 1, 1, true, cols_.ptr, dtype_, stream_);
+  gemm_float(cols_.ptr, conv1_.weight.ptr, conv1_.bias.ptr, nullptr, CT2B200_ACT_GELU, batch * frames, d, mc_.n_mels * 3,
+             conv_out_.ptr, dtype_, stream_);
+  launch_im2col(conv_out_.ptr, false, batch, d, frames, S, 3, 2, 1, false, cols_.ptr, dtype_, stream_);
+  gemm_float(cols_.ptr, conv2_.weight.ptr, conv2_.bias.ptr, nullptr, CT2B200_ACT_GELU, batch * S, d, d * 3, x_.ptr, dtype_, stream_);
+  launch_add_positions(x_.ptr, enc_pos_.ptr, batch * S, S, d, dtype_, stream_);
+  run_encoder_layers(batch, S, nullptr);
+}
+
+void Translator::whisper_encode(const float* features_h, int64_t batch, int64_t frames, float* memory_h) {
+  std::lock_guard<std::mutex> lock(mu_);
+  CT2_REQUIRE(mc_.whisper, "whisper_encode needs a Whisper model");
+  const int64_t S = (frames + 2 - 3) / 2 + 1;
+  CT2_REQUIRE(batch > 0 && frames >= 2 && S <= mc_.max_frames, "Invalid input features shape: too many frames for the encoder");
+  ensure_arena(batch, S, 1, 1);
+  CT2_CUDA_CHECK(cudaMemcpyAsync(features_.ptr, features_h, batch * mc_.n_mels * frames * 4, cudaMemcpyHostToDevice, stream_));
+  run_whisper_encoder(batch, frames);
+  DeviceBuffer f32(static_cast<size_t>(batch) * S * mc_.d_model * 4);
+  launch_convert_to_f32(memory_.ptr, batch * S * mc_.d_model, f32.as<float>(), dtype_, stream_);
+  CT2_CUDA_CHECK(cudaMemcpyAsync(memory_h, f32.ptr, f32.bytes, cudaMemcpyDeviceToHost, stream_));
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+}
+
+std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperRequest& r, float* no_speech_h) {
+  std::lock_guard<std::mutex> lock(mu_);
+  CT2_REQUIRE(mc_.whisper, "whisper_generate needs a Whisper model");
+  const int64_t B = r.batch, P = r.prompt_len, frames = r.frames;
+  const int64_t S = (frames + 2 - 3) / 2 + 1;
+  const int beam = r.beam_size;
+  CT2_REQUIRE(B > 0 && frames >= 2 && S <= mc_.max_frames, "Invalid input features shape: too many frames for the encoder");
+  CT2_REQUIRE(beam >= 1 && beam <= 32, "beam_size must be in [1, 32]");
+  CT2_REQUIRE(r.num_hypotheses >= 1 && r.num_hypotheses <= beam, "num_hypotheses must be in [1, beam_size]");
+  CT2_REQUIRE(r.patience > 0.f && r.patience <= 2.f, "patience must be in (0, 2]");
+  CT2_REQUIRE(r.suppress_ids.size() + r.suppress_ids_begin.size() <= 4096, "too many suppressed tokens");
+  // check_prompts (whisper.cc:168-197): <|startoftranscript|> at the same position in every prompt; this engine also requires
+  // the prompt to END with the task tokens (no text after them) and does not implement the timestamp rules, so the last
+  // task token must be <|notimestamps|> — the token right below the timestamps in the vocabulary
+  CT2_REQUIRE(P >= 2 && P <= 16, "the prompt must hold <|startoftranscript|> and the task tokens (2 to 16 tokens)");
+  int64_t sot_index = -1;
+  for (int64_t b = 0; b < B; ++b) {
+    int64_t idx = -1;
+    for (int64_t t = 0; t < P; ++t) {
+      const int32_t id = r.prompts[b * P + t];
+      CT2_REQUIRE(id >= 0 && id < mc_.tgt_vocab, "prompt id out of range");
+      if (id == r.sot_id && idx < 0) idx = t;
+    }
+    CT2_REQUIRE(idx >= 0, "<|startoftranscript|> token was not found in the prompt");
+    CT2_REQUIRE(sot_index < 0 || idx == sot_index, "<|startoftranscript|> must be at the same position in all prompts");
+    sot_index = idx;
+  }
+  const int64_t start_step = P - 1;
+  const int64_t steps = std::min<int64_t>(r.max_length / 2, r.max_length - start_step);      // whisper.cc:299
+  CT2_REQUIRE(steps >= 1, "max_length is too small for the prompt");
+  ensure_arena(B, S, beam, start_step + steps);
+  const int64_t N = B * beam;
+
+  // ---- inputs ----
+  CT2_CUDA_CHECK(cudaMemcpyAsync(features_.ptr, r.features, B * mc_.n_mels * frames * 4, cudaMemcpyHostToDevice, stream_));
+  int32_t* hp = host_pinned_;
+  for (int64_t t = 0; t < P; ++t)                      // forced inputs [P, N]: prompt token t of the row's batch entry
+    for (int64_t n = 0; n < N; ++n) hp[t * N + n] = r.prompts[(n / beam) * P + t];
+  int32_t* hs = hp + P * N;
+  for (size_t i = 0; i < r.suppress_ids.size(); ++i) hs[i] = r.suppress_ids[i];
+  for (size_t i = 0; i < r.suppress_ids_begin.size(); ++i) hs[r.suppress_ids.size() + i] = r.suppress_ids_begin[i];
+  hs[r.suppress_ids.size() + r.suppress_ids_begin.size()] = r.eot_id;
+  const size_t nsup = r.suppress_ids.size() + r.suppress_ids_begin.size();
+  forced_d_.alloc(P * N * 4);
+  suppress_d_.alloc((nsup + 1) * 4);
+  CT2_CUDA_CHECK(cudaMemcpyAsync(forced_d_.ptr, hp, P * N * 4, cudaMemcpyHostToDevice, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(suppress_d_.ptr, hs, (nsup + 1) * 4, cudaMemcpyHostToDevice, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(end_ids_d_.ptr, suppress_d_.as<int32_t>() + nsup, 4, cudaMemcpyDeviceToDevice, stream_));
+  std::vector<int32_t> lens(B, static_cast<int32_t>(S));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(src_lens_.ptr, lens.data(), B * 4, cudaMemcpyHostToDevice, stream_));
+  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));      // `lens` and the pinned staging are reused below
+
+  // ---- encoder + memory projections ----
+  run_whisper_encoder(B, frames);
+  project_memory(B, S);
+
+  // ---- prompt: WhisperDecoder::forward_prompt on prompt[:-1], one position per step, no search ----
+  BeamState bs = beam_state(B, beam, steps, 0, r.patience, r.length_penalty, r.num_hypotheses, 1);
+  bs.start_step = static_cast<int>(start_step);
+  bs.include_eos = 0;                                  // whisper.cc:309
+  bs.num_disable = static_cast<int>(r.suppress_ids.size());
+  bs.num_begin = static_cast<int>(r.suppress_ids_begin.size());
+  bs.disable_ids = suppress_d_.as<int32_t>();
+  bs.disable_begin = suppress_d_.as<int32_t>() + r.suppress_ids.size();
+  reset_search(bs, r.prompts[0]);
+  CT2_CUDA_CHECK(cudaMemcpyAsync(ids_.ptr, forced_d_.ptr, N * 4, cudaMemcpyDeviceToDevice, stream_));
+  no_speech_d_.alloc(B * 4);
+  for (int64_t t = 0; t < start_step; ++t) {
+    decoder_step(N, beam, B, S);
+    if (no_speech_h && t == sot_index) {
+      CT2_REQUIRE(r.no_speech_id >= 0, "return_no_speech_prob needs the id of <|nospeech|>");
+      launch_token_prob(logits_.ptr, B, mc_.tgt_vocab, static_cast<int64_t>(beam) * mc_.tgt_vocab, r.no_speech_id,
+                        no_speech_d_.as<float>(), dtype_, stream_);
+    }
+    launch_beam_force(bs, forced_d_.as<int32_t>() + (t + 1) * N, stream_);
+  }
+  CT2_REQUIRE(!no_speech_h || sot_index < start_step, "return_no_speech_prob with <|startoftranscript|> as the last prompt "
+                                                      "token is not supported");
+
+  // ---- search ----
+  run_search(bs, S, 0);
+  if (no_speech_h) {
+    CT2_CUDA_CHECK(cudaMemcpyAsync(no_speech_h, no_speech_d_.ptr, B * 4, cudaMemcpyDeviceToHost, stream_));
+    CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
+  }
+  return collect(bs, r.length_penalty, r.num_hypotheses, {});
 }
 
 }  // namespace ct2b200

@@ -23,6 +23,8 @@ struct Seq2SeqConfig {
   bool round_before_cast = true;                     // binary version >= 5 (model.h:87-89)
   bool has_enc_final_norm = false, has_dec_final_norm = false;
   bool start_from_zero_embedding = false;            // Marian / OPUS-MT decoders (transformer.cc:637-640)
+  bool whisper = false;                              // WhisperSpec: Conv1D front-end instead of source embeddings
+  int64_t n_mels = 0, max_frames = 0;                // Whisper: input channels, encoder positions (frames / 2)
   int64_t weight_bytes = 0;
   std::string weights;                               // storage type of the linear layers
 };
@@ -65,6 +67,22 @@ struct TranslationRequest {
   bool return_end_token = false;
 };
 
+// models::Whisper::generate (include/ctranslate2/models/whisper.h:11-60, src/models/whisper.cc:241-390), prompts made of
+// <|startoftranscript|> and task tokens ending with <|notimestamps|> (the timestamp rules are not implemented)
+struct WhisperRequest {
+  const float* features = nullptr;        // host [batch, n_mels, frames] f32
+  int64_t batch = 0, frames = 0;
+  const int32_t* prompts = nullptr;       // host [batch, prompt_len]
+  int64_t prompt_len = 0;
+  int beam_size = 5;
+  float patience = 1.f, length_penalty = 1.f;
+  int64_t max_length = 448;
+  int num_hypotheses = 1;
+  std::vector<int32_t> suppress_ids, suppress_ids_begin;
+  int32_t sot_id = 0, eot_id = 0, no_speech_id = -1;
+  bool return_no_speech_prob = false;
+};
+
 struct TranslationHypotheses {            // per batch entry, best first
   std::vector<std::vector<int32_t>> tokens;
   std::vector<float> scores;
@@ -81,6 +99,10 @@ class Translator {
   std::vector<TranslationHypotheses> translate(const TranslationRequest& req);
   // TransformerEncoder::operator(): memory_h [batch, max_source_len, d_model] f32 host
   void encode(const int32_t* ids_h, const int32_t* lens_h, int64_t batch, int64_t max_source_len, float* memory_h);
+  // WhisperEncoder::operator(): features_h [batch, n_mels, frames] f32 -> memory_h [batch, frames / 2, d_model] f32
+  void whisper_encode(const float* features_h, int64_t batch, int64_t frames, float* memory_h);
+  // models::Whisper::generate; no_speech_h [batch] or null
+  std::vector<TranslationHypotheses> whisper_generate(const WhisperRequest& req, float* no_speech_h);
   // device-timed phases for bench.py: encoder pass, then `steps` decoding steps of batch * beam rows
   void bench(int64_t batch, int64_t source_len, int beam, int64_t steps, int64_t warmup, float* encode_ms, float* decode_ms,
              int64_t* launches);
@@ -93,6 +115,14 @@ class Translator {
   void dense(const DenseWeights& w, const NormWeights* pre, const void* x, int64_t rows, const void* residual, int act, void* y);
   void post_norm(const NormWeights& n, void* x, int64_t rows);
   void run_encoder(int64_t batch, int64_t S);
+  void run_encoder_layers(int64_t batch, int64_t S, const int32_t* lens_d);
+  void run_whisper_encoder(int64_t batch, int64_t frames);
+  BeamState beam_state(int64_t batch, int beam, int64_t max_steps, int64_t min_length, float patience, float length_penalty,
+                       int num_hypotheses, int num_end);
+  void reset_search(const BeamState& bs, int32_t start_id);
+  std::vector<TranslationHypotheses> collect(const BeamState& bs, float length_penalty, int num_hypotheses,
+                                             const std::vector<int32_t>& strip_ids);
+  void run_search(const BeamState& bs, int64_t S, int64_t first_check);
   void project_memory(int64_t batch, int64_t S);
   void decoder_step(int64_t rows, int beam, int64_t batch, int64_t S);
   void beam_step(const BeamState& bs);
@@ -105,8 +135,9 @@ class Translator {
   cudaStream_t stream_ = nullptr;
 
   DenseWeights enc_emb_, dec_emb_, projection_;
+  DenseWeights conv1_, conv2_;   // Whisper: [d, n_mels * 3] / [d, d * 3] in T (+ bias)
   DeviceBuffer enc_pos_, dec_pos_;
-  int64_t num_positions_ = 0;
+  int64_t enc_positions_ = 0, dec_positions_ = 0;
   NormWeights enc_norm_, dec_norm_;
   std::vector<EncoderLayerWeights> enc_;
   std::vector<DecoderLayerWeights> dec_;
@@ -117,6 +148,8 @@ class Translator {
   DeviceBuffer src_ids_, src_lens_, x_, xn_, xq_, xs_, qkv_, ctx_, h_, q_, memory_;
   std::vector<DeviceBuffer> mem_kv_, self_k_, self_v_;
   DeviceBuffer logits_, cum_, cand_scores_, cand_ids_, ids_, end_ids_d_;
+  DeviceBuffer features_, cols_, conv_out_, suppress_d_, forced_d_, no_speech_d_;   // Whisper
+  int64_t cap_frames_ = 0;
   DeviceBuffer counters_;        // step | ticket | num_finished
   DeviceBuffer finished_, top_done_, num_hyp_, alive_, anc_, hyp_tokens_, hyp_len_, hyp_score_;
   int32_t* host_pinned_ = nullptr;

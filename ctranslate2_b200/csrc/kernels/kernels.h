@@ -190,6 +190,11 @@ void launch_attention_cross(const void* q, const void* kv, const int32_t* length
 struct BeamState {
   int batch = 0, beam = 1, vocab = 0, stride = 0, max_steps = 0, max_hyp = 0, max_candidates = 1, num_hypotheses = 1;
   int early_exit = 0, num_end = 0, min_length = 0;
+  int start_step = 0;               // absolute position of the first search step (prompt positions come before)
+  int include_eos = 1;              // DecodingOptions::include_eos_in_hypotheses
+  int num_disable = 0, num_begin = 0;
+  const int32_t* disable_ids = nullptr;     // SuppressTokens: disabled at every step
+  const int32_t* disable_begin = nullptr;   // SuppressTokensBegin: disabled at the first search step
   const int32_t* end_ids = nullptr;
   int32_t* step = nullptr;          // [1] current step, advanced by the update kernel
   int32_t* ticket = nullptr;        // [1]
@@ -205,8 +210,16 @@ struct BeamState {
   float* hyp_score = nullptr;       // [batch, max_hyp] cumulative log-probability (not normalised)
 };
 void launch_beam_init(void* cum, int32_t* ids, int64_t rows, int beam, int start_id, int dtype, cudaStream_t st);
-void launch_beam_logprobs(void* logits, int64_t rows, int64_t vocab, const void* cum, const int32_t* step_ptr, int min_length,
-                          const int32_t* end_ids, int num_end, int dtype, cudaStream_t st);
+void launch_beam_logprobs(void* logits, const void* cum, const BeamState& s, int dtype, cudaStream_t st);
+// one prompt position without a search step: next ids = forced_next [rows], identity ancestry, step + 1
+void launch_beam_force(const BeamState& s, const int32_t* forced_next, cudaStream_t st);
+// out[r] = softmax(logits[r * row_stride : +vocab])[token]
+void launch_token_prob(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int token, float* out, int dtype,
+                       cudaStream_t st);
+// ops::Conv1D as im2col (+ the float Dense): cols [batch * Tout, Cin * K] T from x [batch, Cin, Tin] (channel_major) or [batch, Tin, Cin]
+void launch_im2col(const void* x, bool x_is_f32, int64_t batch, int64_t Cin, int64_t Tin, int64_t Tout, int K, int stride,
+                   int padding, bool channel_major, void* cols, int dtype, cudaStream_t st);
+void launch_add_positions(void* x, const void* pos, int64_t rows, int64_t time, int64_t depth, int dtype, cudaStream_t st);
 void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, int dtype,
                         cudaStream_t st);
 // float32 Dense (true fp32 FMAs): c [m,n] = a [m,k] . b [n,k]^T with bias / activation / residual

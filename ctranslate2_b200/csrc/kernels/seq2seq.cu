@@ -229,19 +229,27 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
 // ops::LogSoftMax in fp32 -> T, then primitives::add_depth_broadcast of the beam's cumulative score IN T (decoding.cc:548-553).
 template <typename T>
 __global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logits, int64_t vocab, const T* __restrict__ cum,
-                                                            const int32_t* __restrict__ step_ptr, int min_length,
-                                                            const int32_t* __restrict__ end_ids, int num_end) {
+                                                            const int32_t* __restrict__ step_ptr, int start_step, int min_length,
+                                                            const int32_t* __restrict__ end_ids, int num_end,
+                                                            const int32_t* __restrict__ disable_ids, int num_disable,
+                                                            const int32_t* __restrict__ disable_begin, int num_begin) {
   __shared__ float red[32];
   griddep_launch();
   griddep_wait();
   const int64_t row = blockIdx.x;
   T* xr = logits + row * vocab;
-  const int step = *step_ptr;
-  if (step < min_length) {
+  const int step = *step_ptr - start_step;             // steps of the search (the prompt was forwarded before)
+  const T lowest = from_f32<T>(lowest_of<T>());
+  // DisableTokens (decoding_utils.h:20-60): end ids below min_length, SuppressTokens, SuppressTokensBegin at the first step
+  if (step < min_length)
     for (int e = threadIdx.x; e < num_end; e += blockDim.x)
-      if (end_ids[e] >= 0 && end_ids[e] < vocab) xr[end_ids[e]] = from_f32<T>(lowest_of<T>());
-    __syncthreads();
-  }
+      if (end_ids[e] >= 0 && end_ids[e] < vocab) xr[end_ids[e]] = lowest;
+  for (int e = threadIdx.x; e < num_disable; e += blockDim.x)
+    if (disable_ids[e] >= 0 && disable_ids[e] < vocab) xr[disable_ids[e]] = lowest;
+  if (step == 0)
+    for (int e = threadIdx.x; e < num_begin; e += blockDim.x)
+      if (disable_begin[e] >= 0 && disable_begin[e] < vocab) xr[disable_begin[e]] = lowest;
+  __syncthreads();
   float m = -INFINITY;
   for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) m = fmaxf(m, to_f32(xr[j]));
   m = block_reduce<true>(m, red);
@@ -269,7 +277,8 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
   griddep_wait();
   const int i = blockIdx.x;
   const int beam = st.beam, nc = 2 * beam, L = st.stride;
-  const int step = *st.step;
+  const int step = *st.step;                 // absolute position (indexes the K/V arena and the ancestry table)
+  const int rel = step - st.start_step;      // step of the search (indexes the token history)
   const int N = st.batch * beam;
   auto is_end = [&](int w) {
     for (int e = 0; e < st.num_end; ++e)
@@ -285,7 +294,7 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
   __syncthreads();
   if (threadIdx.x == 0) {
     const bool was_finished = st.finished[i] != 0;
-    const bool is_last = step + 1 >= st.max_steps;
+    const bool is_last = rel + 1 >= st.max_steps;
     int secondary = beam, nh = st.num_hyp[i];
     bool top_done = st.top_done[i] != 0;
     for (int k = 0; k < beam; ++k) {
@@ -295,7 +304,8 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
         if (k == 0) top_done = true;
         if (nh < st.max_hyp) {
           s_hyp[k] = nh;
-          st.hyp_len[i * st.max_hyp + nh] = step + 1;
+          // the end token is kept or dropped per include_eos_in_hypotheses (decoding.cc:601-603)
+          st.hyp_len[i * st.max_hyp + nh] = (is_end(s_word[k]) && !st.include_eos) ? rel : rel + 1;
           st.hyp_score[i * st.max_hyp + nh] = s_score[k];
           ++nh;
         }
@@ -332,19 +342,19 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
     if (slot < 0) continue;
     int32_t* dst = st.hyp_tokens + (static_cast<int64_t>(i) * st.max_hyp + slot) * L;
     const int32_t* src = alive_r + static_cast<int64_t>(i * beam + s_origin[k]) * L;
-    for (int t = threadIdx.x; t < step; t += blockDim.x) dst[t] = src[t];
-    if (threadIdx.x == 0) dst[step] = s_word[k];
+    for (int t = threadIdx.x; t < rel; t += blockDim.x) dst[t] = src[t];
+    if (threadIdx.x == 0) dst[rel] = s_word[k];
   }
   // the next beams
   for (int k = 0; k < beam; ++k) {
     const int c = s_active[k];
     const int64_t row = static_cast<int64_t>(i) * beam + k, parent = static_cast<int64_t>(i) * beam + s_origin[c];
     for (int t = threadIdx.x; t < step; t += blockDim.x) {
-      alive_w[row * L + t] = alive_r[parent * L + t];
+      if (t < rel) alive_w[row * L + t] = alive_r[parent * L + t];
       anc_w[row * L + t] = anc_r[parent * L + t];
     }
     if (threadIdx.x == 0) {
-      alive_w[row * L + step] = s_word[c];
+      alive_w[row * L + rel] = s_word[c];
       anc_w[row * L + step] = static_cast<int32_t>(parent);
       st.next_ids[row] = s_word[c];
       cum[row] = from_f32<T>(s_score[c]);
@@ -360,6 +370,70 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
       *st.step = step + 1;
     }
   }
+}
+
+// One prompt position forwarded without a search step (WhisperDecoder::forward_prompt, layers/whisper.cc:66-75; the hard
+// prefix of decode(), decoding.cc:1138-1170): every row keeps its own K/V slot, the next input is the next prompt token.
+__global__ void beam_force_kernel(BeamState st, const int32_t* __restrict__ forced_next /* [rows] */) {
+  const int row = blockIdx.x * blockDim.x + threadIdx.x;
+  const int N = st.batch * st.beam;
+  const int step = *st.step;
+  if (row < N) {
+    st.anc[static_cast<int64_t>(row) * st.stride + step] = row;                                  // both parities: identity
+    st.anc[static_cast<int64_t>(N) * st.stride + static_cast<int64_t>(row) * st.stride + step] = row;
+    st.next_ids[row] = forced_next[row];
+  }
+  __threadfence();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const bool last = atomicAdd(st.ticket, 1) == static_cast<int>(gridDim.x) - 1;
+    if (last) {
+      *st.ticket = 0;
+      *st.step = step + 1;
+    }
+  }
+}
+
+// probability of one token under ops::SoftMax of the row (get_no_speech_probs_from_logits, models/whisper.cc:131-147)
+template <typename T>
+__global__ void __launch_bounds__(256) token_prob_kernel(const T* __restrict__ logits, int64_t vocab, int64_t row_stride,
+                                                         int token, float* __restrict__ out) {
+  __shared__ float red[32];
+  const T* xr = logits + static_cast<int64_t>(blockIdx.x) * row_stride;
+  float m = -INFINITY;
+  for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) m = fmaxf(m, to_f32(xr[j]));
+  m = block_reduce<true>(m, red);
+  float s = 0.f;
+  for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) s += expf(to_f32(xr[j]) - m);
+  s = block_reduce<false>(s, red);
+  if (threadIdx.x == 0) out[blockIdx.x] = round_to<T>(expf(to_f32(xr[token]) - m) / s);
+}
+
+// im2col of ops::Conv1D (src/ops/conv1d_gpu.cu; CPU form conv1d_cpu.cc:128-220): row (b, t) of cols = x[b, ci, t * stride + k -
+// padding] in (ci, k) order, so that conv = cols . W^T with W [Cout, Cin * K] as stored.  channel_major: x is [B, Cin, Tin]
+// (the input features); otherwise x is [B, Tin, Cin] (the previous convolution's GEMM output).
+template <typename TIn, typename T>
+__global__ void im2col_kernel(const TIn* __restrict__ x, int64_t Cin, int64_t Tin, int64_t Tout, int K, int stride, int padding,
+                              bool channel_major, T* __restrict__ cols) {
+  const int64_t r = blockIdx.x;                 // b * Tout + t
+  const int64_t b = r / Tout, t = r % Tout;
+  const int64_t width = Cin * K;
+  for (int64_t j = threadIdx.x; j < width; j += blockDim.x) {
+    const int64_t ci = j / K;
+    const int k = static_cast<int>(j % K);
+    const int64_t tt = t * stride + k - padding;
+    float v = 0.f;
+    if (tt >= 0 && tt < Tin) v = channel_major ? to_f32(x[(b * Cin + ci) * Tin + tt]) : to_f32(x[(b * Tin + tt) * Cin + ci]);
+    cols[r * width + j] = from_f32<T>(v);
+  }
+}
+
+// PositionEncoder::operator() (common.cc:150-172): x[b, t, :] += encodings[t, :], in T
+template <typename T>
+__global__ void add_positions_kernel(T* __restrict__ x, const T* __restrict__ pos, int64_t time, int64_t depth) {
+  const int64_t r = blockIdx.x, t = r % time;
+  for (int64_t j = threadIdx.x; j < depth; j += blockDim.x)
+    x[r * depth + j] = from_f32<T>(to_f32(x[r * depth + j]) + to_f32(pos[t * depth + j]));
 }
 
 // initialize_beam_scores (decoding.cc:84-93): beam 0 of every entry starts at 0, the others at the lowest T
@@ -533,11 +607,47 @@ void launch_beam_init(void* cum, int32_t* ids, int64_t rows, int beam, int start
   check_launch();
 }
 
-void launch_beam_logprobs(void* logits, int64_t rows, int64_t vocab, const void* cum, const int32_t* step_ptr, int min_length,
-                          const int32_t* end_ids, int num_end, int dtype, cudaStream_t st) {
+void launch_beam_logprobs(void* logits, const void* cum, const BeamState& s, int dtype, cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(s.batch) * s.beam;
   if (rows == 0) return;
-  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_logprobs_kernel<T>, dim3(rows), dim3(256), 0, st, static_cast<T*>(logits), vocab,
-                                        static_cast<const T*>(cum), step_ptr, min_length, end_ids, num_end)));
+  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_logprobs_kernel<T>, dim3(rows), dim3(256), 0, st, static_cast<T*>(logits),
+                                        static_cast<int64_t>(s.vocab), static_cast<const T*>(cum), s.step, s.start_step,
+                                        s.min_length, s.end_ids, s.num_end, s.disable_ids, s.num_disable, s.disable_begin,
+                                        s.num_begin)));
+  check_launch();
+}
+
+void launch_beam_force(const BeamState& s, const int32_t* forced_next, cudaStream_t st) {
+  const int rows = s.batch * s.beam;
+  beam_force_kernel<<<div_up(rows, 128), 128, 0, st>>>(s, forced_next);
+  check_launch();
+}
+
+void launch_token_prob(const void* logits, int64_t rows, int64_t vocab, int64_t row_stride, int token, float* out, int dtype,
+                       cudaStream_t st) {
+  if (rows == 0) return;
+  CT2_REQUIRE(token >= 0 && token < vocab, "token_prob: token out of range");
+  CT2_DISPATCH_DTYPE(dtype, (token_prob_kernel<T><<<rows, 256, 0, st>>>(static_cast<const T*>(logits), vocab, row_stride, token, out)));
+  check_launch();
+}
+
+void launch_im2col(const void* x, bool x_is_f32, int64_t batch, int64_t Cin, int64_t Tin, int64_t Tout, int K, int stride,
+                   int padding, bool channel_major, void* cols, int dtype, cudaStream_t st) {
+  if (batch * Tout == 0) return;
+  if (x_is_f32) {
+    CT2_DISPATCH_DTYPE(dtype, (im2col_kernel<float, T><<<batch * Tout, 128, 0, st>>>(static_cast<const float*>(x), Cin, Tin, Tout, K,
+                                                                                    stride, padding, channel_major,
+                                                                                    static_cast<T*>(cols))));
+  } else {
+    CT2_DISPATCH_DTYPE(dtype, (im2col_kernel<T, T><<<batch * Tout, 128, 0, st>>>(static_cast<const T*>(x), Cin, Tin, Tout, K, stride,
+                                                                                padding, channel_major, static_cast<T*>(cols))));
+  }
+  check_launch();
+}
+
+void launch_add_positions(void* x, const void* pos, int64_t rows, int64_t time, int64_t depth, int dtype, cudaStream_t st) {
+  if (rows == 0) return;
+  CT2_DISPATCH_DTYPE(dtype, (add_positions_kernel<T><<<rows, 128, 0, st>>>(static_cast<T*>(x), static_cast<const T*>(pos), time, depth)));
   check_launch();
 }
 

@@ -332,6 +332,29 @@ CT2B200_API int ct2b200_translator_encode(ct2b200_translator* t, const int32_t* 
 CT2B200_API int ct2b200_bench_translate(ct2b200_translator* t, int64_t batch, int64_t source_len, int beam_size, int64_t steps,
                             int64_t warmup, float* encode_ms, float* decode_ms, int64_t* kernel_launches);
 
+/* ---------------------------------------------------------------------------------------------
+ * Whisper: ctranslate2::models::Whisper — include/ctranslate2/models/whisper.h:86-190, src/models/whisper.cc,
+ * WhisperEncoder / WhisperDecoder src/layers/whisper.cc, ops::Conv1D src/ops/conv1d_gpu.cu.  A WhisperSpec directory opens
+ * with ct2b200_translator_open (same handle type; the encoder is the Conv1D front-end instead of source embeddings).
+ * Served: encode, and generate for prompts made of <|startoftranscript|> + task tokens ending with <|notimestamps|> (the
+ * timestamp rules of whisper.cc:395-520 are not implemented; detect_language / align are not provided).
+ * ------------------------------------------------------------------------------------------- */
+CT2B200_API int ct2b200_whisper_info(const ct2b200_translator* t, int* n_mels, int* max_frames, int* d_model, int* vocab_size);
+/* Whisper::encode: features_h [batch, n_mels, frames] f32 host -> memory_h [batch, (frames + 1) / 2, d_model] f32 host. */
+CT2B200_API int ct2b200_whisper_encode(ct2b200_translator* t, const float* features_h, int64_t batch, int64_t frames,
+                           float* memory_h);
+/* Whisper::generate(features, prompts, WhisperOptions): prompts_h [batch, prompt_len] ids; suppress_ids_h = the resolved
+ * WhisperOptions::suppress_tokens (config.json "suppress_ids" for -1), suppress_begin_h = "suppress_ids_begin" when
+ * suppress_blank; out_ids_h [batch, num_hypotheses, max_length] (-1 padded; the decoder runs min(max_length / 2,
+ * max_length - prompt_len + 1) steps, whisper.cc:299), out_lens_h / out_scores_h [batch, num_hypotheses];
+ * no_speech_h [batch] or NULL (return_no_speech_prob; needs no_speech_id). */
+CT2B200_API int ct2b200_whisper_generate(ct2b200_translator* t, const float* features_h, int64_t batch, int64_t frames,
+                             const int32_t* prompts_h, int64_t prompt_len, int beam_size, float patience, float length_penalty,
+                             int64_t max_length, int num_hypotheses, const int32_t* suppress_ids_h, int num_suppress,
+                             const int32_t* suppress_begin_h, int num_begin, int32_t sot_id, int32_t eot_id,
+                             int32_t no_speech_id, int32_t* out_ids_h, int32_t* out_lens_h, float* out_scores_h,
+                             float* no_speech_h);
+
 #ifdef __cplusplus
 }
 #endif

@@ -568,7 +568,7 @@ class Seq2SeqOracle:
         self._float_w: Dict[str, np.ndarray] = {}
         self.num_heads = int(variables.get("encoder/num_heads", np.int16(num_heads)))
         self.enc_emb = "encoder/embeddings_0" if "encoder/embeddings_0/weight" in variables else "encoder/embeddings"
-        self.d = variables[self.enc_emb + "/weight"].shape[1]
+        self.d = variables["decoder/embeddings/weight"].shape[1]
         self.enc_layers = 0
         while f"encoder/layer_{self.enc_layers}/ffn/linear_0/weight" in variables:
             self.enc_layers += 1
@@ -586,6 +586,17 @@ class Seq2SeqOracle:
         self.act = {s: int(attr(s, "activation", ACT_RELU)) for s in ("encoder", "decoder")}
         self.zero_first = bool(variables.get("decoder/start_from_zero_embedding", False))
         self.eps = eps
+
+        def emb_scale(scope):                                    # build_embeddings_scale, transformer.cc:380-402
+            sc = variables.get(scope + "/scale_embeddings", variables.get(scope + "/embeddings/multiply_by_sqrt_depth"))
+            if sc is None or (sc.dtype == np.int8 and bool(sc)):
+                return f32(math.sqrt(self.d))
+            if sc.dtype != np.int8 and float(sc) != 1.0:
+                return f32(sc)
+            return None
+        self.emb_scale = {s: emb_scale(s) for s in ("encoder", "decoder")}
+        if "decoder/position_encodings/encodings" in variables:  # PositionEmbedding instead of the sinusoidal encoder
+            self.pos = variables["decoder/position_encodings/encodings"].astype(f32)
 
     @classmethod
     def from_dir(cls, model_dir: str, flavor: str = "cpu", compute_type: str = "int8") -> "Seq2SeqOracle":
@@ -624,7 +635,8 @@ class Seq2SeqOracle:
         if emb + "/weight_scale" in v:                           # Embeddings::operator(), common.cc:64-81
             sc = v[emb + "/weight_scale"].astype(f32)
             x = (x / (gather_rows(sc, ids)[..., None] if sc.ndim == 1 else sc)).astype(f32)
-        return (x * f32(math.sqrt(self.d))).astype(f32)          # build_embeddings_scale: sqrt(depth)
+        sc = self.emb_scale[scope]
+        return x if sc is None else (x * sc).astype(f32)
 
     def _ln(self, prefix, x):
         return layer_norm(x, self.v[prefix + "/gamma"], self.v[prefix + "/beta"], self.eps)
@@ -740,6 +752,106 @@ class Seq2SeqOracle:
                            length_penalty, num_hypotheses)
 
 
+def conv1d(x: np.ndarray, w: np.ndarray, bias: Optional[np.ndarray], stride: int, padding: int) -> np.ndarray:
+    """ops::Conv1D (src/ops/conv1d.cc, conv1d_cpu.cc:128-220 im2col + GEMM; conv1d_gpu.cu cuDNN): x [B, Cin, T], w [Cout, Cin, K]
+    -> [B, Cout, (T + 2 * padding - K) / stride + 1]."""
+    B, Cin, T = x.shape
+    Cout, _, K = w.shape
+    xp = np.zeros((B, Cin, T + 2 * padding), f32)
+    xp[:, :, padding:padding + T] = x
+    Tout = (T + 2 * padding - K) // stride + 1
+    cols = np.stack([xp[:, :, k:k + stride * Tout:stride] for k in range(K)], axis=2)      # [B, Cin, K, Tout]
+    y = np.einsum("bckt,ock->bot", cols, w.astype(f32)).astype(f32)
+    return y if bias is None else (y + bias.astype(f32)[None, :, None]).astype(f32)
+
+
+class WhisperOracle(Seq2SeqOracle):
+    """fp32 restatement of models::WhisperReplica (src/models/whisper.cc:106-390) without timestamp rules: WhisperEncoder
+    (src/layers/whisper.cc:8-63: conv1 + GELU, conv2 stride 2 + GELU, stored positions, pre-norm GELU layers, LayerNorm), the
+    TransformerDecoder with cross-attention and stored positions, forward_prompt on the task tokens, then the search with
+    SuppressTokens / SuppressTokensBegin and hypotheses that exclude the end token."""
+
+    def __init__(self, variables, config: Optional[dict] = None, **kw):
+        super().__init__(variables, **kw)
+        self.config = config or {}
+        self.pre_norm["encoder"], self.act["encoder"] = True, ACT_GELU
+        vocab = self.v["decoder/embeddings/weight"].shape[0]
+        self.vocab = vocab
+
+    @classmethod
+    def from_dir(cls, model_dir: str, flavor: str = "cpu", compute_type: str = "int8") -> "WhisperOracle":
+        _, _, variables, aliases = read_model_bin(model_dir + "/model.bin")
+        for alias, target in aliases.items():
+            variables[alias] = variables[target]
+            if target + "_scale" in variables:
+                variables[alias + "_scale"] = variables[target + "_scale"]
+        with open(os.path.join(model_dir, "config.json")) as f:
+            config = json.load(f)
+        with open(os.path.join(model_dir, "vocabulary.json")) as f:
+            tokens = json.load(f)
+        o = cls(variables, config=config, flavor=flavor, binary_version=6, compute_type=compute_type)
+        o.sot, o.eot = tokens.index("<|startoftranscript|>"), tokens.index("<|endoftext|>")
+        o.no_timestamps = tokens.index("<|notimestamps|>")
+        o.no_speech = tokens.index("<|nospeech|>") if "<|nospeech|>" in tokens else tokens.index("<|nocaptions|>")
+        return o
+
+    def encode_features(self, features: np.ndarray) -> np.ndarray:
+        """features [B, n_mels, T] -> [B, T / 2, d]."""
+        v = self.v
+        x = activation(conv1d(features.astype(f32), v["encoder/conv1/weight"], v["encoder/conv1/bias"], 1, 1), ACT_GELU)
+        x = activation(conv1d(x, v["encoder/conv2/weight"], v["encoder/conv2/bias"], 2, 1), ACT_GELU)
+        x = np.ascontiguousarray(x.transpose(0, 2, 1))
+        B, S, _ = x.shape
+        x = (x + v["encoder/position_encodings/encodings"].astype(f32)[:S][None]).astype(f32)
+        lens_rows = np.full(B * self.num_heads * S, S)
+        for l in range(self.enc_layers):
+            p = f"encoder/layer_{l}/"
+
+            def attn(h, res):
+                q, k, v_ = np.split(self._dense(p + "self_attention/linear_0", h), 3, axis=-1)
+                return self._dense(p + "self_attention/linear_1", self._attend(q, k, v_, lens_rows), residual=res)
+
+            def ffn(h, res):
+                return self._dense(p + "ffn/linear_1", self._dense(p + "ffn/linear_0", h, act=ACT_GELU), residual=res)
+
+            x = self._sublayer("encoder", p + "self_attention", x, attn)
+            x = self._sublayer("encoder", p + "ffn", x, ffn)
+        return self._ln("encoder/layer_norm", x)
+
+    def generate(self, features: np.ndarray, prompts: np.ndarray, beam_size: int = 5, patience: float = 1.0,
+                 num_hypotheses: int = 1, length_penalty: float = 1.0, max_length: int = 448, suppress_blank: bool = True,
+                 suppress_default: bool = True):
+        """prompts [B, P]: <|startoftranscript|> + task tokens ending with <|notimestamps|> (the timestamp rules are not
+        restated).  Returns (per entry [(tokens, score), ...] best first, no_speech_probs [B])."""
+        prompts = np.asarray(prompts)
+        B, P = prompts.shape
+        assert P >= 2 and (prompts[:, -1] == self.no_timestamps).all(), "prompts must end with <|notimestamps|>"
+        memory = self.encode_features(features)
+        self.start(memory, np.full(B, memory.shape[1]), beam_size)
+        no_speech = np.zeros(B, f32)
+        for t in range(P - 1):                                   # WhisperDecoder::forward_prompt on prompt[:-1]
+            logits = self.step(np.repeat(prompts[:, t], beam_size), t)
+            if (prompts[:, t] == self.sot).all():
+                no_speech = softmax(logits[::beam_size])[:, self.no_speech]
+        start_step = P - 1
+        steps = min(max_length // 2, max_length - start_step)
+        disable = list(self.config.get("suppress_ids", [])) if suppress_default else []
+        disable_begin = list(self.config.get("suppress_ids_begin", [])) if suppress_blank else []
+        lowest = np.finfo(f32).min
+
+        def hook(step, logits):                                  # SuppressTokens, SuppressTokensBegin (decoding_utils.cc:152-188)
+            for t in disable:
+                logits[:, t] = lowest
+            if step == 0:
+                for t in disable_begin:
+                    logits[:, t] = lowest
+
+        res = beam_search(lambda ids, s: self.step(ids, start_step + s), self.reorder, prompts[:, -1], self.vocab, beam_size,
+                          steps, 0, [self.eot], length_penalty, num_hypotheses, patience, include_eos_in_hypotheses=False,
+                          logits_hook=hook)
+        return res, no_speech
+
+
 def apply_logits_processors(logits: np.ndarray, sampled: Sequence[int], repetition_penalty: float = 1.0,
                             no_repeat_ngram_size: int = 0, suppress_sequences: Sequence[Sequence[int]] = (),
                             disable_ids: Sequence[int] = ()) -> None:
@@ -779,7 +891,7 @@ def apply_logits_processors(logits: np.ndarray, sampled: Sequence[int], repetiti
 
 def beam_search(step_fn, reorder_fn, start_ids: np.ndarray, vocab: int, beam_size: int, max_length: int,
                 min_length: int = 0, end_ids: Sequence[int] = (), length_penalty: float = 1.0, num_hypotheses: int = 1,
-                patience: float = 1.0):
+                patience: float = 1.0, include_eos_in_hypotheses: bool = True, logits_hook=None):
     """BeamSearch::search (src/decoding.cc:425-720).  No prefix bias, no coverage penalty; hypotheses keep their end token
     while they are scored (include_eos_in_hypotheses = true, decoding.h:154) and lose it in the returned tokens.
     step_fn(ids [B*beam], step) -> logits [B*beam, vocab] (advances the decoder state); reorder_fn(index [B*beam]) gathers the
@@ -808,6 +920,8 @@ def beam_search(step_fn, reorder_fn, start_ids: np.ndarray, vocab: int, beam_siz
         if step < min_length:
             for e in end_ids:
                 logits[:, e] = lowest                                                 # apply_min_length + DisableTokens
+        if logits_hook is not None:
+            logits_hook(step, logits)                                                 # LogitsProcessor chain (SuppressTokens ...)
         with np.errstate(over="ignore"):
             lp = (softmax(logits, log=True) + scores[:, None]).astype(f32).reshape(B, beam_size * V)
         cand_scores, cand_ids = topk(lp, ncand)
@@ -825,7 +939,8 @@ def beam_search(step_fn, reorder_fn, start_ids: np.ndarray, vocab: int, beam_siz
                 if not finished[i] and (int(word[i, k]) in end_ids or is_last):
                     if k == 0:
                         top_done[i] = True
-                    hyps[i].append((seqs[k][:step + 1], float(cand_scores[i, k])))
+                    drop = int(word[i, k]) in end_ids and not include_eos_in_hypotheses   # decoding.cc:601-603
+                    hyps[i].append((seqs[k][:step] if drop else seqs[k][:step + 1], float(cand_scores[i, k])))
                     for j in range(secondary, ncand):
                         if int(word[i, j]) not in end_ids:
                             nxt, secondary = j, j + 1
@@ -848,7 +963,8 @@ def beam_search(step_fn, reorder_fn, start_ids: np.ndarray, vocab: int, beam_siz
         ids, scores = new_ids.reshape(-1), new_scores.reshape(-1).astype(f32)
     out = []
     for i in range(B):
-        final = [(t, float(sc / (len(t) ** length_penalty))) for t, sc in hyps[i]]
+        with np.errstate(divide="ignore"):
+            final = [(t, float(f32(sc) / f32(f32(len(t)) ** f32(length_penalty)))) for t, sc in hyps[i]]
         order = sorted(range(len(final)), key=lambda j: -final[j][1])                  # std::sort, descending score
         best = []
         for j in order[:num_hypotheses]:

@@ -24,6 +24,7 @@
 #include <ctranslate2/generator.h>
 #include <ctranslate2/models/language_model.h>
 #include <ctranslate2/models/sequence_to_sequence.h>
+#include <ctranslate2/models/whisper.h>
 #include <ctranslate2/translator.h>
 #include <ctranslate2/ops/ops.h>
 #include <ctranslate2/utils.h>
@@ -263,6 +264,73 @@ int ref_translate(void* handle, const int32_t* source_ids, int B, int S, int bea
         out_scores[o] = have ? results[b].scores.at(h) : 0.f;
         for (int i = 0; i < max_len; ++i)
           out_ids[o * max_len + i] = (have && i < out_lens[o]) ? static_cast<int32_t>(t->target->to_id(results[b].hypotheses[h][i])) : -1;
+      }
+    }
+  });
+}
+
+// ---- Whisper (include/ctranslate2/models/whisper.h:86-190) ----
+struct RefWhisper {
+  std::unique_ptr<models::Whisper> pool;
+};
+
+void* ref_whisper_open(const char* model_dir, const char* compute_type, int intra_threads) {
+  RefWhisper* w = nullptr;
+  int rc = guarded([&] {
+    auto holder = std::make_unique<RefWhisper>();
+    ReplicaPoolConfig config;
+    config.num_threads_per_replica = intra_threads > 0 ? intra_threads : 0;
+    holder->pool = std::make_unique<models::Whisper>(model_dir, g_device, str_to_compute_type(compute_type),
+                                                     std::vector<int>{0}, /*tensor_parallel=*/false, config);
+    w = holder.release();
+  });
+  return rc == 0 ? w : nullptr;
+}
+void ref_whisper_close(void* handle) { delete static_cast<RefWhisper*>(handle); }
+
+// features [B, n_mels, T] fp32 -> encoder output [B, T / 2, d] fp32 (out_capacity floats)
+int ref_whisper_encode(void* handle, const float* features, int B, int n_mels, int T, float* out, int64_t out_capacity) {
+  auto* w = static_cast<RefWhisper*>(handle);
+  return guarded([&] {
+    StorageView f = view_f32(features, {B, n_mels, T});
+    StorageView enc = w->pool->encode(f, /*to_cpu=*/true).get();
+    StorageView e32 = enc.to_float32();
+    if (e32.size() > out_capacity) throw std::runtime_error("ref_whisper_encode: output buffer too small");
+    std::memcpy(out, e32.data<float>(), e32.size() * sizeof(float));
+  });
+}
+
+// prompts [B, P] ids; out_ids [B, num_hyp, max_len] (-1 padded), out_lens / out_scores [B, num_hyp], no_speech [B]
+int ref_whisper_generate(void* handle, const float* features, int B, int n_mels, int T, const int32_t* prompts, int P,
+                         int beam_size, float patience, int num_hyp, float length_penalty, int max_length, int suppress_blank,
+                         int suppress_default, int32_t* out_ids, int32_t* out_lens, float* out_scores, float* no_speech) {
+  auto* w = static_cast<RefWhisper*>(handle);
+  return guarded([&] {
+    StorageView f = view_f32(features, {B, n_mels, T});
+    std::vector<std::vector<size_t>> pr(B);
+    for (int b = 0; b < B; ++b)
+      for (int i = 0; i < P; ++i) pr[b].push_back(prompts[b * P + i]);
+    models::WhisperOptions opt;
+    opt.beam_size = beam_size;
+    opt.patience = patience;
+    opt.num_hypotheses = num_hyp;
+    opt.length_penalty = length_penalty;
+    opt.max_length = max_length;
+    opt.return_scores = true;
+    opt.return_no_speech_prob = no_speech != nullptr;
+    opt.suppress_blank = suppress_blank != 0;
+    opt.suppress_tokens = suppress_default ? std::vector<int>{-1} : std::vector<int>{};
+    auto futures = w->pool->generate(f, pr, opt);
+    for (int b = 0; b < B; ++b) {
+      auto r = futures[b].get();
+      if (no_speech) no_speech[b] = r.no_speech_prob;
+      for (int h = 0; h < num_hyp; ++h) {
+        const bool have = h < static_cast<int>(r.sequences_ids.size());
+        const int64_t o = static_cast<int64_t>(b) * num_hyp + h;
+        out_lens[o] = have ? static_cast<int32_t>(r.sequences_ids[h].size()) : -1;
+        out_scores[o] = have && h < static_cast<int>(r.scores.size()) ? r.scores[h] : 0.f;
+        for (int i = 0; i < max_length; ++i)
+          out_ids[o * max_length + i] = (have && i < out_lens[o]) ? static_cast<int32_t>(r.sequences_ids[h][i]) : -1;
       }
     }
   });

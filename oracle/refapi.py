@@ -230,6 +230,45 @@ class RefTranslator:
                 for b in range(B)]
 
 
+
+class RefWhisper:
+    """The unmodified reference's models::Whisper (encode / generate) over features and prompt ids."""
+
+    def __init__(self, model_dir: str, compute_type: str = "float32", threads: int = 0):
+        lib().ref_whisper_open.restype = ctypes.c_void_p
+        self.h = lib().ref_whisper_open(model_dir.encode(), compute_type.encode(), threads)
+        if not self.h:
+            raise RuntimeError(lib().ref_last_error().decode())
+
+    def close(self):
+        if self.h and lib is not None:
+            lib().ref_whisper_close(ctypes.c_void_p(self.h))
+            self.h = None
+
+    def encode(self, features: np.ndarray, d_model: int) -> np.ndarray:
+        f = np.ascontiguousarray(features, np.float32)
+        B, M, T = f.shape
+        out = np.zeros((B, (T + 1) // 2, d_model), np.float32)
+        _check(lib().ref_whisper_encode(ctypes.c_void_p(self.h), _p(f), B, M, T, _p(out), ctypes.c_int64(out.size)))
+        return out
+
+    def generate(self, features: np.ndarray, prompts, beam_size=5, patience=1.0, num_hypotheses=1, length_penalty=1.0,
+                 max_length=448, suppress_blank=True, suppress_default=True):
+        """Returns (per entry [(ids, score), ...] best first, no_speech_probs [B])."""
+        f = np.ascontiguousarray(features, np.float32)
+        B, M, T = f.shape
+        pr = np.ascontiguousarray(np.array(prompts, np.int32))
+        out = np.zeros((B, num_hypotheses, max_length), np.int32)
+        lens = np.zeros((B, num_hypotheses), np.int32)
+        scores = np.zeros((B, num_hypotheses), np.float32)
+        nsp = np.zeros(B, np.float32)
+        _check(lib().ref_whisper_generate(ctypes.c_void_p(self.h), _p(f), B, M, T, _p(pr), pr.shape[1], beam_size,
+                                          ctypes.c_float(patience), num_hypotheses, ctypes.c_float(length_penalty), max_length,
+                                          int(suppress_blank), int(suppress_default), _p(out), _p(lens), _p(scores), _p(nsp)))
+        res = [[(out[b, h, :lens[b, h]].tolist(), float(scores[b, h])) for h in range(num_hypotheses) if lens[b, h] >= 0]
+               for b in range(B)]
+        return res, nsp
+
 def layer_norm(gamma, beta, x, eps=1e-5):
     x = _c(x, np.float32)
     r, c = x.shape

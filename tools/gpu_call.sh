@@ -47,7 +47,7 @@ stage_shims() {    # the reference's own gtests with libct2b200 interposed under
   echo "shim gtests exit $?" >> $OUT/ref_gtests_on_b200.txt
 }
 stage_translate() {   # encoder-decoder path: tests first, then the OPUS-MT-shaped bench record
-  timeout 900 python -m pytest tests/test_gpu_translator.py -q > $OUT/pytest_translator.log 2>&1
+  timeout 900 python -m pytest tests/test_gpu_translator.py tests/test_gpu_whisper.py -q > $OUT/pytest_translator.log 2>&1
   echo "translator tests exit $?" >> $OUT/pytest_translator.log
 }
 

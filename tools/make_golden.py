@@ -276,6 +276,51 @@ def make_seq2seq_fixture():
     print("seq2seq fixture:", sum(len(m["cases"]) for e in fixture.values() for m in e["models"].values()), "cases")
 
 
+WHISPER_CASES = [  # (beam, num_hypotheses, length_penalty, max_length, suppress_blank)
+    (1, 1, 1.0, 24, True), (3, 2, 1.0, 24, True), (5, 3, 1.0, 30, True), (5, 1, 0.0, 24, False), (2, 2, 0.7, 16, True)]
+
+
+def whisper_inputs(seed, batch, n_mels, frames):
+    return (np.random.default_rng(seed).standard_normal((batch, n_mels, frames)) * 2).astype(np.float32)
+
+
+def make_whisper_fixture():
+    """Whisper path (SURVEY §8 f3): outputs of the UNMODIFIED reference's models::Whisper (oracle/_ref, CPU) on a tiny WhisperSpec
+    model written by converters/synthetic.py (2 + 2 layers, d 64, 4 heads, 16 mel bins, 60 frames): encoder output, generate
+    (greedy and beam, several hypotheses, length penalties, suppress_blank on / off) and no-speech probabilities, in float32
+    and int8.  The features are re-generated from their seeds by the tests."""
+    from ctranslate2_b200.converters.synthetic import WhisperConfig, whisper_vocabulary, write_whisper_model
+    from oracle import refapi
+    cfg = WhisperConfig(encoder_layers=2, decoder_layers=2, num_heads=4, d_model=64, n_mels=16, max_source_positions=30,
+                        max_target_positions=64, text_tokens=100, languages=3, timestamps=11)
+    mdir = os.path.join(OUT, "tiny_whisper")
+    write_whisper_model(mdir, cfg, "int8", seed=5)
+    vocab = whisper_vocabulary(cfg)
+    sot = vocab.index("<|startoftranscript|>")
+    fixture = {"n_mels": 16, "frames": 60, "d_model": 64, "models": {}}
+    for compute in ("float32", "int8"):
+        w = refapi.RefWhisper(mdir, compute, 2)
+        cases = []
+        for ci, (beam, nh, lp, mx, blank) in enumerate(WHISPER_CASES):
+            for rep in range(3):
+                seed, batch = 300 + 10 * ci + rep, 1 + (ci + rep) % 4
+                feats = whisper_inputs(seed, batch, 16, 60)
+                prompts = [[sot, sot + 1 + (b % 3), vocab.index("<|transcribe|>" if b % 2 == 0 else "<|translate|>"),
+                            vocab.index("<|notimestamps|>")] for b in range(batch)]
+                res, nsp = w.generate(feats, prompts, beam_size=beam, num_hypotheses=nh, length_penalty=lp, max_length=mx,
+                                      suppress_blank=blank)
+                cases.append({"seed": seed, "batch": batch, "prompts": prompts, "beam_size": beam, "num_hypotheses": nh,
+                              "length_penalty": lp, "max_length": mx, "suppress_blank": blank,
+                              "sequences": [[h[0] for h in r] for r in res], "scores": [[h[1] for h in r] for r in res],
+                              "no_speech_prob": [float(x) for x in nsp]})
+        enc = w.encode(whisper_inputs(7, 2, 16, 60), 64)
+        fixture["models"][compute] = {"cases": cases, "encode_seed": 7, "encoder_output": enc.tolist()}
+        w.close()
+    with open(os.path.join(OUT, "whisper_ref.json"), "w") as f:
+        json.dump(fixture, f)
+    print("whisper fixture:", sum(len(m["cases"]) for m in fixture["models"].values()), "cases")
+
+
 def main():
     os.makedirs(OUT, exist_ok=True)
     if "--scores-only" in sys.argv:
@@ -286,6 +331,9 @@ def main():
         return
     if "--ragged-only" in sys.argv:
         make_ragged_fixture()
+        return
+    if "--whisper-only" in sys.argv:
+        make_whisper_fixture()
         return
     if "--seq2seq-only" in sys.argv:
         make_seq2seq_fixture()
@@ -361,6 +409,7 @@ def main():
     make_ragged_fixture()
     make_score_fixture()
     make_seq2seq_fixture()
+    make_whisper_fixture()
     print("done")
 
 
