@@ -13,6 +13,8 @@ tokens per sequence.  One JSON line on stdout (rank 0):
   variants = the four points of BASELINE.json's metric — INT8 and AWQ-INT4 at bsz 1 and 32 — device-timed decode
              (ms/step, tokens/s, fraction of the HBM roofline of the step), each beside `ref_cuda`: the UNMODIFIED
              reference's own CUDA build (oracle/_ref_cuda: cuBLAS INT8 GEMM / its AWQ kernels) on the same GPU
+  translate = BASELINE.json configs[1] (OPUS-MT-shaped Transformer-base INT8, 64 sentences, beam 4): device-timed decoding
+             steps, end-to-end target tokens/s through Translator.translate_batch, beside the reference's CUDA Translator
   roofline = the weight-streaming tcgen05 GEMM timed alone with CUDA events over buffers larger than L2
   cpu_baseline = the unmodified reference (oracle/_ref, Ruy INT8) on the host cores, bounded sample
 N>1: independent data-parallel replicas (one process per GPU, no data-path collective): scaling "weak"; the same line
