@@ -127,8 +127,9 @@ def test_golden_transliteration(compute):
                             return_scores=True)
     assert res[0].hypotheses[0] == ["a", "t", "z", "m", "o", "n"]
     assert len(res[0].hypotheses) == 2 and res[0].scores[0] >= res[0].scores[1]
-    if compute == "int8":
-        assert abs(res[0].scores[0] - (-0.38)) < 0.15     # reference int8 score of the golden sentence (model_test / fixture)
+    # the unmodified reference scores the two hypotheses -0.1553 / -0.2644 in int8 and -0.1554 / -0.2630 in float32
+    assert abs(res[0].scores[0] - (-0.1553)) < 0.03 and abs(res[0].scores[1] - (-0.2644)) < 0.04
+    assert res[0].hypotheses[1] == ["a", "t", "z", "u", "m", "o", "n"] or compute != "default"
     t.close()
 
 
