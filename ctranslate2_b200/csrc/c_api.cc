@@ -7,6 +7,7 @@
 #include <string>
 
 #include "common.cuh"
+#include "host/beam.h"
 #include "host/engine.h"
 #include "host/translator.h"
 #include "kernels/kernels.h"
@@ -379,6 +380,39 @@ CT2B200_API int ct2b200_generate_batch_scores(ct2b200_generator* g, const int32_
     r.return_scores = true;
     r.length_penalty = length_penalty;
     g->impl->generate(r, out_ids, out_lens, out_scores);
+  });
+}
+
+CT2B200_API int ct2b200_generate_batch_beam(ct2b200_generator* g, const int32_t* prompt_ids, int64_t batch, int64_t prompt_len,
+                                int64_t max_length, int64_t min_length, const int32_t* end_ids, int num_end_ids,
+                                int return_end_token, int beam_size, float patience, float length_penalty, int num_hypotheses,
+                                int32_t* out_ids, int32_t* out_lens, float* out_scores) {
+  return guarded([&] {
+    CT2_REQUIRE(g && prompt_ids && out_ids && out_lens && out_scores, "generate_batch_beam: null argument");
+    std::vector<int32_t> lens(static_cast<size_t>(std::max<int64_t>(batch, 0)), static_cast<int32_t>(prompt_len));
+    GenerationRequest r;
+    r.prompt_ids = prompt_ids;
+    r.prompt_lens = lens.data();
+    r.batch = batch;
+    r.max_prompt_len = prompt_len;
+    r.max_length = max_length;
+    r.min_length = min_length;
+    r.end_ids.assign(end_ids, end_ids + (end_ids ? num_end_ids : 0));
+    r.return_end_token = return_end_token != 0;
+    r.beam_size = beam_size;
+    r.patience = patience;
+    r.length_penalty = length_penalty;
+    r.num_hypotheses = num_hypotheses;
+    const std::vector<TranslationHypotheses> res = g->impl->generate_beam(r);
+    for (int64_t b = 0; b < batch; ++b)
+      for (int h = 0; h < num_hypotheses; ++h) {
+        int32_t* dst = out_ids + (b * num_hypotheses + h) * max_length;
+        const bool have = h < static_cast<int>(res[b].tokens.size());
+        const int64_t len = have ? static_cast<int64_t>(res[b].tokens[h].size()) : 0;
+        for (int64_t i = 0; i < max_length; ++i) dst[i] = i < len ? res[b].tokens[h][i] : -1;
+        out_lens[b * num_hypotheses + h] = have ? static_cast<int32_t>(len) : -1;
+        out_scores[b * num_hypotheses + h] = have ? res[b].scores[h] : 0.f;
+      }
   });
 }
 

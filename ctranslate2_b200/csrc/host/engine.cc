@@ -3,6 +3,8 @@
 // src/decoding.cc, src/models/language_model.cc, src/generator.cc.
 #include "engine.h"
 
+#include "beam.h"
+
 #include "../kernels/gemm_decode_common.cuh"
 
 #include <cuda_profiler_api.h>
@@ -1011,6 +1013,38 @@ void LlamaDecoder::project_rows(const int32_t* rows_d, int64_t n, void* logits_o
   project(gathered_.ptr, n, logits_out_d);
 }
 
+void LlamaDecoder::reorder_cache(const int32_t* parent_d, int beam, int64_t rows, int64_t positions) {
+  CT2_REQUIRE(tp_.world == 1, "beam search does not run tensor parallel");
+  CT2_REQUIRE(rows <= max_batch_ && positions <= max_len_, "reorder_cache: exceeds the KV arena");
+  if (k_alt_.empty()) {
+    k_alt_.resize(mc_.num_layers);
+    v_alt_.resize(mc_.num_layers);
+    for (int l = 0; l < mc_.num_layers; ++l) {
+      k_alt_[l].alloc(k_cache_[l].bytes);
+      v_alt_[l].alloc(v_cache_[l].bytes);
+      // whole 64-key boxes are staged by the attention kernels: positions past the end must hold finite values
+      CT2_CUDA_CHECK(cudaMemsetAsync(k_alt_[l].ptr, 0, k_alt_[l].bytes, stream_));
+      CT2_CUDA_CHECK(cudaMemsetAsync(v_alt_[l].ptr, 0, v_alt_[l].bytes, stream_));
+    }
+  }
+  for (int l = 0; l < mc_.num_layers; ++l) {
+    launch_kv_gather(k_cache_[l].ptr, v_cache_[l].ptr, k_alt_[l].ptr, v_alt_[l].ptr, parent_d, beam, rows, heads_kv_, max_len_,
+                     mc_.head_dim, positions, dtype_, stream_);
+    std::swap(k_cache_[l], k_alt_[l]);
+    std::swap(v_cache_[l], v_alt_[l]);
+  }
+  cache_swapped_ = !cache_swapped_;
+}
+
+void LlamaDecoder::restore_cache_orientation() {
+  if (!cache_swapped_) return;
+  for (int l = 0; l < mc_.num_layers; ++l) {
+    std::swap(k_cache_[l], k_alt_[l]);
+    std::swap(v_cache_[l], v_alt_[l]);
+  }
+  cache_swapped_ = false;
+}
+
 void LlamaDecoder::forward_step(const int32_t* ids_d, const int32_t* lens_d, int64_t batch, void* logits_out_d) {
   CT2_REQUIRE(batch <= max_batch_, "forward_step: batch exceeds the KV arena");
   embed(ids_d, batch);
@@ -1235,6 +1269,71 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
     for (int64_t t = 0; t < r.max_length; ++t)
       out_ids[b * r.max_length + t] = t < static_cast<int64_t>(results[b].size()) ? results[b][t] : -1;
   }
+}
+
+// Generator::generate_batch with beam_size > 1.  The decoder-only engine keeps contiguous per-row caches (its attention kernels
+// stage whole 64-key boxes by TMA), so beams are reordered by re-gathering the rows into the second cache set after every step
+// (Decoder::update_state does the same on every cached tensor); the search itself is the device-resident one of beam.h.
+std::vector<TranslationHypotheses> Generator::generate_beam(const GenerationRequest& r) {
+  std::lock_guard<std::mutex> lock(mu_);
+  LlamaDecoder& d = *decoder_;
+  cudaStream_t st = d.stream();
+  const int64_t B = r.batch, P = r.max_prompt_len, L = r.max_length;
+  const int beam = r.beam_size;
+  const int64_t N = B * beam;
+  CT2_REQUIRE(B > 0 && beam >= 2 && beam <= 32, "generate_beam: beam_size must be in [2, 32]");
+  CT2_REQUIRE(N <= d.max_batch(), "generate_batch: batch x beam_size exceeds max_batch");
+  CT2_REQUIRE(r.num_hypotheses >= 1 && r.num_hypotheses <= beam, "num_hypotheses must be in [1, beam_size]");
+  CT2_REQUIRE(r.patience > 0.f && r.patience <= 2.f, "patience must be in (0, 2]");
+  CT2_REQUIRE(L >= 1 && r.min_length <= L, "min_length is greater than max_length");
+  CT2_REQUIRE(r.end_ids.size() <= 64, "at most 64 end tokens");
+  for (int64_t b = 0; b < B; ++b)
+    CT2_REQUIRE(r.prompt_lens[b] == P && P >= 1, "beam search needs prompts of equal length (at least the start token)");
+  CT2_REQUIRE(P + L <= d.max_length(), "generate_batch: prompt + max_length exceeds max_length of the KV arena");
+  if (!beam_) beam_ = std::make_unique<BeamSearchArena>();
+  beam_->ensure(B, beam, L, dtype_size(d.dtype()));
+  const int64_t V = d.config().vocab, fwd = P - 1;
+
+  // prompt pass on B rows, then replicate_state: rows b -> b * beam + k
+  int32_t* hp = host_pinned_;
+  for (int64_t b = 0; b < B; ++b)
+    for (int64_t t = 0; t < fwd; ++t) hp[b * fwd + t] = r.prompt_ids[b * P + t];
+  int32_t* hend = hp + B * fwd;
+  for (size_t i = 0; i < r.end_ids.size(); ++i) hend[i] = r.end_ids[i];
+  if (fwd > 0) {
+    CT2_CUDA_CHECK(cudaMemcpyAsync(prompt_d_.ptr, hp, B * fwd * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+    run_prefill(prompt_d_.as<int32_t>(), B, fwd);
+    d.reorder_cache(nullptr, beam, N, fwd);
+  }
+  if (!r.end_ids.empty())
+    CT2_CUDA_CHECK(cudaMemcpyAsync(beam_->end_ids.ptr, hend, r.end_ids.size() * 4, cudaMemcpyHostToDevice, st));
+  BeamState bs = beam_->state(B, beam, V, L, r.min_length, r.patience, r.length_penalty, r.num_hypotheses,
+                              static_cast<int>(r.end_ids.size()));
+  // every row of entry b starts from its last prompt token
+  std::vector<int32_t> start(N);
+  for (int64_t n = 0; n < N; ++n) start[n] = r.prompt_ids[(n / beam) * P + P - 1];
+  beam_->reset(bs, 0, d.dtype(), st);
+  CT2_CUDA_CHECK(cudaMemcpyAsync(beam_->next_ids.ptr, start.data(), N * 4, cudaMemcpyHostToDevice, st));
+  CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+
+  const char* poll_env = std::getenv("CT2B200_EOS_POLL");
+  const int64_t poll = std::max<int64_t>(1, poll_env ? std::atoll(poll_env) : 4);
+  const int64_t first_check = std::max<int64_t>(0, r.min_length);
+  for (int64_t s = 0; s < L; ++s) {
+    launch_fill_i32(lens_d_.as<int32_t>(), N, static_cast<int32_t>(fwd + s), st);
+    d.forward_step(beam_->next_ids.as<int32_t>(), lens_d_.as<int32_t>(), N, d.logits_buffer());
+    beam_->step(d.logits_buffer(), bs, d.dtype(), st);
+    if (s + 1 == L) break;
+    d.reorder_cache(beam_->parent.as<int32_t>(), beam, N, fwd + s + 1);
+    if (s >= first_check && (s - first_check) % poll == poll - 1) {
+      CT2_CUDA_CHECK(cudaMemcpyAsync(beam_->host, bs.num_finished, 4, cudaMemcpyDeviceToHost, st));
+      CT2_CUDA_CHECK(cudaStreamSynchronize(st));
+      if (*beam_->host >= B) break;
+    }
+  }
+  auto out = beam_->collect(bs, r.length_penalty, r.num_hypotheses, r.return_end_token ? std::vector<int32_t>{} : r.end_ids, st);
+  d.restore_cache_orientation();
+  return out;
 }
 
 void Generator::forward(const int32_t* ids_h, int64_t batch, int64_t time, bool log_probs, float* logits_h) {

@@ -137,6 +137,13 @@ class LlamaDecoder {
   // project rows (indices into the rows of the last forward_prefill) of the hidden state to the vocabulary
   void project_rows(const int32_t* rows_d, int64_t n, void* logits_out_d);
   void* logits_buffer() const { return logits_.ptr; }       // [max_batch, vocab] T
+  // Beam search on the contiguous per-row caches (Decoder::replicate_state / update_state, decoder.cc:33-139): the K/V rows are
+  // re-gathered into a second cache set (allocated on first use) and the two sets swap roles.
+  // parent_d == null: row r takes the first `positions` cached positions of row r / beam (replicate after the prompt pass);
+  // otherwise of row parent_d[r] (reorder after a search step).
+  void reorder_cache(const int32_t* parent_d, int beam, int64_t rows, int64_t positions);
+  // after a beam search: the primary cache set is the one captured CUDA graphs point to (contents are dead by then)
+  void restore_cache_orientation();
   // tensor parallel bootstrap (one process per GPU): this rank's exchange buffer as a cudaIpcMemHandle (64 bytes),
   // then the handles of all ranks in rank order
   int tp_size() const { return tp_.world; }
@@ -194,12 +201,15 @@ class LlamaDecoder {
   std::vector<LayerWeights> layers_;
   DeviceBuffer sin_, cos_;        // f32 [max_len, head_dim]
   std::vector<DeviceBuffer> k_cache_, v_cache_;   // per layer [max_batch, Hkv, max_len, D] T
+  std::vector<DeviceBuffer> k_alt_, v_alt_;       // beam search: the other cache set (reorder_cache swaps them)
+  bool cache_swapped_ = false;
 
   // activations (rows = max(chunk_rows, max_batch))
   DeviceBuffer x_, xq_, xs_, qkv_, attn_, h_, logits_, gathered_, attn_ws_;
   DeviceBuffer xn_, scratch_mn_, scratch_nk_;   // float/AWQ arms: normed activations, up-projection, dequantized weight
 };
 
+struct TranslationHypotheses;
 struct GenerationRequest {
   const int32_t* prompt_ids = nullptr;     // host [batch, max_prompt_len]
   const int32_t* prompt_lens = nullptr;    // host [batch]
@@ -208,6 +218,9 @@ struct GenerationRequest {
   bool return_end_token = false;
   bool return_scores = false;              // GenerationOptions::return_scores
   float length_penalty = 1.f;              // score / length^length_penalty (decoding.cc:189-203)
+  int beam_size = 1;                       // > 1: BeamSearch::search (generate_beam)
+  float patience = 1.f;
+  int num_hypotheses = 1;
 };
 
 class Generator {
@@ -217,6 +230,9 @@ class Generator {
   LlamaDecoder& decoder() { return *decoder_; }
   // Generator::generate_batch (greedy): fills out_ids [batch, max_length] (-1 padded) and out_lens.
   void generate(const GenerationRequest& req, int32_t* out_ids, int32_t* out_lens, float* out_scores = nullptr);
+  // Generator::generate_batch with beam_size > 1 (decoding.cc:425-720; prompt pass language_model.cc:217-238): prompts of equal
+  // length; per entry the best num_hypotheses hypotheses (end token stripped unless return_end_token) and their scores
+  std::vector<TranslationHypotheses> generate_beam(const GenerationRequest& req);
   // Generator::forward_batch
   void forward(const int32_t* ids_h, int64_t batch, int64_t time, bool log_probs, float* logits_h);
   void bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, int64_t warmup, float* prefill_ms,
@@ -237,6 +253,7 @@ class Generator {
   bool graph_scores_ = false;
   int32_t* host_pinned_ = nullptr;
   size_t host_pinned_elems_ = 0;
+  std::unique_ptr<struct BeamSearchArena> beam_;   // created by the first beam search
   cudaGraphExec_t graph_ = nullptr;
   int64_t graph_nodes_ = 0;
   int64_t graph_batch_ = -1, graph_min_len_ = -1;

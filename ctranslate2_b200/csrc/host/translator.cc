@@ -269,9 +269,6 @@ Translator::Translator(const std::string& model_dir, const ct2b200_generator_con
   };
   enc_positions_ = load_positions("encoder", enc_pos_);
   dec_positions_ = load_positions("decoder", dec_pos_);
-  end_ids_d_.alloc(64 * sizeof(int32_t));
-  counters_.alloc(64);
-  CT2_CUDA_CHECK(cudaMemset(counters_.ptr, 0, 64));
   SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
   CT2_CUDA_CHECK(cudaDeviceSynchronize());
 }
@@ -300,10 +297,11 @@ void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t 
   cap_src_ = std::max(cap_src_, src_len);
   cap_beam_ = std::max(cap_beam_, beam);
   cap_steps_ = std::max(cap_steps_, max_steps);
+  const size_t es = dtype_size(dtype_);
+  beam_.ensure(cap_batch_, cap_beam_, cap_steps_, es);          // same capacities: its stride is the K/V stride
   const int64_t B = cap_batch_, S = cap_src_, L = cap_steps_, N = B * cap_beam_;
   const int64_t R = std::max(B * S, N), d = mc_.d_model, F = mc_.ffn_dim, V = mc_.tgt_vocab;
   cap_rows_ = R;
-  const size_t es = dtype_size(dtype_);
   src_ids_.alloc(B * S * 4);
   src_lens_.alloc(B * 4);
   x_.alloc(R * d * es);
@@ -324,28 +322,13 @@ void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t 
     self_v_[l].alloc(N * L * d * es);
   }
   logits_.alloc(N * V * es);
-  cum_.alloc(N * es);
-  cand_scores_.alloc(B * 2 * cap_beam_ * es);
-  cand_ids_.alloc(B * 2 * cap_beam_ * 4);
-  ids_.alloc(N * 4);
-  finished_.alloc(B * 4);
-  top_done_.alloc(B * 4);
-  num_hyp_.alloc(B * 4);
-  alive_.alloc(2 * N * L * 4);
-  anc_.alloc(2 * N * L * 4);
-  CT2_CUDA_CHECK(cudaMemset(anc_.ptr, 0, anc_.bytes));
-  const int64_t maxh = 3 * cap_beam_;      // round(beam * patience) + beam with patience <= 2
-  hyp_tokens_.alloc(B * maxh * L * 4);
-  hyp_len_.alloc(B * maxh * 4);
-  hyp_score_.alloc(B * maxh * 4);
   if (mc_.whisper) {
     const int64_t frames = 2 * S;                        // conv2 halves the frames
     features_.alloc(B * mc_.n_mels * frames * 4);
     cols_.alloc(std::max(B * frames * mc_.n_mels * 3, B * S * d * 3) * es);
     conv_out_.alloc(B * frames * d * es);
   }
-  const size_t need = static_cast<size_t>(B) * S + B + static_cast<size_t>(B) * maxh * (L + 2) + B + 256 +
-                      static_cast<size_t>(N) * 16 + 8192;
+  const size_t need = static_cast<size_t>(B) * S + B + 64 + static_cast<size_t>(N) * 16 + 8192;
   if (need > host_pinned_elems_) {
     if (host_pinned_) cudaFreeHost(host_pinned_);
     CT2_CUDA_CHECK(cudaMallocHost(&host_pinned_, need * sizeof(int32_t)));
@@ -423,14 +406,14 @@ void Translator::decoder_step(int64_t rows, int beam, int64_t batch, int64_t S) 
   const int64_t d = mc_.d_model;
   const float scale = 1.f / std::sqrt(static_cast<float>(mc_.head_dim));
   const bool pre = mc_.dec_pre_norm;
-  const int32_t* step_ptr = counters_.as<int32_t>();
+  const int32_t* step_ptr = beam_.counters.as<int32_t>();
   launch_embed_pos(dec_emb_.weight.ptr, dec_emb_.kind == DenseWeights::INT8 ? dec_emb_.scale.as<float>() : nullptr,
-                   ids_.as<int32_t>(), rows, d, mc_.dec_emb_scale, dec_pos_.ptr, 1, step_ptr, mc_.start_from_zero_embedding, x_.ptr, dtype_,
+                   beam_.next_ids.as<int32_t>(), rows, d, mc_.dec_emb_scale, dec_pos_.ptr, 1, step_ptr, mc_.start_from_zero_embedding, x_.ptr, dtype_,
                    stream_);
   for (int l = 0; l < mc_.dec_layers; ++l) {
     DecoderLayerWeights& w = dec_[l];
     dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr);
-    launch_attention_beam_self(qkv_.ptr, self_k_[l].ptr, self_v_[l].ptr, anc_.as<int32_t>(), step_ptr, rows,
+    launch_attention_beam_self(qkv_.ptr, self_k_[l].ptr, self_v_[l].ptr, beam_.anc.as<int32_t>(), step_ptr, rows,
                                static_cast<int>(cap_steps_), mc_.num_heads, mc_.head_dim, scale, ctx_.ptr, dtype_, stream_);
     dense(w.self.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
     if (!pre) post_norm(w.self.norm, x_.ptr, rows);
@@ -446,19 +429,11 @@ void Translator::decoder_step(int64_t rows, int beam, int64_t batch, int64_t S) 
   dense(projection_, mc_.has_dec_final_norm ? &dec_norm_ : nullptr, x_.ptr, rows, nullptr, -1, logits_.ptr);
 }
 
-// log-probabilities + cumulative scores, TopK of 2 * beam candidates per entry, bookkeeping (decoding.cc:536-700)
-void Translator::beam_step(const BeamState& bs) {
-  launch_beam_logprobs(logits_.ptr, cum_.ptr, bs, dtype_, stream_);
-  launch_topk(logits_.ptr, bs.batch, static_cast<int64_t>(bs.beam) * bs.vocab, 2 * bs.beam, cand_scores_.ptr,
-              cand_ids_.as<int32_t>(), dtype_, stream_);
-  launch_beam_update(bs, cand_scores_.ptr, cand_ids_.as<int32_t>(), cum_.ptr, dtype_, stream_);
-}
-
 void Translator::launch_or_capture_step(const BeamState& bs, int64_t S) {
   const int64_t rows = static_cast<int64_t>(bs.batch) * bs.beam;
   if (!use_graph_) {
     decoder_step(rows, bs.beam, bs.batch, S);
-    beam_step(bs);
+    beam_.step(logits_.ptr, bs, dtype_, stream_);
     return;
   }
   if (!graph_) {
@@ -467,7 +442,7 @@ void Translator::launch_or_capture_step(const BeamState& bs, int64_t S) {
     CT2_CUDA_CHECK(cudaStreamBeginCapture(stream_, cudaStreamCaptureModeThreadLocal));
     try {
       decoder_step(rows, bs.beam, bs.batch, S);
-      beam_step(bs);
+      beam_.step(logits_.ptr, bs, dtype_, stream_);
     } catch (...) {
       cudaStreamEndCapture(stream_, &g);
       if (g) cudaGraphDestroy(g);
@@ -488,44 +463,6 @@ void Translator::launch_or_capture_step(const BeamState& bs, int64_t S) {
 // =============================================================================================
 // the search (shared by translate_batch and Whisper::generate)
 // =============================================================================================
-BeamState Translator::beam_state(int64_t batch, int beam, int64_t max_steps, int64_t min_length, float patience,
-                                 float length_penalty, int num_hypotheses, int num_end) {
-  BeamState bs;
-  bs.batch = static_cast<int>(batch);
-  bs.beam = beam;
-  bs.vocab = static_cast<int>(mc_.tgt_vocab);
-  bs.stride = static_cast<int>(cap_steps_);
-  bs.max_steps = static_cast<int>(max_steps);
-  bs.max_hyp = static_cast<int>(3 * cap_beam_);
-  bs.min_length = static_cast<int>(min_length);
-  bs.max_candidates = std::max(1, static_cast<int>(std::lround(beam * patience)));   // decoding.cc:415-418
-  bs.num_hypotheses = num_hypotheses;
-  bs.early_exit = length_penalty == 0.f ? 1 : 0;
-  bs.num_end = num_end;
-  bs.end_ids = end_ids_d_.as<int32_t>();
-  bs.step = counters_.as<int32_t>();
-  bs.ticket = bs.step + 1;
-  bs.num_finished = bs.step + 2;
-  bs.finished = finished_.as<int32_t>();
-  bs.top_done = top_done_.as<int32_t>();
-  bs.num_hyp = num_hyp_.as<int32_t>();
-  bs.alive = alive_.as<int32_t>();
-  bs.anc = anc_.as<int32_t>();
-  bs.next_ids = ids_.as<int32_t>();
-  bs.hyp_tokens = hyp_tokens_.as<int32_t>();
-  bs.hyp_len = hyp_len_.as<int32_t>();
-  bs.hyp_score = hyp_score_.as<float>();
-  return bs;
-}
-
-void Translator::reset_search(const BeamState& bs, int32_t start_id) {
-  CT2_CUDA_CHECK(cudaMemsetAsync(counters_.ptr, 0, 64, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(finished_.ptr, 0, bs.batch * 4, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(top_done_.ptr, 0, bs.batch * 4, stream_));
-  CT2_CUDA_CHECK(cudaMemsetAsync(num_hyp_.ptr, 0, bs.batch * 4, stream_));
-  launch_beam_init(cum_.ptr, ids_.as<int32_t>(), static_cast<int64_t>(bs.batch) * bs.beam, bs.beam, start_id, dtype_, stream_);
-}
-
 // the decoding loop: one captured step per position; the host only polls the "finished entries" counter
 void Translator::run_search(const BeamState& bs, int64_t S, int64_t first_check) {
   // everything the captured step bakes in (kernel arguments are values)
@@ -541,7 +478,7 @@ void Translator::run_search(const BeamState& bs, int64_t S, int64_t first_check)
   }
   const char* poll_env = std::getenv("CT2B200_EOS_POLL");
   const int64_t poll = std::max<int64_t>(1, poll_env ? std::atoll(poll_env) : 4);
-  int32_t* hfin = host_pinned_ + host_pinned_elems_ - 16;
+  int32_t* hfin = beam_.host;
   for (int64_t s = 0; s < bs.max_steps; ++s) {
     launch_or_capture_step(bs, S);
     if (s + 1 == bs.max_steps) break;
@@ -551,42 +488,6 @@ void Translator::run_search(const BeamState& bs, int64_t S, int64_t first_check)
       if (*hfin >= bs.batch) break;
     }
   }
-}
-
-// finalize_result (decoding.cc:189-254) on the host: normalise, sort, keep num_hypotheses, strip `strip_ids` from the tail
-std::vector<TranslationHypotheses> Translator::collect(const BeamState& bs, float length_penalty, int num_hypotheses,
-                                                       const std::vector<int32_t>& strip_ids) {
-  const int64_t B = bs.batch, maxh = bs.max_hyp, stride = bs.stride;
-  int32_t* h_nh = host_pinned_;
-  int32_t* h_len = h_nh + B;
-  float* h_score = reinterpret_cast<float*>(h_len + B * maxh);
-  int32_t* h_tok = h_len + 2 * B * maxh;
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_nh, num_hyp_.ptr, B * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_len, hyp_len_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_score, hyp_score_.ptr, B * maxh * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(h_tok, hyp_tokens_.ptr, B * maxh * stride * 4, cudaMemcpyDeviceToHost, stream_));
-  CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
-  std::vector<TranslationHypotheses> out(B);
-  for (int64_t b = 0; b < B; ++b) {
-    const int nh = h_nh[b];
-    std::vector<float> sc(nh);
-    for (int j = 0; j < nh; ++j) {
-      const float len = static_cast<float>(h_len[b * maxh + j]);
-      sc[j] = h_score[b * maxh + j] / std::pow(len, length_penalty);
-    }
-    std::vector<int> order(nh);
-    std::iota(order.begin(), order.end(), 0);
-    std::stable_sort(order.begin(), order.end(), [&](int a, int c) { return sc[a] > sc[c]; });
-    if (static_cast<int>(order.size()) > num_hypotheses) order.resize(num_hypotheses);
-    for (int j : order) {
-      const int32_t* t = h_tok + (b * maxh + j) * stride;
-      std::vector<int32_t> toks(t, t + h_len[b * maxh + j]);
-      while (!toks.empty() && std::find(strip_ids.begin(), strip_ids.end(), toks.back()) != strip_ids.end()) toks.pop_back();
-      out[b].tokens.push_back(std::move(toks));
-      out[b].scores.push_back(sc[j]);
-    }
-  }
-  return out;
 }
 
 // =============================================================================================
@@ -624,18 +525,18 @@ std::vector<TranslationHypotheses> Translator::translate(const TranslationReques
   CT2_CUDA_CHECK(cudaMemcpyAsync(src_ids_.ptr, hp, B * S * 4, cudaMemcpyHostToDevice, stream_));
   CT2_CUDA_CHECK(cudaMemcpyAsync(src_lens_.ptr, hl, B * 4, cudaMemcpyHostToDevice, stream_));
   if (!r.end_ids.empty())
-    CT2_CUDA_CHECK(cudaMemcpyAsync(end_ids_d_.ptr, hend, r.end_ids.size() * 4, cudaMemcpyHostToDevice, stream_));
+    CT2_CUDA_CHECK(cudaMemcpyAsync(beam_.end_ids.ptr, hend, r.end_ids.size() * 4, cudaMemcpyHostToDevice, stream_));
 
   // ---- encoder + memory projections ----
   run_encoder(B, S);
   project_memory(B, S);
 
   // ---- beam search: the earliest step at which an entry can be complete is min_decoding_length ----
-  BeamState bs = beam_state(B, beam, L, r.min_decoding_length, r.patience, r.length_penalty, r.num_hypotheses,
-                            static_cast<int>(r.end_ids.size()));
-  reset_search(bs, r.start_id);
+  BeamState bs = beam_.state(B, beam, mc_.tgt_vocab, L, r.min_decoding_length, r.patience, r.length_penalty, r.num_hypotheses,
+                             static_cast<int>(r.end_ids.size()));
+  beam_.reset(bs, r.start_id, dtype_, stream_);
   run_search(bs, S, std::max<int64_t>(0, r.min_decoding_length));
-  return collect(bs, r.length_penalty, r.num_hypotheses, r.return_end_token ? std::vector<int32_t>{} : r.end_ids);
+  return beam_.collect(bs, r.length_penalty, r.num_hypotheses, r.return_end_token ? std::vector<int32_t>{} : r.end_ids, stream_);
 }
 
 void Translator::encode(const int32_t* ids_h, const int32_t* lens_h, int64_t batch, int64_t S, float* memory_h) {
@@ -667,7 +568,7 @@ void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t step
   for (size_t i = 0; i < ids.size(); ++i) ids[i] = static_cast<int32_t>((7919ull * i + 3) % mc_.src_vocab);
   CT2_CUDA_CHECK(cudaMemcpy(src_ids_.ptr, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
   CT2_CUDA_CHECK(cudaMemcpy(src_lens_.ptr, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice));
-  BeamState bs = beam_state(batch, beam, L, 0, 1.f, 1.f, 1, 0);      // no end token: nothing finishes before the last step
+  BeamState bs = beam_.state(batch, beam, mc_.tgt_vocab, L, 0, 1.f, 1.f, 1, 0);   // no end token: nothing finishes early
   std::vector<int64_t> key = {-1, batch, beam, source_len, bs.stride, L};
   if (key != graph_key_) {
     if (graph_) {
@@ -688,7 +589,7 @@ void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t step
   run_encoder(batch, source_len);
   project_memory(batch, source_len);
   cudaEventRecord(e1, stream_);
-  reset_search(bs, 1);
+  beam_.reset(bs, 1, dtype_, stream_);
   for (int64_t s = 0; s < warmup; ++s) launch_or_capture_step(bs, source_len);
   CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
   const int64_t l0 = g_kernel_launches.load();
@@ -784,7 +685,7 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
   suppress_d_.alloc((nsup + 1) * 4);
   CT2_CUDA_CHECK(cudaMemcpyAsync(forced_d_.ptr, hp, P * N * 4, cudaMemcpyHostToDevice, stream_));
   CT2_CUDA_CHECK(cudaMemcpyAsync(suppress_d_.ptr, hs, (nsup + 1) * 4, cudaMemcpyHostToDevice, stream_));
-  CT2_CUDA_CHECK(cudaMemcpyAsync(end_ids_d_.ptr, suppress_d_.as<int32_t>() + nsup, 4, cudaMemcpyDeviceToDevice, stream_));
+  CT2_CUDA_CHECK(cudaMemcpyAsync(beam_.end_ids.ptr, suppress_d_.as<int32_t>() + nsup, 4, cudaMemcpyDeviceToDevice, stream_));
   std::vector<int32_t> lens(B, static_cast<int32_t>(S));
   CT2_CUDA_CHECK(cudaMemcpyAsync(src_lens_.ptr, lens.data(), B * 4, cudaMemcpyHostToDevice, stream_));
   CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));      // `lens` and the pinned staging are reused below
@@ -794,15 +695,15 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
   project_memory(B, S);
 
   // ---- prompt: WhisperDecoder::forward_prompt on prompt[:-1], one position per step, no search ----
-  BeamState bs = beam_state(B, beam, steps, 0, r.patience, r.length_penalty, r.num_hypotheses, 1);
+  BeamState bs = beam_.state(B, beam, mc_.tgt_vocab, steps, 0, r.patience, r.length_penalty, r.num_hypotheses, 1);
   bs.start_step = static_cast<int>(start_step);
   bs.include_eos = 0;                                  // whisper.cc:309
   bs.num_disable = static_cast<int>(r.suppress_ids.size());
   bs.num_begin = static_cast<int>(r.suppress_ids_begin.size());
   bs.disable_ids = suppress_d_.as<int32_t>();
   bs.disable_begin = suppress_d_.as<int32_t>() + r.suppress_ids.size();
-  reset_search(bs, r.prompts[0]);
-  CT2_CUDA_CHECK(cudaMemcpyAsync(ids_.ptr, forced_d_.ptr, N * 4, cudaMemcpyDeviceToDevice, stream_));
+  beam_.reset(bs, r.prompts[0], dtype_, stream_);
+  CT2_CUDA_CHECK(cudaMemcpyAsync(beam_.next_ids.ptr, forced_d_.ptr, N * 4, cudaMemcpyDeviceToDevice, stream_));
   no_speech_d_.alloc(B * 4);
   for (int64_t t = 0; t < start_step; ++t) {
     decoder_step(N, beam, B, S);
@@ -822,7 +723,7 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
     CT2_CUDA_CHECK(cudaMemcpyAsync(no_speech_h, no_speech_d_.ptr, B * 4, cudaMemcpyDeviceToHost, stream_));
     CT2_CUDA_CHECK(cudaStreamSynchronize(stream_));
   }
-  return collect(bs, r.length_penalty, r.num_hypotheses, {});
+  return beam_.collect(bs, r.length_penalty, r.num_hypotheses, {}, stream_);
 }
 
 }  // namespace ct2b200

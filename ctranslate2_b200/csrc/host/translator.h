@@ -9,6 +9,7 @@
 #include <string>
 #include <vector>
 
+#include "beam.h"
 #include "engine.h"
 
 namespace ct2b200 {
@@ -83,10 +84,6 @@ struct WhisperRequest {
   bool return_no_speech_prob = false;
 };
 
-struct TranslationHypotheses {            // per batch entry, best first
-  std::vector<std::vector<int32_t>> tokens;
-  std::vector<float> scores;
-};
 
 class Translator {
  public:
@@ -117,15 +114,9 @@ class Translator {
   void run_encoder(int64_t batch, int64_t S);
   void run_encoder_layers(int64_t batch, int64_t S, const int32_t* lens_d);
   void run_whisper_encoder(int64_t batch, int64_t frames);
-  BeamState beam_state(int64_t batch, int beam, int64_t max_steps, int64_t min_length, float patience, float length_penalty,
-                       int num_hypotheses, int num_end);
-  void reset_search(const BeamState& bs, int32_t start_id);
-  std::vector<TranslationHypotheses> collect(const BeamState& bs, float length_penalty, int num_hypotheses,
-                                             const std::vector<int32_t>& strip_ids);
   void run_search(const BeamState& bs, int64_t S, int64_t first_check);
   void project_memory(int64_t batch, int64_t S);
   void decoder_step(int64_t rows, int beam, int64_t batch, int64_t S);
-  void beam_step(const BeamState& bs);
   void launch_or_capture_step(const BeamState& bs, int64_t S);
 
   std::mutex mu_;                // translate / encode / bench are serialised per translator
@@ -147,11 +138,10 @@ class Translator {
   int cap_beam_ = 0;
   DeviceBuffer src_ids_, src_lens_, x_, xn_, xq_, xs_, qkv_, ctx_, h_, q_, memory_;
   std::vector<DeviceBuffer> mem_kv_, self_k_, self_v_;
-  DeviceBuffer logits_, cum_, cand_scores_, cand_ids_, ids_, end_ids_d_;
+  DeviceBuffer logits_;
+  BeamSearchArena beam_;         // search state: next ids, scores, histories, ancestry, hypotheses, counters
   DeviceBuffer features_, cols_, conv_out_, suppress_d_, forced_d_, no_speech_d_;   // Whisper
   int64_t cap_frames_ = 0;
-  DeviceBuffer counters_;        // step | ticket | num_finished
-  DeviceBuffer finished_, top_done_, num_hyp_, alive_, anc_, hyp_tokens_, hyp_len_, hyp_score_;
   int32_t* host_pinned_ = nullptr;
   size_t host_pinned_elems_ = 0;
 

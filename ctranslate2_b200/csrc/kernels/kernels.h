@@ -205,6 +205,7 @@ struct BeamState {
   int32_t* alive = nullptr;         // [2][N, stride] token history of the live beams (double-buffered by step parity)
   int32_t* anc = nullptr;           // [2][N, stride] cache slot holding position t of the row's history
   int32_t* next_ids = nullptr;      // [N] input ids of the next step
+  int32_t* parent = nullptr;        // [N] or null: the row each next beam continues (gather index of Decoder::update_state)
   int32_t* hyp_tokens = nullptr;    // [batch, max_hyp, stride]
   int32_t* hyp_len = nullptr;       // [batch, max_hyp]
   float* hyp_score = nullptr;       // [batch, max_hyp] cumulative log-probability (not normalised)
@@ -222,6 +223,11 @@ void launch_im2col(const void* x, bool x_is_f32, int64_t batch, int64_t Cin, int
 void launch_add_positions(void* x, const void* pos, int64_t rows, int64_t time, int64_t depth, int dtype, cudaStream_t st);
 void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, int dtype,
                         cudaStream_t st);
+// Decoder::update_state / replicate_state for the contiguous per-row caches of the decoder-only engine (decoder.cc:33-139):
+// dst[row] = src[parent[row]] (parent == null: src[row / beam]) for positions [0, positions) of every kv head;
+// caches [rows, Hkv, max_len, D] T
+void launch_kv_gather(const void* src_k, const void* src_v, void* dst_k, void* dst_v, const int32_t* parent, int beam, int64_t rows,
+                      int Hkv, int64_t max_len, int D, int64_t positions, int dtype, cudaStream_t st);
 // float32 Dense (true fp32 FMAs): c [m,n] = a [m,k] . b [n,k]^T with bias / activation / residual
 void gemm_f32(const float* A, const float* B, const float* bias, const float* residual, int act, int64_t M, int64_t N,
               int64_t K, float* C, cudaStream_t st);

@@ -4,6 +4,7 @@
 // batch entry), and the device side of BeamSearch::search: log-softmax + cumulative scores, candidate bookkeeping,
 // hypothesis registration and the beam reindex as an index remap (no K/V bytes move when beams are reordered).
 // Reference kernels / functions these replace are cited per kernel (paths relative to the reference tree).
+#include <algorithm>
 #include <cfloat>
 
 #include "../common.cuh"
@@ -357,6 +358,7 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
       alive_w[row * L + rel] = s_word[c];
       anc_w[row * L + step] = static_cast<int32_t>(parent);
       st.next_ids[row] = s_word[c];
+      if (st.parent) st.parent[row] = static_cast<int32_t>(parent);
       cum[row] = from_f32<T>(s_score[c]);
     }
   }
@@ -434,6 +436,19 @@ __global__ void add_positions_kernel(T* __restrict__ x, const T* __restrict__ po
   const int64_t r = blockIdx.x, t = r % time;
   for (int64_t j = threadIdx.x; j < depth; j += blockDim.x)
     x[r * depth + j] = from_f32<T>(to_f32(x[r * depth + j]) + to_f32(pos[t * depth + j]));
+}
+
+// rows of a contiguous K/V cache re-gathered after a search step (or replicated beam times after the prompt pass)
+__global__ void kv_gather_kernel(const uint4* __restrict__ src_k, const uint4* __restrict__ src_v, uint4* __restrict__ dst_k,
+                                 uint4* __restrict__ dst_v, const int32_t* __restrict__ parent, int beam, int Hkv,
+                                 int64_t head_stride16, int64_t copy16) {
+  const int64_t row = blockIdx.x / Hkv, h = blockIdx.x % Hkv;
+  const int64_t from = parent ? parent[row] : row / beam;
+  const int64_t so = (from * Hkv + h) * head_stride16, dof = (row * Hkv + h) * head_stride16;
+  for (int64_t i = threadIdx.x + static_cast<int64_t>(blockIdx.y) * blockDim.x; i < copy16; i += static_cast<int64_t>(blockDim.x) * gridDim.y) {
+    dst_k[dof + i] = src_k[so + i];
+    dst_v[dof + i] = src_v[so + i];
+  }
 }
 
 // initialize_beam_scores (decoding.cc:84-93): beam 0 of every entry starts at 0, the others at the lowest T
@@ -656,6 +671,19 @@ void launch_beam_update(const BeamState& s, const void* cand_scores, const int32
   CT2_REQUIRE(s.beam >= 1 && s.beam <= 32, "beam_size must be in [1, 32]");
   CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_update_kernel<T>, dim3(s.batch), dim3(128), 0, st, s,
                                         static_cast<const T*>(cand_scores), cand_ids, static_cast<T*>(cum))));
+  check_launch();
+}
+
+void launch_kv_gather(const void* src_k, const void* src_v, void* dst_k, void* dst_v, const int32_t* parent, int beam, int64_t rows,
+                      int Hkv, int64_t max_len, int D, int64_t positions, int dtype, cudaStream_t st) {
+  if (rows == 0 || positions == 0) return;
+  const size_t es = dtype_size(dtype);
+  CT2_REQUIRE((static_cast<size_t>(D) * es) % 16 == 0, "kv_gather: head rows must be multiples of 16 bytes");
+  const int64_t head_stride16 = max_len * D * es / 16, copy16 = positions * D * es / 16;
+  const int chunks = static_cast<int>(std::min<int64_t>(8, (copy16 + 255) / 256));
+  kv_gather_kernel<<<dim3(static_cast<unsigned>(rows * Hkv), chunks), 256, 0, st>>>(
+      static_cast<const uint4*>(src_k), static_cast<const uint4*>(src_v), static_cast<uint4*>(dst_k), static_cast<uint4*>(dst_v),
+      parent, beam, Hkv, head_stride16, copy16);
   check_launch();
 }
 

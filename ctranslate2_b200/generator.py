@@ -176,11 +176,15 @@ class Generator:
                        return_end_token: bool = False, return_scores: bool = False, length_penalty: float = 1.0,
                        **unsupported) -> List[GenerationResult]:
         """start_tokens: list of token-string lists, or list of id lists / int array [batch, len]."""
-        if beam_size != 1 or sampling_topk != 1:
-            raise ValueError("this engine implements greedy search (beam_size=1, sampling_topk=1)")
+        if sampling_topk != 1:
+            raise ValueError("this engine implements best-candidate search (sampling_topk=1)")
+        if beam_size < 1:
+            raise ValueError("The beam size must be > 0")
         if include_prompt_in_result:
             raise ValueError("include_prompt_in_result=True forces the prompt through the decode loop token by "
                              "token (decoding.cc:21-67); pass False (docs/performance.md)")
+        patience = unsupported.pop("patience", 1) if beam_size > 1 else 1
+        num_hypotheses = unsupported.pop("num_hypotheses", 1) if beam_size > 1 else 1
         _check_options(unsupported, max_length, min_length)
         rows = [list(r) for r in start_tokens]
         if not rows:
@@ -195,6 +199,27 @@ class Generator:
         for b, r in enumerate(rows):
             ids[b, :len(r)] = r
         end_ids = np.array(self._end_ids(end_token), np.int32)
+        if beam_size > 1:
+            # BeamSearch::search on the device (ct2b200_generate_batch_beam): prompts of equal length
+            if int(lens.min()) != P:
+                raise ValueError("beam search needs prompts of equal length")
+            if not 1 <= num_hypotheses <= beam_size:
+                raise ValueError("The number of hypotheses cannot be greater than beam_size * patience")
+            hyp = np.empty((B, num_hypotheses, max_length), np.int32)
+            hyp_lens = np.empty((B, num_hypotheses), np.int32)
+            hyp_scores = np.zeros((B, num_hypotheses), np.float32)
+            p = ctypes.c_void_p
+            check(lib().ct2b200_generate_batch_beam(
+                p(self._h), ids.ctypes.data_as(p), ctypes.c_int64(B), ctypes.c_int64(P), ctypes.c_int64(max_length),
+                ctypes.c_int64(min_length), end_ids.ctypes.data_as(p), int(end_ids.size), int(return_end_token), int(beam_size),
+                ctypes.c_float(patience), ctypes.c_float(length_penalty), int(num_hypotheses), hyp.ctypes.data_as(p),
+                hyp_lens.ctypes.data_as(p), hyp_scores.ctypes.data_as(p)))
+            results = []
+            for b in range(B):
+                seqs = [hyp[b, h, :hyp_lens[b, h]].tolist() for h in range(num_hypotheses) if hyp_lens[b, h] >= 0]
+                results.append(GenerationResult([[self._tokens[i] for i in s] for s in seqs], seqs,
+                                                [float(hyp_scores[b, h]) for h in range(len(seqs))] if return_scores else []))
+            return results
         out = np.empty((B, max_length), np.int32)
         out_lens = np.empty(B, np.int32)
         scores = np.zeros(B, np.float32)

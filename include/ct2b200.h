@@ -274,6 +274,15 @@ CT2B200_API int ct2b200_generate_batch_scores(ct2b200_generator* g, const int32_
                            const int32_t* end_ids_h, int num_end_ids, int return_end_token, float length_penalty,
                            int32_t* out_ids_h, int32_t* out_lens_h, float* out_scores_h);
 
+/* Generator::generate_batch_async with beam_size > 1 (BeamSearch::search, src/decoding.cc:425-720; GenerationOptions beam_size,
+ * patience, length_penalty, num_hypotheses): prompts of equal length; out_ids_h [batch, num_hypotheses, max_length] (-1 padded),
+ * out_lens_h / out_scores_h [batch, num_hypotheses] (length -1 = fewer hypotheses than asked); batch * beam_size <= max_batch.
+ * Scores: cumulative log-probability / length^length_penalty, the end token counted (decoding.h:154). */
+CT2B200_API int ct2b200_generate_batch_beam(ct2b200_generator* g, const int32_t* prompt_ids_h, int64_t batch, int64_t prompt_len,
+                                int64_t max_length, int64_t min_length, const int32_t* end_ids_h, int num_end_ids,
+                                int return_end_token, int beam_size, float patience, float length_penalty, int num_hypotheses,
+                                int32_t* out_ids_h, int32_t* out_lens_h, float* out_scores_h);
+
 /* Generator::forward_batch_async(ids, return_log_probs) — full-sequence forward from position 0.
  * ids_h [batch, time] int32 host; logits_h [batch, time, vocab] f32 host. */
 CT2B200_API int ct2b200_forward_batch(ct2b200_generator* g, const int32_t* ids_h, int64_t batch, int64_t time,
