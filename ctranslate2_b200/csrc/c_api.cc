@@ -609,7 +609,8 @@ CT2B200_API int ct2b200_whisper_generate(ct2b200_translator* t, const float* fea
                              const int32_t* prompts, int64_t prompt_len, int beam_size, float patience, float length_penalty,
                              int64_t max_length, int num_hypotheses, const int32_t* suppress_ids, int num_suppress,
                              const int32_t* suppress_begin, int num_begin, int32_t sot_id, int32_t eot_id, int32_t no_speech_id,
-                             int32_t* out_ids, int32_t* out_lens, float* out_scores, float* no_speech) {
+                             int32_t no_timestamps_id, int max_initial_timestamp_index, int32_t* out_ids, int32_t* out_lens,
+                             float* out_scores, float* no_speech) {
   return guarded([&] {
     CT2_REQUIRE(t && features && prompts && out_ids && out_lens && out_scores, "whisper_generate: null argument");
     WhisperRequest r;
@@ -628,6 +629,8 @@ CT2B200_API int ct2b200_whisper_generate(ct2b200_translator* t, const float* fea
     r.sot_id = sot_id;
     r.eot_id = eot_id;
     r.no_speech_id = no_speech_id;
+    r.no_timestamps_id = no_timestamps_id;
+    r.max_initial_timestamp_index = max_initial_timestamp_index;
     const std::vector<TranslationHypotheses> res = t->impl->whisper_generate(r, no_speech);
     for (int64_t b = 0; b < batch; ++b)
       for (int h = 0; h < num_hypotheses; ++h) {

@@ -468,7 +468,7 @@ void Translator::run_search(const BeamState& bs, int64_t S, int64_t first_check)
   // everything the captured step bakes in (kernel arguments are values)
   std::vector<int64_t> key = {bs.batch, bs.beam, S, bs.stride, bs.max_steps, bs.min_length, bs.max_hyp, bs.max_candidates,
                               bs.num_hypotheses, bs.early_exit, bs.num_end, bs.start_step, bs.include_eos, bs.num_disable,
-                              bs.num_begin};
+                              bs.num_begin, bs.ts_begin, bs.ts_end, bs.ts_eot, bs.ts_no_timestamps, bs.ts_max_initial};
   if (key != graph_key_) {
     if (graph_) {
       cudaGraphExecDestroy(graph_);
@@ -649,10 +649,10 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
   CT2_REQUIRE(r.num_hypotheses >= 1 && r.num_hypotheses <= beam, "num_hypotheses must be in [1, beam_size]");
   CT2_REQUIRE(r.patience > 0.f && r.patience <= 2.f, "patience must be in (0, 2]");
   CT2_REQUIRE(r.suppress_ids.size() + r.suppress_ids_begin.size() <= 4096, "too many suppressed tokens");
-  // check_prompts (whisper.cc:168-197): <|startoftranscript|> at the same position in every prompt; this engine also requires
-  // the prompt to END with the task tokens (no text after them) and does not implement the timestamp rules, so the last
-  // task token must be <|notimestamps|> — the token right below the timestamps in the vocabulary
-  CT2_REQUIRE(P >= 2 && P <= 16, "the prompt must hold <|startoftranscript|> and the task tokens (2 to 16 tokens)");
+  // check_prompts (whisper.cc:168-197): <|startoftranscript|> at the same position in every prompt and the same number of
+  // task tokens after it; this engine also requires the prompt to END with the task tokens (no text after them)
+  CT2_REQUIRE(P >= 1 && P <= 16, "the prompt must hold <|startoftranscript|> and the task tokens (1 to 16 tokens)");
+  CT2_REQUIRE(r.no_timestamps_id > r.sot_id && r.no_timestamps_id < mc_.tgt_vocab - 1, "no_timestamps_id must follow sot_id");
   int64_t sot_index = -1;
   for (int64_t b = 0; b < B; ++b) {
     int64_t idx = -1;
@@ -664,7 +664,11 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
     CT2_REQUIRE(idx >= 0, "<|startoftranscript|> token was not found in the prompt");
     CT2_REQUIRE(sot_index < 0 || idx == sot_index, "<|startoftranscript|> must be at the same position in all prompts");
     sot_index = idx;
+    for (int64_t t = idx; t < P; ++t)                  // get_prompt_length (whisper.cc:156-166)
+      CT2_REQUIRE(r.prompts[b * P + t] >= r.sot_id && r.prompts[b * P + t] <= r.no_timestamps_id,
+                  "text after the task tokens (a decoding prefix) is not supported");
   }
+  bool timestamps = r.prompts[P - 1] != r.no_timestamps_id;             // whisper.cc:325, decided on the first prompt
   const int64_t start_step = P - 1;
   const int64_t steps = std::min<int64_t>(r.max_length / 2, r.max_length - start_step);      // whisper.cc:299
   CT2_REQUIRE(steps >= 1, "max_length is too small for the prompt");
@@ -702,6 +706,13 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
   bs.num_begin = static_cast<int>(r.suppress_ids_begin.size());
   bs.disable_ids = suppress_d_.as<int32_t>();
   bs.disable_begin = suppress_d_.as<int32_t>() + r.suppress_ids.size();
+  if (timestamps) {
+    bs.ts_begin = r.no_timestamps_id + 1;
+    bs.ts_end = static_cast<int>(mc_.tgt_vocab) - 1;
+    bs.ts_eot = r.eot_id;
+    bs.ts_no_timestamps = r.no_timestamps_id;
+    bs.ts_max_initial = bs.ts_begin + r.max_initial_timestamp_index;
+  }
   beam_.reset(bs, r.prompts[0], dtype_, stream_);
   CT2_CUDA_CHECK(cudaMemcpyAsync(beam_.next_ids.ptr, forced_d_.ptr, N * 4, cudaMemcpyDeviceToDevice, stream_));
   no_speech_d_.alloc(B * 4);

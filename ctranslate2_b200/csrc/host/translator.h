@@ -68,8 +68,9 @@ struct TranslationRequest {
   bool return_end_token = false;
 };
 
-// models::Whisper::generate (include/ctranslate2/models/whisper.h:11-60, src/models/whisper.cc:241-390), prompts made of
-// <|startoftranscript|> and task tokens ending with <|notimestamps|> (the timestamp rules are not implemented)
+// models::Whisper::generate (include/ctranslate2/models/whisper.h:11-60, src/models/whisper.cc:232-390), prompts made of
+// previous-text tokens, <|startoftranscript|> and the task tokens (no text after them); the timestamp rules
+// (whisper.cc:742-860) apply unless the last task token is <|notimestamps|>
 struct WhisperRequest {
   const float* features = nullptr;        // host [batch, n_mels, frames] f32
   int64_t batch = 0, frames = 0;
@@ -80,7 +81,8 @@ struct WhisperRequest {
   int64_t max_length = 448;
   int num_hypotheses = 1;
   std::vector<int32_t> suppress_ids, suppress_ids_begin;
-  int32_t sot_id = 0, eot_id = 0, no_speech_id = -1;
+  int32_t sot_id = 0, eot_id = 0, no_speech_id = -1, no_timestamps_id = -1;
+  int max_initial_timestamp_index = 50;
   bool return_no_speech_prob = false;
 };
 

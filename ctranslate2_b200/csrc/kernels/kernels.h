@@ -195,6 +195,8 @@ struct BeamState {
   int num_disable = 0, num_begin = 0;
   const int32_t* disable_ids = nullptr;     // SuppressTokens: disabled at every step
   const int32_t* disable_begin = nullptr;   // SuppressTokensBegin: disabled at the first search step
+  // Whisper's ApplyTimestampRules (src/models/whisper.cc:742-860); ts_begin = 0 disables them
+  int ts_begin = 0, ts_end = 0, ts_eot = 0, ts_no_timestamps = 0, ts_max_initial = 0;
   const int32_t* end_ids = nullptr;
   int32_t* step = nullptr;          // [1] current step, advanced by the update kernel
   int32_t* ticket = nullptr;        // [1]

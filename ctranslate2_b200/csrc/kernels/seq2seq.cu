@@ -229,27 +229,83 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
 // Step 1 per row of [B*beam, V]: DisableTokens of the end ids while step < min_length (apply_min_length, decoding.cc:60-81),
 // ops::LogSoftMax in fp32 -> T, then primitives::add_depth_broadcast of the beam's cumulative score IN T (decoding.cc:548-553).
 template <typename T>
-__global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logits, int64_t vocab, const T* __restrict__ cum,
-                                                            const int32_t* __restrict__ step_ptr, int start_step, int min_length,
-                                                            const int32_t* __restrict__ end_ids, int num_end,
-                                                            const int32_t* __restrict__ disable_ids, int num_disable,
-                                                            const int32_t* __restrict__ disable_begin, int num_begin) {
+__global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logits, const T* __restrict__ cum, BeamState st) {
   __shared__ float red[32];
+  __shared__ int s_check;
   griddep_launch();
   griddep_wait();
-  const int64_t row = blockIdx.x;
+  const int64_t row = blockIdx.x, vocab = st.vocab;
   T* xr = logits + row * vocab;
-  const int step = *step_ptr - start_step;             // steps of the search (the prompt was forwarded before)
+  const int abs_step = *st.step;
+  const int step = abs_step - st.start_step;           // steps of the search (the prompt was forwarded before)
   const T lowest = from_f32<T>(lowest_of<T>());
+  auto disable_range = [&](int lo, int hi) {           // [lo, hi)
+    for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) xr[j] = lowest;
+  };
   // DisableTokens (decoding_utils.h:20-60): end ids below min_length, SuppressTokens, SuppressTokensBegin at the first step
-  if (step < min_length)
-    for (int e = threadIdx.x; e < num_end; e += blockDim.x)
-      if (end_ids[e] >= 0 && end_ids[e] < vocab) xr[end_ids[e]] = lowest;
-  for (int e = threadIdx.x; e < num_disable; e += blockDim.x)
-    if (disable_ids[e] >= 0 && disable_ids[e] < vocab) xr[disable_ids[e]] = lowest;
+  if (step < st.min_length)
+    for (int e = threadIdx.x; e < st.num_end; e += blockDim.x)
+      if (st.end_ids[e] >= 0 && st.end_ids[e] < vocab) xr[st.end_ids[e]] = lowest;
+  for (int e = threadIdx.x; e < st.num_disable; e += blockDim.x)
+    if (st.disable_ids[e] >= 0 && st.disable_ids[e] < vocab) xr[st.disable_ids[e]] = lowest;
   if (step == 0)
-    for (int e = threadIdx.x; e < num_begin; e += blockDim.x)
-      if (disable_begin[e] >= 0 && disable_begin[e] < vocab) xr[disable_begin[e]] = lowest;
+    for (int e = threadIdx.x; e < st.num_begin; e += blockDim.x)
+      if (st.disable_begin[e] >= 0 && st.disable_begin[e] < vocab) xr[st.disable_begin[e]] = lowest;
+  if (st.ts_begin > 0) {
+    // ApplyTimestampRules (models/whisper.cc:764-838) on this row's history
+    const int64_t N = static_cast<int64_t>(st.batch) * st.beam;
+    const int32_t* hist = st.alive + static_cast<int64_t>(abs_step & 1) * N * st.stride + row * st.stride;
+    if (threadIdx.x == 0) {
+      s_check = 0;
+      xr[st.ts_no_timestamps] = lowest;
+    }
+    __syncthreads();
+    if (step == 0) {
+      disable_range(0, st.ts_begin);                                   // a timestamp comes first,
+      disable_range(st.ts_max_initial + 1, st.ts_end + 1);             // not later than max_initial_timestamp
+    } else {
+      const int last = hist[step - 1];
+      if (last >= st.ts_begin) {
+        const int penult = step - 1 > 0 ? hist[step - 2] : last;
+        if (penult >= st.ts_begin) {
+          disable_range(st.ts_begin, st.ts_end + 1);                   // timestamps come in pairs: text has to follow
+        } else {
+          disable_range(0, st.ts_eot);                                 // text cannot follow a single timestamp
+          disable_range(st.ts_begin, last);
+          if (threadIdx.x == 0) s_check = 1;
+        }
+      } else {
+        if (threadIdx.x == 0) s_check = 1;
+        int prev = -1;                                                 // timestamps do not decrease
+        for (int t = step - 1; t >= 0; --t)
+          if (hist[t] >= st.ts_begin) {
+            prev = hist[t];
+            break;
+          }
+        if (prev >= 0) disable_range(st.ts_begin, prev + 1);
+      }
+    }
+    __syncthreads();
+    if (s_check) {
+      // if the probability mass of the timestamps exceeds every text token, a timestamp is sampled (should_sample_timestamp)
+      float m = -INFINITY;
+      for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) m = fmaxf(m, to_f32(xr[j]));
+      m = block_reduce<true>(m, red);
+      float s = 0.f;
+      for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) s += expf(to_f32(xr[j]) - m);
+      s = block_reduce<false>(s, red);
+      const float logs = logf(s);
+      float tmax = -INFINITY, smax = -INFINITY;
+      for (int j = threadIdx.x; j < st.ts_begin; j += blockDim.x) tmax = fmaxf(tmax, round_to<T>(to_f32(xr[j]) - m - logs));
+      for (int j = st.ts_begin + threadIdx.x; j <= st.ts_end; j += blockDim.x) smax = fmaxf(smax, round_to<T>(to_f32(xr[j]) - m - logs));
+      tmax = block_reduce<true>(tmax, red);
+      smax = block_reduce<true>(smax, red);
+      float ssum = 0.f;
+      for (int j = st.ts_begin + threadIdx.x; j <= st.ts_end; j += blockDim.x) ssum += expf(round_to<T>(to_f32(xr[j]) - m - logs) - smax);
+      ssum = block_reduce<false>(ssum, red);
+      if (smax + logf(ssum) > tmax) disable_range(0, st.ts_begin);
+    }
+  }
   __syncthreads();
   float m = -INFINITY;
   for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) m = fmaxf(m, to_f32(xr[j]));
@@ -626,9 +682,7 @@ void launch_beam_logprobs(void* logits, const void* cum, const BeamState& s, int
   const int64_t rows = static_cast<int64_t>(s.batch) * s.beam;
   if (rows == 0) return;
   CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_logprobs_kernel<T>, dim3(rows), dim3(256), 0, st, static_cast<T*>(logits),
-                                        static_cast<int64_t>(s.vocab), static_cast<const T*>(cum), s.step, s.start_step,
-                                        s.min_length, s.end_ids, s.num_end, s.disable_ids, s.num_disable, s.disable_begin,
-                                        s.num_begin)));
+                                        static_cast<const T*>(cum), s)));
   check_launch();
 }
 

@@ -3,7 +3,8 @@
 Mirrors python/cpp/whisper.cc / include/ctranslate2/models/whisper.h: `encode(features)` and `generate(features, prompts, ...)`
 with the WhisperOptions of whisper.h:11-60.  Vocabulary lookups and the model's config.json (suppress_ids,
 suppress_ids_begin) are handled here, as WhisperReplica does (src/models/whisper.cc:61-92, 311-323).  Served prompts:
-`<|startoftranscript|>` + task tokens ending with `<|notimestamps|>`; the timestamp rules are not implemented."""
+previous-text tokens, `<|startoftranscript|>` and the task tokens (no text after them); the timestamp rules
+(whisper.cc:742-860) run on the device unless the prompt ends with `<|notimestamps|>`."""
 from __future__ import annotations
 
 import ctypes
@@ -107,8 +108,6 @@ class Whisper:
         P = len(rows[0])
         if any(len(r) != P for r in rows):
             raise ValueError("The generate method currently requires each batch to have the same number of task tokens")
-        if any(r[-1] != self.no_timestamps_id for r in rows):
-            raise ValueError("this engine does not implement the timestamp rules: prompts must end with <|notimestamps|>")
         suppress = []
         for t in suppress_tokens:
             if t >= 0:
@@ -128,7 +127,8 @@ class Whisper:
             p(self._h), f.ctypes.data_as(p), ctypes.c_int64(B), ctypes.c_int64(T), pr.ctypes.data_as(p), ctypes.c_int64(P),
             int(beam_size), ctypes.c_float(patience), ctypes.c_float(length_penalty), ctypes.c_int64(max_length),
             int(num_hypotheses), sup.ctypes.data_as(p), int(sup.size), beg.ctypes.data_as(p), int(beg.size),
-            ctypes.c_int32(self.sot_id), ctypes.c_int32(self.eot_id), ctypes.c_int32(self.no_speech_id), out.ctypes.data_as(p),
+            ctypes.c_int32(self.sot_id), ctypes.c_int32(self.eot_id), ctypes.c_int32(self.no_speech_id),
+            ctypes.c_int32(self.no_timestamps_id), int(max_initial_timestamp_index), out.ctypes.data_as(p),
             lens.ctypes.data_as(p), scores.ctypes.data_as(p), nsp.ctypes.data_as(p) if return_no_speech_prob else None))
         results = []
         for b in range(B):

@@ -345,8 +345,9 @@ CT2B200_API int ct2b200_bench_translate(ct2b200_translator* t, int64_t batch, in
  * Whisper: ctranslate2::models::Whisper — include/ctranslate2/models/whisper.h:86-190, src/models/whisper.cc,
  * WhisperEncoder / WhisperDecoder src/layers/whisper.cc, ops::Conv1D src/ops/conv1d_gpu.cu.  A WhisperSpec directory opens
  * with ct2b200_translator_open (same handle type; the encoder is the Conv1D front-end instead of source embeddings).
- * Served: encode, and generate for prompts made of <|startoftranscript|> + task tokens ending with <|notimestamps|> (the
- * timestamp rules of whisper.cc:395-520 are not implemented; detect_language / align are not provided).
+ * Served: encode, and generate for prompts made of previous-text tokens, <|startoftranscript|> and the task tokens (no text
+ * after them), with the timestamp rules (whisper.cc:742-860) unless the last task token is <|notimestamps|>;
+ * detect_language / align are not provided.
  * ------------------------------------------------------------------------------------------- */
 CT2B200_API int ct2b200_whisper_info(const ct2b200_translator* t, int* n_mels, int* max_frames, int* d_model, int* vocab_size);
 /* Whisper::encode: features_h [batch, n_mels, frames] f32 host -> memory_h [batch, (frames + 1) / 2, d_model] f32 host. */
@@ -361,8 +362,8 @@ CT2B200_API int ct2b200_whisper_generate(ct2b200_translator* t, const float* fea
                              const int32_t* prompts_h, int64_t prompt_len, int beam_size, float patience, float length_penalty,
                              int64_t max_length, int num_hypotheses, const int32_t* suppress_ids_h, int num_suppress,
                              const int32_t* suppress_begin_h, int num_begin, int32_t sot_id, int32_t eot_id,
-                             int32_t no_speech_id, int32_t* out_ids_h, int32_t* out_lens_h, float* out_scores_h,
-                             float* no_speech_h);
+                             int32_t no_speech_id, int32_t no_timestamps_id, int max_initial_timestamp_index,
+                             int32_t* out_ids_h, int32_t* out_lens_h, float* out_scores_h, float* no_speech_h);
 
 #ifdef __cplusplus
 }

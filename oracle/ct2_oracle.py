@@ -820,12 +820,14 @@ class WhisperOracle(Seq2SeqOracle):
 
     def generate(self, features: np.ndarray, prompts: np.ndarray, beam_size: int = 5, patience: float = 1.0,
                  num_hypotheses: int = 1, length_penalty: float = 1.0, max_length: int = 448, suppress_blank: bool = True,
-                 suppress_default: bool = True):
-        """prompts [B, P]: <|startoftranscript|> + task tokens ending with <|notimestamps|> (the timestamp rules are not
-        restated).  Returns (per entry [(tokens, score), ...] best first, no_speech_probs [B])."""
+                 suppress_default: bool = True, max_initial_timestamp_index: int = 50):
+        """prompts [B, P]: <|startoftranscript|> + task tokens (no text after them); ApplyTimestampRules (whisper.cc:742-860)
+        unless the last one is <|notimestamps|>.  Returns (per entry [(tokens, score), ...] best first, no_speech_probs [B])."""
         prompts = np.asarray(prompts)
         B, P = prompts.shape
-        assert P >= 2 and (prompts[:, -1] == self.no_timestamps).all(), "prompts must end with <|notimestamps|>"
+        assert P >= 2
+        timestamps = prompts[0, -1] != self.no_timestamps
+        ts_begin, ts_end = self.no_timestamps + 1, self.vocab - 1
         memory = self.encode_features(features)
         self.start(memory, np.full(B, memory.shape[1]), beam_size)
         no_speech = np.zeros(B, f32)
@@ -839,16 +841,59 @@ class WhisperOracle(Seq2SeqOracle):
         disable_begin = list(self.config.get("suppress_ids_begin", [])) if suppress_blank else []
         lowest = np.finfo(f32).min
 
+        state = {"seq": [[] for _ in range(B * beam_size)]}
+
         def hook(step, logits):                                  # SuppressTokens, SuppressTokensBegin (decoding_utils.cc:152-188)
             for t in disable:
                 logits[:, t] = lowest
             if step == 0:
                 for t in disable_begin:
                     logits[:, t] = lowest
+            if not timestamps:
+                return
+            check = []
+            for n in range(logits.shape[0]):                     # ApplyTimestampRules::apply, sample_begin = 0
+                seq = state["seq"][n]
+                logits[n, self.no_timestamps] = lowest
+                if step == 0:
+                    logits[n, :ts_begin] = lowest
+                    logits[n, ts_begin + max_initial_timestamp_index + 1:ts_end + 1] = lowest
+                else:
+                    last = seq[step - 1]
+                    if last >= ts_begin:
+                        penult = seq[step - 2] if step - 1 > 0 else last
+                        if penult >= ts_begin:
+                            logits[n, ts_begin:ts_end + 1] = lowest
+                        else:
+                            logits[n, :self.eot] = lowest
+                            logits[n, ts_begin:last] = lowest
+                            check.append(n)
+                    else:
+                        check.append(n)
+                        for t in range(step - 1, -1, -1):
+                            if seq[t] >= ts_begin:
+                                logits[n, ts_begin:seq[t] + 1] = lowest
+                                break
+            if check:
+                with np.errstate(over="ignore"):
+                    lp = softmax(logits, log=True)
+                for n in check:
+                    ts = lp[n, ts_begin:ts_end + 1]
+                    mx = ts.max()
+                    if f32(mx + np.log(np.exp(ts - mx, dtype=f32).sum(dtype=f32))) > lp[n, :ts_begin].max():
+                        logits[n, :ts_begin] = lowest
 
-        res = beam_search(lambda ids, s: self.step(ids, start_step + s), self.reorder, prompts[:, -1], self.vocab, beam_size,
-                          steps, 0, [self.eot], length_penalty, num_hypotheses, patience, include_eos_in_hypotheses=False,
-                          logits_hook=hook)
+        def step_fn(ids, s):
+            if s > 0:                                            # the search gathered the beams: ids are the new last tokens
+                state["seq"] = [state["seq"][g] + [int(t)] for g, t in zip(state["gather"], ids)]
+            return self.step(ids, start_step + s)
+
+        def reorder(index):
+            state["gather"] = [int(i) for i in index]
+            self.reorder(index)
+
+        res = beam_search(step_fn, reorder, prompts[:, -1], self.vocab, beam_size, steps, 0, [self.eot], length_penalty,
+                          num_hypotheses, patience, include_eos_in_hypotheses=False, logits_hook=hook)
         return res, no_speech
 
 

@@ -1,5 +1,6 @@
 """Whisper path on the GPU: ctranslate2_b200.Whisper — Conv1D front-end (im2col + float Dense), GELU encoder,
-cross-attention decoder, prompt forwarding and the device-resident search with SuppressTokens / SuppressTokensBegin —
+cross-attention decoder, prompt forwarding and the device-resident search with SuppressTokens / SuppressTokensBegin and the
+timestamp rules (ApplyTimestampRules, whisper.cc:742-860) —
 through the C-ABI, against the committed outputs of the UNMODIFIED reference's models::Whisper
 (tests/golden/whisper_ref.json) and the oracle run live.  float32: every token equal, scores to 2e-4; int8 / float16: the
 majority criterion of tests/test_gpu_translator.py (a d = 64 model amplifies single rounding flips)."""
@@ -82,7 +83,9 @@ def test_tokens_interface_and_errors():
     b = w.generate(x, [[w.sot_id, w.sot_id + 1, w._ids["<|transcribe|>"], w.no_timestamps_id]], beam_size=2)
     assert a[0].sequences_ids == b[0].sequences_ids and a[0].sequences[0] == [w._tokens[i] for i in a[0].sequences_ids[0]]
     with pytest.raises(ValueError):
-        w.generate(x, [[w.sot_id, w._ids["<|transcribe|>"]]])                 # timestamps would be required
+        w.generate(x, [[w.sot_id, w._ids["<|transcribe|>"], 5]])              # text after the task tokens (decoding prefix)
+    ts = w.generate(x, [[w.sot_id, w.sot_id + 1, w._ids["<|transcribe|>"]]], beam_size=2)[0].sequences_ids[0]
+    assert ts[0] > w.no_timestamps_id                                          # with timestamps the output starts with one
     with pytest.raises(ValueError):
         w.generate(inputs(1, 1, n_mels=8), [[w.sot_id, w.no_timestamps_id]])   # wrong number of mel bins
     with pytest.raises(ValueError):

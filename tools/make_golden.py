@@ -276,8 +276,9 @@ def make_seq2seq_fixture():
     print("seq2seq fixture:", sum(len(m["cases"]) for e in fixture.values() for m in e["models"].values()), "cases")
 
 
-WHISPER_CASES = [  # (beam, num_hypotheses, length_penalty, max_length, suppress_blank)
-    (1, 1, 1.0, 24, True), (3, 2, 1.0, 24, True), (5, 3, 1.0, 30, True), (5, 1, 0.0, 24, False), (2, 2, 0.7, 16, True)]
+WHISPER_CASES = [  # (beam, num_hypotheses, length_penalty, max_length, suppress_blank, timestamps)
+    (1, 1, 1.0, 24, True, False), (3, 2, 1.0, 24, True, False), (5, 3, 1.0, 30, True, False), (5, 1, 0.0, 24, False, False),
+    (2, 2, 0.7, 16, True, False), (1, 1, 1.0, 30, True, True), (5, 2, 1.0, 30, True, True), (3, 3, 1.0, 24, False, True)]
 
 
 def whisper_inputs(seed, batch, n_mels, frames):
@@ -301,16 +302,17 @@ def make_whisper_fixture():
     for compute in ("float32", "int8"):
         w = refapi.RefWhisper(mdir, compute, 2)
         cases = []
-        for ci, (beam, nh, lp, mx, blank) in enumerate(WHISPER_CASES):
+        for ci, (beam, nh, lp, mx, blank, stamps) in enumerate(WHISPER_CASES):
             for rep in range(3):
                 seed, batch = 300 + 10 * ci + rep, 1 + (ci + rep) % 4
                 feats = whisper_inputs(seed, batch, 16, 60)
-                prompts = [[sot, sot + 1 + (b % 3), vocab.index("<|transcribe|>" if b % 2 == 0 else "<|translate|>"),
-                            vocab.index("<|notimestamps|>")] for b in range(batch)]
+                # with timestamps the prompt ends with the task token and ApplyTimestampRules shapes the output
+                prompts = [[sot, sot + 1 + (b % 3), vocab.index("<|transcribe|>" if b % 2 == 0 else "<|translate|>")] +
+                           ([] if stamps else [vocab.index("<|notimestamps|>")]) for b in range(batch)]
                 res, nsp = w.generate(feats, prompts, beam_size=beam, num_hypotheses=nh, length_penalty=lp, max_length=mx,
                                       suppress_blank=blank)
                 cases.append({"seed": seed, "batch": batch, "prompts": prompts, "beam_size": beam, "num_hypotheses": nh,
-                              "length_penalty": lp, "max_length": mx, "suppress_blank": blank,
+                              "length_penalty": lp, "max_length": mx, "suppress_blank": blank, "timestamps": stamps,
                               "sequences": [[h[0] for h in r] for r in res], "scores": [[h[1] for h in r] for r in res],
                               "no_speech_prob": [float(x) for x in nsp]})
         enc = w.encode(whisper_inputs(7, 2, 16, 60), 64)
