@@ -34,7 +34,7 @@ stage_tests() {    # opt-in kernels first, bounded: a hang (grid barrier, mbarri
   fi
   echo "validated: FUSE_ROWS=$FUSE AWQ_DECODE=$AWQD" > $OUT/validated.txt
   # the whole GPU suite with the defaults of the tree, then once more with the validated opt-ins switched on
-  timeout 1500 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1
+  timeout 1500 python -m pytest tests -m gpu -q --tb=short > $OUT/pytest_gpu.log 2>&1
   echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
   CT2B200_FUSE_ROWS=$FUSE CT2B200_AWQ_DECODE=$AWQD timeout 1500 python -m pytest tests/test_gpu_engine.py tests/test_gpu_ops.py tests/test_gpu_awq.py \
     -m gpu -q > $OUT/pytest_gpu_optin.log 2>&1
@@ -47,7 +47,7 @@ stage_shims() {    # the reference's own gtests with libct2b200 interposed under
   echo "shim gtests exit $?" >> $OUT/ref_gtests_on_b200.txt
 }
 stage_translate() {   # encoder-decoder path: tests first, then the OPUS-MT-shaped bench record
-  timeout 900 python -m pytest tests/test_gpu_translator.py tests/test_gpu_whisper.py -q > $OUT/pytest_translator.log 2>&1
+  timeout 900 python -m pytest tests/test_gpu_translator.py tests/test_gpu_whisper.py -q --tb=short > $OUT/pytest_translator.log 2>&1
   echo "translator tests exit $?" >> $OUT/pytest_translator.log
 }
 
@@ -95,7 +95,7 @@ stage_ncufull() {  # full captures of the AWQ gate/up kernel and of the INT8 one
     -o $OUT/r02_gemm_decode python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
 }
 stage_bench() {
-  timeout 1500 python bench.py > $OUT/bench.json 2> $OUT/bench.err
+  ( time timeout 1500 python bench.py > $OUT/bench.json 2> $OUT/bench.err ) 2> $OUT/bench.time
   echo "bench exit $?" >> $OUT/bench.err
 }
 
