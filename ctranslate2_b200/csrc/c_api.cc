@@ -10,6 +10,7 @@
 #include "host/beam.h"
 #include "host/engine.h"
 #include "host/translator.h"
+#include "kernels/beam_decide.h"
 #include "kernels/kernels.h"
 
 using namespace ct2b200;
@@ -566,6 +567,30 @@ CT2B200_API int ct2b200_translate_batch(ct2b200_translator* t, const int32_t* so
         out_lens[b * num_hypotheses + h] = have ? static_cast<int32_t>(len) : -1;
         out_scores[b * num_hypotheses + h] = have ? res[b].scores[h] : 0.f;
       }
+  });
+}
+
+CT2B200_API int ct2b200_beam_decide_host(int beam_size, const int32_t* words, const int32_t* end_ids, int num_end_ids, int step,
+                             int max_steps, int max_hyp, int max_candidates, int num_hypotheses, int early_exit, int include_eos,
+                             int32_t* state_io, int32_t* active, int32_t* hyp_slot, int32_t* hyp_len) {
+  return guarded([&] {
+    CT2_REQUIRE(words && state_io && active && hyp_slot && hyp_len, "beam_decide_host: null argument");
+    CT2_REQUIRE(beam_size >= 1 && beam_size <= kMaxBeam, "beam_size must be in [1, 32]");
+    int w[2 * kMaxBeam];
+    for (int i = 0; i < 2 * beam_size; ++i) w[i] = words[i];
+    BeamDecision d;
+    beam_decide(beam_size, w, end_ids, end_ids ? num_end_ids : 0, step, max_steps, state_io[2] != 0, state_io[1], state_io[0], max_hyp,
+                max_candidates, num_hypotheses, early_exit, include_eos, d);
+    if (!state_io[2]) {
+      state_io[0] = d.num_hyp;
+      state_io[1] = d.top_done;
+      state_io[2] = d.finished;
+    }
+    for (int k = 0; k < beam_size; ++k) {
+      active[k] = d.active[k];
+      hyp_slot[k] = d.hyp_slot[k];
+      hyp_len[k] = d.hyp_len[k];
+    }
   });
 }
 

@@ -8,6 +8,7 @@
 #include <cfloat>
 
 #include "../common.cuh"
+#include "beam_decide.h"
 #include "kernels.h"
 
 namespace ct2b200 {
@@ -337,11 +338,6 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
   const int step = *st.step;                 // absolute position (indexes the K/V arena and the ancestry table)
   const int rel = step - st.start_step;      // step of the search (indexes the token history)
   const int N = st.batch * beam;
-  auto is_end = [&](int w) {
-    for (int e = 0; e < st.num_end; ++e)
-      if (st.end_ids[e] == w) return true;
-    return false;
-  };
   if (threadIdx.x < nc) {
     const int flat = cand_ids[i * nc + threadIdx.x];
     s_origin[threadIdx.x] = flat / st.vocab;
@@ -351,38 +347,21 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
   __syncthreads();
   if (threadIdx.x == 0) {
     const bool was_finished = st.finished[i] != 0;
-    const bool is_last = rel + 1 >= st.max_steps;
-    int secondary = beam, nh = st.num_hyp[i];
-    bool top_done = st.top_done[i] != 0;
+    BeamDecision d;
+    beam_decide(beam, s_word, st.end_ids, st.num_end, rel, st.max_steps, was_finished, st.top_done[i], st.num_hyp[i], st.max_hyp,
+                st.max_candidates, st.num_hypotheses, st.early_exit, st.include_eos, d);
     for (int k = 0; k < beam; ++k) {
-      int next = k;
-      s_hyp[k] = -1;
-      if (!was_finished && (is_end(s_word[k]) || is_last)) {
-        if (k == 0) top_done = true;
-        if (nh < st.max_hyp) {
-          s_hyp[k] = nh;
-          // the end token is kept or dropped per include_eos_in_hypotheses (decoding.cc:601-603)
-          st.hyp_len[i * st.max_hyp + nh] = (is_end(s_word[k]) && !st.include_eos) ? rel : rel + 1;
-          st.hyp_score[i * st.max_hyp + nh] = s_score[k];
-          ++nh;
-        }
-        for (int j = secondary; j < nc; ++j)
-          if (!is_end(s_word[j])) {
-            next = j;
-            secondary = j + 1;
-            break;
-          }
+      s_active[k] = d.active[k];
+      s_hyp[k] = d.hyp_slot[k];
+      if (d.hyp_slot[k] >= 0) {
+        st.hyp_len[i * st.max_hyp + d.hyp_slot[k]] = d.hyp_len[k];
+        st.hyp_score[i * st.max_hyp + d.hyp_slot[k]] = s_score[k];
       }
-      s_active[k] = next;
     }
     if (!was_finished) {
-      bool fin;
-      if (is_last) fin = true;
-      else if (st.early_exit) fin = top_done && nh >= st.num_hypotheses;
-      else fin = nh >= st.max_candidates;
-      st.num_hyp[i] = nh;
-      st.top_done[i] = top_done ? 1 : 0;
-      if (fin) {
+      st.num_hyp[i] = d.num_hyp;
+      st.top_done[i] = d.top_done;
+      if (d.finished) {
         st.finished[i] = 1;
         atomicAdd(st.num_finished, 1);
       }

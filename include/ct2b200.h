@@ -333,6 +333,14 @@ CT2B200_API int ct2b200_translate_batch(ct2b200_translator* t, const int32_t* so
                             int64_t max_decoding_length, int64_t min_decoding_length, int num_hypotheses, int32_t start_id,
                             const int32_t* end_ids_h, int num_end_ids, int return_end_token, int32_t* out_ids_h,
                             int32_t* out_lens_h, float* out_scores_h);
+/* Host only (no device): the per-entry bookkeeping of one BeamSearch::search step (decoding.cc:595-663) — the SAME function the
+ * device kernel runs (csrc/kernels/beam_decide.h).  words_h [2 * beam_size] = the candidates' tokens in TopK order.  Outputs:
+ * active_h [beam] (candidate each next beam continues), hyp_slot_h / hyp_len_h [beam] (hypothesis registered for candidate k, or
+ * -1), state_io_h = {num_hyp, top_done, finished} updated in place. */
+CT2B200_API int ct2b200_beam_decide_host(int beam_size, const int32_t* words_h, const int32_t* end_ids_h, int num_end_ids, int step,
+                             int max_steps, int max_hyp, int max_candidates, int num_hypotheses, int early_exit,
+                             int include_eos, int32_t* state_io_h, int32_t* active_h, int32_t* hyp_slot_h, int32_t* hyp_len_h);
+
 /* TransformerEncoder::operator() — memory_h [batch, max_source_len, d_model] f32 host (padded positions are unspecified). */
 CT2B200_API int ct2b200_translator_encode(ct2b200_translator* t, const int32_t* source_ids_h, const int32_t* source_lens_h,
                               int64_t batch, int64_t max_source_len, float* memory_h);

@@ -958,7 +958,7 @@ def beam_search(step_fn, reorder_fn, start_ids: np.ndarray, vocab: int, beam_siz
     finished = [False] * B
     top_done = [False] * B
     ncand = 2 * beam_size
-    max_candidates = int(round(beam_size * patience))
+    max_candidates = int(math.floor(beam_size * patience + 0.5))                      # std::round: half away from zero
     early_exit = length_penalty == 0
     for step in range(max_length):
         logits = np.array(step_fn(ids, step), f32)                                    # [B*beam, V]
