@@ -331,20 +331,27 @@ def translate_record(device_index, with_ref_cuda, batch=64, beam=4, max_len=256)
            "launches_per_step": int(launches // 64), "e2e_target_tokens": toks, "e2e_seconds": round(sec, 4),
            "e2e_tokens_per_s": round(toks / sec, 1), "h2d_bytes": int(sum(len(r) for r in srcs) * 4), "d2h_bytes": toks * 4}
     t.close()
-    if with_ref_cuda and os.path.exists(os.path.join(ROOT, "oracle", "_ref_cuda", "libct2ref_cuda_driver.so")):
-        src_path = os.path.join(os.path.dirname(mdir), "opus_sources.json")
-        json.dump([r[:-1] for r in srcs], open(src_path, "w"))       # the reference appends </s> itself (add_source_eos)
-        cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_cuda_worker.py"), "translate-bench", mdir, "int8_float16",
-               src_path, str(beam), str(max_len)]
-        try:
-            r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
-            line = [l for l in r.stdout.splitlines() if l.startswith("{")]
-            rec["ref_cuda"] = json.loads(line[-1]) if (r.returncode == 0 and line) else {"error": (r.stderr or r.stdout)[-300:]}
-            if "tokens_per_s" in rec["ref_cuda"]:
-                rec["vs_ref_cuda"] = round(rec["e2e_tokens_per_s"] / rec["ref_cuda"]["tokens_per_s"], 2)
-        except Exception as ex:
-            rec["ref_cuda"] = {"error": str(ex)[-300:]}
     return rec
+
+
+def translate_reference(rec, batch=64, beam=4, max_len=256):
+    """The unmodified reference's CUDA Translator on the same model and sentences (its own process)."""
+    import numpy as np
+    if not os.path.exists(os.path.join(ROOT, "oracle", "_ref_cuda", "libct2ref_cuda_driver.so")):
+        return {"ref_cuda": {"unavailable": "oracle/_ref_cuda is not built (make -f oracle/Makefile.ref_cuda)"}}
+    mdir = seq2seq_model_dir()
+    rng = np.random.default_rng(42)
+    srcs = [[int(x) for x in rng.integers(3, 58101, size=int(rng.integers(10, 51)))] for _ in range(batch)]
+    src_path = os.path.join(os.path.dirname(mdir), "opus_sources.json")
+    json.dump(srcs, open(src_path, "w"))                             # the reference appends </s> itself (add_source_eos)
+    cmd = [sys.executable, os.path.join(ROOT, "tools", "ref_cuda_worker.py"), "translate-bench", mdir, "int8_float16",
+           src_path, str(beam), str(max_len)]
+    r = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
+    line = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    out = {"ref_cuda": json.loads(line[-1]) if (r.returncode == 0 and line) else {"error": (r.stderr or r.stdout)[-300:]}}
+    if "tokens_per_s" in out["ref_cuda"]:
+        out["vs_ref_cuda"] = round(rec["e2e_tokens_per_s"] / out["ref_cuda"]["tokens_per_s"], 2)
+    return out
 
 
 def measure_variant(ct2, torch, name, weights, batch, plen, steps, warmup, device_index, peak, with_ref_cuda):
@@ -385,7 +392,7 @@ def main():
     ap.add_argument("--no-graph", action="store_true")
     ap.add_argument("--no-variants", action="store_true", help="skip the INT8/AWQ x bsz 1/32 sub-records and ref_cuda")
     ap.add_argument("--no-tp", action="store_true", help="N > 1: skip the tensor-parallel record")
-    ap.add_argument("--side-budget", type=float, default=420.0,
+    ap.add_argument("--side-budget", type=float, default=240.0,
                     help="seconds the variants / translate side records may spend before they stop launching reference CUDA runs")
     ap.add_argument("--weights", default="int8", choices=["int8", "awq"],
                     help="int8 = the headline INT8 configuration; awq = the AWQ-INT4 (group 128, AWQ_GEMM layout) variant")
@@ -541,23 +548,37 @@ def main():
     except Exception as ex:  # keep the headline even if the side measurement fails
         line["roofline"] = {"error": str(ex)}
     if world == 1 and not args.no_variants:
-        # the four points BASELINE.json's metric names, each beside the reference's own CUDA build on this GPU; the side
-        # records stop adding reference runs once the run has used its time budget (the headline above is already measured)
+        # the four points BASELINE.json's metric names (device-timed, always), then the OPUS-MT-shaped translation record, then
+        # the reference's own CUDA build beside each of them for as long as the side budget lasts (most important first)
         t_side = time.time()
         variants = {}
         for wname in ("int8", "awq"):
             for b in (1, 32):
                 key = "%s_b%d" % (wname, b)
                 try:
-                    variants[key] = measure_variant(ct2, torch, args.model, wname, b, P, 64, W, local_rank, peak,
-                                                    time.time() - t_side < args.side_budget)
+                    variants[key] = measure_variant(ct2, torch, args.model, wname, b, P, 64, W, local_rank, peak, False)
                 except Exception as ex:
                     variants[key] = {"error": str(ex)[-300:]}
         line["variants"] = variants
         try:
-            line["translate"] = translate_record(local_rank, time.time() - t_side < args.side_budget)
+            line["translate"] = translate_record(local_rank, False)
         except Exception as ex:
             line["translate"] = {"error": str(ex)[-300:]}
+        for key in ("int8_b32", "awq_b32", "int8_b1", "awq_b1"):
+            if time.time() - t_side > args.side_budget or "error" in variants[key]:
+                variants[key].setdefault("ref_cuda", {"skipped": "side budget of %.0f s used up" % args.side_budget})
+                continue
+            wname, b = key.split("_b")
+            quant = "awq_gemm" if wname == "awq" else "int8_float16"
+            r = ref_cuda_bench(args.model, quant, "float16" if wname == "awq" else "int8_float16", int(b), P)
+            variants[key]["ref_cuda"] = r
+            if "decode_tokens_per_s" in r:
+                variants[key]["vs_ref_cuda"] = round(variants[key]["tokens_per_s"] / r["decode_tokens_per_s"], 2)
+        if "error" not in line["translate"] and time.time() - t_side <= args.side_budget:
+            try:
+                line["translate"].update(translate_reference(line["translate"]))
+            except Exception as ex:
+                line["translate"]["ref_cuda"] = {"error": str(ex)[-300:]}
     if awq:
         line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference",
                                 "sample": "none: the reference has no CPU implementation of the AWQ ops "
