@@ -534,6 +534,7 @@ void dense_awq(const void* x, const AwqNative& w, const void* bias, const void* 
     gemm_f16_tc(x, scratch_nk_f16, bias, residual, act, m, w.n, w.k, y, CT2B200_F16, st);
     return;
   }
+  if (dense_awq_gemv(x, w, bias, residual, act, m, y, st)) return;
   if (dense_awq_decode(x, w, bias, residual, act, m, y, st)) return;
   AwqParams p{};
   p.fl = FloatEpilogue{bias, residual, y, act, w.n};
@@ -555,6 +556,7 @@ void dense_awq_glu(const void* x, const AwqNative& wg, const AwqNative& wu, int 
     launch_mul_inplace_f16(h, scratch_mn_f16, m * wg.n, st);
     return;
   }
+  if (dense_awq_glu_gemv(x, wg, wu, act, m, h, st)) return;
   if (dense_awq_glu_decode(x, wg, wu, act, m, h, st)) return;
   AwqParams p{};
   p.glu = FloatGluEpilogue{h, act, wg.n};

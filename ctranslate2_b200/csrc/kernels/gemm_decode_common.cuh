@@ -18,6 +18,7 @@ constexpr int kMaxStages = 10;
 // defaults of the opt-in features (flipped to 1 once validated on hardware)
 #define CT2B200_DEFAULT_FUSE_ROWS 0
 #define CT2B200_DEFAULT_AWQ_DECODE 0
+#define CT2B200_DEFAULT_AWQ_GEMV 0
 
 struct DecParams {
   int64_t n;            // output channels (weight rows)

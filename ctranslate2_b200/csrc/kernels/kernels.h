@@ -120,6 +120,10 @@ bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const
                       cudaStream_t st);
 bool dense_awq_glu_decode(const void* x, const AwqNative& wg, const AwqNative& wu, int act, int64_t m, void* h,
                           cudaStream_t st);
+// awq_gemv.cu — CUDA-core kernel for m <= 4 (no tensor cores, no barriers); false = not enabled / shape not covered
+bool dense_awq_gemv(const void* x, const AwqNative& w, const void* bias, const void* residual, int act, int64_t m, void* y,
+                    cudaStream_t st);
+bool dense_awq_glu_gemv(const void* x, const AwqNative& wg, const AwqNative& wu, int act, int64_t m, void* h, cudaStream_t st);
 void awq_repack(const int32_t* qweight, const void* scales, const int32_t* qzeros, int layout, int group, int64_t n,
                 int64_t k, int32_t* wp, void* sc, void* zr, cudaStream_t st);
 void awq_dequantize_ref_layout(const int32_t* qweight, const void* scales, const int32_t* qzeros, int layout, int group,

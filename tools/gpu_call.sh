@@ -32,11 +32,18 @@ stage_tests() {    # opt-in kernels first, bounded: a hang (grid barrier, mbarri
     echo "AWQ decode kernel NOT validated" >> $OUT/pytest_awq.log
     AWQD=0
   fi
-  echo "validated: FUSE_ROWS=$FUSE AWQ_DECODE=$AWQD" > $OUT/validated.txt
+  CT2B200_AWQ_GEMV=1 timeout 600 python -m pytest tests/test_gpu_awq.py tests/test_gpu_ref_cuda.py -q -k "awq" > $OUT/pytest_awq_gemv.log 2>&1
+  echo "awq gemv tests exit $?" >> $OUT/pytest_awq_gemv.log
+  GEMV=1
+  if ! grep -q " passed" $OUT/pytest_awq_gemv.log || grep -q "failed\|exit 124" $OUT/pytest_awq_gemv.log; then
+    echo "AWQ GEMV kernel NOT validated" >> $OUT/pytest_awq_gemv.log
+    GEMV=0
+  fi
+  echo "validated: FUSE_ROWS=$FUSE AWQ_DECODE=$AWQD AWQ_GEMV=$GEMV" > $OUT/validated.txt
   # the whole GPU suite with the defaults of the tree, then once more with the validated opt-ins switched on
   timeout 1500 python -m pytest tests -m gpu -q --tb=short > $OUT/pytest_gpu.log 2>&1
   echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
-  CT2B200_FUSE_ROWS=$FUSE CT2B200_AWQ_DECODE=$AWQD timeout 1500 python -m pytest tests/test_gpu_engine.py tests/test_gpu_ops.py tests/test_gpu_awq.py \
+  CT2B200_FUSE_ROWS=$FUSE CT2B200_AWQ_DECODE=$AWQD CT2B200_AWQ_GEMV=$GEMV timeout 1500 python -m pytest tests/test_gpu_engine.py tests/test_gpu_ops.py tests/test_gpu_awq.py \
     -m gpu -q > $OUT/pytest_gpu_optin.log 2>&1
   echo "gpu suite (opt-ins on) exit $?" >> $OUT/pytest_gpu_optin.log
 }
@@ -61,13 +68,11 @@ stage_sweeps() {   # decode step sweeps (8B, 64 steps after the 1024-token promp
     run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24 CT2B200_GEMM_ROWSTEP=1
   done
 }
+awq_run() { echo "== AWQ batch=$1 CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3" >> $OUT/sweep.log
+  CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3 timeout 600 python tools/decode_once.py $1 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1; }
 stage_awq() {
-  for B in 1 32; do
-    for D in 0 1; do
-      echo "== AWQ batch=$B CT2B200_AWQ_DECODE=$D" >> $OUT/sweep.log
-      CT2B200_AWQ_DECODE=$D timeout 600 python tools/decode_once.py $B 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
-    done
-  done
+  awq_run 1 0 0; awq_run 1 1 0; awq_run 1 0 1; awq_run 4 0 1
+  awq_run 32 0 0; awq_run 32 1 0
 }
 
 stage_refbench() { # the reference's CUDA build on the same workload (bounded: 16 / 80 generated tokens)
