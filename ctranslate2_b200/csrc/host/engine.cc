@@ -5,7 +5,6 @@
 
 #include "beam.h"
 
-#include "../kernels/gemm_decode_common.cuh"
 
 #include <cuda_profiler_api.h>
 #include <fcntl.h>
@@ -724,9 +723,6 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
     tp_.tick.alloc(256);
     CT2_CUDA_CHECK(cudaMemset(tp_.tick.ptr, 0, 256));
   }
-  grid_bar_.alloc(256);
-  CT2_CUDA_CHECK(cudaMemset(grid_bar_.ptr, 0, 256));
-  fuse_rows_ = dec::row_prephase_enabled();            // CT2B200_FUSE_ROWS
   SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
   CT2_CUDA_CHECK(cudaDeviceSynchronize());
 }
@@ -756,29 +752,10 @@ void LlamaDecoder::dense(const DenseWeights& w, const int8_t* xq, const float* x
   }
 }
 
-namespace {
-NextWeights successor(const DenseWeights* next, const DenseWeights* next_up) {
-  NextWeights nw;
-  if (next && next->kind == DenseWeights::INT8) {
-    nw.w = next->weight.ptr;
-    nw.w2 = next_up ? next_up->weight.ptr : nullptr;
-    nw.n = next->n;
-    nw.k = next->k;
-  }
-  return nw;
-}
-}  // namespace
-
+// [RMSNorm +] Quantize + Dense.  (A row pre-phase that ran the row op inside the decode GEMM behind a grid barrier was measured
+// slower than these two launches under programmatic dependent launch and removed: profiles/README.md, round 2.)
 void LlamaDecoder::dense_from_rows(const DenseWeights& w, const void* x_rows, const void* gamma, int64_t cols, int64_t m,
-                                   const void* residual, int act, void* y, const DenseWeights* next,
-                                   const DenseWeights* next_up) {
-  const bool tc = gemm_impl_ == CT2B200_GEMM_TCGEN05 || (gemm_impl_ == CT2B200_GEMM_AUTO && env_gemm_impl() != CT2B200_GEMM_MMA_SYNC);
-  if (fuse_rows_ && tc && m <= 64) {
-    RowPre pre{gamma ? 2 : 1, x_rows, gamma, mc_.eps, grid_bar_.as<unsigned>()};
-    DenseEpilogue e{xs_.as<float>(), w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
-    const NextWeights nw = successor(next, next_up);
-    if (gemm_s8_decode(xq_.as<int8_t>(), w.weight.as<int8_t>(), m, w.n, w.k, e, dtype_, stream_, &pre, &nw)) return;
-  }
+                                   const void* residual, int act, void* y) {
   if (gamma)
     launch_rms_norm(gamma, x_rows, m, cols, mc_.eps, false, nullptr, xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
   else
@@ -787,16 +764,8 @@ void LlamaDecoder::dense_from_rows(const DenseWeights& w, const void* x_rows, co
 }
 
 void LlamaDecoder::glu_from_rows(const DenseWeights& gate, const DenseWeights& up, const void* x_rows, const void* gamma,
-                                 int64_t m, void* h, const DenseWeights* next) {
+                                 int64_t m, void* h) {
   GluEpilogue g{xs_.as<float>(), gate.scale.as<float>(), up.scale.as<float>(), h, mc_.activation, gate.n};
-  const bool tc = gemm_impl_ == CT2B200_GEMM_TCGEN05 || (gemm_impl_ == CT2B200_GEMM_AUTO && env_gemm_impl() != CT2B200_GEMM_MMA_SYNC);
-  if (fuse_rows_ && tc && m <= 64) {
-    RowPre pre{gamma ? 2 : 1, x_rows, gamma, mc_.eps, grid_bar_.as<unsigned>()};
-    const NextWeights nw = successor(next, nullptr);
-    if (gemm_s8_glu_decode(xq_.as<int8_t>(), gate.weight.as<int8_t>(), up.weight.as<int8_t>(), m, gate.n, gate.k, g, dtype_,
-                           stream_, &pre, &nw))
-      return;
-  }
   if (gamma)
     launch_rms_norm(gamma, x_rows, m, gate.k, mc_.eps, false, nullptr, xq_.as<int8_t>(), xs_.as<float>(), dtype_, stream_);
   else
@@ -849,19 +818,17 @@ void LlamaDecoder::layers_forward(int64_t rows, int64_t batch, int64_t time, int
     }
     return;
   }
-  // Per layer: [RMSNorm + Quantize +] QKV Dense, attention, [Quantize +] out Dense (+ residual), [RMSNorm + Quantize +] gate/up
-  // Dense with SwiGLU, [Quantize +] down Dense (+ residual).  At decode (rows <= 64) the bracketed row ops run as the
-  // pre-phase of the following GEMM: 5 launches per layer.
+  // Per layer: RMSNorm + Quantize, QKV Dense, attention, Quantize, out Dense (+ residual), RMSNorm + Quantize, gate/up Dense with
+  // SwiGLU, Quantize, down Dense (+ residual): 9 launches, every one with programmatic dependent launch.
   for (int l = 0; l < mc_.num_layers; ++l) {
     LayerWeights& lw = layers_[l];
     // --- self attention (attention.cc:442-615) ---
-    dense_from_rows(lw.qkv, x_.ptr, lw.attn_gamma.ptr, mc_.d_model, rows, nullptr, -1, qkv_.ptr, &lw.out);
+    dense_from_rows(lw.qkv, x_.ptr, lw.attn_gamma.ptr, mc_.d_model, rows, nullptr, -1, qkv_.ptr);
     attention(l);
-    dense_from_rows(lw.out, attn_.ptr, nullptr, static_cast<int64_t>(H) * D, rows, x_.ptr, -1, x_.ptr, &lw.gate, &lw.up);
+    dense_from_rows(lw.out, attn_.ptr, nullptr, static_cast<int64_t>(H) * D, rows, x_.ptr, -1, x_.ptr);
     // --- feed forward (transformer.cc:21-51) ---
-    glu_from_rows(lw.gate, lw.up, x_.ptr, lw.ffn_gamma.ptr, rows, h_.ptr, &lw.down);
-    dense_from_rows(lw.down, h_.ptr, nullptr, mc_.ffn_dim, rows, x_.ptr, -1, x_.ptr,
-                    l + 1 < mc_.num_layers ? &layers_[l + 1].qkv : nullptr);
+    glu_from_rows(lw.gate, lw.up, x_.ptr, lw.ffn_gamma.ptr, rows, h_.ptr);
+    dense_from_rows(lw.down, h_.ptr, nullptr, mc_.ffn_dim, rows, x_.ptr, -1, x_.ptr);
   }
 }
 

@@ -160,14 +160,11 @@ class LlamaDecoder {
   DeviceBuffer load_float_vector(const ModelFile& f, const std::string& name);
   void dense(const DenseWeights& w, const int8_t* xq, const float* xs, const void* x_float, int64_t m,
              const void* residual, int act, void* y);
-  // INT8 Dense whose input rows are still in T: [RMSNorm +] Quantize + Dense.  Decode steps (m <= 64) run it as ONE launch
-  // (row pre-phase of gemm_decode.cu); otherwise the row kernel and the GEMM are launched separately (same bits).
-  // next / next_up: the Dense (pair) that follows in the step; its weights are prefetched into L2 (successor prefetch)
+  // INT8 Dense whose input rows are still in T: [RMSNorm +] Quantize (row kernel) + Dense
   void dense_from_rows(const DenseWeights& w, const void* x_rows, const void* gamma, int64_t cols, int64_t m,
-                       const void* residual, int act, void* y, const DenseWeights* next = nullptr,
-                       const DenseWeights* next_up = nullptr);
+                       const void* residual, int act, void* y);
   void glu_from_rows(const DenseWeights& gate, const DenseWeights& up, const void* x_rows, const void* gamma, int64_t m,
-                     void* h, const DenseWeights* next = nullptr);
+                     void* h);
   void layers_forward(int64_t rows, int64_t batch, int64_t time, int64_t offset, const int32_t* lens_d);
   void project(const void* x_rows, int64_t rows, void* logits_out);
   void embed(const int32_t* ids_d, int64_t rows);
@@ -192,8 +189,6 @@ class LlamaDecoder {
   cudaStream_t stream_ = nullptr;
   int64_t max_batch_ = 0, max_len_ = 0, chunk_rows_ = 0;
   int attn_splits_ = 1;
-  bool fuse_rows_ = false;         // CT2B200_FUSE_ROWS: row pre-phase of the decode GEMM instead of separate row kernels
-  DeviceBuffer grid_bar_;          // grid barrier words of the row pre-phase
 
   DenseWeights embeddings_;       // int8 [V,d] + scale, or T [V,d]
   DenseWeights projection_;

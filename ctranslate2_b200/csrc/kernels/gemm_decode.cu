@@ -53,8 +53,7 @@ struct DecSmem {
 template <typename T, int KIND, int BN, int NB, int CS>
 __global__ void __launch_bounds__(kTcThreads, 2)
     gemm_decode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
-                       const __grid_constant__ CUtensorMap tm_w2, const __grid_constant__ CUtensorMap tm_n,
-                       const __grid_constant__ CUtensorMap tm_n2, const DecParams p) {
+                       const __grid_constant__ CUtensorMap tm_w2, const DecParams p) {
   using S = DecSmem<BN, NB>;
   constexpr int kElem = Elem<KIND>::bytes;
   constexpr int BK = kSwizzleBytes / kElem;
@@ -71,9 +70,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(ctrl);               // [kMaxStages]
   uint64_t* empty_bar = full_bar + kMaxStages;                           // [kMaxStages]
   uint64_t* acc_bar = empty_bar + kMaxStages;                            // accumulators complete
-  uint64_t* pre_done = acc_bar + 1;                                      // row pre-phase: int8 rows of every CTA are visible
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(pre_done + 1);
-  float* pre_red = reinterpret_cast<float*>(ctrl + 256);                 // 4 floats (row_ops.cuh reductions)
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_bar + 1);
   uint32_t* red = reinterpret_cast<uint32_t*>(ctrl + S::kCtrl);          // [CS src][NB][cpr][128] (CS > 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -89,7 +86,6 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       mbar_init(empty_bar + s, 1);
     }
     mbar_init(acc_bar, 1);
-    mbar_init(pre_done, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -113,31 +109,13 @@ __global__ void __launch_bounds__(kTcThreads, 2)
       auto acts = [&](int s, int kb) {
         tma_load_2d(smem + s * S::kStage + S::kA, &tm_x, full_bar + s, kb * BK, 0, kEvictLast);
       };
-      // successor prefetch: box j of the next kernel = (matrix j % nb, tile (j / nb) % tiles, K block (j / nb) / tiles)
-      int pf_j = static_cast<int>(blockIdx.x);
-      auto prefetch_one = [&]() {
-        if (pf_j < p.pf_boxes) {
-          const int which = pf_j % p.pf_nb, rest = pf_j / p.pf_nb;
-          const int t2 = rest % p.pf_tiles, kb2 = rest / p.pf_tiles;
-          tma_prefetch_2d(which == 0 ? &tm_n : &tm_n2, kb2 * p.pf_bk, t2 * p.pf_rows);
-          pf_j += static_cast<int>(gridDim.x);
-        }
-      };
       const int pre = min(nstages, nkb);
 #pragma unroll 1
       for (int i = 0; i < pre; ++i) {                  // weights of the first ring fill: before the dependency wait
         mbar_expect_tx(full_bar + i, stage_tx);
         weights(i, kb_lo + i);
       }
-#pragma unroll 1
-      for (int i = 0; i < pre; ++i) prefetch_one();
       griddep_wait();
-      if constexpr (KIND == 0) {
-        if (p.pre_mode != 0) {                         // the int8 rows are written by this grid: wait for the grid barrier
-          mbar_wait(pre_done, 0);
-          asm volatile("fence.proxy.async.global;" ::: "memory");
-        }
-      }
 #pragma unroll 1
       for (int i = 0; i < pre; ++i) acts(i, kb_lo + i);
 #pragma unroll 1
@@ -147,10 +125,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
         mbar_expect_tx(full_bar + s, stage_tx);
         weights(s, kb_lo + it);
         acts(s, kb_lo + it);
-        prefetch_one();
       }
-#pragma unroll 1
-      while (pf_j < p.pf_boxes) prefetch_one();         // what the cap allows beyond one box per own K block
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
@@ -182,34 +157,6 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     const bool row_ok = rloc < p.tile_rows && arow < p.n;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
     griddep_wait();                                    // a_scale / residual come from the previous kernels
-    if constexpr (KIND == 0) {
-      if (p.pre_mode != 0) {
-        // ===== row pre-phase: these 128 threads quantize row blockIdx.x (+ gridDim.x ...) of the activations =====
-        const int t = static_cast<int>(threadIdx.x) - 64;
-        const T* px = static_cast<const T*>(p.pre_x);
-        const T* pg = static_cast<const T*>(p.pre_gamma);
-        const bool wide = rowop::nv_for<T>(p.pre_cols) != 4;
-#pragma unroll 1
-        for (int64_t r = blockIdx.x; r < p.m; r += gridDim.x) {
-          const T* xr = px + r * p.pre_cols;
-          int8_t* qr = p.pre_q + r * p.pre_cols;
-          if (p.pre_mode == 2) {
-            if (wide) rowop::row_op_128<T, 1, rowop::kMaxNV>(xr, pg, p.pre_cols, p.pre_eps, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
-            else rowop::row_op_128<T, 1, 4>(xr, pg, p.pre_cols, p.pre_eps, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
-          } else {
-            if (wide) rowop::row_op_128<T, 0, rowop::kMaxNV>(xr, nullptr, p.pre_cols, 0.f, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
-            else rowop::row_op_128<T, 0, 4>(xr, nullptr, p.pre_cols, 0.f, false, qr, p.pre_s + r, nullptr, pre_red, t, 1);
-          }
-        }
-        __threadfence();                               // this thread's row bytes are visible at gpu scope
-        rowop::bar128(1);
-        if (t == 0) {
-          grid_barrier(p.pre_bar, gridDim.x);
-          mbar_arrive(pre_done);                       // releases the TMA producer's activation loads
-        }
-        rowop::bar128(1);                              // the epilogue reads a_scale of every row: after the grid barrier
-      }
-    }
     float sw0 = 1.f, sw1 = 1.f, bias_t = 0.f;
     if (row_ok) {
       if constexpr (KIND == 0) {
@@ -395,8 +342,8 @@ DecPlan plan_decode(int64_t n, int kb_total, int sm_count) {
 }
 
 template <typename T, int KIND, int BN, int NB, int CS>
-void launch_decode(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tmw2, const CUtensorMap& tmn,
-                   const CUtensorMap& tmn2, const DecParams& p, const DecPlan& plan, cudaStream_t st) {
+void launch_decode(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& tmw2, const DecParams& p,
+                   const DecPlan& plan, cudaStream_t st) {
   configure_once<T, KIND, BN, NB, CS>();
   auto kernel = gemm_decode_kernel<T, KIND, BN, NB, CS>;
   cudaLaunchConfig_t cfg{};
@@ -420,7 +367,7 @@ void launch_decode(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtenso
   }
   cfg.attrs = attr;
   cfg.numAttrs = na;
-  CT2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmx, tmw, tmw2, tmn, tmn2, p));
+  CT2_CUDA_CHECK(cudaLaunchKernelEx(&cfg, kernel, tmx, tmw, tmw2, p));
   check_launch();
 }
 
@@ -453,31 +400,11 @@ bool run_decode(const void* x, const void* w, const void* w2, int64_t m, int64_t
   const CUtensorMap tmx = make_operand_map(x, m, k, elem, KIND, BN);
   const CUtensorMap tmw = make_operand_map(w, n, k, elem, KIND, plan.tile_rows);
   const CUtensorMap tmw2 = make_operand_map(w2 ? w2 : w, n, k, elem, KIND, plan.tile_rows);
-  // successor prefetch: the next Dense's plan gives the boxes its CTAs will load first
-  CUtensorMap tmn = tmw, tmn2 = tmw2;
-  p.pf_boxes = 0;
-  p.pf_tiles = p.pf_nb = p.pf_rows = 1;
-  p.pf_bk = kSwizzleBytes / elem;
-  static const int pf_mb = std::max(0, env_int("CT2B200_L2_PREFETCH_MB", 24));
-  if (next && next->w && pf_mb > 0 && KIND == 0) {
-    const int kb2 = div_up(next->k, kSwizzleBytes / elem);
-    const DecPlan np = next->w2 ? plan_decode<T, KIND, BN, 2>(next->n, kb2, sms) : plan_decode<T, KIND, BN, 1>(next->n, kb2, sms);
-    if (np.cs != 0) {
-      tmn = make_operand_map(next->w, next->n, next->k, elem, KIND, np.tile_rows);
-      tmn2 = make_operand_map(next->w2 ? next->w2 : next->w, next->n, next->k, elem, KIND, np.tile_rows);
-      p.pf_nb = next->w2 ? 2 : 1;
-      p.pf_tiles = np.tiles;
-      p.pf_rows = np.tile_rows;
-      const int64_t total = static_cast<int64_t>(np.tiles) * kb2 * p.pf_nb;
-      const int64_t cap = static_cast<int64_t>(pf_mb) * 1024 * 1024 / (static_cast<int64_t>(np.tile_rows) * kSwizzleBytes);
-      p.pf_boxes = static_cast<int>(std::min(total, cap));
-    }
-  }
   switch (plan.cs) {
-    case 1: launch_decode<T, KIND, BN, NB, 1>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
-    case 2: launch_decode<T, KIND, BN, NB, 2>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
-    case 3: launch_decode<T, KIND, BN, NB, 3>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
-    default: launch_decode<T, KIND, BN, NB, 4>(tmx, tmw, tmw2, tmn, tmn2, p, plan, st); break;
+    case 1: launch_decode<T, KIND, BN, NB, 1>(tmx, tmw, tmw2, p, plan, st); break;
+    case 2: launch_decode<T, KIND, BN, NB, 2>(tmx, tmw, tmw2, p, plan, st); break;
+    case 3: launch_decode<T, KIND, BN, NB, 3>(tmx, tmw, tmw2, p, plan, st); break;
+    default: launch_decode<T, KIND, BN, NB, 4>(tmx, tmw, tmw2, p, plan, st); break;
   }
   return true;
 }
@@ -500,25 +427,12 @@ bool decode_kernel_enabled() {
 // The three entry points return false when the shape is not covered (m > 64, raw int32 output, more tiles than one
 // wave holds): the caller then uses the general persistent kernel of gemm_tc.cu.
 namespace {
-// fills the pre-phase fields; false = the row shape / alignment is not covered by row_ops.cuh
-bool set_row_pre(DecParams& p, const RowPre* pre, const int8_t* A, const float* a_scale, int64_t K, int dtype) {
-  if (!pre || pre->mode == 0) return true;
-  if (!row_prephase_enabled()) return false;           // the caller launches the row kernel and the GEMM separately
-  bool ok = false;
-  CT2_DISPATCH_DTYPE(dtype, (ok = rowop::covers<T>(K)));
-  if (!ok || (reinterpret_cast<uintptr_t>(pre->x) & 15) || (reinterpret_cast<uintptr_t>(pre->gamma) & 15) ||
-      (reinterpret_cast<uintptr_t>(A) & 7) || pre->bar == nullptr || (pre->mode == 2 && pre->gamma == nullptr))
-    return false;
-  p.pre_mode = pre->mode;
-  p.pre_x = pre->x;
-  p.pre_gamma = pre->gamma;
-  p.pre_eps = pre->eps;
-  p.pre_q = const_cast<int8_t*>(A);
-  p.pre_s = const_cast<float*>(a_scale);
-  p.pre_cols = K;
-  p.pre_bar = pre->bar;
-  return true;
-}
+// The row pre-phase ([RMSNorm +] Quantize of the activations inside this kernel, behind a grid barrier) and the successor
+// prefetch into L2 were measured on the B200 (profiles/README.md, round 2): bit-identical, but SLOWER than the separate row
+// kernels under programmatic dependent launch (decode step 2.37 -> 2.63 ms at bsz 1, 3.22 -> 3.50 ms at bsz 32 — every CTA waits
+// at the barrier for the slowest row, and the extra code took the kernel from 70-86 to 168 registers).  They were removed;
+// callers that pass a RowPre get `false` and launch the row kernel themselves.
+bool set_row_pre(DecParams&, const RowPre* pre, const int8_t*, const float*, int64_t, int) { return !pre || pre->mode == 0; }
 }  // namespace
 
 bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& e, int dtype,

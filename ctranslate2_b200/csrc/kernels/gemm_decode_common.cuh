@@ -15,9 +15,8 @@ using namespace tc;
 
 constexpr int kMaxStages = 10;
 
-// defaults of the opt-in features (flipped to 1 once validated on hardware)
-#define CT2B200_DEFAULT_FUSE_ROWS 0
-#define CT2B200_DEFAULT_AWQ_DECODE 0
+// defaults of the switchable kernels: 1 once a GPU session has validated them (profiles/README.md), 0 = opt-in until then
+#define CT2B200_DEFAULT_AWQ_DECODE 1
 #define CT2B200_DEFAULT_AWQ_GEMV 0
 
 struct DecParams {
@@ -35,51 +34,8 @@ struct DecParams {
   void* y;                  // [m, n] T
   int act;
   int64_t ldy;
-  // Row pre-phase (INT8 kernels): the activations arrive as T rows and are quantized INSIDE this kernel — CTA r < m runs
-  // ops::Quantize (pre_mode 1) or ops::RMSNorm + ops::Quantize (pre_mode 2) for row r (row_ops.cuh, bit-identical to the
-  // standalone row kernel), all CTAs meet at a grid barrier, then the int8 rows are staged by TMA as before.  The weight ring
-  // was filled before that, so HBM keeps streaming under it.  0 = the int8 rows / scales were produced by an earlier kernel.
-  int pre_mode;
-  const void* pre_x;        // [m, k] T
-  const void* pre_gamma;    // [k] T (pre_mode 2)
-  float pre_eps;
-  int8_t* pre_q;            // [m, k] (the tensor tm_x maps)
-  float* pre_s;             // [m] (= a_scale)
-  int64_t pre_cols;         // k
-  unsigned* pre_bar;        // grid barrier: {arrivals, generation}, zero-initialised, owned by the caller
-  // Successor prefetch: the weights of the NEXT Dense of the step are constants, so while this kernel streams its own tiles
-  // its TMA thread also asks for the boxes the next kernel will load first (cp.async.bulk.prefetch.tensor -> L2), one box
-  // per own K block, k-block-major over the next kernel's tiles so that every one of its CTAs finds the head of its stream
-  // in L2.  HBM then keeps streaming through this kernel's epilogue and the next kernel's prologue.  pf_boxes = 0: off.
-  int pf_boxes;             // boxes to prefetch in total (capped by CT2B200_L2_PREFETCH_MB)
-  int pf_tiles;             // tiles of the next kernel
-  int pf_rows;              // its tile height (box rows)
-  int pf_nb;                // 1, or 2 when it streams a gate/up pair (tm_n and tm_n2)
-  int pf_bk;                // elements per 128-byte K block of its weights
 };
 
-__device__ __forceinline__ void tma_prefetch_2d(const CUtensorMap* map, int c0, int c1) {
-  asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];" ::"l"(map), "r"(c0), "r"(c1) : "memory");
-}
-
-// One thread per CTA: all `nctas` CTAs of the (co-resident, single-wave) grid meet here.  bar[0] counts arrivals, bar[1] is
-// the generation; the last arriver resets the count and bumps the generation (release), the others spin on it (acquire).
-__device__ __forceinline__ void grid_barrier(unsigned* bar, unsigned nctas) {
-  unsigned gen;
-  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(gen) : "l"(bar + 1) : "memory");
-  __threadfence();
-  const unsigned prev = atomicAdd(bar, 1u);
-  if (prev == nctas - 1) {
-    bar[0] = 0u;
-    __threadfence();
-    asm volatile("st.release.gpu.global.u32 [%0], %1;" ::"l"(bar + 1), "r"(gen + 1) : "memory");
-  } else {
-    unsigned now;
-    do {
-      asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(now) : "l"(bar + 1) : "memory");
-    } while (now == gen);
-  }
-}
 
 template <int KIND> struct Elem { static constexpr int bytes = KIND == 0 ? 1 : 2; };
 
@@ -151,11 +107,6 @@ inline int env_int(const char* name, int fallback) {
   const char* e = std::getenv(name);
   return e ? std::atoi(e) : fallback;
 }
-
-// Features whose hardware validation is recorded in profiles/README.md are on by default; the others stay opt-in until a GPU
-// session has run their bit-identity tests (tools/gpu_call.sh runs them with the switch set):
-//   CT2B200_FUSE_ROWS   row pre-phase of the decode GEMM (grid barrier inside the kernel)
-inline bool row_prephase_enabled() { return env_int("CT2B200_FUSE_ROWS", CT2B200_DEFAULT_FUSE_ROWS) != 0; }
 
 // co-resident clusters of `cs` CTAs of `kernel` (cs == 1: one CTA per SM)
 template <typename K>

@@ -347,9 +347,8 @@ def test_invalid_arguments_raise():
 @pytest.mark.parametrize("dtype", ["float16", "bfloat16"])
 @pytest.mark.parametrize("mnk", [(1, 512, 1024), (5, 6144, 4096), (32, 4096, 4096), (64, 4096, 14336), (33, 1000, 2048)])
 def test_dense_int8_rows_fused_is_bit_identical(dtype, mnk):
-    """Row pre-phase of the decode GEMM (gemm_decode.cu + row_ops.cuh): [RMSNorm +] Quantize + Dense in ONE launch gives
-    exactly the bits of the separate ops::Quantize / RMSNorm + Quantize kernels followed by the fused Dense — int8 rows,
-    scales and outputs; repeated calls reuse the grid-barrier words."""
+    """ct2b200_dense_s8_rows / _glu_rows ([RMSNorm +] Quantize + Dense from T rows) give exactly the bits of the separate
+    ops::Quantize / RMSNorm + Quantize calls followed by the fused Dense — int8 rows, scales and outputs, call after call."""
     m, n, k = mnk
     r = np.random.default_rng(m + n)
     x = dev(r.standard_normal((m, k)).astype(np.float32) * 3, TDT[dtype])

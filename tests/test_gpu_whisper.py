@@ -79,16 +79,19 @@ def test_quantized_and_half_generation_agree_statistically(fixture, compute):
 def test_tokens_interface_and_errors():
     w = Whisper(MODEL, compute_type="float32")
     x = inputs(1, 1)
-    a = w.generate(x, [["<|startoftranscript|>", "<|l0|>", "<|transcribe|>", "<|notimestamps|>"]], beam_size=2)
-    b = w.generate(x, [[w.sot_id, w.sot_id + 1, w._ids["<|transcribe|>"], w.no_timestamps_id]], beam_size=2)
+    # the tiny model stores 64 decoder positions: like the reference, positions past the table are an error
+    a = w.generate(x, [["<|startoftranscript|>", "<|l0|>", "<|transcribe|>", "<|notimestamps|>"]], beam_size=2, max_length=40)
+    b = w.generate(x, [[w.sot_id, w.sot_id + 1, w._ids["<|transcribe|>"], w.no_timestamps_id]], beam_size=2, max_length=40)
+    with pytest.raises(ValueError):
+        w.generate(x, [[w.sot_id, w.no_timestamps_id]], beam_size=2)          # default max_length 448 > 64 positions
     assert a[0].sequences_ids == b[0].sequences_ids and a[0].sequences[0] == [w._tokens[i] for i in a[0].sequences_ids[0]]
     with pytest.raises(ValueError):
-        w.generate(x, [[w.sot_id, w._ids["<|transcribe|>"], 5]])              # text after the task tokens (decoding prefix)
-    ts = w.generate(x, [[w.sot_id, w.sot_id + 1, w._ids["<|transcribe|>"]]], beam_size=2)[0].sequences_ids[0]
+        w.generate(x, [[w.sot_id, w._ids["<|transcribe|>"], 5]], max_length=40)   # text after the task tokens (decoding prefix)
+    ts = w.generate(x, [[w.sot_id, w.sot_id + 1, w._ids["<|transcribe|>"]]], beam_size=2, max_length=40)[0].sequences_ids[0]
     assert ts[0] > w.no_timestamps_id                                          # with timestamps the output starts with one
     with pytest.raises(ValueError):
-        w.generate(inputs(1, 1, n_mels=8), [[w.sot_id, w.no_timestamps_id]])   # wrong number of mel bins
+        w.generate(inputs(1, 1, n_mels=8), [[w.sot_id, w.no_timestamps_id]], max_length=40)   # wrong number of mel bins
     with pytest.raises(ValueError):
-        w.generate(x, [[w._ids["<|transcribe|>"], w.no_timestamps_id]])        # no <|startoftranscript|>
+        w.generate(x, [[w._ids["<|transcribe|>"], w.no_timestamps_id]], max_length=40)        # no <|startoftranscript|>
     assert w.generate(x[:0], []) == []
     w.close()

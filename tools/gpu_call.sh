@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench ncu ncufull bench translate
+# stages: golden tests shims sweeps awq refbench ncu ncufull bench translate bisect trprofile
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -18,13 +18,6 @@ stage_golden() {   # the reference's CUDA kernels on seeded inputs -> fixtures (
 }
 
 stage_tests() {    # opt-in kernels first, bounded: a hang (grid barrier, mbarrier protocol) must not take the box
-  CT2B200_FUSE_ROWS=1 timeout 300 python -m pytest tests/test_gpu_ops.py -q -x -k "rows_fused" > $OUT/pytest_fused.log 2>&1
-  echo "fused rows exit $?" >> $OUT/pytest_fused.log
-  FUSE=1
-  if ! grep -q " passed" $OUT/pytest_fused.log || grep -q "failed\|exit 124" $OUT/pytest_fused.log; then
-    echo "row pre-phase NOT validated" >> $OUT/pytest_fused.log
-    FUSE=0
-  fi
   CT2B200_AWQ_DECODE=1 timeout 600 python -m pytest tests/test_gpu_awq.py tests/test_gpu_ref_cuda.py -q -k "awq" > $OUT/pytest_awq.log 2>&1
   echo "awq tests exit $?" >> $OUT/pytest_awq.log
   AWQD=1
@@ -39,11 +32,11 @@ stage_tests() {    # opt-in kernels first, bounded: a hang (grid barrier, mbarri
     echo "AWQ GEMV kernel NOT validated" >> $OUT/pytest_awq_gemv.log
     GEMV=0
   fi
-  echo "validated: FUSE_ROWS=$FUSE AWQ_DECODE=$AWQD AWQ_GEMV=$GEMV" > $OUT/validated.txt
+  echo "validated: AWQ_DECODE=$AWQD AWQ_GEMV=$GEMV" > $OUT/validated.txt
   # the whole GPU suite with the defaults of the tree, then once more with the validated opt-ins switched on
   timeout 1500 python -m pytest tests -m gpu -q --tb=short > $OUT/pytest_gpu.log 2>&1
   echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
-  CT2B200_FUSE_ROWS=$FUSE CT2B200_AWQ_DECODE=$AWQD CT2B200_AWQ_GEMV=$GEMV timeout 1500 python -m pytest tests/test_gpu_engine.py tests/test_gpu_ops.py tests/test_gpu_awq.py \
+  CT2B200_AWQ_DECODE=$AWQD CT2B200_AWQ_GEMV=$GEMV timeout 1500 python -m pytest tests/test_gpu_engine.py tests/test_gpu_ops.py tests/test_gpu_awq.py \
     -m gpu -q > $OUT/pytest_gpu_optin.log 2>&1
   echo "gpu suite (opt-ins on) exit $?" >> $OUT/pytest_gpu_optin.log
 }
@@ -59,13 +52,9 @@ stage_translate() {   # encoder-decoder path: tests first, then the OPUS-MT-shap
 }
 
 run() { echo "== B=$B $*" >> $OUT/sweep.log; env "$@" timeout 300 python tools/decode_once.py $B 64 int8_float16 8b int8_float16 >> $OUT/sweep.log 2>&1; }
-stage_sweeps() {   # decode step sweeps (8B, 64 steps after the 1024-token prompt)
+stage_sweeps() {   # decode step of the INT8 8B model (64 steps after the 1024-token prompt)
   for B in 1 32; do
-    run CT2B200_FUSE_ROWS=0 CT2B200_L2_PREFETCH_MB=0
-    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=0
-    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=8
-    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24
-    run CT2B200_FUSE_ROWS=1 CT2B200_L2_PREFETCH_MB=24 CT2B200_GEMM_ROWSTEP=1
+    run CT2B200_PDL=1
   done
 }
 awq_run() { echo "== AWQ batch=$1 CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3" >> $OUT/sweep.log
@@ -102,6 +91,25 @@ stage_ncufull() {  # full captures of the AWQ gate/up kernel and of the INT8 one
 stage_bench() {
   ( time timeout 1500 python bench.py > $OUT/bench.json 2> $OUT/bench.err ) 2> $OUT/bench.time
   echo "bench exit $?" >> $OUT/bench.err
+}
+
+stage_bisect() {   # which commit broke the ragged 8B schedule / the eager scores test / the 8B comparison with the reference?
+  T="tests/test_gpu_engine.py::test_full_size_llama8b_properties tests/test_gpu_engine.py::test_generate_scores_match_reference"
+  for c in f7cebc7 f70f032 1a7d296 dc2c628; do
+    echo "=== commit $c" >> $OUT/bisect.log
+    ( cd bisect/$c && timeout 600 python -m pytest $T -q --tb=line 2>&1 | tail -6 ) >> $OUT/bisect.log
+  done
+  echo "=== HEAD" >> $OUT/bisect.log
+  timeout 600 python -m pytest $T -q --tb=line 2>&1 | tail -6 >> $OUT/bisect.log
+  for e in CT2B200_EOS_POLL=1 CT2B200_PDL=0 CT2B200_GEMM_DECODE=0 CT2B200_ATTN_DECODE=simt; do
+    echo "=== HEAD $e" >> $OUT/bisect.log
+    env $e timeout 600 python -m pytest $T -q --tb=line 2>&1 | tail -6 >> $OUT/bisect.log
+  done
+}
+stage_trprofile() {   # launch list of the OPUS-MT-shaped decoding step + timing
+  timeout 300 python tools/translate_once.py 64 4 64 > $OUT/translate_once.log 2>&1
+  timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_translate.csv python tools/translate_once.py 64 4 2 >> $OUT/translate_once.log 2>&1
 }
 
 for s in "$@"; do
