@@ -6,7 +6,8 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libct2b200.so")
+# CT2B200_LIB: another build of the same sources (python -m ctranslate2_b200.build --variant NAME), for A/B experiments
+LIB_PATH = os.environ.get("CT2B200_LIB") or os.path.join(_HERE, "libct2b200.so")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "ct2b200.h")
 _lib = None
 

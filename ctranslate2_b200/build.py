@@ -24,6 +24,13 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-li
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-x", "cu"]
 
 
+# Experimental builds beside the product library: libct2b200_<variant>.so, loaded through CT2B200_LIB.
+VARIANTS = {
+    # no read-only (ld.global.nc) loads: the compiler only emits them for `const T* __restrict__` parameters
+    "norestrict": ["-D__restrict__="],
+}
+
+
 def _deps_hash(src):
     h = hashlib.sha1()
     for root, _, files in os.walk(CSRC):
@@ -50,7 +57,12 @@ def _compile(src, force):
     return obj
 
 
-def build(force=False, verbose=True):
+def build(force=False, verbose=True, variant=None):
+    global OUT, OBJ, FLAGS
+    if variant:
+        OUT = os.path.join(HERE, "libct2b200_%s.so" % variant)
+        OBJ = os.path.join(HERE, "_build_" + variant)
+        FLAGS = FLAGS + VARIANTS[variant]
     os.makedirs(OBJ, exist_ok=True)
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, force), SOURCES))
@@ -68,4 +80,5 @@ def build(force=False, verbose=True):
 
 
 if __name__ == "__main__":
-    build(force="--force" in sys.argv)
+    build(force="--force" in sys.argv,
+          variant=sys.argv[sys.argv.index("--variant") + 1] if "--variant" in sys.argv else None)

@@ -124,7 +124,8 @@ class ModelWriter:
 
 def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int8_float16",
                       seed: int = 1234, init_std: float = 0.02, fast_int8: bool = False,
-                      extra: Optional[Dict] = None, omit=()) -> None:
+                      extra: Optional[Dict] = None, omit=(), embedding_std: Optional[float] = None,
+                      residual_std: Optional[float] = None) -> None:
     """Writes a random-init Llama-class model directory.
 
     quantization: "int8" / "int8_float32" / "int8_float16" / "int8_bfloat16" (int8 linear + embedding
@@ -134,11 +135,18 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
     fast_int8: draw int8 weights and scales directly (same distribution as quantizing N(0, std^2)
     rows whose amax sits near 4 sigma) instead of quantizing an fp32 draw — used for the 8B bench
     model where generating 8e9 gaussians on the host would dominate the run.
+    embedding_std / residual_std: standard deviation of the embedding rows and of the two matrices that write into the
+    residual stream (attention linear_1, ffn linear_1); default init_std.  With init_std everywhere a deep random model is
+    chaotic (every layer's update is ~100x the embedding it started from: fp16-level input differences grow to 20 % of
+    the logits after 32 layers, measured against the reference's own float16 vs int8 runs), which no trained checkpoint is;
+    embedding_std = 1 with a small residual_std keeps perturbations bounded so whole-model comparisons are meaningful.
     """
+    emb_std = init_std if embedding_std is None else embedding_std
+    res_std = init_std if residual_std is None else residual_std
     rng = np.random.default_rng(seed)
     awq_layout = {"awq_gemm": 1, "awq_gemv": 2}.get(quantization, 0)
     if awq_layout:
-        return _write_llama_awq(model_dir, cfg, awq_layout, seed, init_std, fast_int8)
+        return _write_llama_awq(model_dir, cfg, awq_layout, seed, init_std, fast_int8, emb_std, res_std)
     is_int8 = quantization.startswith("int8")
     ftype = {"int8": "float32", "int8_float32": "float32", "int8_float16": "float16",
              "int8_bfloat16": "bfloat16"}.get(quantization, quantization)
@@ -164,17 +172,18 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
             state["off"] = (off + take + 12289) % base.size
         return out
 
-    def linear(prefix, n, k):
+    def linear(prefix, n, k, std=None):
+        std = init_std if std is None else std
         if is_int8 and fast_int8:
             # uniform int8 in [-127,127] (std 73.3) with scale = 73.3/std: the dequantized weights have
             # standard deviation init_std; drawn directly as bytes (about 1 GB/s on one host core)
             q = fast_block(n * k).reshape(n, k)
             q[:, 0] = 127    # each row attains its amax, as a real quantized row does
-            scale = np.full((n,), 73.3 / init_std, np.float32) * rng.uniform(0.9, 1.1, size=n).astype(np.float32)
+            scale = np.full((n,), 73.3 / std, np.float32) * rng.uniform(0.9, 1.1, size=n).astype(np.float32)
             w.add(prefix + "/weight", q, "int8")
             w.add(prefix + "/weight_scale", scale, "float32")
             return
-        wt = (rng.standard_normal((n, k), dtype=np.float32) * np.float32(init_std))
+        wt = (rng.standard_normal((n, k), dtype=np.float32) * np.float32(std))
         if is_int8:
             q, scale = quantize_int8(wt)
             w.add(prefix + "/weight", q, "int8")
@@ -187,7 +196,7 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
     w.add("decoder/alibi_use_positive_positions", np.int8(0))
     w.add("decoder/alignment_heads", np.int16(1))
     w.add("decoder/alignment_layer", np.int16(-1))
-    linear("decoder/embeddings", cfg.vocab_size, d)
+    linear("decoder/embeddings", cfg.vocab_size, d, emb_std)
     gamma0 = None
     for l in range(cfg.num_layers):
         p = f"decoder/layer_{l}/"
@@ -195,11 +204,11 @@ def write_llama_model(model_dir: str, cfg: LlamaConfig, quantization: str = "int
         w.add(p + "ffn/layer_norm/gamma", g, ftype)
         linear(p + "ffn/linear_0", cfg.ffn_dim, d)
         linear(p + "ffn/linear_0_noact", cfg.ffn_dim, d)
-        linear(p + "ffn/linear_1", d, cfg.ffn_dim)
+        linear(p + "ffn/linear_1", d, cfg.ffn_dim, res_std)
         g = (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32)
         w.add(p + "self_attention/layer_norm/gamma", g, ftype)
         linear(p + "self_attention/linear_0", (cfg.num_heads + 2 * cfg.num_heads_kv) * D, d)
-        linear(p + "self_attention/linear_1", d, cfg.num_heads * D)
+        linear(p + "self_attention/linear_1", d, cfg.num_heads * D, res_std)
         w.add(p + "self_attention/num_heads_kv", np.int32(cfg.num_heads_kv))
         w.add(p + "self_attention/head_dim", np.int32(cfg.head_dim))
         w.add(p + "self_attention/rotary_base", np.float32(cfg.rotary_base))
@@ -240,12 +249,14 @@ def _pack_nibbles(m: np.ndarray, order) -> np.ndarray:
     return out.view(np.int32)
 
 
-def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
+def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast, emb_std=None, res_std=None):
     """AWQ-INT4 (group 128) Llama directory as the AutoAWQ -> CTranslate2 converter lays it out
     (converters/transformers.py:1697-1843 with quant_type AWQ_GEMM / AWQ_GEMV): linear layers carry int32
     `weight` + float16 `weight_scale` + int32 `weight_zero`; embeddings, norms and lm_head stay float16;
     config.json records quantization_type / bits / group size (src/models/model.cc:636-637)."""
     rng = np.random.default_rng(seed)
+    emb_std = init_std if emb_std is None else emb_std
+    res_std = init_std if res_std is None else res_std
     G = 128
     d, D = cfg.d_model, cfg.head_dim
     w = ModelWriter(model_dir)
@@ -261,17 +272,18 @@ def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
 
     packed_cache = {}
 
-    def linear(prefix, n, k):
-        if fast and (n, k) in packed_cache:
+    def linear(prefix, n, k, std=None):
+        std = init_std if std is None else std
+        if fast and (n, k, std) in packed_cache:
             # bench-sized models: layers of the same shape share one set of packed arrays (packing 7e9 nibbles in
             # numpy takes minutes; the values do not matter for a throughput measurement)
-            for suffix, (arr, dt) in packed_cache[(n, k)].items():
+            for suffix, (arr, dt) in packed_cache[(n, k, std)].items():
                 w.add(prefix + suffix, arr, dt)
             return
-        _linear(prefix, n, k)
+        _linear(prefix, n, k, std)
 
-    def _linear(prefix, n, k):
-        scales = (rng.uniform(0.6, 1.4, size=(k // G, n)) * (init_std / 2.5)).astype(np.float16)
+    def _linear(prefix, n, k, std):
+        scales = (rng.uniform(0.6, 1.4, size=(k // G, n)) * (std / 2.5)).astype(np.float16)
         zeros = rng.integers(6, 10, size=(k // G, n))
         q = nibbles(k, n)                                   # [K, N] values 0..15
         if layout == 1:
@@ -289,11 +301,11 @@ def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
         for suffix, (arr, dt) in arrays.items():
             w.add(prefix + suffix, arr, dt)
         if fast:
-            packed_cache[(n, k)] = arrays
+            packed_cache[(n, k, std)] = arrays
 
-    def dense_f16(prefix, n, k):
+    def dense_f16(prefix, n, k, std=None):
         reps = -(-(n * k) // (1 << 22))
-        vals = (np.tile(base, reps)[:n * k].astype(np.float32) - 7.5) * (init_std / 4.6)
+        vals = (np.tile(base, reps)[:n * k].astype(np.float32) - 7.5) * ((init_std if std is None else std) / 4.6)
         w.add(prefix + "/weight", vals.reshape(n, k), "float16")
 
     w.add("decoder/activation", np.int8(2))
@@ -301,16 +313,16 @@ def _write_llama_awq(model_dir, cfg, layout, seed, init_std, fast):
     w.add("decoder/alibi_use_positive_positions", np.int8(0))
     w.add("decoder/alignment_heads", np.int16(1))
     w.add("decoder/alignment_layer", np.int16(-1))
-    dense_f16("decoder/embeddings", cfg.vocab_size, d)
+    dense_f16("decoder/embeddings", cfg.vocab_size, d, emb_std)
     for l in range(cfg.num_layers):
         p = f"decoder/layer_{l}/"
         w.add(p + "ffn/layer_norm/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), "float16")
         linear(p + "ffn/linear_0", cfg.ffn_dim, d)
         linear(p + "ffn/linear_0_noact", cfg.ffn_dim, d)
-        linear(p + "ffn/linear_1", d, cfg.ffn_dim)
+        linear(p + "ffn/linear_1", d, cfg.ffn_dim, res_std)
         w.add(p + "self_attention/layer_norm/gamma", (1.0 + 0.1 * rng.standard_normal(d)).astype(np.float32), "float16")
         linear(p + "self_attention/linear_0", (cfg.num_heads + 2 * cfg.num_heads_kv) * D, d)
-        linear(p + "self_attention/linear_1", d, cfg.num_heads * D)
+        linear(p + "self_attention/linear_1", d, cfg.num_heads * D, res_std)
         w.add(p + "self_attention/num_heads_kv", np.int32(cfg.num_heads_kv))
         w.add(p + "self_attention/head_dim", np.int32(cfg.head_dim))
         w.add(p + "self_attention/rotary_base", np.float32(cfg.rotary_base))

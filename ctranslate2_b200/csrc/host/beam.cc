@@ -24,8 +24,8 @@ bool BeamSearchArena::ensure(int64_t batch, int beam, int64_t steps, size_t es) 
   cap_steps = std::max(cap_steps, steps);
   const int64_t B = cap_batch, L = cap_steps, N = B * cap_beam, maxh = max_hyp();
   cum.alloc(N * es);
-  cand_scores.alloc(B * 2 * cap_beam * es);
-  cand_ids.alloc(B * 2 * cap_beam * 4);
+  cand_scores.alloc(N * 2 * cap_beam * es);        // [B, 2 beam] (entry candidates) or [B * beam, 2 beam] (row candidates)
+  cand_ids.alloc(N * 2 * cap_beam * 4);
   next_ids.alloc(N * 4);
   parent.alloc(N * 4);
   finished.alloc(B * 4);
@@ -52,6 +52,7 @@ BeamState BeamSearchArena::state(int64_t batch, int beam, int64_t vocab, int64_t
   bs.batch = static_cast<int>(batch);
   bs.beam = beam;
   bs.vocab = static_cast<int>(vocab);
+  bs.vocab_ld = vocab;
   bs.stride = static_cast<int>(cap_steps);
   bs.max_steps = static_cast<int>(max_steps);
   bs.max_hyp = static_cast<int>(max_hyp());
@@ -86,10 +87,16 @@ void BeamSearchArena::reset(const BeamState& bs, int32_t start_id, int dtype, cu
 }
 
 void BeamSearchArena::step(void* logits, const BeamState& bs, int dtype, cudaStream_t st) {
+  if (bs.beam <= 8) {                              // one pass over the logits, nothing written back
+    launch_beam_rows(logits, cum.ptr, bs, cand_scores.ptr, cand_ids.as<int32_t>(), dtype, st);
+    launch_beam_update(bs, cand_scores.ptr, cand_ids.as<int32_t>(), cum.ptr, true, dtype, st);
+    return;
+  }
+  CT2_REQUIRE(bs.vocab_ld == bs.vocab, "beam search with beam_size > 8 needs contiguous logits rows");
   launch_beam_logprobs(logits, cum.ptr, bs, dtype, st);
   launch_topk(logits, bs.batch, static_cast<int64_t>(bs.beam) * bs.vocab, 2 * bs.beam, cand_scores.ptr, cand_ids.as<int32_t>(), dtype,
               st);
-  launch_beam_update(bs, cand_scores.ptr, cand_ids.as<int32_t>(), cum.ptr, dtype, st);
+  launch_beam_update(bs, cand_scores.ptr, cand_ids.as<int32_t>(), cum.ptr, false, dtype, st);
 }
 
 // finalize_result (decoding.cc:189-254): normalise by length^penalty, sort (stable: equal scores keep registration order), keep

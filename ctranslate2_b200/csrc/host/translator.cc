@@ -321,7 +321,7 @@ void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t 
     self_k_[l].alloc(N * L * d * es);
     self_v_[l].alloc(N * L * d * es);
   }
-  logits_.alloc(N * V * es);
+  logits_.alloc(N * ((V + 7) / 8 * 8) * es);
   if (mc_.whisper) {
     const int64_t frames = 2 * S;                        // conv2 halves the frames
     features_.alloc(B * mc_.n_mels * frames * 4);
@@ -340,14 +340,17 @@ void Translator::ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t 
 // layers
 // =============================================================================================
 void Translator::dense(const DenseWeights& w, const NormWeights* pre, const void* x, int64_t rows, const void* residual,
-                       int act, void* y) {
+                       int act, void* y, bool prequantized, int64_t ldy) {
+  if (ldy == 0) ldy = w.n;
   if (w.kind == DenseWeights::INT8) {
-    if (pre)
+    if (prequantized)
+      ;                                            // the post-norm kernel before this call left Quantize(x) in xq_ / xs_
+    else if (pre)
       launch_layer_norm(x, pre->gamma.ptr, pre->beta.ptr, rows, w.k, mc_.eps, nullptr, xq_.as<int8_t>(), xs_.as<float>(),
                         mc_.round_before_cast, dtype_, stream_);
     else
       launch_quantize_rows(x, dtype_, rows, w.k, mc_.round_before_cast, xq_.as<int8_t>(), xs_.as<float>(), stream_);
-    DenseEpilogue e{xs_.as<float>(), w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, w.n};
+    DenseEpilogue e{xs_.as<float>(), w.scale.as<float>(), w.bias.ptr, residual, y, nullptr, act, ldy};
     gemm_s8(xq_.as<int8_t>(), w.weight.as<int8_t>(), rows, w.n, w.k, e, dtype_, CT2B200_GEMM_AUTO, stream_);
   } else {
     const void* src = x;
@@ -355,12 +358,28 @@ void Translator::dense(const DenseWeights& w, const NormWeights* pre, const void
       launch_layer_norm(x, pre->gamma.ptr, pre->beta.ptr, rows, w.k, mc_.eps, xn_.ptr, nullptr, nullptr, true, dtype_, stream_);
       src = xn_.ptr;
     }
+    CT2_REQUIRE(ldy == w.n, "float Dense writes contiguous rows");
     gemm_float(src, w.weight.ptr, w.bias.ptr, residual, act, rows, w.n, w.k, y, dtype_, stream_);
   }
 }
 
-void Translator::post_norm(const NormWeights& n, void* x, int64_t rows) {
-  launch_layer_norm(x, n.gamma.ptr, n.beta.ptr, rows, mc_.d_model, mc_.eps, x, nullptr, nullptr, true, dtype_, stream_);
+// Row stride of the logits for a search: INT8 projections write rows padded to a multiple of 8 elements (16-byte stores in the
+// GEMM epilogue and 16-byte loads in the scoring kernel whatever the vocabulary size, e.g. 58101); the beam > 8 path runs
+// ops::TopK over the flattened [beam * vocab] scores and needs them contiguous.
+void Translator::set_logits_ld(BeamState& bs) {
+  const int64_t V = mc_.tgt_vocab;
+  logits_ld_ = (projection_.kind == DenseWeights::INT8 && bs.beam <= 8) ? (V + 7) / 8 * 8 : V;
+  bs.vocab_ld = logits_ld_;
+}
+
+// Post-norm sublayer end (transformer.cc:35-38, attention.cc:603-606): x = LayerNorm(x).  When the consumer is an INT8 Dense
+// the same launch also leaves its Quantize (of the rounded output, as the reference's separate op reads it) in xq_ / xs_;
+// returns whether it did, for the `prequantized` argument of that Dense.
+bool Translator::post_norm(const NormWeights& n, void* x, int64_t rows, const DenseWeights* next) {
+  const bool q = next && next->kind == DenseWeights::INT8 && next->k == mc_.d_model;
+  launch_layer_norm(x, n.gamma.ptr, n.beta.ptr, rows, mc_.d_model, mc_.eps, x, q ? xq_.as<int8_t>() : nullptr,
+                    q ? xs_.as<float>() : nullptr, q ? mc_.round_before_cast : true, dtype_, stream_);
+  return q;
 }
 
 // TransformerEncoder::operator() (transformer.cc:427-471); rows = batch * S, padded positions are computed and ignored
@@ -376,16 +395,17 @@ void Translator::run_encoder_layers(int64_t batch, int64_t S, const int32_t* len
   const int64_t rows = batch * S, d = mc_.d_model;
   const float scale = 1.f / std::sqrt(static_cast<float>(mc_.head_dim));
   const bool pre = mc_.enc_pre_norm;
+  bool xq = false;                                 // xq_ / xs_ already hold Quantize(x_) (left by a post-norm launch)
   for (int l = 0; l < mc_.enc_layers; ++l) {
     EncoderLayerWeights& w = enc_[l];
-    dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr);
+    dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr, xq);
     launch_attention_encoder(qkv_.ptr, lens_d, batch, static_cast<int>(S), mc_.num_heads, mc_.head_dim, scale, ctx_.ptr, dtype_,
                              stream_);
     dense(w.self.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
-    if (!pre) post_norm(w.self.norm, x_.ptr, rows);
-    dense(w.ffn.ff1, pre ? &w.ffn.norm : nullptr, x_.ptr, rows, nullptr, mc_.enc_activation, h_.ptr);
+    xq = !pre && post_norm(w.self.norm, x_.ptr, rows, &w.ffn.ff1);
+    dense(w.ffn.ff1, pre ? &w.ffn.norm : nullptr, x_.ptr, rows, nullptr, mc_.enc_activation, h_.ptr, xq);
     dense(w.ffn.ff2, nullptr, h_.ptr, rows, x_.ptr, -1, x_.ptr);
-    if (!pre) post_norm(w.ffn.norm, x_.ptr, rows);
+    xq = !pre && post_norm(w.ffn.norm, x_.ptr, rows, l + 1 < mc_.enc_layers ? &enc_[l + 1].self.in : nullptr);
   }
   if (mc_.has_enc_final_norm)
     launch_layer_norm(x_.ptr, enc_norm_.gamma.ptr, enc_norm_.beta.ptr, rows, d, mc_.eps, memory_.ptr, nullptr, nullptr, true, dtype_,
@@ -410,23 +430,25 @@ void Translator::decoder_step(int64_t rows, int beam, int64_t batch, int64_t S) 
   launch_embed_pos(dec_emb_.weight.ptr, dec_emb_.kind == DenseWeights::INT8 ? dec_emb_.scale.as<float>() : nullptr,
                    beam_.next_ids.as<int32_t>(), rows, d, mc_.dec_emb_scale, dec_pos_.ptr, 1, step_ptr, mc_.start_from_zero_embedding, x_.ptr, dtype_,
                    stream_);
+  bool xq = false;                                 // xq_ / xs_ already hold Quantize(x_) (left by a post-norm launch)
   for (int l = 0; l < mc_.dec_layers; ++l) {
     DecoderLayerWeights& w = dec_[l];
-    dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr);
+    dense(w.self.in, pre ? &w.self.norm : nullptr, x_.ptr, rows, nullptr, -1, qkv_.ptr, xq);
     launch_attention_beam_self(qkv_.ptr, self_k_[l].ptr, self_v_[l].ptr, beam_.anc.as<int32_t>(), step_ptr, rows,
                                static_cast<int>(cap_steps_), mc_.num_heads, mc_.head_dim, scale, ctx_.ptr, dtype_, stream_);
     dense(w.self.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
-    if (!pre) post_norm(w.self.norm, x_.ptr, rows);
-    dense(w.cross.in, pre ? &w.cross.norm : nullptr, x_.ptr, rows, nullptr, -1, q_.ptr);
+    xq = !pre && post_norm(w.self.norm, x_.ptr, rows, &w.cross.in);
+    dense(w.cross.in, pre ? &w.cross.norm : nullptr, x_.ptr, rows, nullptr, -1, q_.ptr, xq);
     launch_attention_cross(q_.ptr, mem_kv_[l].ptr, src_lens_.as<int32_t>(), rows, beam, static_cast<int>(S), mc_.num_heads,
                            mc_.head_dim, scale, ctx_.ptr, dtype_, stream_);
     dense(w.cross.out, nullptr, ctx_.ptr, rows, x_.ptr, -1, x_.ptr);
-    if (!pre) post_norm(w.cross.norm, x_.ptr, rows);
-    dense(w.ffn.ff1, pre ? &w.ffn.norm : nullptr, x_.ptr, rows, nullptr, mc_.dec_activation, h_.ptr);
+    xq = !pre && post_norm(w.cross.norm, x_.ptr, rows, &w.ffn.ff1);
+    dense(w.ffn.ff1, pre ? &w.ffn.norm : nullptr, x_.ptr, rows, nullptr, mc_.dec_activation, h_.ptr, xq);
     dense(w.ffn.ff2, nullptr, h_.ptr, rows, x_.ptr, -1, x_.ptr);
-    if (!pre) post_norm(w.ffn.norm, x_.ptr, rows);
+    xq = !pre && post_norm(w.ffn.norm, x_.ptr, rows,
+                           l + 1 < mc_.dec_layers ? &dec_[l + 1].self.in : (mc_.has_dec_final_norm ? nullptr : &projection_));
   }
-  dense(projection_, mc_.has_dec_final_norm ? &dec_norm_ : nullptr, x_.ptr, rows, nullptr, -1, logits_.ptr);
+  dense(projection_, mc_.has_dec_final_norm ? &dec_norm_ : nullptr, x_.ptr, rows, nullptr, -1, logits_.ptr, xq, logits_ld_);
 }
 
 void Translator::launch_or_capture_step(const BeamState& bs, int64_t S) {
@@ -466,7 +488,7 @@ void Translator::launch_or_capture_step(const BeamState& bs, int64_t S) {
 // the decoding loop: one captured step per position; the host only polls the "finished entries" counter
 void Translator::run_search(const BeamState& bs, int64_t S, int64_t first_check) {
   // everything the captured step bakes in (kernel arguments are values)
-  std::vector<int64_t> key = {bs.batch, bs.beam, S, bs.stride, bs.max_steps, bs.min_length, bs.max_hyp, bs.max_candidates,
+  std::vector<int64_t> key = {bs.batch, bs.beam, S, bs.vocab_ld, bs.stride, bs.max_steps, bs.min_length, bs.max_hyp, bs.max_candidates,
                               bs.num_hypotheses, bs.early_exit, bs.num_end, bs.start_step, bs.include_eos, bs.num_disable,
                               bs.num_begin, bs.ts_begin, bs.ts_end, bs.ts_eot, bs.ts_no_timestamps, bs.ts_max_initial};
   if (key != graph_key_) {
@@ -534,6 +556,7 @@ std::vector<TranslationHypotheses> Translator::translate(const TranslationReques
   // ---- beam search: the earliest step at which an entry can be complete is min_decoding_length ----
   BeamState bs = beam_.state(B, beam, mc_.tgt_vocab, L, r.min_decoding_length, r.patience, r.length_penalty, r.num_hypotheses,
                              static_cast<int>(r.end_ids.size()));
+  set_logits_ld(bs);
   beam_.reset(bs, r.start_id, dtype_, stream_);
   run_search(bs, S, std::max<int64_t>(0, r.min_decoding_length));
   return beam_.collect(bs, r.length_penalty, r.num_hypotheses, r.return_end_token ? std::vector<int32_t>{} : r.end_ids, stream_);
@@ -569,6 +592,7 @@ void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t step
   CT2_CUDA_CHECK(cudaMemcpy(src_ids_.ptr, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
   CT2_CUDA_CHECK(cudaMemcpy(src_lens_.ptr, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice));
   BeamState bs = beam_.state(batch, beam, mc_.tgt_vocab, L, 0, 1.f, 1.f, 1, 0);   // no end token: nothing finishes early
+  set_logits_ld(bs);
   std::vector<int64_t> key = {-1, batch, beam, source_len, bs.stride, L};
   if (key != graph_key_) {
     if (graph_) {
@@ -700,6 +724,7 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
 
   // ---- prompt: WhisperDecoder::forward_prompt on prompt[:-1], one position per step, no search ----
   BeamState bs = beam_.state(B, beam, mc_.tgt_vocab, steps, 0, r.patience, r.length_penalty, r.num_hypotheses, 1);
+  set_logits_ld(bs);
   bs.start_step = static_cast<int>(start_step);
   bs.include_eos = 0;                                  // whisper.cc:309
   bs.num_disable = static_cast<int>(r.suppress_ids.size());
@@ -720,7 +745,7 @@ std::vector<TranslationHypotheses> Translator::whisper_generate(const WhisperReq
     decoder_step(N, beam, B, S);
     if (no_speech_h && t == sot_index) {
       CT2_REQUIRE(r.no_speech_id >= 0, "return_no_speech_prob needs the id of <|nospeech|>");
-      launch_token_prob(logits_.ptr, B, mc_.tgt_vocab, static_cast<int64_t>(beam) * mc_.tgt_vocab, r.no_speech_id,
+      launch_token_prob(logits_.ptr, B, mc_.tgt_vocab, static_cast<int64_t>(beam) * logits_ld_, r.no_speech_id,
                         no_speech_d_.as<float>(), dtype_, stream_);
     }
     launch_beam_force(bs, forced_d_.as<int32_t>() + (t + 1) * N, stream_);

@@ -111,8 +111,10 @@ class Translator {
   void load_norm(const ModelFile& f, const std::string& prefix, NormWeights& n);
   void ensure_arena(int64_t batch, int64_t src_len, int beam, int64_t max_steps);
   // Dense on T rows (quantizes them for int8 weights); `pre` = the LayerNorm applied first (fused with the quantization)
-  void dense(const DenseWeights& w, const NormWeights* pre, const void* x, int64_t rows, const void* residual, int act, void* y);
-  void post_norm(const NormWeights& n, void* x, int64_t rows);
+  void dense(const DenseWeights& w, const NormWeights* pre, const void* x, int64_t rows, const void* residual, int act, void* y,
+             bool prequantized = false, int64_t ldy = 0);
+  void set_logits_ld(BeamState& bs);
+  bool post_norm(const NormWeights& n, void* x, int64_t rows, const DenseWeights* next);
   void run_encoder(int64_t batch, int64_t S);
   void run_encoder_layers(int64_t batch, int64_t S, const int32_t* lens_d);
   void run_whisper_encoder(int64_t batch, int64_t frames);
@@ -141,6 +143,7 @@ class Translator {
   DeviceBuffer src_ids_, src_lens_, x_, xn_, xq_, xs_, qkv_, ctx_, h_, q_, memory_;
   std::vector<DeviceBuffer> mem_kv_, self_k_, self_v_;
   DeviceBuffer logits_;
+  int64_t logits_ld_ = 0;                 // row stride of logits_ for the current search (set_logits_ld)
   BeamSearchArena beam_;         // search state: next ids, scores, histories, ancestry, hypotheses, counters
   DeviceBuffer features_, cols_, conv_out_, suppress_d_, forced_d_, no_speech_d_;   // Whisper
   int64_t cap_frames_ = 0;

@@ -1,7 +1,7 @@
-// awq_gemv.cu — AWQ-INT4 Dense for a handful of rows (m <= 4) on the CUDA cores: the latency path of the decode step.
+// awq_gemv.cu — AWQ-INT4 Dense for one or two rows on the CUDA cores: the latency path of the decode step (batch 1).
 //
 // Replaces ops::GemvAwq (src/ops/awq/gemv_gpu.cu:289-470: one warp per output channel, fp32 FMAs, a second launch for the
-// split-K sum at m > 8) + bias / activation / Mul.  At m = 1..4 the tensor cores have nothing to amortise: the work is
+// split-K sum at m > 8) + bias / activation / Mul.  At m = 1, 2 the tensor cores have nothing to amortise: the work is
 // streaming 0.5 byte per weight and turning it into fp16 once.  One warp owns one output channel; per trip a lane loads 16
 // bytes of packed nibbles (32 channels, one quantization group), turns them into the exact integers q - z as fp16 with the
 // lop3 magic-number trick of awq_common.cuh and multiplies them with the activation rows in packed half2 math; 16 products
@@ -12,7 +12,8 @@
 // pipeline hand-over per K block instead).  No shared memory, no barriers; the activations come through L1.
 //
 // Native layout (ct2b200_awq_repack): wp int32 [n, k/8] (word w of row c = channels 8w .. 8w+7 in nibbles {0,4,1,5,2,6,3,7}),
-// sc / zr fp16 [n, k/group].  k % 32 == 0, group % 32 == 0.
+// sc / zr fp16 [n, k/group].  group = 128 (what AutoAWQ writes and the reference's kernels assume), k % 128 == 0, k <= 16384;
+// other shapes and m > 2 go to the tensor-core kernels (awq_decode.cu, awq.cu).
 #include "awq_common.cuh"
 #include "gemm_decode_common.cuh"
 #include "kernels.h"
@@ -38,68 +39,113 @@ struct GemvParams {
   int act;
 };
 
+// One warp = one output channel.  A "trip" is 1024 input channels (a lane owns 32 of them = one 16-byte load of nibbles);
+// trips are processed four at a time with all their weight loads issued first, so a lane keeps 64 (NB = 2: 128) bytes of the
+// HBM stream in flight — with 24+ resident warps per SM that covers the bandwidth-delay product (~40 KB per SM).  The
+// group scales / zeros of the row (k / 128 of each) are fetched once with coalesced loads — lane g holds group g + 32 c
+// of chunk c — and handed to the lane that needs them by shuffle: trip u of chunk c uses group 32 c + 8 u + lane / 4.
+constexpr int kChunkTrips = 4;
+constexpr int kMaxChunks = 4;          // k <= 16384
+
 template <int M, int NB>
 __global__ void __launch_bounds__(kWarps * 32) awq_gemv_kernel(const __half* __restrict__ x, GemvWeight w0, GemvWeight w1,
                                                                GemvParams p) {
   griddep_launch();
-  griddep_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t ch = static_cast<int64_t>(blockIdx.x) * kWarps + warp;
-  if (ch >= p.n) return;
-  const int64_t words = p.k / 8, ng = p.k / p.group;
+  if (ch >= p.n) {
+    griddep_wait();
+    return;
+  }
+  const int64_t words = p.k / 8;
+  const int ng = static_cast<int>(p.k / 128);
+  const int chunks = static_cast<int>((p.k + 4095) / 4096);
+
+  // the weights, scales and zeros never depend on the previous kernel: requested before the dependency wait
+  __half sc_r[NB][kMaxChunks], zr_r[NB][kMaxChunks];
+#pragma unroll
+  for (int b = 0; b < NB; ++b) {
+    const GemvWeight& w = b == 0 ? w0 : w1;
+#pragma unroll
+    for (int c = 0; c < kMaxChunks; ++c) {
+      const int g = c * 32 + lane;
+      sc_r[b][c] = g < ng ? w.sc[ch * ng + g] : __float2half(0.f);
+      zr_r[b][c] = g < ng ? w.zr[ch * ng + g] : __float2half(0.f);
+    }
+  }
   float acc[NB][M];
 #pragma unroll
   for (int b = 0; b < NB; ++b)
 #pragma unroll
     for (int r = 0; r < M; ++r) acc[b][r] = 0.f;
 
-  // a lane's 32 channels of trip `it` start at k0 = it * 1024 + lane * 32
-  for (int64_t k0 = static_cast<int64_t>(lane) * 32; k0 < p.k; k0 += 1024) {
-    uint4 q[NB];
-    __half2 zb[NB], zt[NB];
-    float sc_f[NB];
+  uint4 q[NB][kChunkTrips];
+  auto load_chunk = [&](int c) {
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const GemvWeight& w = b == 0 ? w0 : w1;
-      q[b] = __ldcs(reinterpret_cast<const uint4*>(w.wp + ch * words + k0 / 8));      // streamed once: evict first
-      const int64_t g = ch * ng + k0 / p.group;
-      const __half sc = w.sc[g], zp = w.zr[g];
-      zb[b] = __half2half2(__hadd(__float2half(1024.f), zp));
-      zt[b] = __half2half2(__hneg(__hadd(__float2half(64.f), zp)));
-      sc_f[b] = __half2float(sc);
+    for (int u = 0; u < kChunkTrips; ++u) {
+      const int64_t k0 = (static_cast<int64_t>(c) * kChunkTrips + u) * 1024 + lane * 32;
+#pragma unroll
+      for (int b = 0; b < NB; ++b) {
+        const GemvWeight& w = b == 0 ? w0 : w1;
+        q[b][u] = k0 < p.k ? __ldcs(reinterpret_cast<const uint4*>(w.wp + ch * words + k0 / 8)) : make_uint4(0, 0, 0, 0);
+      }
     }
-    uint4 xv[M][4];
+  };
+  load_chunk(0);
+  griddep_wait();                                  // the activations come from the previous kernel
+
 #pragma unroll
-    for (int r = 0; r < M; ++r)
+  for (int c = 0; c < kMaxChunks; ++c) {
+    if (c >= chunks) break;
 #pragma unroll
-      for (int j = 0; j < 4; ++j) xv[r][j] = __ldg(reinterpret_cast<const uint4*>(x + r * p.k + k0) + j);
+    for (int u = 0; u < kChunkTrips; ++u) {
+      const int64_t k0 = (static_cast<int64_t>(c) * kChunkTrips + u) * 1024 + lane * 32;
+      const bool live = k0 < p.k;                                        // warp-uniform only for whole trips: predicate per lane
+      __half2 zb[NB], zt[NB];
+      float sc_f[NB];
 #pragma unroll
-    for (int b = 0; b < NB; ++b) {
-      const uint32_t wq[4] = {q[b].x, q[b].y, q[b].z, q[b].w};
+      for (int b = 0; b < NB; ++b) {
+        const int src = u * 8 + (lane >> 2);
+        const __half sc = __shfl_sync(0xffffffffu, sc_r[b][c], src), zp = __shfl_sync(0xffffffffu, zr_r[b][c], src);
+        zb[b] = __half2half2(__hadd(__float2half(1024.f), zp));
+        zt[b] = __half2half2(__hneg(__hadd(__float2half(64.f), zp)));
+        sc_f[b] = live ? __half2float(sc) : 0.f;
+      }
+      uint4 xv[M][4];
 #pragma unroll
-      for (int half_trip = 0; half_trip < 2; ++half_trip) {      // 16 channels -> one half2 partial sum per row
-        __half2 part[M];
+      for (int r = 0; r < M; ++r)
 #pragma unroll
-        for (int r = 0; r < M; ++r) part[r] = __float2half2_rn(0.f);
+        for (int j = 0; j < 4; ++j)
+          xv[r][j] = live ? *(reinterpret_cast<const uint4*>(x + r * p.k + k0) + j) : make_uint4(0, 0, 0, 0);
 #pragma unroll
-        for (int jj = 0; jj < 2; ++jj) {
-          const int j = half_trip * 2 + jj;
-          const uint4 d = awq_unscaled_word(wq[j], zb[b], zt[b]);
-          const __half2* dv = reinterpret_cast<const __half2*>(&d);
+      for (int b = 0; b < NB; ++b) {
+        const uint32_t wq[4] = {q[b][u].x, q[b][u].y, q[b][u].z, q[b][u].w};
+#pragma unroll
+        for (int half_trip = 0; half_trip < 2; ++half_trip) {      // 16 channels -> one half2 partial sum per row
+          __half2 part[M];
+#pragma unroll
+          for (int r = 0; r < M; ++r) part[r] = __float2half2_rn(0.f);
+#pragma unroll
+          for (int jj = 0; jj < 2; ++jj) {
+            const int j = half_trip * 2 + jj;
+            const uint4 d = awq_unscaled_word(wq[j], zb[b], zt[b]);
+            const __half2* dv = reinterpret_cast<const __half2*>(&d);
+#pragma unroll
+            for (int r = 0; r < M; ++r) {
+              const __half2* xh = reinterpret_cast<const __half2*>(&xv[r][j]);
+#pragma unroll
+              for (int i = 0; i < 4; ++i) part[r] = __hfma2(dv[i], xh[i], part[r]);
+            }
+          }
 #pragma unroll
           for (int r = 0; r < M; ++r) {
-            const __half2* xh = reinterpret_cast<const __half2*>(&xv[r][j]);
-#pragma unroll
-            for (int i = 0; i < 4; ++i) part[r] = __hfma2(dv[i], xh[i], part[r]);
+            const float2 f = __half22float2(part[r]);
+            acc[b][r] = fmaf(f.x + f.y, sc_f[b], acc[b][r]);
           }
-        }
-#pragma unroll
-        for (int r = 0; r < M; ++r) {
-          const float2 f = __half22float2(part[r]);
-          acc[b][r] = fmaf(f.x + f.y, sc_f[b], acc[b][r]);
         }
       }
     }
+    if (c + 1 < chunks) load_chunk(c + 1);
   }
 #pragma unroll
   for (int b = 0; b < NB; ++b)
@@ -125,21 +171,17 @@ void launch_gemv(const void* x, const AwqNative& a, const AwqNative* b, int64_t 
                                        static_cast<const __half*>(b->zr)} : w0;
   const dim3 grid(static_cast<unsigned>((a.n + kWarps - 1) / kWarps)), block(kWarps * 32);
   const __half* xh = static_cast<const __half*>(x);
-  switch (m) {
-    case 1: launch_pdl(awq_gemv_kernel<1, NB>, grid, block, 0, st, xh, w0, w1, p); break;
-    case 2: launch_pdl(awq_gemv_kernel<2, NB>, grid, block, 0, st, xh, w0, w1, p); break;
-    case 3: launch_pdl(awq_gemv_kernel<3, NB>, grid, block, 0, st, xh, w0, w1, p); break;
-    default: launch_pdl(awq_gemv_kernel<4, NB>, grid, block, 0, st, xh, w0, w1, p); break;
-  }
+  if (m == 1) launch_pdl(awq_gemv_kernel<1, NB>, grid, block, 0, st, xh, w0, w1, p);
+  else launch_pdl(awq_gemv_kernel<2, NB>, grid, block, 0, st, xh, w0, w1, p);
   check_launch();
 }
 
 bool covered(const AwqNative& w, int64_t m, const void* x) {
-  return m >= 1 && m <= 4 && w.k % 32 == 0 && w.group % 32 == 0 && w.k % w.group == 0 &&
-         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w.wp) & 15) == 0 && (w.k / 8) % 4 == 0;
+  return m >= 1 && m <= 2 && w.group == 128 && w.k % 128 == 0 && w.k <= 4096 * kMaxChunks &&
+         (reinterpret_cast<uintptr_t>(x) & 15) == 0 && (reinterpret_cast<uintptr_t>(w.wp) & 15) == 0;
 }
 
-// CT2B200_AWQ_GEMV: 1 = use this kernel for m <= 4 (opt-in until its hardware validation is recorded in profiles/README.md)
+// CT2B200_AWQ_GEMV: 1 = use this kernel for m <= 2 (opt-in until its hardware validation is recorded in profiles/README.md)
 bool enabled() { return dec::env_int("CT2B200_AWQ_GEMV", CT2B200_DEFAULT_AWQ_GEMV) != 0; }
 
 }  // namespace

@@ -193,6 +193,7 @@ void launch_attention_cross(const void* q, const void* kv, const int32_t* length
 // device state of BeamSearch::search (decoding.cc:425-720); N = batch * beam rows, `stride` = allocated steps per row
 struct BeamState {
   int batch = 0, beam = 1, vocab = 0, stride = 0, max_steps = 0, max_hyp = 0, max_candidates = 1, num_hypotheses = 1;
+  int64_t vocab_ld = 0;             // row stride of the logits (>= vocab; a multiple of 8 lets the kernels use 16-byte accesses)
   int early_exit = 0, num_end = 0, min_length = 0;
   int start_step = 0;               // absolute position of the first search step (prompt positions come before)
   int include_eos = 1;              // DecodingOptions::include_eos_in_hypotheses
@@ -218,6 +219,10 @@ struct BeamState {
 };
 void launch_beam_init(void* cum, int32_t* ids, int64_t rows, int beam, int start_id, int dtype, cudaStream_t st);
 void launch_beam_logprobs(void* logits, const void* cum, const BeamState& s, int dtype, cudaStream_t st);
+// beam <= 8: scores + the top 2 * beam of every ROW in one launch (row_scores T / row_ids int32 [batch * beam, 2 * beam], ids
+// flattened over [beam, vocab]); launch_beam_update(per_row = true) merges the rows of an entry
+void launch_beam_rows(void* logits, const void* cum, const BeamState& s, void* row_scores, int32_t* row_ids, int dtype,
+                      cudaStream_t st);
 // one prompt position without a search step: next ids = forced_next [rows], identity ancestry, step + 1
 void launch_beam_force(const BeamState& s, const int32_t* forced_next, cudaStream_t st);
 // out[r] = softmax(logits[r * row_stride : +vocab])[token]
@@ -227,7 +232,7 @@ void launch_token_prob(const void* logits, int64_t rows, int64_t vocab, int64_t 
 void launch_im2col(const void* x, bool x_is_f32, int64_t batch, int64_t Cin, int64_t Tin, int64_t Tout, int K, int stride,
                    int padding, bool channel_major, void* cols, int dtype, cudaStream_t st);
 void launch_add_positions(void* x, const void* pos, int64_t rows, int64_t time, int64_t depth, int dtype, cudaStream_t st);
-void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, int dtype,
+void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, bool per_row, int dtype,
                         cudaStream_t st);
 // Decoder::update_state / replicate_state for the contiguous per-row caches of the decoder-only engine (decoder.cc:33-139):
 // dst[row] = src[parent[row]] (parent == null: src[row / beam]) for positions [0, positions) of every kv head;

@@ -126,6 +126,7 @@ struct AttnGeneric {
   int H, D;
   float scale;
   int max_keys;              // capacity of the per-warp score buffer
+  bool vec_ok;               // every row start (q, k, v, caches, out) is 16-byte aligned
 };
 
 constexpr int kAttnWarps = 4;
@@ -181,21 +182,32 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
     if constexpr (MODE == 1) return (j == step ? n : static_cast<int64_t>(anc[j])) * a.S + j;
     else return base + j;
   };
-  // scores: one key per lane
-  float m = -INFINITY;
-  for (int j = lane; j < nkeys; j += 32) {
-    const T* kr = kb + key_row(j) * a.kv_stride + h * D;
+  // 16-byte loads of the key rows / paired loads of the value rows when the layout allows (head_dim 64, 128, ...: every model
+  // this kernel serves); the accumulation order over a row is the same in both forms
+  constexpr int NV = Vec16<T>::N;
+  const bool vec = a.vec_ok && D % NV == 0;
+  auto dot_row = [&](const T* kr) {
     float dot = 0.f;
-    if constexpr (MODE == 1) {
-      if (j == step) {          // own key: not necessarily visible through the cache pointer yet
-        const T* knew = static_cast<const T*>(a.q) + n * a.q_stride + d_model + h * D;
-        for (int i = 0; i < D; ++i) dot += qs[i] * to_f32(knew[i]);
-      } else {
-        for (int i = 0; i < D; ++i) dot += qs[i] * to_f32(kr[i]);
+    if (vec) {
+      for (int c = 0; c < D; c += NV) {
+        const Vec16<T> kk = ld16(kr + c);
+#pragma unroll
+        for (int i = 0; i < NV; ++i) dot += qs[c + i] * to_f32(kk.v[i]);
       }
     } else {
       for (int i = 0; i < D; ++i) dot += qs[i] * to_f32(kr[i]);
     }
+    return dot;
+  };
+  // scores: one key per lane
+  float m = -INFINITY;
+  for (int j = lane; j < nkeys; j += 32) {
+    const T* kr = kb + key_row(j) * a.kv_stride + h * D;
+    if constexpr (MODE == 1) {
+      // own key: not necessarily visible through the cache pointer yet
+      if (j == step) kr = static_cast<const T*>(a.q) + n * a.q_stride + d_model + h * D;
+    }
+    const float dot = dot_row(kr);
     const float s = round_to<T>(dot * a.scale);
     sc[j] = s;
     m = fmaxf(m, s);
@@ -206,8 +218,32 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
   sum = warp_sum(sum);
   for (int j = lane; j < nkeys; j += 32) sc[j] = round_to<T>(expf(sc[j] - m) / sum);
   __syncwarp();
-  // context: one output dimension per lane
   T* orow = static_cast<T*>(a.out) + n * a.out_stride + h * D;
+  auto value_row = [&](int j) -> const T* {
+    if constexpr (MODE == 1) {
+      if (j == step) return static_cast<const T*>(a.q) + n * a.q_stride + 2 * d_model + h * D;
+    }
+    return vb + key_row(j) * a.kv_stride + h * D;
+  };
+  if (vec && sizeof(T) == 2 && D % 64 == 0) {
+    // context: two adjacent output dimensions per lane, one 4-byte load per key (a warp reads 128 contiguous bytes)
+    for (int i = 2 * lane; i < D; i += 64) {
+      float a0 = 0.f, a1 = 0.f;
+      for (int j = 0; j < nkeys; ++j) {
+        const T* vr = value_row(j);
+        const uint32_t w = *reinterpret_cast<const uint32_t*>(vr + i);
+        T e[2];
+        *reinterpret_cast<uint32_t*>(e) = w;
+        const float p = sc[j];
+        a0 += p * to_f32(e[0]);
+        a1 += p * to_f32(e[1]);
+      }
+      T o[2] = {from_f32<T>(a0), from_f32<T>(a1)};
+      *reinterpret_cast<uint32_t*>(orow + i) = *reinterpret_cast<const uint32_t*>(o);
+    }
+    return;
+  }
+  // context: one output dimension per lane
   for (int i = lane; i < D; i += 32) {
     float acc = 0.f;
     for (int j = 0; j < nkeys; ++j) {
@@ -229,21 +265,16 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
 // ---------------------------------------------------------------------------------------------
 // Step 1 per row of [B*beam, V]: DisableTokens of the end ids while step < min_length (apply_min_length, decoding.cc:60-81),
 // ops::LogSoftMax in fp32 -> T, then primitives::add_depth_broadcast of the beam's cumulative score IN T (decoding.cc:548-553).
+// DisableTokens (decoding_utils.h:20-60) on one row of logits, in place: the end ids below min_length, SuppressTokens,
+// SuppressTokensBegin at the first step, Whisper's ApplyTimestampRules.  Ends with a block barrier.
 template <typename T>
-__global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logits, const T* __restrict__ cum, BeamState st) {
-  __shared__ float red[32];
-  __shared__ int s_check;
-  griddep_launch();
-  griddep_wait();
-  const int64_t row = blockIdx.x, vocab = st.vocab;
-  T* xr = logits + row * vocab;
-  const int abs_step = *st.step;
+__device__ __forceinline__ void beam_mask_row(T* xr, const BeamState& st, int64_t row, int abs_step, float* red, int* s_check) {
+  const int64_t vocab = st.vocab;
   const int step = abs_step - st.start_step;           // steps of the search (the prompt was forwarded before)
   const T lowest = from_f32<T>(lowest_of<T>());
   auto disable_range = [&](int lo, int hi) {           // [lo, hi)
     for (int j = lo + threadIdx.x; j < hi; j += blockDim.x) xr[j] = lowest;
   };
-  // DisableTokens (decoding_utils.h:20-60): end ids below min_length, SuppressTokens, SuppressTokensBegin at the first step
   if (step < st.min_length)
     for (int e = threadIdx.x; e < st.num_end; e += blockDim.x)
       if (st.end_ids[e] >= 0 && st.end_ids[e] < vocab) xr[st.end_ids[e]] = lowest;
@@ -257,7 +288,7 @@ __global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logi
     const int64_t N = static_cast<int64_t>(st.batch) * st.beam;
     const int32_t* hist = st.alive + static_cast<int64_t>(abs_step & 1) * N * st.stride + row * st.stride;
     if (threadIdx.x == 0) {
-      s_check = 0;
+      *s_check = 0;
       xr[st.ts_no_timestamps] = lowest;
     }
     __syncthreads();
@@ -273,10 +304,10 @@ __global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logi
         } else {
           disable_range(0, st.ts_eot);                                 // text cannot follow a single timestamp
           disable_range(st.ts_begin, last);
-          if (threadIdx.x == 0) s_check = 1;
+          if (threadIdx.x == 0) *s_check = 1;
         }
       } else {
-        if (threadIdx.x == 0) s_check = 1;
+        if (threadIdx.x == 0) *s_check = 1;
         int prev = -1;                                                 // timestamps do not decrease
         for (int t = step - 1; t >= 0; --t)
           if (hist[t] >= st.ts_begin) {
@@ -287,7 +318,7 @@ __global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logi
       }
     }
     __syncthreads();
-    if (s_check) {
+    if (*s_check) {
       // if the probability mass of the timestamps exceeds every text token, a timestamp is sampled (should_sample_timestamp)
       float m = -INFINITY;
       for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) m = fmaxf(m, to_f32(xr[j]));
@@ -308,6 +339,17 @@ __global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logi
     }
   }
   __syncthreads();
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logits, const T* __restrict__ cum, BeamState st) {
+  __shared__ float red[32];
+  __shared__ int s_check;
+  griddep_launch();
+  griddep_wait();
+  const int64_t row = blockIdx.x, vocab = st.vocab;
+  T* xr = logits + row * st.vocab_ld;
+  beam_mask_row(xr, st, row, *st.step, red, &s_check);
   float m = -INFINITY;
   for (int64_t j = threadIdx.x; j < vocab; j += blockDim.x) m = fmaxf(m, to_f32(xr[j]));
   m = block_reduce<true>(m, red);
@@ -320,6 +362,105 @@ __global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logi
     xr[j] = from_f32<T>(round_to<T>(to_f32(xr[j]) - m - logs) + c);
 }
 
+// Steps 1 + 2 in one pass over the logits (beam <= 8): the scores above are never written back.  A candidate of the entry's
+// top 2 * beam (ops::TopK over the flattened [beam * vocab] scores, decoding.cc:556-563) is necessarily among the top
+// 2 * beam of its own row, so every row selects its own — each thread keeps a sorted list of its best KT scores (the same
+// T-rounded values the three-kernel path stores) and the lists are merged by 2 * beam block-wide arg-max rounds — and
+// beam_update_kernel merges the beam rows of an entry.  Order everywhere: (score desc, flattened index asc), the order of
+// topk_kernel (rowwise.cu).  Rows whose stride allows it are read with 16-byte loads.
+constexpr int kRowsThreads = 512;
+
+template <typename T, typename F>
+__device__ __forceinline__ void for_row_elements(const T* xr, int64_t n, bool vec_ok, F f) {
+  constexpr int N = Vec16<T>::N;
+  if (vec_ok) {
+    const int64_t nvec = n / N;
+    for (int64_t vi = threadIdx.x; vi < nvec; vi += blockDim.x) {
+      const Vec16<T> d = ld16(xr + vi * N);
+#pragma unroll
+      for (int i = 0; i < N; ++i) f(to_f32(d.v[i]), static_cast<int32_t>(vi * N + i));
+    }
+    for (int64_t j = nvec * N + threadIdx.x; j < n; j += blockDim.x) f(to_f32(xr[j]), static_cast<int32_t>(j));
+  } else {
+    for (int64_t j = threadIdx.x; j < n; j += blockDim.x) f(to_f32(xr[j]), static_cast<int32_t>(j));
+  }
+}
+
+__device__ __forceinline__ bool score_better(float v, int32_t i, float bv, int32_t bi) { return v > bv || (v == bv && i < bi); }
+
+template <typename T, int KT>
+__global__ void __launch_bounds__(kRowsThreads) beam_rows_kernel(T* __restrict__ logits, const T* __restrict__ cum, BeamState st,
+                                                                T* __restrict__ row_scores, int32_t* __restrict__ row_ids) {
+  __shared__ float red[32];
+  __shared__ int s_check;
+  __shared__ float s_bv[2][kRowsThreads / 32];
+  __shared__ int32_t s_bi[2][kRowsThreads / 32];
+  griddep_launch();
+  griddep_wait();
+  const int64_t row = blockIdx.x, vocab = st.vocab;
+  T* xr = logits + row * st.vocab_ld;
+  beam_mask_row(xr, st, row, *st.step, red, &s_check);
+  const bool vec_ok = (reinterpret_cast<uintptr_t>(xr) & 15) == 0;
+  float m = -INFINITY;
+  for_row_elements(xr, vocab, vec_ok, [&](float v, int32_t) { m = fmaxf(m, v); });
+  m = block_reduce<true>(m, red);
+  float s = 0.f;
+  for_row_elements(xr, vocab, vec_ok, [&](float v, int32_t) { s += expf(v - m); });
+  s = block_reduce<false>(s, red);
+  const float logs = logf(s);
+  const float c = to_f32(cum[row]);
+  float tv[KT];
+  int32_t ti[KT];
+#pragma unroll
+  for (int k = 0; k < KT; ++k) { tv[k] = -INFINITY; ti[k] = INT32_MAX; }
+  for_row_elements(xr, vocab, vec_ok, [&](float x, int32_t j) {
+    const float v = round_to<T>(round_to<T>(x - m - logs) + c);
+    if (score_better(v, j, tv[KT - 1], ti[KT - 1])) {
+      tv[KT - 1] = v;
+      ti[KT - 1] = j;
+#pragma unroll
+      for (int k = KT - 1; k > 0; --k)
+        if (score_better(tv[k], ti[k], tv[k - 1], ti[k - 1])) {
+          const float fv = tv[k]; tv[k] = tv[k - 1]; tv[k - 1] = fv;
+          const int32_t fi = ti[k]; ti[k] = ti[k - 1]; ti[k - 1] = fi;
+        }
+    }
+  });
+  // merge: 2 * beam rounds; the thread that owns the round's best pops it
+  const int nc = 2 * st.beam, lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int64_t base = (row % st.beam) * vocab;
+  for (int r = 0; r < nc; ++r) {
+    float bv = tv[0];
+    int32_t bi = ti[0];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (score_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (lane == 0) { s_bv[r & 1][warp] = bv; s_bi[r & 1][warp] = bi; }
+    __syncthreads();
+    bv = lane < kRowsThreads / 32 ? s_bv[r & 1][lane] : -INFINITY;
+    bi = lane < kRowsThreads / 32 ? s_bi[r & 1][lane] : INT32_MAX;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const float ov = __shfl_xor_sync(0xffffffffu, bv, o);
+      const int32_t oi = __shfl_xor_sync(0xffffffffu, bi, o);
+      if (score_better(ov, oi, bv, bi)) { bv = ov; bi = oi; }
+    }
+    if (ti[0] == bi && bi != INT32_MAX) {            // indices are unique: exactly one owner
+#pragma unroll
+      for (int k = 0; k + 1 < KT; ++k) { tv[k] = tv[k + 1]; ti[k] = ti[k + 1]; }
+      tv[KT - 1] = -INFINITY;
+      ti[KT - 1] = INT32_MAX;
+    }
+    if (threadIdx.x == 0) {
+      row_scores[row * nc + r] = from_f32<T>(bv);
+      row_ids[row * nc + r] = bi == INT32_MAX ? -1 : static_cast<int32_t>(base + bi);
+    }
+  }
+}
+
 // Step 3 (step 2 = ops::TopK of 2 * beam candidates over the flattened [beam * vocab] scores, rowwise.cu): one CTA per batch
 // entry walks the candidates exactly like decoding.cc:595-663 — a candidate among the first `beam` that ends (end token, or
 // last step) is registered as a hypothesis and its slot refilled from the secondary list — then rebuilds the beam state:
@@ -327,9 +468,12 @@ __global__ void __launch_bounds__(256) beam_logprobs_kernel(T* __restrict__ logi
 // Finished entries keep decoding (their results are frozen); the last CTA to finish advances the step counter.
 template <typename T>
 __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T* __restrict__ cand_scores,
-                                                          const int32_t* __restrict__ cand_ids, T* __restrict__ cum) {
+                                                          const int32_t* __restrict__ cand_ids, T* __restrict__ cum,
+                                                          bool per_row) {
   __shared__ int s_origin[64], s_word[64], s_active[32], s_hyp[32];
   __shared__ float s_score[64];
+  __shared__ float s_cv[128];
+  __shared__ int32_t s_ci[128];
   __shared__ int s_last;
   griddep_launch();
   griddep_wait();
@@ -338,7 +482,29 @@ __global__ void __launch_bounds__(128) beam_update_kernel(BeamState st, const T*
   const int step = *st.step;                 // absolute position (indexes the K/V arena and the ancestry table)
   const int rel = step - st.start_step;      // step of the search (indexes the token history)
   const int N = st.batch * beam;
-  if (threadIdx.x < nc) {
+  if (per_row) {
+    // candidates [beam rows][nc] of beam_rows_kernel: the entry's top nc by rank (the order is total: ids are unique)
+    const int total = beam * nc;             // <= 128
+    float v = -INFINITY;
+    int32_t id = INT32_MAX;
+    if (threadIdx.x < total) {
+      v = to_f32(cand_scores[static_cast<int64_t>(i) * total + threadIdx.x]);
+      id = cand_ids[static_cast<int64_t>(i) * total + threadIdx.x];
+      if (id < 0) id = INT32_MAX;
+    }
+    s_cv[threadIdx.x] = v;
+    s_ci[threadIdx.x] = id;
+    __syncthreads();
+    if (threadIdx.x < total && id != INT32_MAX) {
+      int rank = 0;
+      for (int j = 0; j < total; ++j) rank += score_better(s_cv[j], s_ci[j], v, id) ? 1 : 0;
+      if (rank < nc) {
+        s_origin[rank] = id / st.vocab;
+        s_word[rank] = id % st.vocab;
+        s_score[rank] = v;
+      }
+    }
+  } else if (threadIdx.x < nc) {
     const int flat = cand_ids[i * nc + threadIdx.x];
     s_origin[threadIdx.x] = flat / st.vocab;
     s_word[threadIdx.x] = flat % st.vocab;
@@ -564,7 +730,14 @@ void launch_layer_norm(const void* x, const void* gamma, const void* beta, int64
 
 namespace {
 template <typename T, int MODE>
-void launch_attn_mode(const AttnGeneric& a, cudaStream_t st) {
+void launch_attn_mode(const AttnGeneric& a_in, cudaStream_t st) {
+  AttnGeneric a = a_in;
+  {
+    const size_t es = sizeof(T);
+    auto al = [&](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
+    a.vec_ok = al(a.q) && al(a.k) && al(a.v) && al(a.out) && al(a.k_cache) && al(a.v_cache) && (a.q_stride * es) % 16 == 0 &&
+               (a.kv_stride * es) % 16 == 0 && (a.out_stride * es) % 16 == 0 && (static_cast<size_t>(a.D) * es) % 16 == 0;
+  }
   const size_t smem = static_cast<size_t>(kAttnWarps) * (a.max_keys + a.D) * sizeof(float);
   CT2_REQUIRE(smem <= 200 * 1024, "attention: too many keys for the generic kernel");
   auto kernel = attention_generic_kernel<T, MODE>;
@@ -665,6 +838,21 @@ void launch_beam_logprobs(void* logits, const void* cum, const BeamState& s, int
   check_launch();
 }
 
+void launch_beam_rows(void* logits, const void* cum, const BeamState& s, void* row_scores, int32_t* row_ids, int dtype,
+                      cudaStream_t st) {
+  const int64_t rows = static_cast<int64_t>(s.batch) * s.beam;
+  if (rows == 0) return;
+  CT2_REQUIRE(s.beam >= 1 && s.beam <= 8, "beam_rows: beam_size must be in [1, 8]");
+  if (s.beam <= 4) {
+    CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_rows_kernel<T, 8>, dim3(rows), dim3(kRowsThreads), 0, st, static_cast<T*>(logits),
+                                          static_cast<const T*>(cum), s, static_cast<T*>(row_scores), row_ids)));
+  } else {
+    CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_rows_kernel<T, 16>, dim3(rows), dim3(kRowsThreads), 0, st, static_cast<T*>(logits),
+                                          static_cast<const T*>(cum), s, static_cast<T*>(row_scores), row_ids)));
+  }
+  check_launch();
+}
+
 void launch_beam_force(const BeamState& s, const int32_t* forced_next, cudaStream_t st) {
   const int rows = s.batch * s.beam;
   beam_force_kernel<<<div_up(rows, 128), 128, 0, st>>>(s, forced_next);
@@ -699,11 +887,12 @@ void launch_add_positions(void* x, const void* pos, int64_t rows, int64_t time, 
   check_launch();
 }
 
-void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, int dtype,
+void launch_beam_update(const BeamState& s, const void* cand_scores, const int32_t* cand_ids, void* cum, bool per_row, int dtype,
                         cudaStream_t st) {
   CT2_REQUIRE(s.beam >= 1 && s.beam <= 32, "beam_size must be in [1, 32]");
+  CT2_REQUIRE(!per_row || s.beam <= 8, "beam_update: per-row candidates need beam_size <= 8");
   CT2_DISPATCH_DTYPE(dtype, (launch_pdl(beam_update_kernel<T>, dim3(s.batch), dim3(128), 0, st, s,
-                                        static_cast<const T*>(cand_scores), cand_ids, static_cast<T*>(cum))));
+                                        static_cast<const T*>(cand_scores), cand_ids, static_cast<T*>(cum), per_row)));
   check_launch();
 }
 

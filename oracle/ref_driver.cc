@@ -738,5 +738,39 @@ int ref_generate_timed(void* handle, const int32_t* prompt_ids, int B, int P, in
   });
 }
 
+// Per-step host timestamps of one greedy generate_batch through the public per-step callback (generation.h:77): stamps[s] =
+// seconds since the call started at which step s of batch entry 0 was delivered.  The prompt pass ends at stamps[0]; the decode
+// time per step is the slope of the later stamps — no difference of two prompt-dominated wall times is needed.
+int ref_generate_steps(void* handle, const int32_t* prompt_ids, int B, int P, int max_len, int end_id, double* stamps,
+                       double* seconds) {
+  auto* g = static_cast<RefGenerator*>(handle);
+  return guarded([&] {
+    std::vector<std::vector<std::string>> prompts(B);
+    for (int b = 0; b < B; ++b)
+      for (int t = 0; t < P; ++t)
+        prompts[b].push_back(g->vocab->to_token(prompt_ids[b * P + t]));
+    GenerationOptions opt;
+    opt.beam_size = 1;
+    opt.sampling_topk = 1;
+    opt.max_length = max_len;
+    opt.min_length = max_len;
+    opt.include_prompt_in_result = false;
+    opt.return_scores = false;
+    opt.end_token = std::vector<size_t>{static_cast<size_t>(end_id)};
+    for (int s = 0; s < max_len; ++s) stamps[s] = -1.0;
+    cudaDeviceSynchronize();
+    const auto t0 = std::chrono::steady_clock::now();
+    opt.callback = [&](GenerationStepResult r) {
+      if (r.batch_id == 0 && r.step < static_cast<size_t>(max_len) && stamps[r.step] < 0)
+        stamps[r.step] = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      return false;
+    };
+    auto futures = g->generator->generate_batch_async(prompts, opt, /*max_batch_size=*/0);
+    for (auto& f : futures) f.get();
+    cudaDeviceSynchronize();
+    *seconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+  });
+}
+
 }  // extern "C"
 #endif  // REF_DRIVER_CUDA

@@ -431,3 +431,17 @@ def _generate_timed(self, prompts, max_length, end_id=2):
 
 
 RefGenerator.generate_timed = _generate_timed
+
+
+def _generate_steps(self, prompts, max_length, end_id=2):
+    """(stamps [max_length], seconds): host time at which every step of batch entry 0 was delivered to the public per-step
+    callback (generation.h:77) during one greedy generate_batch; stamps[0] is the end of the prompt pass."""
+    prompts = _c(prompts, np.int32)
+    B, P = prompts.shape
+    stamps = np.zeros(max_length, np.float64)
+    sec = ctypes.c_double()
+    _check(lib().ref_generate_steps(ctypes.c_void_p(self.h), _p(prompts), B, P, max_length, end_id, _p(stamps), ctypes.byref(sec)))
+    return stamps, sec.value
+
+
+RefGenerator.generate_steps = _generate_steps

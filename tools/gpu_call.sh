@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench ncu ncufull bench translate bisect trprofile
+# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -17,28 +17,11 @@ stage_golden() {   # the reference's CUDA kernels on seeded inputs -> fixtures (
   cp $OUT/awq_ref_cuda.npz $OUT/dense_s8_ref_cuda.npz tests/golden/ 2>/dev/null
 }
 
-stage_tests() {    # opt-in kernels first, bounded: a hang (grid barrier, mbarrier protocol) must not take the box
-  CT2B200_AWQ_DECODE=1 timeout 600 python -m pytest tests/test_gpu_awq.py tests/test_gpu_ref_cuda.py -q -k "awq" > $OUT/pytest_awq.log 2>&1
-  echo "awq tests exit $?" >> $OUT/pytest_awq.log
-  AWQD=1
-  if ! grep -q " passed" $OUT/pytest_awq.log || grep -q "failed\|exit 124" $OUT/pytest_awq.log; then
-    echo "AWQ decode kernel NOT validated" >> $OUT/pytest_awq.log
-    AWQD=0
-  fi
+stage_tests() {    # the opt-in kernel first, bounded; then the whole GPU suite with the defaults of the tree
   CT2B200_AWQ_GEMV=1 timeout 600 python -m pytest tests/test_gpu_awq.py tests/test_gpu_ref_cuda.py -q -k "awq" > $OUT/pytest_awq_gemv.log 2>&1
   echo "awq gemv tests exit $?" >> $OUT/pytest_awq_gemv.log
-  GEMV=1
-  if ! grep -q " passed" $OUT/pytest_awq_gemv.log || grep -q "failed\|exit 124" $OUT/pytest_awq_gemv.log; then
-    echo "AWQ GEMV kernel NOT validated" >> $OUT/pytest_awq_gemv.log
-    GEMV=0
-  fi
-  echo "validated: AWQ_DECODE=$AWQD AWQ_GEMV=$GEMV" > $OUT/validated.txt
-  # the whole GPU suite with the defaults of the tree, then once more with the validated opt-ins switched on
   timeout 1500 python -m pytest tests -m gpu -q --tb=short > $OUT/pytest_gpu.log 2>&1
   echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
-  CT2B200_AWQ_DECODE=$AWQD CT2B200_AWQ_GEMV=$GEMV timeout 1500 python -m pytest tests/test_gpu_engine.py tests/test_gpu_ops.py tests/test_gpu_awq.py \
-    -m gpu -q > $OUT/pytest_gpu_optin.log 2>&1
-  echo "gpu suite (opt-ins on) exit $?" >> $OUT/pytest_gpu_optin.log
 }
 
 stage_shims() {    # the reference's own gtests with libct2b200 interposed under its ops (oracle/Makefile.shims)
@@ -60,8 +43,7 @@ stage_sweeps() {   # decode step of the INT8 8B model (64 steps after the 1024-t
 awq_run() { echo "== AWQ batch=$1 CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3" >> $OUT/sweep.log
   CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3 timeout 600 python tools/decode_once.py $1 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1; }
 stage_awq() {
-  awq_run 1 0 0; awq_run 1 1 0; awq_run 1 0 1; awq_run 4 0 1
-  awq_run 32 0 0; awq_run 32 1 0
+  awq_run 1 1 0; awq_run 1 1 1; awq_run 2 1 0; awq_run 2 1 1
 }
 
 stage_refbench() { # the reference's CUDA build on the same workload (bounded: 16 / 80 generated tokens)
@@ -93,17 +75,30 @@ stage_bench() {
   echo "bench exit $?" >> $OUT/bench.err
 }
 
-stage_bisect() {   # which commit broke the ragged 8B schedule / the eager scores test / the 8B comparison with the reference?
-  T="tests/test_gpu_engine.py::test_full_size_llama8b_properties tests/test_gpu_engine.py::test_generate_scores_match_reference"
-  for c in f7cebc7 f70f032 1a7d296 dc2c628; do
-    echo "=== commit $c" >> $OUT/bisect.log
-    ( cd bisect/$c && timeout 600 python -m pytest $T -q --tb=line 2>&1 | tail -6 ) >> $OUT/bisect.log
+stage_pdlrace() {  # eager decode loop under programmatic dependent launch: product build vs a build without ld.global.nc
+  T=tests/test_gpu_engine.py::test_generate_scores_match_reference
+  for i in 1 2 3; do
+    echo "=== product build, run $i" >> $OUT/pdlrace.log
+    timeout 300 python -m pytest $T -q --tb=line 2>&1 | tail -3 >> $OUT/pdlrace.log
+    echo "=== norestrict build (no read-only loads), run $i" >> $OUT/pdlrace.log
+    CT2B200_LIB=$PWD/ctranslate2_b200/libct2b200_norestrict.so timeout 300 python -m pytest $T -q --tb=line 2>&1 | tail -3 >> $OUT/pdlrace.log
   done
-  echo "=== HEAD" >> $OUT/bisect.log
-  timeout 600 python -m pytest $T -q --tb=line 2>&1 | tail -6 >> $OUT/bisect.log
-  for e in CT2B200_EOS_POLL=1 CT2B200_PDL=0 CT2B200_GEMM_DECODE=0 CT2B200_ATTN_DECODE=simt; do
-    echo "=== HEAD $e" >> $OUT/bisect.log
-    env $e timeout 600 python -m pytest $T -q --tb=line 2>&1 | tail -6 >> $OUT/bisect.log
+  echo "=== compute-sanitizer memcheck, eager" >> $OUT/pdlrace.log
+  timeout 900 compute-sanitizer --tool memcheck --print-limit 5 python -m pytest "$T[False]" -q --tb=line 2>&1 | tail -25 >> $OUT/pdlrace.log
+}
+stage_refstamps() { # the reference's CUDA build: decode ms/step from the per-step callback stamps
+  python -c "import bench; bench.model_dir('8b','int8_float16'); bench.model_dir('8b','awq_gemm')" 2>> $OUT/ref_cuda_stamps.log
+  for b in 1 32; do
+    timeout 600 python tools/ref_cuda_worker.py bench $M8 int8_float16 $b 1024 8 48 >> $OUT/ref_cuda_stamps.log 2>&1
+    timeout 600 python tools/ref_cuda_worker.py bench $MA float16 $b 1024 8 48 >> $OUT/ref_cuda_stamps.log 2>&1
+  done
+}
+stage_smemsweep() { # does a smaller operand ring (successor GEMM co-resident earlier) help the INT8 step?
+  for B in 1 32; do
+    run CT2B200_PDL=1
+    run CT2B200_GEMM_SMEM_KB=112
+    run CT2B200_GEMM_SMEM_KB=96
+    run CT2B200_GEMM_SMEM_KB=64
   done
 }
 stage_trprofile() {   # launch list of the OPUS-MT-shaped decoding step + timing
