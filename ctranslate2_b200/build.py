@@ -24,10 +24,18 @@ FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-std=c++17", "-O3", "-li
          "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr", "-x", "cu"]
 
 
+# No read-only-path loads (ld.global.nc): nvcc emits them for `const T* __restrict__` kernel parameters, on the promise that the
+# data is not written while the kernel is alive.  Under programmatic dependent launch a kernel is alive BEFORE its producer has
+# finished (it is scheduled early and blocks in griddepcontrol.wait), so the promise does not hold for activations: measured on
+# the B200, the eager decode loop (steps queued back to back, deep chains of co-resident kernels) returned stale logits in 3 of
+# 3 runs with these loads and in 0 of 3 without (profiles/README.md, round 2).  The qualifier is therefore compiled away for
+# device code; weights stream through TMA, so nothing that matters used that path.
+NO_NC_LOADS = "-D__restrict__="
+FLAGS.append(NO_NC_LOADS)
+
 # Experimental builds beside the product library: libct2b200_<variant>.so, loaded through CT2B200_LIB.
 VARIANTS = {
-    # no read-only (ld.global.nc) loads: the compiler only emits them for `const T* __restrict__` parameters
-    "norestrict": ["-D__restrict__="],
+    "restrict": None,      # keep __restrict__ (the pre-fix behaviour), for A/B timing
 }
 
 
@@ -62,7 +70,8 @@ def build(force=False, verbose=True, variant=None):
     if variant:
         OUT = os.path.join(HERE, "libct2b200_%s.so" % variant)
         OBJ = os.path.join(HERE, "_build_" + variant)
-        FLAGS = FLAGS + VARIANTS[variant]
+        assert variant in VARIANTS
+        FLAGS = [f for f in FLAGS if f != NO_NC_LOADS]
     os.makedirs(OBJ, exist_ok=True)
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, force), SOURCES))

@@ -162,6 +162,10 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
 bool pdl_enabled();
+// The next kernel this thread launches is a plain stream-ordered launch: it starts after EVERYTHING before it has completed.
+// The step graphs get this boundary for free (consecutive graph launches are fully ordered); the eager decode loops ask for
+// it at the first kernel of every step, so that programmatic overlap never spans two steps in either mode.
+void pdl_fence_next_launch();
 // true the first time (kernel, tag) is seen ON THE CURRENT DEVICE: function attributes (dynamic shared memory limit, carve-out)
 // and occupancy queries are per device, and a process may open generators on several (tag 0 = carve-out, 1 = smem limit)
 bool mark_configured(const void* kernel, int tag = 0);

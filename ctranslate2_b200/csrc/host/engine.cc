@@ -1221,6 +1221,7 @@ void Generator::generate(const GenerationRequest& r, int32_t* out_ids, int32_t* 
       CT2_CUDA_CHECK(cudaGraphLaunch(graph_, st));
       count_launch(static_cast<int>(graph_nodes_));
     } else {
+      pdl_fence_next_launch();
       launch_step(B, r.min_length, static_cast<int>(r.end_ids.size()));
     }
     if (s + 1 == total_steps || (s >= first_eos_step && (s - first_eos_step) % poll == poll - 1)) consume(s + 1);

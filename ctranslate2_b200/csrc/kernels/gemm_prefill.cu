@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         bs[et] = bv;
       }
       float sa = 1.f;
-      if constexpr (KIND == 0) sa = row_ok ? __ldg(p.a_scale + row) : 1.f;
+      if constexpr (KIND == 0) sa = row_ok ? p.a_scale[row] : 1.f;      // written by the previous kernel: not through the read-only path (build.py)
       epi_sync();                                  // column constants of this tile are in place
       mbar_wait(acc_full + buf, (seq >> 1) & 1);
       tc_fence_after();

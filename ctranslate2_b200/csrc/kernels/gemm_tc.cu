@@ -105,7 +105,7 @@ __device__ __forceinline__ void epi_load(const TcParams& p, int64_t arow, int64_
       in.st0 = __ldg(w_scale0 + arow);
       if constexpr (NB == 2) in.st1 = __ldg(w_scale1 + arow);
     } else {
-      in.st0 = __ldg(x_scale + arow);
+      in.st0 = x_scale[arow];                   // activation scales come from the previous kernel: plain loads (build.py)
     }
   }
   if (bias && kSwap) in.bias_t = to_f32(bias[arow]);
@@ -114,7 +114,7 @@ __device__ __forceinline__ void epi_load(const TcParams& p, int64_t arow, int64_
     const bool ok = j < in.ncols;
     if constexpr (KIND == 0) {
       if constexpr (kSwap) {
-        in.sj0[j] = ok ? __ldg(x_scale + brow0 + j * bstep) : 1.f;
+        in.sj0[j] = ok ? x_scale[brow0 + j * bstep] : 1.f;
       } else {
         in.sj0[j] = ok ? __ldg(w_scale0 + brow0 + j * bstep) : 1.f;
         if constexpr (NB == 2) in.sj1[j] = ok ? __ldg(w_scale1 + brow0 + j * bstep) : 1.f;

@@ -23,13 +23,23 @@ bool mark_configured(const void* kernel, int tag) {
   return seen.insert({kernel, tag, dev}).second;
 }
 
+namespace {
+thread_local bool t_pdl_fence = false;
+}
+
 bool pdl_enabled() {
   static const bool on = [] {
     const char* e = std::getenv("CT2B200_PDL");
     return !(e && e[0] == '0');
   }();
+  if (t_pdl_fence) {            // one launch on this thread with a full stream dependency (pdl_fence_next_launch)
+    t_pdl_fence = false;
+    return false;
+  }
   return on;
 }
+
+void pdl_fence_next_launch() { t_pdl_fence = true; }
 
 constexpr int kRowThreads = 256;
 

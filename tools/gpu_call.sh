@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep
+# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep tp2
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -105,6 +105,14 @@ stage_trprofile() {   # launch list of the OPUS-MT-shaped decoding step + timing
   timeout 300 python tools/translate_once.py 64 4 64 > $OUT/translate_once.log 2>&1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/r02_launches_translate.csv python tools/translate_once.py 64 4 2 >> $OUT/translate_once.log 2>&1
+}
+
+stage_tp2() {      # needs gpurun --gpus 2: tensor-parallel parity (tests/tp_worker.py) and the bench line with its `tp` record
+  timeout 900 python -m pytest tests/test_gpu_tp.py -q --tb=short > $OUT/pytest_tp.log 2>&1
+  echo "tp tests exit $?" >> $OUT/pytest_tp.log
+  timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+    bench.py --gpus 2 --steps 256 --warmup 3 > $OUT/bench_gpus2.json 2> $OUT/bench_gpus2.err
+  echo "bench --gpus 2 exit $?" >> $OUT/bench_gpus2.err
 }
 
 for s in "$@"; do
