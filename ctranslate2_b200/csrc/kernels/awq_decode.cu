@@ -6,11 +6,13 @@
 // Same plan as gemm_decode.cu (one tile per CTA, "swap AB": 128 output channels = the UMMA M side, activations = N side;
 // DSMEM split-K cluster chosen so that tiles x CS fills the SMs in one wave; weights prefetched before griddepcontrol.wait),
 // plus what 4-bit weights need:
-//   * the only bytes that come from HBM are the packed nibbles: 4 KB per 128-row x 64-channel block.  They get a deep TMA
-//     ring (up to 24 blocks in flight per SM); each ring slot also carries the block's 128 {scale, zero} pairs (512 B, one
-//     cp.async.bulk from the group-major array) and the activation block, so the transform warps never touch global memory.
-//     (Round 1 fetched the pairs with per-thread global loads inside the loop: ncu showed 64 % of the transform warps'
-//     samples on long_scoreboard and the kernel at 0.2 of the HBM peak.)
+//   * the only bytes that come from HBM are the packed nibbles.  A ring slot holds a SUPER-BLOCK of four K blocks (256 input
+//     channels): per weight one TMA box of 128 rows x 128 bytes (SWIZZLE_128B, so that the 32 rows a warp reads land in
+//     different banks), the {scale, zero} pairs of its groups (512 B each, cp.async.bulk from the group-major array) and the
+//     four activation atoms, so the transform warps never touch global memory.  The box width matters: TMA works row by row,
+//     and with one box per 64-channel block (128 rows x 32 bytes — the first version of this kernel) the row requests, not the
+//     bytes, set the pace: ncu showed every transform warp parked on the "slot full" barrier, 10 GB/s per SM and DRAM at 7-16 %.
+//     (Before that, round 1 fetched the pairs with per-thread global loads inside the loop: 64 % long_scoreboard.)
 //   * the dequantized fp16 operand never goes back to shared memory.  int4 -> fp16 at HBM speed is 5.8 TB/s of nibbles =
 //     23 TB/s of fp16, i.e. 82 B/clk/SM written + 82 B/clk/SM read by the tensor core: more than the 128 B/clk of the shared
 //     memory port.  Instead the thread that owns output channel r converts the 64 channels of its row in registers
@@ -38,27 +40,31 @@ constexpr int kDeqWarps = 16;          // 4 transform groups of 4 warps; group g
 constexpr int kGroups = 4;             // blocks are converted CONCURRENTLY (LDS -> lop3/hfma -> tcgen05.st is a latency chain)
 constexpr int kGroupWarps = kDeqWarps / kGroups;
 constexpr int kBKh = 64;               // fp16 channels per K block (one 128-byte swizzle atom of the activation operand)
-constexpr int kPacked = kTileM * kBKh / 2;      // 4096 bytes of nibbles per weight per block
-constexpr int kPairs = 1024;                    // slot of the 128 {scale, zero} pairs (512 B) of a weight; 1 KB keeps the
-                                                // 128B-swizzled activation operand behind it 1024-byte aligned
+constexpr int kSub = 4;                         // K blocks per ring slot = transform groups: group g converts sub-block g
+constexpr int kSlotK = kSub * kBKh;             // 256 input channels per slot
+constexpr int kPacked = kTileM * kSlotK / 2;    // 16 KB of nibbles per weight per slot (128 rows x 128 B, SWIZZLE_128B)
+constexpr int kPairBytes = 512;                 // the 128 {scale, zero} pairs of one group of a weight
+constexpr int kPairs = kSub * kPairBytes;       // up to 4 groups per slot (group 64); 2 KB keeps what follows 1024-byte aligned
 constexpr int kAColsPerBlock = kBKh / 2;        // 32 TMEM columns hold the 64 fp16 channels of a block
 // TMEM: accumulators in columns [0, 128), dequantized A stages above.  Block `it` uses A stage it % kAStages.
 constexpr int kAccColsMax = 128;
 template <int NB> struct AStages { static constexpr int value = (512 - kAccColsMax) / (NB * kAColsPerBlock); };   // 12 / 6
 constexpr int kMaxAStages = 12;
-constexpr int kMaxP = 24;
+constexpr int kMaxP = 8;
 
 struct AwqDecParams {
   DecParams d;
   int64_t k;
   int group;
   int p_stages;                  // depth of the packed / pairs / activation ring
+  int sb_total;                  // super-blocks (256 channels) along K
   const __half2* sz[2];          // {scale, zero} [k/group, n] (group-major): 512 contiguous bytes per tile and group
 };
 
 template <int BN, int NB>
 struct AwqDecSmem {
-  static constexpr int kP = NB * (kPacked + kPairs) + BN * kSwizzleBytes;   // one ring slot: nibbles | pairs | activations
+  static constexpr int kAct = BN * kSwizzleBytes;                           // one activation atom (64 channels)
+  static constexpr int kP = NB * (kPacked + kPairs) + kSub * kAct;          // one ring slot: nibbles | pairs | 4 activation atoms
   static constexpr int kCtrl = 1024;
   static size_t red_bytes(int cs) { return cs > 1 ? static_cast<size_t>(cs) * NB * (BN / 16) * ((16 + cs - 1) / cs) * kTileM * 4 : 0; }
   static size_t bytes(int p_stages, int cs) {
@@ -121,14 +127,15 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int tile = blockIdx.x / CS;
   const int crank = CS > 1 ? static_cast<int>(blockIdx.x % CS) : 0;
-  const int kb_lo = crank * p.kb_total / CS, kb_hi = (crank + 1) * p.kb_total / CS;
-  const int nkb = kb_hi - kb_lo;
+  const int sb_lo = crank * ap.sb_total / CS, sb_hi = (crank + 1) * ap.sb_total / CS;
+  const int nsb = sb_hi - sb_lo;                                   // super-blocks of this CTA
   const int a0 = tile * p.tile_rows;
+  const int ngs = max(1, kSlotK / ap.group);                       // distinct groups inside a super-block (group >= 64)
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < PD; ++s) {
       mbar_init(p_full + s, 1);
-      mbar_init(p_free + s, kGroupWarps + 1);
+      mbar_init(p_free + s, kDeqWarps + 1);
     }
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(a_ready + s, kGroupWarps);
@@ -152,37 +159,38 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       const int rows_here = static_cast<int>(min(static_cast<int64_t>(p.tile_rows), p.n - a0));
       const uint32_t pair_bytes = static_cast<uint32_t>(rows_here) * 4u;
-      const uint32_t tx = static_cast<uint32_t>(NB * p.tile_rows * (kBKh / 2)) + NB * pair_bytes + BN * kSwizzleBytes;
-      auto weights = [&](int s, int kb) {
+      const uint32_t tx = static_cast<uint32_t>(NB * p.tile_rows * (kSlotK / 2)) + NB * ngs * pair_bytes + kSub * S::kAct;
+      auto weights = [&](int s, int sb) {
         uint8_t* st = p_ring + static_cast<size_t>(s) * S::kP;
-        const int64_t g = (static_cast<int64_t>(kb) * kBKh) / ap.group;
-        tma_load_2d(st, &tm_w, p_full + s, kb * (kBKh / 2), a0, kEvictFirst);
-        bulk_load(st + NB * kPacked, ap.sz[0] + g * p.n + a0, pair_bytes, p_full + s);
-        if (NB == 2) {
-          tma_load_2d(st + kPacked, &tm_w2, p_full + s, kb * (kBKh / 2), a0, kEvictFirst);
-          bulk_load(st + NB * kPacked + kPairs, ap.sz[1] + g * p.n + a0, pair_bytes, p_full + s);
+        const int64_t g0 = (static_cast<int64_t>(sb) * kSlotK) / ap.group;
+        tma_load_2d(st, &tm_w, p_full + s, sb * (kSlotK / 2), a0, kEvictFirst);
+        if (NB == 2) tma_load_2d(st + kPacked, &tm_w2, p_full + s, sb * (kSlotK / 2), a0, kEvictFirst);
+        for (int g = 0; g < ngs; ++g) {
+          bulk_load(st + NB * kPacked + g * kPairBytes, ap.sz[0] + (g0 + g) * p.n + a0, pair_bytes, p_full + s);
+          if (NB == 2) bulk_load(st + NB * kPacked + kPairs + g * kPairBytes, ap.sz[1] + (g0 + g) * p.n + a0, pair_bytes, p_full + s);
         }
       };
-      auto acts = [&](int s, int kb) {
-        tma_load_2d(p_ring + static_cast<size_t>(s) * S::kP + NB * (kPacked + kPairs), &tm_x, p_full + s, kb * kBKh, 0,
-                    kEvictLast);
+      auto acts = [&](int s, int sb) {
+        uint8_t* at = p_ring + static_cast<size_t>(s) * S::kP + NB * (kPacked + kPairs);
+#pragma unroll
+        for (int j = 0; j < kSub; ++j) tma_load_2d(at + j * S::kAct, &tm_x, p_full + s, (sb * kSub + j) * kBKh, 0, kEvictLast);
       };
-      const int pre = min(PD, nkb);
+      const int pre = min(PD, nsb);
 #pragma unroll 1
       for (int i = 0; i < pre; ++i) {
         mbar_expect_tx(p_full + i, tx);
-        weights(i, kb_lo + i);
+        weights(i, sb_lo + i);
       }
       griddep_wait();
 #pragma unroll 1
-      for (int i = 0; i < pre; ++i) acts(i, kb_lo + i);
+      for (int i = 0; i < pre; ++i) acts(i, sb_lo + i);
 #pragma unroll 1
-      for (int it = pre; it < nkb; ++it) {
+      for (int it = pre; it < nsb; ++it) {
         const int s = it % PD;
         mbar_wait(p_free + s, ((it / PD) & 1) ^ 1);
         mbar_expect_tx(p_full + s, tx);
-        weights(s, kb_lo + it);
-        acts(s, kb_lo + it);
+        weights(s, sb_lo + it);
+        acts(s, sb_lo + it);
       }
     }
   } else if (warp == 1) {
@@ -190,19 +198,24 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       constexpr uint32_t idesc = make_idesc<1>(BN);
 #pragma unroll 1
-      for (int it = 0; it < nkb; ++it) {
-        const int sp = it % PD, sa = it % kAStages;
-        mbar_wait(p_full + sp, (it / PD) & 1);                    // activations of this block landed
-        mbar_wait(a_ready + sa, (it / kAStages) & 1);             // weights dequantized into TMEM
-        tc_fence_after();
-        const uint32_t ta = tmem_base + kAccColsMax + sa * (NB * kAColsPerBlock);
-        const uint64_t db = make_smem_desc(smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * (kPacked + kPairs)));
+      for (int sb = 0; sb < nsb; ++sb) {
+        const int sp = sb % PD;
+        mbar_wait(p_full + sp, (sb / PD) & 1);                    // activations of this super-block landed
+        const uint32_t act0 = smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * (kPacked + kPairs));
+#pragma unroll 1
+        for (int j = 0; j < kSub; ++j) {
+          const int it = sb * kSub + j, sa = it % kAStages;
+          mbar_wait(a_ready + sa, (it / kAStages) & 1);           // weights dequantized into TMEM
+          tc_fence_after();
+          const uint32_t ta = tmem_base + kAccColsMax + sa * (NB * kAColsPerBlock);
+          const uint64_t db = make_smem_desc(act0 + j * S::kAct);
 #pragma unroll
-        for (int w = 0; w < NB; ++w)
+          for (int w = 0; w < NB; ++w)
 #pragma unroll
-          for (int k = 0; k < kBKh / 16; ++k)                     // K = 16 per instruction = 8 TMEM columns of A
-            umma_ts_f16(tmem_base + w * BN, ta + w * kAColsPerBlock + k * 8, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-        umma_commit(a_free + sa);
+            for (int k = 0; k < kBKh / 16; ++k)                   // K = 16 per instruction = 8 TMEM columns of A
+              umma_ts_f16(tmem_base + w * BN, ta + w * kAColsPerBlock + k * 8, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
+          umma_commit(a_free + sa);
+        }
         umma_commit(p_free + sp);
       }
       umma_commit(acc_bar);
@@ -215,22 +228,28 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int quad = warp & 3;
     const int r = quad * 32 + lane;
     const uint32_t lane_base = static_cast<uint32_t>(quad * 32) << 16;
+    // group grp converts sub-block grp of every super-block; its 32 bytes of row r are the 16-byte chunks 2 grp, 2 grp + 1
+    // of the row's 128 bytes, stored at chunk ^ (r % 8) by the 128-byte swizzle
+    const int pair_slot = (grp * kBKh) / ap.group < ngs ? (grp * kBKh) / ap.group : ngs - 1;
+    const uint32_t ch0 = static_cast<uint32_t>((2 * grp) ^ (r & 7)) * 16u, ch1 = static_cast<uint32_t>((2 * grp + 1) ^ (r & 7)) * 16u;
 #pragma unroll 1
-    for (int it = grp; it < nkb; it += kGroups) {
-      const int sp = it % PD, sa = it % kAStages;
-      mbar_wait(p_full + sp, (it / PD) & 1);
+    for (int sb = 0; sb < nsb; ++sb) {
+      const int it = sb * kSub + grp;
+      const int sp = sb % PD, sa = it % kAStages;
+      mbar_wait(p_full + sp, (sb / PD) & 1);
       const uint8_t* pk = p_ring + static_cast<size_t>(sp) * S::kP;
       const uint32_t ta = tmem_base + lane_base + kAccColsMax + sa * (NB * kAColsPerBlock);
 #pragma unroll
       for (int w = 0; w < NB; ++w) {
         uint32_t v[32];
-        const __half2 sz = *reinterpret_cast<const __half2*>(pk + NB * kPacked + w * kPairs + r * 4);
+        const __half2 sz = *reinterpret_cast<const __half2*>(pk + NB * kPacked + w * kPairs + pair_slot * kPairBytes + r * 4);
         const __half sc = __low2half(sz), zp = __high2half(sz);
         const __half2 zb = __half2half2(__hadd(__float2half(1024.f), zp));
         const __half2 zt = __half2half2(__hneg(__hadd(__float2half(64.f), zp)));
         const __half2 s2 = __half2half2(sc);
-        const uint4 w0 = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2));
-        const uint4 w1 = *reinterpret_cast<const uint4*>(pk + w * kPacked + r * (kBKh / 2) + 16);
+        const uint8_t* row = pk + w * kPacked + r * kSwizzleBytes;
+        const uint4 w0 = *reinterpret_cast<const uint4*>(row + ch0);
+        const uint4 w1 = *reinterpret_cast<const uint4*>(row + ch1);
         const uint32_t words[8] = {w0.x, w0.y, w0.z, w0.w, w1.x, w1.y, w1.z, w1.w};
 #pragma unroll
         for (int c = 0; c < 8; ++c) {                  // word c = channels 8c .. 8c+7 = TMEM columns 4c .. 4c+3
@@ -346,14 +365,14 @@ struct AwqPlan {
 };
 
 CUtensorMap make_packed_map(const void* wp, int64_t n, int64_t k, int box_rows) {
-  // wp as bytes [n, k/2]; box = box_rows x 32 bytes, no swizzle
+  // wp as bytes [n, k/2]; box = box_rows x 128 bytes (a super-block of 256 channels), 128-byte swizzle
   CUtensorMap m;
   cuuint64_t dims[2] = {static_cast<cuuint64_t>(k / 2), static_cast<cuuint64_t>(n)};
   cuuint64_t strides[1] = {static_cast<cuuint64_t>(k / 2)};
-  cuuint32_t box[2] = {static_cast<cuuint32_t>(kBKh / 2), static_cast<cuuint32_t>(box_rows)};
+  cuuint32_t box[2] = {static_cast<cuuint32_t>(kSlotK / 2), static_cast<cuuint32_t>(box_rows)};
   cuuint32_t estr[2] = {1, 1};
   const CUresult r = get_tensor_map_encoder()(&m, CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(wp), dims, strides, box,
-                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                              estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) throw std::runtime_error("cuTensorMapEncodeTiled (awq) failed with code " + std::to_string(r));
   return m;
@@ -391,7 +410,7 @@ int clusters_for(int p_stages, int sm_count) {
 }
 
 template <int BN, int NB>
-AwqPlan plan_awq(int64_t n, int kb_total, int sm_count) {
+AwqPlan plan_awq(int64_t n, int kb_total /* super-blocks */, int sm_count) {
   static std::mutex mu;
   static std::map<std::tuple<int, int64_t, int>, AwqPlan> cache;
   int dev = 0;
@@ -425,7 +444,7 @@ AwqPlan plan_awq(int64_t n, int kb_total, int sm_count) {
       const int rows = force_rows ? force_rows : 128;
       const int tiles = static_cast<int>((n + rows - 1) / rows);
       if (tiles > maxc) continue;
-      const double cost = static_cast<double>(nkb) + (cs > 1 ? 3.0 : 0.0);
+      const double cost = static_cast<double>(nkb) + (cs > 1 ? 1.0 : 0.0);     // super-blocks per CTA + the exchange
       if (cost < best_cost) {
         best_cost = cost;
         best.cs = cs;
@@ -473,12 +492,13 @@ void launch(const CUtensorMap& tmx, const CUtensorMap& tmw, const CUtensorMap& t
 
 template <int BN, int NB>
 bool run(const void* x, const AwqNative& w, const AwqNative* w2, int64_t m, AwqDecParams p, cudaStream_t st) {
-  const int kb_total = div_up(w.k, kBKh);
-  const AwqPlan plan = plan_awq<BN, NB>(w.n, kb_total, sm_count_of_current_device());
+  const int sb_total = static_cast<int>(w.k / kSlotK);
+  const AwqPlan plan = plan_awq<BN, NB>(w.n, sb_total, sm_count_of_current_device());
   if (plan.cs == 0) return false;
   p.d.n = w.n;
   p.d.m = m;
-  p.d.kb_total = kb_total;
+  p.d.kb_total = sb_total * kSub;
+  p.sb_total = sb_total;
   p.d.tile_rows = plan.tile_rows;
   p.d.stages = plan.p_stages;
   p.k = w.k;
@@ -517,7 +537,7 @@ bool glu_enabled() { return env_int("CT2B200_AWQ_DECODE_GLU", env_int("CT2B200_A
 // false = shape not covered (more tiles than one wave holds, group not a multiple of 64): caller uses gemm_awq_tc_kernel
 bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const void* residual, int act, int64_t m, void* y,
                       cudaStream_t st) {
-  if (!enabled() || m < 1 || m > 64 || w.group % kBKh != 0 || w.k % kBKh != 0 || w.sz == nullptr || w.n % 8 != 0) return false;
+  if (!enabled() || m < 1 || m > 64 || w.group % kBKh != 0 || w.k % kSlotK != 0 || w.sz == nullptr || w.n % 8 != 0) return false;
   AwqDecParams p{};
   p.d.bias = bias;
   p.d.residual = residual;
@@ -528,7 +548,7 @@ bool dense_awq_decode(const void* x, const AwqNative& w, const void* bias, const
 }
 
 bool dense_awq_glu_decode(const void* x, const AwqNative& wg, const AwqNative& wu, int act, int64_t m, void* h, cudaStream_t st) {
-  if (!glu_enabled() || m < 1 || m > 64 || wg.group % kBKh != 0 || wg.k % kBKh != 0 || wg.group != wu.group ||
+  if (!glu_enabled() || m < 1 || m > 64 || wg.group % kBKh != 0 || wg.k % kSlotK != 0 || wg.group != wu.group ||
       wg.sz == nullptr || wu.sz == nullptr || wg.n % 8 != 0)
     return false;
   AwqDecParams p{};

@@ -58,7 +58,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
   constexpr int kElem = Elem<KIND>::bytes;
   constexpr int BK = kSwizzleBytes / kElem;
   constexpr int kAccCols = BN * NB;
-  constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : 128;
+  constexpr uint32_t kTmemCols = kAccCols <= 32 ? 32 : kAccCols <= 64 ? 64 : kAccCols <= 128 ? 128 : kAccCols <= 256 ? 256 : 512;
   // split-K ownership: inside every 16-column chunk, column j belongs to rank j % CS (slot j / CS of that chunk)
   constexpr int cp16 = (16 + CS - 1) / CS;             // owned columns per chunk
   constexpr int cpr = (BN / 16) * cp16;                // owned column slots per rank
@@ -311,6 +311,7 @@ DecPlan plan_decode(int64_t n, int kb_total, int sm_count) {
     if (cs > 1 && kb_total < 2 * cs) continue;
     const int nkb = (kb_total + cs - 1) / cs;
     const int stages = stages_for<BN, NB>(cs, nkb);
+    if (DecSmem<BN, NB>::bytes(stages, cs) > 226 * 1024) continue;      // wide activation tiles: the exchange buffer does not fit
     int maxc = 0;
     switch (cs) {
       case 1: maxc = clusters_for<T, KIND, BN, NB, 1>(stages, sm_count); break;
@@ -414,7 +415,21 @@ bool run_decode_m(const void* x, const void* w, const void* w2, int64_t m, int64
                   cudaStream_t st, const NextWeights* next = nullptr) {
   if (m <= 16) return run_decode<T, KIND, 16, NB>(x, w, w2, m, n, k, p, st, next);
   if (m <= 32) return run_decode<T, KIND, 32, NB>(x, w, w2, m, n, k, p, st, next);
-  return run_decode<T, KIND, 64, NB>(x, w, w2, m, n, k, p, st, next);
+  if (m <= 64) return run_decode<T, KIND, 64, NB>(x, w, w2, m, n, k, p, st, next);
+  if constexpr (KIND == 0 && NB == 1) {
+    if (m <= 128) return run_decode<T, KIND, 128, NB>(x, w, w2, m, n, k, p, st, next);
+    if (m <= 256) return run_decode<T, KIND, 256, NB>(x, w, w2, m, n, k, p, st, next);
+  }
+  return false;
+}
+
+// Rows this kernel takes.  Up to 64 it is the weight-streaming kernel of the decode step.  CT2B200_GEMM_DECODE_MAXM (up to 256)
+// also sends the small Dense layers of wide batches here (Transformer-base at batch x beam = 256: the whole weight matrix is a few
+// hundred KB, the launch is latency-bound, and one lean tile per CTA on 8-32 SMs beats the persistent 128 x 256-tile kernel of
+// gemm_prefill.cu on 4-16); only matrices of at most 4 M weights, so that compute-bound prompt GEMMs never come here.
+int decode_max_m(int64_t n, int64_t k) {
+  static const int max_m = std::max(64, std::min(256, env_int("CT2B200_GEMM_DECODE_MAXM", CT2B200_DEFAULT_GEMM_DECODE_MAXM)));
+  return n * k <= (4 << 20) ? max_m : 64;
 }
 
 bool decode_kernel_enabled() {
@@ -437,7 +452,7 @@ bool set_row_pre(DecParams&, const RowPre* pre, const int8_t*, const float*, int
 
 bool gemm_s8_decode(const int8_t* A, const int8_t* B, int64_t M, int64_t N, int64_t K, const DenseEpilogue& e, int dtype,
                     cudaStream_t st, const RowPre* pre, const NextWeights* next) {
-  if (!decode_kernel_enabled() || M > 64 || M < 1 || e.a_scale == nullptr || K % 16 != 0) return false;
+  if (!decode_kernel_enabled() || M > decode_max_m(N, K) || M < 1 || e.a_scale == nullptr || K % 16 != 0) return false;
   DecParams p{};
   if (!set_row_pre(p, pre, A, e.a_scale, K, dtype)) return false;
   p.a_scale = e.a_scale;

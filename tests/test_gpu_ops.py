@@ -109,7 +109,7 @@ def test_dequantize_gemm_output(dt):
 @gpu
 @pytest.mark.parametrize("impl", IMPLS)
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("mnk", [(1, 256, 512), (8, 1000, 1024), (32, 4096, 4096), (200, 512, 768)])
+@pytest.mark.parametrize("mnk", [(1, 256, 512), (8, 1000, 1024), (32, 4096, 4096), (200, 512, 768), (100, 520, 2048)])
 def test_dense_int8_fused(impl, dt, mnk):
     """Dense = Quantize -> Gemm -> Dequantize(+bias, act) -> Add(residual), one launch, vs the oracle."""
     m, n, k = mnk

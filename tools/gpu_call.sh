@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep tp2
+# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles tp2
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -43,7 +43,7 @@ stage_sweeps() {   # decode step of the INT8 8B model (64 steps after the 1024-t
 awq_run() { echo "== AWQ batch=$1 CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3" >> $OUT/sweep.log
   CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3 timeout 600 python tools/decode_once.py $1 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1; }
 stage_awq() {
-  awq_run 1 1 0; awq_run 1 1 1; awq_run 2 1 0; awq_run 2 1 1
+  awq_run 1 1 0; awq_run 1 1 1; awq_run 32 1 0; awq_run 32 0 0; awq_run 8 1 0
 }
 
 stage_refbench() { # the reference's CUDA build on the same workload (bounded: 16 / 80 generated tokens)
@@ -64,11 +64,10 @@ stage_ncu() {      # launch lists of the INT8 step (2 steps) at bsz 32 and 1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/r02_launches_awq_b1.csv env CT2B200_AWQ_DECODE=1 python tools/decode_once.py 1 2 float16 8b awq_gemm >> $OUT/ncu_list.log 2>&1
 }
-stage_ncufull() {  # full captures of the AWQ gate/up kernel and of the INT8 one
-  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 5 \
-    -o $OUT/r02_awq_decode env CT2B200_AWQ_DECODE=1 python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
-  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_decode_kernel -c 5 \
-    -o $OUT/r02_gemm_decode python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
+stage_ncufull() {  # full capture of the AWQ decode kernel (qkv / out / gate+up / down of two layers)
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 6 \
+    -o $OUT/r02_awq_decode_v2 python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
+  timeout 300 python tools/ncu_extract.py $OUT/r02_awq_decode_v2.ncu-rep > $OUT/r02_ncu_awq_v2.md 2>> $OUT/ncu_awq.log
 }
 stage_bench() {
   ( time timeout 1500 python bench.py > $OUT/bench.json 2> $OUT/bench.err ) 2> $OUT/bench.time
@@ -107,6 +106,15 @@ stage_trprofile() {   # launch list of the OPUS-MT-shaped decoding step + timing
     --log-file $OUT/r02_launches_translate.csv python tools/translate_once.py 64 4 2 >> $OUT/translate_once.log 2>&1
 }
 
+stage_widetiles() { # the decode GEMM with 128 / 256 activation rows (opt-in): parity, then the translation step with and without it
+  CT2B200_GEMM_DECODE_MAXM=256 timeout 900 python -m pytest tests/test_gpu_ops.py tests/test_gpu_translator.py -q -k "dense or translat or golden or reference" --tb=short > $OUT/pytest_widetiles.log 2>&1
+  echo "wide tiles tests exit $?" >> $OUT/pytest_widetiles.log
+  timeout 300 python tools/translate_once.py 64 4 64 > $OUT/translate_widetiles.log 2>&1
+  CT2B200_GEMM_DECODE_MAXM=256 timeout 300 python tools/translate_once.py 64 4 64 >> $OUT/translate_widetiles.log 2>&1
+  CT2B200_GEMM_DECODE_MAXM=128 timeout 300 python tools/translate_once.py 64 4 64 >> $OUT/translate_widetiles.log 2>&1
+  CT2B200_GEMM_DECODE_MAXM=256 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_translate_wide.csv python tools/translate_once.py 64 4 2 >> $OUT/translate_widetiles.log 2>&1
+}
 stage_tp2() {      # needs gpurun --gpus 2: tensor-parallel parity (tests/tp_worker.py) and the bench line with its `tp` record
   timeout 900 python -m pytest tests/test_gpu_tp.py -q --tb=short > $OUT/pytest_tp.log 2>&1
   echo "tp tests exit $?" >> $OUT/pytest_tp.log
