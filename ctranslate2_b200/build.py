@@ -36,6 +36,7 @@ FLAGS.append(NO_NC_LOADS)
 # Experimental builds beside the product library: libct2b200_<variant>.so, loaded through CT2B200_LIB.
 VARIANTS = {
     "restrict": None,      # keep __restrict__ (the pre-fix behaviour), for A/B timing
+    "awqtrace": ["-DCT2B200_AWQ_TRACE"],      # awq_decode.cu prints the pipeline stamps of CTA 0
 }
 
 
@@ -71,7 +72,7 @@ def build(force=False, verbose=True, variant=None):
         OUT = os.path.join(HERE, "libct2b200_%s.so" % variant)
         OBJ = os.path.join(HERE, "_build_" + variant)
         assert variant in VARIANTS
-        FLAGS = [f for f in FLAGS if f != NO_NC_LOADS]
+        FLAGS = [f for f in FLAGS if f != NO_NC_LOADS] if VARIANTS[variant] is None else FLAGS + VARIANTS[variant]
     os.makedirs(OBJ, exist_ok=True)
     with concurrent.futures.ThreadPoolExecutor(max_workers=min(8, len(SOURCES))) as ex:
         objs = list(ex.map(lambda s: _compile(s, force), SOURCES))

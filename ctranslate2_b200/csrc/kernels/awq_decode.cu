@@ -98,6 +98,16 @@ __device__ __forceinline__ void bulk_load(void* smem_dst, const void* gsrc, uint
                ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(bytes), "r"(smem_u32(bar)) : "memory");
 }
 
+// -DCT2B200_AWQ_TRACE (python -m ctranslate2_b200.build --variant awqtrace): CTA 0 records SM cycle stamps of the pipeline
+// events of its first 16 super-blocks and prints them when it is done.  Not compiled into the product library.
+#ifdef CT2B200_AWQ_TRACE
+#define AWQ_TRACE_DECL __shared__ long long s_trace[16][12];
+#define AWQ_TRACE(sb, slot) do { if (blockIdx.x == 0 && (sb) < 16) s_trace[sb][slot] = clock64(); } while (0)
+#else
+#define AWQ_TRACE_DECL
+#define AWQ_TRACE(sb, slot) do { } while (0)
+#endif
+
 template <int BN, int NB, int CS>
 __global__ void __launch_bounds__(kThreads, 1)
     awq_decode_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
@@ -112,6 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   static_assert(BN * NB <= kAccColsMax, "accumulators exceed their TMEM columns");
 
   extern __shared__ uint8_t smem_raw[];
+  AWQ_TRACE_DECL
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* p_ring = smem;                                         // [p_stages][nibbles NB x 4 KB | pairs NB x 512 B | x BN x 128 B]
   const int PD = ap.p_stages;
@@ -178,6 +189,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int pre = min(PD, nsb);
 #pragma unroll 1
       for (int i = 0; i < pre; ++i) {
+        AWQ_TRACE(i, 0);
         mbar_expect_tx(p_full + i, tx);
         weights(i, sb_lo + i);
       }
@@ -188,6 +200,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int it = pre; it < nsb; ++it) {
         const int s = it % PD;
         mbar_wait(p_free + s, ((it / PD) & 1) ^ 1);
+        AWQ_TRACE(it, 0);
         mbar_expect_tx(p_full + s, tx);
         weights(s, sb_lo + it);
         acts(s, sb_lo + it);
@@ -201,11 +214,14 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int sb = 0; sb < nsb; ++sb) {
         const int sp = sb % PD;
         mbar_wait(p_full + sp, (sb / PD) & 1);                    // activations of this super-block landed
+        AWQ_TRACE(sb, 1);
         const uint32_t act0 = smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * (kPacked + kPairs));
 #pragma unroll 1
         for (int j = 0; j < kSub; ++j) {
           const int it = sb * kSub + j, sa = it % kAStages;
           mbar_wait(a_ready + sa, (it / kAStages) & 1);           // weights dequantized into TMEM
+          if (j == 0) AWQ_TRACE(sb, 2);
+          if (j == kSub - 1) AWQ_TRACE(sb, 3);
           tc_fence_after();
           const uint32_t ta = tmem_base + kAccColsMax + sa * (NB * kAColsPerBlock);
           const uint64_t db = make_smem_desc(act0 + j * S::kAct);
@@ -217,6 +233,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           umma_commit(a_free + sa);
         }
         umma_commit(p_free + sp);
+        AWQ_TRACE(sb, 4);
       }
       umma_commit(acc_bar);
     }
@@ -237,6 +254,8 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int it = sb * kSub + grp;
       const int sp = sb % PD, sa = it % kAStages;
       mbar_wait(p_full + sp, (sb / PD) & 1);
+      if (threadIdx.x == 6 * 32) AWQ_TRACE(sb, 5);
+      if (threadIdx.x == 18 * 32) AWQ_TRACE(sb, 9);
       const uint8_t* pk = p_ring + static_cast<size_t>(sp) * S::kP;
       const uint32_t ta = tmem_base + lane_base + kAccColsMax + sa * (NB * kAColsPerBlock);
 #pragma unroll
@@ -260,13 +279,19 @@ __global__ void __launch_bounds__(kThreads, 1)
           v[4 * c + 3] = d.w;
         }
         // the A stage is free once the MMAs of block it - kAStages have retired (waited for AFTER the first conversion)
-        if (w == 0 && it >= kAStages) {
-          mbar_wait(a_free + sa, ((it / kAStages) & 1) ^ 1);
-          tc_fence_after();
+        if (w == 0) {
+          if (threadIdx.x == 6 * 32) AWQ_TRACE(sb, 6);
+          if (it >= kAStages) {
+            mbar_wait(a_free + sa, ((it / kAStages) & 1) ^ 1);
+            tc_fence_after();
+          }
+          if (threadIdx.x == 6 * 32) AWQ_TRACE(sb, 7);
         }
         tmem_st32(ta + w * kAColsPerBlock, v);
       }
       tmem_st_wait();
+      if (threadIdx.x == 6 * 32) AWQ_TRACE(sb, 8);
+      if (threadIdx.x == 18 * 32) AWQ_TRACE(sb, 10);
       tc_fence_before();
       __syncwarp();
       if (lane == 0) {
@@ -353,6 +378,18 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   tc_fence_before();
   __syncthreads();
+#ifdef CT2B200_AWQ_TRACE
+  if (blockIdx.x == 0 && threadIdx.x == 0) {
+    const long long t0 = s_trace[0][0];
+    printf("awq trace BN=%d NB=%d CS=%d PD=%d nsb=%d: per super-block [tma issue | mma: acts landed, a_ready(0), a_ready(3), commit | "
+           "group0: slot full, converted, a_free, st done | group3: slot full, st done] cycles since the first issue\n",
+           BN, NB, CS, PD, nsb);
+    for (int sb = 0; sb < min(nsb, 16); ++sb)
+      printf("  sb %2d: %6lld | %6lld %6lld %6lld %6lld | %6lld %6lld %6lld %6lld | %6lld %6lld\n", sb, s_trace[sb][0] - t0,
+             s_trace[sb][1] - t0, s_trace[sb][2] - t0, s_trace[sb][3] - t0, s_trace[sb][4] - t0, s_trace[sb][5] - t0,
+             s_trace[sb][6] - t0, s_trace[sb][7] - t0, s_trace[sb][8] - t0, s_trace[sb][9] - t0, s_trace[sb][10] - t0);
+  }
+#endif
   if (warp == 1) {
     tc_fence_after();
     tmem_dealloc(tmem_base, kTmemCols);
@@ -381,7 +418,11 @@ CUtensorMap make_packed_map(const void* wp, int64_t n, int64_t k, int box_rows) 
 template <int BN, int NB>
 int p_stages_for(int cs, int nkb) {
   using S = AwqDecSmem<BN, NB>;
+#ifdef CT2B200_AWQ_TRACE
+  const size_t cap = 212 * 1024;          // room for the static trace buffer
+#else
   const size_t cap = 220 * 1024;
+#endif
   const size_t fixed = S::kCtrl + S::red_bytes(cs) + 1024;
   if (fixed + 2 * S::kP > cap) return 0;
   int st = static_cast<int>((cap - fixed) / S::kP);
@@ -391,7 +432,11 @@ int p_stages_for(int cs, int nkb) {
 
 template <int BN, int NB, int CS>
 void configure_once() {
+#ifdef CT2B200_AWQ_TRACE
+  allow_dynamic_smem(awq_decode_kernel<BN, NB, CS>, 222 * 1024);
+#else
   allow_dynamic_smem(awq_decode_kernel<BN, NB, CS>, 226 * 1024);
+#endif
 }
 
 template <int BN, int NB, int CS>

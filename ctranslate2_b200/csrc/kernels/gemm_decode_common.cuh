@@ -17,7 +17,7 @@ constexpr int kMaxStages = 10;
 
 // defaults of the switchable kernels: 1 once a GPU session has validated them (profiles/README.md), 0 = opt-in until then
 #define CT2B200_DEFAULT_AWQ_DECODE 1
-#define CT2B200_DEFAULT_AWQ_GEMV 0
+#define CT2B200_DEFAULT_AWQ_GEMV 1
 #define CT2B200_DEFAULT_GEMM_DECODE_MAXM 64
 
 struct DecParams {

@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles tp2
+# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace tp2
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -43,7 +43,7 @@ stage_sweeps() {   # decode step of the INT8 8B model (64 steps after the 1024-t
 awq_run() { echo "== AWQ batch=$1 CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3" >> $OUT/sweep.log
   CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3 timeout 600 python tools/decode_once.py $1 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1; }
 stage_awq() {
-  awq_run 1 1 0; awq_run 1 1 1; awq_run 32 1 0; awq_run 32 0 0; awq_run 8 1 0
+  awq_run 1 1 1; awq_run 32 1 0
 }
 
 stage_refbench() { # the reference's CUDA build on the same workload (bounded: 16 / 80 generated tokens)
@@ -114,6 +114,9 @@ stage_widetiles() { # the decode GEMM with 128 / 256 activation rows (opt-in): p
   CT2B200_GEMM_DECODE_MAXM=128 timeout 300 python tools/translate_once.py 64 4 64 >> $OUT/translate_widetiles.log 2>&1
   CT2B200_GEMM_DECODE_MAXM=256 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/r02_launches_translate_wide.csv python tools/translate_once.py 64 4 2 >> $OUT/translate_widetiles.log 2>&1
+}
+stage_awqtrace() { # pipeline stamps of the AWQ decode kernel (trace build)
+  CT2B200_LIB=$PWD/ctranslate2_b200/libct2b200_awqtrace.so timeout 300 python tools/awq_trace.py 32 > $OUT/awq_trace.log 2>&1
 }
 stage_tp2() {      # needs gpurun --gpus 2: tensor-parallel parity (tests/tp_worker.py) and the bench line with its `tp` record
   timeout 900 python -m pytest tests/test_gpu_tp.py -q --tb=short > $OUT/pytest_tp.log 2>&1
