@@ -192,7 +192,7 @@ __global__ void __launch_bounds__(kThreads, 2)
 #pragma unroll
   for (int s = 0; s < kStages - 1; ++s) {
     if (lu < u1) {
-      if (tid == 0) load_unit(s, lc);
+      if (warp == 0 && tc::elect_one()) load_unit(s, lc);
       advance(lc);
       ++lu;
     }
@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   for (int64_t u = u0; u < u1; ++u, ++it) {
     const int stage = it % kStages;
     if (lu < u1) {                                 // refills the stage consumed in iteration it - 1 (trailing __syncthreads)
-      if (tid == 0) load_unit((it + kStages - 1) % kStages, lc);
+      if (warp == 0 && tc::elect_one()) load_unit((it + kStages - 1) % kStages, lc);
       advance(lc);
       ++lu;
     }

@@ -311,7 +311,7 @@ __global__ void __launch_bounds__(kThreads, 2)
   const bool owner = pos >= s0 && pos < s1;                     // this slice holds position `pos`
   const int kt_pos = owner ? (pos - s0) / kDecTile : -1;
   __syncthreads();                                              // mbarrier inits (thread 0) before anyone may wait on them
-  if (tid == 0) {
+  if (warp == 0 && tc::elect_one()) {                           // single-thread role: tc_common.cuh, elect_one
 #pragma unroll
     for (int st = 0; st < kDecStages - 1; ++st)
       if (st < ntiles && st != kt_pos) load_tile(st, st);
@@ -329,7 +329,7 @@ __global__ void __launch_bounds__(kThreads, 2)
     asm volatile("fence.proxy.async;" ::: "memory");            // generic-proxy stores before the TMA (async proxy) reads
   }
   __syncthreads();
-  if (tid == 0 && kt_pos >= 0 && kt_pos < kDecStages - 1) load_tile(kt_pos, kt_pos);
+  if (warp == 0 && kt_pos >= 0 && kt_pos < kDecStages - 1 && tc::elect_one()) load_tile(kt_pos, kt_pos);
 
   // Q as A fragments: rows 0..G-1 = heads, rows G..15 = 0
   uint32_t qf[D / 16][2];
@@ -346,7 +346,8 @@ __global__ void __launch_bounds__(kThreads, 2)
   for (int kt = 0; kt < ntiles; ++kt) {
     const int stage = kt % kDecStages;
     // the stage refilled here was consumed in iteration kt - 1 (trailing __syncthreads)
-    if (tid == 0 && kt + kDecStages - 1 < ntiles) load_tile((kt + kDecStages - 1) % kDecStages, kt + kDecStages - 1);
+    if (warp == 0 && kt + kDecStages - 1 < ntiles && tc::elect_one())
+      load_tile((kt + kDecStages - 1) % kDecStages, kt + kDecStages - 1);
     tc::mbar_wait(full_bar + stage, (kt / kDecStages) & 1);
     tile_step<T, D, true>(cx, sK_u32 + stage * Ctx::kTileBytes, sV_u32 + stage * Ctx::kTileBytes, warp, lane, qf, acc,
                           s1 - (s0 + kt * kDecTile));

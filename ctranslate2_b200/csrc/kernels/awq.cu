@@ -219,7 +219,7 @@ __global__ void __launch_bounds__(kAwqThreads, 1)
 
   if (warp == 0) {
     // ===== TMA producer: packed weight tile(s) + activation tile =====
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       int tile = static_cast<int>(u_begin / KB);
       int kb = static_cast<int>(u_begin - tile * KB);
@@ -257,7 +257,7 @@ __global__ void __launch_bounds__(kAwqThreads, 1)
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<1>(BN);     // kind::f16, fp16 operands, fp32 accumulate
       int it = 0, seg = 0;
       for (int64_t u = u_begin; u < u_end; ++seg) {

@@ -167,7 +167,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 0) {
     // ===== TMA producer: packed nibbles, {scale, zero} pairs (both weights are constants: issued before the grid
     // dependency resolves) and the activation block =====
-    if (lane == 0) {
+    if (elect_one()) {
       const int rows_here = static_cast<int>(min(static_cast<int64_t>(p.tile_rows), p.n - a0));
       const uint32_t pair_bytes = static_cast<uint32_t>(rows_here) * 4u;
       const uint32_t tx = static_cast<uint32_t>(NB * p.tile_rows * (kSlotK / 2)) + NB * ngs * pair_bytes + kSub * S::kAct;
@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<1>(BN);
 #pragma unroll 1
       for (int sb = 0; sb < nsb; ++sb) {

@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       const uint32_t stage_tx = static_cast<uint32_t>(NB * p.tile_rows * kSwizzleBytes + S::kB);
       auto weights = [&](int s, int kb) {
         uint8_t* sa = smem + s * S::kStage;
@@ -129,7 +129,7 @@ __global__ void __launch_bounds__(kTcThreads, 2)
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<KIND>(BN);
 #pragma unroll 1
       for (int it = 0; it < nkb; ++it) {

@@ -106,7 +106,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       griddep_wait();                              // the activations come from the previous kernel
       int it = 0;
 #pragma unroll 1
@@ -128,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<KIND>(kBN);
       int it = 0, seq = 0;
 #pragma unroll 1

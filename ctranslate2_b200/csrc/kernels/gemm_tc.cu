@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
   if (warp == 0) {
     // ===== TMA producer =====
-    if (lane == 0) {
+    if (elect_one()) {
       int it = 0;
       int tile = static_cast<int>(u_begin / KB);
       int kb = static_cast<int>(u_begin - tile * KB);
@@ -340,7 +340,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     }
   } else if (warp == 1) {
     // ===== MMA issuer =====
-    if (lane == 0) {
+    if (elect_one()) {
       constexpr uint32_t idesc = make_idesc<KIND>(BN);
       int it = 0, seg = 0;
       for (int64_t u = u_begin; u < u_end; ++seg) {

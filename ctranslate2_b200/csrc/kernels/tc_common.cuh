@@ -28,6 +28,21 @@ __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
 __device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
 }
+// One lane of a CONVERGED warp, chosen by elect.sync.  The single-thread roles (TMA producer, MMA issuer) must be entered through
+// this and not through `lane == 0`: tcgen05.mma / cp.async.bulk.tensor execute on the uniform datapath, and inside a branch the
+// compiler cannot prove single-threaded it wraps EVERY such instruction in an ELECT ... BRA.U.ANY loop over the active lanes
+// (~70 cycles per MMA measured with the stamp trace of awq_decode.cu: 32 MMAs of a 256-channel block took 3 400 cycles).
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "elect.sync _|p, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
   asm volatile(
       "{\n"
