@@ -46,9 +46,15 @@ constexpr int kPacked = kTileM * kSlotK / 2;    // 16 KB of nibbles per weight p
 constexpr int kPairBytes = 512;                 // the 128 {scale, zero} pairs of one group of a weight
 constexpr int kPairs = kSub * kPairBytes;       // up to 4 groups per slot (group 64); 2 KB keeps what follows 1024-byte aligned
 constexpr int kAColsPerBlock = kBKh / 2;        // 32 TMEM columns hold the 64 fp16 channels of a block
-// TMEM: accumulators in columns [0, 128), dequantized A stages above.  Block `it` uses A stage it % kAStages.
-constexpr int kAccColsMax = 128;
-template <int NB> struct AStages { static constexpr int value = (512 - kAccColsMax) / (NB * kAColsPerBlock); };   // 12 / 6
+// TMEM: TWO accumulator sets (one per MMA issuer: a single thread issuing the 8-32 small MMAs of a slot, with their barrier
+// waits and commits, was the pace-setter of the kernel — 1 700 of 2 400 cycles per slot in the stamp trace) in columns
+// [0, 2 * NB * BN), dequantized A stages above.  Block `it` uses A stage it % kAStages.
+constexpr int kIssuers = 2;
+template <int BN, int NB> struct AStages {
+  static constexpr int acc_cols = kIssuers * NB * BN;
+  static constexpr int raw = (512 - acc_cols) / (NB * kAColsPerBlock);
+  static constexpr int value = raw > 12 ? 12 : raw;             // 14 -> 12 | 7 / 6 / 4 (NB = 2, BN = 16 / 32 / 64)
+};
 constexpr int kMaxAStages = 12;
 constexpr int kMaxP = 8;
 
@@ -118,8 +124,9 @@ __global__ void __launch_bounds__(kThreads, 1)
   constexpr uint32_t kTmemCols = 512;
   constexpr int cp16 = (16 + CS - 1) / CS;
   constexpr int cpr = (BN / 16) * cp16;
-  constexpr int kAStages = AStages<NB>::value;
-  static_assert(BN * NB <= kAccColsMax, "accumulators exceed their TMEM columns");
+  constexpr int kAStages = AStages<BN, NB>::value;
+  constexpr int kAccCols = AStages<BN, NB>::acc_cols;      // accumulator set i at columns [i * NB * BN, +NB * BN)
+  static_assert(kAStages >= kSub, "every transform group needs an A stage");
 
   extern __shared__ uint8_t smem_raw[];
   AWQ_TRACE_DECL
@@ -146,13 +153,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (threadIdx.x == 0) {
     for (int s = 0; s < PD; ++s) {
       mbar_init(p_full + s, 1);
-      mbar_init(p_free + s, kDeqWarps + 1);
+      mbar_init(p_free + s, kDeqWarps + kIssuers);
     }
     for (int s = 0; s < kAStages; ++s) {
       mbar_init(a_ready + s, kGroupWarps);
       mbar_init(a_free + s, 1);
     }
-    mbar_init(acc_bar, 1);
+    mbar_init(acc_bar, kIssuers);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -163,6 +170,39 @@ __global__ void __launch_bounds__(kThreads, 1)
   const uint32_t tmem_base = *tmem_slot;
   griddep_launch();
   if (CS > 1) cluster_arrive();
+
+  // ===== MMA issuer `half` (warp 1: 0, warp 2: 1): sub-blocks 2 half, 2 half + 1 of every slot into accumulator set `half` =====
+  auto mma_issuer = [&](int half) {
+    constexpr uint32_t idesc = make_idesc<1>(BN);
+    const uint32_t acc = tmem_base + half * (NB * BN);
+#pragma unroll 1
+    for (int sb = 0; sb < nsb; ++sb) {
+      const int sp = sb % PD;
+      mbar_wait(p_full + sp, (sb / PD) & 1);                    // activations of this super-block landed
+      if (half == 0) AWQ_TRACE(sb, 1);
+      const uint32_t act0 = smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * (kPacked + kPairs));
+#pragma unroll 1
+      for (int jj = 0; jj < kSub / kIssuers; ++jj) {
+        const int j = half * (kSub / kIssuers) + jj;
+        const int it = sb * kSub + j, sa = it % kAStages;
+        mbar_wait(a_ready + sa, (it / kAStages) & 1);           // weights dequantized into TMEM
+        if (half == 0 && jj == 0) AWQ_TRACE(sb, 2);
+        if (half == 0 && jj == 1) AWQ_TRACE(sb, 3);
+        tc_fence_after();
+        const uint32_t ta = tmem_base + kAccCols + sa * (NB * kAColsPerBlock);
+        const uint64_t db = make_smem_desc(act0 + j * S::kAct);
+#pragma unroll
+        for (int w = 0; w < NB; ++w)
+#pragma unroll
+          for (int k = 0; k < kBKh / 16; ++k)                   // K = 16 per instruction = 8 TMEM columns of A
+            umma_ts_f16(acc + w * BN, ta + w * kAColsPerBlock + k * 8, db + 2 * k, idesc, (sb > 0 || jj > 0 || k > 0) ? 1u : 0u);
+        umma_commit(a_free + sa);
+      }
+      umma_commit(p_free + sp);
+      if (half == 0) AWQ_TRACE(sb, 4);
+    }
+    umma_commit(acc_bar);
+  };
 
   if (warp == 0) {
     // ===== TMA producer: packed nibbles, {scale, zero} pairs (both weights are constants: issued before the grid
@@ -207,36 +247,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       }
     }
   } else if (warp == 1) {
-    // ===== MMA issuer =====
-    if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc<1>(BN);
-#pragma unroll 1
-      for (int sb = 0; sb < nsb; ++sb) {
-        const int sp = sb % PD;
-        mbar_wait(p_full + sp, (sb / PD) & 1);                    // activations of this super-block landed
-        AWQ_TRACE(sb, 1);
-        const uint32_t act0 = smem_u32(p_ring + static_cast<size_t>(sp) * S::kP + NB * (kPacked + kPairs));
-#pragma unroll 1
-        for (int j = 0; j < kSub; ++j) {
-          const int it = sb * kSub + j, sa = it % kAStages;
-          mbar_wait(a_ready + sa, (it / kAStages) & 1);           // weights dequantized into TMEM
-          if (j == 0) AWQ_TRACE(sb, 2);
-          if (j == kSub - 1) AWQ_TRACE(sb, 3);
-          tc_fence_after();
-          const uint32_t ta = tmem_base + kAccColsMax + sa * (NB * kAColsPerBlock);
-          const uint64_t db = make_smem_desc(act0 + j * S::kAct);
-#pragma unroll
-          for (int w = 0; w < NB; ++w)
-#pragma unroll
-            for (int k = 0; k < kBKh / 16; ++k)                   // K = 16 per instruction = 8 TMEM columns of A
-              umma_ts_f16(tmem_base + w * BN, ta + w * kAColsPerBlock + k * 8, db + 2 * k, idesc, (it > 0 || k > 0) ? 1u : 0u);
-          umma_commit(a_free + sa);
-        }
-        umma_commit(p_free + sp);
-        AWQ_TRACE(sb, 4);
-      }
-      umma_commit(acc_bar);
-    }
+    if (elect_one()) mma_issuer(0);
   } else if (warp >= 6) {
     // ===== transform warps: nibbles -> fp16 (q - z) * s, registers -> TMEM =====
     // thread -> (transform group, tile row).  A warp may only touch TMEM lanes [32 * (warp % 4), +32): the row quadrant of a
@@ -257,7 +268,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (threadIdx.x == 6 * 32) AWQ_TRACE(sb, 5);
       if (threadIdx.x == 18 * 32) AWQ_TRACE(sb, 9);
       const uint8_t* pk = p_ring + static_cast<size_t>(sp) * S::kP;
-      const uint32_t ta = tmem_base + lane_base + kAccColsMax + sa * (NB * kAColsPerBlock);
+      const uint32_t ta = tmem_base + lane_base + kAccCols + sa * (NB * kAColsPerBlock);
 #pragma unroll
       for (int w = 0; w < NB; ++w) {
         uint32_t v[32];
@@ -306,17 +317,31 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int64_t arow = static_cast<int64_t>(a0) + rloc;
     const bool row_ok = rloc < p.tile_rows && arow < p.n;
     const uint32_t taddr = tmem_base + (static_cast<uint32_t>(q * 32) << 16);
+    if (warp == 2) {                                   // the second MMA issuer lives in an epilogue warp (idle until the end)
+      if (elect_one()) mma_issuer(1);
+      __syncwarp();
+    }
     griddep_wait();
     float bias_t = 0.f;
     if (row_ok && p.bias) bias_t = to_f32(static_cast<const T*>(p.bias)[arow]);
     mbar_wait(acc_bar, 0);
     tc_fence_after();
+    // the two accumulator sets are partial sums over alternate halves of every slot
+    auto load_acc = [&](int c0, uint32_t (&r)[NB][16]) {
+#pragma unroll
+      for (int w = 0; w < NB; ++w) {
+        uint32_t r1[16];
+        tmem_ld16x16(taddr + w * BN + c0, r[w]);
+        tmem_ld16x16(taddr + NB * BN + w * BN + c0, r1);
+#pragma unroll
+        for (int j = 0; j < 16; ++j) r[w][j] = __float_as_uint(__uint_as_float(r[w][j]) + __uint_as_float(r1[j]));
+      }
+    };
     if constexpr (CS == 1) {
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[NB][16];
-#pragma unroll
-        for (int w = 0; w < NB; ++w) tmem_ld16x16(taddr + w * BN + c0, r[w]);
+        load_acc(c0, r);
         if (row_ok && c0 < p.m) dec_finish<T, 1, NB, 16>(p, r, arow, c0, 1, 16, 1.f, 1.f, bias_t);
       }
     } else {
@@ -330,8 +355,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll 1
       for (int c0 = 0; c0 < BN; c0 += 16) {
         uint32_t r[NB][16];
-#pragma unroll
-        for (int w = 0; w < NB; ++w) tmem_ld16x16(taddr + w * BN + c0, r[w]);
+        load_acc(c0, r);
         const uint32_t chunk_off = static_cast<uint32_t>((c0 / 16) * cp16 * kTileM * 4);
 #pragma unroll
         for (int j = 0; j < 16; ++j)

@@ -48,17 +48,19 @@ struct GemvParams {
 // loads — lane g holds group g + 32 c — and handed to the lane that needs them by shuffle: trip t uses group 8 t + lane / 4.
 constexpr int kMaxQuads = 4;           // quads of 4 trips: k <= 16384
 
-template <int NB, int R>
+// KS = warps per row group: with KS = 2 the pairs of trips alternate between two adjacent warps and the partial sums meet in
+// shared memory.  Small matrices need it to have enough warps in flight: out-proj (4096 x 4096) is 1024 row groups = 7 warps
+// per SM, and a warp only keeps 4 KB of the stream in flight.
+template <int NB, int R, int KS>
 __global__ void __launch_bounds__(kWarps * 32) awq_gemv_kernel(const __half* __restrict__ x, GemvWeight w0, GemvWeight w1,
                                                                GemvParams p) {
   constexpr int NS = NB * R;           // weight rows streamed by this warp
+  __shared__ float s_part[kWarps][NS];
   griddep_launch();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t ch0 = (static_cast<int64_t>(blockIdx.x) * kWarps + warp) * R;
-  if (ch0 >= p.n) {
-    griddep_wait();
-    return;
-  }
+  const int ks = warp % KS;
+  const int64_t ch0 = ((static_cast<int64_t>(blockIdx.x) * kWarps + warp) / KS) * R;
+  const bool active = ch0 < p.n;       // warp-uniform; inactive warps still reach the barrier below
   const int64_t words = p.k / 8;
   const int ng = static_cast<int>(p.k / 128);
   const int trips = static_cast<int>((p.k + 1023) / 1024);
@@ -93,7 +95,7 @@ __global__ void __launch_bounds__(kWarps * 32) awq_gemv_kernel(const __half* __r
         q[s][u] = k0 < p.k ? __ldcs(reinterpret_cast<const uint4*>(wrow[s] + k0 / 8)) : make_uint4(0, 0, 0, 0);
     }
   };
-  load_pair(0);
+  if (active) load_pair(2 * ks);
   griddep_wait();                                  // the activations come from the previous kernel
 
 #pragma unroll
@@ -103,6 +105,7 @@ __global__ void __launch_bounds__(kWarps * 32) awq_gemv_kernel(const __half* __r
     for (int h = 0; h < 2; ++h) {
       const int t0 = c * 4 + h * 2;
       if (t0 >= trips) break;
+      if (!active || (KS > 1 && ((c * 2 + h) % KS) != ks)) continue;       // the other warp of the row group owns this pair
 #pragma unroll
       for (int u = 0; u < 2; ++u) {
         const int64_t k0 = static_cast<int64_t>(t0 + u) * 1024 + lane * 32;
@@ -136,12 +139,23 @@ __global__ void __launch_bounds__(kWarps * 32) awq_gemv_kernel(const __half* __r
           }
         }
       }
-      if (t0 + 2 < trips) load_pair(t0 + 2);
+      if (t0 + 2 * KS < trips) load_pair(t0 + 2 * KS);
     }
   }
 #pragma unroll
   for (int s = 0; s < NS; ++s) acc[s] = warp_sum(acc[s]);
-  if (lane == 0) {
+  if constexpr (KS > 1) {
+    if (lane == 0 && ks != 0)
+#pragma unroll
+      for (int s = 0; s < NS; ++s) s_part[warp][s] = acc[s];
+    __syncthreads();
+    if (ks != 0) return;
+#pragma unroll
+    for (int o = 1; o < KS; ++o)
+#pragma unroll
+      for (int s = 0; s < NS; ++s) acc[s] += s_part[warp + o][s];
+  }
+  if (lane == 0 && active) {
 #pragma unroll
     for (int r = 0; r < R; ++r) {
       const int64_t ch = ch0 + r;
@@ -163,10 +177,19 @@ void launch_gemv(const void* x, const AwqNative& a, const AwqNative* b, const Ge
   const GemvWeight w0{static_cast<const uint32_t*>(a.wp), static_cast<const __half*>(a.sc), static_cast<const __half*>(a.zr)};
   const GemvWeight w1 = b ? GemvWeight{static_cast<const uint32_t*>(b->wp), static_cast<const __half*>(b->sc),
                                        static_cast<const __half*>(b->zr)} : w0;
-  const dim3 grid(static_cast<unsigned>((a.n + kWarps * R - 1) / (kWarps * R))), block(kWarps * 32);
+  const int64_t groups = (a.n + R - 1) / R;        // row groups = warps at KS = 1
   // (a variant whose register copy of the scales is sized for k <= 4096 — 103 instead of 128 registers — measured SLOWER: 2.94 vs
   // 2.69 ms per 8B decode step; the occupancy is 2 CTAs per SM either way)
-  launch_pdl(awq_gemv_kernel<NB, R>, grid, block, 0, st, static_cast<const __half*>(x), w0, w1, p);
+  const int force_ks = dec::env_int("CT2B200_AWQ_GEMV_KS", 0);
+  const bool split = force_ks ? force_ks == 2 : (groups < 2 * 148 * kWarps && a.k >= 4096);
+  const dim3 block(kWarps * 32);
+  if (split) {
+    const dim3 grid(static_cast<unsigned>((groups * 2 + kWarps - 1) / kWarps));
+    launch_pdl(awq_gemv_kernel<NB, R, 2>, grid, block, 0, st, static_cast<const __half*>(x), w0, w1, p);
+  } else {
+    const dim3 grid(static_cast<unsigned>((groups + kWarps - 1) / kWarps));
+    launch_pdl(awq_gemv_kernel<NB, R, 1>, grid, block, 0, st, static_cast<const __half*>(x), w0, w1, p);
+  }
   check_launch();
 }
 
