@@ -507,13 +507,21 @@ AwqPlan plan_awq(int64_t n, int kb_total /* super-blocks */, int sm_count) {
       case 3: maxc = clusters_for<BN, NB, 3>(ps, sm_count); break;
       default: maxc = clusters_for<BN, NB, 4>(ps, sm_count); break;
     }
-    // the transform converts all 128 rows of a block whatever the tile height, so only full-height tiles make sense
-    // (a pinned CT2B200_GEMM_ROWS is honoured for the tests); cost = K blocks per CTA (+ the cluster exchange)
-    {
-      const int rows = force_rows ? force_rows : 128;
+    // Tile height.  The transform converts all 128 rows of a block whatever the tile height, so full-height tiles waste nothing;
+    // but since the kernel waits on the HBM stream rather than on the conversion (stamp trace, profiles/README.md), a shorter
+    // tile that puts the stream on more SMs wins when 128-row tiles leave many idle: gate/up of Llama-3-8B is 112 tiles of 128
+    // rows on 148 SMs, 138 tiles of 104.  cost = streamed rows x K blocks per CTA (+ the cluster exchange).
+    const int full = static_cast<int>((n + 127) / 128);
+    int cand[2] = {128, 128};
+    if (!force_rows && full * 10 < maxc * 9) {
+      const int r = static_cast<int>((((n + maxc - 1) / maxc) + 7) / 8 * 8);
+      if (r >= 64 && r < 128) cand[1] = r;
+    }
+    for (int ci = 0; ci < 2; ++ci) {
+      const int rows = force_rows ? force_rows : cand[ci];
       const int tiles = static_cast<int>((n + rows - 1) / rows);
       if (tiles > maxc) continue;
-      const double cost = static_cast<double>(nkb) + (cs > 1 ? 1.0 : 0.0);     // super-blocks per CTA + the exchange
+      const double cost = static_cast<double>(nkb) * (rows / 128.0) + (cs > 1 ? 1.0 : 0.0);
       if (cost < best_cost) {
         best_cost = cost;
         best.cs = cs;

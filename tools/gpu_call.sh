@@ -44,8 +44,8 @@ awq_run() { echo "== AWQ batch=$1 CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3" >> 
   CT2B200_AWQ_DECODE=$2 CT2B200_AWQ_GEMV=$3 timeout 600 python tools/decode_once.py $1 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1; }
 stage_awq() {
   awq_run 1 1 1; awq_run 32 1 0; awq_run 8 1 0
-  echo "== AWQ batch=1 GEMV K split pinned to 1" >> $OUT/sweep.log
-  CT2B200_AWQ_GEMV_KS=1 timeout 600 python tools/decode_once.py 1 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
+  echo "== AWQ batch=32, full-height tiles pinned" >> $OUT/sweep.log
+  CT2B200_GEMM_ROWS=128 timeout 600 python tools/decode_once.py 32 64 float16 8b awq_gemm >> $OUT/sweep.log 2>&1
 }
 
 stage_refbench() { # the reference's CUDA build on the same workload (bounded: 16 / 80 generated tokens)
