@@ -199,6 +199,17 @@ __global__ void __launch_bounds__(kThreads, 1)
       const T* rrow = p.residual ? static_cast<const T*>(p.residual) + row * p.ldy + n0 : nullptr;
 #pragma unroll 1
       for (int c0 = half * kColsPerWarp; c0 < (half + 1) * kColsPerWarp; c0 += 32) {
+        // The residual of the whole 32-column chunk is requested before the accumulators are read.  y may alias the residual
+        // (in-place x += Dense(...)), so loads left between the stores below stay in program order: one L2 round trip per
+        // 16-byte vector, 16 per thread and tile (the 128 x 256 tile of a 512-wide Dense took 15.7 us, most of it this chain).
+        Vec16<T> res[32 / kVec];
+        if constexpr (NB == 1) {
+          if (rrow && row_ok) {
+#pragma unroll
+            for (int v = 0; v < 32 / kVec; ++v)
+              if (n0 + c0 + v * kVec < p.n) res[v] = ld16(rrow + c0 + v * kVec);
+          }
+        }
         uint32_t r0[32];
         tmem_ld32(taddr + c0, r0);
         if constexpr (NB == 2) {
@@ -231,8 +242,6 @@ __global__ void __launch_bounds__(kThreads, 1)
 #pragma unroll
             for (int v0 = 0; v0 < 32; v0 += kVec) {
               if (n0 + c0 + v0 >= p.n) break;
-              Vec16<T> res;
-              if (rrow) res = ld16(rrow + c0 + v0);
               Vec16<T> o;
 #pragma unroll
               for (int i = 0; i < kVec; ++i) {
@@ -242,7 +251,7 @@ __global__ void __launch_bounds__(kThreads, 1)
                 else v = __uint_as_float(r0[v0 + i]);
                 v = round_to<T>(round_to<T>(v) + bs[c]);
                 if (p.act >= 0) v = round_to<T>(pre_act(v, p.act));
-                if (rrow) v = v + to_f32(res.v[i]);
+                if (rrow) v = v + to_f32(res[v0 / kVec].v[i]);
                 o.v[i] = from_f32<T>(v);
               }
               st16(yrow + c0 + v0, o);

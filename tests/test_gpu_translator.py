@@ -168,15 +168,17 @@ def test_cuda_graph_and_eager_steps_agree(fixture):
 
 
 @gpu
-def test_beam_matches_oracle_on_long_batches():
-    """Larger batch / longer decode than the fixture: 16 sources, beam 4, 40 steps, vs the oracle live (float32)."""
+@pytest.mark.parametrize("beam,nh", [(4, 3), (7, 2), (10, 2)])
+def test_beam_matches_oracle_on_long_batches(beam, nh):
+    """Larger batch / longer decode than the fixture: 16 sources, 40 steps, vs the oracle live (float32).  Beam 4 and 7 take the
+    one-pass scoring kernel with 8- and 16-entry per-thread lists, beam 10 the LogSoftMax + ops::TopK path."""
     t = Translator(MODELS["postnorm"], compute_type="float32")
     oracle = O.Seq2SeqOracle.from_dir(MODELS["postnorm"], compute_type="float32")
     rng = np.random.default_rng(5)
     srcs = [[int(x) for x in rng.integers(3, 120, size=int(rng.integers(3, 30)))] for _ in range(16)]
-    c = dict(sources=srcs, beam_size=4, num_hypotheses=3, max_length=40, min_length=5, length_penalty=1.0)
+    c = dict(sources=srcs, beam_size=beam, num_hypotheses=nh, max_length=40, min_length=5, length_penalty=1.0)
     hyps, scores = _run(t, c)
-    want = oracle.translate(srcs, beam_size=4, num_hypotheses=3, max_length=40, min_length=5, eos=END, bos=START)
+    want = oracle.translate(srcs, beam_size=beam, num_hypotheses=nh, max_length=40, min_length=5, eos=END, bos=START)
     assert hyps == [[h[0] for h in w] for w in want]
     for s, w in zip(scores, want):
         np.testing.assert_allclose(s, [h[1] for h in w], atol=3e-4)

@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace tp2
+# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace probe tp2
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -119,6 +119,10 @@ stage_widetiles() { # the decode GEMM with 128 / 256 activation rows (opt-in): p
 }
 stage_awqtrace() { # pipeline stamps of the AWQ decode kernel (trace build)
   CT2B200_LIB=$PWD/ctranslate2_b200/libct2b200_awqtrace.so timeout 300 python tools/awq_trace.py 32 > $OUT/awq_trace.log 2>&1
+}
+stage_probe() {    # ingest rate of one CTA per SM as a function of the TMA request shape (tools/probes/tma_probe.cu)
+  [ -x tools/probes/tma_probe ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probes/tma_probe tools/probes/tma_probe.cu -lcuda
+  timeout 120 tools/probes/tma_probe > $OUT/tma_probe.log 2>&1
 }
 stage_tp2() {      # needs gpurun --gpus 2: tensor-parallel parity (tests/tp_worker.py) and the bench line with its `tp` record
   timeout 900 python -m pytest tests/test_gpu_tp.py -q --tb=short > $OUT/pytest_tp.log 2>&1
