@@ -60,15 +60,18 @@ __device__ __noinline__ float pre_act(float x, int act) {
 
 __device__ __forceinline__ void epi_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-// T = output dtype (2 or 4 bytes), KIND = 0 s8 / 1 f16 / 2 bf16, NB = 2: gate/up fusion
-template <typename T, int KIND, int NB>
+// T = output dtype (2 or 4 bytes), KIND = 0 s8 / 1 f16 / 2 bf16, NB = 2: gate/up fusion, BN = accumulator columns per tile:
+// 256, or 64 for Dense layers whose 128 x 256 tiles would occupy a handful of SMs (Transformer-base at 256 rows: 4 tiles; the
+// shared-memory stage layout stays that of the wide tile, a narrow tile simply uses the first 64 rows of the B slot)
+template <typename T, int KIND, int NB, int BN = kBN>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_prefill_kernel(const __grid_constant__ CUtensorMap tm_x, const __grid_constant__ CUtensorMap tm_w,
                         const __grid_constant__ CUtensorMap tm_w2, const PreParams p) {
   constexpr int kElem = Elem<KIND>::bytes;
   constexpr int BK = kSwizzleBytes / kElem;
-  constexpr int kWRows = NB == 2 ? kBN / 2 : kBN;      // weight rows per TMA box
-  constexpr int kOutCols = NB == 2 ? kBN / 2 : kBN;    // output columns per tile
+  static_assert(NB == 1 || BN == kBN, "narrow tiles are for the plain Dense");
+  constexpr int kWRows = NB == 2 ? BN / 2 : BN;        // weight rows per TMA box
+  constexpr int kOutCols = NB == 2 ? BN / 2 : BN;      // output columns per tile
 
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -119,7 +122,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (it >= kStages) mbar_wait(empty_bar + s, ((it / kStages) & 1) ^ 1);
           uint8_t* sa = smem + s * kStage;
           uint8_t* sb = sa + kStageA;
-          mbar_expect_tx(full_bar + s, kStage);
+          mbar_expect_tx(full_bar + s, kStageA + BN * kSwizzleBytes);
           tma_load_2d(sa, &tm_x, full_bar + s, kb * BK, m0, kEvictLast);
           tma_load_2d(sb, &tm_w, full_bar + s, kb * BK, n0, kEvictFirst);
           if (NB == 2) tma_load_2d(sb + kWRows * kSwizzleBytes, &tm_w2, full_bar + s, kb * BK, n0, kEvictFirst);
@@ -129,14 +132,14 @@ __global__ void __launch_bounds__(kThreads, 1)
   } else if (warp == 1) {
     // ===== MMA issuer =====
     if (elect_one()) {
-      constexpr uint32_t idesc = make_idesc<KIND>(kBN);
+      constexpr uint32_t idesc = make_idesc<KIND>(BN);
       int it = 0, seq = 0;
 #pragma unroll 1
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++seq) {
         const int buf = seq & 1;
         if (seq >= 2) mbar_wait(acc_empty + buf, ((seq >> 1) & 1) ^ 1);   // the epilogue drained this buffer
         tc_fence_after();
-        const uint32_t acc = tmem_base + buf * kBN;
+        const uint32_t acc = tmem_base + buf * BN;
 #pragma unroll 1
         for (int kb = 0; kb < KB; ++kb, ++it) {
           const int s = it % kStages;
@@ -183,8 +186,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           if constexpr (KIND == 0) sv = col < p.n ? __ldg((et < kOutCols ? p.w_scale0 : p.w_scale1) + col) : 1.f;
         } else {
           const int64_t col = static_cast<int64_t>(n0) + et;
-          if constexpr (KIND == 0) sv = col < p.n ? __ldg(p.w_scale0 + col) : 1.f;
-          if (bias) bv = col < p.n ? to_f32(bias[col]) : 0.f;
+          const bool mine = et < kOutCols && col < p.n;
+          if constexpr (KIND == 0) sv = mine ? __ldg(p.w_scale0 + col) : 1.f;
+          if (bias) bv = mine ? to_f32(bias[col]) : 0.f;
         }
         ws[et] = sv;
         bs[et] = bv;
@@ -194,7 +198,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       epi_sync();                                  // column constants of this tile are in place
       mbar_wait(acc_full + buf, (seq >> 1) & 1);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + buf * kBN + (static_cast<uint32_t>(q * 32) << 16);
+      const uint32_t taddr = tmem_base + buf * BN + (static_cast<uint32_t>(q * 32) << 16);
       T* yrow = static_cast<T*>(p.y) + row * p.ldy + n0;
       const T* rrow = p.residual ? static_cast<const T*>(p.residual) + row * p.ldy + n0 : nullptr;
 #pragma unroll 1
@@ -274,13 +278,13 @@ __global__ void __launch_bounds__(kThreads, 1)
   }
 }
 
-template <typename T, int KIND, int NB>
-void launch_prefill(const void* x, const void* w, const void* w2, int64_t m, int64_t n, int64_t k, PreParams p,
-                    cudaStream_t st) {
+template <typename T, int KIND, int NB, int BN>
+void launch_prefill_bn(const void* x, const void* w, const void* w2, int64_t m, int64_t n, int64_t k, PreParams p, int sms,
+                       cudaStream_t st) {
   constexpr int elem = Elem<KIND>::bytes;
-  auto kernel = gemm_prefill_kernel<T, KIND, NB>;
+  auto kernel = gemm_prefill_kernel<T, KIND, NB, BN>;
   allow_dynamic_smem(kernel, kSmemBytes);
-  constexpr int out_cols = NB == 2 ? kBN / 2 : kBN;
+  constexpr int out_cols = NB == 2 ? BN / 2 : BN;
   p.m = m;
   p.n = n;
   p.kb_total = div_up(k, kSwizzleBytes / elem);
@@ -289,18 +293,33 @@ void launch_prefill(const void* x, const void* w, const void* w2, int64_t m, int
   const CUtensorMap tmx = make_operand_map(x, m, k, elem, KIND, kTileM);
   const CUtensorMap tmw = make_operand_map(w, n, k, elem, KIND, out_cols);
   const CUtensorMap tmw2 = make_operand_map(w2 ? w2 : w, n, k, elem, KIND, out_cols);
-  int dev = 0, sms = 148;
+  const int64_t tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
+  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(sms, tiles));
+  launch_pdl(kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, tmx, tmw, tmw2, p);
+  check_launch();
+}
+
+template <typename T, int KIND, int NB>
+void launch_prefill(const void* x, const void* w, const void* w2, int64_t m, int64_t n, int64_t k, const PreParams& p,
+                    cudaStream_t st) {
+  int dev = 0;
   cudaGetDevice(&dev);
   static int cached_dev = -1, cached_sms = 148;
   if (cached_dev != dev) {
     cudaDeviceGetAttribute(&cached_sms, cudaDevAttrMultiProcessorCount, dev);
     cached_dev = dev;
   }
-  sms = cached_sms;
-  const int64_t tiles = static_cast<int64_t>(p.tiles_m) * p.tiles_n;
-  const unsigned grid = static_cast<unsigned>(std::min<int64_t>(sms, tiles));
-  launch_pdl(kernel, dim3(grid), dim3(kThreads), kSmemBytes, st, tmx, tmw, tmw2, p);
-  check_launch();
+  const int sms = cached_sms;
+  if constexpr (NB == 1) {
+    // latency-bound regime: the wide tiles would run on fewer than a quarter of the SMs -> 64-column tiles (CT2B200_GEMM_PREFILL_BN pins)
+    static const int force_bn = [] { const char* e = std::getenv("CT2B200_GEMM_PREFILL_BN"); return e ? std::atoi(e) : 0; }();
+    const int64_t wide_tiles = static_cast<int64_t>(div_up(m, kTileM)) * div_up(n, kBN);
+    if (force_bn == 64 || (force_bn == 0 && wide_tiles * 4 <= sms)) {
+      launch_prefill_bn<T, KIND, NB, 64>(x, w, w2, m, n, k, p, sms, st);
+      return;
+    }
+  }
+  launch_prefill_bn<T, KIND, NB, kBN>(x, w, w2, m, n, k, p, sms, st);
 }
 
 bool prefill_kernel_enabled() {

@@ -52,6 +52,65 @@ __global__ void embed_pos_kernel(const void* __restrict__ w, const float* __rest
 // y = T((x - mean) * rsqrt(var + eps) * gamma + beta); optionally followed by ops::Quantize of T(y) (quantize_gpu.cu:57-105;
 // `round` = false reproduces models of binary version < 5, model.h:87-89).  y and (q, scale) may both be requested.
 // ---------------------------------------------------------------------------------------------
+// Rows of at most 8 * 256 elements: every thread keeps its (up to NV) elements and their normalised values in registers — one
+// read of x, gamma and beta instead of four, same arithmetic and rounding points as the general kernel below.
+template <typename T, int NV>
+__global__ void __launch_bounds__(256) layer_norm_small_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
+                                                               const T* __restrict__ beta, int64_t cols, float eps,
+                                                               T* __restrict__ y, int8_t* __restrict__ q, float* __restrict__ scale,
+                                                               bool round) {
+  __shared__ float red[32];
+  griddep_launch();
+  griddep_wait();
+  const int64_t row = blockIdx.x;
+  const T* xr = x + row * cols;
+  float v[NV];
+  float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int64_t j = threadIdx.x + static_cast<int64_t>(i) * 256;
+    v[i] = j < cols ? to_f32(xr[j]) : 0.f;
+    s1 += v[i];
+    s2 += v[i] * v[i];
+  }
+  s1 = block_reduce<false>(s1, red);
+  s2 = block_reduce<false>(s2, red);
+  const float inv_n = 1.f / static_cast<float>(cols);
+  const float mean = s1 * inv_n;
+  const float rstd = rsqrtf(fmaxf(s2 * inv_n - mean * mean, 0.f) + eps);
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const int64_t j = threadIdx.x + static_cast<int64_t>(i) * 256;
+    if (j < cols) {
+      const float g = gamma ? to_f32(gamma[j]) : 1.f, b = beta ? to_f32(beta[j]) : 0.f;
+      v[i] = round_to<T>((v[i] - mean) * rstd * g + b);
+      amax = fmaxf(amax, fabsf(v[i]));
+    }
+  }
+  if (q) {
+    amax = block_reduce<true>(amax, red);
+    const float s = amax != 0.f ? 127.f / amax : 1.f;
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int64_t j = threadIdx.x + static_cast<int64_t>(i) * 256;
+      if (j < cols) {
+        const float w = v[i] * s;
+        q[row * cols + j] = static_cast<int8_t>(round ? nearbyintf(w) : w);
+      }
+    }
+    if (threadIdx.x == 0) scale[row] = s;
+  }
+  if (y) {
+    T* yr = y + row * cols;   // y may alias x: every thread rewrites only the elements it read
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+      const int64_t j = threadIdx.x + static_cast<int64_t>(i) * 256;
+      if (j < cols) yr[j] = from_f32<T>(v[i]);
+    }
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) layer_norm_kernel(const T* __restrict__ x, const T* __restrict__ gamma,
                                                          const T* __restrict__ beta, int64_t cols, float eps,
@@ -229,7 +288,8 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
     // context: two adjacent output dimensions per lane, one 4-byte load per key (a warp reads 128 contiguous bytes)
     for (int i = 2 * lane; i < D; i += 64) {
       float a0 = 0.f, a1 = 0.f;
-      for (int j = 0; j < nkeys; ++j) {
+#pragma unroll 8
+      for (int j = 0; j < nkeys; ++j) {              // unrolled: eight value rows in flight, sums in key order
         const T* vr = value_row(j);
         const uint32_t w = *reinterpret_cast<const uint32_t*>(vr + i);
         T e[2];
@@ -246,6 +306,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
   // context: one output dimension per lane
   for (int i = lane; i < D; i += 32) {
     float acc = 0.f;
+#pragma unroll 4
     for (int j = 0; j < nkeys; ++j) {
       const T* vr;
       if constexpr (MODE == 1) {
@@ -405,7 +466,12 @@ __global__ void __launch_bounds__(kRowsThreads) beam_rows_kernel(T* __restrict__
   for_row_elements(xr, vocab, vec_ok, [&](float v, int32_t) { m = fmaxf(m, v); });
   m = block_reduce<true>(m, red);
   float s = 0.f;
-  for_row_elements(xr, vocab, vec_ok, [&](float v, int32_t) { s += expf(v - m); });
+  // 2-byte logits: exp through ex2.approx (2 ulp of a sum that is rounded to 11 / 8 mantissa bits afterwards); float logits keep expf
+  if constexpr (sizeof(T) == 2) {
+    for_row_elements(xr, vocab, vec_ok, [&](float v, int32_t) { s += exp2f((v - m) * 1.4426950408889634f); });
+  } else {
+    for_row_elements(xr, vocab, vec_ok, [&](float v, int32_t) { s += expf(v - m); });
+  }
   s = block_reduce<false>(s, red);
   const float logs = logf(s);
   const float c = to_f32(cum[row]);
@@ -722,9 +788,19 @@ void launch_embed_pos(const void* w, const float* w_scale, const int32_t* ids, i
 void launch_layer_norm(const void* x, const void* gamma, const void* beta, int64_t rows, int64_t cols, float eps, void* y,
                        int8_t* q, float* scale, bool round, int dtype, cudaStream_t st) {
   if (rows == 0) return;
-  CT2_DISPATCH_DTYPE(dtype, (launch_pdl(layer_norm_kernel<T>, dim3(rows), dim3(256), 0, st, static_cast<const T*>(x),
-                                        static_cast<const T*>(gamma), static_cast<const T*>(beta), cols, eps,
-                                        static_cast<T*>(y), q, scale, round)));
+  if (cols <= 512) {
+    CT2_DISPATCH_DTYPE(dtype, (launch_pdl(layer_norm_small_kernel<T, 2>, dim3(rows), dim3(256), 0, st, static_cast<const T*>(x),
+                                          static_cast<const T*>(gamma), static_cast<const T*>(beta), cols, eps,
+                                          static_cast<T*>(y), q, scale, round)));
+  } else if (cols <= 2048) {
+    CT2_DISPATCH_DTYPE(dtype, (launch_pdl(layer_norm_small_kernel<T, 8>, dim3(rows), dim3(256), 0, st, static_cast<const T*>(x),
+                                          static_cast<const T*>(gamma), static_cast<const T*>(beta), cols, eps,
+                                          static_cast<T*>(y), q, scale, round)));
+  } else {
+    CT2_DISPATCH_DTYPE(dtype, (launch_pdl(layer_norm_kernel<T>, dim3(rows), dim3(256), 0, st, static_cast<const T*>(x),
+                                          static_cast<const T*>(gamma), static_cast<const T*>(beta), cols, eps,
+                                          static_cast<T*>(y), q, scale, round)));
+  }
   check_launch();
 }
 
