@@ -190,7 +190,10 @@ struct AttnGeneric {
 
 constexpr int kAttnWarps = 4;
 
-template <typename T, int MODE>
+// DT = head_dim known at compile time (64, 128: the loops over a key / value row unroll, so the 16-byte loads of a row are all
+// in flight at once — with a run-time bound they were issued one L2 round trip at a time: 82 % long_scoreboard at 21 % occupancy,
+// profiles/r02_ncu_translate.md), 0 = any head_dim
+template <typename T, int MODE, int DT>
 __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(AttnGeneric a) {
   extern __shared__ float smem_f[];
   griddep_launch();
@@ -200,7 +203,7 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
   if (unit >= a.rows * a.H) return;
   const int64_t n = unit / a.H;
   const int h = static_cast<int>(unit % a.H);
-  const int D = a.D, d_model = a.H * a.D;
+  const int D = DT > 0 ? DT : a.D, d_model = a.H * D;
   float* qs = smem_f + static_cast<size_t>(warp) * (a.max_keys + D);
   float* sc = qs + D;
   const T* qrow = static_cast<const T*>(a.q) + n * a.q_stride + h * D;
@@ -248,10 +251,20 @@ __global__ void __launch_bounds__(kAttnWarps * 32) attention_generic_kernel(Attn
   auto dot_row = [&](const T* kr) {
     float dot = 0.f;
     if (vec) {
-      for (int c = 0; c < D; c += NV) {
-        const Vec16<T> kk = ld16(kr + c);
+      if constexpr (DT > 0) {
+        Vec16<T> kk[DT / NV];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) dot += qs[c + i] * to_f32(kk.v[i]);
+        for (int c = 0; c < DT / NV; ++c) kk[c] = ld16(kr + c * NV);
+#pragma unroll
+        for (int c = 0; c < DT / NV; ++c)
+#pragma unroll
+          for (int i = 0; i < NV; ++i) dot += qs[c * NV + i] * to_f32(kk[c].v[i]);
+      } else {
+        for (int c = 0; c < D; c += NV) {
+          const Vec16<T> kk = ld16(kr + c);
+#pragma unroll
+          for (int i = 0; i < NV; ++i) dot += qs[c + i] * to_f32(kk.v[i]);
+        }
       }
     } else {
       for (int i = 0; i < D; ++i) dot += qs[i] * to_f32(kr[i]);
@@ -816,7 +829,8 @@ void launch_attn_mode(const AttnGeneric& a_in, cudaStream_t st) {
   }
   const size_t smem = static_cast<size_t>(kAttnWarps) * (a.max_keys + a.D) * sizeof(float);
   CT2_REQUIRE(smem <= 200 * 1024, "attention: too many keys for the generic kernel");
-  auto kernel = attention_generic_kernel<T, MODE>;
+  auto kernel = a.D == 64 ? attention_generic_kernel<T, MODE, 64>
+                : a.D == 128 ? attention_generic_kernel<T, MODE, 128> : attention_generic_kernel<T, MODE, 0>;
   if (smem > 48 * 1024) {
     // the attribute is per device: set it whenever the request grows (cheap, idempotent)
     CT2_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));

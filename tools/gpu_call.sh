@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace probe tp2
+# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace probe ncutr tp2
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -119,6 +119,11 @@ stage_widetiles() { # the decode GEMM with 128 / 256 activation rows (opt-in): p
 }
 stage_awqtrace() { # pipeline stamps of the AWQ decode kernel (trace build)
   CT2B200_LIB=$PWD/ctranslate2_b200/libct2b200_awqtrace.so timeout 300 python tools/awq_trace.py 32 > $OUT/awq_trace.log 2>&1
+}
+stage_ncutr() {     # full capture of the two slowest kernels of the translation step
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:"beam_rows" -c 2 \
+    -o $OUT/r02_translate_kernels python tools/translate_once.py 64 4 2 > $OUT/ncu_tr.log 2>&1
+  timeout 300 python tools/ncu_extract.py $OUT/r02_translate_kernels.ncu-rep > $OUT/r02_ncu_translate.md 2>> $OUT/ncu_tr.log
 }
 stage_probe() {    # ingest rate of one CTA per SM as a function of the TMA request shape (tools/probes/tma_probe.cu)
   [ -x tools/probes/tma_probe ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probes/tma_probe tools/probes/tma_probe.cu -lcuda
