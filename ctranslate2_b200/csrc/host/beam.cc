@@ -11,6 +11,7 @@ BeamSearchArena::BeamSearchArena() {
   end_ids.alloc(64 * sizeof(int32_t));
   counters.alloc(64);
   CT2_CUDA_CHECK(cudaMemset(counters.ptr, 0, 64));
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());   // legacy-stream memset vs the engine's non-blocking stream
 }
 
 BeamSearchArena::~BeamSearchArena() {
@@ -34,6 +35,7 @@ bool BeamSearchArena::ensure(int64_t batch, int beam, int64_t steps, size_t es) 
   alive.alloc(2 * N * L * 4);
   anc.alloc(2 * N * L * 4);
   CT2_CUDA_CHECK(cudaMemset(anc.ptr, 0, anc.bytes));
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());   // legacy-stream memset vs the engine's non-blocking stream
   hyp_tokens.alloc(B * maxh * L * 4);
   hyp_len.alloc(B * maxh * 4);
   hyp_score.alloc(B * maxh * 4);

@@ -216,9 +216,16 @@ std::vector<uint8_t> convert_to_dtype(const HostVariable& v, int dtype) {
   return out;
 }
 
+// Host (pageable: the model file) -> device.  cudaMemcpy may return once the data sits in the driver's staging buffer, BEFORE the
+// DMA into `dst` has finished; the kernels and device-to-device copies that follow run on the engine's own non-blocking stream,
+// which does not wait for the legacy stream.  Without the synchronisation the tensor-parallel shard cut right after the upload
+// read a partly written matrix now and then (float16 weights, 2 x B200: logits off by 6-7 % in 5 of 6 runs, tests/tp_worker.py).
 void upload(DeviceBuffer& dst, const void* src, size_t n) {
   dst.alloc(n);
-  if (n) CT2_CUDA_CHECK(cudaMemcpy(dst.ptr, src, n, cudaMemcpyHostToDevice));
+  if (n) {
+    CT2_CUDA_CHECK(cudaMemcpy(dst.ptr, src, n, cudaMemcpyHostToDevice));
+    CT2_CUDA_CHECK(cudaDeviceSynchronize());
+  }
 }
 
 namespace {
@@ -710,6 +717,7 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
   attn_splits_ = attention_decode_splits(max_batch_, heads_kv_, max_len_, sm_count_);
   attn_ws_.alloc(attention_decode_workspace_bytes(max_batch_, heads_, mc_.head_dim, std::max(attn_splits_, 80)));
   CT2_CUDA_CHECK(cudaMemset(attn_ws_.ptr, 0, attn_ws_.bytes));
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());   // legacy-stream memset vs the engine's non-blocking stream
   if (tp_.world > 1) {
     // exchange buffer of this rank: [flags 2x8 u32 | pad to 256] [amax words 2 x 8 x R] [partials 2 x R x d_model]
     tp_.flags_off = 0;
@@ -720,8 +728,10 @@ LlamaDecoder::LlamaDecoder(const ModelFile& f, const ct2b200_generator_config& c
     tp_.part_off[1] = tp_.part_off[0] + part_bytes;
     tp_.exchange.alloc(tp_.part_off[1] + part_bytes);
     CT2_CUDA_CHECK(cudaMemset(tp_.exchange.ptr, 0, tp_.exchange.bytes));
+    CT2_CUDA_CHECK(cudaDeviceSynchronize());   // legacy-stream memset vs the engine's non-blocking stream
     tp_.tick.alloc(256);
     CT2_CUDA_CHECK(cudaMemset(tp_.tick.ptr, 0, 256));
+    CT2_CUDA_CHECK(cudaDeviceSynchronize());   // legacy-stream memset vs the engine's non-blocking stream
   }
   SplitKWorkspace::get(stream_);   // create the split-K scratch outside any graph capture
   CT2_CUDA_CHECK(cudaDeviceSynchronize());
@@ -1039,6 +1049,7 @@ Generator::Generator(const std::string& model_dir, const ct2b200_generator_confi
   row_start_d_.alloc(B * sizeof(int32_t));            // first loop step whose sample is a generated token, per row
   CT2_CUDA_CHECK(cudaMemset(row_start_d_.ptr, 0, row_start_d_.bytes));
   CT2_CUDA_CHECK(cudaMemset(sample_ws_.ptr, 0, sample_ws_.bytes));
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());   // legacy-stream memset vs the engine's non-blocking stream
   prompt_d_.alloc(B * L * sizeof(int32_t));
   host_pinned_elems_ = static_cast<size_t>(B) * (L + 2) + 256;   // prompt block | forced inputs | gen[4] | end ids[64] | row starts[B]
   CT2_CUDA_CHECK(cudaMallocHost(&host_pinned_, host_pinned_elems_ * sizeof(int32_t)));
@@ -1345,6 +1356,7 @@ void Generator::bench_decode(int64_t batch, int64_t prompt_len, int64_t steps, i
   CT2_CUDA_CHECK(cudaMemcpy(prompt_d_.ptr, ids.data(), ids.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
   int32_t gen[8] = {static_cast<int32_t>(prompt_len - 1), 0, 0, 0, INT32_MAX, 0, 0, 0};
   CT2_CUDA_CHECK(cudaMemcpy(step_d_.ptr, gen, sizeof(gen), cudaMemcpyHostToDevice));
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());      // pageable H2D: the DMA may still be running when cudaMemcpy returns (see upload())
   cudaEvent_t e0, e1, e2, e3;
   cudaEventCreate(&e0);
   cudaEventCreate(&e1);

@@ -591,6 +591,7 @@ void Translator::bench(int64_t batch, int64_t source_len, int beam, int64_t step
   for (size_t i = 0; i < ids.size(); ++i) ids[i] = static_cast<int32_t>((7919ull * i + 3) % mc_.src_vocab);
   CT2_CUDA_CHECK(cudaMemcpy(src_ids_.ptr, ids.data(), ids.size() * 4, cudaMemcpyHostToDevice));
   CT2_CUDA_CHECK(cudaMemcpy(src_lens_.ptr, lens.data(), lens.size() * 4, cudaMemcpyHostToDevice));
+  CT2_CUDA_CHECK(cudaDeviceSynchronize());      // pageable H2D: the DMA may still be running when cudaMemcpy returns (see upload())
   BeamState bs = beam_.state(batch, beam, mc_.tgt_vocab, L, 0, 1.f, 1.f, 1, 0);   // no end token: nothing finishes early
   set_logits_ld(bs);
   std::vector<int64_t> key = {-1, batch, beam, source_len, bs.stride, L};

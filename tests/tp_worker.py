@@ -54,9 +54,13 @@ def main():
         first_tok_match = sum(int(a[0] == b[0]) for a, b in zip(tokens, ref_tokens))
         out[quant] = dict(rel_rms=err, tol=tol, same_across_ranks=same_across_ranks, repeat_identical=tokens == tokens2,
                           first_tokens_equal=first_tok_match, tokens_equal=int(tokens == ref_tokens))
-        assert same_across_ranks, "ranks disagree"
-        assert tokens == tokens2, "second call differs"
-        assert err <= tol, (quant, err)
+        if os.environ.get("TP_WORKER_REPORT_ONLY"):      # debugging aid: print every case instead of stopping at the first
+            if rank == 0:
+                print("TP_CASE " + json.dumps({quant: out[quant]}), flush=True)
+        else:
+            assert same_across_ranks, "ranks disagree"
+            assert tokens == tokens2, "second call differs"
+            assert err <= tol, (quant, err)
         g.close()
         dist.barrier()
     if rank == 0:

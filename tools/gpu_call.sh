@@ -66,10 +66,13 @@ stage_ncu() {      # launch lists of the INT8 step (2 steps) at bsz 32 and 1
   timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
     --log-file $OUT/r02_launches_awq_b1.csv env CT2B200_AWQ_DECODE=1 python tools/decode_once.py 1 2 float16 8b awq_gemm >> $OUT/ncu_list.log 2>&1
 }
-stage_ncufull() {  # full capture of the AWQ decode kernel (qkv / out / gate+up / down of two layers)
+stage_ncufull() {  # full captures of the AWQ decode kernel and of the INT8 decode GEMM (qkv / out / gate+up / down of two layers)
   timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:awq_decode_kernel -c 6 \
-    -o $OUT/r02_awq_decode_v2 python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
-  timeout 300 python tools/ncu_extract.py $OUT/r02_awq_decode_v2.ncu-rep > $OUT/r02_ncu_awq_v2.md 2>> $OUT/ncu_awq.log
+    -o $OUT/r02_awq_decode_v3 python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
+  timeout 300 python tools/ncu_extract.py $OUT/r02_awq_decode_v3.ncu-rep > $OUT/r02_ncu_awq_v3.md 2>> $OUT/ncu_awq.log
+  timeout 900 ncu --set full --clock-control none --import-source on --profile-from-start off -k regex:gemm_decode_kernel -c 6 \
+    -o $OUT/r02_gemm_decode_v3 python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
+  timeout 300 python tools/ncu_extract.py $OUT/r02_gemm_decode_v3.ncu-rep > $OUT/r02_ncu_gemm_v3.md 2>> $OUT/ncu_gemm.log
 }
 stage_bench() {
   ( time timeout 1500 python bench.py > $OUT/bench.json 2> $OUT/bench.err ) 2> $OUT/bench.time
@@ -128,6 +131,22 @@ stage_ncutr() {     # full capture of the two slowest kernels of the translation
 stage_probe() {    # ingest rate of one CTA per SM as a function of the TMA request shape (tools/probes/tma_probe.cu)
   [ -x tools/probes/tma_probe ] || nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/probes/tma_probe tools/probes/tma_probe.cu -lcuda
   timeout 120 tools/probes/tma_probe > $OUT/tma_probe.log 2>&1
+}
+stage_tpcheck() {   # needs gpurun --gpus 2: the parity test, then the worker three more times (the upload race was intermittent)
+  timeout 600 python -m pytest tests/test_gpu_tp.py -q --tb=short > $OUT/pytest_tp.log 2>&1
+  echo "tp tests exit $?" >> $OUT/pytest_tp.log
+  for i in 1 2 3; do
+    echo "=== repeat $i" >> $OUT/tpdebug.log
+    TP_WORKER_REPORT_ONLY=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29517 tests/tp_worker.py 2>&1 | grep "TP_CASE\|Error\|error" >> $OUT/tpdebug.log
+  done
+}
+stage_tpdebug() {   # needs gpurun --gpus 2: the tensor-parallel parity worker under the switches that changed this round
+  for e in A=0 CT2B200_GEMM_PREFILL_BN=256 CT2B200_GEMM_PREFILL=0 CT2B200_PDL=0 CT2B200_GEMM_DECODE=0; do
+    echo "=== $e" >> $OUT/tpdebug.log
+    env $e TP_WORKER_REPORT_ONLY=1 timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 \
+      --master-port 29517 tests/tp_worker.py 2>&1 | grep "TP_CASE\|Error\|error" >> $OUT/tpdebug.log
+  done
 }
 stage_tp2() {      # needs gpurun --gpus 2: tensor-parallel parity (tests/tp_worker.py) and the bench line with its `tp` record
   timeout 900 python -m pytest tests/test_gpu_tp.py -q --tb=short > $OUT/pytest_tp.log 2>&1
