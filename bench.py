@@ -357,6 +357,41 @@ def translate_reference(rec, batch=64, beam=4, max_len=256):
     return out
 
 
+class TpWatchdog:
+    """Bounds the tensor-parallel side record of `--gpus N`.  Its collectives are spin waits on peer flags inside kernels
+    (tp_rows.cu), so a rank that raised — or a world size the kernels misbehave at — blocks the other ranks on the device,
+    where no Python exception can reach them.  On expiry (or fire()) rank 0 prints the line it already holds, with the reason
+    under `tp.error`, and the process leaves with os._exit(0) (a blocked CUDA call cannot be unwound)."""
+
+    def __init__(self, seconds, line):
+        self.line, self.seconds = line, seconds
+        self._done = threading.Event()
+        self._lock = threading.Lock()
+        self._t = threading.Thread(target=self._run, daemon=True)
+        self._t.start()
+
+    def _run(self):
+        if not self._done.wait(self.seconds):
+            self.fire("tensor-parallel record timed out after %.0f s (watchdog)" % self.seconds)
+
+    def fire(self, why):
+        with self._lock:
+            if self._done.is_set():
+                return
+            self._done.set()
+            if self.line is not None:
+                self.line["tp"] = {"error": why[-300:]}
+                self.line.setdefault("roofline", {"error": "not measured: the tensor-parallel record before it did not finish"})
+                sys.stdout.write(json.dumps(self.line) + "\n")
+                sys.stdout.flush()
+            sys.stderr.write("bench.py: %s; leaving\n" % why)
+            sys.stderr.flush()
+            os._exit(0)
+
+    def cancel(self):
+        self._done.set()
+
+
 def measure_variant(ct2, torch, name, weights, batch, plen, steps, warmup, device_index, peak, with_ref_cuda):
     """One point of the metric: device-timed decode of `steps` steps after the `plen`-token prompt."""
     awq = weights == "awq"
@@ -399,6 +434,8 @@ def main():
                     help="seconds the variants / translate side records may spend before they stop launching reference CUDA runs")
     ap.add_argument("--weights", default="int8", choices=["int8", "awq"],
                     help="int8 = the headline INT8 configuration; awq = the AWQ-INT4 (group 128, AWQ_GEMM layout) variant")
+    ap.add_argument("--tp-timeout", type=float, default=300.0,
+                    help="N > 1: seconds the tensor-parallel side record may take before the replica line is printed without it")
     ap.add_argument("--tp", action="store_true",
                     help="N > 1: ONE tensor-parallel generator over the N GPUs (strong scaling) as the headline instead of N replicas")
     args = ap.parse_args()
@@ -495,9 +532,33 @@ def main():
     e2e = e2e_run(K)
     e2e_full = e2e if K == 1024 else (e2e_run(1024) if not tp else None)
 
+    # ---- the replica / single-GPU line is complete here; rank 0 keeps it so that a failing side record cannot lose it ----
+    line = None
+    if rank == 0:
+        peak, how = measured_peaks()
+        ctx_mean = P + K / 2.0
+        sb = step_bytes(args.model, B, ctx_mean, args.weights)
+        step_gbs = sb / (dec_ms / K * 1e-3) / 1e9
+        config.update({"step_bytes_algorithmic": int(sb), "step_GBps": round(step_gbs, 1),
+                       "step_roofline_frac": round(step_gbs / peak, 4), "prefill_ms": round(pre_ms, 2),
+                       "prefill_tokens_per_s": round(B * (P - 1) / (pre_ms * 1e-3), 1), "weight_bytes": info["weight_bytes"]})
+        line = {"metric": "generate_batch tokens/sec", "value": round(value, 2), "unit": "tokens/s", "n_gpus": world,
+                "steps": K, "warmup": W, "ms_per_step": round(dec_ms / K, 4), "higher_is_better": True,
+                "scaling": "strong" if tp else "weak", "vs_baseline": None,
+                "dtype": ("s4 weights -> f16 (tcgen05 kind::f16, f32 accumulate)" if awq else
+                          "s8 (int8 x int8 -> s32 on tcgen05; f16 activations, f32 epilogue/softmax)"),
+                "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
+                "gpu_launches": int(launches)}
+        if e2e_full is not None:
+            line["e2e_full"] = e2e_full
+
     # ---- N > 1: ONE tensor-parallel generator over the same GPUs (strong scaling of the same step) ----
+    # The collectives of that generator are spin waits on peer flags inside kernels: a rank that fails (or a world size the
+    # fused kernels were never run at) would leave the others waiting forever and the driver without ANY line.  A watchdog
+    # bounds the section: on expiry rank 0 prints the replica line with the failure recorded and every rank exits.
     tp_rec = None
     if world > 1 and not tp and not args.no_tp:
+        watchdog = TpWatchdog(args.tp_timeout, line)
         gen.close()
         del gen
         torch.cuda.empty_cache()
@@ -520,26 +581,17 @@ def main():
             tgen.close()
         except Exception as ex:
             tp_rec = {"error": str(ex)[-300:]}
+            # the peers of a failed rank wait for it inside a kernel: do not leave them (and the driver) hanging
+            if "timed out" not in tp_rec["error"]:
+                watchdog.fire("rank %d: %s" % (rank, tp_rec["error"]))
+        try:
+            sync_all()                        # every rank has left the section (a stuck peer trips the watchdog instead)
+        finally:
+            watchdog.cancel()
         gen = None
 
     if rank != 0:
         return
-    peak, how = measured_peaks()
-    ctx_mean = P + K / 2.0
-    sb = step_bytes(args.model, B, ctx_mean, args.weights)
-    step_gbs = sb / (dec_ms / K * 1e-3) / 1e9
-    config.update({"step_bytes_algorithmic": int(sb), "step_GBps": round(step_gbs, 1),
-                   "step_roofline_frac": round(step_gbs / peak, 4), "prefill_ms": round(pre_ms, 2),
-                   "prefill_tokens_per_s": round(B * (P - 1) / (pre_ms * 1e-3), 1), "weight_bytes": info["weight_bytes"]})
-    line = {"metric": "generate_batch tokens/sec", "value": round(value, 2), "unit": "tokens/s", "n_gpus": world,
-            "steps": K, "warmup": W, "ms_per_step": round(dec_ms / K, 4), "higher_is_better": True, "scaling": "strong" if tp else "weak",
-            "vs_baseline": None,
-            "dtype": ("s4 weights -> f16 (tcgen05 kind::f16, f32 accumulate)" if awq else
-                      "s8 (int8 x int8 -> s32 on tcgen05; f16 activations, f32 epilogue/softmax)"),
-            "data": "synthetic", "config": config, "clocks": clocks.summary(), "e2e": e2e,
-            "gpu_launches": int(launches)}
-    if e2e_full is not None:
-        line["e2e_full"] = e2e_full
     if tp_rec is not None:
         line["tp"] = tp_rec
     if gen is not None:

@@ -250,8 +250,15 @@ class Generator:
         if rows and rows[0] and isinstance(rows[0][0], str):
             rows = [self._ids(r) for r in rows]
         _validate_ids(rows, self.vocab_size)
-        ids = np.ascontiguousarray(np.array(rows, np.int32))
-        B, T = ids.shape
+        if not rows or min(len(r) for r in rows) == 0:
+            raise ValueError("forward_batch: empty batch or empty sequence")
+        # ragged batches (the reference passes `lengths`, models/language_model.cc:135-160): rows are padded on the right
+        # with id 0; under the causal mask the positions < len(row) never see the padding, positions >= len(row) hold
+        # unspecified values exactly as in the reference's padded output
+        B, T = len(rows), max(len(r) for r in rows)
+        ids = np.zeros((B, T), np.int32)
+        for i, r in enumerate(rows):
+            ids[i, :len(r)] = r
         logits = np.empty((B, T, self.vocab_size), np.float32)
         check(lib().ct2b200_forward_batch(ctypes.c_void_p(self._h), ids.ctypes.data_as(ctypes.c_void_p),
                                           ctypes.c_int64(B), ctypes.c_int64(T), int(return_log_probs),

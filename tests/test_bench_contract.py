@@ -55,3 +55,25 @@ def test_reference_arm_under_torchrun_prints_one_line(tmp_path):
     assert len(lines) == 1, r.stdout
     d = json.loads(lines[0])
     assert d["impl"] == "reference" and d["value"] > 0
+
+
+def test_tp_watchdog_prints_the_replica_line_and_leaves():
+    """`bench.py --gpus N` adds a tensor-parallel side record whose collectives are spin waits inside kernels: a failing rank
+    must not cost the driver its line.  The watchdog prints the line rank 0 already holds (failure under `tp.error`) and
+    exits 0; a cancelled watchdog does nothing."""
+    code = ("import bench, time\n"
+            "w = bench.TpWatchdog(0.3, {'metric': 'generate_batch tokens/sec', 'value': 1.0})\n"
+            "time.sleep(20)\nprint('not reached')\n")
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60)
+    assert r.returncode == 0, r.stderr
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    assert len(lines) == 1 and "not reached" not in r.stdout
+    d = json.loads(lines[0])
+    assert d["value"] == 1.0 and "timed out" in d["tp"]["error"] and "error" in d["roofline"]
+    # ranks other than 0 hold no line: they leave silently
+    code = "import bench, time\nw = bench.TpWatchdog(0.3, None)\ntime.sleep(20)\nprint('not reached')\n"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60)
+    assert r.returncode == 0 and r.stdout == ""
+    code = "import bench, time\nw = bench.TpWatchdog(0.3, {'a': 1})\nw.cancel()\ntime.sleep(1)\nprint('alive')\n"
+    r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60)
+    assert r.stdout.strip() == "alive"
