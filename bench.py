@@ -634,6 +634,15 @@ def main():
                 line["translate"].update(translate_reference(line["translate"]))
             except Exception as ex:
                 line["translate"]["ref_cuda"] = {"error": str(ex)[-300:]}
+        # the reference's best attention (vendored FlashAttention-2 split-KV, flash_attention=True) on the headline
+        # point, last in the side budget (with the cuBLAS GEMMs around it the reference's step is not attention-bound)
+        for key in ("int8_b32", "int8_b1"):
+            if time.time() - t_side > args.side_budget or "error" in variants[key]:
+                continue
+            r = ref_cuda_bench(args.model, "int8_float16", "int8_float16", int(key.split("_b")[1]), P, flash=True)
+            variants[key]["ref_cuda_flash"] = r
+            if "decode_tokens_per_s" in r:
+                variants[key]["vs_ref_cuda_flash"] = round(variants[key]["tokens_per_s"] / r["decode_tokens_per_s"], 2)
     if awq:
         line["cpu_baseline"] = {"value": None, "unit": "tokens/s", "cores": 0, "kind": "reference",
                                 "sample": "none: the reference has no CPU implementation of the AWQ ops "
