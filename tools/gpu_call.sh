@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace probe ncutr tp2
+# stages: final golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace probe ncutr tp2
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -154,6 +154,17 @@ stage_tp2() {      # needs gpurun --gpus 2: tensor-parallel parity (tests/tp_wor
   timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
     bench.py --gpus 2 --steps 256 --warmup 3 > $OUT/bench_gpus2.json 2> $OUT/bench_gpus2.err
   echo "bench --gpus 2 exit $?" >> $OUT/bench_gpus2.err
+}
+
+stage_final() {    # last call of the round (bounded to the GPU minutes left): the whole suite like the driver runs it, smoke(),
+                   # the launch list of the final kernels, then the default bench line with a short side budget
+  ( time timeout 480 python -m pytest tests -m gpu -q --tb=short --durations=8 > $OUT/pytest_gpu.log 2>&1 ) 2> $OUT/pytest_gpu.time
+  echo "gpu suite exit $?" >> $OUT/pytest_gpu.log
+  timeout 120 python __graft_entry__.py --smoke > $OUT/smoke.log 2>&1; echo "smoke exit $?" >> $OUT/smoke.log
+  timeout 150 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_b32_final.csv python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_list.log 2>&1
+  ( time timeout 420 python bench.py --side-budget 100 > $OUT/bench.json 2> $OUT/bench.err ) 2> $OUT/bench.time
+  echo "bench exit $?" >> $OUT/bench.err
 }
 
 for s in "$@"; do
