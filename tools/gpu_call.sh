@@ -2,7 +2,7 @@
 # tools/gpu_call.sh — the command list of ONE gpurun call, as named stages (what each call measured is summarised in
 # profiles/README.md).  Everything it writes goes to gpurun_out/ (merged back by gpurun).
 #   /usr/local/graft/bin/gpurun --timeout 1500 -- 'bash tools/gpu_call.sh tests sweeps ncu'
-# stages: final golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace probe ncutr tp2
+# stages: final ncufinal golden tests shims sweeps awq refbench refstamps ncu ncufull bench translate pdlrace trprofile smemsweep widetiles awqtrace probe ncutr tp2
 set -u
 cd "$(dirname "$0")/.."
 OUT=gpurun_out
@@ -165,6 +165,23 @@ stage_final() {    # last call of the round (bounded to the GPU minutes left): t
     --log-file $OUT/r02_launches_b32_final.csv python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_list.log 2>&1
   ( time timeout 420 python bench.py --side-budget 100 > $OUT/bench.json 2> $OUT/bench.err ) 2> $OUT/bench.time
   echo "bench exit $?" >> $OUT/bench.err
+}
+
+stage_ncufinal() { # full captures of the final kernels (INT8 decode GEMMs of two layers, decode attention, AWQ decode kernel) + launch lists
+  timeout 170 ncu --set full --clock-control none --profile-from-start off -k regex:gemm_decode_kernel -c 8 \
+    -o $OUT/r02_final_gemm_decode python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_gemm.log 2>&1
+  timeout 60 python tools/ncu_extract.py $OUT/r02_final_gemm_decode.ncu-rep > $OUT/r02_ncu_final_gemm_decode.md 2>> $OUT/ncu_gemm.log
+  timeout 120 ncu --set full --clock-control none --profile-from-start off -k regex:attention_decode -c 2 \
+    -o $OUT/r02_final_attention python tools/decode_once.py 32 2 int8_float16 8b int8_float16 > $OUT/ncu_attn.log 2>&1
+  timeout 60 python tools/ncu_extract.py $OUT/r02_final_attention.ncu-rep > $OUT/r02_ncu_final_attention.md 2>> $OUT/ncu_attn.log
+  timeout 170 ncu --set full --clock-control none --profile-from-start off -k regex:awq_decode_kernel -c 6 \
+    -o $OUT/r02_final_awq_decode python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_awq.log 2>&1
+  timeout 60 python tools/ncu_extract.py $OUT/r02_final_awq_decode.ncu-rep > $OUT/r02_ncu_final_awq_decode.md 2>> $OUT/ncu_awq.log
+  timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_awq_b32_final.csv python tools/decode_once.py 32 2 float16 8b awq_gemm > $OUT/ncu_list.log 2>&1
+  timeout 120 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --csv \
+    --log-file $OUT/r02_launches_b1_final.csv python tools/decode_once.py 1 2 int8_float16 8b int8_float16 >> $OUT/ncu_list.log 2>&1
+  ls -la $OUT/*.ncu-rep >> $OUT/ncu_list.log 2>&1
 }
 
 for s in "$@"; do
