@@ -171,8 +171,9 @@ def gemm_roofline(name, batch, device):
     peak, how = measured_peaks()
     ach = alg / (ms * 1e-3) / 1e9
     # dram__bytes_read.sum + dram__bytes_write.sum of this kernel in the committed ncu --set full capture
-    # (profiles/r01_ncu_full_b32_v4.md: 117.73 MB + 3.95 MB at m = 32); null for shapes that were not captured
-    traffic = 121676544 if (name == "8b" and batch == 32) else None
+    # (profiles/r02_ncu_final_gemm_decode.md, the final kernel: 117,725,952 B read + 4,043,008 B written at m = 32; round 1's
+    # capture of the first lean kernel read 121,676,544 B in total); null for shapes that were not captured
+    traffic = 121768960 if (name == "8b" and batch == 32) else None
     return {"bound": "hbm", "kernel": "gemm_decode_kernel<s8, NB=2 gate/up + SwiGLU> (ffn gate/up %dx%d, m=%d)" % (2 * f, d, batch),
             "achieved": round(ach, 1), "peak": peak, "unit": "GB/s", "frac": round(ach / peak, 4),
             "traffic": traffic, "bytes_per_launch": alg, "us_per_launch": round(ms * 1e3, 2), "peak_source": how}
