@@ -77,3 +77,63 @@ def test_tp_watchdog_prints_the_replica_line_and_leaves():
     code = "import bench, time\nw = bench.TpWatchdog(0.3, {'a': 1})\nw.cancel()\ntime.sleep(1)\nprint('alive')\n"
     r = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, cwd=ROOT, timeout=60)
     assert r.stdout.strip() == "alive"
+
+
+_KEYS = ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline",
+         "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline")
+
+
+def _run_stub(world, mode="ok", extra=(), port=29941):
+    env = dict(os.environ, STUB_TP_MODE=mode)
+    worker = os.path.join(ROOT, "tests", "bench_stub_worker.py")
+    if world == 1:
+        cmd = [sys.executable, worker, "--steps", "8", "--warmup", "3"] + list(extra)
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world), "--master-addr",
+               "127.0.0.1", "--master-port", str(port), worker, "--gpus", str(world), "--steps", "8", "--warmup", "3"] + list(extra)
+    r = subprocess.run(cmd, capture_output=True, text=True, env=env, timeout=280)
+    lines = [l for l in r.stdout.splitlines() if l.startswith("{")]
+    return r, lines
+
+
+@pytest.mark.timeout(300)
+def test_own_arm_control_flow_one_gpu_stubbed_device():
+    """bench.py's own arm with the device layer stubbed (tests/bench_stub_worker.py): ONE line with every key of the contract,
+    the four variants, translate and cpu_baseline records."""
+    r, lines = _run_stub(1)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in _KEYS + ("e2e_full", "variants", "translate", "cpu_baseline"):
+        assert k in d, k
+    assert d["n_gpus"] == 1 and d["scaling"] == "weak" and d["value"] == pytest.approx(32 * 8 / (3.0 * 8 * 1e-3), rel=1e-6)
+    assert set(d["variants"]) == {"int8_b1", "int8_b32", "awq_b1", "awq_b32"} and "ref_cuda_flash" in d["variants"]["int8_b32"]
+    assert "tp" not in d
+
+
+@pytest.mark.timeout(300)
+def test_own_arm_under_torchrun_world2_gloo_replicas_and_tp_record():
+    """`--gpus 2` as the driver launches it (gloo stands in for nccl): rank 0 prints ONE line, value aggregates both replicas
+    (weak scaling), and the `tp` record carries the strong-scaling step of one tensor-parallel generator."""
+    r, lines = _run_stub(2, port=29942)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1, r.stdout
+    d = json.loads(lines[0])
+    for k in _KEYS:
+        assert k in d, k
+    assert d["n_gpus"] == 2 and d["scaling"] == "weak" and d["value"] == pytest.approx(2 * 32 * 8 / (3.0 * 8 * 1e-3), rel=1e-6)
+    assert d["config"]["global_batch"] == 64
+    assert d["tp"]["parallelism"] == "tp2" and d["tp"]["scaling"] == "strong" and d["tp"]["ms_per_step"] == pytest.approx(2.7)
+    assert d["tp"]["speedup_vs_one_gpu_step"] == pytest.approx(3.0 / 2.7, abs=1e-3)
+
+
+@pytest.mark.timeout(300)
+@pytest.mark.parametrize("mode", ["raise_rank1", "hang_rank1"])
+def test_tp_record_failure_keeps_the_replica_line(mode):
+    """A rank that cannot build its tensor-parallel shard, or one that never leaves a peer-flag wait: the driver still gets the
+    replica line (exit 0, ONE line) with the failure under `tp.error`."""
+    r, lines = _run_stub(2, mode=mode, extra=("--tp-timeout", "6"), port=29943 if mode == "raise_rank1" else 29944)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert len(lines) == 1, r.stdout + r.stderr[-1500:]
+    d = json.loads(lines[0])
+    assert d["n_gpus"] == 2 and d["value"] > 0 and "error" in d["tp"], d.get("tp")
