@@ -193,6 +193,24 @@ class Generator:
             rows = [self._ids(r) for r in rows]
         _validate_ids(rows, self.vocab_size)
         B = len(rows)
+        cap = self.max_batch_size // beam_size
+        if B > cap >= 1:
+            # A request larger than the arena: the reference's replica pool re-batches it by max_batch_size, longest examples
+            # first, and returns the results in request order (src/batch_reader.cc rebatch_input / load_examples).  Every row
+            # equals the row decoded alone, so the split does not change any result.
+            if beam_size > 1 and len({len(r) for r in rows}) > 1:
+                raise ValueError("beam search needs prompts of equal length")
+            order = sorted(range(B), key=lambda i: -len(rows[i]))
+            results: List[Optional[GenerationResult]] = [None] * B
+            for c in range(0, B, cap):
+                idx = order[c:c + cap]
+                sub = self.generate_batch([rows[i] for i in idx], max_length=max_length, min_length=min_length,
+                                          beam_size=beam_size, end_token=end_token, return_end_token=return_end_token,
+                                          return_scores=return_scores, length_penalty=length_penalty,
+                                          **({"patience": patience, "num_hypotheses": num_hypotheses} if beam_size > 1 else {}))
+                for i, r in zip(idx, sub):
+                    results[i] = r
+            return results
         lens = np.array([len(r) for r in rows], np.int32)
         P = int(lens.max())
         ids = np.zeros((B, P), np.int32)
