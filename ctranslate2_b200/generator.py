@@ -185,6 +185,11 @@ class Generator:
                              "token (decoding.cc:21-67); pass False (docs/performance.md)")
         patience = unsupported.pop("patience", 1) if beam_size > 1 else 1
         num_hypotheses = unsupported.pop("num_hypotheses", 1) if beam_size > 1 else 1
+        # max_batch_size of the call (python/cpp/generator.cc: inputs beyond it are sorted by length and split into chunks of
+        # that many examples); batch_type "tokens" is not implemented
+        request_cap = unsupported.pop("max_batch_size", 0)
+        if isinstance(request_cap, bool) or not isinstance(request_cap, (int, np.integer)) or request_cap < 0:
+            raise ValueError("max_batch_size must be a non-negative integer")
         _check_options(unsupported, max_length, min_length)
         rows = [list(r) for r in start_tokens]
         if not rows:
@@ -194,6 +199,8 @@ class Generator:
         _validate_ids(rows, self.vocab_size)
         B = len(rows)
         cap = self.max_batch_size // beam_size
+        if request_cap > 0:
+            cap = min(cap, int(request_cap))
         if B > cap >= 1:
             # A request larger than the arena: the reference's replica pool re-batches it by max_batch_size, longest examples
             # first, and returns the results in request order (src/batch_reader.cc rebatch_input / load_examples).  Every row

@@ -85,3 +85,16 @@ def test_beam_requests_keep_their_argument_errors_when_rebatched(gen):
     with pytest.raises(ValueError):
         g.generate_batch([[1, 2, 3], [1, 2], [4, 5, 6]], max_length=4, beam_size=2)      # cap = 2 rows per call; ragged prompts
     assert fake.calls == []
+
+
+def test_max_batch_size_of_the_call_splits_below_the_arena(gen):
+    g, fake = gen
+    prompts = [[10 * (i + 1)] * (1 + i % 3) for i in range(5)]
+    res = g.generate_batch(prompts, max_length=2, min_length=2, end_token=[2], max_batch_size=2)
+    assert [x.sequences_ids[0][0] for x in res] == [p[0] + 1 for p in prompts]
+    assert [len(c[1]) for c in fake.calls] == [2, 2, 1]
+    for bad in (-1, 1.5, True):
+        with pytest.raises(ValueError):
+            g.generate_batch(prompts, max_length=2, max_batch_size=bad)
+    with pytest.raises(ValueError):
+        g.generate_batch(prompts, max_length=2, batch_type="tokens")
